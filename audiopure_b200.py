@@ -1,0 +1,24 @@
+"""Import alias: ``import audiopure_b200`` loads the package directory
+``diffusion-model-for-audio-defense_b200/`` (whose name is not a valid Python
+identifier) under the importable name ``audiopure_b200``.
+"""
+import importlib.util
+import os
+import sys
+
+_PKG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                        "diffusion-model-for-audio-defense_b200")
+
+
+def _load():
+    name = "audiopure_b200"
+    spec = importlib.util.spec_from_file_location(
+        name, os.path.join(_PKG_DIR, "__init__.py"),
+        submodule_search_locations=[_PKG_DIR])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_load()

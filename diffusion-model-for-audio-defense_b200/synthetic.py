@@ -1,0 +1,185 @@
+"""Deterministic synthetic weights and waveforms (SURVEY.md §8c "Weights", §8d "Synthetic inputs").
+
+The DiffWave and ResNeXt checkpoints of the reference are not in its tree
+(README.md:3 points at Google Drive), so throughput and parity are measured
+on seeded random-init weights of the named architectures.  Every tensor is
+drawn from its own PCG64 stream keyed by (seed, crc32(name)), so the result
+does not depend on creation order, torch's RNG, or the torch version.
+
+State-dict names and shapes are exactly the reference's:
+  * WaveNet_Speech_Commands  -- diffusion_models/DiffWave_Unconditional/WaveNet.py:138-172
+    (legacy weight-norm keys ``conv.weight_g`` / ``conv.weight_v``)
+  * CifarResNeXt             -- audio_models/ConvNets_SpeechCommands/models/resnext.py:67-142
+  * M5                       -- audio_models/M5/M5Net.py:4-38
+  * KWSModel                 -- audio_models/RCNN_KWS/model.py:66-113
+
+``final_conv.2`` is zero-initialised in the reference (WaveNet.py:43-44), which
+makes eps == 0 and every parity check vacuous; it is re-randomised here.
+"""
+from __future__ import annotations
+
+import zlib
+from collections import OrderedDict
+
+import numpy as np
+
+DEFAULT_WAVENET_CONFIG = dict(  # configs/config.json:7-17
+    in_channels=1, res_channels=256, skip_channels=256, out_channels=1,
+    num_res_layers=36, dilation_cycle=12,
+    diffusion_step_embed_dim_in=128, diffusion_step_embed_dim_mid=512,
+    diffusion_step_embed_dim_out=512)
+DEFAULT_DIFFUSION_CONFIG = dict(T=200, beta_0=0.0001, beta_T=0.02)  # configs/config.json:2-6
+
+
+def _rng(seed: int, name: str) -> np.random.Generator:
+    return np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
+
+
+def _normal(seed, name, shape, std):
+    return (_rng(seed, name).standard_normal(shape) * std).astype(np.float32)
+
+
+def _uniform(seed, name, shape, lo, hi):
+    return _rng(seed, name).uniform(lo, hi, shape).astype(np.float32)
+
+
+def _wn_conv(sd, seed, prefix, cout, cin, k):
+    """Weight-normed Conv1d: v ~ kaiming normal, g = ||v|| * U(0.8, 1.2), bias ~ U(+-1/sqrt(fan_in))."""
+    fan_in = cin * k
+    v = _normal(seed, prefix + ".weight_v", (cout, cin, k), np.sqrt(2.0 / fan_in))
+    norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2))).astype(np.float32)
+    g = norm * _uniform(seed, prefix + ".weight_g", (cout,), 0.8, 1.2)
+    b = _uniform(seed, prefix + ".bias", (cout,), -1, 1) / np.float32(np.sqrt(fan_in))
+    sd[prefix + ".bias"] = b.astype(np.float32)
+    sd[prefix + ".weight_g"] = g.reshape(cout, 1, 1).astype(np.float32)
+    sd[prefix + ".weight_v"] = v
+
+
+def _linear(sd, seed, prefix, cout, cin, bias=True, gain=1.0):
+    bound = gain / np.sqrt(cin)
+    sd[prefix + ".weight"] = _uniform(seed, prefix + ".weight", (cout, cin), -bound, bound)
+    if bias:
+        sd[prefix + ".bias"] = _uniform(seed, prefix + ".bias", (cout,), -bound, bound)
+
+
+def wavenet_state_dict(seed: int = 0, config: dict | None = None) -> "OrderedDict[str, np.ndarray]":
+    """Seeded state dict with the reference's 408 keys (for the default config)."""
+    c = dict(DEFAULT_WAVENET_CONFIG)
+    if config:
+        c.update(config)
+    C, S = c["res_channels"], c["skip_channels"]
+    e_in, e_mid, e_out = (c["diffusion_step_embed_dim_in"], c["diffusion_step_embed_dim_mid"],
+                          c["diffusion_step_embed_dim_out"])
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    _wn_conv(sd, seed, "init_conv.0.conv", C, c["in_channels"], 1)
+    _linear(sd, seed, "residual_layer.fc_t1", e_mid, e_in)
+    _linear(sd, seed, "residual_layer.fc_t2", e_out, e_mid)
+    for n in range(c["num_res_layers"]):
+        p = f"residual_layer.residual_blocks.{n}"
+        _linear(sd, seed, p + ".fc_t", C, e_out)
+        _wn_conv(sd, seed, p + ".dilated_conv_layer.conv", 2 * C, C, 3)
+        _wn_conv(sd, seed, p + ".res_conv", C, C, 1)
+        _wn_conv(sd, seed, p + ".skip_conv", S, C, 1)
+    _wn_conv(sd, seed, "final_conv.0.conv", S, S, 1)
+    sd["final_conv.2.conv.weight"] = _normal(seed, "final_conv.2.conv.weight",
+                                             (c["out_channels"], S, 1), np.sqrt(2.0 / S))
+    sd["final_conv.2.conv.bias"] = _uniform(seed, "final_conv.2.conv.bias", (c["out_channels"],), -0.05, 0.05)
+    return sd
+
+
+def _bn(sd, seed, prefix, ch):
+    sd[prefix + ".weight"] = _uniform(seed, prefix + ".weight", (ch,), 0.5, 1.5)
+    sd[prefix + ".bias"] = _normal(seed, prefix + ".bias", (ch,), 0.1)
+    sd[prefix + ".running_mean"] = _normal(seed, prefix + ".running_mean", (ch,), 0.1)
+    sd[prefix + ".running_var"] = _uniform(seed, prefix + ".running_var", (ch,), 0.5, 1.5)
+    sd[prefix + ".num_batches_tracked"] = np.array(1, dtype=np.int64)
+
+
+def _conv2d(sd, seed, name, cout, cin_per_group, kh, kw):
+    fan_out = cout * kh * kw
+    sd[name + ".weight"] = _normal(seed, name + ".weight", (cout, cin_per_group, kh, kw), np.sqrt(2.0 / fan_out))
+
+
+def resnext_state_dict(seed: int = 0, nlabels: int = 10, cardinality: int = 8, depth: int = 29,
+                       base_width: int = 64, widen_factor: int = 4, in_channels: int = 1):
+    """CifarResNeXt state dict (resnext.py:67-142); BN gets non-trivial running stats."""
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    block_depth = (depth - 2) // 9
+    stages = [64, 64 * widen_factor, 128 * widen_factor, 256 * widen_factor]
+    _conv2d(sd, seed, "conv_1_3x3", 64, in_channels, 3, 3)
+    _bn(sd, seed, "bn_1", 64)
+    for s in range(3):
+        cin, cout = stages[s], stages[s + 1]
+        for b in range(block_depth):
+            p = f"stage_{s + 1}.stage_{s + 1}_bottleneck_{b}"
+            bin_ = cin if b == 0 else cout
+            width_ratio = cout / (widen_factor * 64.0)
+            D = cardinality * int(base_width * width_ratio)
+            _conv2d(sd, seed, p + ".conv_reduce", D, bin_, 1, 1)
+            _bn(sd, seed, p + ".bn_reduce", D)
+            _conv2d(sd, seed, p + ".conv_conv", D, D // cardinality, 3, 3)
+            _bn(sd, seed, p + ".bn", D)
+            _conv2d(sd, seed, p + ".conv_expand", cout, D, 1, 1)
+            _bn(sd, seed, p + ".bn_expand", cout)
+            if bin_ != cout:
+                _conv2d(sd, seed, p + ".shortcut.shortcut_conv", cout, bin_, 1, 1)
+                _bn(sd, seed, p + ".shortcut.shortcut_bn", cout)
+    _linear(sd, seed, "classifier", nlabels, stages[3], gain=4.0)
+    return sd
+
+
+def m5_state_dict(seed: int = 0, n_input=1, first_kernel_size=160, n_output=10, n_channel=32):
+    """M5 state dict (M5Net.py:4-20)."""
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    shapes = [("conv1", n_channel, n_input, first_kernel_size), ("conv2", n_channel, n_channel, 3),
+              ("conv3", 2 * n_channel, n_channel, 3), ("conv4", 2 * n_channel, 2 * n_channel, 3)]
+    for i, (name, co, ci, k) in enumerate(shapes):
+        bound = 1.0 / np.sqrt(ci * k)
+        sd[name + ".weight"] = _uniform(seed, name + ".weight", (co, ci, k), -bound, bound) * np.float32(2.0)
+        sd[name + ".bias"] = _uniform(seed, name + ".bias", (co,), -bound, bound)
+        _bn(sd, seed, f"bn{i + 1}", co)
+    _linear(sd, seed, "fc1", n_output, 2 * n_channel, gain=4.0)
+    return sd
+
+
+def kws_state_dict(seed: int = 0, in_size=32, hidden_size=64, kernel_size=(20, 5), gru_num_layers=2, num_classes=4):
+    """KWSModel state dict (RCNN_KWS/model.py:5-113): 24 tensors."""
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    p = "CRNN_model.sepconv"
+    b0 = 1.0 / np.sqrt(kernel_size[1])
+    sd[p + ".0.weight"] = _uniform(seed, p + ".0.weight", (in_size, 1, kernel_size[1]), -b0, b0)
+    sd[p + ".0.bias"] = _uniform(seed, p + ".0.bias", (in_size,), -b0, b0)
+    groups = int(in_size / kernel_size[0])
+    cin_g = in_size // groups
+    b1 = 1.0 / np.sqrt(cin_g)
+    sd[p + ".1.weight"] = _uniform(seed, p + ".1.weight", (hidden_size, cin_g, 1), -b1, b1)
+    sd[p + ".1.bias"] = _uniform(seed, p + ".1.bias", (hidden_size,), -b1, b1)
+    H = hidden_size
+    bg = 1.0 / np.sqrt(H)
+    for layer in range(gru_num_layers):
+        in_l = H if layer == 0 else 2 * H
+        for suffix in ("", "_reverse"):
+            g = "CRNN_model.gru."
+            sd[f"{g}weight_ih_l{layer}{suffix}"] = _uniform(seed, f"{g}weight_ih_l{layer}{suffix}", (3 * H, in_l), -bg, bg)
+            sd[f"{g}weight_hh_l{layer}{suffix}"] = _uniform(seed, f"{g}weight_hh_l{layer}{suffix}", (3 * H, H), -bg, bg)
+            sd[f"{g}bias_ih_l{layer}{suffix}"] = _uniform(seed, f"{g}bias_ih_l{layer}{suffix}", (3 * H,), -bg, bg)
+            sd[f"{g}bias_hh_l{layer}{suffix}"] = _uniform(seed, f"{g}bias_hh_l{layer}{suffix}", (3 * H,), -bg, bg)
+    _linear(sd, seed, "attn_layer.Wx_b", 2 * H, 2 * H)
+    _linear(sd, seed, "attn_layer.Vt", 1, 2 * H, bias=False)
+    _linear(sd, seed, "apply_attn.U", num_classes, 2 * H, bias=False, gain=4.0)
+    return sd
+
+
+def synthetic_waveforms(batch: int, length: int = 16000, seed: int = 1234, sample_rate: int = 16000) -> np.ndarray:
+    """x = clamp(0.1*randn + 0.3*sin(2*pi*f*n/sr), -1, 1), f ~ U(100, 4000) per sample."""
+    rng = np.random.Generator(np.random.PCG64([seed, 0x5C09]))
+    f = rng.uniform(100.0, 4000.0, size=(batch, 1, 1))
+    n = np.arange(length, dtype=np.float64).reshape(1, 1, length)
+    x = 0.1 * rng.standard_normal((batch, 1, length)) + 0.3 * np.sin(2 * np.pi * f * n / sample_rate)
+    return np.clip(x, -1.0, 1.0).astype(np.float32)
+
+
+def host_noise(shape, seed: int = 2024, index: int = 0) -> np.ndarray:
+    """Host-generated standard-normal tensors handed identically to the oracle and the CUDA path."""
+    rng = np.random.Generator(np.random.PCG64([seed, index]))
+    return rng.standard_normal(shape).astype(np.float32)

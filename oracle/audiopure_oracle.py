@@ -1,0 +1,516 @@
+"""CPU ORACLE for the AudioPure purification-and-classify hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is imported, linked or
+executed by the product (``diffusion-model-for-audio-defense_b200/``); only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may use it, and only as the checker / reported baseline.
+
+It is an independent functional restatement (plain torch CPU tensor ops on
+explicit weight dicts -- no nn.Module, no code copied) of the reference
+algorithm; every function cites the reference file:line it follows (paths are
+relative to the reference repo root).
+
+PARITY PIN: the reference ships no tests, golden vectors or fixtures for this
+path, so the oracle is pinned against *outputs of the
+reference itself*, produced in the build container by
+``tests/golden/make_golden.py`` (imports the unmodified reference through a
+4-line shim) and committed under ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` checks the oracle against them.  The one piece
+that cannot be pinned that way is the third-party Euler-Maruyama stepping of
+``torchsde==0.2.5`` (requirements.txt:15; not installed, no network): it is
+restated from its published algorithm in ``sde_euler_schedule`` and marked
+"parity unpinned (torchsde stepping)".
+
+Weights are dicts name -> array with the reference's state-dict keys.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def _t(a, dtype):
+    if isinstance(a, torch.Tensor):
+        return a.to(dtype)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+
+
+# --------------------------------------------------------------------------------------
+# a1  calc_diffusion_hyperparams                     DiffWave_Unconditional/util.py:96-123
+# --------------------------------------------------------------------------------------
+def diffusion_hyperparams(T: int = 200, beta_0: float = 1e-4, beta_T: float = 0.02):
+    """float32, sequential in-place cumprod exactly as util.py:111-117 does it."""
+    beta = torch.linspace(beta_0, beta_T, T, dtype=torch.float32)
+    alpha = 1 - beta
+    alpha_bar = alpha.clone()
+    beta_tilde = beta.clone()
+    for t in range(1, T):
+        alpha_bar[t] = alpha_bar[t] * alpha_bar[t - 1]
+        beta_tilde[t] = beta_tilde[t] * ((1 - alpha_bar[t - 1]) / (1 - alpha_bar[t]))
+    sigma = torch.sqrt(beta_tilde)
+    return {"T": T, "Beta": beta, "Alpha": alpha, "Alpha_bar": alpha_bar, "Sigma": sigma}
+
+
+# --------------------------------------------------------------------------------------
+# a2  calc_diffusion_step_embedding                  DiffWave_Unconditional/util.py:68-93
+# --------------------------------------------------------------------------------------
+def step_embedding(steps: torch.Tensor, dim_in: int = 128) -> torch.Tensor:
+    """steps (B,1) -> (B, dim_in) = [sin(t*w_j), cos(t*w_j)], w_j = exp(-j ln(1e4)/(half-1))."""
+    half = dim_in // 2
+    scale = np.log(10000) / (half - 1)                       # util.py:86 (python float64)
+    w = torch.exp(torch.arange(half) * -scale)               # util.py:87 (float32 result)
+    arg = steps.to(torch.float32) * w                        # util.py:88
+    return torch.cat((torch.sin(arg), torch.cos(arg)), 1)    # util.py:89-90
+
+
+# --------------------------------------------------------------------------------------
+# a5  weight-norm fold                               WaveNet.py:27-28,66-73 (nn.utils.weight_norm, dim=0)
+# --------------------------------------------------------------------------------------
+def fold_weight_norm(g, v, dtype=torch.float32) -> torch.Tensor:
+    """w = g * v / ||v||_2, norm over all dims but 0."""
+    g = _t(g, dtype)
+    v = _t(v, dtype)
+    norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1)))
+    return v * (g.reshape(norm.shape) / norm)
+
+
+def _swish(x):
+    return x * torch.sigmoid(x)                              # WaveNet.py:10-11
+
+
+# --------------------------------------------------------------------------------------
+# a3,a4,a6  WaveNet_Speech_Commands.forward          WaveNet.py:75-97,120-135,164-172
+# --------------------------------------------------------------------------------------
+def wavenet_forward(sd: dict, audio, steps, num_res_layers: int = 36, dilation_cycle: int = 12,
+                    embed_dim_in: int = 128, dtype=torch.float32, return_internals: bool = False):
+    """audio (B,1,L), steps (B,1) -> eps (B,1,L).
+
+    Reproduces the in-place alias at WaveNet.py:77,84: ``h = x; h += part_t`` mutates x, so the residual
+    output is ((x + part_t) + res) * sqrt(.5).
+    """
+    w = lambda k: _t(sd[k], dtype)
+    wn = lambda p: fold_weight_norm(sd[p + ".weight_g"], sd[p + ".weight_v"], dtype)
+    x = _t(audio, dtype)
+    steps = _t(steps, dtype)
+    # init conv 1x1 + custom ReLU                            WaveNet.py:147,13-19
+    h = F.conv1d(x, wn("init_conv.0.conv"), w("init_conv.0.conv.bias"))
+    h = torch.maximum(h, torch.zeros_like(h))
+    # step embedding                                          WaveNet.py:124-126
+    emb = step_embedding(steps, embed_dim_in).to(dtype)
+    emb = _swish(F.linear(emb, w("residual_layer.fc_t1.weight"), w("residual_layer.fc_t1.bias")))
+    emb = _swish(F.linear(emb, w("residual_layer.fc_t2.weight"), w("residual_layer.fc_t2.bias")))
+    skip_total = torch.zeros_like(h)
+    internals = {}
+    for n in range(num_res_layers):                          # WaveNet.py:131-133
+        p = f"residual_layer.residual_blocks.{n}"
+        d = 2 ** (n % dilation_cycle)                        # WaveNet.py:117
+        C = h.shape[1]
+        part_t = F.linear(emb, w(p + ".fc_t.weight"), w(p + ".fc_t.bias")).reshape(-1, C, 1)
+        u = h + part_t                                       # WaveNet.py:82-84 (aliasing: x becomes u too)
+        a = F.conv1d(u, wn(p + ".dilated_conv_layer.conv"), w(p + ".dilated_conv_layer.conv.bias"),
+                     dilation=d, padding=d)                  # WaveNet.py:26,87
+        o = torch.tanh(a[:, :C]) * torch.sigmoid(a[:, C:])   # WaveNet.py:90
+        res = F.conv1d(o, wn(p + ".res_conv"), w(p + ".res_conv.bias"))
+        skip = F.conv1d(o, wn(p + ".skip_conv"), w(p + ".skip_conv.bias"))
+        if return_internals and n in (0, 1, num_res_layers - 1):
+            internals[f"u{n}"] = u
+            internals[f"o{n}"] = o
+        h = (u + res) * math.sqrt(0.5)                       # WaveNet.py:97 with x == u
+        skip_total = skip_total + skip                       # WaveNet.py:133
+    s = skip_total * math.sqrt(1.0 / num_res_layers)         # WaveNet.py:135
+    y = F.relu(F.conv1d(s, wn("final_conv.0.conv"), w("final_conv.0.conv.bias")))   # WaveNet.py:160-161
+    eps = F.conv1d(y, w("final_conv.2.conv.weight"), w("final_conv.2.conv.bias"))   # WaveNet.py:162
+    if return_internals:
+        internals["skip_scaled"] = s
+        return eps, internals
+    return eps
+
+
+# --------------------------------------------------------------------------------------
+# a7-a10  DiffWave DDPM purifier                     diffusion_models/diffwave_ddpm.py
+# --------------------------------------------------------------------------------------
+class NoiseSource:
+    """Pops pre-generated host noise tensors in call order: z_diffuse, z_{t*-1}, ..., z_1."""
+
+    def __init__(self, tensors):
+        self.tensors = [_t(z, torch.float32) for z in tensors]
+        self.i = 0
+
+    def __call__(self, shape):
+        z = self.tensors[self.i]
+        self.i += 1
+        assert tuple(z.shape) == tuple(shape), (z.shape, shape)
+        return z
+
+
+def ddpm_diffuse(x0, hp, reverse_timestep: int, noise):
+    """diffwave_ddpm.py:49-73: x_t = sqrt(ab[t*-1]) x0 + sqrt(1-ab[t*-1]) z."""
+    x0 = _t(x0, torch.float32)
+    ab = hp["Alpha_bar"][reverse_timestep - 1]
+    z = noise(x0.shape)
+    return torch.sqrt(ab) * x0 + torch.sqrt(1 - ab) * z
+
+
+def ddpm_coefficients(hp, t: int):
+    """diffwave_ddpm.py:159-160: (c_eps, 1/sqrt(alpha) as applied, sigma) in float32."""
+    alpha, ab, sigma = hp["Alpha"], hp["Alpha_bar"], hp["Sigma"]
+    return (1 - alpha[t]) / torch.sqrt(1 - ab[t]), torch.sqrt(alpha[t]), sigma[t]
+
+
+def ddpm_reverse(sd, x_t, hp, reverse_timestep: int, noise, eps_fn=None, **wn_kw):
+    """diffwave_ddpm.py:75-104,143-164: ancestral sampling t = t*-1 .. 0."""
+    x = _t(x_t, torch.float32).clone()
+    eps_fn = eps_fn or (lambda xx, tt: wavenet_forward(sd, xx, tt * torch.ones(xx.shape[0], 1), **wn_kw))
+    for t in range(reverse_timestep - 1, -1, -1):
+        eps = eps_fn(x, t).to(torch.float32)
+        c_eps, sqrt_alpha, sigma = ddpm_coefficients(hp, t)
+        mu = (x - c_eps * eps) / sqrt_alpha
+        x = mu + sigma * noise(x.shape) if t > 0 else mu
+    return x
+
+
+def ddpm_forward(sd, x0, hp, reverse_timestep: int, noise, **kw):
+    """DiffWave.forward, diffwave_ddpm.py:36-47."""
+    return ddpm_reverse(sd, ddpm_diffuse(x0, hp, reverse_timestep, noise), hp, reverse_timestep, noise, **kw)
+
+
+def predict_x0_from_eps(hp, x_t, t: int, eps):
+    """diffwave_ddpm.py:195-205."""
+    ab = hp["Alpha_bar"]
+    return (1 / ab).sqrt()[t] * _t(x_t, torch.float32) - (1 / ab - 1).sqrt()[t] * _t(eps, torch.float32)
+
+
+def one_shot_denoise(sd, x_t, hp, reverse_timestep: int, eps_fn=None, **wn_kw):
+    """diffwave_ddpm.py:174-182."""
+    x_t = _t(x_t, torch.float32)
+    t = reverse_timestep - 1
+    eps_fn = eps_fn or (lambda xx, tt: wavenet_forward(sd, xx, tt * torch.ones(xx.shape[0], 1), **wn_kw))
+    return predict_x0_from_eps(hp, x_t, t, eps_fn(x_t, t))
+
+
+def two_shot_denoise(sd, x_t, hp, reverse_timestep: int, eps_fn=None, **wn_kw):
+    """diffwave_ddpm.py:184-193,207-226."""
+    x_t = _t(x_t, torch.float32)
+    t = reverse_timestep - 1
+    eps_fn = eps_fn or (lambda xx, tt: wavenet_forward(sd, xx, tt * torch.ones(xx.shape[0], 1), **wn_kw))
+    alpha, ab, beta = hp["Alpha"], hp["Alpha_bar"], hp["Beta"]
+    eps = eps_fn(x_t, t)
+    mu = (ab[t] / alpha[0]).sqrt()
+    sig = (1 - ab[t] - (ab[t] / alpha[0]) * beta[0] ** 2).sqrt()
+    x1 = (x_t - sig * eps) / mu
+    c_eps, sqrt_alpha, _ = ddpm_coefficients(hp, 0)
+    return (x1 - c_eps * eps_fn(x1, 0)) / sqrt_alpha
+
+
+def fast_reverse_tables(hp, reverse_timestep: int, K: int = 3):
+    """diffwave_ddpm.py:118-131: respaced K-step schedule (S, Alpha_new, Alpha_bar_new, Beta_tilde_new)."""
+    ab = hp["Alpha_bar"]
+    S = torch.round(torch.linspace(1, reverse_timestep, K)).int() - 1
+    beta_new, beta_tilde_new = torch.zeros(K), torch.zeros(K)
+    for i in range(K):
+        if i > 0:
+            beta_new[i] = 1 - ab[S[i]] / ab[S[i - 1]]
+            beta_tilde_new[i] = (1 - ab[S[i - 1]]) / (1 - ab[S[i]]) * beta_new[i]
+        else:
+            beta_new[i] = 1 - ab[S[i]]
+            beta_tilde_new[i] = 0
+    alpha_new = 1 - beta_new
+    return S, alpha_new, torch.cumprod(alpha_new, dim=0), beta_tilde_new
+
+
+def fast_reverse(sd, x_t, hp, reverse_timestep: int, noise, eps_fn=None, K: int = 3, **wn_kw):
+    """diffwave_ddpm.py:106-141 (note: sigma = Beta_tilde_new[t], not its sqrt, and noise is added at t=0 too)."""
+    x = _t(x_t, torch.float32)
+    eps_fn = eps_fn or (lambda xx, tt: wavenet_forward(sd, xx, tt * torch.ones(xx.shape[0], 1), **wn_kw))
+    S, alpha_new, ab_new, bt_new = fast_reverse_tables(hp, reverse_timestep, K)
+    for t in range(K - 1, -1, -1):
+        eps = eps_fn(x, int(S[t]))
+        mu = (x - (1 - alpha_new[t]) / torch.sqrt(1 - ab_new[t]) * eps) / torch.sqrt(alpha_new[t])
+        x = mu + bt_new[t] * noise(x.shape)
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# a12-a13  reverse VP-SDE purifier                   diffusion_models/diffwave_sde.py
+# --------------------------------------------------------------------------------------
+def sde_tables(N: int = 200, beta_min: float = 0.02, beta_max: float = 4.0):
+    """RevVPSDE.__init__, diffwave_sde.py:53-60 (RevDiffWave passes beta_min=1e-4*T, beta_max=0.02*T, :155-158)."""
+    betas = torch.linspace(beta_min / N, beta_max / N, N)
+    alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+    return {"N": N, "beta_0": beta_min, "beta_1": beta_max, "discrete_betas": betas,
+            "alphas_cumprod": alphas_cumprod, "sqrt_1m_alphas_cumprod": torch.sqrt(1.0 - alphas_cumprod)}
+
+
+def sde_euler_schedule(t_star: int, T: int = 200):
+    """Solver-time grid of torchsde's fixed-step Euler for ts = linspace(1 - t*/T, 1 - 1e-5, 2), dt = 1/T.
+
+    PARITY UNPINNED (torchsde==0.2.5 is absent): restated from its published fixed-step loop
+    ``while curr_t < t1: next_t = min(curr_t + dt, t1); step(curr_t, next_t)`` with float32 tensor time
+    (ts is a float32 tensor, diffwave_sde.py:196; dt is a python float).
+    Returns a list of (s, ds) float32 pairs: f and g are evaluated at solver time s, step length ds.
+    """
+    ts = torch.linspace(1 - t_star / T, 1 - 1e-5, 2)          # diffwave_sde.py:194-196 (float32)
+    curr, t1 = ts[0], ts[1]
+    dt = 1.0 / T
+    out = []
+    while bool(curr < t1):
+        nxt = torch.minimum(curr + dt, t1)
+        out.append((curr.clone(), (nxt - curr).clone()))
+        curr = nxt
+    return out
+
+
+def sde_step_coefficients(tab, s: torch.Tensor):
+    """RevVPSDE.f / .g at solver time s (diffwave_sde.py:69-133).  Returns dict with the discrete index d,
+    beta(tau), 1/sqrt(1-ab[d]) and the diffusion coefficient g."""
+    N = tab["N"]
+    tau = 1 - s                                                # f(), g(): t' = 1 - t       :121,130
+    d = int((tau.float() * N).long())                          # _scale_timesteps          :69-71
+    beta = tab["beta_0"] + (tau * N - 1) / (N - 1) * (tab["beta_1"] - tab["beta_0"])   # :75
+    if d > 0:                                                  # :108-113
+        scale = torch.sqrt(1 - tab["alphas_cumprod"][d - 1]) / torch.sqrt(1 - tab["alphas_cumprod"][d])
+    else:
+        scale = torch.tensor(0.0)
+    return {"d": d, "beta": beta, "sqrt_1m_ab": tab["sqrt_1m_alphas_cumprod"][d], "g": scale * torch.sqrt(beta)}
+
+
+def sde_purify(sd, x0, t_star: int, noise, T: int = 200, eps_fn=None, **wn_kw):
+    """RevDiffWave.audio_editing_sample with sample_step=1, rand_t=False (diffwave_sde.py:166-211).
+
+    noise order: e (diffusion), then one N(0,1) tensor per Euler step (dW = sqrt(ds) * z).
+    """
+    x0 = _t(x0, torch.float32)
+    tab = sde_tables(T, 0.0001 * T, 0.02 * T)
+    eps_fn = eps_fn or (lambda xx, tt: wavenet_forward(sd, xx, tt * torch.ones(xx.shape[0], 1), **wn_kw))
+    a = (1 - tab["discrete_betas"]).cumprod(dim=0)             # :189
+    e = noise(x0.shape)
+    x = x0 * a[t_star - 1].sqrt() + e * (1.0 - a[t_star - 1]).sqrt()   # :190
+    for s, ds in sde_euler_schedule(t_star, T):
+        c = sde_step_coefficients(tab, s)
+        eps = eps_fn(x, c["d"]).to(torch.float32)              # compute_eps_t(x, disc_steps[0])   :94
+        drift = -0.5 * c["beta"] * x                            # vpsde_fn                          :80
+        score = -eps / c["sqrt_1m_ab"]                          #                                   :98
+        rdrift = drift - c["beta"] * score                      # diffusion**2 == beta              :103
+        f = -rdrift                                             #                                   :124
+        x = x + f * ds + c["g"] * torch.sqrt(ds) * noise(x.shape)
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# a14  mel front end (torchaudio MelSpectrogram + AmplitudeToDB restated)     SURVEY.md Appendix C
+# --------------------------------------------------------------------------------------
+def _hz_to_mel(f, scale):
+    f = np.asarray(f, dtype=np.float64)
+    if scale == "htk":
+        return 2595.0 * np.log10(1.0 + f / 700.0)
+    f_sp = 200.0 / 3
+    mels = f / f_sp
+    min_log_hz, logstep = 1000.0, math.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-30) / min_log_hz) / logstep, mels)
+
+
+def _mel_to_hz(m, scale):
+    m = np.asarray(m, dtype=np.float64)
+    if scale == "htk":
+        return 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    f_sp = 200.0 / 3
+    min_log_hz, logstep = 1000.0, math.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_filterbank(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int,
+                   norm: str | None, mel_scale: str) -> np.ndarray:
+    """Triangular filterbank (n_freqs, n_mels), torchaudio.functional.melscale_fbanks semantics."""
+    all_freqs = np.linspace(0, sample_rate // 2, n_freqs)
+    m_pts = np.linspace(_hz_to_mel(f_min, mel_scale), _hz_to_mel(f_max, mel_scale), n_mels + 2)
+    f_pts = _mel_to_hz(m_pts, mel_scale)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts[None, :] - all_freqs[:, None]
+    down = -slopes[:, :-2] / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    fb = np.maximum(0.0, np.minimum(down, up))
+    if norm == "slaney":
+        fb = fb * (2.0 / (f_pts[2:n_mels + 2] - f_pts[:n_mels]))[None, :]
+    return fb.astype(np.float32)
+
+
+MEL_SC09 = dict(sample_rate=16000, n_fft=2048, hop_length=512, n_mels=32, norm="slaney",
+                pad_mode="constant", mel_scale="slaney")      # certified_robustness_eval.py:85-86
+MEL_KWS = dict(sample_rate=16000, n_fft=400, hop_length=200, n_mels=32, norm=None,
+               pad_mode="reflect", mel_scale="htk")           # kws_adaptive_attack_eval.py:74-75 (torchaudio defaults)
+
+
+def mel_db(wave, sample_rate=16000, n_fft=2048, hop_length=512, n_mels=32, norm="slaney",
+           pad_mode="constant", mel_scale="slaney", dtype=torch.float64):
+    """(B,1,L) -> (B,1,n_mels,1+L//hop): centre-padded STFT (periodic hann, win=n_fft) as an explicit DFT,
+    power, mel filterbank, 10*log10(clamp(.,1e-10)) (AmplitudeToDB('power'), ref 1, no top_db)."""
+    x = _t(wave, dtype)
+    B, _, L = x.shape
+    pad = n_fft // 2
+    xp = F.pad(x, (pad, pad), mode=pad_mode)[:, 0]                                  # (B, L+n_fft)
+    n_frames = 1 + L // hop_length
+    frames = xp.unfold(1, n_fft, hop_length)[:, :n_frames]                          # (B, F, n_fft)
+    n = torch.arange(n_fft, dtype=torch.float64)
+    win = (0.5 - 0.5 * torch.cos(2 * math.pi * n / n_fft))                           # periodic hann
+    k = torch.arange(n_fft // 2 + 1, dtype=torch.float64)
+    ang = 2 * math.pi * torch.outer(n, k) / n_fft
+    fw = frames * win.to(dtype)
+    re = fw @ torch.cos(ang).to(dtype)
+    im = fw @ (-torch.sin(ang)).to(dtype)
+    power = re * re + im * im                                                       # (B, F, n_freqs)
+    fb = _t(mel_filterbank(n_fft // 2 + 1, 0.0, sample_rate / 2, n_mels, sample_rate, norm, mel_scale), dtype)
+    mel = power @ fb                                                                 # (B, F, n_mels)
+    db = 10.0 * torch.log10(torch.clamp(mel, min=1e-10))
+    return db.transpose(1, 2).unsqueeze(1).to(torch.float32)                        # (B,1,n_mels,F)
+
+
+# --------------------------------------------------------------------------------------
+# a15  CifarResNeXt                                  audio_models/ConvNets_SpeechCommands/models/resnext.py
+# --------------------------------------------------------------------------------------
+def _bn_eval(sd, p, x, dtype, eps=1e-5):
+    w, b = _t(sd[p + ".weight"], dtype), _t(sd[p + ".bias"], dtype)
+    m, v = _t(sd[p + ".running_mean"], dtype), _t(sd[p + ".running_var"], dtype)
+    shape = (1, -1) + (1,) * (x.dim() - 2)
+    return (x - m.reshape(shape)) / torch.sqrt(v.reshape(shape) + eps) * w.reshape(shape) + b.reshape(shape)
+
+
+def resnext_forward(sd, spec, cardinality=8, depth=29, widen_factor=4, dtype=torch.float32):
+    """(B,1,32,32) -> (B,nlabels) logits; resnext.py:56-64 (bottleneck), :134-142 (net)."""
+    w = lambda k: _t(sd[k], dtype)
+    x = _t(spec, dtype)
+    x = F.relu(_bn_eval(sd, "bn_1", F.conv2d(x, w("conv_1_3x3.weight"), padding=1), dtype))
+    block_depth = (depth - 2) // 9
+    stages = [64, 64 * widen_factor, 128 * widen_factor, 256 * widen_factor]
+    for s in range(3):
+        for b in range(block_depth):
+            p = f"stage_{s + 1}.stage_{s + 1}_bottleneck_{b}"
+            stride = 2 if (b == 0 and s > 0) else 1
+            y = F.relu(_bn_eval(sd, p + ".bn_reduce", F.conv2d(x, w(p + ".conv_reduce.weight")), dtype))
+            y = F.relu(_bn_eval(sd, p + ".bn", F.conv2d(y, w(p + ".conv_conv.weight"), stride=stride, padding=1,
+                                                        groups=cardinality), dtype))
+            y = _bn_eval(sd, p + ".bn_expand", F.conv2d(y, w(p + ".conv_expand.weight")), dtype)
+            if (p + ".shortcut.shortcut_conv.weight") in sd:
+                r = _bn_eval(sd, p + ".shortcut.shortcut_bn",
+                             F.conv2d(x, w(p + ".shortcut.shortcut_conv.weight"), stride=stride), dtype)
+            else:
+                r = x
+            x = F.relu(r + y)
+    x = F.avg_pool2d(x, 8, 1).reshape(-1, stages[3])
+    return F.linear(x, w("classifier.weight"), w("classifier.bias"))
+
+
+# --------------------------------------------------------------------------------------
+# a17  M5                                            audio_models/M5/M5Net.py:21-38
+# --------------------------------------------------------------------------------------
+def m5_forward(sd, wave, stride=16, dtype=torch.float32):
+    w = lambda k: _t(sd[k], dtype)
+    x = _t(wave, dtype)
+    for i in range(1, 5):
+        x = F.conv1d(x, w(f"conv{i}.weight"), w(f"conv{i}.bias"), stride=stride if i == 1 else 1)
+        x = F.max_pool1d(F.relu(_bn_eval(sd, f"bn{i}", x, dtype)), 4)
+    x = F.avg_pool1d(x, x.shape[-1]).reshape(x.shape[0], -1)
+    return F.log_softmax(F.linear(x, w("fc1.weight"), w("fc1.bias")), dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# a18  KWSModel (RCNN_KWS)                           audio_models/RCNN_KWS/model.py:5-113
+# --------------------------------------------------------------------------------------
+def _gru_dir(x, w_ih, w_hh, b_ih, b_hh, reverse):
+    """x (T,B,I) -> (T,B,H); torch.nn.GRU gate order r,z,n."""
+    T, B, _ = x.shape
+    H = w_hh.shape[1]
+    h = torch.zeros(B, H, dtype=x.dtype)
+    outs = [None] * T
+    order = range(T - 1, -1, -1) if reverse else range(T)
+    for t in order:
+        gi = F.linear(x[t], w_ih, b_ih)
+        gh = F.linear(h, w_hh, b_hh)
+        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+        z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1 - z) * n + z * h
+        outs[t] = h
+    return torch.stack(outs, 0)
+
+
+def kws_forward(sd, spec, kernel_size=(20, 5), stride=(8, 2), gru_num_layers=2, dtype=torch.float32):
+    """(B,1,32,W) -> (B,4) log-probs."""
+    w = lambda k: _t(sd[k], dtype)
+    x = _t(spec, dtype)
+    x = x.squeeze(1) if x.dim() == 4 else x                                         # model.py:94
+    in_size = x.shape[1]
+    x = F.conv1d(x, w("CRNN_model.sepconv.0.weight"), w("CRNN_model.sepconv.0.bias"), stride=stride[1],
+                 groups=in_size)                                                     # model.py:7-9
+    x = F.conv1d(x, w("CRNN_model.sepconv.1.weight"), w("CRNN_model.sepconv.1.bias"), stride=stride[0],
+                 groups=int(in_size / kernel_size[0]))                               # model.py:10-11
+    x = x.permute(2, 0, 1)                                                           # (seq,B,H)  model.py:28
+    for layer in range(gru_num_layers):
+        g = "CRNN_model.gru."
+        fwd = _gru_dir(x, w(f"{g}weight_ih_l{layer}"), w(f"{g}weight_hh_l{layer}"),
+                       w(f"{g}bias_ih_l{layer}"), w(f"{g}bias_hh_l{layer}"), False)
+        bwd = _gru_dir(x, w(f"{g}weight_ih_l{layer}_reverse"), w(f"{g}weight_hh_l{layer}_reverse"),
+                       w(f"{g}bias_ih_l{layer}_reverse"), w(f"{g}bias_hh_l{layer}_reverse"), True)
+        x = torch.cat((fwd, bwd), dim=2)
+    e = F.linear(torch.tanh(F.linear(x, w("attn_layer.Wx_b.weight"), w("attn_layer.Wx_b.bias"))),
+                 w("attn_layer.Vt.weight"))[..., 0].transpose(0, 1)                  # (B,seq)  model.py:105-108
+    a = F.softmax(e, dim=-1).unsqueeze(1)                                            # model.py:59
+    c = torch.bmm(a, x.transpose(0, 1))[:, 0]                                        # model.py:58,60
+    return F.log_softmax(F.linear(c, w("apply_attn.U.weight")), dim=-1)             # model.py:61-62
+
+
+# --------------------------------------------------------------------------------------
+# a20  AcousticSystem.forward                        acoustic_system.py:27-51
+# --------------------------------------------------------------------------------------
+def acoustic_rescale(x):
+    x = _t(x, torch.float32)
+    if 0.9 * x.max() > 1 and 0.9 * x.min() < -1:             # acoustic_system.py:29-30
+        x = x / (2 ** 15)
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# a21  RobustCertificate                             robustness_eval/certified_robust.py
+# --------------------------------------------------------------------------------------
+def compute_t_star(hp, sigma: float) -> int:
+    """certified_robust.py:50-51,102-110."""
+    alpha_bar_star = 1 / (1 + sigma ** 2)
+    return int(torch.abs(hp["Alpha_bar"] - alpha_bar_star).min(0, keepdim=True)[1].item()) + 1
+
+
+def lower_conf_bound(k: int, n: int, alpha: float = 0.001) -> float:
+    """certified_robust.py:113-117: statsmodels proportion_confint(k, n, 2*alpha, 'beta')[0]
+    == Clopper-Pearson lower bound beta.ppf(alpha, k, n-k+1) (0 when k == 0)."""
+    from scipy.stats import beta
+    if k == 0:
+        return 0.0
+    return float(beta.ppf(alpha, k, n - k + 1))
+
+
+def certify_from_counts(counts0, counts, n: int, sigma: float, alpha: float = 0.001):
+    """certified_robust.py:84-96: (y_pred, radius)."""
+    from scipy.stats import norm
+    c_a = int(np.argmax(np.asarray(counts0)))
+    pa = lower_conf_bound(int(counts[c_a]), n, alpha)
+    if pa > 0.5:
+        return c_a, float(sigma * norm.ppf(pa))
+    return -1, 0.0
+
+
+def smooth_counts(logits_fn, x, n: int, sigma: float, batch_size: int, noise, num_classes: int, hp):
+    """certified_robust.py:33-67 with the diffusion denoiser: x (1,1,L); logits_fn(x_in, t_star) -> (b,K)."""
+    x = _t(x, torch.float32)
+    batches = [batch_size] * (n // batch_size) + ([n % batch_size] if n % batch_size else [])
+    counts = np.zeros(num_classes, dtype=np.int64)
+    alpha_bar_star = 1 / (1 + sigma ** 2)
+    t_star = compute_t_star(hp, sigma)
+    for b in batches:
+        x_in = x.repeat(b, 1, 1) + sigma * noise((b,) + tuple(x.shape[1:]))
+        x_in = alpha_bar_star ** 0.5 * x_in
+        pred = logits_fn(x_in, t_star).max(1)[1]
+        counts += np.bincount(pred.numpy(), minlength=num_classes)
+    return counts

@@ -1,0 +1,174 @@
+"""Pins the CPU oracle (oracle/audiopure_oracle.py) against outputs of the UNMODIFIED reference
+(tests/golden/reference_golden.npz, produced by tests/golden/make_golden.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import audiopure_b200  # noqa: F401
+from audiopure_b200 import synthetic
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import audiopure_oracle as orc  # noqa: E402
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def sd_full():
+    return synthetic.wavenet_state_dict(seed=0)
+
+
+@pytest.fixture(scope="module")
+def hp():
+    return orc.diffusion_hyperparams(200, 1e-4, 0.02)
+
+
+def noise_list(seed, n, shape):
+    return orc.NoiseSource([synthetic.host_noise(shape, seed, i) for i in range(n)])
+
+
+def test_hyperparams_bit_exact(golden, hp):
+    for k in ("Beta", "Alpha", "Alpha_bar", "Sigma"):
+        assert np.array_equal(hp[k].numpy(), golden["hp_" + k]), k
+    # KATs quoted in SURVEY.md §8 a1
+    np.testing.assert_allclose(hp["Alpha_bar"][:3].numpy(), [0.99989998, 0.99970001, 0.99940014], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(hp["Sigma"][:3].numpy(), [0.01, 0.00816578, 0.01224867], rtol=0, atol=1e-8)
+
+
+def test_step_embedding(golden):
+    e = orc.step_embedding(torch.from_numpy(golden["emb_steps"]), 128).numpy()
+    np.testing.assert_allclose(e, golden["emb"], rtol=0, atol=1e-6)
+    assert abs(e[1, 0] - 0.84147) < 1e-5 and abs(e[1, 64] - 0.54030) < 1e-5
+
+
+@pytest.mark.parametrize("key,L,B,t,seed", [("eps_full_L1024_t1", 1024, 2, 1.0, 1234),
+                                            ("eps_full_L1024_t65", 1024, 2, 65.0, 1234),
+                                            ("eps_full_L3001_t7", 3001, 1, 7.0, 77)])
+def test_wavenet_full(golden, sd_full, key, L, B, t, seed):
+    x = synthetic.synthetic_waveforms(B, L, seed=seed)
+    eps = orc.wavenet_forward(sd_full, x, t * torch.ones(B, 1)).numpy()
+    assert rel_l2(eps, golden[key]) < 2e-5
+
+
+def test_wavenet_small_config(golden):
+    cfg = dict(synthetic.DEFAULT_WAVENET_CONFIG, res_channels=64, skip_channels=64, num_res_layers=5, dilation_cycle=3)
+    sd = synthetic.wavenet_state_dict(seed=3, config=cfg)
+    x = synthetic.synthetic_waveforms(3, 500, seed=5)
+    eps = orc.wavenet_forward(sd, x, 3.0 * torch.ones(3, 1), num_res_layers=5, dilation_cycle=3).numpy()
+    assert rel_l2(eps, golden["eps_small_L500_t3"]) < 2e-5
+
+
+def test_ddpm_purifier(golden, sd_full, hp):
+    x = synthetic.synthetic_waveforms(2, 1024, seed=1234)
+    y2 = orc.ddpm_forward(sd_full, x, hp, 2, noise_list(2024, 2, x.shape)).numpy()
+    assert rel_l2(y2, golden["ddpm_t2_L1024"]) < 1e-5
+    y3 = orc.ddpm_forward(sd_full, x, hp, 3, noise_list(2025, 3, x.shape)).numpy()
+    assert rel_l2(y3, golden["ddpm_t3_L1024"]) < 1e-5
+
+
+def test_one_two_shot_and_fast_reverse(golden, sd_full, hp):
+    x = synthetic.synthetic_waveforms(2, 1024, seed=1234)
+    assert rel_l2(orc.one_shot_denoise(sd_full, x, hp, 66).numpy(), golden["oneshot_t66_L1024"]) < 1e-5
+    assert rel_l2(orc.two_shot_denoise(sd_full, x, hp, 66).numpy(), golden["twoshot_t66_L1024"]) < 1e-5
+    y = orc.fast_reverse(sd_full, x, hp, 9, noise_list(2026, 3, x.shape)).numpy()
+    assert rel_l2(y, golden["fastrev_t9_L1024"]) < 1e-5
+
+
+def test_sde_drift_and_diffusion(golden, sd_full):
+    """RevVPSDE.f / .g (diffwave_sde.py:117-133) at fixed solver times; x is (B, L) flattened audio."""
+    x = torch.from_numpy(synthetic.synthetic_waveforms(2, 1024, seed=1234))
+    tab = orc.sde_tables(200, 0.0001 * 200, 0.02 * 200)
+    for i, s in enumerate(golden["sde_s"]):
+        c = orc.sde_step_coefficients(tab, torch.tensor(s, dtype=torch.float32))
+        eps = orc.wavenet_forward(sd_full, x, c["d"] * torch.ones(2, 1))
+        f = -(-0.5 * c["beta"] * x - c["beta"] * (-eps / c["sqrt_1m_ab"]))
+        assert rel_l2(f.reshape(2, -1).numpy(), golden["sde_f"][i]) < 1e-5, s
+        np.testing.assert_allclose(np.full(2, float(c["g"])), golden["sde_g"][i], rtol=1e-6, atol=1e-8)
+
+
+def test_sde_schedule_indices():
+    """Float32 step-index hazard, SURVEY.md §8 a13: d = t*-1..0 for t* <= 6, t*..1 for t* >= 7."""
+    tab = orc.sde_tables(200, 0.0001 * 200, 0.02 * 200)
+    for t_star in range(1, 11):
+        sched = orc.sde_euler_schedule(t_star, 200)
+        ds = [orc.sde_step_coefficients(tab, s)["d"] for s, _ in sched]
+        assert len(sched) == t_star
+        expect = list(range(t_star - 1, -1, -1)) if t_star <= 6 else list(range(t_star, 0, -1))
+        assert ds == expect, (t_star, ds)
+        assert abs(float(sched[-1][1]) - 0.00499) < 2e-5
+
+
+def test_sde_equals_ddpm_for_small_t(sd_full, hp):
+    """With shared noise the Euler chain matches the DDPM chain to first order for t* <= 6."""
+    cfg = dict(synthetic.DEFAULT_WAVENET_CONFIG, res_channels=64, skip_channels=64, num_res_layers=5, dilation_cycle=3)
+    sd = synthetic.wavenet_state_dict(seed=3, config=cfg)
+    kw = dict(num_res_layers=5, dilation_cycle=3)
+    x = synthetic.synthetic_waveforms(2, 400, seed=5)
+    a = orc.ddpm_forward(sd, x, hp, 3, noise_list(7, 3, x.shape), **kw).numpy()
+    b = orc.sde_purify(sd, x, 3, noise_list(7, 4, x.shape), **kw).numpy()
+    assert rel_l2(b, a) < 2e-3
+
+
+def test_mel_front_ends(golden):
+    x = synthetic.synthetic_waveforms(2, 16000, seed=99)
+    sc = orc.mel_db(x, **orc.MEL_SC09).numpy()
+    assert sc.shape == (2, 1, 32, 32)
+    assert np.abs(sc - golden["mel_sc09"]).max() < 2e-3     # dB; torchaudio runs an fp32 FFT
+    kw = orc.mel_db(x, **orc.MEL_KWS).numpy()
+    assert kw.shape == (2, 1, 32, 81)
+    assert np.abs(kw - golden["mel_kws"]).max() < 2e-3
+    fb = orc.mel_filterbank(1025, 0.0, 8000.0, 32, 16000, "slaney", "slaney")
+    np.testing.assert_allclose(fb, golden["mel_sc09_fb"], rtol=1e-4, atol=1e-7)
+    fbk = orc.mel_filterbank(201, 0.0, 8000.0, 32, 16000, None, "htk")
+    np.testing.assert_allclose(fbk, golden["mel_kws_fb"], rtol=1e-4, atol=5e-6)
+
+
+def test_classifiers(golden):
+    rx = orc.resnext_forward(synthetic.resnext_state_dict(seed=0), golden["mel_sc09"]).numpy()
+    np.testing.assert_allclose(rx, golden["resnext_logits"], rtol=0, atol=2e-4)
+    assert np.array_equal(rx.argmax(1), golden["resnext_logits"].argmax(1))
+    x = synthetic.synthetic_waveforms(2, 16000, seed=99)
+    m5 = orc.m5_forward(synthetic.m5_state_dict(seed=0), x).numpy()
+    np.testing.assert_allclose(m5, golden["m5_logprobs"], rtol=0, atol=1e-4)
+    kws = orc.kws_forward(synthetic.kws_state_dict(seed=0), golden["mel_kws"]).numpy()
+    np.testing.assert_allclose(kws, golden["kws_logprobs"], rtol=0, atol=1e-4)
+
+
+def test_acoustic_system_end_to_end(golden, sd_full, hp):
+    x = synthetic.synthetic_waveforms(1, 16000, seed=1234)
+    pur = orc.ddpm_forward(sd_full, orc.acoustic_rescale(x), hp, 2, noise_list(2027, 2, x.shape))
+    assert rel_l2(pur.numpy(), golden["system_purified"]) < 1e-5
+    rsd = synthetic.resnext_state_dict(seed=0)
+    logits = orc.resnext_forward(rsd, orc.mel_db(pur, **orc.MEL_SC09)).numpy()
+    np.testing.assert_allclose(logits, golden["system_logits"], rtol=0, atol=2e-3)
+    assert logits.argmax(1)[0] == golden["system_logits"].argmax(1)[0]
+    raw = orc.resnext_forward(rsd, orc.mel_db(orc.acoustic_rescale(x * 2 ** 15), **orc.MEL_SC09)).numpy()
+    np.testing.assert_allclose(raw, golden["system_logits_int16_nodefense"], rtol=0, atol=2e-3)
+
+
+def test_certification(golden, sd_full, hp):
+    assert [orc.compute_t_star(hp, s) for s in (0.25, 0.5, 1.0)] == list(golden["smooth_t_star"]) == [34, 66, 117]
+    x = synthetic.synthetic_waveforms(1, 16000, seed=1234)
+    rsd = synthetic.resnext_state_dict(seed=0)
+
+    def logits_fn(x_in, t_star):
+        x0 = orc.one_shot_denoise(sd_full, x_in, hp, t_star)
+        return orc.resnext_forward(rsd, orc.mel_db(x0, **orc.MEL_SC09))
+
+    shapes = [(5, 1, 16000), (5, 1, 16000), (2, 1, 16000)]
+    noise = orc.NoiseSource([synthetic.host_noise(s, 2028, i) for i, s in enumerate(shapes)])
+    counts = orc.smooth_counts(logits_fn, x, 12, 0.5, 5, noise, 10, hp)
+    assert np.array_equal(counts, golden["smooth_counts_n12"])
+    # Clopper-Pearson KATs (scipy), SURVEY.md §8 a21
+    assert abs(orc.lower_conf_bound(99000, 100000) - 0.988989) < 1e-6
+    y, r = orc.certify_from_counts([0, 5, 95], [0, 1000, 99000], 100000, 0.5)
+    assert y == 2 and abs(r - 1.1450) < 1e-3
+    y, r = orc.certify_from_counts([0, 100], [0, 100000], 100000, 0.5)
+    assert y == 1 and abs(r - 1.9057) < 1e-3
+    assert orc.certify_from_counts([60, 40], [50200, 49800], 100000, 0.5) == (-1, 0.0)

@@ -1,0 +1,83 @@
+"""Build libaudiopure_b200.so (sm_100a only) in-tree with nvcc.
+
+The library is plain C ABI (include/audiopure.h); it links the static CUDA runtime and resolves the one driver entry
+point it needs (cuTensorMapEncodeTiled) at run time, so it loads -- and exports all its symbols -- on a machine without
+a GPU or libcuda.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libaudiopure_b200.so")
+STAMP = LIB_PATH + ".stamp"
+SOURCES = ["ap_update.cu", "ap_wavenet.cu", "ap_wavenet_tc.cu", "ap_mel.cu", "ap_classifier.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    names = sorted(os.listdir(CSRC)) + ["../../include/audiopure.h", "../build.py"]
+    for name in names:
+        path = os.path.join(CSRC, name)
+        if os.path.isfile(path):
+            h.update(name.encode())
+            with open(path, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as f:
+        return f.read().strip() == _fingerprint()
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu under csrc/ for sm_100a and link the shared library.  Returns its path."""
+    if not force and is_current():
+        return LIB_PATH
+    nvcc = _nvcc()
+    objdir = os.path.join(PKG_DIR, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs, log = [], []
+    for src, obj, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {src}\n{out}")
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+        objs.append(obj)
+    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-cudart", "static", "-Xlinker", "--no-undefined"]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if out.returncode != 0:
+        raise RuntimeError(f"link failed:\n{out.stdout}")
+    with open(os.path.join(objdir, "nvcc.log"), "w") as f:
+        f.write("\n".join(log))
+    with open(STAMP, "w") as f:
+        f.write(_fingerprint())
+    if verbose:
+        print("\n".join(log))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

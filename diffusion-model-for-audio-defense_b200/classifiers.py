@@ -1,0 +1,149 @@
+"""Classifier drop-ins: ``Classifier(x) -> logits / log-probs`` (acoustic_system.py:49, certified_robust.py:30).
+
+  * ``ResNeXtClassifier``  CifarResNeXt, audio_models/ConvNets_SpeechCommands/models/resnext.py:67-142
+  * ``M5Classifier``       M5, audio_models/M5/M5Net.py:4-38
+  * ``KWSClassifier``      KWSModel, audio_models/RCNN_KWS/model.py:66-113
+Each takes the reference module's ``state_dict()`` (tensors or numpy arrays).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["ResNeXtClassifier", "M5Classifier", "KWSClassifier", "create_model"]
+
+
+def _np32(t) -> np.ndarray:
+    if isinstance(t, torch.Tensor):
+        t = t.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(t, dtype=np.float32))
+
+
+class _Classifier(torch.nn.Module):
+    kind = -1
+
+    def _create(self, cfg: "_lib.ClassifierCfg", weights, device):
+        self._lib = _lib.load()
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        dev = device if isinstance(device, int) else (torch.device(device).index or 0)
+        self._weights = [_np32(w) for w in weights]
+        self._handle = C.c_void_p()
+        _lib.check(self._lib.ap_classifier_create(C.byref(self._handle), C.byref(cfg), _lib.ptr_array(self._weights),
+                                                  len(self._weights), dev), "ap_classifier_create")
+        self.num_classes = cfg.num_classes
+
+    def _run(self, x: torch.Tensor, B: int, in_len: int) -> torch.Tensor:
+        if not x.is_cuda:
+            raise _lib.AudioPureError(f"{type(self).__name__}: input must be a CUDA tensor (there is no CPU path)")
+        if x.requires_grad and torch.is_grad_enabled():
+            raise _lib.AudioPureError(f"{type(self).__name__}: inference-only (input requires grad)")
+        x = x.detach().to(torch.float32).contiguous()
+        out = torch.empty(B, self.num_classes, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(self._lib.ap_classifier_forward(self._handle, x.data_ptr(), out.data_ptr(), B, in_len,
+                                                       _lib.stream_ptr()), "ap_classifier_forward")
+        return out
+
+    def cuda(self, device=None):
+        return self
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            try:
+                self._lib.ap_classifier_destroy(h)
+            except Exception:
+                pass
+
+
+def _strip(sd: dict) -> dict:
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items() if not k.endswith("num_batches_tracked")}
+
+
+class ResNeXtClassifier(_Classifier):
+    def __init__(self, state_dict: dict, nlabels=10, cardinality=8, depth=29, base_width=64, widen_factor=4,
+                 in_channels=1, device=None):
+        super().__init__()
+        sd = _strip(state_dict)
+        bn = lambda p: [sd[p + ".weight"], sd[p + ".bias"], sd[p + ".running_mean"], sd[p + ".running_var"]]
+        w = [sd["conv_1_3x3.weight"], *bn("bn_1")]
+        for s in range(3):
+            for b in range((depth - 2) // 9):
+                p = f"stage_{s + 1}.stage_{s + 1}_bottleneck_{b}"
+                w += [sd[p + ".conv_reduce.weight"], *bn(p + ".bn_reduce"), sd[p + ".conv_conv.weight"], *bn(p + ".bn"),
+                      sd[p + ".conv_expand.weight"], *bn(p + ".bn_expand")]
+                if p + ".shortcut.shortcut_conv.weight" in sd:
+                    w += [sd[p + ".shortcut.shortcut_conv.weight"], *bn(p + ".shortcut.shortcut_bn")]
+        w += [sd["classifier.weight"], sd["classifier.bias"]]
+        cfg = _lib.ClassifierCfg(_lib.AP_CLS_RESNEXT, nlabels, cardinality, depth, base_width, widen_factor, in_channels,
+                                 0, 0, 0, 0, 0)
+        self._create(cfg, w, device)
+
+    def forward(self, spec: torch.Tensor) -> torch.Tensor:
+        assert spec.ndim == 4 and tuple(spec.shape[1:]) == (1, 32, 32), f"expected (B,1,32,32), got {tuple(spec.shape)}"
+        return self._run(spec, spec.shape[0], 32)
+
+
+class M5Classifier(_Classifier):
+    def __init__(self, state_dict: dict, n_input=1, first_kernel_size=160, n_output=10, stride=16, n_channel=32,
+                 device=None):
+        super().__init__()
+        assert n_input == 1
+        sd = _strip(state_dict)
+        w = []
+        for i in range(1, 5):
+            w += [sd[f"conv{i}.weight"], sd[f"conv{i}.bias"], sd[f"bn{i}.weight"], sd[f"bn{i}.bias"],
+                  sd[f"bn{i}.running_mean"], sd[f"bn{i}.running_var"]]
+        w += [sd["fc1.weight"], sd["fc1.bias"]]
+        cfg = _lib.ClassifierCfg(_lib.AP_CLS_M5, n_output, 0, 0, 0, 0, 1, first_kernel_size, stride, n_channel, 0, 0)
+        self._create(cfg, w, device)
+
+    def forward(self, wav: torch.Tensor) -> torch.Tensor:
+        assert wav.ndim == 3 and wav.shape[1] == 1, f"expected (B,1,L), got {tuple(wav.shape)}"
+        return self._run(wav, wav.shape[0], wav.shape[2])
+
+
+class KWSClassifier(_Classifier):
+    def __init__(self, state_dict: dict, in_size=32, hidden_size=64, num_classes=4, device=None):
+        super().__init__()
+        sd = _strip(state_dict)
+        w = [sd["CRNN_model.sepconv.0.weight"], sd["CRNN_model.sepconv.0.bias"], sd["CRNN_model.sepconv.1.weight"],
+             sd["CRNN_model.sepconv.1.bias"]]
+        for layer in range(2):
+            for suffix in ("", "_reverse"):
+                w += [sd[f"CRNN_model.gru.{n}_l{layer}{suffix}"] for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+        w += [sd["attn_layer.Wx_b.weight"], sd["attn_layer.Wx_b.bias"], sd["attn_layer.Vt.weight"], sd["apply_attn.U.weight"]]
+        cfg = _lib.ClassifierCfg(_lib.AP_CLS_KWS, num_classes, 0, 0, 0, 0, 1, 0, 0, 0, in_size, hidden_size)
+        self._create(cfg, w, device)
+        self.in_size = in_size
+
+    def forward(self, spec: torch.Tensor) -> torch.Tensor:
+        x = spec.squeeze(1) if spec.ndim == 4 else spec          # model.py:94
+        assert x.ndim == 3 and x.shape[1] == self.in_size, f"expected (B,1,{self.in_size},W), got {tuple(spec.shape)}"
+        return self._run(x, x.shape[0], x.shape[2])
+
+
+def create_model(path: str, device=None):
+    """audio_models/ConvNets_SpeechCommands/create_model.py:8-16: unpickle a whole (DataParallel) module and rebuild
+    it on the B200 kernels from its state dict.  Needs the reference's model classes importable for the unpickle."""
+    model = torch.load(path, map_location="cpu", weights_only=False)
+    if hasattr(model, "module"):
+        model = model.module
+    name = type(model).__name__
+    sd = model.state_dict()
+    if name == "CifarResNeXt":
+        return ResNeXtClassifier(sd, nlabels=model.nlabels, cardinality=model.cardinality, depth=model.depth,
+                                 base_width=model.base_width, widen_factor=model.widen_factor,
+                                 in_channels=model.conv_1_3x3.in_channels, device=device)
+    if name == "M5":
+        return M5Classifier(sd, first_kernel_size=model.conv1.kernel_size[0], n_output=model.fc1.out_features,
+                            stride=model.conv1.stride[0], n_channel=model.conv1.out_channels, device=device)
+    if name == "KWSModel":
+        return KWSClassifier(sd, in_size=model.in_size, hidden_size=model.hidden_size, num_classes=model.num_classes,
+                             device=device)
+    raise NotImplementedError(f"create_model: classifier {name} has no B200 kernel path (SURVEY.md section 2, row 8a)")

@@ -1,0 +1,547 @@
+// K5 / K6: classifier forward passes (replace Classifier(spec) at acoustic_system.py:49 / certified_robust.py:30).
+//   AP_CLS_RESNEXT  CifarResNeXt (models/resnext.py:23-142): every convolution is an implicit GEMM over NHWC activations
+//                   (rows = output pixels, K = taps x input channels of the group) with eval-mode BatchNorm folded into
+//                   the weights/bias and the residual add + ReLU fused into the epilogue.
+//   AP_CLS_M5       M5 (audio_models/M5/M5Net.py:4-38)            conv1d/BN/ReLU/maxpool x4, avgpool, fc, log_softmax
+//   AP_CLS_KWS      KWSModel (audio_models/RCNN_KWS/model.py:5-113)  sepconv, 2-layer bi-GRU, attention, fc, log_softmax
+#include <cmath>
+#include <memory>
+
+#include "ap_common.cuh"
+#include "ap_internal.h"
+#include "ap_sgemm.cuh"
+
+namespace ap {
+
+// ---------------------------------------------------------------------------------------------- conv as implicit GEMM
+// in: NHWC [B][H][W][Ctot]; group z uses channels [z*Cg, (z+1)*Cg); k = (r*kw + s)*Cg + c
+template <bool VEC> struct Conv2dLoader {
+  const float* in;
+  int H, W, Ctot, Cg, kh, kw, stride, pad, Ho, Wo;
+  __device__ __forceinline__ float one(int z, int b, int oh, int ow, int k) const {
+    const int rs = k / Cg, c = k - rs * Cg, r = rs / kw, s = rs - r * kw;
+    const int ih = oh * stride + r - pad, iw = ow * stride + s - pad;
+    if (ih < 0 || ih >= H || iw < 0 || iw >= W) return 0.f;
+    return in[((static_cast<long long>(b) * H + ih) * W + iw) * Ctot + z * Cg + c];
+  }
+  __device__ __forceinline__ float4 load4(int z, int m, int k, int M, int K) const {
+    if (m >= M || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const int b = m / (Ho * Wo), rem = m - b * (Ho * Wo), oh = rem / Wo, ow = rem - oh * Wo;
+    if (VEC) {
+      const int rs = k / Cg, c = k - rs * Cg, r = rs / kw, s = rs - r * kw;
+      const int ih = oh * stride + r - pad, iw = ow * stride + s - pad;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+      return *reinterpret_cast<const float4*>(in + ((static_cast<long long>(b) * H + ih) * W + iw) * Ctot + z * Cg + c);
+    }
+    float4 v;
+    v.x = one(z, b, oh, ow, k);
+    v.y = k + 1 < K ? one(z, b, oh, ow, k + 1) : 0.f;
+    v.z = k + 2 < K ? one(z, b, oh, ow, k + 2) : 0.f;
+    v.w = k + 3 < K ? one(z, b, oh, ow, k + 3) : 0.f;
+    return v;
+  }
+};
+// out[m][z*Ng + n] = act(acc + bias [+ residual])
+struct ConvEpi {
+  float* out;
+  const float* bias;
+  const float* residual;
+  int Ctot, Ng, relu;
+  __device__ __forceinline__ void put(int z, int m, int n, float acc) const {
+    if (n >= Ng) return;
+    const int ch = z * Ng + n;
+    const long long idx = static_cast<long long>(m) * Ctot + ch;
+    float v = acc + bias[ch];
+    if (residual) v += residual[idx];
+    out[idx] = relu ? fmaxf(v, 0.f) : v;
+  }
+  __device__ __forceinline__ void store(int z, int m, int n0, int tx, const float (&lo)[4], const float (&hi)[4], int) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      put(z, m, n0 + tx * 4 + j, lo[j]);
+      put(z, m, n0 + 64 + tx * 4 + j, hi[j]);
+    }
+  }
+};
+
+struct ConvLayer {
+  int Cin = 0, Cout = 0, kh = 1, kw = 1, stride = 1, pad = 0, groups = 1;
+  int Cg = 0, Ng = 0, Ngp = 0, K = 0;
+  DevBuf w, bias;
+  // w_t: torch [Cout][Cin/groups][kh][kw]; optional BatchNorm(eval) folded: scale = gamma/sqrt(var+eps), shift = beta - mean*scale
+  int init(int cin, int cout, int kh_, int kw_, int stride_, int pad_, int groups_, const float* w_t, const float* conv_bias,
+           const float* bn_w, const float* bn_b, const float* bn_m, const float* bn_v) {
+    Cin = cin, Cout = cout, kh = kh_, kw = kw_, stride = stride_, pad = pad_, groups = groups_;
+    Cg = cin / groups, Ng = cout / groups, Ngp = ((Ng + 127) / 128) * 128, K = kh * kw * Cg;
+    std::vector<float> wp(static_cast<size_t>(groups) * K * Ngp, 0.f), bp(cout);
+    for (int o = 0; o < cout; ++o) {
+      float scale = 1.f, shift = conv_bias ? conv_bias[o] : 0.f;
+      if (bn_w) {
+        scale = bn_w[o] / std::sqrt(bn_v[o] + 1e-5f);
+        shift = bn_b[o] + (shift - bn_m[o]) * scale;
+      }
+      bp[o] = shift;
+      const int g = o / Ng, n = o - g * Ng;
+      for (int c = 0; c < Cg; ++c)
+        for (int r = 0; r < kh; ++r)
+          for (int s = 0; s < kw; ++s)
+            wp[(static_cast<size_t>(g) * K + (r * kw + s) * Cg + c) * Ngp + n] =
+                w_t[((static_cast<size_t>(o) * Cg + c) * kh + r) * kw + s] * scale;
+    }
+    AP_CUDA(w.upload(wp.data(), wp.size() * sizeof(float)));
+    AP_CUDA(bias.upload(bp.data(), bp.size() * sizeof(float)));
+    return AP_OK;
+  }
+  int run(const float* in, int B, int H, int W, float* out, const float* residual, int relu, cudaStream_t st) const {
+    const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    const long long M = static_cast<long long>(B) * Ho * Wo;
+    if (M >= (1ll << 31)) return fail(AP_ERR_INVALID, "conv: too many output pixels");
+    ConvEpi ep{out, bias.as<float>(), residual, Cout, Ng, relu};
+    cudaError_t e;
+    if (Cg % 4 == 0) {
+      Conv2dLoader<true> al{in, H, W, Cin, Cg, kh, kw, stride, pad, Ho, Wo};
+      e = sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
+    } else {
+      Conv2dLoader<false> al{in, H, W, Cin, Cg, kh, kw, stride, pad, Ho, Wo};
+      e = sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
+    }
+    if (e != cudaSuccess) return fail(AP_ERR_CUDA, "conv launch: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return AP_OK;
+  }
+};
+
+// global average pool over P positions + linear: logits[b][k] = fc_b[k] + sum_c fc_w[k][c] * mean_p x[b][p][c]
+__global__ void __launch_bounds__(256) pool_fc_kernel(const float* __restrict__ x, int P, int Cc, const float* __restrict__ fw,
+                                                      const float* __restrict__ fb, int Kc, float* __restrict__ logits,
+                                                      int log_softmax) {
+  extern __shared__ float sm[];   // Cc pooled + Kc logits
+  float* pooled = sm;
+  float* lg = sm + Cc;
+  const int b = blockIdx.x;
+  const float inv = 1.f / static_cast<float>(P);
+  for (int c = threadIdx.x; c < Cc; c += blockDim.x) {
+    float acc = 0.f;
+    for (int pp = 0; pp < P; ++pp) acc += x[(static_cast<long long>(b) * P + pp) * Cc + c];
+    pooled[c] = acc * inv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < Kc; k += blockDim.x >> 5) {
+    float acc = 0.f;
+    for (int c = lane; c < Cc; c += 32) acc = fmaf(fw[k * Cc + c], pooled[c], acc);
+    for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) lg[k] = acc + (fb ? fb[k] : 0.f);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float off = 0.f;
+    if (log_softmax) {
+      float mx = lg[0];
+      for (int k = 1; k < Kc; ++k) mx = fmaxf(mx, lg[k]);
+      float s = 0.f;
+      for (int k = 0; k < Kc; ++k) s += expf(lg[k] - mx);
+      off = mx + logf(s);
+    }
+    for (int k = 0; k < Kc; ++k) logits[b * Kc + k] = lg[k] - off;
+  }
+}
+
+// max_pool1d(kernel 4, stride 4) over channels-last [B][Lin][C] -> [B][Lin/4][C]
+__global__ void __launch_bounds__(256) maxpool4_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int Lin,
+                                                       int Cc) {
+  const int Lout = Lin / 4;
+  const long long total = static_cast<long long>(B) * Lout * Cc;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cc);
+    const long long t = i / Cc;
+    const int l = static_cast<int>(t % Lout);
+    const long long b = t / Lout;
+    const float* p = in + ((b * Lin + 4 * l) * Cc) + c;
+    out[i] = fmaxf(fmaxf(p[0], p[Cc]), fmaxf(p[2 * Cc], p[3 * Cc]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- KWS (RCNN + attention)
+// One CTA per sample; everything lives in shared memory (W <= 512 spectrogram frames).
+struct KwsWeights {
+  const float *dw_w, *dw_b, *pw_w, *pw_b;                 // sepconv.0 (32,1,5) / sepconv.1 (64,32,1)
+  const float* gru[2][2][4];                              // [layer][dir]{w_ih, w_hh, b_ih, b_hh}
+  const float *wx_w, *wx_b, *vt_w, *u_w;                  // attention
+};
+__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(256) kws_kernel(const float* __restrict__ spec, int Wf, int in_size, int H,
+                                                  int num_classes, KwsWeights w, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int W1 = (Wf - 5) / 2 + 1;          // depthwise conv k=5 stride 2          (model.py:7-9)
+  const int T = (W1 - 1) / 8 + 1;           // pointwise conv k=1 stride 8          (model.py:10-11)
+  float* dw = sm;                           // [in_size][W1] (only columns 8*t are needed, kept simple)
+  float* x0 = dw + in_size * W1;            // [T][H]
+  float* x1 = x0 + T * H;                   // [T][2H]
+  float* x2 = x1 + T * 2 * H;               // [T][2H]
+  float* hbuf = x2 + T * 2 * H;             // [2 dirs][H] hidden + [2][3H] gates scratch
+  float* gi = hbuf + 2 * H;                 // [2][3H]
+  float* gh = gi + 2 * 3 * H;               // [2][3H]
+  float* att = gh + 2 * 3 * H;              // [T]
+  const float* sp = spec + static_cast<long long>(b) * in_size * Wf;
+  for (int i = tid; i < in_size * W1; i += nt) {
+    const int c = i / W1, t = i - c * W1;
+    float acc = w.dw_b[c];
+    for (int k = 0; k < 5; ++k) acc = fmaf(w.dw_w[c * 5 + k], sp[c * Wf + 2 * t + k], acc);
+    dw[i] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < T * H; i += nt) {
+    const int t = i / H, o = i - t * H;
+    float acc = w.pw_b[o];
+    for (int c = 0; c < in_size; ++c) acc = fmaf(w.pw_w[o * in_size + c], dw[c * W1 + 8 * t], acc);
+    x0[i] = acc;
+  }
+  __syncthreads();
+  const float* xin = x0;
+  int in_l = H;
+  float* xout = x1;
+  for (int layer = 0; layer < 2; ++layer) {
+    for (int i = tid; i < 2 * H; i += nt) hbuf[i] = 0.f;
+    __syncthreads();
+    for (int step = 0; step < T; ++step) {
+      // both directions in parallel: dir 0 reads time `step`, dir 1 reads time T-1-step
+      for (int i = tid; i < 2 * 3 * H; i += nt) {
+        const int dir = i / (3 * H), g = i - dir * 3 * H;
+        const int t = dir ? T - 1 - step : step;
+        const float* wih = w.gru[layer][dir][0] + static_cast<long long>(g) * in_l;
+        const float* whh = w.gru[layer][dir][1] + static_cast<long long>(g) * H;
+        float a = w.gru[layer][dir][2][g], c = w.gru[layer][dir][3][g];
+        for (int k = 0; k < in_l; ++k) a = fmaf(wih[k], xin[t * in_l + k], a);
+        for (int k = 0; k < H; ++k) c = fmaf(whh[k], hbuf[dir * H + k], c);
+        gi[i] = a, gh[i] = c;
+      }
+      __syncthreads();
+      for (int i = tid; i < 2 * H; i += nt) {
+        const int dir = i / H, j = i - dir * H;
+        const int t = dir ? T - 1 - step : step;
+        const float* a = gi + dir * 3 * H;
+        const float* c = gh + dir * 3 * H;
+        const float r = sigm(a[j] + c[j]), z = sigm(a[H + j] + c[H + j]);
+        const float n = tanhf(a[2 * H + j] + r * c[2 * H + j]);
+        const float hn = (1.f - z) * n + z * hbuf[i];
+        hbuf[i] = hn;
+        xout[t * 2 * H + dir * H + j] = hn;
+      }
+      __syncthreads();
+    }
+    xin = xout, in_l = 2 * H, xout = x2;
+  }
+  // attention (model.py:38-62,105-108): e_t = Vt . tanh(Wx x_t + b); a = softmax_t(e); c = sum_t a_t x_t; out = log_softmax(U c)
+  const float* xf = xin;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int t = warp; t < T; t += nt >> 5) {
+    float acc = 0.f;
+    for (int o = lane; o < 2 * H; o += 32) {
+      float d = w.wx_b[o];
+      for (int k = 0; k < 2 * H; ++k) d = fmaf(w.wx_w[o * 2 * H + k], xf[t * 2 * H + k], d);
+      acc = fmaf(w.vt_w[o], tanhf(d), acc);
+    }
+    for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) att[t] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float mx = att[0];
+    for (int t = 1; t < T; ++t) mx = fmaxf(mx, att[t]);
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) att[t] = expf(att[t] - mx), s += att[t];
+    for (int t = 0; t < T; ++t) att[t] /= s;
+  }
+  __syncthreads();
+  float* ctx = gi;  // reuse: [2H]
+  for (int j = tid; j < 2 * H; j += nt) {
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc = fmaf(att[t], xf[t * 2 * H + j], acc);
+    ctx[j] = acc;
+  }
+  __syncthreads();
+  float* lg = gh;
+  for (int k = warp; k < num_classes; k += nt >> 5) {
+    float acc = 0.f;
+    for (int j = lane; j < 2 * H; j += 32) acc = fmaf(w.u_w[k * 2 * H + j], ctx[j], acc);
+    for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) lg[k] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float mx = lg[0];
+    for (int k = 1; k < num_classes; ++k) mx = fmaxf(mx, lg[k]);
+    float s = 0.f;
+    for (int k = 0; k < num_classes; ++k) s += expf(lg[k] - mx);
+    const float off = mx + logf(s);
+    for (int k = 0; k < num_classes; ++k) out[b * num_classes + k] = lg[k] - off;
+  }
+}
+
+// NCHW with C == 1 is already NHWC; this transposes (B, C, W) -> (B, W, C) for the M5 input when C > 1 (unused: C == 1)
+
+}  // namespace ap
+
+using namespace ap;
+
+struct Bottleneck {
+  ConvLayer reduce, conv, expand, shortcut;
+  bool has_shortcut = false;
+  int stride = 1, D = 0, cout = 0;
+};
+
+struct ap_classifier_s {
+  ap_classifier_cfg cfg{};
+  int device = 0;
+  // ResNeXt
+  ConvLayer stem;
+  std::vector<std::unique_ptr<Bottleneck>> blocks;
+  DevBuf fc_w, fc_b;
+  int feat = 0;
+  // M5
+  ConvLayer m5conv[4];
+  // KWS
+  std::vector<std::unique_ptr<DevBuf>> kws_bufs;
+  KwsWeights kws{};
+  // workspace
+  DevBuf buf[5];
+  size_t buf_elems = 0;
+  int chunk = 0;
+};
+
+static int ensure_ws(ap_classifier_t h, size_t elems) {
+  if (elems <= h->buf_elems) return AP_OK;
+  for (auto& b : h->buf) AP_CUDA(b.alloc(elems * sizeof(float)));
+  h->buf_elems = elems;
+  return AP_OK;
+}
+
+static int create_resnext(ap_classifier_t h, const float* const* w, int n_weights) {
+  const ap_classifier_cfg& c = h->cfg;
+  AP_REQUIRE(c.cardinality > 0 && c.base_width > 0 && c.widen_factor > 0 && c.depth >= 11 && c.in_channels == 1,
+             "ap_classifier_create: bad ResNeXt configuration (in_channels must be 1: NCHW == NHWC)");
+  const int block_depth = (c.depth - 2) / 9;
+  const int stages[4] = {64, 64 * c.widen_factor, 128 * c.widen_factor, 256 * c.widen_factor};
+  int expected = 5 + 2;
+  for (int s = 0; s < 3; ++s)
+    for (int b = 0; b < block_depth; ++b) expected += 15 + ((b == 0 && stages[s] != stages[s + 1]) ? 5 : 0);
+  AP_REQUIRE(n_weights == expected, "ap_classifier_create: ResNeXt expects %d weight tensors, got %d", expected, n_weights);
+  int i = 0;
+  int rc = h->stem.init(c.in_channels, 64, 3, 3, 1, 1, 1, w[0], nullptr, w[1], w[2], w[3], w[4]);
+  if (rc != AP_OK) return rc;
+  i = 5;
+  for (int s = 0; s < 3; ++s)
+    for (int b = 0; b < block_depth; ++b) {
+      auto blk = std::make_unique<Bottleneck>();
+      const int cin = b == 0 ? stages[s] : stages[s + 1], cout = stages[s + 1];
+      const int stride = (b == 0 && s > 0) ? 2 : 1;
+      const double width_ratio = cout / (c.widen_factor * 64.0);
+      const int D = c.cardinality * static_cast<int>(c.base_width * width_ratio);
+      blk->stride = stride, blk->D = D, blk->cout = cout;
+      rc = blk->reduce.init(cin, D, 1, 1, 1, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
+      if (rc == AP_OK)
+        rc = blk->conv.init(D, D, 3, 3, stride, 1, c.cardinality, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9]);
+      if (rc == AP_OK)
+        rc = blk->expand.init(D, cout, 1, 1, 1, 0, 1, w[i + 10], nullptr, w[i + 11], w[i + 12], w[i + 13], w[i + 14]);
+      i += 15;
+      if (rc == AP_OK && cin != cout) {
+        blk->has_shortcut = true;
+        rc = blk->shortcut.init(cin, cout, 1, 1, stride, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
+        i += 5;
+      }
+      if (rc != AP_OK) return rc;
+      h->blocks.push_back(std::move(blk));
+    }
+  h->feat = stages[3];
+  AP_CUDA(h->fc_w.upload(w[i], sizeof(float) * c.num_classes * h->feat));
+  AP_CUDA(h->fc_b.upload(w[i + 1], sizeof(float) * c.num_classes));
+  return AP_OK;
+}
+
+static int forward_resnext(ap_classifier_t h, const float* spec, float* logits, int B, cudaStream_t st) {
+  // spatial size fixed by avg_pool2d(x, 8, 1) + view(-1, C): 32x32 input -> 8x8 after two stride-2 stages
+  const int H0 = 32, W0 = 32;
+  int maxc = 64;
+  for (auto& b : h->blocks) maxc = std::max(maxc, std::max(b->D, b->cout));
+  const int chunk = 64;
+  int rc = ensure_ws(h, static_cast<size_t>(std::min(B, chunk)) * H0 * W0 * maxc);
+  if (rc != AP_OK) return rc;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    float* x = h->buf[0].as<float>();
+    float* xo = h->buf[1].as<float>();
+    float* y1 = h->buf[2].as<float>();
+    float* y2 = h->buf[3].as<float>();
+    float* sc = h->buf[4].as<float>();
+    int H = H0, W = W0;
+    rc = h->stem.run(spec + static_cast<size_t>(b0) * h->cfg.in_channels * H0 * W0, bn, H, W, x, nullptr, 1, st);
+    if (rc != AP_OK) return rc;
+    for (auto& blk : h->blocks) {
+      const int Ho = (H - 1) / blk->stride + 1, Wo = (W - 1) / blk->stride + 1;
+      rc = blk->reduce.run(x, bn, H, W, y1, nullptr, 1, st);
+      if (rc == AP_OK) rc = blk->conv.run(y1, bn, H, W, y2, nullptr, 1, st);
+      const float* res = x;
+      if (rc == AP_OK && blk->has_shortcut) {
+        rc = blk->shortcut.run(x, bn, H, W, sc, nullptr, 0, st);
+        res = sc;
+      }
+      if (rc == AP_OK) rc = blk->expand.run(y2, bn, Ho, Wo, xo, res, 1, st);
+      if (rc != AP_OK) return rc;
+      std::swap(x, xo);
+      H = Ho, W = Wo;
+    }
+    AP_REQUIRE(H == 8 && W == 8, "ResNeXt: unexpected final spatial size %dx%d", H, W);
+    const size_t smem = sizeof(float) * (h->feat + h->cfg.num_classes);
+    pool_fc_kernel<<<bn, 256, smem, st>>>(x, H * W, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(), h->cfg.num_classes,
+                                          logits + static_cast<size_t>(b0) * h->cfg.num_classes, 0);
+    AP_LAUNCH_CHECK();
+  }
+  return AP_OK;
+}
+
+// ---- M5: state_dict order conv{i}.weight, conv{i}.bias, bn{i}.{weight,bias,running_mean,running_var} (i=1..4), fc1.weight, fc1.bias
+static int create_m5(ap_classifier_t h, const float* const* w, int n_weights) {
+  const ap_classifier_cfg& c = h->cfg;
+  AP_REQUIRE(n_weights == 26, "ap_classifier_create: M5 expects 26 weight tensors, got %d", n_weights);
+  AP_REQUIRE(c.m5_first_kernel > 0 && c.m5_stride > 0 && c.m5_channels > 0 && c.m5_channels % 4 == 0,
+             "ap_classifier_create: bad M5 configuration");
+  const int n = c.m5_channels;
+  const int cin[4] = {1, n, n, 2 * n}, cout[4] = {n, n, 2 * n, 2 * n}, ks[4] = {c.m5_first_kernel, 3, 3, 3};
+  for (int i = 0; i < 4; ++i) {
+    const float* const* p = w + 6 * i;
+    int rc = h->m5conv[i].init(cin[i], cout[i], 1, ks[i], i == 0 ? c.m5_stride : 1, 0, 1, p[0], p[1], p[2], p[3], p[4], p[5]);
+    if (rc != AP_OK) return rc;
+  }
+  h->feat = 2 * n;
+  AP_CUDA(h->fc_w.upload(w[24], sizeof(float) * c.num_classes * h->feat));
+  AP_CUDA(h->fc_b.upload(w[25], sizeof(float) * c.num_classes));
+  return AP_OK;
+}
+
+static int forward_m5(ap_classifier_t h, const float* wav, float* out, int B, int L, cudaStream_t st) {
+  // treat the waveform as an image of height 1: NHWC [B][1][L][1]
+  const int n = h->cfg.m5_channels;
+  const int L1 = (L - h->cfg.m5_first_kernel) / h->cfg.m5_stride + 1;
+  AP_REQUIRE(L1 >= 4, "M5: input too short (L=%d)", L);
+  const int chunk = 256;
+  int rc = ensure_ws(h, static_cast<size_t>(std::min(B, chunk)) * L1 * 2 * n);
+  if (rc != AP_OK) return rc;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    float* a = h->buf[0].as<float>();   // conv + BN + ReLU output
+    float* p = h->buf[1].as<float>();   // pooled output == next conv input
+    const float* in = wav + static_cast<size_t>(b0) * L;
+    int len = L;
+    for (int i = 0; i < 4; ++i) {
+      const ConvLayer& cv = h->m5conv[i];
+      const int lo = (len - cv.kw) / cv.stride + 1;
+      AP_REQUIRE(lo >= 4, "M5: sequence too short at conv%d", i + 1);
+      rc = cv.run(in, bn, 1, len, a, nullptr, 1, st);      // conv + BN + ReLU (M5Net.py:23-25,...)
+      if (rc != AP_OK) return rc;
+      const long long total = static_cast<long long>(bn) * (lo / 4) * cv.Cout;
+      long long blocks = ceil_div_ll(total, 256);
+      if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+      maxpool4_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, p, bn, lo, cv.Cout);   // M5Net.py:26,...
+      AP_LAUNCH_CHECK();
+      in = p;
+      len = lo / 4;
+    }
+    const size_t smem = sizeof(float) * (h->feat + h->cfg.num_classes);
+    pool_fc_kernel<<<bn, 256, smem, st>>>(in, len, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(), h->cfg.num_classes,
+                                          out + static_cast<size_t>(b0) * h->cfg.num_classes, 1);   // M5Net.py:35-38
+    AP_LAUNCH_CHECK();
+  }
+  return AP_OK;
+}
+
+// ---- KWS: state_dict order (24 tensors): sepconv.0.{weight,bias}, sepconv.1.{weight,bias},
+//      gru.{weight_ih,weight_hh,bias_ih,bias_hh}_l0, ..._l0_reverse, ..._l1, ..._l1_reverse,
+//      attn_layer.Wx_b.{weight,bias}, attn_layer.Vt.weight, apply_attn.U.weight
+static int create_kws(ap_classifier_t h, const float* const* w, int n_weights) {
+  const ap_classifier_cfg& c = h->cfg;
+  AP_REQUIRE(n_weights == 24, "ap_classifier_create: KWS expects 24 weight tensors, got %d", n_weights);
+  AP_REQUIRE(c.kws_in_size == 32 && c.kws_hidden > 0 && c.kws_hidden <= 128, "ap_classifier_create: bad KWS configuration");
+  const int I = c.kws_in_size, H = c.kws_hidden;
+  size_t sizes[24];
+  sizes[0] = I * 5, sizes[1] = I, sizes[2] = static_cast<size_t>(H) * I, sizes[3] = H;
+  int k = 4;
+  for (int layer = 0; layer < 2; ++layer)
+    for (int dir = 0; dir < 2; ++dir) {
+      const int in_l = layer == 0 ? H : 2 * H;
+      sizes[k++] = static_cast<size_t>(3) * H * in_l, sizes[k++] = static_cast<size_t>(3) * H * H, sizes[k++] = 3 * H, sizes[k++] = 3 * H;
+    }
+  sizes[20] = static_cast<size_t>(4) * H * H, sizes[21] = 2 * H, sizes[22] = 2 * H, sizes[23] = static_cast<size_t>(c.num_classes) * 2 * H;
+  const float* d[24];
+  for (int i = 0; i < 24; ++i) {
+    auto buf = std::make_unique<DevBuf>();
+    AP_CUDA(buf->upload(w[i], sizes[i] * sizeof(float)));
+    d[i] = buf->as<float>();
+    h->kws_bufs.push_back(std::move(buf));
+  }
+  h->kws.dw_w = d[0], h->kws.dw_b = d[1], h->kws.pw_w = d[2], h->kws.pw_b = d[3];
+  k = 4;
+  for (int layer = 0; layer < 2; ++layer)
+    for (int dir = 0; dir < 2; ++dir)
+      for (int j = 0; j < 4; ++j) h->kws.gru[layer][dir][j] = d[k++];
+  h->kws.wx_w = d[20], h->kws.wx_b = d[21], h->kws.vt_w = d[22], h->kws.u_w = d[23];
+  return AP_OK;
+}
+
+static int forward_kws(ap_classifier_t h, const float* spec, float* out, int B, int Wf, cudaStream_t st) {
+  const int I = h->cfg.kws_in_size, H = h->cfg.kws_hidden;
+  AP_REQUIRE(Wf >= 5, "KWS: need at least 5 spectrogram frames (got %d)", Wf);
+  const int W1 = (Wf - 5) / 2 + 1, T = (W1 - 1) / 8 + 1;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(I) * W1 + T * H + 2 * T * 2 * H + 2 * H + 2 * 2 * 3 * H + T);
+  AP_REQUIRE(smem <= 200 * 1024, "KWS: spectrogram too long (%d frames)", Wf);
+  static bool attr = false;
+  if (!attr) {
+    AP_CUDA(cudaFuncSetAttribute(kws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  kws_kernel<<<B, 256, smem, st>>>(spec, Wf, I, H, h->cfg.num_classes, h->kws, out);
+  AP_LAUNCH_CHECK();
+  return AP_OK;
+}
+
+extern "C" int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cfg* cfg, const float* const* weights,
+                                    int n_weights, int device) {
+  AP_REQUIRE(out && cfg && weights, "ap_classifier_create: null argument");
+  *out = nullptr;
+  AP_REQUIRE(cfg->num_classes > 0 && cfg->num_classes <= 1024, "ap_classifier_create: bad num_classes %d", cfg->num_classes);
+  for (int i = 0; i < n_weights; ++i) AP_REQUIRE(weights[i], "ap_classifier_create: weight pointer %d is null", i);
+  int rc = select_device(device);
+  if (rc != AP_OK) return rc;
+  auto* h = new ap_classifier_s();
+  h->cfg = *cfg;
+  h->device = device;
+  switch (cfg->kind) {
+    case AP_CLS_RESNEXT: rc = create_resnext(h, weights, n_weights); break;
+    case AP_CLS_M5: rc = create_m5(h, weights, n_weights); break;
+    case AP_CLS_KWS: rc = create_kws(h, weights, n_weights); break;
+    default: rc = fail(AP_ERR_INVALID, "ap_classifier_create: unknown classifier kind %d", cfg->kind);
+  }
+  if (rc != AP_OK) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return AP_OK;
+}
+
+extern "C" void ap_classifier_destroy(ap_classifier_t h) { delete h; }
+
+extern "C" int ap_classifier_forward(ap_classifier_t h, const float* input, float* logits, int B, int in_len, void* stream) {
+  AP_REQUIRE(h && input && logits, "ap_classifier_forward: null argument");
+  AP_REQUIRE(B > 0, "ap_classifier_forward: B must be positive (got %d)", B);
+  AP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (h->cfg.kind) {
+    case AP_CLS_RESNEXT: return forward_resnext(h, input, logits, B, st);
+    case AP_CLS_M5: return forward_m5(h, input, logits, B, in_len, st);
+    default: return forward_kws(h, input, logits, B, in_len, st);
+  }
+}

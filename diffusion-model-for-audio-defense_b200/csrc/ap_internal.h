@@ -1,0 +1,41 @@
+// Internal (non-ABI) declarations shared between the translation units of libaudiopure_b200.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/audiopure.h"
+
+namespace ap {
+
+int num_sms();
+
+// ap_update.cu
+int diffuse(const float* x0, float a, float b, const float* z, uint64_t seed, uint64_t offset, float* xt, long long n,
+            cudaStream_t st);
+int ddpm_step(float* x, const float* eps, float c_eps, float sqrt_alpha, float sigma, const float* z, uint64_t seed,
+              uint64_t offset, long long n, cudaStream_t st);
+int sde_step(float* x, const float* eps, const ap_sde_coef& c, const float* z, uint64_t seed, uint64_t offset,
+             long long n, cudaStream_t st);
+int predict_x0(const float* xt, const float* eps, float a, float b, float* x0, long long n, cudaStream_t st);
+int vote(const float* logits, int B, int K, long long* counts, int* pred, cudaStream_t st);
+
+// ap_wavenet_tc.cu : the bf16 tensor-core (tcgen05 / TMEM / TMA) DiffWave network, C == S == 256 only.
+//   weights: the ap_diffwave_create list (host fp32, weight-norm folded).
+struct TcNet;
+int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* weights);
+void tc_net_destroy(TcNet* n);
+// (re)allocate the activation workspace for `chunk` waveforms of length L and encode the TMA tensor maps
+int tc_net_reserve(TcNet* n, int chunk, int L);
+size_t tc_net_workspace_bytes(const TcNet* n);
+// eps[b, l] for b < B <= chunk.  ptab: device fp32 [num_layers + 1][256] step-embedding projections (row n = fc_t of
+// layer n applied to the embedding; the extra last row is zero).  x, eps: device fp32 (B, L).
+int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st);
+// debug: run init + layers [0, layer]; returns u_{layer+1} and o_layer converted to fp32 (B, L, 256); either may be null
+int tc_net_debug_layer(TcNet* n, const float* x, const float* ptab, int layer, float* u_next, float* gate, int B, int L,
+                       cudaStream_t st);
+
+// per-launch CUDA-event timing of k1_layer ([0]) and k2_head ([1]); read synchronises on the recorded events
+void tc_net_profile(TcNet* n, bool on);
+int tc_net_profile_read(TcNet* n, double* ms, int* count);
+
+}  // namespace ap

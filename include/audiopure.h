@@ -1,0 +1,194 @@
+/* audiopure.h -- C ABI of libaudiopure_b200.so: the B200-native (sm_100a) AudioPure
+ * purification-and-classify hot path.
+ *
+ * The reference (cychomatica/Diffusion-Model-for-Audio-Defense) has no FFI layer: its "operator API" is a set of
+ * duck-typed torch.nn.Modules.  Each entry point below is what a binding for ONE of those reference functions
+ * would call; the reference interface it replaces is cited as file:line (paths relative to the reference root).
+ * The Python host mirror (package audiopure_b200) binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every `const float*` / `float*` below marked "device" is caller-owned GPU memory
+ *    (fp32, contiguous); "host" pointers are CPU memory read during the call only.
+ *  - waveforms are (B, 1, L) fp32 contiguous == (B, L); spectrograms (B, 1, n_mels, frames); logits (B, K).
+ *  - all device work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation inside
+ *    except in *_create / *_reserve.  Handles are not thread-safe: one per (device, stream).
+ *  - return value: 0 = ok, negative = error (AP_ERR_*); ap_last_error() gives the message (thread-local).
+ *  - there is NO CPU fallback: on a machine without an sm_100 GPU every compute entry point returns AP_ERR_CUDA.
+ */
+#ifndef AUDIOPURE_H_
+#define AUDIOPURE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AP_OK 0
+#define AP_ERR_INVALID (-1) /* bad argument / unsupported configuration */
+#define AP_ERR_CUDA (-2)    /* CUDA runtime / driver error, or no usable GPU */
+#define AP_ERR_STATE (-3)   /* handle not in a state that allows the call */
+
+/* arithmetic mode of the DiffWave network */
+#define AP_MODE_BF16 0 /* tcgen05 tensor cores: bf16 operands, fp32 accumulate (TMEM), fp32 x/update arithmetic */
+#define AP_MODE_FP32 1 /* fp32 FFMA path (parity mode, <=1e-5 rel-L2 vs the reference) */
+
+typedef struct ap_diffwave_s* ap_diffwave_t;
+typedef struct ap_mel_s* ap_mel_t;
+typedef struct ap_classifier_s* ap_classifier_t;
+
+const char* ap_last_error(void);
+int ap_version(void);
+/* number of kernels this library has launched since load (process-wide, all handles); bench.py's gpu_launches */
+unsigned long long ap_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Host helpers (no GPU needed)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* w[o,:] = g[o] * v[o,:] / ||v[o,:]||_2 -- torch.nn.utils.weight_norm fold of WaveNet.py:27-28,66-73 (host, fp32 in/out,
+ * fp64 accumulate). */
+int ap_fold_weight_norm(const float* g, const float* v, float* w, int cout, int fan_in);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * DiffWave network (replaces WaveNet_Speech_Commands.forward, DiffWave_Unconditional/WaveNet.py:138-172)
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int in_channels;   /* 1 */
+  int res_channels;  /* 256 */
+  int skip_channels; /* 256 (must equal res_channels) */
+  int out_channels;  /* 1 */
+  int num_res_layers;
+  int dilation_cycle;
+  int embed_dim_in, embed_dim_mid, embed_dim_out; /* 128, 512, 512 */
+} ap_wavenet_cfg; /* == configs/config.json "wavenet_config" */
+
+/* weights: host fp32 pointers, weight-norm already folded, in this order (n = layer index):
+ *   [0] init_w (C)            [1] init_b (C)
+ *   [2] fc_t1_w (mid x in)    [3] fc_t1_b (mid)     [4] fc_t2_w (out x mid)   [5] fc_t2_b (out)
+ *   [6+8n+0] fc_t_w (C x out) [6+8n+1] fc_t_b (C)
+ *   [6+8n+2] dil_w (2C x C x 3, torch Conv1d layout)  [6+8n+3] dil_b (2C)
+ *   [6+8n+4] res_w (C x C)    [6+8n+5] res_b (C)    [6+8n+6] skip_w (S x C)   [6+8n+7] skip_b (S)
+ *   [6+8N+0] final1_w (S x S) [6+8N+1] final1_b (S) [6+8N+2] final2_w (S)     [6+8N+3] final2_b (1)
+ * n_weights must be 6 + 8*num_res_layers + 4.   Replaces create_diffwave_model (diffwave_ddpm.py:395-411). */
+int ap_diffwave_create(ap_diffwave_t* out, const ap_wavenet_cfg* cfg, const float* const* weights, int n_weights,
+                       int device);
+void ap_diffwave_destroy(ap_diffwave_t h);
+/* AP_MODE_BF16 (default when the configuration supports the tensor-core kernels: C == S == 256) or AP_MODE_FP32 */
+int ap_diffwave_set_mode(ap_diffwave_t h, int mode);
+int ap_diffwave_get_mode(ap_diffwave_t h);
+/* Pre-allocate the activation workspace for up to `chunk` waveforms of length L processed at once (larger batches are
+ * processed in chunks).  Called implicitly (with a default chunk) by the first compute call if omitted. */
+int ap_diffwave_reserve(ap_diffwave_t h, int chunk, int L);
+
+/* eps = eps_theta(x, t): WaveNet forward with diffusion_steps == t for every row
+ * (DiffWave.compute_eps_t, diffwave_ddpm.py:166-172).  x, eps: device (B, L). */
+int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* eps, int B, int L, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Per-step updates (HBM-bound elementwise kernels; in-kernel Philox4x32-10 + Box-Muller when z == NULL)
+ * Noise element i of a call uses Philox counter (offset + i/4), key = seed; callers advance `offset` by
+ * ceil(B*L/4) per call (ap_noise_offset_stride) so streams never overlap.
+ * ------------------------------------------------------------------------------------------------------------- */
+uint64_t ap_noise_offset_stride(int B, int L);
+/* x_t = sqrt_ab * x0 + sqrt_1mab * z                               DiffWave._diffusion, diffwave_ddpm.py:49-73 */
+int ap_diffuse(const float* x0, float sqrt_ab, float sqrt_1mab, const float* z_or_null, uint64_t seed, uint64_t offset,
+               float* xt, int B, int L, void* stream);
+/* x = (x - c_eps * eps) / sqrt_alpha + sigma * z   (sigma == 0: no noise read/drawn)
+ *                                                                   compute_coefficients/_reverse, :95-103,:159-160 */
+int ap_ddpm_step(float* x, const float* eps, float c_eps, float sqrt_alpha, float sigma, const float* z_or_null,
+                 uint64_t seed, uint64_t offset, int B, int L, void* stream);
+/* one Euler-Maruyama step of the reverse VP-SDE                      RevVPSDE.f/.g, diffwave_sde.py:73-133 (+ torchsde euler)
+ *   drift = (-0.5*beta)*x ; score = -eps/sqrt_1mab ; f = -(drift - diff2*score) ; x = (x + f*dt) + g*(sqrt_dt*z)
+ * The host builds one row per Euler step with the reference's own float32 arithmetic (diff2 = sqrt(beta)^2 in fp32). */
+typedef struct {
+  float beta, diff2, sqrt_1mab, dt, g, sqrt_dt;
+} ap_sde_coef;
+int ap_sde_step(float* x, const float* eps, const ap_sde_coef* c, const float* z_or_null, uint64_t seed,
+                uint64_t offset, int B, int L, void* stream);
+/* x0 = sqrt_recip_ab * xt - sqrt_recipm1_ab * eps                    _predict_x0_from_eps, diffwave_ddpm.py:195-205 */
+int ap_predict_x0(const float* xt, const float* eps, float sqrt_recip_ab, float sqrt_recipm1_ab, float* x0, int B,
+                  int L, void* stream);
+/* out[b,:] = scale * (x[0,:] + sigma * z[b,:]) : the noisy, rescaled copies of ONE input that
+ * RobustCertificate.smooth_predict builds (certified_robust.py:44-54).  x: device (L), out: device (B, L). */
+int ap_smooth_inputs(const float* x, float sigma, float scale, const float* z_or_null, uint64_t seed, uint64_t offset,
+                     float* out, int B, int L, void* stream);
+/* standard-normal fill (diagnostics / statistical tests of the in-kernel RNG) */
+int ap_randn(float* out, uint64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* Whole DDPM purifier in one call: diffuse to t* then t* ancestral steps (DiffWave.forward, diffwave_ddpm.py:36-47).
+ * coef: host array of n_steps+1 rows {a, b, c, 0}: row 0 = {sqrt_ab, sqrt_1mab} for the diffusion; row 1+i (i-th reverse step,
+ * t = t*-1-i) = {c_eps, sqrt_alpha, sigma, t}.  z_or_null: device (n_steps+1... see below) host-generated noise laid out
+ * as (n_noise, B, L) with n_noise = t* (z_diffuse, z_{t*-1}, ..., z_1), or NULL for in-kernel Philox. */
+int ap_diffwave_purify_ddpm(ap_diffwave_t h, const float* x0, float* out, int t_star, const float* coef4,
+                            const float* z_or_null, uint64_t seed, uint64_t offset, int B, int L, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Log-mel front end (replaces torchaudio MelSpectrogram + AmplitudeToDB built at certified_robustness_eval.py:85-87,
+ * kws_adaptive_attack_eval.py:74-76): DFT-as-GEMM -> power -> mel filterbank -> 10*log10(clamp(., 1e-10)).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int sample_rate, n_fft, hop_length, n_mels;
+  int slaney_norm; /* 1: norm='slaney', 0: None */
+  int slaney_scale; /* 1: mel_scale='slaney', 0: 'htk' */
+  int reflect_pad;  /* 1: pad_mode='reflect', 0: 'constant' (zeros) */
+} ap_mel_cfg;
+int ap_mel_create(ap_mel_t* out, const ap_mel_cfg* cfg, int device);
+void ap_mel_destroy(ap_mel_t h);
+int ap_mel_frames(ap_mel_t h, int L); /* 1 + L / hop */
+/* wav: device (B, L); spec: device (B, n_mels, frames) */
+int ap_mel_db(ap_mel_t h, const float* wav, float* spec, int B, int L, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Classifiers (replace Classifier(spec) at acoustic_system.py:49 / certified_robust.py:30)
+ * ------------------------------------------------------------------------------------------------------------- */
+#define AP_CLS_RESNEXT 0 /* CifarResNeXt, models/resnext.py:67-142 : (B,1,32,32) -> (B,nlabels) logits   */
+#define AP_CLS_M5 1      /* M5, audio_models/M5/M5Net.py:4-38       : (B,1,L)     -> (B,n) log-probs      */
+#define AP_CLS_KWS 2     /* KWSModel, audio_models/RCNN_KWS/model.py:66-113 : (B,1,32,W) -> (B,4) log-probs */
+typedef struct {
+  int kind;
+  int num_classes;
+  /* ResNeXt */
+  int cardinality, depth, base_width, widen_factor, in_channels;
+  /* M5 */
+  int m5_first_kernel, m5_stride, m5_channels;
+  /* KWS */
+  int kws_in_size, kws_hidden;
+} ap_classifier_cfg;
+/* weights: host fp32 pointers in the reference module's state_dict order (num_batches_tracked entries skipped);
+ * BatchNorm (eval) is folded into the preceding convolution at create. */
+int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cfg* cfg, const float* const* weights,
+                         int n_weights, int device);
+void ap_classifier_destroy(ap_classifier_t h);
+/* input: device (B, 1, 32, 32) spectrogram (ResNeXt), (B, L) waveform (M5; in_len = L) or (B, 32, W) (KWS; in_len = W) */
+int ap_classifier_forward(ap_classifier_t h, const float* input, float* logits, int B, int in_len, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Votes (replaces the argmax + per-class .sum().item() loop of smooth_predict, certified_robust.py:59-67)
+ * counts: device int64[K], ACCUMULATED (caller zeroes it); ties resolve to the lowest class index like torch.max.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ap_vote_counts(const float* logits, int B, int K, long long* counts, void* stream);
+int ap_argmax(const float* logits, int B, int K, int* pred, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Self tests of the tcgen05/TMA building blocks (used by tests/ and smoke): run a single-tile UMMA GEMM
+ * D[128x256] = A[128xK] * B[256xK]^T (bf16 in, fp32 out) through TMA + TMEM and write D to `d_out` (device, 128*256).
+ * a_bf16 / b_bf16: device, K-major, raw bf16 bits.  K must be a multiple of 64.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ap_selftest_umma(const uint16_t* a_bf16, const uint16_t* b_bf16, float* d_out, int K, void* stream);
+/* Test hook: run the network up to and including residual layer `layer` (current mode) and return, as fp32 (B, L, C)
+ * channels-last device arrays, the next layer's input u = h + fc_t(emb) (Residual_block input after WaveNet.py:84) and
+ * the gate output tanh*sigmoid (WaveNet.py:90).  Either output may be NULL.  B must fit one workspace chunk. */
+int ap_diffwave_debug_layer(ap_diffwave_t h, const float* x, float t, int layer, float* u_next, float* gate, int B,
+                            int L, void* stream);
+
+/* Measurement hook (bench.py roofline): when enabled, every launch of the two tensor-core kernels is bracketed by CUDA
+ * events recorded on the launching stream.  ap_diffwave_profile_read synchronises on them and returns the summed
+ * device time in ms and the launch count of k1_layer (index 0) and k2_head (index 1) since the last enable. */
+int ap_diffwave_profile(ap_diffwave_t h, int enable);
+int ap_diffwave_profile_read(ap_diffwave_t h, double* ms2, int* count2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOPURE_H_ */

@@ -1,0 +1,321 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through the C ABI, against
+  * the committed outputs of the unmodified reference (tests/golden/reference_golden.npz), and
+  * the CPU oracle (oracle/audiopure_oracle.py) on the same seeded inputs.
+Tolerances (BASELINE.json north_star): purified waveform rel-L2 <= 1e-5 in fp32 mode, <= 1e-2 in bf16 mode; top-1 exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gpu_common import CONFIG_JSON, TorchNormalInjector, cuda, rel_l2, synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 1e-2}
+TOL_EPS = {"fp32": 2e-5, "bf16": 1e-2}
+
+
+@pytest.fixture(scope="module")
+def ap():
+    import audiopure_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import audiopure_oracle
+    return audiopure_oracle
+
+
+@pytest.fixture(scope="module")
+def sd_full():
+    return synthetic.wavenet_state_dict(seed=0)
+
+
+@pytest.fixture(scope="module")
+def diffwave(ap, sd_full):
+    return ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=2, state_dict=sd_full, noise="torch")
+
+
+# ---------------------------------------------------------------------------------------------------- building blocks
+@pytest.mark.parametrize("K", [64, 256, 768])
+def test_umma_selftest(ap, K):
+    """one 128x256xK tile through TMA (SWIZZLE_128B) -> tcgen05.mma -> TMEM -> tcgen05.ld"""
+    from audiopure_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(K)
+    a = torch.randn(128, K, generator=g).to(torch.bfloat16).cuda()
+    b = torch.randn(256, K, generator=g).to(torch.bfloat16).cuda()
+    d = torch.zeros(128, 256, device="cuda")
+    _lib.check(lib.ap_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), K, _lib.stream_ptr()), "selftest")
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t()
+    assert rel_l2(d, ref) < 1e-5
+
+
+def test_update_kernels_match_reference_arithmetic(ap):
+    from audiopure_b200 import _lib
+    lib = _lib.load()
+    for B, L in [(3, 1000), (2, 1023), (1, 5)]:       # vectorised, ragged, tiny
+        g = torch.Generator().manual_seed(B * L)
+        x = torch.randn(B, L, generator=g).cuda()
+        e = torch.randn(B, L, generator=g).cuda()
+        z = torch.randn(B, L, generator=g).cuda()
+        st = _lib.stream_ptr()
+        a, b = float(np.float32(0.9997)), float(np.float32(0.0245))
+        out = torch.empty_like(x)
+        _lib.check(lib.ap_diffuse(x.data_ptr(), a, b, z.data_ptr(), 0, 0, out.data_ptr(), B, L, st))
+        assert torch.equal(out, torch.tensor(a) * x + torch.tensor(b) * z)
+        c, sa, sg = float(np.float32(0.0115)), float(np.float32(0.9999)), float(np.float32(0.0082))
+        y = x.clone()
+        _lib.check(lib.ap_ddpm_step(y.data_ptr(), e.data_ptr(), c, sa, sg, z.data_ptr(), 0, 0, B, L, st))
+        assert torch.equal(y, (x - torch.tensor(c) * e) / torch.tensor(sa) + torch.tensor(sg) * z)
+        y = x.clone()
+        _lib.check(lib.ap_ddpm_step(y.data_ptr(), e.data_ptr(), c, sa, 0.0, None, 0, 0, B, L, st))
+        assert torch.equal(y, (x - torch.tensor(c) * e) / torch.tensor(sa))
+        _lib.check(lib.ap_predict_x0(x.data_ptr(), e.data_ptr(), float(np.float32(1.118)), 0.5, out.data_ptr(), B, L, st))
+        assert torch.equal(out, torch.tensor(np.float32(1.118)) * x - torch.tensor(np.float32(0.5)) * e)
+        x1 = torch.randn(L, generator=g).cuda()
+        so = torch.empty(B, L, device="cuda")
+        _lib.check(lib.ap_smooth_inputs(x1.data_ptr(), 1.0, float(np.float32(0.8944)), z.data_ptr(), 0, 0, so.data_ptr(), B, L, st))
+        assert torch.equal(so, torch.tensor(np.float32(0.8944)) * (x1[None] + z))
+
+
+def test_philox_noise_statistics_and_determinism(ap):
+    from audiopure_b200 import _lib
+    lib = _lib.load()
+    n = 1 << 22
+    a = torch.empty(n, device="cuda")
+    b = torch.empty(n, device="cuda")
+    st = _lib.stream_ptr()
+    _lib.check(lib.ap_randn(a.data_ptr(), n, 1234, 0, st))
+    _lib.check(lib.ap_randn(b.data_ptr(), n, 1234, 0, st))
+    assert torch.equal(a, b)                                    # counter-based: reproducible
+    _lib.check(lib.ap_randn(b.data_ptr(), n // 2, 1234, n // 8, st))
+    assert torch.equal(b[: n // 2], a[n // 2:])                 # offset o == element 4*o of the same stream
+    _lib.check(lib.ap_randn(b.data_ptr(), n, 1235, 0, st))
+    assert not torch.equal(a, b)
+    assert abs(a.mean().item()) < 3e-3 and abs(a.var().item() - 1) < 5e-3
+    assert abs((a ** 4).mean().item() - 3) < 0.05 and a.abs().max().item() < 6.5
+    assert abs(torch.corrcoef(torch.stack([a[:-1], a[1:]]))[0, 1].item()) < 3e-3
+
+
+def test_vote_counts(ap):
+    from audiopure_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(1001, 10, generator=g)
+    logits[5] = 0.0                       # all-tie row -> class 0 like torch.max
+    logits[7, 3] = logits[7, 8] = 9.0     # tie -> lowest index
+    counts = torch.zeros(10, dtype=torch.int64, device="cuda")
+    lc = logits.cuda()
+    _lib.check(lib.ap_vote_counts(lc.data_ptr(), 1001, 10, counts.data_ptr(), _lib.stream_ptr()))
+    _lib.check(lib.ap_vote_counts(lc.data_ptr(), 1001, 10, counts.data_ptr(), _lib.stream_ptr()))   # accumulates
+    ref = torch.bincount(logits.max(1)[1], minlength=10)
+    assert torch.equal(counts.cpu(), 2 * ref) and int(counts.sum()) == 2002
+
+
+# ---------------------------------------------------------------------------------------------------- WaveNet
+def _eps(ap, sd, cfg, x, t, mode):
+    net = ap.WaveNet(sd, mode=mode, **cfg)
+    B = x.shape[0]
+    return net((cuda(x), t * torch.ones(B, 1))).cpu().numpy()
+
+
+@pytest.mark.parametrize("key,L,B,t,seed", [("eps_full_L1024_t1", 1024, 2, 1.0, 1234), ("eps_full_L1024_t65", 1024, 2, 65.0, 1234),
+                                            ("eps_full_L3001_t7", 3001, 1, 7.0, 77)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_wavenet_eps_vs_reference_golden(ap, golden, sd_full, key, L, B, t, seed, mode):
+    x = synthetic.synthetic_waveforms(B, L, seed=seed)
+    eps = _eps(ap, sd_full, synthetic.DEFAULT_WAVENET_CONFIG, x, t, mode)
+    err = rel_l2(eps, golden[key])
+    print(f"{key} {mode}: rel-L2 {err:.3e}")
+    assert err < TOL_EPS[mode]
+
+
+def test_wavenet_small_config_fp32(ap, golden):
+    cfg = dict(synthetic.DEFAULT_WAVENET_CONFIG, res_channels=64, skip_channels=64, num_res_layers=5, dilation_cycle=3)
+    sd = synthetic.wavenet_state_dict(seed=3, config=cfg)
+    net = ap.WaveNet(sd, **cfg)
+    assert net.mode == "fp32"                       # tensor-core kernels need 256 channels
+    with pytest.raises(ap.AudioPureError):
+        net.set_mode("bf16")
+    x = synthetic.synthetic_waveforms(3, 500, seed=5)
+    eps = net((cuda(x), 3.0 * torch.ones(3, 1))).cpu().numpy()
+    assert rel_l2(eps, golden["eps_small_L500_t3"]) < 2e-5
+
+
+def test_wavenet_layers_bf16_vs_fp32_and_oracle(ap, orc, sd_full):
+    """Per-layer localisation: u_{n+1} and the gate output of selected layers, tensor-core path vs fp32 path vs oracle."""
+    B, L, t = 2, 1024, 7.0
+    x = synthetic.synthetic_waveforms(B, L, seed=11)
+    _, internals = orc.wavenet_forward(sd_full, x, t * torch.ones(B, 1), return_internals=True)
+    nets = {m: ap.WaveNet(sd_full, mode=m, **synthetic.DEFAULT_WAVENET_CONFIG) for m in ("fp32", "bf16")}
+    xc = cuda(x)
+    report = []
+    for layer in (0, 1, 5, 11, 12, 23, 35):
+        u32, g32 = nets["fp32"].debug_layer(xc, t, layer)
+        u16, g16 = nets["bf16"].debug_layer(xc, t, layer)
+        report.append((layer, rel_l2(g16, g32), rel_l2(u16, u32)))
+        if f"o{layer}" in internals:     # oracle keeps layers 0, 1, 35: (B, C, L) -> (B, L, C)
+            o = internals[f"o{layer}"].permute(0, 2, 1).numpy()
+            assert rel_l2(g32, o) < 2e-5, f"fp32 gate of layer {layer}"
+        if layer == 0:
+            u1 = internals["u1"].permute(0, 2, 1).numpy()
+            assert rel_l2(u32, u1) < 2e-5
+    print("layer, gate rel-L2 (bf16 vs fp32), u_next rel-L2:", report)
+    for layer, eg, eu in report:
+        assert eg < 2e-2, report
+        if layer != 35:                  # the last block's residual output is unused (WaveNet.py:131-135)
+            assert eu < 2e-2, report
+
+
+def test_wavenet_batch_chunking_and_mixed_steps(ap, sd_full):
+    net = ap.WaveNet(sd_full, mode="bf16", **synthetic.DEFAULT_WAVENET_CONFIG)
+    x = cuda(synthetic.synthetic_waveforms(5, 640, seed=3))
+    net.reserve(2, 640)                              # 5 waveforms through a 2-waveform workspace: 3 chunks
+    a = net.eps(x, 4.0)
+    net.reserve(5, 640)
+    b = net.eps(x, 4.0)
+    assert torch.equal(a, b)
+    steps = torch.tensor([[4.0], [9.0], [4.0], [9.0], [4.0]])
+    c = net((x, steps))
+    assert torch.equal(c[0::2], a[0::2]) and not torch.equal(c[1], a[1])
+
+
+def test_inference_only_and_cpu_inputs_raise(ap, diffwave):
+    x = torch.zeros(1, 1, 256, device="cuda", requires_grad=True)
+    with pytest.raises(ap.AudioPureError):
+        diffwave.model.eps(x, 1.0)
+    with pytest.raises(ap.AudioPureError):
+        diffwave.model.eps(torch.zeros(1, 1, 256), 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------- purifier
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_ddpm_purifier_vs_reference_golden(diffwave, golden, mode):
+    diffwave.model.set_mode(mode)
+    x = cuda(synthetic.synthetic_waveforms(2, 1024, seed=1234))
+    for t_star, seed, key in [(2, 2024, "ddpm_t2_L1024"), (3, 2025, "ddpm_t3_L1024")]:
+        diffwave.reverse_timestep = t_star
+        with TorchNormalInjector(seed) as inj:
+            y = diffwave(x)
+            assert inj.i == t_star
+        err = rel_l2(y, golden[key])
+        print(f"{key} {mode}: rel-L2 {err:.3e}")
+        assert err < TOL[mode]
+    diffwave.reverse_timestep = 66
+    assert rel_l2(diffwave.one_shot_denoise(x), golden["oneshot_t66_L1024"]) < TOL[mode]
+    assert rel_l2(diffwave.two_shot_denoise(x), golden["twoshot_t66_L1024"]) < TOL[mode]
+    diffwave.reverse_timestep = 9
+    with TorchNormalInjector(2026):
+        assert rel_l2(diffwave.fast_reverse(x), golden["fastrev_t9_L1024"]) < TOL[mode]
+
+
+def test_purify_entry_point_philox(ap, sd_full):
+    """ap_diffwave_purify_ddpm (whole purifier in one call) == the step-by-step API on the same Philox stream."""
+    dw = ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=3, state_dict=sd_full, noise="philox", seed=7)
+    x = cuda(synthetic.synthetic_waveforms(2, 768, seed=5))
+    a = dw.purify(x)
+    dw._offset = 0
+    b = dw(x)
+    assert torch.equal(a, b)
+    assert torch.isfinite(a).all() and rel_l2(a, x) < 0.5
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("t_star", [1, 3])
+def test_sde_purifier_vs_oracle(ap, orc, sd_full, mode, t_star):
+    import argparse
+    args = argparse.Namespace(ddpm_path=None, ddpm_config=CONFIG_JSON, t=t_star, score_type="guided_diffusion", rand_t=False,
+                              t_delta=0, use_bm=False, sample_step=1)
+    rdw = ap.RevDiffWave(args, state_dict=sd_full, noise="torch", mode=mode)
+    x = synthetic.synthetic_waveforms(2, 1024, seed=21)
+    n_steps = len(orc.sde_euler_schedule(t_star))
+    zs = [synthetic.host_noise(x.shape, 3000 + t_star, i) for i in range(1 + n_steps)]
+    want = orc.sde_purify(sd_full, x, t_star, orc.NoiseSource(zs)).numpy()
+    it = iter(zs)
+    orig_like, orig_randn = torch.randn_like, torch.randn
+    torch.randn_like = lambda t, **kw: cuda(next(it))
+    torch.randn = lambda *a, **kw: cuda(next(it))
+    try:
+        got = rdw(cuda(x))
+    finally:
+        torch.randn_like, torch.randn = orig_like, orig_randn
+    err = rel_l2(got, want)
+    print(f"sde t*={t_star} {mode}: rel-L2 {err:.3e}")
+    assert err < (2e-5 if mode == "fp32" else 1e-2)
+
+
+# ---------------------------------------------------------------------------------------------------- mel + classifiers
+def test_mel_vs_torchaudio_golden(ap, golden):
+    xm = cuda(synthetic.synthetic_waveforms(2, 16000, seed=99))
+    sc = ap.sc09_transform()(xm).cpu().numpy()
+    assert sc.shape == golden["mel_sc09"].shape == (2, 1, 32, 32)
+    assert np.abs(sc - golden["mel_sc09"]).max() < 2e-3
+    kw = ap.kws_transform()(xm).cpu().numpy()
+    assert kw.shape == golden["mel_kws"].shape == (2, 1, 32, 81)
+    assert np.abs(kw - golden["mel_kws"]).max() < 2e-3
+
+
+def test_classifiers_vs_reference_golden(ap, golden):
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    logits = rx(cuda(golden["mel_sc09"])).cpu().numpy()
+    assert np.abs(logits - golden["resnext_logits"]).max() < 2e-3 * np.abs(golden["resnext_logits"]).max()
+    assert (logits.argmax(1) == golden["resnext_logits"].argmax(1)).all()
+    xm = cuda(synthetic.synthetic_waveforms(2, 16000, seed=99))
+    m5 = ap.M5Classifier(synthetic.m5_state_dict(seed=0))
+    np.testing.assert_allclose(m5(xm).cpu().numpy(), golden["m5_logprobs"], atol=2e-4, rtol=0)
+    kws = ap.KWSClassifier(synthetic.kws_state_dict(seed=0))
+    np.testing.assert_allclose(kws(cuda(golden["mel_kws"])).cpu().numpy(), golden["kws_logprobs"], atol=2e-4, rtol=0)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_acoustic_system_vs_reference_golden(ap, golden, diffwave, mode):
+    diffwave.model.set_mode(mode)
+    diffwave.reverse_timestep = 2
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    system = ap.AcousticSystem(classifier=rx, transform=ap.sc09_transform(), defender=diffwave, defense_type="wave")
+    x1 = cuda(synthetic.synthetic_waveforms(1, 16000, seed=1234))
+    with TorchNormalInjector(2027):
+        purified = diffwave(x1)
+    assert rel_l2(purified, golden["system_purified"]) < TOL[mode]
+    with TorchNormalInjector(2027):
+        logits = system(x1).cpu().numpy()
+    assert logits.argmax(1)[0] == golden["system_logits"].argmax(1)[0]                       # top-1 exact
+    assert np.abs(logits - golden["system_logits"]).max() < (5e-3 if mode == "fp32" else 5e-2) * np.abs(golden["system_logits"]).max()
+    raw = system(x1 * 2 ** 15, defend=False).cpu().numpy()                                   # int16-range branch
+    assert np.abs(raw - golden["system_logits_int16_nodefense"]).max() < 5e-3 * np.abs(raw).max()
+
+
+# ---------------------------------------------------------------------------------------------------- certification
+def test_smooth_predict_counts_vs_reference_golden(ap, golden, diffwave):
+    diffwave.model.set_mode("fp32")
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    rc = ap.RobustCertificate(classifier=rx, transform=ap.sc09_transform(), denoiser=diffwave, num_classes=10, noise="torch")
+    x1 = cuda(synthetic.synthetic_waveforms(1, 16000, seed=1234))
+    with TorchNormalInjector(2028) as inj:
+        counts = rc.smooth_predict(x1, num_sampling=12, sigma=0.5, batch_size=5)     # ragged last batch
+        assert inj.i == 3
+    assert counts.dtype == torch.int64 and int(counts.sum()) == 12
+    assert np.array_equal(counts.numpy(), golden["smooth_counts_n12"])
+    assert [rc.compute_t_star(1 / (1 + s ** 2)) for s in (0.25, 0.5, 1.0)] == list(golden["smooth_t_star"])
+
+
+def test_certify_philox_end_to_end(ap, diffwave):
+    diffwave.model.set_mode("bf16")
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    rc = ap.RobustCertificate(classifier=rx, transform=ap.sc09_transform(), denoiser=diffwave, num_classes=10, seed=5)
+    x = cuda(synthetic.synthetic_waveforms(2, 16000, seed=8))
+    y = torch.tensor([1, 2])
+    y_pred, radius = rc.certify(x, y, sigma=0.5, n_0=16, n=96, batch_size=32)
+    assert y_pred.shape == (2,) and radius.shape == (2,) and radius.dtype == torch.float32
+    rc2 = ap.RobustCertificate(classifier=rx, transform=ap.sc09_transform(), denoiser=diffwave, num_classes=10, seed=5)
+    y_pred2, radius2 = rc2.certify(x, y, sigma=0.5, n_0=16, n=96, batch_size=48)     # other batching, same Philox stream
+    assert torch.equal(y_pred, y_pred2) and torch.equal(radius, radius2)
+    for i in range(2):
+        assert (y_pred[i] == -1 and radius[i] == 0) or (0 <= y_pred[i] < 10 and radius[i] > 0)
+    # Clopper-Pearson KATs
+    assert abs(rc.lower_conf_bound(99000, 100000) - 0.988989) < 1e-5
+    assert abs(rc.lower_conf_bound(100000, 100000) - 0.999931) < 1e-5
+    assert rc.lower_conf_bound(50200, 100000) < 0.5 + 1e-3

@@ -6,7 +6,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import audiopure_b200 as ap  # noqa: E402
 from audiopure_b200 import _lib, synthetic  # noqa: E402

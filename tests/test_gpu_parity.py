@@ -62,23 +62,26 @@ def test_update_kernels_match_reference_arithmetic(ap):
         e = torch.randn(B, L, generator=g).cuda()
         z = torch.randn(B, L, generator=g).cuda()
         st = _lib.stream_ptr()
+        # expected values on the CPU: torch's CUDA true-division by a CPU scalar multiplies by the reciprocal (1 ulp off
+        # IEEE division); the kernels follow the IEEE arithmetic the CPU reference (and the golden vectors) use.
+        xc, ec, zc = x.cpu(), e.cpu(), z.cpu()
         a, b = float(np.float32(0.9997)), float(np.float32(0.0245))
         out = torch.empty_like(x)
         _lib.check(lib.ap_diffuse(x.data_ptr(), a, b, z.data_ptr(), 0, 0, out.data_ptr(), B, L, st))
-        assert torch.equal(out, torch.tensor(a) * x + torch.tensor(b) * z)
+        assert torch.equal(out.cpu(), torch.tensor(a) * xc + torch.tensor(b) * zc)
         c, sa, sg = float(np.float32(0.0115)), float(np.float32(0.9999)), float(np.float32(0.0082))
         y = x.clone()
         _lib.check(lib.ap_ddpm_step(y.data_ptr(), e.data_ptr(), c, sa, sg, z.data_ptr(), 0, 0, B, L, st))
-        assert torch.equal(y, (x - torch.tensor(c) * e) / torch.tensor(sa) + torch.tensor(sg) * z)
+        assert torch.equal(y.cpu(), (xc - torch.tensor(c) * ec) / torch.tensor(sa) + torch.tensor(sg) * zc)
         y = x.clone()
         _lib.check(lib.ap_ddpm_step(y.data_ptr(), e.data_ptr(), c, sa, 0.0, None, 0, 0, B, L, st))
-        assert torch.equal(y, (x - torch.tensor(c) * e) / torch.tensor(sa))
+        assert torch.equal(y.cpu(), (xc - torch.tensor(c) * ec) / torch.tensor(sa))
         _lib.check(lib.ap_predict_x0(x.data_ptr(), e.data_ptr(), float(np.float32(1.118)), 0.5, out.data_ptr(), B, L, st))
-        assert torch.equal(out, torch.tensor(np.float32(1.118)) * x - torch.tensor(np.float32(0.5)) * e)
+        assert torch.equal(out.cpu(), torch.tensor(np.float32(1.118)) * xc - torch.tensor(np.float32(0.5)) * ec)
         x1 = torch.randn(L, generator=g).cuda()
         so = torch.empty(B, L, device="cuda")
         _lib.check(lib.ap_smooth_inputs(x1.data_ptr(), 1.0, float(np.float32(0.8944)), z.data_ptr(), 0, 0, so.data_ptr(), B, L, st))
-        assert torch.equal(so, torch.tensor(np.float32(0.8944)) * (x1[None] + z))
+        assert torch.equal(so.cpu(), torch.tensor(np.float32(0.8944)) * (x1.cpu()[None] + zc))
 
 
 def test_philox_noise_statistics_and_determinism(ap):

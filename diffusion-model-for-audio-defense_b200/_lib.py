@@ -11,7 +11,7 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libaudiopure_b200.so")
 
-AP_MODE_BF16, AP_MODE_FP32 = 0, 1
+AP_MODE_BF16, AP_MODE_FP32, AP_MODE_TF32 = 0, 1, 2
 AP_CLS_RESNEXT, AP_CLS_M5, AP_CLS_KWS = 0, 1, 2
 
 
@@ -69,12 +69,15 @@ SIGNATURES = {
     "ap_classifier_create": (_i, [_PP, C.POINTER(ClassifierCfg), _PP, _i, _i]),
     "ap_classifier_destroy": (None, [_vp]),
     "ap_classifier_forward": (_i, [_vp, _fp, _fp, _i, _i, _vp]),
+    "ap_classifier_set_mode": (_i, [_vp, _i]),
+    "ap_classifier_get_mode": (_i, [_vp]),
     "ap_vote_counts": (_i, [_fp, _i, _i, _vp, _vp]),
     "ap_argmax": (_i, [_fp, _i, _i, _vp, _vp]),
     "ap_selftest_umma": (_i, [_vp, _vp, _fp, _i, _vp]),
     "ap_diffwave_debug_layer": (_i, [_vp, _fp, _f, _i, _fp, _fp, _i, _i, _vp]),
     "ap_diffwave_profile": (_i, [_vp, _i]),
     "ap_diffwave_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "ap_diffwave_debug_counters": (_i, [_vp, _vp]),
 }
 
 _lib = None

@@ -52,6 +52,16 @@ class _Classifier(torch.nn.Module):
     def cuda(self, device=None):
         return self
 
+    def set_mode(self, mode: str):
+        """'tf32' (tensor-core convolutions, default for ResNeXt) or 'fp32' (FFMA everywhere)."""
+        m = {"fp32": _lib.AP_MODE_FP32, "tf32": _lib.AP_MODE_TF32}[mode]
+        _lib.check(self._lib.ap_classifier_set_mode(self._handle, m), "ap_classifier_set_mode")
+        return self
+
+    @property
+    def mode(self) -> str:
+        return "tf32" if self._lib.ap_classifier_get_mode(self._handle) == _lib.AP_MODE_TF32 else "fp32"
+
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
         if h:

@@ -7,7 +7,11 @@
 #include <cmath>
 #include <memory>
 
+#include <cstdlib>
+#include <map>
+
 #include "ap_common.cuh"
+#include "ap_conv_tc.h"
 #include "ap_internal.h"
 #include "ap_sgemm.cuh"
 
@@ -68,12 +72,14 @@ struct ConvLayer {
   int Cin = 0, Cout = 0, kh = 1, kw = 1, stride = 1, pad = 0, groups = 1;
   int Cg = 0, Ng = 0, Ngp = 0, K = 0;
   DevBuf w, bias;
+  ConvTc tc;            // TF32 tensor-core twin (weights [Cout][K] K-major), built when the shape allows
+  bool has_tc = false;
   // w_t: torch [Cout][Cin/groups][kh][kw]; optional BatchNorm(eval) folded: scale = gamma/sqrt(var+eps), shift = beta - mean*scale
   int init(int cin, int cout, int kh_, int kw_, int stride_, int pad_, int groups_, const float* w_t, const float* conv_bias,
-           const float* bn_w, const float* bn_b, const float* bn_m, const float* bn_v) {
+           const float* bn_w, const float* bn_b, const float* bn_m, const float* bn_v, bool want_tc = false) {
     Cin = cin, Cout = cout, kh = kh_, kw = kw_, stride = stride_, pad = pad_, groups = groups_;
     Cg = cin / groups, Ng = cout / groups, Ngp = ((Ng + 127) / 128) * 128, K = kh * kw * Cg;
-    std::vector<float> wp(static_cast<size_t>(groups) * K * Ngp, 0.f), bp(cout);
+    std::vector<float> wp(static_cast<size_t>(groups) * K * Ngp, 0.f), bp(cout), wf(static_cast<size_t>(cout) * K);
     for (int o = 0; o < cout; ++o) {
       float scale = 1.f, shift = conv_bias ? conv_bias[o] : 0.f;
       if (bn_w) {
@@ -85,11 +91,20 @@ struct ConvLayer {
       for (int c = 0; c < Cg; ++c)
         for (int r = 0; r < kh; ++r)
           for (int s = 0; s < kw; ++s)
-            wp[(static_cast<size_t>(g) * K + (r * kw + s) * Cg + c) * Ngp + n] =
-                w_t[((static_cast<size_t>(o) * Cg + c) * kh + r) * kw + s] * scale;
+          {
+            const size_t ti = ((static_cast<size_t>(o) * Cg + c) * kh + r) * kw + s;
+            wf[ti] = w_t[ti] * scale;
+            wp[(static_cast<size_t>(g) * K + (r * kw + s) * Cg + c) * Ngp + n] = wf[ti];
+          }
     }
     AP_CUDA(w.upload(wp.data(), wp.size() * sizeof(float)));
     AP_CUDA(bias.upload(bp.data(), bp.size() * sizeof(float)));
+    // structural part of conv_tc_supported (the spatial part is checked when the layer is bound to buffers)
+    if (want_tc && Cg % 32 == 0 && (Ng == 64 || Ng == 128 || Ng % 256 == 0)) {
+      int rc = tc.init(cin, cout, kh, kw, stride, pad, groups, wf.data(), bp.data());
+      if (rc != AP_OK) return rc;
+      has_tc = true;
+    }
     return AP_OK;
   }
   int run(const float* in, int B, int H, int W, float* out, const float* residual, int relu, cudaStream_t st) const {
@@ -294,9 +309,20 @@ struct Bottleneck {
   int stride = 1, D = 0, cout = 0;
 };
 
+struct ConvStep {   // one convolution of the ResNeXt forward bound to workspace buffers
+  const ConvLayer* L;
+  int in, out, res;     // workspace buffer indices (res < 0: none)
+  int H, W, relu;
+  bool tc;
+  ConvTcBinding bnd;
+};
+
 struct ap_classifier_s {
   ap_classifier_cfg cfg{};
   int device = 0;
+  int mode = AP_MODE_FP32;                        // AP_MODE_TF32: tensor-core convolutions where the shape allows
+  unsigned tc_mask = 7;                           // bit 0: 1x1, bit 1: 3x3 stride 1, bit 2: strided (AP_CLS_TC_MASK, bisecting aid)
+  std::map<int, std::vector<ConvStep>> plans;     // keyed by the number of images in the chunk
   // ResNeXt
   ConvLayer stem;
   std::vector<std::unique_ptr<Bottleneck>> blocks;
@@ -342,15 +368,15 @@ static int create_resnext(ap_classifier_t h, const float* const* w, int n_weight
       const double width_ratio = cout / (c.widen_factor * 64.0);
       const int D = c.cardinality * static_cast<int>(c.base_width * width_ratio);
       blk->stride = stride, blk->D = D, blk->cout = cout;
-      rc = blk->reduce.init(cin, D, 1, 1, 1, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
+      rc = blk->reduce.init(cin, D, 1, 1, 1, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4], true);
       if (rc == AP_OK)
-        rc = blk->conv.init(D, D, 3, 3, stride, 1, c.cardinality, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9]);
+        rc = blk->conv.init(D, D, 3, 3, stride, 1, c.cardinality, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9], true);
       if (rc == AP_OK)
-        rc = blk->expand.init(D, cout, 1, 1, 1, 0, 1, w[i + 10], nullptr, w[i + 11], w[i + 12], w[i + 13], w[i + 14]);
+        rc = blk->expand.init(D, cout, 1, 1, 1, 0, 1, w[i + 10], nullptr, w[i + 11], w[i + 12], w[i + 13], w[i + 14], true);
       i += 15;
       if (rc == AP_OK && cin != cout) {
         blk->has_shortcut = true;
-        rc = blk->shortcut.init(cin, cout, 1, 1, stride, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
+        rc = blk->shortcut.init(cin, cout, 1, 1, stride, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4], true);
         i += 5;
       }
       if (rc != AP_OK) return rc;
@@ -362,42 +388,76 @@ static int create_resnext(ap_classifier_t h, const float* const* w, int n_weight
   return AP_OK;
 }
 
+// Build (once per chunk size) the list of convolutions bound to the five workspace buffers:
+//   0/1 = block input / output (ping-pong), 2 = reduce output, 3 = grouped-conv output, 4 = shortcut
+static int build_plan(ap_classifier_t h, int bn, std::vector<ConvStep>& plan) {
+  plan.clear();
+  int H = 32, W = 32, x = 0, xo = 1;
+  auto add = [&](const ConvLayer* L, int in, int out, int res, int Hin, int Win, int relu) -> int {
+    ConvStep st{};
+    st.L = L, st.in = in, st.out = out, st.res = res, st.H = Hin, st.W = Win, st.relu = relu;
+    const unsigned kind = (L->stride != 1) ? 4u : (L->kh == 1 ? 1u : 2u);
+    st.tc = h->mode == AP_MODE_TF32 && L->has_tc && (h->tc_mask & kind) &&
+            conv_tc_supported(L->Cin, L->Cout, L->groups, Hin, Win, L->kh, L->kw, L->stride, L->pad);
+    if (st.tc) {
+      int rc = L->tc.bind(&st.bnd, h->buf[in].as<float>(), bn, Hin, Win, h->buf[out].as<float>(),
+                          res >= 0 ? h->buf[res].as<float>() : nullptr, relu, 1);
+      if (rc != AP_OK) return rc;
+    }
+    plan.push_back(st);
+    return AP_OK;
+  };
+  for (auto& blk : h->blocks) {
+    const int Ho = (H - 1) / blk->stride + 1, Wo = (W - 1) / blk->stride + 1;
+    int rc = add(&blk->reduce, x, 2, -1, H, W, 1);
+    if (rc == AP_OK) rc = add(&blk->conv, 2, 3, -1, H, W, 1);
+    int res = x;
+    if (rc == AP_OK && blk->has_shortcut) {
+      rc = add(&blk->shortcut, x, 4, -1, H, W, 0);
+      res = 4;
+    }
+    if (rc == AP_OK) rc = add(&blk->expand, 3, xo, res, Ho, Wo, 1);
+    if (rc != AP_OK) return rc;
+    std::swap(x, xo);
+    H = Ho, W = Wo;
+  }
+  AP_REQUIRE(H == 8 && W == 8, "ResNeXt: unexpected final spatial size %dx%d", H, W);
+  return AP_OK;
+}
+
 static int forward_resnext(ap_classifier_t h, const float* spec, float* logits, int B, cudaStream_t st) {
   // spatial size fixed by avg_pool2d(x, 8, 1) + view(-1, C): 32x32 input -> 8x8 after two stride-2 stages
   const int H0 = 32, W0 = 32;
   int maxc = 64;
   for (auto& b : h->blocks) maxc = std::max(maxc, std::max(b->D, b->cout));
   const int chunk = 64;
-  int rc = ensure_ws(h, static_cast<size_t>(std::min(B, chunk)) * H0 * W0 * maxc);
+  const size_t need = static_cast<size_t>(std::min(B, chunk)) * H0 * W0 * maxc;
+  if (need > h->buf_elems) h->plans.clear();     // buffers move: the tensor maps must be re-encoded
+  int rc = ensure_ws(h, need);
   if (rc != AP_OK) return rc;
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int bn = std::min(chunk, B - b0);
-    float* x = h->buf[0].as<float>();
-    float* xo = h->buf[1].as<float>();
-    float* y1 = h->buf[2].as<float>();
-    float* y2 = h->buf[3].as<float>();
-    float* sc = h->buf[4].as<float>();
-    int H = H0, W = W0;
-    rc = h->stem.run(spec + static_cast<size_t>(b0) * h->cfg.in_channels * H0 * W0, bn, H, W, x, nullptr, 1, st);
-    if (rc != AP_OK) return rc;
-    for (auto& blk : h->blocks) {
-      const int Ho = (H - 1) / blk->stride + 1, Wo = (W - 1) / blk->stride + 1;
-      rc = blk->reduce.run(x, bn, H, W, y1, nullptr, 1, st);
-      if (rc == AP_OK) rc = blk->conv.run(y1, bn, H, W, y2, nullptr, 1, st);
-      const float* res = x;
-      if (rc == AP_OK && blk->has_shortcut) {
-        rc = blk->shortcut.run(x, bn, H, W, sc, nullptr, 0, st);
-        res = sc;
-      }
-      if (rc == AP_OK) rc = blk->expand.run(y2, bn, Ho, Wo, xo, res, 1, st);
+    auto it = h->plans.find(bn);
+    if (it == h->plans.end()) {
+      std::vector<ConvStep> plan;
+      rc = build_plan(h, bn, plan);
       if (rc != AP_OK) return rc;
-      std::swap(x, xo);
-      H = Ho, W = Wo;
+      it = h->plans.emplace(bn, std::move(plan)).first;
     }
-    AP_REQUIRE(H == 8 && W == 8, "ResNeXt: unexpected final spatial size %dx%d", H, W);
+    rc = h->stem.run(spec + static_cast<size_t>(b0) * h->cfg.in_channels * H0 * W0, bn, H0, W0, h->buf[0].as<float>(), nullptr, 1, st);
+    if (rc != AP_OK) return rc;
+    int last_out = 0;
+    for (const ConvStep& cs : it->second) {
+      if (cs.tc) rc = cs.L->tc.run(cs.bnd, st);
+      else
+        rc = cs.L->run(h->buf[cs.in].as<float>(), bn, cs.H, cs.W, h->buf[cs.out].as<float>(),
+                       cs.res >= 0 ? h->buf[cs.res].as<float>() : nullptr, cs.relu, st);
+      if (rc != AP_OK) return rc;
+      last_out = cs.out;
+    }
     const size_t smem = sizeof(float) * (h->feat + h->cfg.num_classes);
-    pool_fc_kernel<<<bn, 256, smem, st>>>(x, H * W, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(), h->cfg.num_classes,
-                                          logits + static_cast<size_t>(b0) * h->cfg.num_classes, 0);
+    pool_fc_kernel<<<bn, 256, smem, st>>>(h->buf[last_out].as<float>(), 64, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(),
+                                          h->cfg.num_classes, logits + static_cast<size_t>(b0) * h->cfg.num_classes, 0);
     AP_LAUNCH_CHECK();
   }
   return AP_OK;
@@ -519,7 +579,12 @@ extern "C" int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cf
   h->cfg = *cfg;
   h->device = device;
   switch (cfg->kind) {
-    case AP_CLS_RESNEXT: rc = create_resnext(h, weights, n_weights); break;
+    case AP_CLS_RESNEXT: {
+      rc = create_resnext(h, weights, n_weights);
+      h->mode = AP_MODE_TF32;
+      if (const char* env = std::getenv("AP_CLS_TC_MASK")) h->tc_mask = static_cast<unsigned>(std::atoi(env));
+      break;
+    }
     case AP_CLS_M5: rc = create_m5(h, weights, n_weights); break;
     case AP_CLS_KWS: rc = create_kws(h, weights, n_weights); break;
     default: rc = fail(AP_ERR_INVALID, "ap_classifier_create: unknown classifier kind %d", cfg->kind);
@@ -545,3 +610,12 @@ extern "C" int ap_classifier_forward(ap_classifier_t h, const float* input, floa
     default: return forward_kws(h, input, logits, B, in_len, st);
   }
 }
+
+extern "C" int ap_classifier_set_mode(ap_classifier_t h, int mode) {
+  AP_REQUIRE(h, "ap_classifier_set_mode: null handle");
+  AP_REQUIRE(mode == AP_MODE_FP32 || mode == AP_MODE_TF32, "ap_classifier_set_mode: mode must be AP_MODE_FP32 or AP_MODE_TF32");
+  if (mode != h->mode) h->plans.clear();
+  h->mode = mode;
+  return AP_OK;
+}
+extern "C" int ap_classifier_get_mode(ap_classifier_t h) { return h ? h->mode : AP_ERR_INVALID; }

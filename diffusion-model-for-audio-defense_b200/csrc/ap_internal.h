@@ -36,6 +36,7 @@ int tc_net_debug_layer(TcNet* n, const float* x, const float* ptab, int layer, f
 
 // per-launch CUDA-event timing of k1_layer ([0]) and k2_head ([1]); read synchronises on the recorded events
 void tc_net_profile(TcNet* n, bool on);
+int tc_net_debug_counters(TcNet* n, long long* host16x256);
 int tc_net_profile_read(TcNet* n, double* ms, int* count);
 
 }  // namespace ap

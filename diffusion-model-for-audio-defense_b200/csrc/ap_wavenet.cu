@@ -487,3 +487,11 @@ extern "C" int ap_diffwave_profile_read(ap_diffwave_t h, double* ms2, int* count
   AP_CUDA(cudaSetDevice(h->device));
   return tc_net_profile_read(h->tc, ms2, count2);
 }
+
+// development aid (AP_TC_DEBUG=1): per-CTA wait-cycle counters of the last k1_layer launch, 256 rows x 16 counters
+extern "C" int ap_diffwave_debug_counters(ap_diffwave_t h, long long* host16x256) {
+  AP_REQUIRE(h && h->tc && host16x256, "ap_diffwave_debug_counters: bad arguments");
+  AP_CUDA(cudaSetDevice(h->device));
+  AP_CUDA(cudaDeviceSynchronize());
+  return tc_net_debug_counters(h->tc, host16x256);
+}

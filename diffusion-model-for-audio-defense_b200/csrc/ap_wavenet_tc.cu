@@ -18,9 +18,11 @@
 //               of 32.8 MB per layer per waveform from the layer kernel.)
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
 #include <cmath>
+#include <cstdlib>
 #include <cuda.h>
 
 #include "ap_common.cuh"
+#include "ap_conv_tc.h"
 #include "ap_internal.h"
 #include "ap_ptx.cuh"
 
@@ -30,128 +32,220 @@ namespace tc {
 using namespace ptx;
 
 constexpr int C = 256;                      // channels (res == skip)
-constexpr int TILE_M = 128;                 // positions per tile
+constexpr int TILE_M = 128;                 // positions per tile (per CTA)
 constexpr int A_BYTES = TILE_M * 128;       // [128 rows][64 bf16]  SWIZZLE_128B
-constexpr int B_BYTES = 256 * 128;          // [256 rows][64 bf16]
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NSTAGE = 3;
-constexpr int OUT_OFF = NSTAGE * STAGE_BYTES;   // 4 K-blocks of [128][64] bf16 (gate output / staging)
-constexpr int OUT_BYTES = 4 * A_BYTES;
-constexpr int BIAS_OFF = OUT_OFF + OUT_BYTES;   // 1024 floats
-constexpr int BAR_OFF = BIAS_OFF + 4096;
-constexpr int SMEM_USED = BAR_OFF + 256;
-constexpr int SMEM_BYTES = SMEM_USED + 1024;    // + slack to align the base to 1024 B
+constexpr int OUT_BYTES = 4 * A_BYTES;      // 4 K-blocks of [128][64] bf16 (gate output / staging)
 constexpr int NTHREADS = 320;
 constexpr int EPI_THREADS = 256;
-constexpr uint32_t IDESC = umma_idesc_bf16_f32(128, 256);
 
-enum { BAR_FULL = 0, BAR_EMPTY = 3, BAR_ACC_FULL = 6, BAR_ACC_EMPTY = 8, BAR_OUT_READY = 10, BAR_UC_FULL = 12, BAR_COUNT = 13 };
+// CG = 1: one CTA per tile, tcgen05 cta_group::1 (M = 128).
+// CG = 2: a CTA pair (cluster of 2) works on two adjacent tiles with cta_group::2 (M = 256): each CTA stages its own 128
+//         activation rows and HALF of every weight tile, so both the TMA fill and the MMA operand reads of shared memory
+//         drop from 192 to 128 B/clk per SM (shared memory delivers 128 B/clk, which capped CG = 1 at ~63 % tensor duty).
+template <int CG> struct Geo {
+  static constexpr int B_ROWS = 256 / CG;
+  static constexpr int B_BYTES = B_ROWS * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = CG == 1 ? 3 : 4;
+  static constexpr int OUT_OFF = NSTAGE * STAGE_BYTES;
+  static constexpr int BIAS_OFF = OUT_OFF + OUT_BYTES;   // 1024 floats
+  static constexpr int BAR_OFF = BIAS_OFF + 4096;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + slack to align the base to 1024 B
+  static constexpr uint32_t IDESC = umma_idesc_bf16_f32(128 * CG, 256);
+};
+enum { BAR_FULL = 0, BAR_EMPTY = 4, BAR_ACC_FULL = 8, BAR_ACC_EMPTY = 10, BAR_OUT_READY = 12, BAR_UC_FULL = 14, BAR_COUNT = 15 };
+
+// Per-CTA view of the barrier array and the pair topology
+template <int CG> struct Ctx {
+  uint32_t base, bars, lbars, rank;
+  __device__ __forceinline__ uint32_t bar(int i) const { return bars + 8u * i; }    // local barrier (shared::cta)
+  __device__ __forceinline__ uint32_t lbar(int i) const { return lbars + 8u * i; }  // leader's barrier (shared::cluster)
+  __device__ __forceinline__ uint32_t stage_a(uint32_t s) const { return base + s * Geo<CG>::STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t stage_b(uint32_t s) const { return base + s * Geo<CG>::STAGE_BYTES + A_BYTES; }
+  __device__ __forceinline__ uint32_t out_kb(int kb) const { return base + Geo<CG>::OUT_OFF + kb * A_BYTES; }
+  // consumer -> MMA issuer signals (the issuer lives in the leader CTA)
+  __device__ __forceinline__ void arrive_leader(int i) const {
+    if (CG == 1) mbar_arrive(bar(i));
+    else mbar_arrive_cluster(lbar(i));
+  }
+  // producer: arm the full barrier of stage s for `bytes` per CTA, after the slot was released
+  __device__ __forceinline__ long long arm(uint32_t s, uint32_t ph, uint32_t bytes, int tag) const {
+    const long long w = mbar_wait(bar(BAR_EMPTY + s), ph ^ 1, tag);
+    if (CG == 1) mbar_expect_tx(bar(BAR_FULL + s), bytes);
+    else if (rank == 0) mbar_expect_tx(bar(BAR_FULL + s), 2 * bytes);
+    else mbar_arrive_cluster(lbar(BAR_FULL + s));
+    return w;
+  }
+  __device__ __forceinline__ void load_a(uint32_t s, const CUtensorMap* m, int c0, int c1, int c2) const {
+    if (CG == 1) tma_load_3d(stage_a(s), m, bar(BAR_FULL + s), c0, c1, c2);
+    else tma_load_3d_pair(stage_a(s), m, lbar(BAR_FULL + s), c0, c1, c2);
+  }
+  // weight tile: this CTA's B_ROWS rows starting at row0 (+ rank * B_ROWS)
+  __device__ __forceinline__ void load_b(uint32_t s, const CUtensorMap* m, int k0, int row0) const {
+    if (CG == 1) tma_load_2d(stage_b(s), m, bar(BAR_FULL + s), k0, row0);
+    else tma_load_2d_pair(stage_b(s), m, lbar(BAR_FULL + s), k0, row0 + static_cast<int>(rank) * Geo<CG>::B_ROWS);
+  }
+  // issue the 4 MMAs (K = 16 each) of one 64-wide K-block
+  __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, bool first) const {
+    const uint64_t ad = umma_desc_k_sw128(a_smem), bd = umma_desc_k_sw128(b_smem);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (CG == 1) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, Geo<CG>::IDESC, (first && k == 0) ? 0u : 1u);
+      else umma_bf16_pair(d_tmem, ad + 2 * k, bd + 2 * k, Geo<CG>::IDESC, (first && k == 0) ? 0u : 1u);
+    }
+  }
+  __device__ __forceinline__ void commit(int i) const {   // MMA issuer -> barrier i of every CTA of the pair
+    if (CG == 1) umma_commit(bar(i));
+    else umma_commit_pair(bar(i), 3);
+  }
+};
+
+// common prologue: barrier init, TMEM allocation, cluster handshake.  Returns the TMEM base address.
+template <int CG> __device__ __forceinline__ uint32_t tc_prologue(Ctx<CG>& cx, uint8_t*& gen, int out_ready_count) {
+  extern __shared__ uint8_t smem_raw[];
+  cx.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  gen = smem_raw + (cx.base - smem_u32(smem_raw));
+  cx.bars = cx.base + Geo<CG>::BAR_OFF;
+  cx.rank = CG == 1 ? 0u : cluster_ctarank();
+  cx.lbars = CG == 1 ? cx.bars : mapa_cluster(cx.bars, 0);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + Geo<CG>::BAR_OFF + 8 * BAR_COUNT);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Geo<CG>::NSTAGE; ++i) mbar_init(cx.bar(BAR_FULL + i), CG), mbar_init(cx.bar(BAR_EMPTY + i), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(cx.bar(BAR_ACC_FULL + i), 1);
+      mbar_init(cx.bar(BAR_ACC_EMPTY + i), 8 * CG);
+      mbar_init(cx.bar(BAR_OUT_READY + i), out_ready_count * CG);
+    }
+    mbar_init(cx.bar(BAR_UC_FULL), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    if (CG == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512), tmem_relinquish();
+    else tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512), tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / complete_tx
+  tc_fence_after();
+  return *tmem_slot;
+}
+template <int CG> __device__ __forceinline__ void tc_epilogue_teardown(uint32_t tmem) {
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // nobody exits (or frees TMEM) while the peer may still touch its smem / TMEM
+  if ((threadIdx.x >> 5) == 1) {
+    if (CG == 1) tmem_dealloc(tmem, 512);
+    else tmem_dealloc_pair(tmem, 512);
+  }
+}
+// tile enumeration: unit u = 0, 1, ... of this CTA -> (tile, valid)
+template <int CG> struct Tiles {
+  int n_tiles, first, stride;
+  __device__ __forceinline__ Tiles(int n, uint32_t rank) : n_tiles(n) {
+    if (CG == 1) first = blockIdx.x, stride = gridDim.x;
+    else first = 2 * (blockIdx.x >> 1) + static_cast<int>(rank), stride = 2 * (gridDim.x >> 1);
+  }
+  __device__ __forceinline__ bool more(int tile) const {            // the PAIR still has work
+    return CG == 1 ? tile < n_tiles : (tile & ~1) < n_tiles;
+  }
+};
 
 struct K1Params {
   int n_tiles, tiles_per_sample, dilation, layer, chunk_alloc, last;
   const float* b_dil;   // [2][256] packed chunk order
   const float* b_res;   // [256]
   const float* p_next;  // [256]
+  long long* dbg;       // optional [gridDim.x][16] wait-cycle counters (development aid), or null
 };
 
-// issue the 4 MMAs (K = 16 each) of one 64-wide K-block
-__device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, bool first) {
-  const uint64_t ad = umma_desc_k_sw128(a_smem), bd = umma_desc_k_sw128(b_smem);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
-}
-
+template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUtensorMap tmUout,
          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWd,
          const __grid_constant__ CUtensorMap tmWr, const K1Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  float* s_bias = reinterpret_cast<float*>(gen + BIAS_OFF);   // [0,512) b_dil, [512,768) b_res, [768,1024) p_next
-  const uint32_t bars = base + BAR_OFF;
-  auto bar = [&](int i) { return bars + 8u * i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + BAR_OFF + 8 * BAR_COUNT);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) mbar_init(bar(BAR_FULL + i), 1), mbar_init(bar(BAR_EMPTY + i), 1);
-    for (int i = 0; i < 2; ++i)
-      mbar_init(bar(BAR_ACC_FULL + i), 1), mbar_init(bar(BAR_ACC_EMPTY + i), 8), mbar_init(bar(BAR_OUT_READY + i), 1);
-    mbar_init(bar(BAR_UC_FULL), 1);
-    fence_barrier_init();
-    prefetch_tmap(&tmUin), prefetch_tmap(&tmUout), prefetch_tmap(&tmO), prefetch_tmap(&tmWd), prefetch_tmap(&tmWr);
-  }
-  if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
-    tmem_relinquish();
-  }
+  using G = Geo<CG>;
+  Ctx<CG> cx;
+  uint8_t* gen;
+  const uint32_t tmem = tc_prologue<CG>(cx, gen, 1);
+  float* s_bias = reinterpret_cast<float*>(gen + G::BIAS_OFF);   // [0,512) b_dil, [512,768) b_res, [768,1024) p_next
   for (int i = threadIdx.x; i < 1024; i += NTHREADS)
     s_bias[i] = i < 512 ? p.b_dil[i] : (i < 768 ? p.b_res[i - 512] : p.p_next[i - 768]);
-  tc_fence_before();
+  if (threadIdx.x == 0)
+    prefetch_tmap(&tmUin), prefetch_tmap(&tmUout), prefetch_tmap(&tmO), prefetch_tmap(&tmWd), prefetch_tmap(&tmWr);
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Tiles<CG> tiles(p.n_tiles, cx.rank);
+  const int oob_l0 = p.tiles_per_sample * TILE_M;   // a row coordinate past the end: TMA zero-fills the whole box
 
   if (warp == 0) {
     // ======================================================================================= TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int b = tile / p.tiles_per_sample, l0 = (tile - b * p.tiles_per_sample) * TILE_M;
+      long long w_empty = 0;
+      const long long t_start = clock64();
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride) {
+        const bool valid = tile < p.n_tiles;
+        const int b = valid ? tile / p.tiles_per_sample : 0;
+        const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
         for (int j = 0; j < 2; ++j)
           for (int tap = 0; tap < 3; ++tap)
             for (int kb = 0; kb < 4; ++kb, ++it) {
-              const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
-              mbar_wait(bar(BAR_EMPTY + s), ph ^ 1, 1);
-              mbar_expect_tx(bar(BAR_FULL + s), STAGE_BYTES);
-              tma_load_3d(base + s * STAGE_BYTES, &tmUin, bar(BAR_FULL + s), kb * 64, l0 + (tap - 1) * p.dilation, b);
-              tma_load_2d(base + s * STAGE_BYTES + A_BYTES, &tmWd, bar(BAR_FULL + s), tap * C + kb * 64,
-                          (p.layer * 2 + j) * 256);
+              const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+              w_empty += cx.arm(s, ph, G::STAGE_BYTES, 1);
+              cx.load_a(s, &tmUin, kb * 64, valid ? l0 + (tap - 1) * p.dilation : oob_l0, b);
+              cx.load_b(s, &tmWd, tap * C + kb * 64, (p.layer * 2 + j) * 256);
             }
         if (!p.last)
           for (int kb = 0; kb < 4; ++kb, ++it) {
-            const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
-            mbar_wait(bar(BAR_EMPTY + s), ph ^ 1, 2);
-            mbar_expect_tx(bar(BAR_FULL + s), B_BYTES);
-            tma_load_2d(base + s * STAGE_BYTES + A_BYTES, &tmWr, bar(BAR_FULL + s), kb * 64, p.layer * 256);
+            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+            w_empty += cx.arm(s, ph, G::B_BYTES, 2);
+            cx.load_b(s, &tmWr, kb * 64, p.layer * 256);
           }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 16 + 0] = w_empty, p.dbg[blockIdx.x * 16 + 1] = clock64() - t_start;
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ======================================================================================= MMA issuer
-    if (lane == 0) {
+    // ======================================================================================= MMA issuer (leader CTA)
+    if (lane == 0 && cx.rank == 0) {
       uint32_t it = 0, g = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      long long w_full = 0, w_acc = 0, w_out = 0;
+      const long long t_start = clock64();
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
         for (int j = 0; j < 2; ++j, ++g) {
           const uint32_t r = g & 1;
-          mbar_wait(bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 3);
+          w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 3);
           tc_fence_after();
           for (int kblk = 0; kblk < 12; ++kblk, ++it) {
-            const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
-            mbar_wait(bar(BAR_FULL + s), ph, 4);
+            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+            w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 4);
             tc_fence_after();
-            mma_kblock(tmem + r * 256, base + s * STAGE_BYTES, base + s * STAGE_BYTES + A_BYTES, kblk == 0);
-            umma_commit(bar(BAR_EMPTY + s));
+            cx.mma_kblock(tmem + r * 256, cx.stage_a(s), cx.stage_b(s), kblk == 0);
+            cx.commit(BAR_EMPTY + s);
           }
-          umma_commit(bar(BAR_ACC_FULL + r));
+          cx.commit(BAR_ACC_FULL + r);
         }
         if (!p.last) {
           const uint32_t r = g & 1;
-          mbar_wait(bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 5);
+          w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 5);
           for (int kb = 0; kb < 4; ++kb, ++it) {
-            const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
-            if (kb == 0) mbar_wait(bar(BAR_OUT_READY + 0), ti & 1, 6);
-            if (kb == 2) mbar_wait(bar(BAR_OUT_READY + 1), ti & 1, 7);
-            mbar_wait(bar(BAR_FULL + s), ph, 8);
+            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+            if (kb == 0) w_out += mbar_wait(cx.bar(BAR_OUT_READY + 0), ti & 1, 6);
+            if (kb == 2) w_out += mbar_wait(cx.bar(BAR_OUT_READY + 1), ti & 1, 7);
+            w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 8);
             tc_fence_after();
-            mma_kblock(tmem + r * 256, base + OUT_OFF + kb * A_BYTES, base + s * STAGE_BYTES + A_BYTES, kb == 0);
-            umma_commit(bar(BAR_EMPTY + s));
+            cx.mma_kblock(tmem + r * 256, cx.out_kb(kb), cx.stage_b(s), kb == 0);
+            cx.commit(BAR_EMPTY + s);
           }
-          umma_commit(bar(BAR_ACC_FULL + r));
+          cx.commit(BAR_ACC_FULL + r);
           ++g;
         }
+      }
+      if (p.dbg) {
+        long long* d = p.dbg + blockIdx.x * 16;
+        d[2] = w_full, d[3] = w_acc, d[4] = w_out, d[5] = clock64() - t_start, d[6] = ti;
       }
     }
     __syncwarp();
@@ -163,17 +257,21 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
     const uint32_t row_off = row * 128, sw = row & 7;
     const float sqrt_half = 0.70710678118654752440f;
     uint32_t g = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-      const int b = tile / p.tiles_per_sample, l0 = (tile - b * p.tiles_per_sample) * TILE_M;
+    long long w_accfull = 0, w_uc = 0, w_bar = 0;
+    const long long t_start = clock64();
+    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+      const bool valid = tile < p.n_tiles;
+      const int b = valid ? tile / p.tiles_per_sample : 0;
+      const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
       for (int j = 0; j < 2; ++j, ++g) {
         const uint32_t r = g & 1;
-        mbar_wait(bar(BAR_ACC_FULL + r), (g >> 1) & 1, 9);
+        w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 9);
         tc_fence_after();
         if (j == 0) {  // the staging region is about to be overwritten: previous TMA stores must have read it
           if (etid == 0) bulk_wait_read<0>();
           named_bar_sync(1, EPI_THREADS);
         }
-        const uint32_t kb_base = base + OUT_OFF + (2 * j + hsel) * A_BYTES + row_off;
+        const uint32_t kb_base = cx.out_kb(2 * j + hsel) + row_off;
         const float* bt = s_bias + j * 256 + hsel * 64;       // tanh-half bias; sigmoid half is +128
 #pragma unroll 1
         for (int gq = 0; gq < 2; ++gq) {
@@ -197,26 +295,27 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + r));
+        if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
         named_bar_sync(1, EPI_THREADS);
         if (etid == 0) {
-          tma_store_3d(&tmO, base + OUT_OFF + (2 * j) * A_BYTES, (2 * j) * 64, l0, p.layer * p.chunk_alloc + b);
-          tma_store_3d(&tmO, base + OUT_OFF + (2 * j + 1) * A_BYTES, (2 * j + 1) * 64, l0, p.layer * p.chunk_alloc + b);
-          bulk_commit();
-          mbar_arrive(bar(BAR_OUT_READY + j));
+          if (valid) {
+            tma_store_3d(&tmO, cx.out_kb(2 * j), (2 * j) * 64, l0, p.layer * p.chunk_alloc + b);
+            tma_store_3d(&tmO, cx.out_kb(2 * j + 1), (2 * j + 1) * 64, l0, p.layer * p.chunk_alloc + b);
+            bulk_commit();
+          }
+          cx.arrive_leader(BAR_OUT_READY + j);
         }
       }
       if (!p.last) {
         const uint32_t r = g & 1;
-        mbar_wait(bar(BAR_ACC_FULL + r), (g >> 1) & 1, 10);   // GEMM-2 done: accumulators ready, `out` smem no longer read
+        w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 10);   // GEMM-2 done: accumulators ready, `out` smem no longer read
         tc_fence_after();
         if (etid == 0) {
-          bulk_wait_read<0>();                                 // the O stores have finished reading `out`
-          mbar_expect_tx(bar(BAR_UC_FULL), OUT_BYTES);
-          for (int kb = 0; kb < 4; ++kb)
-            tma_load_3d(base + OUT_OFF + kb * A_BYTES, &tmUin, bar(BAR_UC_FULL), kb * 64, l0, b);
+          bulk_wait_read<0>();                                    // the O stores have finished reading `out`
+          mbar_expect_tx(cx.bar(BAR_UC_FULL), OUT_BYTES);
+          for (int kb = 0; kb < 4; ++kb) tma_load_3d(cx.out_kb(kb), &tmUin, cx.bar(BAR_UC_FULL), kb * 64, l0, b);
         }
-        mbar_wait(bar(BAR_UC_FULL), ti & 1, 11);
+        w_uc += mbar_wait(cx.bar(BAR_UC_FULL), ti & 1, 11);
         const float* br = s_bias + 512 + hsel * 128;
         const float* pn = s_bias + 768 + hsel * 128;
 #pragma unroll 1
@@ -224,7 +323,7 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
           uint32_t acc[32];
           tmem_ld_32x32b_x32(lane_addr + r * 256 + hsel * 128 + gq * 32, acc);
           tmem_ld_wait();
-          const uint32_t kb_base = base + OUT_OFF + (hsel * 2 + (gq >> 1)) * A_BYTES + row_off;
+          const uint32_t kb_base = cx.out_kb(hsel * 2 + (gq >> 1)) + row_off;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t addr = kb_base + ((((gq & 1) * 4 + i) ^ sw) << 4);
@@ -244,20 +343,22 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + r));
+        if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
         named_bar_sync(1, EPI_THREADS);
-        if (etid == 0) {
-          for (int kb = 0; kb < 4; ++kb) tma_store_3d(&tmUout, base + OUT_OFF + kb * A_BYTES, kb * 64, l0, b);
+        if (etid == 0 && valid) {
+          for (int kb = 0; kb < 4; ++kb) tma_store_3d(&tmUout, cx.out_kb(kb), kb * 64, l0, b);
           bulk_commit();
         }
         ++g;
       }
     }
     if (etid == 0) bulk_wait_all<0>();
+    if (p.dbg && etid == 0) {
+      long long* d = p.dbg + blockIdx.x * 16;
+      d[7] = w_accfull, d[8] = w_uc, d[9] = clock64() - t_start, d[10] = w_bar;
+    }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  tc_epilogue_teardown<CG>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------ k2: skip sum + head
@@ -270,85 +371,73 @@ struct K2Params {
   const float* bf2;      // [1]
   float* eps;            // [B][L]
 };
-enum { BAR2_S_READY = 10 };
+enum { BAR2_S_READY = BAR_OUT_READY };
 
+template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWs,
         const __grid_constant__ CUtensorMap tmWf, const K2Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  float* s_bias = reinterpret_cast<float*>(gen + BIAS_OFF);   // [0,256) bskip, [256,512) bf1, [512,768) wf2, [768,896) partial dots
-  const uint32_t bars = base + BAR_OFF;
-  auto bar = [&](int i) { return bars + 8u * i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + BAR_OFF + 8 * BAR_COUNT);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) mbar_init(bar(BAR_FULL + i), 1), mbar_init(bar(BAR_EMPTY + i), 1);
-    for (int i = 0; i < 2; ++i) mbar_init(bar(BAR_ACC_FULL + i), 1), mbar_init(bar(BAR_ACC_EMPTY + i), 8);
-    mbar_init(bar(BAR2_S_READY), 1);
-    fence_barrier_init();
-    prefetch_tmap(&tmO), prefetch_tmap(&tmWs), prefetch_tmap(&tmWf);
-  }
-  if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
-    tmem_relinquish();
-  }
+  using G = Geo<CG>;
+  Ctx<CG> cx;
+  uint8_t* gen;
+  const uint32_t tmem = tc_prologue<CG>(cx, gen, 1);
+  float* s_bias = reinterpret_cast<float*>(gen + G::BIAS_OFF);   // [0,256) bskip, [256,512) bf1, [512,768) wf2, [768,896) partial dots
   for (int i = threadIdx.x; i < 768; i += NTHREADS)
     s_bias[i] = i < 256 ? p.bskip[i] : (i < 512 ? p.bf1[i - 256] : p.wf2[i - 512]);
-  tc_fence_before();
+  if (threadIdx.x == 0) prefetch_tmap(&tmO), prefetch_tmap(&tmWs), prefetch_tmap(&tmWf);
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.num_layers * 4;
+  const Tiles<CG> tiles(p.n_tiles, cx.rank);
+  const int oob_l0 = p.tiles_per_sample * TILE_M;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int b = tile / p.tiles_per_sample, l0 = (tile - b * p.tiles_per_sample) * TILE_M;
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride) {
+        const bool valid = tile < p.n_tiles;
+        const int b = valid ? tile / p.tiles_per_sample : 0;
+        const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
         for (int n = 0; n < p.num_layers; ++n)
           for (int kb = 0; kb < 4; ++kb, ++it) {
-            const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
-            mbar_wait(bar(BAR_EMPTY + s), ph ^ 1, 21);
-            mbar_expect_tx(bar(BAR_FULL + s), STAGE_BYTES);
-            tma_load_3d(base + s * STAGE_BYTES, &tmO, bar(BAR_FULL + s), kb * 64, l0, n * p.chunk_alloc + b);
-            tma_load_2d(base + s * STAGE_BYTES + A_BYTES, &tmWs, bar(BAR_FULL + s), kb * 64, n * 256);
+            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+            cx.arm(s, ph, G::STAGE_BYTES, 21);
+            cx.load_a(s, &tmO, kb * 64, l0, n * p.chunk_alloc + b);
+            cx.load_b(s, &tmWs, kb * 64, n * 256);
           }
         for (int kb = 0; kb < 4; ++kb, ++it) {
-          const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
-          mbar_wait(bar(BAR_EMPTY + s), ph ^ 1, 22);
-          mbar_expect_tx(bar(BAR_FULL + s), B_BYTES);
-          tma_load_2d(base + s * STAGE_BYTES + A_BYTES, &tmWf, bar(BAR_FULL + s), kb * 64, 0);
+          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+          cx.arm(s, ph, G::B_BYTES, 22);
+          cx.load_b(s, &tmWf, kb * 64, 0);
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && cx.rank == 0) {
       uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-        mbar_wait(bar(BAR_ACC_EMPTY + 0), (ti & 1) ^ 1, 23);
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+        mbar_wait(cx.bar(BAR_ACC_EMPTY + 0), (ti & 1) ^ 1, 23);
         tc_fence_after();
         for (int kblk = 0; kblk < nkb; ++kblk, ++it) {
-          const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
-          mbar_wait(bar(BAR_FULL + s), ph, 24);
+          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+          mbar_wait(cx.bar(BAR_FULL + s), ph, 24);
           tc_fence_after();
-          mma_kblock(tmem, base + s * STAGE_BYTES, base + s * STAGE_BYTES + A_BYTES, kblk == 0);
-          umma_commit(bar(BAR_EMPTY + s));
+          cx.mma_kblock(tmem, cx.stage_a(s), cx.stage_b(s), kblk == 0);
+          cx.commit(BAR_EMPTY + s);
         }
-        umma_commit(bar(BAR_ACC_FULL + 0));
-        mbar_wait(bar(BAR_ACC_EMPTY + 1), (ti & 1) ^ 1, 25);
-        mbar_wait(bar(BAR2_S_READY), ti & 1, 26);
+        cx.commit(BAR_ACC_FULL + 0);
+        mbar_wait(cx.bar(BAR_ACC_EMPTY + 1), (ti & 1) ^ 1, 25);
+        mbar_wait(cx.bar(BAR2_S_READY), ti & 1, 26);
         tc_fence_after();
         for (int kb = 0; kb < 4; ++kb, ++it) {
-          const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
-          mbar_wait(bar(BAR_FULL + s), ph, 27);
+          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+          mbar_wait(cx.bar(BAR_FULL + s), ph, 27);
           tc_fence_after();
-          mma_kblock(tmem + 256, base + OUT_OFF + kb * A_BYTES, base + s * STAGE_BYTES + A_BYTES, kb == 0);
-          umma_commit(bar(BAR_EMPTY + s));
+          cx.mma_kblock(tmem + 256, cx.out_kb(kb), cx.stage_b(s), kb == 0);
+          cx.commit(BAR_EMPTY + s);
         }
-        umma_commit(bar(BAR_ACC_FULL + 1));
+        cx.commit(BAR_ACC_FULL + 1);
       }
     }
     __syncwarp();
@@ -359,11 +448,13 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
     const uint32_t row_off = row * 128, sw = row & 7;
     float* s_part = s_bias + 768;
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-      const int b = tile / p.tiles_per_sample, l0 = (tile - b * p.tiles_per_sample) * TILE_M;
+    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+      const bool valid = tile < p.n_tiles;
+      const int b = valid ? tile / p.tiles_per_sample : 0;
+      const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
       // ---- skip sum -> s (bf16, A operand of the head GEMM).  The previous tile's head MMAs finished reading the
       //      staging region before its ACC_FULL[1] fired, which this thread has already waited on.
-      mbar_wait(bar(BAR_ACC_FULL + 0), ti & 1, 28);
+      mbar_wait(cx.bar(BAR_ACC_FULL + 0), ti & 1, 28);
       tc_fence_after();
       const float* bs = s_bias + hsel * 128;
 #pragma unroll 1
@@ -371,7 +462,7 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
         uint32_t acc[32];
         tmem_ld_32x32b_x32(lane_addr + hsel * 128 + gq * 32, acc);
         tmem_ld_wait();
-        const uint32_t kb_base = base + OUT_OFF + (hsel * 2 + (gq >> 1)) * A_BYTES + row_off;
+        const uint32_t kb_base = cx.out_kb(hsel * 2 + (gq >> 1)) + row_off;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint32_t pk[4];
@@ -387,11 +478,11 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + 0));
+      if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 0);
       named_bar_sync(1, EPI_THREADS);
-      if (etid == 0) mbar_arrive(bar(BAR2_S_READY));
+      if (etid == 0) cx.arrive_leader(BAR2_S_READY);
       // ---- head: y = relu(acc + b) ; eps = w2 . y + b2
-      mbar_wait(bar(BAR_ACC_FULL + 1), ti & 1, 29);
+      mbar_wait(cx.bar(BAR_ACC_FULL + 1), ti & 1, 29);
       tc_fence_after();
       const float* bf = s_bias + 256 + hsel * 128;
       const float* w2 = s_bias + 512 + hsel * 128;
@@ -406,16 +497,14 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + 1));
+      if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 1);
       if (hsel == 1) s_part[row] = dot;
       named_bar_sync(1, EPI_THREADS);
-      if (hsel == 0 && l0 + row < p.L) p.eps[static_cast<size_t>(b) * p.L + l0 + row] = dot + s_part[row] + p.bf2[0];
+      if (hsel == 0 && valid && l0 + row < p.L) p.eps[static_cast<size_t>(b) * p.L + l0 + row] = dot + s_part[row] + p.bf2[0];
       named_bar_sync(1, EPI_THREADS);   // s_part is rewritten by the next tile
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  tc_epilogue_teardown<CG>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------ init conv (bf16 out)
@@ -458,8 +547,8 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bars = base + STAGE_BYTES;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + STAGE_BYTES + 64);
+  const uint32_t bars = base + Geo<1>::STAGE_BYTES;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + Geo<1>::STAGE_BYTES + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(bars, 1), mbar_init(bars + 8, 1);
@@ -473,14 +562,16 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  Ctx<1> cx;
+  cx.base = base, cx.bars = bars, cx.lbars = bars, cx.rank = 0;
   if (threadIdx.x == 0) {
     for (int kb = 0; kb < K / 64; ++kb) {
-      mbar_expect_tx(bars, STAGE_BYTES);
+      mbar_expect_tx(bars, Geo<1>::STAGE_BYTES);
       tma_load_2d(base, &tmA, bars, kb * 64, 0);
       tma_load_2d(base + A_BYTES, &tmB, bars, kb * 64, 0);
       mbar_wait(bars, kb & 1, 40);
       tc_fence_after();
-      mma_kblock(tmem, base, base + A_BYTES, kb == 0);
+      cx.mma_kblock(tmem, base, base + A_BYTES, kb == 0);
       umma_commit(bars + 8);
       mbar_wait(bars + 8, kb & 1, 41);   // single stage: wait for the MMAs before refilling
     }
@@ -516,26 +607,34 @@ static EncodeTiledFn encode_fn() {
 }
 // bf16 tensor, innermost dim contiguous; dims/box innermost first; SWIZZLE_128B (box[0] * 2 B == 128 B)
 static int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return fail(AP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t gdim[5], gstride[5];
-  cuuint32_t bx[5], es[5];
+  uint64_t strides[4];
+  uint32_t es[5];
   uint64_t stride = 2;
   for (int i = 0; i < rank; ++i) {
-    gdim[i] = dims[i];
-    bx[i] = box[i];
     es[i] = 1;
     stride *= dims[i];
-    if (i + 1 < rank) gstride[i] = stride;
+    if (i + 1 < rank) strides[i] = stride;
   }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstride, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(AP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
-  return AP_OK;
+  return tma_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ptr, rank, dims, strides, box, es);
 }
 
 }  // namespace tc
+
+int tma_encode(CUtensorMap* m, CUtensorMapDataType dtype, const void* ptr, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  tc::EncodeTiledFn fn = tc::encode_fn();
+  if (!fn) return fail(AP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5], gstride[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i], bx[i] = box[i], es[i] = elem_strides[i];
+    if (i + 1 < rank) gstride[i] = strides_bytes[i];
+  }
+  CUresult r = fn(m, dtype, rank, const_cast<void*>(ptr), gdim, gstride, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return AP_OK;
+}
 
 // ================================================================================================ TcNet
 struct TcNet {
@@ -545,10 +644,13 @@ struct TcNet {
   DevBuf bd, br, bskip, bf1, wf2, bf2, init_w, init_b;     // fp32 vectors
   DevBuf u0, u1, o;
   int chunk = 0, L = 0;
-  CUtensorMap tmU[2], tmO, tmWd, tmWr, tmWs, tmWf;
+  CUtensorMap tmU[2], tmO, tmWd, tmWr, tmWs, tmWf;   // weight maps: box of 256 rows (one CTA per tile)
+  CUtensorMap tmWd2, tmWr2, tmWs2, tmWf2;           // weight maps: box of 128 rows (CTA pairs, each CTA stages half)
+  bool pair = true;                                 // cta_group::2 kernels (AP_TC_PAIR=0 selects the 1-CTA kernels)
   bool attr_set = false;
   // optional per-launch timing (bench.py roofline): CUDA events recorded on the launching stream around k1 / k2
   bool prof = false;
+  DevBuf dbg;                       // wait-cycle counters of the last k1 launch (AP_TC_DEBUG=1)
   std::vector<cudaEvent_t> ev[2];   // [0] = k1 pairs, [1] = k2 pairs (start, stop interleaved)
   size_t ev_used[2] = {0, 0};
   ~TcNet() {
@@ -566,6 +668,11 @@ static cudaEvent_t prof_event(TcNet* n, int which) {
     n->ev[which].push_back(e);
   }
   return n->ev[which][n->ev_used[which]++];
+}
+int tc_net_debug_counters(TcNet* n, long long* host16x256) {
+  if (!n->dbg.p) return fail(AP_ERR_STATE, "set AP_TC_DEBUG=1 before creating the network");
+  AP_CUDA(cudaMemcpy(host16x256, n->dbg.p, sizeof(long long) * 16 * 256, cudaMemcpyDeviceToHost));
+  return AP_OK;
 }
 void tc_net_profile(TcNet* n, bool on) {
   n->prof = on;
@@ -648,6 +755,18 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
     TRY(encode_bf16(&n->tmWr, n->wr.p, 2, d2, bw));
     TRY(encode_bf16(&n->tmWs, n->ws.p, 2, d2, bw));
     TRY(encode_bf16(&n->tmWf, n->wf.p, 2, d3, bw));
+    const uint32_t bw2[2] = {64, 128};
+    TRY(encode_bf16(&n->tmWd2, n->wd.p, 2, d1, bw2));
+    TRY(encode_bf16(&n->tmWr2, n->wr.p, 2, d2, bw2));
+    TRY(encode_bf16(&n->tmWs2, n->ws.p, 2, d2, bw2));
+    TRY(encode_bf16(&n->tmWf2, n->wf.p, 2, d3, bw2));
+    const char* env = std::getenv("AP_TC_PAIR");
+    if (env && env[0] == '0') n->pair = false;
+    env = std::getenv("AP_TC_DEBUG");
+    if (env && env[0] == '1') {
+      TRY((n->dbg.alloc(sizeof(long long) * 16 * 256) == cudaSuccess &&
+           cudaMemset(n->dbg.p, 0, sizeof(long long) * 16 * 256) == cudaSuccess) ? AP_OK : fail(AP_ERR_CUDA, "dbg alloc"));
+    }
   }
 #undef TRY
   if (rc != AP_OK) {
@@ -677,11 +796,29 @@ int tc_net_reserve(TcNet* n, int chunk, int L) {
   if (rc == AP_OK) rc = encode_bf16(&n->tmO, n->o.p, 3, dO, bx);
   if (rc != AP_OK) return rc;
   if (!n->attr_set) {
-    AP_CUDA(cudaFuncSetAttribute(k1_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    AP_CUDA(cudaFuncSetAttribute(k2_head, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2>::SMEM_BYTES));
     n->attr_set = true;
   }
   return AP_OK;
+}
+
+// cluster-of-2 launch (CTA pairs); grid = 2 x min(#pairs, #SMs / 2)
+static int pair_grid(int n_tiles) {
+  const int pairs = (n_tiles + 1) / 2, cap = num_sms() / 2;
+  return 2 * (pairs < cap ? pairs : cap);
+}
+template <class Kernel, class... Args>
+static cudaError_t launch_pair(Kernel kernel, int grid, int smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(tc::NTHREADS), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int L, int layers, cudaStream_t st) {
@@ -704,9 +841,15 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     p.b_dil = n->bd.as<float>() + static_cast<size_t>(l) * 512;
     p.b_res = n->br.as<float>() + static_cast<size_t>(l) * C;
     p.p_next = ptab + static_cast<size_t>(l + 1) * C;
+    p.dbg = n->dbg.as<long long>();
     cudaEvent_t e0 = prof_event(n, 0), e1 = e0 ? prof_event(n, 0) : nullptr;
     if (e1) cudaEventRecord(e0, st);
-    k1_layer<<<grid, NTHREADS, SMEM_BYTES, st>>>(n->tmU[l & 1], n->tmU[(l + 1) & 1], n->tmO, n->tmWd, n->tmWr, p);
+    if (n->pair) {
+      AP_CUDA(launch_pair(k1_layer<2>, pair_grid(n_tiles), Geo<2>::SMEM_BYTES, st, n->tmU[l & 1], n->tmU[(l + 1) & 1], n->tmO,
+                          n->tmWd2, n->tmWr2, p));
+    } else {
+      k1_layer<1><<<grid, NTHREADS, Geo<1>::SMEM_BYTES, st>>>(n->tmU[l & 1], n->tmU[(l + 1) & 1], n->tmO, n->tmWd, n->tmWr, p);
+    }
     if (e1) cudaEventRecord(e1, st);
     AP_LAUNCH_CHECK();
   }
@@ -727,7 +870,11 @@ int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, i
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   cudaEvent_t e0 = prof_event(n, 1), e1 = e0 ? prof_event(n, 1) : nullptr;
   if (e1) cudaEventRecord(e0, st);
-  k2_head<<<grid, NTHREADS, SMEM_BYTES, st>>>(n->tmO, n->tmWs, n->tmWf, p);
+  if (n->pair) {
+    AP_CUDA(launch_pair(k2_head<2>, pair_grid(n_tiles), Geo<2>::SMEM_BYTES, st, n->tmO, n->tmWs2, n->tmWf2, p));
+  } else {
+    k2_head<1><<<grid, NTHREADS, Geo<1>::SMEM_BYTES, st>>>(n->tmO, n->tmWs, n->tmWf, p);
+  }
   if (e1) cudaEventRecord(e1, st);
   AP_LAUNCH_CHECK();
   return AP_OK;
@@ -772,7 +919,7 @@ extern "C" int ap_selftest_umma(const uint16_t* a_bf16, const uint16_t* b_bf16, 
   rc = encode_bf16(&ta, a_bf16, 2, da, ba);
   if (rc == AP_OK) rc = encode_bf16(&tb, b_bf16, 2, db, bb);
   if (rc != AP_OK) return rc;
-  const int smem = STAGE_BYTES + 128 + 1024;
+  const int smem = Geo<1>::STAGE_BYTES + 128 + 1024;
   AP_CUDA(cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, d_out, K);
   AP_LAUNCH_CHECK();

@@ -1,9 +1,10 @@
-"""Quick GPU probe (development aid, not the benchmark): times the tensor-core WaveNet at several chunk sizes."""
+"""Development probe (not the benchmark): times the tensor-core WaveNet and prints the k1_layer wait-cycle counters.
+Usage: AP_TC_DEBUG=1 [AP_TC_PAIR=0|1] python probe.py [B] [chunk]"""
 import ctypes as C
 import os
 import sys
-import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,34 +14,46 @@ from audiopure_b200 import _lib, synthetic  # noqa: E402
 
 
 def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    chunk = int(sys.argv[2]) if len(sys.argv) > 2 else B
     sd = synthetic.wavenet_state_dict(seed=0)
     net = ap.WaveNet(sd, mode="bf16", **synthetic.DEFAULT_WAVENET_CONFIG)
     lib = _lib.load()
     L = 16000
-    for B, chunk in [(8, 8), (32, 16), (32, 32), (64, 64)]:
-        x = torch.from_numpy(synthetic.synthetic_waveforms(B, L, seed=1)).cuda()
-        out = torch.empty_like(x)
-        net.reserve(chunk, L)
+    x = torch.from_numpy(synthetic.synthetic_waveforms(B, L, seed=1)).cuda()
+    out = torch.empty_like(x)
+    net.reserve(chunk, L)
+    net.eps(x, 1.0, out=out)
+    torch.cuda.synchronize()
+    lib.ap_diffwave_profile(net._handle, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 3
+    for _ in range(reps):
         net.eps(x, 1.0, out=out)
-        torch.cuda.synchronize()
-        lib.ap_diffwave_profile(net._handle, 1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        reps = 2
-        for _ in range(reps):
-            net.eps(x, 1.0, out=out)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        pm = (C.c_double * 2)()
-        pc = (C.c_int * 2)()
-        lib.ap_diffwave_profile_read(net._handle, pm, pc)
-        lib.ap_diffwave_profile(net._handle, 0)
-        fl = 606.1e9 * B
-        k1_fl = 14.68e9 * chunk
-        print(f"B={B} chunk={chunk}: {ms:.2f} ms/eps  -> {fl / ms / 1e9:.1f} TFLOP/s overall; "
-              f"k1 avg {pm[0] / max(pc[0], 1):.3f} ms ({k1_fl / (pm[0] / max(pc[0], 1)) / 1e9:.1f} TFLOP/s, n={pc[0]}); "
-              f"k2 avg {pm[1] / max(pc[1], 1):.3f} ms (n={pc[1]})", flush=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    pm, pc = (C.c_double * 2)(), (C.c_int * 2)()
+    lib.ap_diffwave_profile_read(net._handle, pm, pc)
+    lib.ap_diffwave_profile(net._handle, 0)
+    k1 = pm[0] / max(pc[0], 1)
+    print(f"pair={os.environ.get('AP_TC_PAIR', '1')} B={B} chunk={chunk}: {ms:.2f} ms/eps ({606.1 * B / ms:.1f} TFLOP/s); "
+          f"k1 avg {k1:.3f} ms ({14.68 * min(B, chunk) / k1:.1f} TFLOP/s, n={pc[0]}); k2 avg {pm[1] / max(pc[1], 1):.3f} ms", flush=True)
+    if os.environ.get("AP_TC_DEBUG") == "1":
+        buf = np.zeros((256, 16), dtype=np.int64)
+        _lib.check(lib.ap_diffwave_debug_counters(net._handle, buf.ctypes.data))
+        names = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_accempty", "mma_wait_outready", "mma_total",
+                 "tiles", "epi_wait_accfull", "epi_wait_uc", "epi_total", "epi_wbar"]
+        act = buf[buf[:, 1] > 0]
+        lead = act[act[:, 5] > 0]
+        print(f"active CTAs {len(act)}, MMA-issuing CTAs {len(lead)} (last k1 launch; cycles, mean over CTAs)")
+        for i, nm in enumerate(names):
+            src = lead if nm.startswith("mma") or nm == "tiles" else act
+            print(f"  {nm:20s} {src[:, i].mean():14.0f}")
+        t = lead[:, 6].mean()
+        print(f"  per tile: mma_total {lead[:, 5].mean() / t:.0f} clk = ideal MMA {14336 if True else 0} + wait_full {lead[:, 2].mean() / t:.0f}"
+              f" + wait_accempty {lead[:, 3].mean() / t:.0f} + wait_outready {lead[:, 4].mean() / t:.0f} + issue/other")
 
 
 if __name__ == "__main__":

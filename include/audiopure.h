@@ -33,6 +33,7 @@ extern "C" {
 /* arithmetic mode of the DiffWave network */
 #define AP_MODE_BF16 0 /* tcgen05 tensor cores: bf16 operands, fp32 accumulate (TMEM), fp32 x/update arithmetic */
 #define AP_MODE_FP32 1 /* fp32 FFMA path (parity mode, <=1e-5 rel-L2 vs the reference) */
+#define AP_MODE_TF32 2 /* classifiers only: tcgen05 kind::tf32 convolutions (the precision of the reference's cuDNN path) */
 
 typedef struct ap_diffwave_s* ap_diffwave_t;
 typedef struct ap_mel_s* ap_mel_t;
@@ -162,6 +163,9 @@ int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cfg* cfg, con
 void ap_classifier_destroy(ap_classifier_t h);
 /* input: device (B, 1, 32, 32) spectrogram (ResNeXt), (B, L) waveform (M5; in_len = L) or (B, 32, W) (KWS; in_len = W) */
 int ap_classifier_forward(ap_classifier_t h, const float* input, float* logits, int B, int in_len, void* stream);
+/* AP_MODE_TF32 (default for ResNeXt: tensor-core convolutions) or AP_MODE_FP32 (every convolution on the FFMA path) */
+int ap_classifier_set_mode(ap_classifier_t h, int mode);
+int ap_classifier_get_mode(ap_classifier_t h);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Votes (replaces the argmax + per-class .sum().item() loop of smooth_predict, certified_robust.py:59-67)
@@ -187,6 +191,9 @@ int ap_diffwave_debug_layer(ap_diffwave_t h, const float* x, float t, int layer,
  * device time in ms and the launch count of k1_layer (index 0) and k2_head (index 1) since the last enable. */
 int ap_diffwave_profile(ap_diffwave_t h, int enable);
 int ap_diffwave_profile_read(ap_diffwave_t h, double* ms2, int* count2);
+/* Development aid (env AP_TC_DEBUG=1 at create): per-CTA wait-cycle counters of the last k1_layer launch,
+ * host array of 256 x 16 int64 (see csrc/ap_wavenet_tc.cu for the slot meaning). */
+int ap_diffwave_debug_counters(ap_diffwave_t h, long long* host16x256);
 
 #ifdef __cplusplus
 }

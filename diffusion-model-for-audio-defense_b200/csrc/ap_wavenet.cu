@@ -409,7 +409,8 @@ extern "C" int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* 
   const int curL = tc ? h->tc_L : h->L;
   if (chunk == 0 || curL != L) {
     // default chunk: bounded workspace (fp32: 4 * 4 B * 256 ch per position; bf16: ~2.5 KB per position incl. gate history)
-    const long long budget_positions = tc ? (1ll << 20) : (1ll << 18);
+    // bf16: 148 waveforms of 1 s = 18500 tiles = 125 full rounds over 74 CTA pairs (no ragged last wave)
+    const long long budget_positions = tc ? 148ll * 16000 : (1ll << 18);
     long long want = budget_positions / L;
     if (want < 1) want = 1;
     if (want > B) want = B;

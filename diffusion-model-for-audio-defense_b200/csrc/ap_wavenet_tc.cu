@@ -650,7 +650,8 @@ struct TcNet {
   bool attr_set = false;
   // optional per-launch timing (bench.py roofline): CUDA events recorded on the launching stream around k1 / k2
   bool prof = false;
-  DevBuf dbg;                       // wait-cycle counters of the last k1 launch (AP_TC_DEBUG=1)
+  DevBuf dbg;                       // wait-cycle counters of k1 launches of layer dbg_layer (AP_TC_DEBUG=1)
+  int dbg_layer = 35;               // AP_TC_DEBUG_LAYER
   std::vector<cudaEvent_t> ev[2];   // [0] = k1 pairs, [1] = k2 pairs (start, stop interleaved)
   size_t ev_used[2] = {0, 0};
   ~TcNet() {
@@ -762,6 +763,7 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
     TRY(encode_bf16(&n->tmWf2, n->wf.p, 2, d3, bw2));
     const char* env = std::getenv("AP_TC_PAIR");
     if (env && env[0] == '0') n->pair = false;
+    if (const char* e2 = std::getenv("AP_TC_DEBUG_LAYER")) n->dbg_layer = std::atoi(e2);
     env = std::getenv("AP_TC_DEBUG");
     if (env && env[0] == '1') {
       TRY((n->dbg.alloc(sizeof(long long) * 16 * 256) == cudaSuccess &&
@@ -841,7 +843,7 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     p.b_dil = n->bd.as<float>() + static_cast<size_t>(l) * 512;
     p.b_res = n->br.as<float>() + static_cast<size_t>(l) * C;
     p.p_next = ptab + static_cast<size_t>(l + 1) * C;
-    p.dbg = n->dbg.as<long long>();
+    p.dbg = (l == n->dbg_layer) ? n->dbg.as<long long>() : nullptr;
     cudaEvent_t e0 = prof_event(n, 0), e1 = e0 ? prof_event(n, 0) : nullptr;
     if (e1) cudaEventRecord(e0, st);
     if (n->pair) {

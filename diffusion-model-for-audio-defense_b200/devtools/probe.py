@@ -52,7 +52,7 @@ def main():
             src = lead if nm.startswith("mma") or nm == "tiles" else act
             print(f"  {nm:20s} {src[:, i].mean():14.0f}")
         t = lead[:, 6].mean()
-        print(f"  per tile: mma_total {lead[:, 5].mean() / t:.0f} clk = ideal MMA {14336 if True else 0} + wait_full {lead[:, 2].mean() / t:.0f}"
+        print(f"  per tile: mma_total {lead[:, 5].mean() / t:.0f} clk = ideal MMA 14336 (12288 for the last layer) + wait_full {lead[:, 2].mean() / t:.0f}"
               f" + wait_accempty {lead[:, 3].mean() / t:.0f} + wait_outready {lead[:, 4].mean() / t:.0f} + issue/other")
 
 

@@ -43,6 +43,11 @@ def parse_args():
     p.add_argument("--chunk", type=int, default=0, help="waveforms per workspace chunk (0 = library default)")
     p.add_argument("--certify-draws", type=int, default=4096, help="extra certification leg (0 = skip)")
     p.add_argument("--cpu-sample", type=int, default=2, help="waveforms in the cpu_baseline sample (0 = skip)")
+    p.add_argument("--workload", default="sc09", choices=["sc09", "sde", "m5", "kws"],
+                   help="sc09 = BASELINE configs[1] (headline); sde = configs[3] (reverse-SDE purifier, --t-star 1..10); "
+                        "m5 / kws = configs[4] (DDPM purifier + raw-waveform M5 / mel(400,200,32) + RCNN_KWS)")
+    p.add_argument("--t-star", type=int, default=T_STAR)
+    p.add_argument("--length", type=int, default=LENGTH)
     return p.parse_args()
 
 
@@ -54,6 +59,20 @@ def measured_peaks():
         return {"tflops_sustained": d.get("bf16_tflops_sustained"), "tflops_burst": d.get("bf16_tflops"),
                 "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
     return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def workload_config(args, world):
+    purifier = {"sc09": f"DDPM t*={args.t_star}", "sde": f"reverse-SDE (Euler-Maruyama) t*={args.t_star}",
+                "m5": f"DDPM t*={args.t_star}", "kws": f"DDPM t*={args.t_star}"}[args.workload]
+    head = {"sc09": "SC09 log-mel + ResNeXt-29 8x64", "sde": "SC09 log-mel + ResNeXt-29 8x64", "m5": "M5 raw-waveform classifier",
+            "kws": "KWS log-mel (n_fft 400, hop 200, 32 mels) + RCNN_KWS"}[args.workload]
+    name = {"sc09": "BASELINE configs[1]", "sde": "BASELINE configs[3]", "m5": "BASELINE configs[4] (M5)",
+            "kws": "BASELINE configs[4] (RCNN_KWS)"}[args.workload]
+    return {"workload": f"{name}: DiffWave(36 layers, C=256) {purifier} + {head}, batch {args.batch} x "
+                        f"{args.length / 16000:g} s @ 16 kHz per GPU, random-init weights",
+            "batch_per_gpu": args.batch, "length": args.length, "t_star": args.t_star, "mode": args.mode,
+            "parallelism": f"replicas x{world} (no data-path collective)",
+            "l2": "256 MiB buffer rewritten between timed iterations; activations per chunk >> L2"}
 
 
 class ClockSampler:
@@ -140,8 +159,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"DiffWave(36x256) DDPM t*={T_STAR} + mel + ResNeXt-29 8x64, 1 s @ 16 kHz, random-init "
-                                   f"(BASELINE configs[1] per waveform)", "sample_per_step": sample},
+            "config": workload_config(args, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample} waveform per step x {args.steps} steps (torch CPU ops, {cores} threads)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -165,13 +183,26 @@ def run_ours(args):
     lib = _lib.load()
 
     cfg_json = os.path.join(ROOT, "diffusion-model-for-audio-defense_b200", "configs", "config.json")
-    dw = ap.create_diffwave_model(None, cfg_json, reverse_timestep=T_STAR, state_dict=synthetic.wavenet_state_dict(seed=0),
-                                  noise="philox", seed=2024 + rank, mode=args.mode)
+    LENGTH = args.length
+    sd = synthetic.wavenet_state_dict(seed=0)
+    if args.workload == "sde":
+        ns = argparse.Namespace(ddpm_path=None, ddpm_config=cfg_json, t=args.t_star, score_type="guided_diffusion", rand_t=False,
+                                t_delta=0, use_bm=False, sample_step=1)
+        defender = ap.RevDiffWave(ns, state_dict=sd, noise="philox", seed=2024 + rank, mode=args.mode)
+        dw = defender.model
+    else:
+        dw = ap.create_diffwave_model(None, cfg_json, reverse_timestep=args.t_star, state_dict=sd, noise="philox",
+                                      seed=2024 + rank, mode=args.mode)
+        defender = dw
     if args.chunk:
         dw.model.reserve(args.chunk, LENGTH)
-    transform = ap.sc09_transform()
-    classifier = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
-    system = ap.AcousticSystem(classifier=classifier, transform=transform, defender=dw, defense_type="wave")
+    if args.workload == "m5":
+        transform, classifier = None, ap.M5Classifier(synthetic.m5_state_dict(seed=0))
+    elif args.workload == "kws":
+        transform, classifier = ap.kws_transform(), ap.KWSClassifier(synthetic.kws_state_dict(seed=0))
+    else:
+        transform, classifier = ap.sc09_transform(), ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    system = ap.AcousticSystem(classifier=classifier, transform=transform, defender=defender, defense_type="wave")
 
     B = args.batch
     x_host = torch.from_numpy(synthetic.synthetic_waveforms(B, LENGTH, seed=1234 + rank)).pin_memory()
@@ -234,7 +265,7 @@ def run_ours(args):
 
     # ---- certification leg: one-shot denoise at t* = 66 (sigma 0.5), draws sharded over the ranks, one all-reduce
     cert = None
-    if args.certify_draws > 0:
+    if args.certify_draws > 0 and args.workload == "sc09":
         rc = ap.RobustCertificate(classifier=classifier, transform=transform, denoiser=dw, num_classes=10, seed=99)
         x1 = x_dev[:1]
         rc.smooth_predict(x1, num_sampling=min(512 * world, args.certify_draws), sigma=0.5, batch_size=512)
@@ -255,12 +286,11 @@ def run_ours(args):
         peaks = measured_peaks()
         roofline = None
         if args.mode == "bf16" and prof_n[0] > 0:
-            chunk_wf = min(B, max(1, (1 << 20) // LENGTH)) if not args.chunk else min(B, args.chunk)
             k1_ms = prof_ms[0] / prof_n[0]
             # launches over the last (ragged) chunk process fewer waveforms: use the exact average per launch
-            n_layers, evals = 36, T_STAR * args.steps
+            n_layers, evals = 36, args.t_star * args.steps
             avg_wf = B * n_layers * evals / prof_n[0]
-            achieved = K1_GFLOP_PER_WAVEFORM * avg_wf / k1_ms        # GFLOP / ms == TFLOP/s
+            achieved = K1_GFLOP_PER_WAVEFORM * (LENGTH / 16000) * avg_wf / k1_ms        # GFLOP / ms == TFLOP/s
             roofline = {"kernel": "k1_layer (DiffWave residual block: tcgen05 implicit GEMM K=768/N=512 + K=256/N=256, fused "
                                   "gate / residual epilogues)", "bound": "tensor", "achieved": achieved,
                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
@@ -269,7 +299,6 @@ def run_ours(args):
                         "share_of_step": prof_ms[0] / ms,
                         "k2_head": {"avg_launch_ms": prof_ms[1] / max(prof_n[1], 1), "launches": int(prof_n[1]),
                                     "share_of_step": prof_ms[1] / ms}}
-            del chunk_wf
         cpu = None
         if args.cpu_sample > 0:
             import torch as _t
@@ -281,12 +310,9 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
-                "config": {"workload": f"BASELINE configs[1]: DiffWave(36 layers, C=256) DDPM t*={T_STAR} + SC09 log-mel + "
-                                       f"ResNeXt-29 8x64, batch {B} x 1 s @ 16 kHz per GPU, random-init weights",
-                           "batch_per_gpu": B, "length": LENGTH, "t_star": T_STAR, "mode": args.mode,
-                           "parallelism": f"replicas x{world} (no data-path collective)",
-                           "l2": "256 MiB buffer rewritten between timed iterations; activations per chunk >> L2"},
-                "tflops_per_gpu": value / world * (T_STAR * WAVENET_GFLOP + 10.77 + 0.27) / 1e3,
+                "config": workload_config(args, world),
+                "tflops_per_gpu": value / world * (args.t_star * WAVENET_GFLOP * LENGTH / 16000 +
+                                                   (10.77 + 0.27 if args.workload in ("sc09", "sde") else 0.02)) / 1e3,
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                         "d2h_bytes_per_step": int(pred_host.numel() * 8), "ms_per_step": ms_e2e / args.steps},

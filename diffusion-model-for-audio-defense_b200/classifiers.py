@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["ResNeXtClassifier", "M5Classifier", "KWSClassifier", "create_model"]
+__all__ = ["ResNeXtClassifier", "ResNetClassifier", "M5Classifier", "KWSClassifier", "create_model"]
 
 
 def _np32(t) -> np.ndarray:
@@ -99,6 +99,33 @@ class ResNeXtClassifier(_Classifier):
         return self._run(spec, spec.shape[0], 32)
 
 
+class ResNetClassifier(_Classifier):
+    """torchvision-style ResNet-18/34/50/101/152 with ``in_channels`` (models/resnet.py:103-220) on (B,1,32,32) input."""
+    LAYERS = {18: (False, (2, 2, 2, 2)), 34: (False, (3, 4, 6, 3)), 50: (True, (3, 4, 6, 3)), 101: (True, (3, 4, 23, 3)),
+              152: (True, (3, 8, 36, 3))}
+
+    def __init__(self, state_dict: dict, depth: int = 34, num_classes=10, in_channels=1, device=None):
+        super().__init__()
+        sd = _strip(state_dict)
+        bn = lambda p: [sd[p + ".weight"], sd[p + ".bias"], sd[p + ".running_mean"], sd[p + ".running_var"]]
+        bottleneck, counts = self.LAYERS[depth]
+        w = [sd["conv1.weight"], *bn("bn1")]
+        for l, n in enumerate(counts):
+            for b in range(n):
+                p = f"layer{l + 1}.{b}"
+                for j in range(3 if bottleneck else 2):
+                    w += [sd[f"{p}.conv{j + 1}.weight"], *bn(f"{p}.bn{j + 1}")]
+                if f"{p}.downsample.0.weight" in sd:
+                    w += [sd[f"{p}.downsample.0.weight"], *bn(f"{p}.downsample.1")]
+        w += [sd["fc.weight"], sd["fc.bias"]]
+        cfg = _lib.ClassifierCfg(_lib.AP_CLS_RESNET, num_classes, 0, depth, 0, 0, in_channels, 0, 0, 0, 0, 0)
+        self._create(cfg, w, device)
+
+    def forward(self, spec: torch.Tensor) -> torch.Tensor:
+        assert spec.ndim == 4 and tuple(spec.shape[1:]) == (1, 32, 32), f"expected (B,1,32,32), got {tuple(spec.shape)}"
+        return self._run(spec, spec.shape[0], 32)
+
+
 class M5Classifier(_Classifier):
     def __init__(self, state_dict: dict, n_input=1, first_kernel_size=160, n_output=10, stride=16, n_channel=32,
                  device=None):
@@ -150,6 +177,12 @@ def create_model(path: str, device=None):
         return ResNeXtClassifier(sd, nlabels=model.nlabels, cardinality=model.cardinality, depth=model.depth,
                                  base_width=model.base_width, widen_factor=model.widen_factor,
                                  in_channels=model.conv_1_3x3.in_channels, device=device)
+    if name == "ResNet":
+        bottleneck = type(model.layer1[0]).__name__ == "Bottleneck"
+        counts = tuple(len(getattr(model, f"layer{i}")) for i in range(1, 5))
+        depth = {v: k for k, v in ResNetClassifier.LAYERS.items()}[(bottleneck, counts)]
+        return ResNetClassifier(sd, depth=depth, num_classes=model.fc.out_features, in_channels=model.conv1.in_channels,
+                                device=device)
     if name == "M5":
         return M5Classifier(sd, first_kernel_size=model.conv1.kernel_size[0], n_output=model.fc1.out_features,
                             stride=model.conv1.stride[0], n_channel=model.conv1.out_channels, device=device)

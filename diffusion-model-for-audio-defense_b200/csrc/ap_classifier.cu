@@ -4,6 +4,7 @@
 //                   the weights/bias and the residual add + ReLU fused into the epilogue.
 //   AP_CLS_M5       M5 (audio_models/M5/M5Net.py:4-38)            conv1d/BN/ReLU/maxpool x4, avgpool, fc, log_softmax
 //   AP_CLS_KWS      KWSModel (audio_models/RCNN_KWS/model.py:5-113)  sepconv, 2-layer bi-GRU, attention, fc, log_softmax
+#include <algorithm>
 #include <cmath>
 #include <memory>
 
@@ -178,6 +179,29 @@ __global__ void __launch_bounds__(256) maxpool4_kernel(const float* __restrict__
   }
 }
 
+// MaxPool2d(kernel 3, stride 2, padding 1) over NHWC [B][H][W][C] -> [B][Ho][Wo][C]   (torchvision ResNet stem, resnet.py:112)
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H,
+                                                           int W, int Cc) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * Cc;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cc);
+    long long t = i / Cc;
+    const int ow = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const long long b = t / Ho;
+    float m = -INFINITY;
+    for (int r = 0; r < 3; ++r)
+      for (int s = 0; s < 3; ++s) {
+        const int ih = 2 * oh + r - 1, iw = 2 * ow + s - 1;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) m = fmaxf(m, in[((b * H + ih) * W + iw) * Cc + c]);
+      }
+    out[i] = m;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- KWS (RCNN + attention)
 // One CTA per sample; everything lives in shared memory (W <= 512 spectrogram frames).
 struct KwsWeights {
@@ -328,6 +352,13 @@ struct ap_classifier_s {
   std::vector<std::unique_ptr<Bottleneck>> blocks;
   DevBuf fc_w, fc_b;
   int feat = 0;
+  // ResNet family
+  struct ResBlock {
+    ConvLayer c1, c2, c3, down;
+    bool bottleneck = false, has_down = false;
+    int stride = 1, cout = 0;
+  };
+  std::vector<std::unique_ptr<ResBlock>> resblocks;
   // M5
   ConvLayer m5conv[4];
   // KWS
@@ -463,6 +494,118 @@ static int forward_resnext(ap_classifier_t h, const float* spec, float* logits, 
   return AP_OK;
 }
 
+// ---- ResNet family (models/resnet.py:103-220): state_dict order conv1.weight, bn1.{w,b,mean,var}, then per block
+//      conv1, bn1, conv2, bn2, [conv3, bn3,] [downsample.0.weight, downsample.1.{...}], finally fc.weight, fc.bias
+static int create_resnet(ap_classifier_t h, const float* const* w, int n_weights) {
+  const ap_classifier_cfg& c = h->cfg;
+  int counts[4];
+  bool bott = false;
+  switch (c.depth) {
+    case 18: counts[0] = 2, counts[1] = 2, counts[2] = 2, counts[3] = 2; break;
+    case 34: counts[0] = 3, counts[1] = 4, counts[2] = 6, counts[3] = 3; break;
+    case 50: counts[0] = 3, counts[1] = 4, counts[2] = 6, counts[3] = 3, bott = true; break;
+    case 101: counts[0] = 3, counts[1] = 4, counts[2] = 23, counts[3] = 3, bott = true; break;
+    case 152: counts[0] = 3, counts[1] = 8, counts[2] = 36, counts[3] = 3, bott = true; break;
+    default: return fail(AP_ERR_INVALID, "ap_classifier_create: ResNet depth must be 18/34/50/101/152 (got %d)", c.depth);
+  }
+  AP_REQUIRE(c.in_channels == 1, "ap_classifier_create: ResNet in_channels must be 1 (NCHW == NHWC)");
+  const int exp = bott ? 4 : 1;
+  int expected = 5 + 2, inpl = 64;
+  for (int l = 0; l < 4; ++l)
+    for (int b = 0; b < counts[l]; ++b) {
+      const int planes = 64 << l, stride = (b == 0 && l > 0) ? 2 : 1;
+      expected += (bott ? 15 : 10) + ((b == 0 && (stride != 1 || inpl != planes * exp)) ? 5 : 0);
+      inpl = planes * exp;
+    }
+  AP_REQUIRE(n_weights == expected, "ap_classifier_create: ResNet-%d expects %d weight tensors, got %d", c.depth, expected, n_weights);
+  int rc = h->stem.init(1, 64, 7, 7, 2, 3, 1, w[0], nullptr, w[1], w[2], w[3], w[4]);
+  if (rc != AP_OK) return rc;
+  int i = 5;
+  inpl = 64;
+  for (int l = 0; l < 4; ++l)
+    for (int b = 0; b < counts[l]; ++b) {
+      auto blk = std::make_unique<ap_classifier_s::ResBlock>();
+      const int planes = 64 << l, stride = (b == 0 && l > 0) ? 2 : 1;
+      blk->bottleneck = bott, blk->stride = stride, blk->cout = planes * exp;
+      if (bott) {
+        rc = blk->c1.init(inpl, planes, 1, 1, 1, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
+        if (rc == AP_OK) rc = blk->c2.init(planes, planes, 3, 3, stride, 1, 1, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9]);
+        if (rc == AP_OK) rc = blk->c3.init(planes, planes * 4, 1, 1, 1, 0, 1, w[i + 10], nullptr, w[i + 11], w[i + 12], w[i + 13], w[i + 14]);
+        i += 15;
+      } else {
+        rc = blk->c1.init(inpl, planes, 3, 3, stride, 1, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
+        if (rc == AP_OK) rc = blk->c2.init(planes, planes, 3, 3, 1, 1, 1, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9]);
+        i += 10;
+      }
+      if (rc == AP_OK && b == 0 && (stride != 1 || inpl != planes * exp)) {
+        blk->has_down = true;
+        rc = blk->down.init(inpl, planes * exp, 1, 1, stride, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
+        i += 5;
+      }
+      if (rc != AP_OK) return rc;
+      inpl = planes * exp;
+      h->resblocks.push_back(std::move(blk));
+    }
+  h->feat = 512 * exp;
+  AP_CUDA(h->fc_w.upload(w[i], sizeof(float) * c.num_classes * h->feat));
+  AP_CUDA(h->fc_b.upload(w[i + 1], sizeof(float) * c.num_classes));
+  return AP_OK;
+}
+
+static int forward_resnet(ap_classifier_t h, const float* spec, float* logits, int B, int H0, int W0, cudaStream_t st) {
+  // conv1 7x7 s2 -> maxpool 3x3 s2 -> 4 stages; the reference's x.view(B, -1) needs a 1x1 final map (32x32 input)
+  auto half = [](int v) { return (v - 1) / 2 + 1; };
+  const int H1 = half(H0), W1 = half(W0), H2 = half(H1), W2 = half(W1);
+  AP_REQUIRE(half(half(half(H2))) == 1 && half(half(half(W2))) == 1, "ResNet: input %dx%d does not reduce to 1x1", H0, W0);
+  const int chunk = 256;
+  const size_t per = std::max<size_t>(static_cast<size_t>(H1) * W1 * 64, static_cast<size_t>(H2) * W2 * 64 * (h->feat / 512) * 4);
+  int rc = ensure_ws(h, static_cast<size_t>(std::min(B, chunk)) * per);
+  if (rc != AP_OK) return rc;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    float* x = h->buf[0].as<float>();
+    float* xo = h->buf[1].as<float>();
+    float* y1 = h->buf[2].as<float>();
+    float* y2 = h->buf[3].as<float>();
+    float* sc = h->buf[4].as<float>();
+    rc = h->stem.run(spec + static_cast<size_t>(b0) * H0 * W0, bn, H0, W0, y1, nullptr, 1, st);      // resnet.py:146-148
+    if (rc != AP_OK) return rc;
+    {
+      const long long total = static_cast<long long>(bn) * H2 * W2 * 64;
+      long long blocks = ceil_div_ll(total, 256);
+      if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+      maxpool3x3s2_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(y1, x, bn, H1, W1, 64);          // :149
+      AP_LAUNCH_CHECK();
+    }
+    int H = H2, W = W2;
+    for (auto& blk : h->resblocks) {
+      const int Ho = (H - 1) / blk->stride + 1, Wo = (W - 1) / blk->stride + 1;
+      const float* res = x;
+      if (blk->has_down) {
+        rc = blk->down.run(x, bn, H, W, sc, nullptr, 0, st);
+        if (rc != AP_OK) return rc;
+        res = sc;
+      }
+      if (blk->bottleneck) {
+        rc = blk->c1.run(x, bn, H, W, y1, nullptr, 1, st);
+        if (rc == AP_OK) rc = blk->c2.run(y1, bn, H, W, y2, nullptr, 1, st);
+        if (rc == AP_OK) rc = blk->c3.run(y2, bn, Ho, Wo, xo, res, 1, st);
+      } else {
+        rc = blk->c1.run(x, bn, H, W, y1, nullptr, 1, st);
+        if (rc == AP_OK) rc = blk->c2.run(y1, bn, Ho, Wo, xo, res, 1, st);
+      }
+      if (rc != AP_OK) return rc;
+      std::swap(x, xo);
+      H = Ho, W = Wo;
+    }
+    const size_t smem = sizeof(float) * (h->feat + h->cfg.num_classes);
+    pool_fc_kernel<<<bn, 256, smem, st>>>(x, 1, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(), h->cfg.num_classes,
+                                          logits + static_cast<size_t>(b0) * h->cfg.num_classes, 0);   // AvgPool2d(1) + fc, :156-158
+    AP_LAUNCH_CHECK();
+  }
+  return AP_OK;
+}
+
 // ---- M5: state_dict order conv{i}.weight, conv{i}.bias, bn{i}.{weight,bias,running_mean,running_var} (i=1..4), fc1.weight, fc1.bias
 static int create_m5(ap_classifier_t h, const float* const* w, int n_weights) {
   const ap_classifier_cfg& c = h->cfg;
@@ -586,6 +729,7 @@ extern "C" int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cf
       break;
     }
     case AP_CLS_M5: rc = create_m5(h, weights, n_weights); break;
+    case AP_CLS_RESNET: rc = create_resnet(h, weights, n_weights); break;
     case AP_CLS_KWS: rc = create_kws(h, weights, n_weights); break;
     default: rc = fail(AP_ERR_INVALID, "ap_classifier_create: unknown classifier kind %d", cfg->kind);
   }
@@ -607,6 +751,7 @@ extern "C" int ap_classifier_forward(ap_classifier_t h, const float* input, floa
   switch (h->cfg.kind) {
     case AP_CLS_RESNEXT: return forward_resnext(h, input, logits, B, st);
     case AP_CLS_M5: return forward_m5(h, input, logits, B, in_len, st);
+    case AP_CLS_RESNET: return forward_resnet(h, input, logits, B, 32, in_len, st);
     default: return forward_kws(h, input, logits, B, in_len, st);
   }
 }
@@ -614,6 +759,7 @@ extern "C" int ap_classifier_forward(ap_classifier_t h, const float* input, floa
 extern "C" int ap_classifier_set_mode(ap_classifier_t h, int mode) {
   AP_REQUIRE(h, "ap_classifier_set_mode: null handle");
   AP_REQUIRE(mode == AP_MODE_FP32 || mode == AP_MODE_TF32, "ap_classifier_set_mode: mode must be AP_MODE_FP32 or AP_MODE_TF32");
+  AP_REQUIRE(mode == AP_MODE_FP32 || h->cfg.kind == AP_CLS_RESNEXT, "ap_classifier_set_mode: only ResNeXt has tensor-core convolutions");
   if (mode != h->mode) h->plans.clear();
   h->mode = mode;
   return AP_OK;

@@ -128,6 +128,37 @@ def resnext_state_dict(seed: int = 0, nlabels: int = 10, cardinality: int = 8, d
     return sd
 
 
+RESNET_LAYERS = {18: (False, (2, 2, 2, 2)), 34: (False, (3, 4, 6, 3)), 50: (True, (3, 4, 6, 3)), 101: (True, (3, 4, 23, 3)),
+                 152: (True, (3, 8, 36, 3))}
+
+
+def resnet_state_dict(depth: int = 34, seed: int = 0, num_classes: int = 10, in_channels: int = 1):
+    """torchvision-style ResNet state dict (models/resnet.py:103-160), BN with non-trivial running stats."""
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    bottleneck, counts = RESNET_LAYERS[depth]
+    exp = 4 if bottleneck else 1
+    _conv2d(sd, seed, "conv1", 64, in_channels, 7, 7)
+    _bn(sd, seed, "bn1", 64)
+    inpl = 64
+    for l, n in enumerate(counts):
+        planes = 64 << l
+        for b in range(n):
+            p = f"layer{l + 1}.{b}"
+            stride = 2 if (b == 0 and l > 0) else 1
+            if bottleneck:
+                _conv2d(sd, seed, p + ".conv1", planes, inpl, 1, 1); _bn(sd, seed, p + ".bn1", planes)
+                _conv2d(sd, seed, p + ".conv2", planes, planes, 3, 3); _bn(sd, seed, p + ".bn2", planes)
+                _conv2d(sd, seed, p + ".conv3", planes * 4, planes, 1, 1); _bn(sd, seed, p + ".bn3", planes * 4)
+            else:
+                _conv2d(sd, seed, p + ".conv1", planes, inpl, 3, 3); _bn(sd, seed, p + ".bn1", planes)
+                _conv2d(sd, seed, p + ".conv2", planes, planes, 3, 3); _bn(sd, seed, p + ".bn2", planes)
+            if b == 0 and (stride != 1 or inpl != planes * exp):
+                _conv2d(sd, seed, p + ".downsample.0", planes * exp, inpl, 1, 1); _bn(sd, seed, p + ".downsample.1", planes * exp)
+            inpl = planes * exp
+    _linear(sd, seed, "fc", num_classes, 512 * exp, gain=4.0)
+    return sd
+
+
 def m5_state_dict(seed: int = 0, n_input=1, first_kernel_size=160, n_output=10, n_channel=32):
     """M5 state dict (M5Net.py:4-20)."""
     sd: "OrderedDict[str, np.ndarray]" = OrderedDict()

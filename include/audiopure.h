@@ -146,6 +146,7 @@ int ap_mel_db(ap_mel_t h, const float* wav, float* spec, int B, int L, void* str
 #define AP_CLS_RESNEXT 0 /* CifarResNeXt, models/resnext.py:67-142 : (B,1,32,32) -> (B,nlabels) logits   */
 #define AP_CLS_M5 1      /* M5, audio_models/M5/M5Net.py:4-38       : (B,1,L)     -> (B,n) log-probs      */
 #define AP_CLS_KWS 2     /* KWSModel, audio_models/RCNN_KWS/model.py:66-113 : (B,1,32,W) -> (B,4) log-probs */
+#define AP_CLS_RESNET 3  /* ResNet-18/34/50/101/152, models/resnet.py:103-220 : (B,1,32,32) -> (B,num_classes) logits; `depth` selects */
 typedef struct {
   int kind;
   int num_classes;
@@ -161,7 +162,7 @@ typedef struct {
 int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cfg* cfg, const float* const* weights,
                          int n_weights, int device);
 void ap_classifier_destroy(ap_classifier_t h);
-/* input: device (B, 1, 32, 32) spectrogram (ResNeXt), (B, L) waveform (M5; in_len = L) or (B, 32, W) (KWS; in_len = W) */
+/* input: device (B, 1, 32, 32) spectrogram (ResNeXt, ResNet; in_len = 32), (B, L) waveform (M5; in_len = L) or (B, 32, W) (KWS; in_len = W) */
 int ap_classifier_forward(ap_classifier_t h, const float* input, float* logits, int B, int in_len, void* stream);
 /* AP_MODE_TF32 (default for ResNeXt: tensor-core convolutions) or AP_MODE_FP32 (every convolution on the FFMA path) */
 int ap_classifier_set_mode(ap_classifier_t h, int mode);

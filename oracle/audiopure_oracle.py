@@ -405,6 +405,40 @@ def resnext_forward(sd, spec, cardinality=8, depth=29, widen_factor=4, dtype=tor
 
 
 # --------------------------------------------------------------------------------------
+# a16  ResNet family                                 audio_models/ConvNets_SpeechCommands/models/resnet.py:32-160
+# --------------------------------------------------------------------------------------
+RESNET_LAYERS = {18: (False, (2, 2, 2, 2)), 34: (False, (3, 4, 6, 3)), 50: (True, (3, 4, 6, 3)), 101: (True, (3, 4, 23, 3)),
+                 152: (True, (3, 8, 36, 3))}
+
+
+def resnet_forward(sd, spec, depth=34, dtype=torch.float32):
+    """(B,1,32,32) -> (B,num_classes): conv7x7 s2 + BN + ReLU, maxpool 3x3 s2, 4 stages of Basic/Bottleneck blocks,
+    AvgPool2d(1) (identity), flatten, fc   (resnet.py:145-160; blocks :45-62, :80-101)."""
+    w = lambda k: _t(sd[k], dtype)
+    bottleneck, counts = RESNET_LAYERS[depth]
+    x = _t(spec, dtype)
+    x = F.relu(_bn_eval(sd, "bn1", F.conv2d(x, w("conv1.weight"), stride=2, padding=3), dtype))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for l, n in enumerate(counts):
+        for b in range(n):
+            p = f"layer{l + 1}.{b}"
+            stride = 2 if (b == 0 and l > 0) else 1
+            if bottleneck:
+                y = F.relu(_bn_eval(sd, p + ".bn1", F.conv2d(x, w(p + ".conv1.weight")), dtype))
+                y = F.relu(_bn_eval(sd, p + ".bn2", F.conv2d(y, w(p + ".conv2.weight"), stride=stride, padding=1), dtype))
+                y = _bn_eval(sd, p + ".bn3", F.conv2d(y, w(p + ".conv3.weight")), dtype)
+            else:
+                y = F.relu(_bn_eval(sd, p + ".bn1", F.conv2d(x, w(p + ".conv1.weight"), stride=stride, padding=1), dtype))
+                y = _bn_eval(sd, p + ".bn2", F.conv2d(y, w(p + ".conv2.weight"), padding=1), dtype)
+            r = x
+            if (p + ".downsample.0.weight") in sd:
+                r = _bn_eval(sd, p + ".downsample.1", F.conv2d(x, w(p + ".downsample.0.weight"), stride=stride), dtype)
+            x = F.relu(y + r)
+    x = x.reshape(x.shape[0], -1)
+    return F.linear(x, w("fc.weight"), w("fc.bias"))
+
+
+# --------------------------------------------------------------------------------------
 # a17  M5                                            audio_models/M5/M5Net.py:21-38
 # --------------------------------------------------------------------------------------
 def m5_forward(sd, wave, stride=16, dtype=torch.float32):

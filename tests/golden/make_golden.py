@@ -168,6 +168,14 @@ def main():
     with torch.no_grad():
         out["resnext_logits"] = rx(torch.from_numpy(out["mel_sc09"])).numpy()
 
+    # ---- a16: ResNet family (BasicBlock and Bottleneck variants) on the same mel features
+    from models.resnet import resnet34, resnet50
+    for depth, ctor in ((34, resnet34), (50, resnet50)):
+        rn = ctor(num_classes=10, in_channels=1).eval()
+        rn.load_state_dict(to_torch_sd(synthetic.resnet_state_dict(depth=depth, seed=0)))
+        with torch.no_grad():
+            out[f"resnet{depth}_logits"] = rn(torch.from_numpy(out["mel_sc09"])).numpy()
+
     # ---- a17 / a18: M5 and RCNN_KWS
     sys.path.insert(0, os.path.join(REF, "audio_models", "M5"))
     from M5Net import M5

@@ -284,6 +284,17 @@ def test_classifiers_vs_reference_golden(ap, golden):
     np.testing.assert_allclose(kws(cuda(golden["mel_kws"])).cpu().numpy(), golden["kws_logprobs"], atol=2e-4, rtol=0)
 
 
+@pytest.mark.parametrize("depth", [34, 50])
+def test_resnet_family_vs_reference_golden(ap, golden, depth):
+    rn = ap.ResNetClassifier(synthetic.resnet_state_dict(depth=depth, seed=0), depth=depth)
+    logits = rn(cuda(golden["mel_sc09"])).cpu().numpy()
+    want = golden[f"resnet{depth}_logits"]
+    assert np.abs(logits - want).max() < 1e-3 * max(1.0, np.abs(want).max())
+    assert (logits.argmax(1) == want.argmax(1)).all()
+    with pytest.raises(ap.AudioPureError):
+        rn.set_mode("tf32")
+
+
 @pytest.mark.parametrize("mask", [1, 2, 4, 7])
 def test_resnext_tensor_core_convs_by_kind(ap, mask, monkeypatch):
     """tf32 tensor-core convolutions enabled per kind (1: 1x1, 2: 3x3 stride 1, 4: stride 2) against the fp32 FFMA path,

@@ -172,3 +172,11 @@ def test_certification(golden, sd_full, hp):
     y, r = orc.certify_from_counts([0, 100], [0, 100000], 100000, 0.5)
     assert y == 1 and abs(r - 1.9057) < 1e-3
     assert orc.certify_from_counts([60, 40], [50200, 49800], 100000, 0.5) == (-1, 0.0)
+
+
+@pytest.mark.parametrize("depth", [34, 50])
+def test_resnet_family(golden, depth):
+    sd = synthetic.resnet_state_dict(depth=depth, seed=0)
+    logits = orc.resnet_forward(sd, golden["mel_sc09"], depth=depth).numpy()
+    want = golden[f"resnet{depth}_logits"]
+    assert np.abs(logits - want).max() < 1e-4 * max(1.0, np.abs(want).max())

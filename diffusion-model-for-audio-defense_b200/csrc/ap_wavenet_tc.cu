@@ -42,27 +42,33 @@ constexpr int EPI_THREADS = 256;
 // CG = 2: a CTA pair (cluster of 2) works on two adjacent tiles with cta_group::2 (M = 256): each CTA stages its own 128
 //         activation rows and HALF of every weight tile, so both the TMA fill and the MMA operand reads of shared memory
 //         drop from 192 to 128 B/clk per SM (shared memory delivers 128 B/clk, which capped CG = 1 at ~63 % tensor duty).
-template <int CG> struct Geo {
+// KIND 1 = k1_layer (biases live in registers: shared memory goes to a deeper TMA ring), KIND 2 = k2_head (1024 floats of
+// bias / partial-dot scratch in shared memory).
+template <int CG_, int KIND> struct Geo {
+  static constexpr int CG = CG_;
   static constexpr int B_ROWS = 256 / CG;
   static constexpr int B_BYTES = B_ROWS * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = CG == 1 ? 3 : 4;
+  static constexpr int NSTAGE = CG == 1 ? 3 : (KIND == 1 ? 5 : 4);
   static constexpr int OUT_OFF = NSTAGE * STAGE_BYTES;
-  static constexpr int BIAS_OFF = OUT_OFF + OUT_BYTES;   // 1024 floats
-  static constexpr int BAR_OFF = BIAS_OFF + 4096;
+  static constexpr int BIAS_OFF = OUT_OFF + OUT_BYTES;
+  static constexpr int BAR_OFF = BIAS_OFF + (KIND == 1 ? 0 : 4096);
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + slack to align the base to 1024 B
   static constexpr uint32_t IDESC = umma_idesc_bf16_f32(128 * CG, 256);
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+  static_assert(NSTAGE <= 5, "barrier table holds at most 5 stages");
 };
-enum { BAR_FULL = 0, BAR_EMPTY = 4, BAR_ACC_FULL = 8, BAR_ACC_EMPTY = 10, BAR_OUT_READY = 12, BAR_UC_FULL = 14, BAR_COUNT = 15 };
+enum { BAR_FULL = 0, BAR_EMPTY = 5, BAR_ACC_FULL = 10, BAR_ACC_EMPTY = 12, BAR_OUT_READY = 14, BAR_UC_FULL = 16, BAR_COUNT = 17 };
 
 // Per-CTA view of the barrier array and the pair topology
-template <int CG> struct Ctx {
+template <class G> struct Ctx {
+  static constexpr int CG = G::CG;
   uint32_t base, bars, lbars, rank;
   __device__ __forceinline__ uint32_t bar(int i) const { return bars + 8u * i; }    // local barrier (shared::cta)
   __device__ __forceinline__ uint32_t lbar(int i) const { return lbars + 8u * i; }  // leader's barrier (shared::cluster)
-  __device__ __forceinline__ uint32_t stage_a(uint32_t s) const { return base + s * Geo<CG>::STAGE_BYTES; }
-  __device__ __forceinline__ uint32_t stage_b(uint32_t s) const { return base + s * Geo<CG>::STAGE_BYTES + A_BYTES; }
-  __device__ __forceinline__ uint32_t out_kb(int kb) const { return base + Geo<CG>::OUT_OFF + kb * A_BYTES; }
+  __device__ __forceinline__ uint32_t stage_a(uint32_t s) const { return base + s * G::STAGE_BYTES; }
+  __device__ __forceinline__ uint32_t stage_b(uint32_t s) const { return base + s * G::STAGE_BYTES + A_BYTES; }
+  __device__ __forceinline__ uint32_t out_kb(int kb) const { return base + G::OUT_OFF + kb * A_BYTES; }
   // consumer -> MMA issuer signals (the issuer lives in the leader CTA)
   __device__ __forceinline__ void arrive_leader(int i) const {
     if (CG == 1) mbar_arrive(bar(i));
@@ -83,15 +89,15 @@ template <int CG> struct Ctx {
   // weight tile: this CTA's B_ROWS rows starting at row0 (+ rank * B_ROWS)
   __device__ __forceinline__ void load_b(uint32_t s, const CUtensorMap* m, int k0, int row0) const {
     if (CG == 1) tma_load_2d(stage_b(s), m, bar(BAR_FULL + s), k0, row0);
-    else tma_load_2d_pair(stage_b(s), m, lbar(BAR_FULL + s), k0, row0 + static_cast<int>(rank) * Geo<CG>::B_ROWS);
+    else tma_load_2d_pair(stage_b(s), m, lbar(BAR_FULL + s), k0, row0 + static_cast<int>(rank) * G::B_ROWS);
   }
   // issue the 4 MMAs (K = 16 each) of one 64-wide K-block
   __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, bool first) const {
     const uint64_t ad = umma_desc_k_sw128(a_smem), bd = umma_desc_k_sw128(b_smem);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (CG == 1) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, Geo<CG>::IDESC, (first && k == 0) ? 0u : 1u);
-      else umma_bf16_pair(d_tmem, ad + 2 * k, bd + 2 * k, Geo<CG>::IDESC, (first && k == 0) ? 0u : 1u);
+      if (CG == 1) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, G::IDESC, (first && k == 0) ? 0u : 1u);
+      else umma_bf16_pair(d_tmem, ad + 2 * k, bd + 2 * k, G::IDESC, (first && k == 0) ? 0u : 1u);
     }
   }
   __device__ __forceinline__ void commit(int i) const {   // MMA issuer -> barrier i of every CTA of the pair
@@ -101,17 +107,18 @@ template <int CG> struct Ctx {
 };
 
 // common prologue: barrier init, TMEM allocation, cluster handshake.  Returns the TMEM base address.
-template <int CG> __device__ __forceinline__ uint32_t tc_prologue(Ctx<CG>& cx, uint8_t*& gen, int out_ready_count) {
+template <class G> __device__ __forceinline__ uint32_t tc_prologue(Ctx<G>& cx, uint8_t*& gen, int out_ready_count) {
+  constexpr int CG = G::CG;
   extern __shared__ uint8_t smem_raw[];
   cx.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   gen = smem_raw + (cx.base - smem_u32(smem_raw));
-  cx.bars = cx.base + Geo<CG>::BAR_OFF;
+  cx.bars = cx.base + G::BAR_OFF;
   cx.rank = CG == 1 ? 0u : cluster_ctarank();
   cx.lbars = CG == 1 ? cx.bars : mapa_cluster(cx.bars, 0);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + Geo<CG>::BAR_OFF + 8 * BAR_COUNT);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + G::BAR_OFF + 8 * BAR_COUNT);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Geo<CG>::NSTAGE; ++i) mbar_init(cx.bar(BAR_FULL + i), CG), mbar_init(cx.bar(BAR_EMPTY + i), 1);
+    for (int i = 0; i < G::NSTAGE; ++i) mbar_init(cx.bar(BAR_FULL + i), CG), mbar_init(cx.bar(BAR_EMPTY + i), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(cx.bar(BAR_ACC_FULL + i), 1);
       mbar_init(cx.bar(BAR_ACC_EMPTY + i), 8 * CG);
@@ -164,13 +171,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUtensorMap tmUout,
          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWd,
          const __grid_constant__ CUtensorMap tmWr, const K1Params p) {
-  using G = Geo<CG>;
-  Ctx<CG> cx;
+  using G = Geo<CG, 1>;
+  Ctx<G> cx;
   uint8_t* gen;
-  const uint32_t tmem = tc_prologue<CG>(cx, gen, 1);
-  float* s_bias = reinterpret_cast<float*>(gen + G::BIAS_OFF);   // [0,512) b_dil, [512,768) b_res, [768,1024) p_next
-  for (int i = threadIdx.x; i < 1024; i += NTHREADS)
-    s_bias[i] = i < 512 ? p.b_dil[i] : (i < 768 ? p.b_res[i - 512] : p.p_next[i - 768]);
+  const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
   if (threadIdx.x == 0)
     prefetch_tmap(&tmUin), prefetch_tmap(&tmUout), prefetch_tmap(&tmO), prefetch_tmap(&tmWd), prefetch_tmap(&tmWr);
   __syncthreads();
@@ -256,6 +260,19 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t row_off = row * 128, sw = row & 7;
     const float sqrt_half = 0.70710678118654752440f;
+    // per-channel constants live in registers, one channel per lane, and are broadcast with warp shuffles:
+    //   bd_t/bd_s[j][gq]: dilated-conv bias of tanh / sigmoid channel j*128 + hsel*64 + gq*32 + lane
+    //   br/pn[gq]       : res-conv bias and next-layer step-embedding projection of channel hsel*128 + gq*32 + lane
+    float bd_t[2][2], bd_s[2][2], br_r[4], pn_r[4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int gq = 0; gq < 2; ++gq) {
+        bd_t[j][gq] = p.b_dil[j * 256 + hsel * 64 + gq * 32 + lane];
+        bd_s[j][gq] = p.b_dil[j * 256 + 128 + hsel * 64 + gq * 32 + lane];
+      }
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) br_r[gq] = p.b_res[hsel * 128 + gq * 32 + lane], pn_r[gq] = p.p_next[hsel * 128 + gq * 32 + lane];
     uint32_t g = 0, ti = 0;
     long long w_accfull = 0, w_uc = 0, w_bar = 0;
     const long long t_start = clock64();
@@ -272,9 +289,9 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
           named_bar_sync(1, EPI_THREADS);
         }
         const uint32_t kb_base = cx.out_kb(2 * j + hsel) + row_off;
-        const float* bt = s_bias + j * 256 + hsel * 64;       // tanh-half bias; sigmoid half is +128
-#pragma unroll 1
+#pragma unroll
         for (int gq = 0; gq < 2; ++gq) {
+          const float bt_l = j == 0 ? bd_t[0][gq] : bd_t[1][gq], bs_l = j == 0 ? bd_s[0][gq] : bd_s[1][gq];
           uint32_t ta[32], sg[32];
           tmem_ld_32x32b_x32(lane_addr + r * 256 + hsel * 64 + gq * 32, ta);
           tmem_ld_32x32b_x32(lane_addr + r * 256 + 128 + hsel * 64 + gq * 32, sg);
@@ -284,9 +301,11 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int c0 = gq * 32 + i * 8 + 2 * e;
-              const float a0 = __uint_as_float(ta[i * 8 + 2 * e]) + bt[c0], a1 = __uint_as_float(ta[i * 8 + 2 * e + 1]) + bt[c0 + 1];
-              const float s0 = __uint_as_float(sg[i * 8 + 2 * e]) + bt[128 + c0], s1 = __uint_as_float(sg[i * 8 + 2 * e + 1]) + bt[128 + c0 + 1];
+              const int c0 = i * 8 + 2 * e;
+              const float a0 = __uint_as_float(ta[c0]) + __shfl_sync(0xffffffffu, bt_l, c0);
+              const float a1 = __uint_as_float(ta[c0 + 1]) + __shfl_sync(0xffffffffu, bt_l, c0 + 1);
+              const float s0 = __uint_as_float(sg[c0]) + __shfl_sync(0xffffffffu, bs_l, c0);
+              const float s1 = __uint_as_float(sg[c0 + 1]) + __shfl_sync(0xffffffffu, bs_l, c0 + 1);
               pk[e] = pack_bf16x2(tanh_approx(a0) * sigmoid_approx(s0), tanh_approx(a1) * sigmoid_approx(s1));
             }
             st_shared_v4(kb_base + (((gq * 4 + i) ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -316,10 +335,9 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
           for (int kb = 0; kb < 4; ++kb) tma_load_3d(cx.out_kb(kb), &tmUin, cx.bar(BAR_UC_FULL), kb * 64, l0, b);
         }
         w_uc += mbar_wait(cx.bar(BAR_UC_FULL), ti & 1, 11);
-        const float* br = s_bias + 512 + hsel * 128;
-        const float* pn = s_bias + 768 + hsel * 128;
-#pragma unroll 1
+#pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
+          const float br_l = br_r[gq], pn_l = pn_r[gq];
           uint32_t acc[32];
           tmem_ld_32x32b_x32(lane_addr + r * 256 + hsel * 128 + gq * 32, acc);
           tmem_ld_wait();
@@ -332,9 +350,11 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int c0 = gq * 32 + i * 8 + 2 * e;
-              const float h0 = (bf16_lo(uw[e]) + (__uint_as_float(acc[i * 8 + 2 * e]) + br[c0])) * sqrt_half + pn[c0];
-              const float h1 = (bf16_hi(uw[e]) + (__uint_as_float(acc[i * 8 + 2 * e + 1]) + br[c0 + 1])) * sqrt_half + pn[c0 + 1];
+              const int c0 = i * 8 + 2 * e;
+              const float h0 = (bf16_lo(uw[e]) + (__uint_as_float(acc[c0]) + __shfl_sync(0xffffffffu, br_l, c0))) * sqrt_half +
+                               __shfl_sync(0xffffffffu, pn_l, c0);
+              const float h1 = (bf16_hi(uw[e]) + (__uint_as_float(acc[c0 + 1]) + __shfl_sync(0xffffffffu, br_l, c0 + 1))) * sqrt_half +
+                               __shfl_sync(0xffffffffu, pn_l, c0 + 1);
               pk[e] = pack_bf16x2(h0, h1);
             }
             st_shared_v4(addr, make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -377,10 +397,10 @@ template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWs,
         const __grid_constant__ CUtensorMap tmWf, const K2Params p) {
-  using G = Geo<CG>;
-  Ctx<CG> cx;
+  using G = Geo<CG, 2>;
+  Ctx<G> cx;
   uint8_t* gen;
-  const uint32_t tmem = tc_prologue<CG>(cx, gen, 1);
+  const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
   float* s_bias = reinterpret_cast<float*>(gen + G::BIAS_OFF);   // [0,256) bskip, [256,512) bf1, [512,768) wf2, [768,896) partial dots
   for (int i = threadIdx.x; i < 768; i += NTHREADS)
     s_bias[i] = i < 256 ? p.bskip[i] : (i < 512 ? p.bf1[i - 256] : p.wf2[i - 512]);
@@ -547,8 +567,8 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bars = base + Geo<1>::STAGE_BYTES;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + Geo<1>::STAGE_BYTES + 64);
+  const uint32_t bars = base + Geo<1, 1>::STAGE_BYTES;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + Geo<1, 1>::STAGE_BYTES + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(bars, 1), mbar_init(bars + 8, 1);
@@ -562,11 +582,11 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  Ctx<1> cx;
+  Ctx<Geo<1, 1>> cx;
   cx.base = base, cx.bars = bars, cx.lbars = bars, cx.rank = 0;
   if (threadIdx.x == 0) {
     for (int kb = 0; kb < K / 64; ++kb) {
-      mbar_expect_tx(bars, Geo<1>::STAGE_BYTES);
+      mbar_expect_tx(bars, Geo<1, 1>::STAGE_BYTES);
       tma_load_2d(base, &tmA, bars, kb * 64, 0);
       tma_load_2d(base + A_BYTES, &tmB, bars, kb * 64, 0);
       mbar_wait(bars, kb & 1, 40);
@@ -798,10 +818,10 @@ int tc_net_reserve(TcNet* n, int chunk, int L) {
   if (rc == AP_OK) rc = encode_bf16(&n->tmO, n->o.p, 3, dO, bx);
   if (rc != AP_OK) return rc;
   if (!n->attr_set) {
-    AP_CUDA(cudaFuncSetAttribute(k1_layer<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1>::SMEM_BYTES));
-    AP_CUDA(cudaFuncSetAttribute(k2_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1>::SMEM_BYTES));
-    AP_CUDA(cudaFuncSetAttribute(k1_layer<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2>::SMEM_BYTES));
-    AP_CUDA(cudaFuncSetAttribute(k2_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 1>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     n->attr_set = true;
   }
   return AP_OK;
@@ -847,10 +867,10 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     cudaEvent_t e0 = prof_event(n, 0), e1 = e0 ? prof_event(n, 0) : nullptr;
     if (e1) cudaEventRecord(e0, st);
     if (n->pair) {
-      AP_CUDA(launch_pair(k1_layer<2>, pair_grid(n_tiles), Geo<2>::SMEM_BYTES, st, n->tmU[l & 1], n->tmU[(l + 1) & 1], n->tmO,
+      AP_CUDA(launch_pair(k1_layer<2>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, n->tmU[l & 1], n->tmU[(l + 1) & 1], n->tmO,
                           n->tmWd2, n->tmWr2, p));
     } else {
-      k1_layer<1><<<grid, NTHREADS, Geo<1>::SMEM_BYTES, st>>>(n->tmU[l & 1], n->tmU[(l + 1) & 1], n->tmO, n->tmWd, n->tmWr, p);
+      k1_layer<1><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(n->tmU[l & 1], n->tmU[(l + 1) & 1], n->tmO, n->tmWd, n->tmWr, p);
     }
     if (e1) cudaEventRecord(e1, st);
     AP_LAUNCH_CHECK();
@@ -873,9 +893,9 @@ int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, i
   cudaEvent_t e0 = prof_event(n, 1), e1 = e0 ? prof_event(n, 1) : nullptr;
   if (e1) cudaEventRecord(e0, st);
   if (n->pair) {
-    AP_CUDA(launch_pair(k2_head<2>, pair_grid(n_tiles), Geo<2>::SMEM_BYTES, st, n->tmO, n->tmWs2, n->tmWf2, p));
+    AP_CUDA(launch_pair(k2_head<2>, pair_grid(n_tiles), Geo<2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs2, n->tmWf2, p));
   } else {
-    k2_head<1><<<grid, NTHREADS, Geo<1>::SMEM_BYTES, st>>>(n->tmO, n->tmWs, n->tmWf, p);
+    k2_head<1><<<grid, NTHREADS, Geo<1, 2>::SMEM_BYTES, st>>>(n->tmO, n->tmWs, n->tmWf, p);
   }
   if (e1) cudaEventRecord(e1, st);
   AP_LAUNCH_CHECK();
@@ -921,7 +941,7 @@ extern "C" int ap_selftest_umma(const uint16_t* a_bf16, const uint16_t* b_bf16, 
   rc = encode_bf16(&ta, a_bf16, 2, da, ba);
   if (rc == AP_OK) rc = encode_bf16(&tb, b_bf16, 2, db, bb);
   if (rc != AP_OK) return rc;
-  const int smem = Geo<1>::STAGE_BYTES + 128 + 1024;
+  const int smem = Geo<1, 1>::STAGE_BYTES + 128 + 1024;
   AP_CUDA(cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, d_out, K);
   AP_LAUNCH_CHECK();

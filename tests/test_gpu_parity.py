@@ -186,6 +186,50 @@ def test_wavenet_batch_chunking_and_mixed_steps(ap, sd_full):
     assert torch.equal(c[0::2], a[0::2]) and not torch.equal(c[1], a[1])
 
 
+@pytest.mark.parametrize("B,L", [(1, 100), (3, 129), (2, 4097)])
+def test_wavenet_edge_shapes_bf16_vs_fp32(ap, sd_full, B, L):
+    """single partial tile, one position past a tile boundary, odd tile counts (ragged CTA pairs) -- tensor-core path vs the
+    fp32 path (itself pinned to the reference at other shapes)"""
+    nets = {m: ap.WaveNet(sd_full, mode=m, **synthetic.DEFAULT_WAVENET_CONFIG) for m in ("fp32", "bf16")}
+    x = cuda(synthetic.synthetic_waveforms(B, L, seed=L))
+    e32, e16 = nets["fp32"].eps(x, 33.0), nets["bf16"].eps(x, 33.0)
+    assert torch.isfinite(e16).all() and rel_l2(e16, e32) < 1.2e-2
+
+
+def test_error_paths(ap, diffwave):
+    from audiopure_b200 import _lib
+    lib = _lib.load()
+    x = torch.zeros(2, 1, 256, device="cuda")
+    assert lib.ap_diffwave_eps(diffwave.model._handle, x.data_ptr(), 1.0, x.data_ptr(), 0, 256, None) == -1      # B == 0
+    assert b"positive" in lib.ap_last_error()
+    assert lib.ap_diffwave_eps(None, x.data_ptr(), 1.0, x.data_ptr(), 2, 256, None) == -1                          # null handle
+    assert lib.ap_vote_counts(x.data_ptr(), 4, 0, x.data_ptr(), None) == -1                                       # K == 0
+    with pytest.raises(_lib.AudioPureError):
+        ap.MelSpectrogramDB(n_fft=2048, hop_length=512, n_mels=32, pad_mode="reflect")(torch.zeros(1, 1, 512, device="cuda"))
+    with pytest.raises(AssertionError):
+        ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))(torch.zeros(1, 1, 16, 16, device="cuda"))
+
+
+def test_full_size_batch_properties(ap, sd_full):
+    """BASELINE configs[1] size (512 x 1 s, t* = 2, bf16, in-kernel noise): batch independence (rows of the big batch equal
+    the same rows purified alone with the same Philox offsets), determinism, and a bounded purification distance."""
+    dw = ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=2, state_dict=sd_full, noise="philox", seed=11)
+    B, L = 512, 16000
+    x = cuda(synthetic.synthetic_waveforms(B, L, seed=4321))
+    y = dw.purify(x)
+    dw._offset = 0
+    y2 = dw.purify(x)
+    assert torch.equal(y, y2)                                            # deterministic
+    assert torch.isfinite(y).all()
+    d = (y - x).flatten(1).norm(dim=1) / x.flatten(1).norm(dim=1)
+    assert d.max().item() < 0.6 and d.min().item() > 1e-3                # every waveform was diffused and denoised
+    # row r of a (B, L) Philox call uses counters offset + r*L/4 ..., so a single-row call at that offset reproduces it
+    for r in (0, 255, 511):
+        eps_full = dw.model.eps(x, 1.0)[r]
+        eps_one = dw.model.eps(x[r:r + 1], 1.0)[0]
+        assert torch.equal(eps_full, eps_one)                            # network output is batch independent, bit for bit
+
+
 def test_inference_only_and_cpu_inputs_raise(ap, diffwave):
     x = torch.zeros(1, 1, 256, device="cuda", requires_grad=True)
     with pytest.raises(ap.AudioPureError):

@@ -294,7 +294,11 @@ def run_ours(args):
             roofline = {"kernel": "k1_layer (DiffWave residual block: tcgen05 implicit GEMM K=768/N=512 + K=256/N=256, fused "
                                   "gate / residual epilogues)", "bound": "tensor", "achieved": achieved,
                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
-                        "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                        "traffic": 24.19e6 * avg_wf,
+                        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum = 3.097e9 B for a 128-waveform launch "
+                                          "(profiles/r01_k1_pair_ncu_full_summary.txt; algorithmic 3.146e9 B), scaled to this "
+                                          "run's waveforms per launch",
+                        "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                         "avg_launch_ms": k1_ms, "launches": int(prof_n[0]), "waveforms_per_launch": avg_wf,
                         "share_of_step": prof_ms[0] / ms,
                         "k2_head": {"avg_launch_ms": prof_ms[1] / max(prof_n[1], 1), "launches": int(prof_n[1]),

@@ -9,7 +9,7 @@ import importlib
 __version__ = "0.1.0"
 
 _LAZY = {
-    "calc_diffusion_hyperparams": "diffwave", "WaveNet": "diffwave", "DiffWave": "diffwave",
+    "calc_diffusion_hyperparams": "diffwave", "WaveNet": "diffwave", "DiffWave": "diffwave", "ReffWave": "diffwave",
     "create_diffwave_model": "diffwave",
     "RevDiffWave": "diffwave_sde", "RevVPSDE": "diffwave_sde",
     "MelSpectrogramDB": "transforms", "sc09_transform": "transforms", "kws_transform": "transforms",

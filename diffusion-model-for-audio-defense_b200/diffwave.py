@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import AP_MODE_BF16, AP_MODE_FP32, AudioPureError
 
-__all__ = ["calc_diffusion_hyperparams", "WaveNet", "DiffWave", "create_diffwave_model", "wavenet_weight_list"]
+__all__ = ["calc_diffusion_hyperparams", "WaveNet", "DiffWave", "ReffWave", "create_diffwave_model", "wavenet_weight_list"]
 
 
 def calc_diffusion_hyperparams(T: int, beta_0: float, beta_T: float) -> dict:
@@ -370,6 +370,26 @@ class DiffWave(torch.nn.Module):
                                                          coef.ctypes.data, None, self.seed, off, B, L, _lib.stream_ptr()),
                        "ap_diffwave_purify_ddpm")
         return out
+
+
+class ReffWave(DiffWave):
+    """Repeated diffuse + one-shot denoise (diffwave_ddpm.py:251-348): ``num_re`` rounds of
+    ``x <- one_shot_denoise(diffusion(x))`` at the fixed ``reverse_timestep``."""
+
+    def __init__(self, model: WaveNet, diffusion_hyperparams: dict, reverse_timestep: int = 200, num_re: int = 5,
+                 noise: str = "philox", seed: int = 0):
+        super().__init__(model, diffusion_hyperparams, reverse_timestep=reverse_timestep, noise=noise, seed=seed)
+        self.num_re = num_re
+
+    def diffusion(self, x_0):
+        return self._diffusion(x_0)
+
+    def forward(self, waveforms):
+        output = self._as_tensor(waveforms)
+        for _ in range(self.num_re):
+            output = self.diffusion(output)
+            output = self.one_shot_denoise(output)
+        return output
 
 
 def create_diffwave_model(model_path, config_path, reverse_timestep=25, state_dict: dict | None = None,

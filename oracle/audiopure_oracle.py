@@ -205,6 +205,14 @@ def two_shot_denoise(sd, x_t, hp, reverse_timestep: int, eps_fn=None, **wn_kw):
     return (x1 - c_eps * eps_fn(x1, 0)) / sqrt_alpha
 
 
+def reffwave_forward(sd, x0, hp, reverse_timestep: int, num_re: int, noise, eps_fn=None, **wn_kw):
+    """ReffWave.forward, diffwave_ddpm.py:272-283: num_re x (diffuse to t*, one-shot denoise)."""
+    x = _t(x0, torch.float32)
+    for _ in range(num_re):
+        x = one_shot_denoise(sd, ddpm_diffuse(x, hp, reverse_timestep, noise), hp, reverse_timestep, eps_fn=eps_fn, **wn_kw)
+    return x
+
+
 def fast_reverse_tables(hp, reverse_timestep: int, K: int = 3):
     """diffwave_ddpm.py:118-131: respaced K-step schedule (S, Alpha_new, Alpha_bar_new, Beta_tilde_new)."""
     ab = hp["Alpha_bar"]

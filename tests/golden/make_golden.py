@@ -134,6 +134,13 @@ def main():
         out["fastrev_t9_L1024"] = dw.fast_reverse(x.clone()).numpy()
         assert inj.i == 3
 
+    # ---- a11: ReffWave (repeated diffuse + one-shot denoise)
+    from diffusion_models.diffwave_ddpm import ReffWave
+    rw = ReffWave(model=net, diffusion_hyperparams=hp, reverse_timestep=5, num_re=2).eval()
+    with torch.no_grad(), NoiseInjector(2029) as inj:
+        out["reffwave_t5_re2_L1024"] = rw(x.clone()).numpy()
+        assert inj.i == 2
+
     # ---- a12: RevVPSDE drift / diffusion at solver times (sdeint itself is torchsde: absent)
     dw.reverse_timestep = 5
     sde = RevVPSDE(model=dw, score_type="guided_diffusion", beta_min=0.0001 * 200, beta_max=0.02 * 200, N=200,

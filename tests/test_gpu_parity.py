@@ -263,6 +263,17 @@ def test_ddpm_purifier_vs_reference_golden(diffwave, golden, mode):
         assert rel_l2(diffwave.fast_reverse(x), golden["fastrev_t9_L1024"]) < TOL[mode]
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_reffwave_vs_reference_golden(ap, golden, diffwave, mode):
+    diffwave.model.set_mode(mode)
+    rw = ap.ReffWave(diffwave.model, diffwave.diffusion_hyperparams, reverse_timestep=5, num_re=2, noise="torch")
+    x = cuda(synthetic.synthetic_waveforms(2, 1024, seed=1234))
+    with TorchNormalInjector(2029) as inj:
+        y = rw(x)
+        assert inj.i == 2
+    assert rel_l2(y, golden["reffwave_t5_re2_L1024"]) < TOL[mode]
+
+
 def test_purify_entry_point_philox(ap, sd_full):
     """ap_diffwave_purify_ddpm (whole purifier in one call) == the step-by-step API on the same Philox stream."""
     dw = ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=3, state_dict=sd_full, noise="philox", seed=7)

@@ -180,3 +180,9 @@ def test_resnet_family(golden, depth):
     logits = orc.resnet_forward(sd, golden["mel_sc09"], depth=depth).numpy()
     want = golden[f"resnet{depth}_logits"]
     assert np.abs(logits - want).max() < 1e-4 * max(1.0, np.abs(want).max())
+
+
+def test_reffwave(golden, sd_full, hp):
+    x = synthetic.synthetic_waveforms(2, 1024, seed=1234)
+    y = orc.reffwave_forward(sd_full, x, hp, 5, 2, noise_list(2029, 2, x.shape)).numpy()
+    assert rel_l2(y, golden["reffwave_t5_re2_L1024"]) < 1e-5

@@ -425,3 +425,41 @@ def test_certify_philox_end_to_end(ap, diffwave):
     assert abs(rc.lower_conf_bound(99000, 100000) - 0.988989) < 1e-5
     assert abs(rc.lower_conf_bound(100000, 100000) - 0.999931) < 1e-5
     assert rc.lower_conf_bound(50200, 100000) < 0.5 + 1e-3
+
+
+@pytest.mark.parametrize("B", [1, 8])
+def test_cuda_graph_capture_and_replay(ap, sd_full, B):
+    """The whole purify -> mel -> classify pipeline is free of host synchronisation and hidden allocation after warm-up, so
+    it can be captured in a CUDA graph and replayed (small-batch query serving)."""
+    dw = ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=2, state_dict=sd_full, noise="philox", seed=3)
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    system = ap.AcousticSystem(classifier=rx, transform=ap.sc09_transform(), defender=dw.purify, defense_type="wave",
+                               check_int16_range=False)
+    x = cuda(synthetic.synthetic_waveforms(B, 16000, seed=77))
+    dw._offset = 0
+    want = system(x)                       # warm-up: workspaces, tensor maps, kernel attributes
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    dw._offset = 0                         # the Philox offsets are baked into the captured launches
+    with torch.cuda.graph(g):
+        got = system(x)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    x.copy_(cuda(synthetic.synthetic_waveforms(B, 16000, seed=78)))     # new input, same graph
+    g.replay()
+    torch.cuda.synchronize()
+    dw._offset = 0
+    assert torch.equal(got, system(x))
+    def timeit(fn, n=5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    def eager():
+        dw._offset = 0
+        system(x)
+    print(f"B={B}: eager {timeit(eager):.2f} ms, graph replay {timeit(g.replay):.2f} ms per query batch")

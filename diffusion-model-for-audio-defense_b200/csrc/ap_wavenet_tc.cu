@@ -274,7 +274,7 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
 #pragma unroll
     for (int gq = 0; gq < 4; ++gq) br_r[gq] = p.b_res[hsel * 128 + gq * 32 + lane], pn_r[gq] = p.p_next[hsel * 128 + gq * 32 + lane];
     uint32_t g = 0, ti = 0;
-    long long w_accfull = 0, w_uc = 0, w_bar = 0;
+    long long w_accfull = 0, w_uc = 0;
     const long long t_start = clock64();
     for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
       const bool valid = tile < p.n_tiles;
@@ -375,7 +375,7 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
     if (etid == 0) bulk_wait_all<0>();
     if (p.dbg && etid == 0) {
       long long* d = p.dbg + blockIdx.x * 16;
-      d[7] = w_accfull, d[8] = w_uc, d[9] = clock64() - t_start, d[10] = w_bar;
+      d[7] = w_accfull, d[8] = w_uc, d[9] = clock64() - t_start;
     }
   }
   tc_epilogue_teardown<CG>(tmem);

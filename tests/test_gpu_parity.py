@@ -408,6 +408,37 @@ def test_smooth_predict_counts_vs_reference_golden(ap, golden, diffwave):
     assert [rc.compute_t_star(1 / (1 + s ** 2)) for s in (0.25, 0.5, 1.0)] == list(golden["smooth_t_star"])
 
 
+def test_sharded_draws_equal_single_rank(ap, diffwave):
+    """Rank r of W draws slice r of the SAME Philox stream: the per-rank vote vectors of an emulated 3-rank run (ranks
+    executed one after the other on this GPU, no process group) add up to the single-rank counts exactly."""
+    diffwave.model.set_mode("bf16")
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    tr = ap.sc09_transform()
+    x1 = cuda(synthetic.synthetic_waveforms(1, 16000, seed=31))
+
+    class Emulated(ap.RobustCertificate):
+        world, rank = 1, 0
+
+        def _world(self):
+            return self.world, self.rank
+
+        def forward(self, x_in):                                   # checksum of every noisy copy, in draw order
+            self.seen.append(x_in.double().sum(dim=(1, 2)).cpu())
+            return super().forward(x_in)
+
+    def run(world, rank, batch):
+        rc = Emulated(classifier=rx, transform=tr, denoiser=diffwave, num_classes=10, seed=17, distributed=False)
+        rc.world, rc.rank, rc.seen = world, rank, []
+        c = rc.smooth_predict(x1, num_sampling=50, sigma=1.0, batch_size=batch)
+        return c, torch.cat(rc.seen)
+
+    whole, sums = run(1, 0, 32)
+    parts = [run(3, r, 7) for r in range(3)]                       # 17 + 17 + 16 draws, ragged batches of 7
+    assert int(whole.sum()) == 50 and torch.equal(whole, sum(c for c, _ in parts))
+    assert torch.equal(sums, torch.cat([s_ for _, s_ in parts]))   # draw i sees the same noise whichever rank takes it
+    assert sums.unique().numel() == 50                             # and every draw is different
+
+
 def test_certify_philox_end_to_end(ap, diffwave):
     diffwave.model.set_mode("bf16")
     rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))

@@ -16,7 +16,7 @@ _LAZY = {
     "ResNeXtClassifier": "classifiers", "ResNetClassifier": "classifiers", "M5Classifier": "classifiers", "KWSClassifier": "classifiers",
     "create_model": "classifiers",
     "AcousticSystem": "acoustic_system",
-    "RobustCertificate": "certify",
+    "RobustCertificate": "certify", "certify_dataset": "certify",
     "AudioPureError": "_lib",
 }
 

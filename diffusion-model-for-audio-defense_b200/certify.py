@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["RobustCertificate", "shard_draws", "reduce_counts"]
+__all__ = ["RobustCertificate", "shard_draws", "reduce_counts", "certify_dataset"]
 
 
 def shard_draws(n: int, world_size: int, rank: int):
@@ -151,3 +151,33 @@ class RobustCertificate:
 
     def certified_robust_correct(self, y_pred, y_target, r_c, r: float = 1.0):
         return sum(1 for i in range(len(y_pred)) if y_pred[i] == y_target[i] and r_c[i] >= r)
+
+
+def certify_dataset(rc: RobustCertificate, batches, sigma: float, num_sampling: int = 100000, n_0: int = 100,
+                    alpha: float = 0.001, batch_size: int = 512, save_path: str | None = None):
+    """The dataset loop of certified_robustness_eval.py:110-146: certify every input of every batch and keep the
+    reference's record format ``{'id', 'y_true', 'y_pred', 'certified_radius'}``; the JSON file
+    ``<save_path>/sigma=<s>/sigma=<s>_N=<n>.json`` is rewritten after every batch (the reference's resume-by-inspection
+    behaviour).  ``batches`` yields ``(waveforms (B,1,L) or (B,L), targets (B,))`` or dicts with 'samples' / 'target'.
+    Under torch.distributed every rank takes part in every decision (sharded draws); rank 0 writes the file."""
+    import json
+    import os
+    records, total = [], 0
+    is_rank0 = not (torch.distributed.is_available() and torch.distributed.is_initialized()) or torch.distributed.get_rank() == 0
+    for batch in batches:
+        waveforms, targets = (batch["samples"], batch["target"]) if isinstance(batch, dict) else batch
+        if waveforms.ndim == 2:
+            waveforms = torch.unsqueeze(waveforms, 1)
+        waveforms, targets = waveforms.cuda(), targets.cuda()
+        y_cert, r_cert = rc.certify(x=waveforms, y=targets, sigma=sigma, n_0=n_0, n=num_sampling, alpha=alpha,
+                                    batch_size=batch_size)
+        for i in range(waveforms.shape[0]):
+            records.append({"id": i + total, "y_true": targets[i].item(), "y_pred": y_cert[i].item(),
+                            "certified_radius": r_cert[i].item()})
+        total += waveforms.shape[0]
+        if save_path is not None and is_rank0:
+            d = os.path.join(save_path, "sigma={}".format(sigma))
+            os.makedirs(d, exist_ok=True)
+            with open(os.path.join(d, "sigma={}_N={}.json".format(sigma, num_sampling)), "w") as f:
+                json.dump(records, f, indent=4)
+    return records

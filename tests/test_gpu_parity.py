@@ -439,6 +439,21 @@ def test_sharded_draws_equal_single_rank(ap, diffwave):
     assert sums.unique().numel() == 50                             # and every draw is different
 
 
+def test_certify_dataset_records(ap, diffwave, tmp_path):
+    import json
+    diffwave.model.set_mode("bf16")
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    rc = ap.RobustCertificate(classifier=rx, transform=ap.sc09_transform(), denoiser=diffwave, num_classes=10, seed=2)
+    xs = torch.from_numpy(synthetic.synthetic_waveforms(3, 16000, seed=5))
+    batches = [{"samples": xs[:2, 0], "target": torch.tensor([6, 1])}, (xs[2:], torch.tensor([6]))]
+    recs = ap.certify_dataset(rc, batches, sigma=0.5, num_sampling=64, n_0=16, batch_size=32, save_path=str(tmp_path))
+    assert [r["id"] for r in recs] == [0, 1, 2] and set(recs[0]) == {"id", "y_true", "y_pred", "certified_radius"}
+    on_disk = json.load(open(tmp_path / "sigma=0.5" / "sigma=0.5_N=64.json"))
+    assert on_disk == recs
+    for r in recs:
+        assert (r["y_pred"] == -1 and r["certified_radius"] == 0) or (0 <= r["y_pred"] < 10 and r["certified_radius"] > 0)
+
+
 def test_certify_philox_end_to_end(ap, diffwave):
     diffwave.model.set_mode("bf16")
     rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))

@@ -439,6 +439,25 @@ def test_sharded_draws_equal_single_rank(ap, diffwave):
     assert sums.unique().numel() == 50                             # and every draw is different
 
 
+def test_philox_counts_agree_with_reference_noise_within_binomial_tolerance(ap):
+    """Vote counts drawn with the in-kernel Philox generator vs the reference's torch.normal CPU noise (pure randomized
+    smoothing, denoiser=None -- 'randsmooth' in certified_robustness_eval.py:96-97) on an input / classifier pair whose votes
+    split between two classes: the two count vectors are independent samples of the same multinomial."""
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=1))
+    tr = ap.sc09_transform()
+    x1 = cuda(synthetic.synthetic_waveforms(1, 16000, seed=31))
+    n = 600
+    torch.manual_seed(0)
+    c_ref = ap.RobustCertificate(rx, tr, denoiser=None, noise="torch").smooth_predict(x1, n, sigma=0.5, batch_size=200)
+    c_phx = ap.RobustCertificate(rx, tr, denoiser=None, noise="philox", seed=99).smooth_predict(x1, n, sigma=0.5, batch_size=150)
+    print("votes torch.normal:", c_ref.tolist(), " votes philox:", c_phx.tolist())
+    assert int(c_ref.sum()) == n and int(c_phx.sum()) == n
+    assert int(c_ref.max()) < 0.95 * n                                   # a real split, not a degenerate vote
+    p = c_ref.double() / n
+    tol = 4.0 * torch.sqrt(2 * n * p * (1 - p)) + 3                      # 4 sigma of the difference of two binomials
+    assert bool(((c_ref - c_phx).abs().double() <= tol).all())
+
+
 def test_certify_dataset_records(ap, diffwave, tmp_path):
     import json
     diffwave.model.set_mode("bf16")

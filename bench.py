@@ -39,7 +39,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=512, help="waveforms per GPU per step")
-    p.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    p.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32"])
     p.add_argument("--chunk", type=int, default=0, help="waveforms per workspace chunk (0 = library default)")
     p.add_argument("--certify-draws", type=int, default=4096, help="extra certification leg (0 = skip)")
     p.add_argument("--cpu-sample", type=int, default=2, help="waveforms in the cpu_baseline sample (0 = skip)")
@@ -229,7 +229,7 @@ def run_ours(args):
     def timed(fn, steps, profile=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if profile and args.mode == "bf16":
+        if profile and args.mode != "fp32":
             lib.ap_diffwave_profile(dw.model._handle, 1)
         l0 = _lib.launch_count()
         e0.record()
@@ -254,7 +254,7 @@ def run_ours(args):
     ms, launches = timed(step_resident, args.steps, profile=True)
     clocks = sampler.stop() if rank == 0 else None
     prof_ms, prof_n = (C.c_double * 2)(), (C.c_int * 2)()
-    if args.mode == "bf16":
+    if args.mode != "fp32":
         _lib.check(lib.ap_diffwave_profile_read(dw.model._handle, prof_ms, prof_n), "profile_read")
         lib.ap_diffwave_profile(dw.model._handle, 0)
     value = world * B * args.steps / (ms / 1e3)
@@ -285,7 +285,7 @@ def run_ours(args):
     if rank == 0:
         peaks = measured_peaks()
         roofline = None
-        if args.mode == "bf16" and prof_n[0] > 0:
+        if args.mode != "fp32" and prof_n[0] > 0:
             k1_ms = prof_ms[0] / prof_n[0]
             # launches over the last (ragged) chunk process fewer waveforms: use the exact average per launch
             n_layers, evals = 36, args.t_star * args.steps

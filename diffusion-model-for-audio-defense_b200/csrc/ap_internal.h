@@ -24,6 +24,7 @@ int vote(const float* logits, int B, int K, long long* counts, int* pred, cudaSt
 struct TcNet;
 int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* weights);
 void tc_net_destroy(TcNet* n);
+void tc_net_set_dtype(TcNet* n, int dt);   // 0: bf16 operands, 1: fp16 operands (same kernels, same speed)
 // (re)allocate the activation workspace for `chunk` waveforms of length L and encode the TMA tensor maps
 int tc_net_reserve(TcNet* n, int chunk, int L);
 size_t tc_net_workspace_bytes(const TcNet* n);

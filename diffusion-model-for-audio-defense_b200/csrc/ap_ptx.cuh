@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace ap { namespace ptx {
@@ -123,6 +124,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+// fp16 variants (AP_MODE_FP16): saturating conversion, so an out-of-range activation becomes +-65504 instead of inf
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float f16_lo(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xffffu))); }
+__device__ __forceinline__ float f16_hi(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16))); }
+// DT = 0: bf16, DT = 1: fp16
+template <int DT> __device__ __forceinline__ uint32_t pack2(float lo, float hi) { return DT == 0 ? pack_bf16x2(lo, hi) : pack_f16x2(lo, hi); }
+template <int DT> __device__ __forceinline__ float unpack_lo(uint32_t v) { return DT == 0 ? bf16_lo(v) : f16_lo(v); }
+template <int DT> __device__ __forceinline__ float unpack_hi(uint32_t v) { return DT == 0 ? bf16_hi(v) : f16_hi(v); }
 
 // ------------------------------------------------------------------ TMEM allocation (one full warp executes these)
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -202,6 +215,10 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// same with fp16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

@@ -314,9 +314,10 @@ extern "C" void ap_diffwave_destroy(ap_diffwave_t h) {
 
 extern "C" int ap_diffwave_set_mode(ap_diffwave_t h, int mode) {
   AP_REQUIRE(h, "ap_diffwave_set_mode: null handle");
-  AP_REQUIRE(mode == AP_MODE_BF16 || mode == AP_MODE_FP32, "ap_diffwave_set_mode: unknown mode %d", mode);
-  if (mode == AP_MODE_BF16 && !h->tc_capable)
-    return fail(AP_ERR_INVALID, "ap_diffwave_set_mode: the bf16 tensor-core kernels need res_channels == skip_channels == 256");
+  AP_REQUIRE(mode == AP_MODE_BF16 || mode == AP_MODE_FP32 || mode == AP_MODE_FP16, "ap_diffwave_set_mode: unknown mode %d", mode);
+  if (mode != AP_MODE_FP32 && !h->tc_capable)
+    return fail(AP_ERR_INVALID, "ap_diffwave_set_mode: the tensor-core kernels need res_channels == skip_channels == 256");
+  if (mode != AP_MODE_FP32) tc_net_set_dtype(h->tc, mode == AP_MODE_FP16);
   h->mode = mode;
   return AP_OK;
 }
@@ -325,7 +326,7 @@ extern "C" int ap_diffwave_get_mode(ap_diffwave_t h) { return h ? h->mode : AP_E
 extern "C" int ap_diffwave_reserve(ap_diffwave_t h, int chunk, int L) {
   AP_REQUIRE(h && chunk > 0 && L > 0, "ap_diffwave_reserve: bad arguments");
   AP_CUDA(cudaSetDevice(h->device));
-  if (h->mode == AP_MODE_BF16) {
+  if (h->mode != AP_MODE_FP32) {
     if (h->tc_chunk == chunk && h->tc_L == L) return AP_OK;
     int rc = tc_net_reserve(h->tc, chunk, L);
     if (rc != AP_OK) return rc;
@@ -404,7 +405,7 @@ extern "C" int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* 
   AP_REQUIRE(B > 0 && L > 0, "ap_diffwave_eps: B and L must be positive (got %d, %d)", B, L);
   AP_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool tc = h->mode == AP_MODE_BF16;
+  const bool tc = h->mode != AP_MODE_FP32;
   int chunk = tc ? h->tc_chunk : h->chunk;
   const int curL = tc ? h->tc_L : h->L;
   if (chunk == 0 || curL != L) {
@@ -466,7 +467,7 @@ extern "C" int ap_diffwave_debug_layer(ap_diffwave_t h, const float* x, float t,
   if (rc != AP_OK) return rc;
   rc = step_embedding(h, t, st);
   if (rc != AP_OK) return rc;
-  if (h->mode == AP_MODE_BF16) return tc_net_debug_layer(h->tc, x, h->ptab.as<float>(), layer, u_next, gate, B, L, st);
+  if (h->mode != AP_MODE_FP32) return tc_net_debug_layer(h->tc, x, h->ptab.as<float>(), layer, u_next, gate, B, L, st);
   rc = eps_fp32_chunk(h, x, nullptr, B, L, st, layer);
   if (rc != AP_OK) return rc;
   const size_t bytes = static_cast<size_t>(B) * L * h->cfg.res_channels * sizeof(float);

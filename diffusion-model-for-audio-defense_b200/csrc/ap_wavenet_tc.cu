@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "ap_common.cuh"
 #include "ap_conv_tc.h"
@@ -44,8 +45,9 @@ constexpr int EPI_THREADS = 256;
 //         drop from 192 to 128 B/clk per SM (shared memory delivers 128 B/clk, which capped CG = 1 at ~63 % tensor duty).
 // KIND 1 = k1_layer (biases live in registers: shared memory goes to a deeper TMA ring), KIND 2 = k2_head (1024 floats of
 // bias / partial-dot scratch in shared memory).
-template <int CG_, int KIND> struct Geo {
+template <int CG_, int KIND, int DT_ = 0> struct Geo {
   static constexpr int CG = CG_;
+  static constexpr int DT = DT_;   // 0: bf16 operands, 1: fp16 operands
   static constexpr int B_ROWS = 256 / CG;
   static constexpr int B_BYTES = B_ROWS * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -54,7 +56,7 @@ template <int CG_, int KIND> struct Geo {
   static constexpr int BIAS_OFF = OUT_OFF + OUT_BYTES;
   static constexpr int BAR_OFF = BIAS_OFF + (KIND == 1 ? 0 : 4096);
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + slack to align the base to 1024 B
-  static constexpr uint32_t IDESC = umma_idesc_bf16_f32(128 * CG, 256);
+  static constexpr uint32_t IDESC = DT_ == 0 ? umma_idesc_bf16_f32(128 * CG, 256) : umma_idesc_f16_f32(128 * CG, 256);
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
   static_assert(NSTAGE <= 5, "barrier table holds at most 5 stages");
 };
@@ -166,12 +168,12 @@ struct K1Params {
   long long* dbg;       // optional [gridDim.x][16] wait-cycle counters (development aid), or null
 };
 
-template <int CG>
+template <int CG, int DT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUtensorMap tmUout,
          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWd,
          const __grid_constant__ CUtensorMap tmWr, const K1Params p) {
-  using G = Geo<CG, 1>;
+  using G = Geo<CG, 1, DT>;
   Ctx<G> cx;
   uint8_t* gen;
   const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
@@ -306,7 +308,7 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
               const float a1 = __uint_as_float(ta[c0 + 1]) + __shfl_sync(0xffffffffu, bt_l, c0 + 1);
               const float s0 = __uint_as_float(sg[c0]) + __shfl_sync(0xffffffffu, bs_l, c0);
               const float s1 = __uint_as_float(sg[c0 + 1]) + __shfl_sync(0xffffffffu, bs_l, c0 + 1);
-              pk[e] = pack_bf16x2(tanh_approx(a0) * sigmoid_approx(s0), tanh_approx(a1) * sigmoid_approx(s1));
+              pk[e] = pack2<DT>(tanh_approx(a0) * sigmoid_approx(s0), tanh_approx(a1) * sigmoid_approx(s1));
             }
             st_shared_v4(kb_base + (((gq * 4 + i) ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
           }
@@ -351,11 +353,11 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c0 = i * 8 + 2 * e;
-              const float h0 = (bf16_lo(uw[e]) + (__uint_as_float(acc[c0]) + __shfl_sync(0xffffffffu, br_l, c0))) * sqrt_half +
+              const float h0 = (unpack_lo<DT>(uw[e]) + (__uint_as_float(acc[c0]) + __shfl_sync(0xffffffffu, br_l, c0))) * sqrt_half +
                                __shfl_sync(0xffffffffu, pn_l, c0);
-              const float h1 = (bf16_hi(uw[e]) + (__uint_as_float(acc[c0 + 1]) + __shfl_sync(0xffffffffu, br_l, c0 + 1))) * sqrt_half +
+              const float h1 = (unpack_hi<DT>(uw[e]) + (__uint_as_float(acc[c0 + 1]) + __shfl_sync(0xffffffffu, br_l, c0 + 1))) * sqrt_half +
                                __shfl_sync(0xffffffffu, pn_l, c0 + 1);
-              pk[e] = pack_bf16x2(h0, h1);
+              pk[e] = pack2<DT>(h0, h1);
             }
             st_shared_v4(addr, make_uint4(pk[0], pk[1], pk[2], pk[3]));
           }
@@ -393,11 +395,11 @@ struct K2Params {
 };
 enum { BAR2_S_READY = BAR_OUT_READY };
 
-template <int CG>
+template <int CG, int DT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWs,
         const __grid_constant__ CUtensorMap tmWf, const K2Params p) {
-  using G = Geo<CG, 2>;
+  using G = Geo<CG, 2, DT>;
   Ctx<G> cx;
   uint8_t* gen;
   const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
@@ -489,7 +491,7 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c0 = gq * 32 + i * 8 + 2 * e;
-            pk[e] = pack_bf16x2((__uint_as_float(acc[i * 8 + 2 * e]) + bs[c0]) * p.scale,
+            pk[e] = pack2<DT>((__uint_as_float(acc[i * 8 + 2 * e]) + bs[c0]) * p.scale,
                                 (__uint_as_float(acc[i * 8 + 2 * e + 1]) + bs[c0 + 1]) * p.scale);
           }
           st_shared_v4(kb_base + ((((gq & 1) * 4 + i) ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -529,7 +531,8 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
 
 // ------------------------------------------------------------------------------------------------ init conv (bf16 out)
 // u0[m][c] = bf16(max(w[c] x[m] + b[c], 0) + p0[c])      (WaveNet.py:147,13-19 and :84)
-__global__ void __launch_bounds__(256) init_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
+template <int DT>
+__global__ void __launch_bounds__(256) init_h16_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, const float* __restrict__ p0,
                                                         uint4* __restrict__ u, long long M) {
   __shared__ float sw[C], sb[C], sp[C];
@@ -546,17 +549,18 @@ __global__ void __launch_bounds__(256) init_bf16_kernel(const float* __restrict_
     for (int e = 0; e < 4; ++e) {
       const float v0 = fmaxf(fmaf(sw[c + 2 * e], xv, sb[c + 2 * e]), 0.f) + sp[c + 2 * e];
       const float v1 = fmaxf(fmaf(sw[c + 2 * e + 1], xv, sb[c + 2 * e + 1]), 0.f) + sp[c + 2 * e + 1];
-      pk[e] = pack_bf16x2(v0, v1);
+      pk[e] = pack2<DT>(v0, v1);
     }
     u[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
 // bf16 -> fp32 (debug dumps)
-__global__ void bf16_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long n) {
+template <int DT>
+__global__ void h16_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long n) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
-    out[i] = __uint_as_float(static_cast<uint32_t>(in[i]) << 16);
+    out[i] = unpack_lo<DT>(in[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ self test kernel
@@ -661,11 +665,14 @@ struct TcNet {
   ap_wavenet_cfg cfg{};
   int N = 0;
   DevBuf wd, wr, ws, wf;                                   // bf16 operands
+  DevBuf wd_h, wr_h, ws_h, wf_h;                           // fp16 operands (AP_MODE_FP16)
+  int dt = 0;                                              // 0: bf16, 1: fp16
   DevBuf bd, br, bskip, bf1, wf2, bf2, init_w, init_b;     // fp32 vectors
   DevBuf u0, u1, o;
   int chunk = 0, L = 0;
   CUtensorMap tmU[2], tmO, tmWd, tmWr, tmWs, tmWf;   // weight maps: box of 256 rows (one CTA per tile)
   CUtensorMap tmWd2, tmWr2, tmWs2, tmWf2;           // weight maps: box of 128 rows (CTA pairs, each CTA stages half)
+  CUtensorMap tmWd_h, tmWr_h, tmWs_h, tmWf_h, tmWd2_h, tmWr2_h, tmWs2_h, tmWf2_h;   // the same over the fp16 weights
   bool pair = true;                                 // cta_group::2 kernels (AP_TC_PAIR=0 selects the 1-CTA kernels)
   bool attr_set = false;
   // optional per-launch timing (bench.py roofline): CUDA events recorded on the launching stream around k1 / k2
@@ -730,6 +737,13 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
   const int N = n->N = cfg.num_res_layers;
   std::vector<uint16_t> wd(static_cast<size_t>(N) * 512 * 768), wr(static_cast<size_t>(N) * C * C), ws(wr.size()),
       wf(static_cast<size_t>(C) * C);
+  auto to_f16 = [](const std::vector<uint16_t>& bf, const std::vector<float>& src) {
+    (void)bf;
+    std::vector<uint16_t> out(src.size());
+    for (size_t i = 0; i < src.size(); ++i) out[i] = __half_as_ushort(__float2half_rn(src[i]));
+    return out;
+  };
+  std::vector<float> wd_f(wd.size()), wr_f(wr.size()), ws_f(ws.size()), wf_f(wf.size());
   std::vector<float> bd(static_cast<size_t>(N) * 512), br(static_cast<size_t>(N) * C), bskip(C, 0.f);
   std::vector<double> bsum(C, 0.0);
   for (int l = 0; l < N; ++l) {
@@ -740,7 +754,11 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
         bd[static_cast<size_t>(l) * 512 + j * 256 + r] = w[3][oc];
         uint16_t* dst = &wd[((static_cast<size_t>(l) * 2 + j) * 256 + r) * 768];
         for (int tap = 0; tap < 3; ++tap)
-          for (int c = 0; c < C; ++c) dst[tap * C + c] = f32_to_bf16_rne(w[2][(static_cast<size_t>(oc) * C + c) * 3 + tap]);
+          for (int c = 0; c < C; ++c) {
+            const float v = w[2][(static_cast<size_t>(oc) * C + c) * 3 + tap];
+            dst[tap * C + c] = f32_to_bf16_rne(v);
+            wd_f[((static_cast<size_t>(l) * 2 + j) * 256 + r) * 768 + tap * C + c] = v;
+          }
       }
     for (int o = 0; o < C; ++o) {
       br[static_cast<size_t>(l) * C + o] = w[5][o];
@@ -748,18 +766,24 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
       for (int c = 0; c < C; ++c) {
         wr[(static_cast<size_t>(l) * C + o) * C + c] = f32_to_bf16_rne(w[4][static_cast<size_t>(o) * C + c]);
         ws[(static_cast<size_t>(l) * C + o) * C + c] = f32_to_bf16_rne(w[6][static_cast<size_t>(o) * C + c]);
+        wr_f[(static_cast<size_t>(l) * C + o) * C + c] = w[4][static_cast<size_t>(o) * C + c];
+        ws_f[(static_cast<size_t>(l) * C + o) * C + c] = w[6][static_cast<size_t>(o) * C + c];
       }
     }
   }
   for (int o = 0; o < C; ++o) bskip[o] = static_cast<float>(bsum[o]);
   const float* const* tail = weights + 6 + 8 * N;
-  for (size_t i = 0; i < wf.size(); ++i) wf[i] = f32_to_bf16_rne(tail[0][i]);
+  for (size_t i = 0; i < wf.size(); ++i) wf[i] = f32_to_bf16_rne(tail[0][i]), wf_f[i] = tail[0][i];
   int rc = AP_OK;
 #define TRY(e) if (rc == AP_OK) rc = (e)
   TRY(upload_bf16(n->wd, wd));
   TRY(upload_bf16(n->wr, wr));
   TRY(upload_bf16(n->ws, ws));
   TRY(upload_bf16(n->wf, wf));
+  TRY(upload_bf16(n->wd_h, to_f16(wd, wd_f)));
+  TRY(upload_bf16(n->wr_h, to_f16(wr, wr_f)));
+  TRY(upload_bf16(n->ws_h, to_f16(ws, ws_f)));
+  TRY(upload_bf16(n->wf_h, to_f16(wf, wf_f)));
   TRY(upload_f32(n->bd, bd));
   TRY(upload_f32(n->br, br));
   TRY(upload_f32(n->bskip, bskip));
@@ -781,6 +805,14 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
     TRY(encode_bf16(&n->tmWr2, n->wr.p, 2, d2, bw2));
     TRY(encode_bf16(&n->tmWs2, n->ws.p, 2, d2, bw2));
     TRY(encode_bf16(&n->tmWf2, n->wf.p, 2, d3, bw2));
+    TRY(encode_bf16(&n->tmWd_h, n->wd_h.p, 2, d1, bw));
+    TRY(encode_bf16(&n->tmWr_h, n->wr_h.p, 2, d2, bw));
+    TRY(encode_bf16(&n->tmWs_h, n->ws_h.p, 2, d2, bw));
+    TRY(encode_bf16(&n->tmWf_h, n->wf_h.p, 2, d3, bw));
+    TRY(encode_bf16(&n->tmWd2_h, n->wd_h.p, 2, d1, bw2));
+    TRY(encode_bf16(&n->tmWr2_h, n->wr_h.p, 2, d2, bw2));
+    TRY(encode_bf16(&n->tmWs2_h, n->ws_h.p, 2, d2, bw2));
+    TRY(encode_bf16(&n->tmWf2_h, n->wf_h.p, 2, d3, bw2));
     const char* env = std::getenv("AP_TC_PAIR");
     if (env && env[0] == '0') n->pair = false;
     if (const char* e2 = std::getenv("AP_TC_DEBUG_LAYER")) n->dbg_layer = std::atoi(e2);
@@ -800,6 +832,7 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
 }
 
 void tc_net_destroy(TcNet* n) { delete n; }
+void tc_net_set_dtype(TcNet* n, int dt) { n->dt = dt ? 1 : 0; }
 
 size_t tc_net_workspace_bytes(const TcNet* n) { return n->u0.bytes + n->u1.bytes + n->o.bytes; }
 
@@ -818,10 +851,14 @@ int tc_net_reserve(TcNet* n, int chunk, int L) {
   if (rc == AP_OK) rc = encode_bf16(&n->tmO, n->o.p, 3, dO, bx);
   if (rc != AP_OK) return rc;
   if (!n->attr_set) {
-    AP_CUDA(cudaFuncSetAttribute(k1_layer<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 1>::SMEM_BYTES));
-    AP_CUDA(cudaFuncSetAttribute(k2_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 2>::SMEM_BYTES));
-    AP_CUDA(cudaFuncSetAttribute(k1_layer<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1>::SMEM_BYTES));
-    AP_CUDA(cudaFuncSetAttribute(k2_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 1>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 1>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     n->attr_set = true;
   }
   return AP_OK;
@@ -850,8 +887,12 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     long long blocks = ceil_div_ll(M * (C / 8), 256);
     const long long cap = static_cast<long long>(num_sms()) * 8;
     if (blocks > cap) blocks = cap;
-    init_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n->init_w.as<float>(), n->init_b.as<float>(), ptab,
-                                                                    n->u0.as<uint4>(), M);
+    if (n->dt == 0)
+      init_h16_kernel<0><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n->init_w.as<float>(), n->init_b.as<float>(), ptab,
+                                                                        n->u0.as<uint4>(), M);
+    else
+      init_h16_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n->init_w.as<float>(), n->init_b.as<float>(), ptab,
+                                                                        n->u0.as<uint4>(), M);
     AP_LAUNCH_CHECK();
   }
   const int tps = ceil_div(L, TILE_M), n_tiles = tps * B;
@@ -866,12 +907,15 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     p.dbg = (l == n->dbg_layer) ? n->dbg.as<long long>() : nullptr;
     cudaEvent_t e0 = prof_event(n, 0), e1 = e0 ? prof_event(n, 0) : nullptr;
     if (e1) cudaEventRecord(e0, st);
-    if (n->pair) {
-      AP_CUDA(launch_pair(k1_layer<2>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, n->tmU[l & 1], n->tmU[(l + 1) & 1], n->tmO,
-                          n->tmWd2, n->tmWr2, p));
-    } else {
-      k1_layer<1><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(n->tmU[l & 1], n->tmU[(l + 1) & 1], n->tmO, n->tmWd, n->tmWr, p);
-    }
+    const CUtensorMap &ui = n->tmU[l & 1], &uo = n->tmU[(l + 1) & 1];
+    if (n->pair && n->dt == 0)
+      AP_CUDA(launch_pair(k1_layer<2, 0>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, uo, n->tmO, n->tmWd2, n->tmWr2, p));
+    else if (n->pair)
+      AP_CUDA(launch_pair(k1_layer<2, 1>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, uo, n->tmO, n->tmWd2_h, n->tmWr2_h, p));
+    else if (n->dt == 0)
+      k1_layer<1, 0><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(ui, uo, n->tmO, n->tmWd, n->tmWr, p);
+    else
+      k1_layer<1, 1><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(ui, uo, n->tmO, n->tmWd_h, n->tmWr_h, p);
     if (e1) cudaEventRecord(e1, st);
     AP_LAUNCH_CHECK();
   }
@@ -892,11 +936,14 @@ int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, i
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   cudaEvent_t e0 = prof_event(n, 1), e1 = e0 ? prof_event(n, 1) : nullptr;
   if (e1) cudaEventRecord(e0, st);
-  if (n->pair) {
-    AP_CUDA(launch_pair(k2_head<2>, pair_grid(n_tiles), Geo<2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs2, n->tmWf2, p));
-  } else {
-    k2_head<1><<<grid, NTHREADS, Geo<1, 2>::SMEM_BYTES, st>>>(n->tmO, n->tmWs, n->tmWf, p);
-  }
+  if (n->pair && n->dt == 0)
+    AP_CUDA(launch_pair(k2_head<2, 0>, pair_grid(n_tiles), Geo<2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs2, n->tmWf2, p));
+  else if (n->pair)
+    AP_CUDA(launch_pair(k2_head<2, 1>, pair_grid(n_tiles), Geo<2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs2_h, n->tmWf2_h, p));
+  else if (n->dt == 0)
+    k2_head<1, 0><<<grid, NTHREADS, Geo<1, 2>::SMEM_BYTES, st>>>(n->tmO, n->tmWs, n->tmWf, p);
+  else
+    k2_head<1, 1><<<grid, NTHREADS, Geo<1, 2>::SMEM_BYTES, st>>>(n->tmO, n->tmWs_h, n->tmWf_h, p);
   if (e1) cudaEventRecord(e1, st);
   AP_LAUNCH_CHECK();
   return AP_OK;
@@ -913,11 +960,13 @@ int tc_net_debug_layer(TcNet* n, const float* x, const float* ptab, int layer, f
   const uint16_t* un = ((layer + 1) & 1) ? n->u1.as<uint16_t>() : n->u0.as<uint16_t>();
   const uint16_t* on = n->o.as<uint16_t>() + static_cast<size_t>(layer) * n->chunk * L * C;
   if (u_next) {
-    bf16_to_f32_kernel<<<num_sms() * 4, 256, 0, st>>>(un, u_next, cnt);
+    if (n->dt == 0) h16_to_f32_kernel<0><<<num_sms() * 4, 256, 0, st>>>(un, u_next, cnt);
+    else h16_to_f32_kernel<1><<<num_sms() * 4, 256, 0, st>>>(un, u_next, cnt);
     AP_LAUNCH_CHECK();
   }
   if (gate) {
-    bf16_to_f32_kernel<<<num_sms() * 4, 256, 0, st>>>(on, gate, cnt);
+    if (n->dt == 0) h16_to_f32_kernel<0><<<num_sms() * 4, 256, 0, st>>>(on, gate, cnt);
+    else h16_to_f32_kernel<1><<<num_sms() * 4, 256, 0, st>>>(on, gate, cnt);
     AP_LAUNCH_CHECK();
   }
   return AP_OK;

@@ -112,13 +112,13 @@ class WaveNet(torch.nn.Module):
 
     # -- arithmetic mode ------------------------------------------------------------------------------------------
     def set_mode(self, mode: str) -> "WaveNet":
-        m = {"bf16": AP_MODE_BF16, "fp32": AP_MODE_FP32}[mode]
+        m = {"bf16": AP_MODE_BF16, "fp32": AP_MODE_FP32, "fp16": _lib.AP_MODE_FP16}[mode]
         _lib.check(self._lib.ap_diffwave_set_mode(self._handle, m), "ap_diffwave_set_mode")
         return self
 
     @property
     def mode(self) -> str:
-        return "bf16" if self._lib.ap_diffwave_get_mode(self._handle) == AP_MODE_BF16 else "fp32"
+        return {AP_MODE_BF16: "bf16", AP_MODE_FP32: "fp32", _lib.AP_MODE_FP16: "fp16"}[self._lib.ap_diffwave_get_mode(self._handle)]
 
     def reserve(self, chunk: int, length: int) -> None:
         _lib.check(self._lib.ap_diffwave_reserve(self._handle, int(chunk), int(length)), "ap_diffwave_reserve")

@@ -33,6 +33,8 @@ extern "C" {
 /* arithmetic mode of the DiffWave network */
 #define AP_MODE_BF16 0 /* tcgen05 tensor cores: bf16 operands, fp32 accumulate (TMEM), fp32 x/update arithmetic */
 #define AP_MODE_FP32 1 /* fp32 FFMA path (parity mode, <=1e-5 rel-L2 vs the reference) */
+#define AP_MODE_FP16 3 /* DiffWave only: the same tcgen05 kernels with fp16 operands (11-bit mantissa: ~8x smaller eps error than
+                          bf16 at the same speed; conversions saturate at +-65504) */
 #define AP_MODE_TF32 2 /* classifiers only: tcgen05 kind::tf32 convolutions (the precision of the reference's cuDNN path) */
 
 typedef struct ap_diffwave_s* ap_diffwave_t;
@@ -75,7 +77,7 @@ typedef struct {
 int ap_diffwave_create(ap_diffwave_t* out, const ap_wavenet_cfg* cfg, const float* const* weights, int n_weights,
                        int device);
 void ap_diffwave_destroy(ap_diffwave_t h);
-/* AP_MODE_BF16 (default when the configuration supports the tensor-core kernels: C == S == 256) or AP_MODE_FP32 */
+/* AP_MODE_BF16 (default when the configuration supports the tensor-core kernels: C == S == 256), AP_MODE_FP16 or AP_MODE_FP32 */
 int ap_diffwave_set_mode(ap_diffwave_t h, int mode);
 int ap_diffwave_get_mode(ap_diffwave_t h);
 /* Pre-allocate the activation workspace for up to `chunk` waveforms of length L processed at once (larger batches are

@@ -11,8 +11,8 @@ from gpu_common import CONFIG_JSON, TorchNormalInjector, cuda, rel_l2, synthetic
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-5, "bf16": 1e-2}
-TOL_EPS = {"fp32": 2e-5, "bf16": 1e-2}
+TOL = {"fp32": 1e-5, "bf16": 1e-2, "fp16": 1e-3}
+TOL_EPS = {"fp32": 2e-5, "bf16": 1e-2, "fp16": 2e-3}
 
 
 @pytest.fixture(scope="module")
@@ -127,7 +127,7 @@ def _eps(ap, sd, cfg, x, t, mode):
 
 @pytest.mark.parametrize("key,L,B,t,seed", [("eps_full_L1024_t1", 1024, 2, 1.0, 1234), ("eps_full_L1024_t65", 1024, 2, 65.0, 1234),
                                             ("eps_full_L3001_t7", 3001, 1, 7.0, 77)])
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
 def test_wavenet_eps_vs_reference_golden(ap, golden, sd_full, key, L, B, t, seed, mode):
     x = synthetic.synthetic_waveforms(B, L, seed=seed)
     eps = _eps(ap, sd_full, synthetic.DEFAULT_WAVENET_CONFIG, x, t, mode)
@@ -243,7 +243,7 @@ def test_inference_only_and_cpu_inputs_raise(ap, diffwave):
 
 
 # ---------------------------------------------------------------------------------------------------- purifier
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
 def test_ddpm_purifier_vs_reference_golden(diffwave, golden, mode):
     diffwave.model.set_mode(mode)
     x = cuda(synthetic.synthetic_waveforms(2, 1024, seed=1234))

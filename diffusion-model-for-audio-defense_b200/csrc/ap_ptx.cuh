@@ -42,9 +42,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trapped launch (cudaErrorLaunchFailure), never a hung GPU.
-// Returns the number of cycles spent waiting (0 when the phase had already completed).
+// Returns the number of cycles spent waiting.  (try_wait may itself suspend the thread for a while before it reports
+// success, so the clock is read before the first attempt: the wait-cycle counters would otherwise under-report.)
 __device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
-  if (mbar_try_wait(bar, parity)) return 0;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
@@ -65,6 +65,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// L2 prefetch of a 3-D box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -115,6 +121,17 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 32-byte global accesses (one full sector per thread), not allocated in L1
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 // two fp32 -> packed bf16x2 (lo in bits [0,16), hi in bits [16,32)), round to nearest even
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -264,6 +281,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------ register reallocation between warp groups
+// every warp of the (4-warp, aligned) warp group executes the same instruction; N is a multiple of 8 in [24, 256]
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ------------------------------------------------------------------ math
 __device__ __forceinline__ float tanh_approx(float x) {

@@ -16,9 +16,11 @@
 //              s[128 x 256] = sum_n O_n . Ws_n   (K = 36 * 256) ; y = relu((s + sum b) * sqrt(1/N) . Wf + b) ; eps = w2 . y + b2
 //              (skip_total = sum_n skip_n is linear in o_n, so deferring it removes the fp32 skip read-modify-write
 //               of 32.8 MB per layer per waveform from the layer kernel.)
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-3 idle, warps 4..11 =
+// epilogue.  k1 moves registers from warp group 0 to the epilogue groups with setmaxnreg (96 / 200 per thread).
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -35,32 +37,33 @@ using namespace ptx;
 constexpr int C = 256;                      // channels (res == skip)
 constexpr int TILE_M = 128;                 // positions per tile (per CTA)
 constexpr int A_BYTES = TILE_M * 128;       // [128 rows][64 bf16]  SWIZZLE_128B
-constexpr int OUT_BYTES = 4 * A_BYTES;      // 4 K-blocks of [128][64] bf16 (gate output / staging)
-constexpr int NTHREADS = 320;
+constexpr int OUT_BYTES = 4 * A_BYTES;      // 4 K-blocks of [128][64] bf16 (gate output / skip-sum staging)
+constexpr int NTHREADS = 384;               // warp group 0: TMA producer, MMA issuer, 2 idle warps; groups 1-2: epilogue
+constexpr int EPI_WARP0 = 4;                // first epilogue warp (warp-group aligned: setmaxnreg works per warp group)
 constexpr int EPI_THREADS = 256;
 
 // CG = 1: one CTA per tile, tcgen05 cta_group::1 (M = 128).
 // CG = 2: a CTA pair (cluster of 2) works on two adjacent tiles with cta_group::2 (M = 256): each CTA stages its own 128
 //         activation rows and HALF of every weight tile, so both the TMA fill and the MMA operand reads of shared memory
 //         drop from 192 to 128 B/clk per SM (shared memory delivers 128 B/clk, which capped CG = 1 at ~63 % tensor duty).
-// KIND 1 = k1_layer (biases live in registers: shared memory goes to a deeper TMA ring), KIND 2 = k2_head (1024 floats of
-// bias / partial-dot scratch in shared memory).
+// KIND 1 = k1_layer, KIND 2 = k2_head.  Per-channel biases are kernel parameters (constant bank), so shared memory holds
+// only the TMA ring (5 stages in pair mode), one 64 KB staging tile and 1 KB of scratch.
 template <int CG_, int KIND, int DT_ = 0> struct Geo {
   static constexpr int CG = CG_;
   static constexpr int DT = DT_;   // 0: bf16 operands, 1: fp16 operands
   static constexpr int B_ROWS = 256 / CG;
   static constexpr int B_BYTES = B_ROWS * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = CG == 1 ? 3 : (KIND == 1 ? 5 : 4);
+  static constexpr int NSTAGE = CG == 1 ? 3 : 5;
   static constexpr int OUT_OFF = NSTAGE * STAGE_BYTES;
   static constexpr int BIAS_OFF = OUT_OFF + OUT_BYTES;
-  static constexpr int BAR_OFF = BIAS_OFF + (KIND == 1 ? 0 : 4096);
+  static constexpr int BAR_OFF = BIAS_OFF + 1024;   // k1: c2[256]; k2: 128 partial dots
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + slack to align the base to 1024 B
   static constexpr uint32_t IDESC = DT_ == 0 ? umma_idesc_bf16_f32(128 * CG, 256) : umma_idesc_f16_f32(128 * CG, 256);
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
   static_assert(NSTAGE <= 5, "barrier table holds at most 5 stages");
 };
-enum { BAR_FULL = 0, BAR_EMPTY = 5, BAR_ACC_FULL = 10, BAR_ACC_EMPTY = 12, BAR_OUT_READY = 14, BAR_UC_FULL = 16, BAR_COUNT = 17 };
+enum { BAR_FULL = 0, BAR_EMPTY = 5, BAR_ACC_FULL = 10, BAR_ACC_EMPTY = 12, BAR_OUT_READY = 14, BAR_UC_FULL = 17, BAR_COUNT = 18 };
 
 // Per-CTA view of the barrier array and the pair topology
 template <class G> struct Ctx {
@@ -124,8 +127,8 @@ template <class G> __device__ __forceinline__ uint32_t tc_prologue(Ctx<G>& cx, u
     for (int i = 0; i < 2; ++i) {
       mbar_init(cx.bar(BAR_ACC_FULL + i), 1);
       mbar_init(cx.bar(BAR_ACC_EMPTY + i), 8 * CG);
-      mbar_init(cx.bar(BAR_OUT_READY + i), out_ready_count * CG);
     }
+    for (int i = 0; i < 3; ++i) mbar_init(cx.bar(BAR_OUT_READY + i), out_ready_count * CG);
     mbar_init(cx.bar(BAR_UC_FULL), 1);
     fence_barrier_init();
   }
@@ -161,55 +164,217 @@ template <int CG> struct Tiles {
 };
 
 struct K1Params {
-  int n_tiles, tiles_per_sample, dilation, layer, chunk_alloc, last;
-  const float* b_dil;   // [2][256] packed chunk order
+  int n_tiles, tiles_per_sample, dilation, layer, chunk_alloc, last, L;
   const float* b_res;   // [256]
   const float* p_next;  // [256]
+  const uint16_t* u_in; // [chunk][L][256] this layer's input (also read through tmUin as the GEMM-1 A operand)
+  uint16_t* u_out;      // [chunk][L][256] next layer's input
   long long* dbg;       // optional [gridDim.x][16] wait-cycle counters (development aid), or null
+  // dilated-conv biases in packed chunk order: [j][0..127] tanh bias of gate channel 128 j + c, [j][128..255] HALF the
+  // sigmoid bias of the same channel (sigmoid(s) = 0.5 tanh(0.5 s) + 0.5).  They live in the kernel-parameter constant
+  // bank, so the bias add is a constant operand of the FADD / FFMA: no shared-memory or shuffle traffic in the epilogue.
+  float bd[512];
 };
+
+// Order of the accumulation jobs of one CTA (pair), shared by the TMA producer, the MMA issuer and the epilogue warps:
+//   G1c0(0) G1c1(0) | G1c0(1) G2(0) G1c1(1) | G1c0(2) G2(1) G1c1(2) | ... | G2(T-1)
+// GEMM-2 of tile t is issued one chunk late, behind chunk 0 of tile t+1, so the tensor pipe never waits for the gate
+// epilogue of chunk 1 (its only input dependency).  Job g accumulates into TMEM region g & 1; the gate epilogue frees its
+// region as soon as the accumulators are in registers (before the MUFU work) and holds the packed gate values in
+// registers until GEMM-2 of the previous tile has finished reading the 64 KB staging tile.  The residual epilogue does
+// not touch shared memory: u is read and u' written with 32-byte-per-thread global accesses (full sectors), which
+// takes its four 64 KB passes off the shared-memory crossbar (the resource that bounds this kernel).
+template <class G, int HSEL>
+__device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p, const uint32_t tmem,
+                                            const Tiles<G::CG>& tiles, const CUtensorMap* tmO, const uint32_t c2_addr) {
+  constexpr int DT = G::DT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q4 = warp & 3, etid = threadIdx.x - EPI_WARP0 * 32;
+  const int row = q4 * 32 + lane;                       // position within the tile == TMEM lane
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+  const uint32_t row_off = row * 128, sw = row & 7;
+  const float sqrt_half = 0.70710678118654752440f;
+  const int oob_l0 = p.tiles_per_sample * TILE_M;
+  uint32_t g = 0;
+  long long w_accfull = 0, w_g2 = 0, w_bulk = 0;
+  const long long t_start = clock64();
+
+  // ---- gate epilogue of chunk J: o = tanh(a_t + b) * sigmoid(a_s + b) -> bf16 -> staging (A operand of GEMM-2) + O
+  auto gate = [&](auto jc, uint32_t ti, bool valid, int b, int l0) {
+    constexpr int J = decltype(jc)::value;
+    const uint32_t r = g & 1;
+    w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 9);
+    tc_fence_after();
+    uint32_t ta[2][32], sg[2][32];
+#pragma unroll
+    for (int gq = 0; gq < 2; ++gq) {
+      tmem_ld_32x32b_x32(lane_addr + r * 256 + HSEL * 64 + gq * 32, ta[gq]);
+      tmem_ld_32x32b_x32(lane_addr + r * 256 + 128 + HSEL * 64 + gq * 32, sg[gq]);
+    }
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);   // accumulators are in registers: the region is free again
+    uint32_t pk[2][4][4];
+#pragma unroll
+    for (int gq = 0; gq < 2; ++gq)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c0 = i * 8 + 2 * e;
+          const int cb = J * 256 + HSEL * 64 + gq * 32 + c0;
+          const float t0 = tanh_approx(__uint_as_float(ta[gq][c0]) + p.bd[cb]);
+          const float t1 = tanh_approx(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]);
+          const float s0 = tanh_approx(fmaf(__uint_as_float(sg[gq][c0]), 0.5f, p.bd[cb + 128]));
+          const float s1 = tanh_approx(fmaf(__uint_as_float(sg[gq][c0 + 1]), 0.5f, p.bd[cb + 129]));
+          pk[gq][i][e] = pack2<DT>(t0 * fmaf(s0, 0.5f, 0.5f), t1 * fmaf(s1, 0.5f, 0.5f));
+        }
+    // the staging tile still holds o of the previous tile until its GEMM-2 (the NEXT job, g + 1) has completed
+    if (etid == 0) {                                       // and the O store of chunk J of the previous tile has read it
+      if (J == 0 && !p.last && ti > 0) {
+        w_g2 += mbar_wait(cx.bar(BAR_ACC_FULL + ((g + 1) & 1)), ((g + 1) >> 1) & 1, 12);
+        tc_fence_after();
+      }
+      const long long t0 = clock64();
+      bulk_wait_read<1>();
+      w_bulk += clock64() - t0;
+    }
+    named_bar_sync(1, EPI_THREADS);
+    const uint32_t kb_base = cx.out_kb(2 * J + HSEL) + row_off;
+#pragma unroll
+    for (int gq = 0; gq < 2; ++gq)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        st_shared_v4(kb_base + (((gq * 4 + i) ^ sw) << 4), make_uint4(pk[gq][i][0], pk[gq][i][1], pk[gq][i][2], pk[gq][i][3]));
+    fence_proxy_async_smem();
+    named_bar_sync(1, EPI_THREADS);
+    if (etid == 0) {
+      if (valid) {
+        tma_store_3d(tmO, cx.out_kb(2 * J), (2 * J) * 64, l0, p.layer * p.chunk_alloc + b);
+        tma_store_3d(tmO, cx.out_kb(2 * J + 1), (2 * J + 1) * 64, l0, p.layer * p.chunk_alloc + b);
+      }
+      bulk_commit();                                       // always a group (possibly empty): wait_group counts stay uniform
+      cx.arrive_leader(BAR_OUT_READY + J);
+    }
+    ++g;
+  };
+
+  // ---- residual epilogue: u' = (u + r) * sqrt(.5) + (b_res * sqrt(.5) + p_next) -> bf16, global -> registers -> global
+  auto residual = [&](bool valid, int b, int l0) {
+    const uint32_t r = g & 1;
+    const bool live = valid && l0 + row < p.L;
+    const size_t goff = (static_cast<size_t>(b) * p.L + (live ? l0 + row : 0)) * C + HSEL * 128;
+    uint32_t uu[8][8];
+    if (live) {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) ld_global_v8(p.u_in + goff + v * 16, uu[v]);
+    }
+    w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 10);
+    tc_fence_after();
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(lane_addr + r * 256 + HSEL * 128 + gq * 32, acc);
+      tmem_ld_wait();
+      if (gq == 3) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {                        // 16 channels = one 32-byte access
+        const int ch = HSEL * 128 + gq * 32 + i * 16;
+        uint32_t pk[8];
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const uint4 cv = ld_shared_v4(c2_addr + (ch + e4 * 4) * 4);   // warp-uniform address: broadcast
+          const uint32_t w0 = uu[gq * 2 + i][e4 * 2], w1 = uu[gq * 2 + i][e4 * 2 + 1];
+          const int a0 = i * 16 + e4 * 4;
+          pk[e4 * 2] = pack2<DT>(fmaf(unpack_lo<DT>(w0) + __uint_as_float(acc[a0]), sqrt_half, __uint_as_float(cv.x)),
+                                 fmaf(unpack_hi<DT>(w0) + __uint_as_float(acc[a0 + 1]), sqrt_half, __uint_as_float(cv.y)));
+          pk[e4 * 2 + 1] = pack2<DT>(fmaf(unpack_lo<DT>(w1) + __uint_as_float(acc[a0 + 2]), sqrt_half, __uint_as_float(cv.z)),
+                                     fmaf(unpack_hi<DT>(w1) + __uint_as_float(acc[a0 + 3]), sqrt_half, __uint_as_float(cv.w)));
+        }
+        if (live) st_global_v8(p.u_out + goff + (gq * 2 + i) * 16, pk);
+      }
+    }
+    ++g;
+  };
+
+  uint32_t ti = 0;
+  bool pvalid = false;
+  int pb = 0, pl0 = 0;
+  for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+    const bool valid = tile < p.n_tiles;
+    const int b = valid ? tile / p.tiles_per_sample : 0;
+    const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+    gate(std::integral_constant<int, 0>{}, ti, valid, b, l0);
+    if (!p.last && ti > 0) residual(pvalid, pb, pl0);
+    gate(std::integral_constant<int, 1>{}, ti, valid, b, l0);
+    pvalid = valid, pb = b, pl0 = l0;
+  }
+  if (!p.last && ti > 0) residual(pvalid, pb, pl0);
+  if (etid == 0) bulk_wait_all<0>();
+  if (p.dbg && etid == 0) {
+    long long* d = p.dbg + blockIdx.x * 16;
+    d[7] = w_accfull, d[8] = w_g2, d[9] = clock64() - t_start, d[10] = w_bulk;
+  }
+}
 
 template <int CG, int DT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUtensorMap tmUout,
+k1_layer(const __grid_constant__ CUtensorMap tmUin,
          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWd,
-         const __grid_constant__ CUtensorMap tmWr, const K1Params p) {
+         const __grid_constant__ CUtensorMap tmWr, const __grid_constant__ K1Params p) {
   using G = Geo<CG, 1, DT>;
   Ctx<G> cx;
   uint8_t* gen;
   const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
+  {  // c2[c] = b_res[c] * sqrt(.5) + p_next[c]: the per-channel constant of the residual update (WaveNet.py:84,97)
+    float* s_c2 = reinterpret_cast<float*>(gen + G::BIAS_OFF);
+    for (int i = threadIdx.x; i < C; i += NTHREADS) s_c2[i] = fmaf(p.b_res[i], 0.70710678118654752440f, p.p_next[i]);
+  }
   if (threadIdx.x == 0)
-    prefetch_tmap(&tmUin), prefetch_tmap(&tmUout), prefetch_tmap(&tmO), prefetch_tmap(&tmWd), prefetch_tmap(&tmWr);
+    prefetch_tmap(&tmUin), prefetch_tmap(&tmO), prefetch_tmap(&tmWd), prefetch_tmap(&tmWr);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Tiles<CG> tiles(p.n_tiles, cx.rank);
   const int oob_l0 = p.tiles_per_sample * TILE_M;   // a row coordinate past the end: TMA zero-fills the whole box
 
+  if (warp < EPI_WARP0) setmaxnreg_dec<96>();
   if (warp == 0) {
     // ======================================================================================= TMA producer
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, ti = 0;
       long long w_empty = 0;
       const long long t_start = clock64();
-      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride) {
+      auto load_g1 = [&](int j, bool valid, int b, int l0) {
+        for (int tap = 0; tap < 3; ++tap)
+          for (int kb = 0; kb < 4; ++kb, ++it) {
+            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+            w_empty += cx.arm(s, ph, G::STAGE_BYTES, 1);
+            cx.load_a(s, &tmUin, kb * 64, valid ? l0 + (tap - 1) * p.dilation : oob_l0, b);
+            cx.load_b(s, &tmWd, tap * C + kb * 64, (p.layer * 2 + j) * 256);
+          }
+      };
+      auto load_wr = [&]() {
+        for (int kb = 0; kb < 4; ++kb, ++it) {
+          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+          w_empty += cx.arm(s, ph, G::B_BYTES, 2);
+          cx.load_b(s, &tmWr, kb * 64, p.layer * 256);
+        }
+      };
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
         const bool valid = tile < p.n_tiles;
         const int b = valid ? tile / p.tiles_per_sample : 0;
         const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
-        for (int j = 0; j < 2; ++j)
-          for (int tap = 0; tap < 3; ++tap)
-            for (int kb = 0; kb < 4; ++kb, ++it) {
-              const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-              w_empty += cx.arm(s, ph, G::STAGE_BYTES, 1);
-              cx.load_a(s, &tmUin, kb * 64, valid ? l0 + (tap - 1) * p.dilation : oob_l0, b);
-              cx.load_b(s, &tmWd, tap * C + kb * 64, (p.layer * 2 + j) * 256);
-            }
-        if (!p.last)
-          for (int kb = 0; kb < 4; ++kb, ++it) {
-            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-            w_empty += cx.arm(s, ph, G::B_BYTES, 2);
-            cx.load_b(s, &tmWr, kb * 64, p.layer * 256);
-          }
+        load_g1(0, valid, b, l0);
+        if (!p.last && ti > 0) load_wr();
+        load_g1(1, valid, b, l0);
       }
+      if (!p.last && ti > 0) load_wr();
       if (p.dbg) p.dbg[blockIdx.x * 16 + 0] = w_empty, p.dbg[blockIdx.x * 16 + 1] = clock64() - t_start;
     }
     __syncwarp();
@@ -219,166 +384,53 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
       uint32_t it = 0, g = 0, ti = 0;
       long long w_full = 0, w_acc = 0, w_out = 0;
       const long long t_start = clock64();
-      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
-        for (int j = 0; j < 2; ++j, ++g) {
-          const uint32_t r = g & 1;
-          w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 3);
+      auto gemm1 = [&]() {
+        const uint32_t r = g & 1;
+        w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 3);
+        tc_fence_after();
+        for (int kblk = 0; kblk < 12; ++kblk, ++it) {
+          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+          w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 4);
           tc_fence_after();
-          for (int kblk = 0; kblk < 12; ++kblk, ++it) {
-            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-            w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 4);
-            tc_fence_after();
-            cx.mma_kblock(tmem + r * 256, cx.stage_a(s), cx.stage_b(s), kblk == 0);
-            cx.commit(BAR_EMPTY + s);
-          }
-          cx.commit(BAR_ACC_FULL + r);
+          cx.mma_kblock(tmem + r * 256, cx.stage_a(s), cx.stage_b(s), kblk == 0);
+          cx.commit(BAR_EMPTY + s);
         }
-        if (!p.last) {
-          const uint32_t r = g & 1;
-          w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 5);
-          for (int kb = 0; kb < 4; ++kb, ++it) {
-            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-            if (kb == 0) w_out += mbar_wait(cx.bar(BAR_OUT_READY + 0), ti & 1, 6);
-            if (kb == 2) w_out += mbar_wait(cx.bar(BAR_OUT_READY + 1), ti & 1, 7);
-            w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 8);
-            tc_fence_after();
-            cx.mma_kblock(tmem + r * 256, cx.out_kb(kb), cx.stage_b(s), kb == 0);
-            cx.commit(BAR_EMPTY + s);
-          }
-          cx.commit(BAR_ACC_FULL + r);
-          ++g;
+        cx.commit(BAR_ACC_FULL + r);
+        ++g;
+      };
+      auto gemm2 = [&](uint32_t t_idx) {
+        const uint32_t r = g & 1;
+        w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 5);
+        tc_fence_after();
+        for (int kb = 0; kb < 4; ++kb, ++it) {
+          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+          if ((kb & 1) == 0) w_out += mbar_wait(cx.bar(BAR_OUT_READY + (kb >> 1)), t_idx & 1, 6);
+          w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 8);
+          tc_fence_after();
+          cx.mma_kblock(tmem + r * 256, cx.out_kb(kb), cx.stage_b(s), kb == 0);
+          cx.commit(BAR_EMPTY + s);
         }
+        cx.commit(BAR_ACC_FULL + r);
+        ++g;
+      };
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+        gemm1();
+        if (!p.last && ti > 0) gemm2(ti - 1);
+        gemm1();
       }
+      if (!p.last && ti > 0) gemm2(ti - 1);
       if (p.dbg) {
         long long* d = p.dbg + blockIdx.x * 16;
         d[2] = w_full, d[3] = w_acc, d[4] = w_out, d[5] = clock64() - t_start, d[6] = ti;
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp >= EPI_WARP0) {
     // ======================================================================================= epilogue (8 warps)
-    const int q = warp & 3, hsel = (warp - 2) >> 2, etid = threadIdx.x - 64;
-    const int row = q * 32 + lane;                       // position within the tile == TMEM lane
-    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t row_off = row * 128, sw = row & 7;
-    const float sqrt_half = 0.70710678118654752440f;
-    // per-channel constants live in registers, one channel per lane, and are broadcast with warp shuffles:
-    //   bd_t/bd_s[j][gq]: dilated-conv bias of tanh / sigmoid channel j*128 + hsel*64 + gq*32 + lane
-    //   br/pn[gq]       : res-conv bias and next-layer step-embedding projection of channel hsel*128 + gq*32 + lane
-    float bd_t[2][2], bd_s[2][2], br_r[4], pn_r[4];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int gq = 0; gq < 2; ++gq) {
-        bd_t[j][gq] = p.b_dil[j * 256 + hsel * 64 + gq * 32 + lane];
-        bd_s[j][gq] = p.b_dil[j * 256 + 128 + hsel * 64 + gq * 32 + lane];
-      }
-#pragma unroll
-    for (int gq = 0; gq < 4; ++gq) br_r[gq] = p.b_res[hsel * 128 + gq * 32 + lane], pn_r[gq] = p.p_next[hsel * 128 + gq * 32 + lane];
-    uint32_t g = 0, ti = 0;
-    long long w_accfull = 0, w_uc = 0;
-    const long long t_start = clock64();
-    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
-      const bool valid = tile < p.n_tiles;
-      const int b = valid ? tile / p.tiles_per_sample : 0;
-      const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
-      for (int j = 0; j < 2; ++j, ++g) {
-        const uint32_t r = g & 1;
-        w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 9);
-        tc_fence_after();
-        if (j == 0) {  // the staging region is about to be overwritten: previous TMA stores must have read it
-          if (etid == 0) bulk_wait_read<0>();
-          named_bar_sync(1, EPI_THREADS);
-        }
-        const uint32_t kb_base = cx.out_kb(2 * j + hsel) + row_off;
-#pragma unroll
-        for (int gq = 0; gq < 2; ++gq) {
-          const float bt_l = j == 0 ? bd_t[0][gq] : bd_t[1][gq], bs_l = j == 0 ? bd_s[0][gq] : bd_s[1][gq];
-          uint32_t ta[32], sg[32];
-          tmem_ld_32x32b_x32(lane_addr + r * 256 + hsel * 64 + gq * 32, ta);
-          tmem_ld_32x32b_x32(lane_addr + r * 256 + 128 + hsel * 64 + gq * 32, sg);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c0 = i * 8 + 2 * e;
-              const float a0 = __uint_as_float(ta[c0]) + __shfl_sync(0xffffffffu, bt_l, c0);
-              const float a1 = __uint_as_float(ta[c0 + 1]) + __shfl_sync(0xffffffffu, bt_l, c0 + 1);
-              const float s0 = __uint_as_float(sg[c0]) + __shfl_sync(0xffffffffu, bs_l, c0);
-              const float s1 = __uint_as_float(sg[c0 + 1]) + __shfl_sync(0xffffffffu, bs_l, c0 + 1);
-              pk[e] = pack2<DT>(tanh_approx(a0) * sigmoid_approx(s0), tanh_approx(a1) * sigmoid_approx(s1));
-            }
-            st_shared_v4(kb_base + (((gq * 4 + i) ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-          }
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
-        named_bar_sync(1, EPI_THREADS);
-        if (etid == 0) {
-          if (valid) {
-            tma_store_3d(&tmO, cx.out_kb(2 * j), (2 * j) * 64, l0, p.layer * p.chunk_alloc + b);
-            tma_store_3d(&tmO, cx.out_kb(2 * j + 1), (2 * j + 1) * 64, l0, p.layer * p.chunk_alloc + b);
-            bulk_commit();
-          }
-          cx.arrive_leader(BAR_OUT_READY + j);
-        }
-      }
-      if (!p.last) {
-        const uint32_t r = g & 1;
-        w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 10);   // GEMM-2 done: accumulators ready, `out` smem no longer read
-        tc_fence_after();
-        if (etid == 0) {
-          bulk_wait_read<0>();                                    // the O stores have finished reading `out`
-          mbar_expect_tx(cx.bar(BAR_UC_FULL), OUT_BYTES);
-          for (int kb = 0; kb < 4; ++kb) tma_load_3d(cx.out_kb(kb), &tmUin, cx.bar(BAR_UC_FULL), kb * 64, l0, b);
-        }
-        w_uc += mbar_wait(cx.bar(BAR_UC_FULL), ti & 1, 11);
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          const float br_l = br_r[gq], pn_l = pn_r[gq];
-          uint32_t acc[32];
-          tmem_ld_32x32b_x32(lane_addr + r * 256 + hsel * 128 + gq * 32, acc);
-          tmem_ld_wait();
-          const uint32_t kb_base = cx.out_kb(hsel * 2 + (gq >> 1)) + row_off;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t addr = kb_base + ((((gq & 1) * 4 + i) ^ sw) << 4);
-            const uint4 uv = ld_shared_v4(addr);
-            const uint32_t uw[4] = {uv.x, uv.y, uv.z, uv.w};
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c0 = i * 8 + 2 * e;
-              const float h0 = (unpack_lo<DT>(uw[e]) + (__uint_as_float(acc[c0]) + __shfl_sync(0xffffffffu, br_l, c0))) * sqrt_half +
-                               __shfl_sync(0xffffffffu, pn_l, c0);
-              const float h1 = (unpack_hi<DT>(uw[e]) + (__uint_as_float(acc[c0 + 1]) + __shfl_sync(0xffffffffu, br_l, c0 + 1))) * sqrt_half +
-                               __shfl_sync(0xffffffffu, pn_l, c0 + 1);
-              pk[e] = pack2<DT>(h0, h1);
-            }
-            st_shared_v4(addr, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-          }
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
-        named_bar_sync(1, EPI_THREADS);
-        if (etid == 0 && valid) {
-          for (int kb = 0; kb < 4; ++kb) tma_store_3d(&tmUout, cx.out_kb(kb), kb * 64, l0, b);
-          bulk_commit();
-        }
-        ++g;
-      }
-    }
-    if (etid == 0) bulk_wait_all<0>();
-    if (p.dbg && etid == 0) {
-      long long* d = p.dbg + blockIdx.x * 16;
-      d[7] = w_accfull, d[8] = w_uc, d[9] = clock64() - t_start;
-    }
+    const uint32_t c2_addr = cx.base + G::BIAS_OFF;
+    setmaxnreg_inc<200>();
+    if (((warp - EPI_WARP0) >> 2) == 0) k1_epilogue<G, 0>(cx, p, tmem, tiles, &tmO, c2_addr);
+    else k1_epilogue<G, 1>(cx, p, tmem, tiles, &tmO, c2_addr);
   }
   tc_epilogue_teardown<CG>(tmem);
 }
@@ -387,25 +439,91 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
 struct K2Params {
   int n_tiles, tiles_per_sample, L, num_layers, chunk_alloc;
   float scale;           // sqrt(1/N)
-  const float* bskip;    // [256] sum over layers of the skip-conv biases
-  const float* bf1;      // [256]
-  const float* wf2;      // [256]
   const float* bf2;      // [1]
   float* eps;            // [B][L]
+  // per-channel vectors in the kernel-parameter constant bank (constant operands of the epilogue FMAs):
+  float bskip_scaled[256];   // (sum over layers of the skip-conv biases) * sqrt(1/N)
+  float bf1[256];            // final_conv.0 bias
+  float wf2[256];            // final_conv.2 (256 -> 1) weight
 };
 enum { BAR2_S_READY = BAR_OUT_READY };
+
+// epilogue of k2 for the column half HSEL (channels HSEL*128 .. +127)
+template <class G, int HSEL>
+__device__ __forceinline__ void k2_epilogue(const Ctx<G>& cx, const K2Params& p, const uint32_t tmem,
+                                            const Tiles<G::CG>& tiles, float* s_part) {
+  constexpr int DT = G::DT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q4 = warp & 3, etid = threadIdx.x - EPI_WARP0 * 32;
+  const int row = q4 * 32 + lane;
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+  const uint32_t row_off = row * 128, sw = row & 7;
+  const int oob_l0 = p.tiles_per_sample * TILE_M;
+  uint32_t ti = 0;
+  for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+    const bool valid = tile < p.n_tiles;
+    const int b = valid ? tile / p.tiles_per_sample : 0;
+    const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+    // ---- skip sum -> s (bf16, A operand of the head GEMM).  The previous tile's head MMAs finished reading the
+    //      staging region before its ACC_FULL[1] fired, which this thread has already waited on.
+    mbar_wait(cx.bar(BAR_ACC_FULL + 0), ti & 1, 28);
+    tc_fence_after();
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(lane_addr + HSEL * 128 + gq * 32, acc);
+      tmem_ld_wait();
+      const uint32_t kb_base = cx.out_kb(HSEL * 2 + (gq >> 1)) + row_off;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c0 = HSEL * 128 + gq * 32 + i * 8 + 2 * e;
+          pk[e] = pack2<DT>(fmaf(__uint_as_float(acc[i * 8 + 2 * e]), p.scale, p.bskip_scaled[c0]),
+                            fmaf(__uint_as_float(acc[i * 8 + 2 * e + 1]), p.scale, p.bskip_scaled[c0 + 1]));
+        }
+        st_shared_v4(kb_base + ((((gq & 1) * 4 + i) ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 0);
+    named_bar_sync(1, EPI_THREADS);
+    if (etid == 0) cx.arrive_leader(BAR2_S_READY);
+    // ---- head: y = relu(acc + b) ; eps = w2 . y + b2
+    mbar_wait(cx.bar(BAR_ACC_FULL + 1), ti & 1, 29);
+    tc_fence_after();
+    float dot = 0.f;
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(lane_addr + 256 + HSEL * 128 + gq * 32, acc);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        dot = fmaf(fmaxf(__uint_as_float(acc[e]) + p.bf1[HSEL * 128 + gq * 32 + e], 0.f), p.wf2[HSEL * 128 + gq * 32 + e], dot);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 1);
+    if (HSEL == 1) s_part[row] = dot;
+    named_bar_sync(1, EPI_THREADS);
+    if (HSEL == 0 && valid && l0 + row < p.L) p.eps[static_cast<size_t>(b) * p.L + l0 + row] = dot + s_part[row] + p.bf2[0];
+    named_bar_sync(1, EPI_THREADS);   // s_part is rewritten by the next tile
+  }
+}
 
 template <int CG, int DT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWs,
-        const __grid_constant__ CUtensorMap tmWf, const K2Params p) {
+        const __grid_constant__ CUtensorMap tmWf, const __grid_constant__ K2Params p) {
   using G = Geo<CG, 2, DT>;
   Ctx<G> cx;
   uint8_t* gen;
   const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
-  float* s_bias = reinterpret_cast<float*>(gen + G::BIAS_OFF);   // [0,256) bskip, [256,512) bf1, [512,768) wf2, [768,896) partial dots
-  for (int i = threadIdx.x; i < 768; i += NTHREADS)
-    s_bias[i] = i < 256 ? p.bskip[i] : (i < 512 ? p.bf1[i - 256] : p.wf2[i - 512]);
+  float* s_part = reinterpret_cast<float*>(gen + G::BIAS_OFF);   // [128] partial dots of the upper column half
   if (threadIdx.x == 0) prefetch_tmap(&tmO), prefetch_tmap(&tmWs), prefetch_tmap(&tmWf);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -463,68 +581,9 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
       }
     }
     __syncwarp();
-  } else {
-    const int q = warp & 3, hsel = (warp - 2) >> 2, etid = threadIdx.x - 64;
-    const int row = q * 32 + lane;
-    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t row_off = row * 128, sw = row & 7;
-    float* s_part = s_bias + 768;
-    uint32_t ti = 0;
-    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
-      const bool valid = tile < p.n_tiles;
-      const int b = valid ? tile / p.tiles_per_sample : 0;
-      const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
-      // ---- skip sum -> s (bf16, A operand of the head GEMM).  The previous tile's head MMAs finished reading the
-      //      staging region before its ACC_FULL[1] fired, which this thread has already waited on.
-      mbar_wait(cx.bar(BAR_ACC_FULL + 0), ti & 1, 28);
-      tc_fence_after();
-      const float* bs = s_bias + hsel * 128;
-#pragma unroll 1
-      for (int gq = 0; gq < 4; ++gq) {
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(lane_addr + hsel * 128 + gq * 32, acc);
-        tmem_ld_wait();
-        const uint32_t kb_base = cx.out_kb(hsel * 2 + (gq >> 1)) + row_off;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c0 = gq * 32 + i * 8 + 2 * e;
-            pk[e] = pack2<DT>((__uint_as_float(acc[i * 8 + 2 * e]) + bs[c0]) * p.scale,
-                                (__uint_as_float(acc[i * 8 + 2 * e + 1]) + bs[c0 + 1]) * p.scale);
-          }
-          st_shared_v4(kb_base + ((((gq & 1) * 4 + i) ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 0);
-      named_bar_sync(1, EPI_THREADS);
-      if (etid == 0) cx.arrive_leader(BAR2_S_READY);
-      // ---- head: y = relu(acc + b) ; eps = w2 . y + b2
-      mbar_wait(cx.bar(BAR_ACC_FULL + 1), ti & 1, 29);
-      tc_fence_after();
-      const float* bf = s_bias + 256 + hsel * 128;
-      const float* w2 = s_bias + 512 + hsel * 128;
-      float dot = 0.f;
-#pragma unroll 1
-      for (int gq = 0; gq < 4; ++gq) {
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(lane_addr + 256 + hsel * 128 + gq * 32, acc);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) dot = fmaf(fmaxf(__uint_as_float(acc[e]) + bf[gq * 32 + e], 0.f), w2[gq * 32 + e], dot);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 1);
-      if (hsel == 1) s_part[row] = dot;
-      named_bar_sync(1, EPI_THREADS);
-      if (hsel == 0 && valid && l0 + row < p.L) p.eps[static_cast<size_t>(b) * p.L + l0 + row] = dot + s_part[row] + p.bf2[0];
-      named_bar_sync(1, EPI_THREADS);   // s_part is rewritten by the next tile
-    }
+  } else if (warp >= EPI_WARP0) {
+    if (((warp - EPI_WARP0) >> 2) == 0) k2_epilogue<G, 0>(cx, p, tmem, tiles, s_part);
+    else k2_epilogue<G, 1>(cx, p, tmem, tiles, s_part);
   }
   tc_epilogue_teardown<CG>(tmem);
 }
@@ -667,7 +726,9 @@ struct TcNet {
   DevBuf wd, wr, ws, wf;                                   // bf16 operands
   DevBuf wd_h, wr_h, ws_h, wf_h;                           // fp16 operands (AP_MODE_FP16)
   int dt = 0;                                              // 0: bf16, 1: fp16
-  DevBuf bd, br, bskip, bf1, wf2, bf2, init_w, init_b;     // fp32 vectors
+  DevBuf br, bf2, init_w, init_b;                          // fp32 vectors
+  std::vector<float> bskip_host, bf1_host, wf2_host;       // k2's per-channel vectors (kernel params)
+  std::vector<float> bd_host;                              // [N][512] dilated-conv biases in k1's packed order (kernel params)
   DevBuf u0, u1, o;
   int chunk = 0, L = 0;
   CUtensorMap tmU[2], tmO, tmWd, tmWr, tmWs, tmWf;   // weight maps: box of 256 rows (one CTA per tile)
@@ -751,7 +812,7 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
     for (int j = 0; j < 2; ++j)
       for (int r = 0; r < 256; ++r) {
         const int oc = r < 128 ? 128 * j + r : C + 128 * j + (r - 128);
-        bd[static_cast<size_t>(l) * 512 + j * 256 + r] = w[3][oc];
+        bd[static_cast<size_t>(l) * 512 + j * 256 + r] = r < 128 ? w[3][oc] : 0.5f * w[3][oc];   // sigmoid half: see K1Params
         uint16_t* dst = &wd[((static_cast<size_t>(l) * 2 + j) * 256 + r) * 768];
         for (int tap = 0; tap < 3; ++tap)
           for (int c = 0; c < C; ++c) {
@@ -784,11 +845,11 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
   TRY(upload_bf16(n->wr_h, to_f16(wr, wr_f)));
   TRY(upload_bf16(n->ws_h, to_f16(ws, ws_f)));
   TRY(upload_bf16(n->wf_h, to_f16(wf, wf_f)));
-  TRY(upload_f32(n->bd, bd));
+  n->bd_host = bd;
   TRY(upload_f32(n->br, br));
-  TRY(upload_f32(n->bskip, bskip));
-  TRY(upload_f32(n->bf1, std::vector<float>(tail[1], tail[1] + C)));
-  TRY(upload_f32(n->wf2, std::vector<float>(tail[2], tail[2] + C)));
+  n->bskip_host = bskip;
+  n->bf1_host.assign(tail[1], tail[1] + C);
+  n->wf2_host.assign(tail[2], tail[2] + C);
   TRY(upload_f32(n->bf2, std::vector<float>(tail[3], tail[3] + 1)));
   TRY(upload_f32(n->init_w, std::vector<float>(weights[0], weights[0] + C)));
   TRY(upload_f32(n->init_b, std::vector<float>(weights[1], weights[1] + C)));
@@ -900,22 +961,24 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
   for (int l = 0; l < layers; ++l) {
     K1Params p;
     p.n_tiles = n_tiles, p.tiles_per_sample = tps, p.dilation = 1 << (l % n->cfg.dilation_cycle), p.layer = l;
-    p.chunk_alloc = n->chunk, p.last = (l == n->N - 1);
-    p.b_dil = n->bd.as<float>() + static_cast<size_t>(l) * 512;
+    p.chunk_alloc = n->chunk, p.last = (l == n->N - 1), p.L = L;
+    p.u_in = (l & 1) ? n->u1.as<uint16_t>() : n->u0.as<uint16_t>();
+    p.u_out = (l & 1) ? n->u0.as<uint16_t>() : n->u1.as<uint16_t>();
+    std::memcpy(p.bd, n->bd_host.data() + static_cast<size_t>(l) * 512, sizeof(p.bd));
     p.b_res = n->br.as<float>() + static_cast<size_t>(l) * C;
     p.p_next = ptab + static_cast<size_t>(l + 1) * C;
     p.dbg = (l == n->dbg_layer) ? n->dbg.as<long long>() : nullptr;
     cudaEvent_t e0 = prof_event(n, 0), e1 = e0 ? prof_event(n, 0) : nullptr;
     if (e1) cudaEventRecord(e0, st);
-    const CUtensorMap &ui = n->tmU[l & 1], &uo = n->tmU[(l + 1) & 1];
+    const CUtensorMap& ui = n->tmU[l & 1];
     if (n->pair && n->dt == 0)
-      AP_CUDA(launch_pair(k1_layer<2, 0>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, uo, n->tmO, n->tmWd2, n->tmWr2, p));
+      AP_CUDA(launch_pair(k1_layer<2, 0>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2, n->tmWr2, p));
     else if (n->pair)
-      AP_CUDA(launch_pair(k1_layer<2, 1>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, uo, n->tmO, n->tmWd2_h, n->tmWr2_h, p));
+      AP_CUDA(launch_pair(k1_layer<2, 1>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2_h, n->tmWr2_h, p));
     else if (n->dt == 0)
-      k1_layer<1, 0><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(ui, uo, n->tmO, n->tmWd, n->tmWr, p);
+      k1_layer<1, 0><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(ui, n->tmO, n->tmWd, n->tmWr, p);
     else
-      k1_layer<1, 1><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(ui, uo, n->tmO, n->tmWd_h, n->tmWr_h, p);
+      k1_layer<1, 1><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(ui, n->tmO, n->tmWd_h, n->tmWr_h, p);
     if (e1) cudaEventRecord(e1, st);
     AP_LAUNCH_CHECK();
   }
@@ -931,7 +994,8 @@ int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, i
   K2Params p;
   p.n_tiles = n_tiles, p.tiles_per_sample = tps, p.L = L, p.num_layers = n->N, p.chunk_alloc = n->chunk;
   p.scale = static_cast<float>(std::sqrt(1.0 / n->N));
-  p.bskip = n->bskip.as<float>(), p.bf1 = n->bf1.as<float>(), p.wf2 = n->wf2.as<float>(), p.bf2 = n->bf2.as<float>();
+  p.bf2 = n->bf2.as<float>();
+  for (int c = 0; c < C; ++c) p.bskip_scaled[c] = n->bskip_host[c] * p.scale, p.bf1[c] = n->bf1_host[c], p.wf2[c] = n->wf2_host[c];
   p.eps = eps;
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   cudaEvent_t e0 = prof_event(n, 1), e1 = e0 ? prof_event(n, 1) : nullptr;

@@ -44,7 +44,7 @@ def main():
         buf = np.zeros((256, 16), dtype=np.int64)
         _lib.check(lib.ap_diffwave_debug_counters(net._handle, buf.ctypes.data))
         names = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_accempty", "mma_wait_outready", "mma_total",
-                 "tiles", "epi_wait_accfull", "epi_wait_uc", "epi_total"]
+                 "tiles", "epi_wait_accfull", "epi_wait_g2", "epi_total", "epi_wait_bulk"]
         act = buf[buf[:, 1] > 0]
         lead = act[act[:, 5] > 0]
         print(f"active CTAs {len(act)}, MMA-issuing CTAs {len(lead)} (last k1 launch; cycles, mean over CTAs)")

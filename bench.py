@@ -39,7 +39,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=512, help="waveforms per GPU per step")
-    p.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32"])
+    p.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32", "bf16x3"])
     p.add_argument("--chunk", type=int, default=0, help="waveforms per workspace chunk (0 = library default)")
     p.add_argument("--certify-draws", type=int, default=4096, help="extra certification leg (0 = skip)")
     p.add_argument("--cpu-sample", type=int, default=2, help="waveforms in the cpu_baseline sample (0 = skip)")
@@ -294,11 +294,12 @@ def run_ours(args):
             roofline = {"kernel": "k1_layer (DiffWave residual block: tcgen05 implicit GEMM K=768/N=512 + K=256/N=256, fused "
                                   "gate / residual epilogues)", "bound": "tensor", "achieved": achieved,
                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
-                        "traffic": 24.19e6 * avg_wf,
+                        "traffic": 24.19e6 * avg_wf if args.mode != "bf16x3" else None,
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum = 3.097e9 B for a 128-waveform launch "
                                           "(profiles/r01_k1_pair_ncu_full_summary.txt; algorithmic 3.146e9 B), scaled to this "
-                                          "run's waveforms per launch",
+                                          "run's waveforms per launch" if args.mode != "bf16x3" else "no ncu capture of the split kernel",
                         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                        "mma_flops_per_algorithmic_flop": 3 if args.mode == "bf16x3" else 1,
                         "avg_launch_ms": k1_ms, "launches": int(prof_n[0]), "waveforms_per_launch": avg_wf,
                         "share_of_step": prof_ms[0] / ms,
                         "k2_head": {"avg_launch_ms": prof_ms[1] / max(prof_n[1], 1), "launches": int(prof_n[1]),

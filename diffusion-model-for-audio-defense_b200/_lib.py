@@ -12,7 +12,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # AP_LIB_PATH: development aid (devtools/ab_compare.py loads two builds of the library back to back on one GPU box)
 LIB_PATH = os.environ.get("AP_LIB_PATH") or os.path.join(_PKG_DIR, "libaudiopure_b200.so")
 
-AP_MODE_BF16, AP_MODE_FP32, AP_MODE_TF32, AP_MODE_FP16 = 0, 1, 2, 3
+AP_MODE_BF16, AP_MODE_FP32, AP_MODE_TF32, AP_MODE_FP16, AP_MODE_BF16X3 = 0, 1, 2, 3, 4
 AP_CLS_RESNEXT, AP_CLS_M5, AP_CLS_KWS, AP_CLS_RESNET = 0, 1, 2, 3
 
 

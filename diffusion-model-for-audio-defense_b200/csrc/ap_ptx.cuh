@@ -150,9 +150,9 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 __device__ __forceinline__ float f16_lo(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xffffu))); }
 __device__ __forceinline__ float f16_hi(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16))); }
 // DT = 0: bf16, DT = 1: fp16
-template <int DT> __device__ __forceinline__ uint32_t pack2(float lo, float hi) { return DT == 0 ? pack_bf16x2(lo, hi) : pack_f16x2(lo, hi); }
-template <int DT> __device__ __forceinline__ float unpack_lo(uint32_t v) { return DT == 0 ? bf16_lo(v) : f16_lo(v); }
-template <int DT> __device__ __forceinline__ float unpack_hi(uint32_t v) { return DT == 0 ? bf16_hi(v) : f16_hi(v); }
+template <int DT> __device__ __forceinline__ uint32_t pack2(float lo, float hi) { return DT == 1 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+template <int DT> __device__ __forceinline__ float unpack_lo(uint32_t v) { return DT == 1 ? f16_lo(v) : bf16_lo(v); }
+template <int DT> __device__ __forceinline__ float unpack_hi(uint32_t v) { return DT == 1 ? f16_hi(v) : bf16_hi(v); }
 
 // ------------------------------------------------------------------ TMEM allocation (one full warp executes these)
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -294,5 +294,15 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f); }
+// fp32-class variants (absolute error ~1e-7): tanh(x) = 1 - 2 / (1 + e^{2x}), sigmoid(x) = 1 / (1 + e^{-x}).
+// Saturation is exact: e^{2x} -> inf gives 1, e^{2x} -> 0 gives -1 (x clamped so that 1 + e^{..} stays below 2^126,
+// the range in which the fast division is accurate).
+__device__ __forceinline__ float tanh_exp(float x) {
+  const float e = __expf(2.f * fminf(fmaxf(x, -40.f), 40.f));
+  return 1.f - __fdividef(2.f, 1.f + e);
+}
+__device__ __forceinline__ float sigmoid_exp(float x) {
+  return __fdividef(1.f, 1.f + __expf(-fminf(fmaxf(x, -80.f), 80.f)));
+}
 
 }}  // namespace ap::ptx

@@ -314,10 +314,12 @@ extern "C" void ap_diffwave_destroy(ap_diffwave_t h) {
 
 extern "C" int ap_diffwave_set_mode(ap_diffwave_t h, int mode) {
   AP_REQUIRE(h, "ap_diffwave_set_mode: null handle");
-  AP_REQUIRE(mode == AP_MODE_BF16 || mode == AP_MODE_FP32 || mode == AP_MODE_FP16, "ap_diffwave_set_mode: unknown mode %d", mode);
+  AP_REQUIRE(mode == AP_MODE_BF16 || mode == AP_MODE_FP32 || mode == AP_MODE_FP16 || mode == AP_MODE_BF16X3,
+             "ap_diffwave_set_mode: unknown mode %d", mode);
   if (mode != AP_MODE_FP32 && !h->tc_capable)
     return fail(AP_ERR_INVALID, "ap_diffwave_set_mode: the tensor-core kernels need res_channels == skip_channels == 256");
-  if (mode != AP_MODE_FP32) tc_net_set_dtype(h->tc, mode == AP_MODE_FP16);
+  if (mode != AP_MODE_FP32) tc_net_set_dtype(h->tc, mode == AP_MODE_FP16 ? 1 : (mode == AP_MODE_BF16X3 ? 2 : 0));
+  if (mode != h->mode && (mode == AP_MODE_BF16X3 || h->mode == AP_MODE_BF16X3)) h->tc_chunk = 0;   // workspace layout changes
   h->mode = mode;
   return AP_OK;
 }
@@ -411,7 +413,8 @@ extern "C" int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* 
   if (chunk == 0 || curL != L) {
     // default chunk: bounded workspace (fp32: 4 * 4 B * 256 ch per position; bf16: ~2.5 KB per position incl. gate history)
     // bf16: 148 waveforms of 1 s = 18500 tiles = 125 full rounds over 74 CTA pairs (no ragged last wave)
-    const long long budget_positions = tc ? 148ll * 16000 : (1ll << 18);
+    // bf16x3: two planes per tensor, so half as many waveforms in the same workspace
+    const long long budget_positions = tc ? (h->mode == AP_MODE_BF16X3 ? 74ll : 148ll) * 16000 : (1ll << 18);
     long long want = budget_positions / L;
     if (want < 1) want = 1;
     if (want > B) want = B;

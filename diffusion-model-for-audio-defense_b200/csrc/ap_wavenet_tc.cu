@@ -48,18 +48,25 @@ constexpr int EPI_THREADS = 256;
 //         drop from 192 to 128 B/clk per SM (shared memory delivers 128 B/clk, which capped CG = 1 at ~63 % tensor duty).
 // KIND 1 = k1_layer, KIND 2 = k2_head.  Per-channel biases are kernel parameters (constant bank), so shared memory holds
 // only the TMA ring (5 stages in pair mode), one 64 KB staging tile and 1 KB of scratch.
+//
+// DT = 2 ("bf16x3", AP_MODE_BF16X3): fp32-class arithmetic on the bf16 tensor cores.  Every activation and weight is kept as
+// a pair of bf16 planes hi = bf16(v), lo = bf16(v - hi) (16 significand bits together) and every product is accumulated
+// as hi*hi + lo*hi + hi*lo in fp32 (the dropped lo*lo term is below 2^-18 relative), i.e. three MMAs per K step.  The
+// staging tile holds both planes (128 KB), which leaves a 3-stage ring.
 template <int CG_, int KIND, int DT_ = 0> struct Geo {
   static constexpr int CG = CG_;
-  static constexpr int DT = DT_;   // 0: bf16 operands, 1: fp16 operands
+  static constexpr int DT = DT_;   // 0: bf16 operands, 1: fp16 operands, 2: bf16 hi/lo split operands
+  static constexpr bool SPLIT = DT_ == 2;
+  static constexpr int NCOMBO = SPLIT ? 3 : 1;   // (A plane, B plane) pairs per K block: (hi,hi) [, (lo,hi), (hi,lo)]
   static constexpr int B_ROWS = 256 / CG;
   static constexpr int B_BYTES = B_ROWS * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = CG == 1 ? 3 : 5;
+  static constexpr int NSTAGE = CG == 1 ? (SPLIT ? 2 : 3) : (SPLIT ? 3 : 5);
   static constexpr int OUT_OFF = NSTAGE * STAGE_BYTES;
-  static constexpr int BIAS_OFF = OUT_OFF + OUT_BYTES;
+  static constexpr int BIAS_OFF = OUT_OFF + (SPLIT ? 2 : 1) * OUT_BYTES;
   static constexpr int BAR_OFF = BIAS_OFF + 1024;   // k1: c2[256]; k2: 128 partial dots
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + slack to align the base to 1024 B
-  static constexpr uint32_t IDESC = DT_ == 0 ? umma_idesc_bf16_f32(128 * CG, 256) : umma_idesc_f16_f32(128 * CG, 256);
+  static constexpr uint32_t IDESC = DT_ == 1 ? umma_idesc_f16_f32(128 * CG, 256) : umma_idesc_bf16_f32(128 * CG, 256);
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
   static_assert(NSTAGE <= 5, "barrier table holds at most 5 stages");
 };
@@ -170,6 +177,9 @@ struct K1Params {
   const uint16_t* u_in; // [chunk][L][256] this layer's input (also read through tmUin as the GEMM-1 A operand)
   uint16_t* u_out;      // [chunk][L][256] next layer's input
   long long* dbg;       // optional [gridDim.x][16] wait-cycle counters (development aid), or null
+  // hi/lo split mode (DT = 2): offset of the lo plane in the third coordinate of the U / O tensor maps and in the rows of
+  // the Wd / Wr maps (0 otherwise); the lo plane of u_in / u_out starts u_plane * L * 256 elements after the hi plane
+  int u_plane, o_plane, wd_plane, wr_plane;
   // dilated-conv biases in packed chunk order: [j][0..127] tanh bias of gate channel 128 j + c, [j][128..255] HALF the
   // sigmoid bias of the same channel (sigmoid(s) = 0.5 tanh(0.5 s) + 0.5).  They live in the kernel-parameter constant
   // bank, so the bias add is a constant operand of the FADD / FFMA: no shared-memory or shuffle traffic in the epilogue.
@@ -216,6 +226,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     __syncwarp();
     if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);   // accumulators are in registers: the region is free again
     uint32_t pk[2][4][4];
+    uint32_t pl[G::SPLIT ? 2 : 1][4][4];   // lo plane (split mode)
 #pragma unroll
     for (int gq = 0; gq < 2; ++gq)
 #pragma unroll
@@ -224,11 +235,27 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
         for (int e = 0; e < 4; ++e) {
           const int c0 = i * 8 + 2 * e;
           const int cb = J * 256 + HSEL * 64 + gq * 32 + c0;
-          const float t0 = tanh_approx(__uint_as_float(ta[gq][c0]) + p.bd[cb]);
-          const float t1 = tanh_approx(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]);
-          const float s0 = tanh_approx(fmaf(__uint_as_float(sg[gq][c0]), 0.5f, p.bd[cb + 128]));
-          const float s1 = tanh_approx(fmaf(__uint_as_float(sg[gq][c0 + 1]), 0.5f, p.bd[cb + 129]));
-          pk[gq][i][e] = pack2<DT>(t0 * fmaf(s0, 0.5f, 0.5f), t1 * fmaf(s1, 0.5f, 0.5f));
+          if constexpr (G::SPLIT) {
+            // fp32-class gate: exp-based tanh / sigmoid (MUFU.TANH is good to ~2^-11 only); p.bd holds HALF the sigmoid bias
+            const float o0 = tanh_exp(__uint_as_float(ta[gq][c0]) + p.bd[cb]) *
+                             sigmoid_exp(fmaf(2.f, p.bd[cb + 128], __uint_as_float(sg[gq][c0])));
+            const float o1 = tanh_exp(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]) *
+                             sigmoid_exp(fmaf(2.f, p.bd[cb + 129], __uint_as_float(sg[gq][c0 + 1])));
+            const uint32_t hi = pack_bf16x2(o0, o1);
+            pk[gq][i][e] = hi;
+            pl[gq][i][e] = pack_bf16x2(o0 - bf16_lo(hi), o1 - bf16_hi(hi));
+          } else {
+            const float t0 = tanh_approx(__uint_as_float(ta[gq][c0]) + p.bd[cb]);
+            const float t1 = tanh_approx(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]);
+            const float s0 = tanh_approx(fmaf(__uint_as_float(sg[gq][c0]), 0.5f, p.bd[cb + 128]));
+            const float s1 = tanh_approx(fmaf(__uint_as_float(sg[gq][c0 + 1]), 0.5f, p.bd[cb + 129]));
+#ifdef AP_ABLATE_NO_MATH
+            pk[gq][i][e] = ta[gq][c0] ^ sg[gq][c0 + 1];
+            (void)t0, (void)t1, (void)s0, (void)s1;
+#else
+            pk[gq][i][e] = pack2<DT>(t0 * fmaf(s0, 0.5f, 0.5f), t1 * fmaf(s1, 0.5f, 0.5f));
+#endif
+          }
         }
     // the staging tile still holds o of the previous tile until its GEMM-2 (the NEXT job, g + 1) has completed
     if (etid == 0) {                                       // and the O store of chunk J of the previous tile has read it
@@ -245,14 +272,26 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
 #pragma unroll
     for (int gq = 0; gq < 2; ++gq)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) {
         st_shared_v4(kb_base + (((gq * 4 + i) ^ sw) << 4), make_uint4(pk[gq][i][0], pk[gq][i][1], pk[gq][i][2], pk[gq][i][3]));
+        if constexpr (G::SPLIT)   // lo plane: K-blocks 4..7 of the staging tile
+          st_shared_v4(kb_base + 4 * A_BYTES + (((gq * 4 + i) ^ sw) << 4),
+                       make_uint4(pl[gq][i][0], pl[gq][i][1], pl[gq][i][2], pl[gq][i][3]));
+      }
     fence_proxy_async_smem();
     named_bar_sync(1, EPI_THREADS);
     if (etid == 0) {
+#ifdef AP_ABLATE_NO_OSTORE
+      if (false) {
+#else
       if (valid) {
+#endif
         tma_store_3d(tmO, cx.out_kb(2 * J), (2 * J) * 64, l0, p.layer * p.chunk_alloc + b);
         tma_store_3d(tmO, cx.out_kb(2 * J + 1), (2 * J + 1) * 64, l0, p.layer * p.chunk_alloc + b);
+        if constexpr (G::SPLIT) {
+          tma_store_3d(tmO, cx.out_kb(4 + 2 * J), (2 * J) * 64, l0, p.o_plane + p.layer * p.chunk_alloc + b);
+          tma_store_3d(tmO, cx.out_kb(4 + 2 * J + 1), (2 * J + 1) * 64, l0, p.o_plane + p.layer * p.chunk_alloc + b);
+        }
       }
       bulk_commit();                                       // always a group (possibly empty): wait_group counts stay uniform
       cx.arrive_leader(BAR_OUT_READY + J);
@@ -263,12 +302,19 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
   // ---- residual epilogue: u' = (u + r) * sqrt(.5) + (b_res * sqrt(.5) + p_next) -> bf16, global -> registers -> global
   auto residual = [&](bool valid, int b, int l0) {
     const uint32_t r = g & 1;
+#ifdef AP_ABLATE_NO_RESID_IO
+    const bool live = false;
+#else
     const bool live = valid && l0 + row < p.L;
+#endif
     const size_t goff = (static_cast<size_t>(b) * p.L + (live ? l0 + row : 0)) * C + HSEL * 128;
-    uint32_t uu[8][8];
-    if (live) {
+    const size_t lo_off = static_cast<size_t>(p.u_plane) * p.L * C;     // split mode: the lo plane
+    uint32_t uu[G::SPLIT ? 1 : 8][8];
+    if constexpr (!G::SPLIT) {
+      if (live) {
 #pragma unroll
-      for (int v = 0; v < 8; ++v) ld_global_v8(p.u_in + goff + v * 16, uu[v]);
+        for (int v = 0; v < 8; ++v) ld_global_v8(p.u_in + goff + v * 16, uu[v]);
+      }
     }
     w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 10);
     tc_fence_after();
@@ -283,20 +329,41 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
         if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
       }
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {                        // 16 channels = one 32-byte access
+      for (int i = 0; i < 2; ++i) {                        // 16 channels = one 32-byte access (per plane)
         const int ch = HSEL * 128 + gq * 32 + i * 16;
-        uint32_t pk[8];
+        uint32_t pk[8], pl[8], uh[8], ul[8];
+        if constexpr (G::SPLIT) {
+          if (live) {
+            ld_global_v8(p.u_in + goff + (gq * 2 + i) * 16, uh);
+            ld_global_v8(p.u_in + lo_off + goff + (gq * 2 + i) * 16, ul);
+          }
+        }
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4) {
           const uint4 cv = ld_shared_v4(c2_addr + (ch + e4 * 4) * 4);   // warp-uniform address: broadcast
-          const uint32_t w0 = uu[gq * 2 + i][e4 * 2], w1 = uu[gq * 2 + i][e4 * 2 + 1];
+          const float cc[4] = {__uint_as_float(cv.x), __uint_as_float(cv.y), __uint_as_float(cv.z), __uint_as_float(cv.w)};
           const int a0 = i * 16 + e4 * 4;
-          pk[e4 * 2] = pack2<DT>(fmaf(unpack_lo<DT>(w0) + __uint_as_float(acc[a0]), sqrt_half, __uint_as_float(cv.x)),
-                                 fmaf(unpack_hi<DT>(w0) + __uint_as_float(acc[a0 + 1]), sqrt_half, __uint_as_float(cv.y)));
-          pk[e4 * 2 + 1] = pack2<DT>(fmaf(unpack_lo<DT>(w1) + __uint_as_float(acc[a0 + 2]), sqrt_half, __uint_as_float(cv.z)),
-                                     fmaf(unpack_hi<DT>(w1) + __uint_as_float(acc[a0 + 3]), sqrt_half, __uint_as_float(cv.w)));
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float u0, u1;
+            if constexpr (G::SPLIT) {
+              u0 = bf16_lo(uh[e4 * 2 + h]) + bf16_lo(ul[e4 * 2 + h]);
+              u1 = bf16_hi(uh[e4 * 2 + h]) + bf16_hi(ul[e4 * 2 + h]);
+            } else {
+              u0 = unpack_lo<DT>(uu[gq * 2 + i][e4 * 2 + h]);
+              u1 = unpack_hi<DT>(uu[gq * 2 + i][e4 * 2 + h]);
+            }
+            const float v0 = fmaf(u0 + __uint_as_float(acc[a0 + 2 * h]), sqrt_half, cc[2 * h]);
+            const float v1 = fmaf(u1 + __uint_as_float(acc[a0 + 2 * h + 1]), sqrt_half, cc[2 * h + 1]);
+            const uint32_t hi = pack2<DT>(v0, v1);
+            pk[e4 * 2 + h] = hi;
+            if constexpr (G::SPLIT) pl[e4 * 2 + h] = pack_bf16x2(v0 - bf16_lo(hi), v1 - bf16_hi(hi));
+          }
         }
-        if (live) st_global_v8(p.u_out + goff + (gq * 2 + i) * 16, pk);
+        if (live) {
+          st_global_v8(p.u_out + goff + (gq * 2 + i) * 16, pk);
+          if constexpr (G::SPLIT) st_global_v8(p.u_out + lo_off + goff + (gq * 2 + i) * 16, pl);
+        }
       }
     }
     ++g;
@@ -350,21 +417,24 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
       uint32_t it = 0, ti = 0;
       long long w_empty = 0;
       const long long t_start = clock64();
+      // split mode: per K block the (A plane, B plane) pairs (hi,hi), (lo,hi), (hi,lo), each its own ring stage
       auto load_g1 = [&](int j, bool valid, int b, int l0) {
         for (int tap = 0; tap < 3; ++tap)
-          for (int kb = 0; kb < 4; ++kb, ++it) {
-            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-            w_empty += cx.arm(s, ph, G::STAGE_BYTES, 1);
-            cx.load_a(s, &tmUin, kb * 64, valid ? l0 + (tap - 1) * p.dilation : oob_l0, b);
-            cx.load_b(s, &tmWd, tap * C + kb * 64, (p.layer * 2 + j) * 256);
-          }
+          for (int kb = 0; kb < 4; ++kb)
+            for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
+              const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+              w_empty += cx.arm(s, ph, G::STAGE_BYTES, 1);
+              cx.load_a(s, &tmUin, kb * 64, valid ? l0 + (tap - 1) * p.dilation : oob_l0, b + (cmb == 1 ? p.u_plane : 0));
+              cx.load_b(s, &tmWd, tap * C + kb * 64, (p.layer * 2 + j) * 256 + (cmb == 2 ? p.wd_plane : 0));
+            }
       };
       auto load_wr = [&]() {
-        for (int kb = 0; kb < 4; ++kb, ++it) {
-          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-          w_empty += cx.arm(s, ph, G::B_BYTES, 2);
-          cx.load_b(s, &tmWr, kb * 64, p.layer * 256);
-        }
+        for (int kb = 0; kb < 4; ++kb)
+          for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
+            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+            w_empty += cx.arm(s, ph, G::B_BYTES, 2);
+            cx.load_b(s, &tmWr, kb * 64, p.layer * 256 + (cmb == 2 ? p.wr_plane : 0));
+          }
       };
       for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
         const bool valid = tile < p.n_tiles;
@@ -388,7 +458,7 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
         const uint32_t r = g & 1;
         w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 3);
         tc_fence_after();
-        for (int kblk = 0; kblk < 12; ++kblk, ++it) {
+        for (int kblk = 0; kblk < 12 * G::NCOMBO; ++kblk, ++it) {
           const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
           w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 4);
           tc_fence_after();
@@ -402,13 +472,15 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
         const uint32_t r = g & 1;
         w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 5);
         tc_fence_after();
-        for (int kb = 0; kb < 4; ++kb, ++it) {
-          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+        for (int kb = 0; kb < 4; ++kb) {
           if ((kb & 1) == 0) w_out += mbar_wait(cx.bar(BAR_OUT_READY + (kb >> 1)), t_idx & 1, 6);
-          w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 8);
-          tc_fence_after();
-          cx.mma_kblock(tmem + r * 256, cx.out_kb(kb), cx.stage_b(s), kb == 0);
-          cx.commit(BAR_EMPTY + s);
+          for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
+            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+            w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 8);
+            tc_fence_after();
+            cx.mma_kblock(tmem + r * 256, cx.out_kb(kb + (cmb == 1 ? 4 : 0)), cx.stage_b(s), kb == 0 && cmb == 0);
+            cx.commit(BAR_EMPTY + s);
+          }
         }
         cx.commit(BAR_ACC_FULL + r);
         ++g;
@@ -441,6 +513,7 @@ struct K2Params {
   float scale;           // sqrt(1/N)
   const float* bf2;      // [1]
   float* eps;            // [B][L]
+  int o_plane, ws_plane, wf_plane;   // hi/lo split mode (DT = 2): offsets of the lo planes in the O / Ws / Wf tensor maps
   // per-channel vectors in the kernel-parameter constant bank (constant operands of the epilogue FMAs):
   float bskip_scaled[256];   // (sum over layers of the skip-conv biases) * sqrt(1/N)
   float bf1[256];            // final_conv.0 bias
@@ -476,14 +549,18 @@ __device__ __forceinline__ void k2_epilogue(const Ctx<G>& cx, const K2Params& p,
       const uint32_t kb_base = cx.out_kb(HSEL * 2 + (gq >> 1)) + row_off;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint32_t pk[4];
+        uint32_t pk[4], pl[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c0 = HSEL * 128 + gq * 32 + i * 8 + 2 * e;
-          pk[e] = pack2<DT>(fmaf(__uint_as_float(acc[i * 8 + 2 * e]), p.scale, p.bskip_scaled[c0]),
-                            fmaf(__uint_as_float(acc[i * 8 + 2 * e + 1]), p.scale, p.bskip_scaled[c0 + 1]));
+          const float v0 = fmaf(__uint_as_float(acc[i * 8 + 2 * e]), p.scale, p.bskip_scaled[c0]);
+          const float v1 = fmaf(__uint_as_float(acc[i * 8 + 2 * e + 1]), p.scale, p.bskip_scaled[c0 + 1]);
+          pk[e] = pack2<DT>(v0, v1);
+          if constexpr (G::SPLIT) pl[e] = pack_bf16x2(v0 - bf16_lo(pk[e]), v1 - bf16_hi(pk[e]));
         }
         st_shared_v4(kb_base + ((((gq & 1) * 4 + i) ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        if constexpr (G::SPLIT)
+          st_shared_v4(kb_base + 4 * A_BYTES + ((((gq & 1) * 4 + i) ^ sw) << 4), make_uint4(pl[0], pl[1], pl[2], pl[3]));
       }
     }
     tc_fence_before();
@@ -527,7 +604,7 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
   if (threadIdx.x == 0) prefetch_tmap(&tmO), prefetch_tmap(&tmWs), prefetch_tmap(&tmWf);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = p.num_layers * 4;
+  const int nkb = p.num_layers * 4 * G::NCOMBO;
   const Tiles<CG> tiles(p.n_tiles, cx.rank);
   const int oob_l0 = p.tiles_per_sample * TILE_M;
 
@@ -539,17 +616,19 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
         const int b = valid ? tile / p.tiles_per_sample : 0;
         const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
         for (int n = 0; n < p.num_layers; ++n)
-          for (int kb = 0; kb < 4; ++kb, ++it) {
+          for (int kb = 0; kb < 4; ++kb)
+            for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
+              const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+              cx.arm(s, ph, G::STAGE_BYTES, 21);
+              cx.load_a(s, &tmO, kb * 64, l0, n * p.chunk_alloc + b + (cmb == 1 ? p.o_plane : 0));
+              cx.load_b(s, &tmWs, kb * 64, n * 256 + (cmb == 2 ? p.ws_plane : 0));
+            }
+        for (int kb = 0; kb < 4; ++kb)
+          for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
             const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-            cx.arm(s, ph, G::STAGE_BYTES, 21);
-            cx.load_a(s, &tmO, kb * 64, l0, n * p.chunk_alloc + b);
-            cx.load_b(s, &tmWs, kb * 64, n * 256);
+            cx.arm(s, ph, G::B_BYTES, 22);
+            cx.load_b(s, &tmWf, kb * 64, cmb == 2 ? p.wf_plane : 0);
           }
-        for (int kb = 0; kb < 4; ++kb, ++it) {
-          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-          cx.arm(s, ph, G::B_BYTES, 22);
-          cx.load_b(s, &tmWf, kb * 64, 0);
-        }
       }
     }
     __syncwarp();
@@ -570,13 +649,14 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
         mbar_wait(cx.bar(BAR_ACC_EMPTY + 1), (ti & 1) ^ 1, 25);
         mbar_wait(cx.bar(BAR2_S_READY), ti & 1, 26);
         tc_fence_after();
-        for (int kb = 0; kb < 4; ++kb, ++it) {
-          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-          mbar_wait(cx.bar(BAR_FULL + s), ph, 27);
-          tc_fence_after();
-          cx.mma_kblock(tmem + 256, cx.out_kb(kb), cx.stage_b(s), kb == 0);
-          cx.commit(BAR_EMPTY + s);
-        }
+        for (int kb = 0; kb < 4; ++kb)
+          for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
+            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+            mbar_wait(cx.bar(BAR_FULL + s), ph, 27);
+            tc_fence_after();
+            cx.mma_kblock(tmem + 256, cx.out_kb(kb + (cmb == 1 ? 4 : 0)), cx.stage_b(s), kb == 0 && cmb == 0);
+            cx.commit(BAR_EMPTY + s);
+          }
         cx.commit(BAR_ACC_FULL + 1);
       }
     }
@@ -612,6 +692,41 @@ __global__ void __launch_bounds__(256) init_h16_kernel(const float* __restrict__
     }
     u[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
+}
+
+// split mode: u0 as hi / lo bf16 planes (`lo_off` uint4 elements apart)
+__global__ void __launch_bounds__(256) init_split_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ b, const float* __restrict__ p0,
+                                                          uint4* __restrict__ u, long long lo_off, long long M) {
+  __shared__ float sw[C], sb[C], sp[C];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[i] = w[i], sb[i] = b[i], sp[i] = p0[i];
+  __syncthreads();
+  const long long total = M * (C / 8);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i >> 5;
+    const int c = static_cast<int>(i & 31) * 8;
+    const float xv = x[m];
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // the same roundings as the fp32 path (init_f32_kernel): mul, add, relu, add
+      const float v0 = __fadd_rn(fmaxf(__fadd_rn(__fmul_rn(sw[c + 2 * e], xv), sb[c + 2 * e]), 0.f), sp[c + 2 * e]);
+      const float v1 = __fadd_rn(fmaxf(__fadd_rn(__fmul_rn(sw[c + 2 * e + 1], xv), sb[c + 2 * e + 1]), 0.f), sp[c + 2 * e + 1]);
+      ph[e] = pack_bf16x2(v0, v1);
+      pl[e] = pack_bf16x2(v0 - bf16_lo(ph[e]), v1 - bf16_hi(ph[e]));
+    }
+    u[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    u[lo_off + i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+// hi + lo planes -> fp32 (debug dumps, split mode)
+__global__ void split_to_f32_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, float* __restrict__ out,
+                                    long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = bf16_lo(hi[i]) + bf16_lo(lo[i]);
 }
 
 // bf16 -> fp32 (debug dumps)
@@ -725,7 +840,10 @@ struct TcNet {
   int N = 0;
   DevBuf wd, wr, ws, wf;                                   // bf16 operands
   DevBuf wd_h, wr_h, ws_h, wf_h;                           // fp16 operands (AP_MODE_FP16)
-  int dt = 0;                                              // 0: bf16, 1: fp16
+  DevBuf wd_s, wr_s, ws_s, wf_s;                           // bf16 hi plane followed by the lo plane (AP_MODE_BF16X3)
+  CUtensorMap tmWd_s, tmWr_s, tmWs_s, tmWf_s;              // over both planes, box of 128 rows (CTA pairs only)
+  int dt = 0;                                              // 0: bf16, 1: fp16, 2: bf16 hi/lo split (bf16x3)
+  bool ws_split = false;                                   // layout of the reserved workspace (two planes per tensor)
   DevBuf br, bf2, init_w, init_b;                          // fp32 vectors
   std::vector<float> bskip_host, bf1_host, wf2_host;       // k2's per-channel vectors (kernel params)
   std::vector<float> bd_host;                              // [N][512] dilated-conv biases in k1's packed order (kernel params)
@@ -845,6 +963,22 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
   TRY(upload_bf16(n->wr_h, to_f16(wr, wr_f)));
   TRY(upload_bf16(n->ws_h, to_f16(ws, ws_f)));
   TRY(upload_bf16(n->wf_h, to_f16(wf, wf_f)));
+  auto to_split = [](const std::vector<float>& src) {   // hi plane, then lo = bf16(v - hi)
+    std::vector<uint16_t> out(2 * src.size());
+    for (size_t i = 0; i < src.size(); ++i) {
+      const uint16_t hi = f32_to_bf16_rne(src[i]);
+      uint32_t hb = static_cast<uint32_t>(hi) << 16;
+      float hf;
+      std::memcpy(&hf, &hb, 4);
+      out[i] = hi;
+      out[src.size() + i] = f32_to_bf16_rne(src[i] - hf);
+    }
+    return out;
+  };
+  TRY(upload_bf16(n->wd_s, to_split(wd_f)));
+  TRY(upload_bf16(n->wr_s, to_split(wr_f)));
+  TRY(upload_bf16(n->ws_s, to_split(ws_f)));
+  TRY(upload_bf16(n->wf_s, to_split(wf_f)));
   n->bd_host = bd;
   TRY(upload_f32(n->br, br));
   n->bskip_host = bskip;
@@ -874,6 +1008,11 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
     TRY(encode_bf16(&n->tmWr2_h, n->wr_h.p, 2, d2, bw2));
     TRY(encode_bf16(&n->tmWs2_h, n->ws_h.p, 2, d2, bw2));
     TRY(encode_bf16(&n->tmWf2_h, n->wf_h.p, 2, d3, bw2));
+    const uint64_t s1[2] = {768, static_cast<uint64_t>(N) * 1024}, s2[2] = {256, static_cast<uint64_t>(N) * 512}, s3[2] = {256, 512};
+    TRY(encode_bf16(&n->tmWd_s, n->wd_s.p, 2, s1, bw2));
+    TRY(encode_bf16(&n->tmWr_s, n->wr_s.p, 2, s2, bw2));
+    TRY(encode_bf16(&n->tmWs_s, n->ws_s.p, 2, s2, bw2));
+    TRY(encode_bf16(&n->tmWf_s, n->wf_s.p, 2, s3, bw2));
     const char* env = std::getenv("AP_TC_PAIR");
     if (env && env[0] == '0') n->pair = false;
     if (const char* e2 = std::getenv("AP_TC_DEBUG_LAYER")) n->dbg_layer = std::atoi(e2);
@@ -893,19 +1032,21 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
 }
 
 void tc_net_destroy(TcNet* n) { delete n; }
-void tc_net_set_dtype(TcNet* n, int dt) { n->dt = dt ? 1 : 0; }
+void tc_net_set_dtype(TcNet* n, int dt) { n->dt = dt; }
 
 size_t tc_net_workspace_bytes(const TcNet* n) { return n->u0.bytes + n->u1.bytes + n->o.bytes; }
 
 int tc_net_reserve(TcNet* n, int chunk, int L) {
   using namespace tc;
-  const size_t per = static_cast<size_t>(chunk) * L * C * sizeof(uint16_t);
+  const int planes = n->dt == 2 ? 2 : 1;   // split mode: hi plane [chunk] followed by the lo plane [chunk]
+  const size_t per = static_cast<size_t>(planes) * chunk * L * C * sizeof(uint16_t);
+  n->u0.release(), n->u1.release(), n->o.release();
   AP_CUDA(n->u0.alloc(per));
   AP_CUDA(n->u1.alloc(per));
   AP_CUDA(n->o.alloc(per * n->N));
-  n->chunk = chunk, n->L = L;
-  const uint64_t du[3] = {256, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk)};
-  const uint64_t dO[3] = {256, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk) * n->N};
+  n->chunk = chunk, n->L = L, n->ws_split = planes == 2;
+  const uint64_t du[3] = {256, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk) * planes};
+  const uint64_t dO[3] = {256, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk) * n->N * planes};
   const uint32_t bx[3] = {64, 128, 1};
   int rc = encode_bf16(&n->tmU[0], n->u0.p, 3, du, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmU[1], n->u1.p, 3, du, bx);
@@ -920,6 +1061,8 @@ int tc_net_reserve(TcNet* n, int chunk, int L) {
     AP_CUDA(cudaFuncSetAttribute(k2_head<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k2_head<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2, 2>::SMEM_BYTES));
     n->attr_set = true;
   }
   return AP_OK;
@@ -948,7 +1091,11 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     long long blocks = ceil_div_ll(M * (C / 8), 256);
     const long long cap = static_cast<long long>(num_sms()) * 8;
     if (blocks > cap) blocks = cap;
-    if (n->dt == 0)
+    if (n->dt == 2)
+      init_split_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n->init_w.as<float>(), n->init_b.as<float>(), ptab,
+                                                                       n->u0.as<uint4>(),
+                                                                       static_cast<long long>(n->chunk) * L * (C / 8), M);
+    else if (n->dt == 0)
       init_h16_kernel<0><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n->init_w.as<float>(), n->init_b.as<float>(), ptab,
                                                                         n->u0.as<uint4>(), M);
     else
@@ -968,10 +1115,14 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     p.b_res = n->br.as<float>() + static_cast<size_t>(l) * C;
     p.p_next = ptab + static_cast<size_t>(l + 1) * C;
     p.dbg = (l == n->dbg_layer) ? n->dbg.as<long long>() : nullptr;
+    p.u_plane = p.o_plane = p.wd_plane = p.wr_plane = 0;
+    if (n->dt == 2) p.u_plane = n->chunk, p.o_plane = n->N * n->chunk, p.wd_plane = n->N * 512, p.wr_plane = n->N * 256;
     cudaEvent_t e0 = prof_event(n, 0), e1 = e0 ? prof_event(n, 0) : nullptr;
     if (e1) cudaEventRecord(e0, st);
     const CUtensorMap& ui = n->tmU[l & 1];
-    if (n->pair && n->dt == 0)
+    if (n->dt == 2)
+      AP_CUDA(launch_pair(k1_layer<2, 2>, pair_grid(n_tiles), Geo<2, 1, 2>::SMEM_BYTES, st, ui, n->tmO, n->tmWd_s, n->tmWr_s, p));
+    else if (n->pair && n->dt == 0)
       AP_CUDA(launch_pair(k1_layer<2, 0>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2, n->tmWr2, p));
     else if (n->pair)
       AP_CUDA(launch_pair(k1_layer<2, 1>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2_h, n->tmWr2_h, p));
@@ -987,7 +1138,9 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
 
 int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st) {
   using namespace tc;
-  if (B > n->chunk || L != n->L) return fail(AP_ERR_STATE, "tc_net_eps: workspace reserved for chunk %d x L %d", n->chunk, n->L);
+  if (B > n->chunk || L != n->L || n->ws_split != (n->dt == 2))
+    return fail(AP_ERR_STATE, "tc_net_eps: workspace reserved for chunk %d x L %d (%s layout)", n->chunk, n->L,
+                n->ws_split ? "split" : "single-plane");
   int rc = tc_run_layers(n, x, ptab, B, L, n->N, st);
   if (rc != AP_OK) return rc;
   const int tps = ceil_div(L, TILE_M), n_tiles = tps * B;
@@ -995,12 +1148,16 @@ int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, i
   p.n_tiles = n_tiles, p.tiles_per_sample = tps, p.L = L, p.num_layers = n->N, p.chunk_alloc = n->chunk;
   p.scale = static_cast<float>(std::sqrt(1.0 / n->N));
   p.bf2 = n->bf2.as<float>();
+  p.o_plane = p.ws_plane = p.wf_plane = 0;
+  if (n->dt == 2) p.o_plane = n->N * n->chunk, p.ws_plane = n->N * 256, p.wf_plane = 256;
   for (int c = 0; c < C; ++c) p.bskip_scaled[c] = n->bskip_host[c] * p.scale, p.bf1[c] = n->bf1_host[c], p.wf2[c] = n->wf2_host[c];
   p.eps = eps;
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   cudaEvent_t e0 = prof_event(n, 1), e1 = e0 ? prof_event(n, 1) : nullptr;
   if (e1) cudaEventRecord(e0, st);
-  if (n->pair && n->dt == 0)
+  if (n->dt == 2)
+    AP_CUDA(launch_pair(k2_head<2, 2>, pair_grid(n_tiles), Geo<2, 2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs_s, n->tmWf_s, p));
+  else if (n->pair && n->dt == 0)
     AP_CUDA(launch_pair(k2_head<2, 0>, pair_grid(n_tiles), Geo<2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs2, n->tmWf2, p));
   else if (n->pair)
     AP_CUDA(launch_pair(k2_head<2, 1>, pair_grid(n_tiles), Geo<2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs2_h, n->tmWf2_h, p));
@@ -1017,12 +1174,24 @@ int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, i
 int tc_net_debug_layer(TcNet* n, const float* x, const float* ptab, int layer, float* u_next, float* gate, int B, int L,
                        cudaStream_t st) {
   using namespace tc;
-  if (B > n->chunk || L != n->L) return fail(AP_ERR_STATE, "tc_net_debug_layer: workspace mismatch");
+  if (B > n->chunk || L != n->L || n->ws_split != (n->dt == 2)) return fail(AP_ERR_STATE, "tc_net_debug_layer: workspace mismatch");
   int rc = tc_run_layers(n, x, ptab, B, L, layer + 1, st);
   if (rc != AP_OK) return rc;
   const long long cnt = static_cast<long long>(B) * L * C;
   const uint16_t* un = ((layer + 1) & 1) ? n->u1.as<uint16_t>() : n->u0.as<uint16_t>();
   const uint16_t* on = n->o.as<uint16_t>() + static_cast<size_t>(layer) * n->chunk * L * C;
+  if (n->dt == 2) {
+    const size_t plane = static_cast<size_t>(n->chunk) * L * C;
+    if (u_next) {
+      split_to_f32_kernel<<<num_sms() * 4, 256, 0, st>>>(un, un + plane, u_next, cnt);
+      AP_LAUNCH_CHECK();
+    }
+    if (gate) {
+      split_to_f32_kernel<<<num_sms() * 4, 256, 0, st>>>(on, on + plane * n->N, gate, cnt);
+      AP_LAUNCH_CHECK();
+    }
+    return AP_OK;
+  }
   if (u_next) {
     if (n->dt == 0) h16_to_f32_kernel<0><<<num_sms() * 4, 256, 0, st>>>(un, u_next, cnt);
     else h16_to_f32_kernel<1><<<num_sms() * 4, 256, 0, st>>>(un, u_next, cnt);

@@ -2,7 +2,7 @@
 sustained (power-capped) timing of the tensor-core WaveNet.  Box-to-box and boost-vs-sustained differences are larger
 than the few-percent kernel changes this is used to judge.
 
-Usage: python ab_compare.py libA.so libB.so [rounds] [seconds_per_measurement]
+Usage: python ab_compare.py libA.so libB.so [libC.so ...] [rounds] [seconds_per_measurement]
        python ab_compare.py --one lib.so seconds     (internal: one measurement, prints a JSON line)"""
 import ctypes as C
 import json
@@ -52,11 +52,12 @@ def one(seconds):
 def main():
     if sys.argv[1] == "--one":
         return one(float(sys.argv[3]))
-    libs = [os.path.abspath(sys.argv[1]), os.path.abspath(sys.argv[2])]
-    rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-    secs = sys.argv[4] if len(sys.argv) > 4 else "12"
+    libs = [os.path.abspath(a) for a in sys.argv[1:] if a.endswith(".so")]
+    nums = [a for a in sys.argv[1:] if not a.endswith(".so")]
+    rounds = int(nums[0]) if nums else 2
+    secs = nums[1] if len(nums) > 1 else "12"
     for r in range(rounds):
-        for name, lib in zip("AB", libs):
+        for name, lib in zip("ABCDEFGH", libs):
             env = dict(os.environ, AP_LIB_PATH=lib)
             o = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", lib, secs], env=env,
                                capture_output=True, text=True)

@@ -112,13 +112,14 @@ class WaveNet(torch.nn.Module):
 
     # -- arithmetic mode ------------------------------------------------------------------------------------------
     def set_mode(self, mode: str) -> "WaveNet":
-        m = {"bf16": AP_MODE_BF16, "fp32": AP_MODE_FP32, "fp16": _lib.AP_MODE_FP16}[mode]
+        m = {"bf16": AP_MODE_BF16, "fp32": AP_MODE_FP32, "fp16": _lib.AP_MODE_FP16, "bf16x3": _lib.AP_MODE_BF16X3}[mode]
         _lib.check(self._lib.ap_diffwave_set_mode(self._handle, m), "ap_diffwave_set_mode")
         return self
 
     @property
     def mode(self) -> str:
-        return {AP_MODE_BF16: "bf16", AP_MODE_FP32: "fp32", _lib.AP_MODE_FP16: "fp16"}[self._lib.ap_diffwave_get_mode(self._handle)]
+        return {AP_MODE_BF16: "bf16", AP_MODE_FP32: "fp32", _lib.AP_MODE_FP16: "fp16",
+                _lib.AP_MODE_BF16X3: "bf16x3"}[self._lib.ap_diffwave_get_mode(self._handle)]
 
     def reserve(self, chunk: int, length: int) -> None:
         _lib.check(self._lib.ap_diffwave_reserve(self._handle, int(chunk), int(length)), "ap_diffwave_reserve")

@@ -35,6 +35,10 @@ extern "C" {
 #define AP_MODE_FP32 1 /* fp32 FFMA path (parity mode, <=1e-5 rel-L2 vs the reference) */
 #define AP_MODE_FP16 3 /* DiffWave only: the same tcgen05 kernels with fp16 operands (11-bit mantissa: ~8x smaller eps error than
                           bf16 at the same speed; conversions saturate at +-65504) */
+#define AP_MODE_BF16X3 4 /* DiffWave only: fp32-class arithmetic on the bf16 tensor cores.  Activations and weights are kept as
+                            bf16 hi/lo plane pairs (16 significand bits) and every product is accumulated as
+                            hi*hi + lo*hi + hi*lo in fp32: three MMAs per K step, ~1e-5 eps error, <=1e-5 on the purified
+                            waveform (the fp32-mode bar) at several times the speed of the FFMA path */
 #define AP_MODE_TF32 2 /* classifiers only: tcgen05 kind::tf32 convolutions (the precision of the reference's cuDNN path) */
 
 typedef struct ap_diffwave_s* ap_diffwave_t;
@@ -77,7 +81,8 @@ typedef struct {
 int ap_diffwave_create(ap_diffwave_t* out, const ap_wavenet_cfg* cfg, const float* const* weights, int n_weights,
                        int device);
 void ap_diffwave_destroy(ap_diffwave_t h);
-/* AP_MODE_BF16 (default when the configuration supports the tensor-core kernels: C == S == 256), AP_MODE_FP16 or AP_MODE_FP32 */
+/* AP_MODE_BF16 (default when the configuration supports the tensor-core kernels: C == S == 256), AP_MODE_FP16,
+ * AP_MODE_BF16X3 or AP_MODE_FP32 */
 int ap_diffwave_set_mode(ap_diffwave_t h, int mode);
 int ap_diffwave_get_mode(ap_diffwave_t h);
 /* Pre-allocate the activation workspace for up to `chunk` waveforms of length L processed at once (larger batches are

@@ -11,8 +11,13 @@ from gpu_common import CONFIG_JSON, TorchNormalInjector, cuda, rel_l2, synthetic
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-5, "bf16": 1e-2, "fp16": 1e-3}
-TOL_EPS = {"fp32": 2e-5, "bf16": 1e-2, "fp16": 2e-3}
+# north_star: purified waveform within 1e-2 (bf16) / 1e-5 (fp32 mode) relative L2 of the reference.  bf16x3 is the
+# fp32-class tensor-core mode (hi/lo bf16 planes, 3 MMAs per product): it is held to the fp32 bar on the waveform.
+TOL = {"fp32": 1e-5, "bf16": 1e-2, "fp16": 1e-3, "bf16x3": 1e-5}
+TOL_EPS = {"fp32": 2e-5, "bf16": 1e-2, "fp16": 2e-3, "bf16x3": 1e-4}
+# one-/two-shot x0 at t* = 66 weight eps by 0.5 (a DDPM step by ~0.012), so the 16-significand-bit eps error of bf16x3
+# (2.3e-5..3e-5) shows as ~1.1e-5 there and as 5e-7..9e-7 on the purified waveform
+TOL_X0 = dict(TOL, bf16x3=2e-5)
 
 
 @pytest.fixture(scope="module")
@@ -127,7 +132,7 @@ def _eps(ap, sd, cfg, x, t, mode):
 
 @pytest.mark.parametrize("key,L,B,t,seed", [("eps_full_L1024_t1", 1024, 2, 1.0, 1234), ("eps_full_L1024_t65", 1024, 2, 65.0, 1234),
                                             ("eps_full_L3001_t7", 3001, 1, 7.0, 77)])
-@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16", "bf16x3"])
 def test_wavenet_eps_vs_reference_golden(ap, golden, sd_full, key, L, B, t, seed, mode):
     x = synthetic.synthetic_waveforms(B, L, seed=seed)
     eps = _eps(ap, sd_full, synthetic.DEFAULT_WAVENET_CONFIG, x, t, mode)
@@ -190,11 +195,12 @@ def test_wavenet_batch_chunking_and_mixed_steps(ap, sd_full):
 def test_wavenet_edge_shapes_bf16_vs_fp32(ap, sd_full, B, L):
     """single partial tile, one position past a tile boundary, odd tile counts (ragged CTA pairs) -- tensor-core path vs the
     fp32 path (itself pinned to the reference at other shapes)"""
-    nets = {m: ap.WaveNet(sd_full, mode=m, **synthetic.DEFAULT_WAVENET_CONFIG) for m in ("fp32", "bf16")}
+    nets = {m: ap.WaveNet(sd_full, mode=m, **synthetic.DEFAULT_WAVENET_CONFIG) for m in ("fp32", "bf16", "bf16x3")}
     x = cuda(synthetic.synthetic_waveforms(B, L, seed=L))
-    e32, e16 = nets["fp32"].eps(x, 33.0), nets["bf16"].eps(x, 33.0)
-    err = rel_l2(e16, e32)
-    print(f"eps bf16 vs fp32 at B={B} L={L}: rel-L2 {err:.3e}")
+    e32, e16, ex3 = nets["fp32"].eps(x, 33.0), nets["bf16"].eps(x, 33.0), nets["bf16x3"].eps(x, 33.0)
+    err, err3 = rel_l2(e16, e32), rel_l2(ex3, e32)
+    print(f"eps bf16 vs fp32 at B={B} L={L}: rel-L2 {err:.3e}; bf16x3 vs fp32: {err3:.3e}")
+    assert torch.isfinite(ex3).all() and err3 < 2e-4
     # clips much shorter than the receptive field have a small eps norm (most taps read zero padding), so the same
     # absolute bf16 noise is a larger relative error than at L >= 1024 (7e-3..9.5e-3): measured 1.5e-2..1.7e-2
     assert torch.isfinite(e16).all() and err < (2.5e-2 if L < 1024 else 1.2e-2)
@@ -243,7 +249,7 @@ def test_inference_only_and_cpu_inputs_raise(ap, diffwave):
 
 
 # ---------------------------------------------------------------------------------------------------- purifier
-@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16", "bf16x3"])
 def test_ddpm_purifier_vs_reference_golden(diffwave, golden, mode):
     diffwave.model.set_mode(mode)
     x = cuda(synthetic.synthetic_waveforms(2, 1024, seed=1234))
@@ -256,8 +262,8 @@ def test_ddpm_purifier_vs_reference_golden(diffwave, golden, mode):
         print(f"{key} {mode}: rel-L2 {err:.3e}")
         assert err < TOL[mode]
     diffwave.reverse_timestep = 66
-    assert rel_l2(diffwave.one_shot_denoise(x), golden["oneshot_t66_L1024"]) < TOL[mode]
-    assert rel_l2(diffwave.two_shot_denoise(x), golden["twoshot_t66_L1024"]) < TOL[mode]
+    assert rel_l2(diffwave.one_shot_denoise(x), golden["oneshot_t66_L1024"]) < TOL_X0[mode]
+    assert rel_l2(diffwave.two_shot_denoise(x), golden["twoshot_t66_L1024"]) < TOL_X0[mode]
     diffwave.reverse_timestep = 9
     with TorchNormalInjector(2026):
         assert rel_l2(diffwave.fast_reverse(x), golden["fastrev_t9_L1024"]) < TOL[mode]

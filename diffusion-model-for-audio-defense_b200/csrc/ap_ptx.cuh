@@ -42,9 +42,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trapped launch (cudaErrorLaunchFailure), never a hung GPU.
-// Returns the number of cycles spent waiting.  (try_wait may itself suspend the thread for a while before it reports
-// success, so the clock is read before the first attempt: the wait-cycle counters would otherwise under-report.)
+// Returns the number of cycles spent waiting.  try_wait may itself suspend the thread for a while before it reports
+// success, so the default (fast) build under-reports: it reads the clock only on the slow path, which keeps the wait to
+// two instructions in the MMA-issue loop.  Build with -DAP_TC_TIMED_WAITS (devtools/build_variant.sh) for exact counters.
 __device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
+#ifndef AP_TC_TIMED_WAITS
+  if (mbar_try_wait(bar, parity)) return 0;
+#endif
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz

@@ -450,7 +450,10 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
     __syncwarp();
   } else if (warp == 1) {
     // ======================================================================================= MMA issuer (leader CTA)
-    if (lane == 0 && cx.rank == 0) {
+    // The whole warp runs the loop (warp-uniform control flow keeps the smem descriptors and barrier addresses in uniform
+    // registers); one elected lane issues the tcgen05 instructions.  With a single divergent lane the compiler emitted
+    // ~105 dependent SASS instructions per K block (ELECT + 5 R2UR per MMA): ~570 clk of issue for 512 clk of tensor work.
+    if (cx.rank == 0) {
       uint32_t it = 0, g = 0, ti = 0;
       long long w_full = 0, w_acc = 0, w_out = 0;
       const long long t_start = clock64();
@@ -462,10 +465,14 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
           const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
           w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 4);
           tc_fence_after();
-          cx.mma_kblock(tmem + r * 256, cx.stage_a(s), cx.stage_b(s), kblk == 0);
-          cx.commit(BAR_EMPTY + s);
+          if (elect_one()) {
+            cx.mma_kblock(tmem + r * 256, cx.stage_a(s), cx.stage_b(s), kblk == 0);
+            cx.commit(BAR_EMPTY + s);
+          }
+          __syncwarp();
         }
-        cx.commit(BAR_ACC_FULL + r);
+        if (elect_one()) cx.commit(BAR_ACC_FULL + r);
+        __syncwarp();
         ++g;
       };
       auto gemm2 = [&](uint32_t t_idx) {
@@ -478,11 +485,15 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
             const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
             w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 8);
             tc_fence_after();
-            cx.mma_kblock(tmem + r * 256, cx.out_kb(kb + (cmb == 1 ? 4 : 0)), cx.stage_b(s), kb == 0 && cmb == 0);
-            cx.commit(BAR_EMPTY + s);
+            if (elect_one()) {
+              cx.mma_kblock(tmem + r * 256, cx.out_kb(kb + (cmb == 1 ? 4 : 0)), cx.stage_b(s), kb == 0 && cmb == 0);
+              cx.commit(BAR_EMPTY + s);
+            }
+            __syncwarp();
           }
         }
-        cx.commit(BAR_ACC_FULL + r);
+        if (elect_one()) cx.commit(BAR_ACC_FULL + r);
+        __syncwarp();
         ++g;
       };
       for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
@@ -491,12 +502,11 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
         gemm1();
       }
       if (!p.last && ti > 0) gemm2(ti - 1);
-      if (p.dbg) {
+      if (p.dbg && lane == 0) {
         long long* d = p.dbg + blockIdx.x * 16;
         d[2] = w_full, d[3] = w_acc, d[4] = w_out, d[5] = clock64() - t_start, d[6] = ti;
       }
     }
-    __syncwarp();
   } else if (warp >= EPI_WARP0) {
     // ======================================================================================= epilogue (8 warps)
     const uint32_t c2_addr = cx.base + G::BIAS_OFF;
@@ -633,7 +643,7 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && cx.rank == 0) {
+    if (cx.rank == 0) {   // whole warp, one elected lane issues (see k1_layer)
       uint32_t it = 0, ti = 0;
       for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
         mbar_wait(cx.bar(BAR_ACC_EMPTY + 0), (ti & 1) ^ 1, 23);
@@ -642,10 +652,14 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
           const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
           mbar_wait(cx.bar(BAR_FULL + s), ph, 24);
           tc_fence_after();
-          cx.mma_kblock(tmem, cx.stage_a(s), cx.stage_b(s), kblk == 0);
-          cx.commit(BAR_EMPTY + s);
+          if (elect_one()) {
+            cx.mma_kblock(tmem, cx.stage_a(s), cx.stage_b(s), kblk == 0);
+            cx.commit(BAR_EMPTY + s);
+          }
+          __syncwarp();
         }
-        cx.commit(BAR_ACC_FULL + 0);
+        if (elect_one()) cx.commit(BAR_ACC_FULL + 0);
+        __syncwarp();
         mbar_wait(cx.bar(BAR_ACC_EMPTY + 1), (ti & 1) ^ 1, 25);
         mbar_wait(cx.bar(BAR2_S_READY), ti & 1, 26);
         tc_fence_after();
@@ -654,13 +668,16 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
             const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
             mbar_wait(cx.bar(BAR_FULL + s), ph, 27);
             tc_fence_after();
-            cx.mma_kblock(tmem + 256, cx.out_kb(kb + (cmb == 1 ? 4 : 0)), cx.stage_b(s), kb == 0 && cmb == 0);
-            cx.commit(BAR_EMPTY + s);
+            if (elect_one()) {
+              cx.mma_kblock(tmem + 256, cx.out_kb(kb + (cmb == 1 ? 4 : 0)), cx.stage_b(s), kb == 0 && cmb == 0);
+              cx.commit(BAR_EMPTY + s);
+            }
+            __syncwarp();
           }
-        cx.commit(BAR_ACC_FULL + 1);
+        if (elect_one()) cx.commit(BAR_ACC_FULL + 1);
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp >= EPI_WARP0) {
     if (((warp - EPI_WARP0) >> 2) == 0) k2_epilogue<G, 0>(cx, p, tmem, tiles, s_part);
     else k2_epilogue<G, 1>(cx, p, tmem, tiles, s_part);

@@ -89,26 +89,28 @@ k_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32_f32(128, p.NT);
-      uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++ti) {
-        const uint32_t r = ti & 1;
-        mbar_wait(bar(BAR_ACC_EMPTY + r), ((ti >> 1) & 1) ^ 1, 52);
+    // the whole warp runs the loop (uniform control flow keeps descriptors in uniform registers); one elected lane issues
+    const uint32_t idesc = umma_idesc_tf32_f32(128, p.NT);
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++ti) {
+      const uint32_t r = ti & 1;
+      mbar_wait(bar(BAR_ACC_EMPTY + r), ((ti >> 1) & 1) ^ 1, 52);
+      tc_fence_after();
+      for (int kblk = 0; kblk < nk; ++kblk, ++it) {
+        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
+        mbar_wait(bar(BAR_FULL + st), ph, 53);
         tc_fence_after();
-        for (int kblk = 0; kblk < nk; ++kblk, ++it) {
-          const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
-          mbar_wait(bar(BAR_FULL + st), ph, 53);
-          tc_fence_after();
+        if (elect_one()) {
           const uint64_t ad = umma_desc_k_sw128(base + st * STAGE_BYTES), bd = umma_desc_k_sw128(base + st * STAGE_BYTES + A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_tf32(tmem + r * 256, ad + 2 * k, bd + 2 * k, idesc, (kblk == 0 && k == 0) ? 0u : 1u);
           umma_commit(bar(BAR_EMPTY + st));
         }
-        umma_commit(bar(BAR_ACC_FULL + r));
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(bar(BAR_ACC_FULL + r));
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int q = warp & 3, hs = (warp - 2) >> 2;
     const int htid = (threadIdx.x - 64) & 127;                    // thread index within the half-group

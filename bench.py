@@ -42,7 +42,8 @@ def parse_args():
     p.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32", "bf16x3"])
     p.add_argument("--chunk", type=int, default=0, help="waveforms per workspace chunk (0 = library default)")
     p.add_argument("--certify-draws", type=int, default=4096, help="extra certification leg (0 = skip)")
-    p.add_argument("--cpu-sample", type=int, default=2, help="waveforms in the cpu_baseline sample (0 = skip)")
+    p.add_argument("--cpu-sample", type=int, default=16,
+                   help="waveforms in the cpu_baseline sample (0 = skip); 16 = BASELINE configs[0], ~15-20 s of host work")
     p.add_argument("--workload", default="sc09", choices=["sc09", "sde", "m5", "kws"],
                    help="sc09 = BASELINE configs[1] (headline); sde = configs[3] (reverse-SDE purifier, --t-star 1..10); "
                         "m5 / kws = configs[4] (DDPM purifier + raw-waveform M5 / mel(400,200,32) + RCNN_KWS)")
@@ -149,7 +150,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = 1
+    sample = 4                      # waveforms per step: a bounded sample of the 512-waveform workload (~4 s of host work)
     for _ in range(min(args.warmup, 1)):
         oracle_pipeline(sample)
     t = 0.0
@@ -161,7 +162,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} waveform per step x {args.steps} steps (torch CPU ops, {cores} threads)"},
+                             "sample": f"{sample} waveforms per step x {args.steps} steps (torch CPU ops, {cores} threads)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -294,9 +295,9 @@ def run_ours(args):
             roofline = {"kernel": "k1_layer (DiffWave residual block: tcgen05 implicit GEMM K=768/N=512 + K=256/N=256, fused "
                                   "gate / residual epilogues)", "bound": "tensor", "achieved": achieved,
                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
-                        "traffic": 24.19e6 * avg_wf if args.mode != "bf16x3" else None,
-                        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum = 3.097e9 B for a 128-waveform launch "
-                                          "(profiles/r01_k1_pair_ncu_full_summary.txt; algorithmic 3.146e9 B), scaled to this "
+                        "traffic": 24.38e6 * avg_wf if args.mode != "bf16x3" else None,
+                        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum = 3.120e9 B for a 128-waveform launch "
+                                          "(profiles/r01_k1_v5_ncu_full_summary.txt; algorithmic 3.146e9 B), scaled to this "
                                           "run's waveforms per launch" if args.mode != "bf16x3" else "no ncu capture of the split kernel",
                         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                         "mma_flops_per_algorithmic_flop": 3 if args.mode == "bf16x3" else 1,

@@ -72,6 +72,15 @@ template <int CG_, int KIND, int DT_ = 0> struct Geo {
 };
 enum { BAR_FULL = 0, BAR_EMPTY = 5, BAR_ACC_FULL = 10, BAR_ACC_EMPTY = 12, BAR_OUT_READY = 14, BAR_UC_FULL = 17, BAR_COUNT = 18 };
 
+// position in the TMA ring: stage index and phase parity (no division in the producer / MMA-issue loops)
+template <int NSTAGE> struct RingPos {
+  uint32_t s = 0, ph = 0;
+  __device__ __forceinline__ RingPos& operator++() {
+    if (++s == NSTAGE) s = 0, ph ^= 1;
+    return *this;
+  }
+};
+
 // Per-CTA view of the barrier array and the pair topology
 template <class G> struct Ctx {
   static constexpr int CG = G::CG;
@@ -87,12 +96,14 @@ template <class G> struct Ctx {
     else mbar_arrive_cluster(lbar(i));
   }
   // producer: arm the full barrier of stage s for `bytes` per CTA, after the slot was released
-  __device__ __forceinline__ long long arm(uint32_t s, uint32_t ph, uint32_t bytes, int tag) const {
-    const long long w = mbar_wait(bar(BAR_EMPTY + s), ph ^ 1, tag);
+  //           (wait_empty: every lane of the producer warp; arm: the elected lane, followed by its TMA loads)
+  __device__ __forceinline__ long long wait_empty(uint32_t s, uint32_t ph, int tag) const {
+    return mbar_wait(bar(BAR_EMPTY + s), ph ^ 1, tag);
+  }
+  __device__ __forceinline__ void arm(uint32_t s, uint32_t bytes) const {
     if (CG == 1) mbar_expect_tx(bar(BAR_FULL + s), bytes);
     else if (rank == 0) mbar_expect_tx(bar(BAR_FULL + s), 2 * bytes);
     else mbar_arrive_cluster(lbar(BAR_FULL + s));
-    return w;
   }
   __device__ __forceinline__ void load_a(uint32_t s, const CUtensorMap* m, int c0, int c1, int c2) const {
     if (CG == 1) tma_load_3d(stage_a(s), m, bar(BAR_FULL + s), c0, c1, c2);
@@ -413,8 +424,9 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
   if (warp < EPI_WARP0) setmaxnreg_dec<96>();
   if (warp == 0) {
     // ======================================================================================= TMA producer
-    if (lane == 0) {
-      uint32_t it = 0, ti = 0;
+    {   // whole warp, warp-uniform control flow; one elected lane arms the barrier and issues the loads
+      RingPos<G::NSTAGE> it;
+      uint32_t ti = 0;
       long long w_empty = 0;
       const long long t_start = clock64();
       // split mode: per K block the (A plane, B plane) pairs (hi,hi), (lo,hi), (hi,lo), each its own ring stage
@@ -422,18 +434,26 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
         for (int tap = 0; tap < 3; ++tap)
           for (int kb = 0; kb < 4; ++kb)
             for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
-              const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-              w_empty += cx.arm(s, ph, G::STAGE_BYTES, 1);
-              cx.load_a(s, &tmUin, kb * 64, valid ? l0 + (tap - 1) * p.dilation : oob_l0, b + (cmb == 1 ? p.u_plane : 0));
-              cx.load_b(s, &tmWd, tap * C + kb * 64, (p.layer * 2 + j) * 256 + (cmb == 2 ? p.wd_plane : 0));
+              const uint32_t s = it.s, ph = it.ph;
+              w_empty += cx.wait_empty(s, ph, 1);
+              if (elect_one()) {
+                cx.arm(s, G::STAGE_BYTES);
+                cx.load_a(s, &tmUin, kb * 64, valid ? l0 + (tap - 1) * p.dilation : oob_l0, b + (cmb == 1 ? p.u_plane : 0));
+                cx.load_b(s, &tmWd, tap * C + kb * 64, (p.layer * 2 + j) * 256 + (cmb == 2 ? p.wd_plane : 0));
+              }
+              __syncwarp();
             }
       };
       auto load_wr = [&]() {
         for (int kb = 0; kb < 4; ++kb)
           for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
-            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-            w_empty += cx.arm(s, ph, G::B_BYTES, 2);
-            cx.load_b(s, &tmWr, kb * 64, p.layer * 256 + (cmb == 2 ? p.wr_plane : 0));
+            const uint32_t s = it.s, ph = it.ph;
+            w_empty += cx.wait_empty(s, ph, 2);
+            if (elect_one()) {
+              cx.arm(s, G::B_BYTES);
+              cx.load_b(s, &tmWr, kb * 64, p.layer * 256 + (cmb == 2 ? p.wr_plane : 0));
+            }
+            __syncwarp();
           }
       };
       for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
@@ -445,7 +465,7 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
         load_g1(1, valid, b, l0);
       }
       if (!p.last && ti > 0) load_wr();
-      if (p.dbg) p.dbg[blockIdx.x * 16 + 0] = w_empty, p.dbg[blockIdx.x * 16 + 1] = clock64() - t_start;
+      if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + 0] = w_empty, p.dbg[blockIdx.x * 16 + 1] = clock64() - t_start;
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -454,7 +474,8 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
     // registers); one elected lane issues the tcgen05 instructions.  With a single divergent lane the compiler emitted
     // ~105 dependent SASS instructions per K block (ELECT + 5 R2UR per MMA): ~570 clk of issue for 512 clk of tensor work.
     if (cx.rank == 0) {
-      uint32_t it = 0, g = 0, ti = 0;
+      RingPos<G::NSTAGE> it;
+      uint32_t g = 0, ti = 0;
       long long w_full = 0, w_acc = 0, w_out = 0;
       const long long t_start = clock64();
       auto gemm1 = [&]() {
@@ -462,7 +483,7 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
         w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 3);
         tc_fence_after();
         for (int kblk = 0; kblk < 12 * G::NCOMBO; ++kblk, ++it) {
-          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+          const uint32_t s = it.s, ph = it.ph;
           w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 4);
           tc_fence_after();
           if (elect_one()) {
@@ -482,7 +503,7 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
         for (int kb = 0; kb < 4; ++kb) {
           if ((kb & 1) == 0) w_out += mbar_wait(cx.bar(BAR_OUT_READY + (kb >> 1)), t_idx & 1, 6);
           for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
-            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+            const uint32_t s = it.s, ph = it.ph;
             w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 8);
             tc_fence_after();
             if (elect_one()) {
@@ -619,8 +640,8 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
   const int oob_l0 = p.tiles_per_sample * TILE_M;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
+    {   // whole warp, one elected lane issues (see k1_layer)
+      RingPos<G::NSTAGE> it;
       for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride) {
         const bool valid = tile < p.n_tiles;
         const int b = valid ? tile / p.tiles_per_sample : 0;
@@ -628,28 +649,37 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
         for (int n = 0; n < p.num_layers; ++n)
           for (int kb = 0; kb < 4; ++kb)
             for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
-              const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-              cx.arm(s, ph, G::STAGE_BYTES, 21);
-              cx.load_a(s, &tmO, kb * 64, l0, n * p.chunk_alloc + b + (cmb == 1 ? p.o_plane : 0));
-              cx.load_b(s, &tmWs, kb * 64, n * 256 + (cmb == 2 ? p.ws_plane : 0));
+              const uint32_t s = it.s, ph = it.ph;
+              cx.wait_empty(s, ph, 21);
+              if (elect_one()) {
+                cx.arm(s, G::STAGE_BYTES);
+                cx.load_a(s, &tmO, kb * 64, l0, n * p.chunk_alloc + b + (cmb == 1 ? p.o_plane : 0));
+                cx.load_b(s, &tmWs, kb * 64, n * 256 + (cmb == 2 ? p.ws_plane : 0));
+              }
+              __syncwarp();
             }
         for (int kb = 0; kb < 4; ++kb)
           for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
-            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
-            cx.arm(s, ph, G::B_BYTES, 22);
-            cx.load_b(s, &tmWf, kb * 64, cmb == 2 ? p.wf_plane : 0);
+            const uint32_t s = it.s, ph = it.ph;
+            cx.wait_empty(s, ph, 22);
+            if (elect_one()) {
+              cx.arm(s, G::B_BYTES);
+              cx.load_b(s, &tmWf, kb * 64, cmb == 2 ? p.wf_plane : 0);
+            }
+            __syncwarp();
           }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (cx.rank == 0) {   // whole warp, one elected lane issues (see k1_layer)
-      uint32_t it = 0, ti = 0;
+      RingPos<G::NSTAGE> it;
+      uint32_t ti = 0;
       for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
         mbar_wait(cx.bar(BAR_ACC_EMPTY + 0), (ti & 1) ^ 1, 23);
         tc_fence_after();
         for (int kblk = 0; kblk < nkb; ++kblk, ++it) {
-          const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+          const uint32_t s = it.s, ph = it.ph;
           mbar_wait(cx.bar(BAR_FULL + s), ph, 24);
           tc_fence_after();
           if (elect_one()) {
@@ -665,7 +695,7 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
         tc_fence_after();
         for (int kb = 0; kb < 4; ++kb)
           for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
-            const uint32_t s = it % G::NSTAGE, ph = (it / G::NSTAGE) & 1;
+            const uint32_t s = it.s, ph = it.ph;
             mbar_wait(cx.bar(BAR_FULL + s), ph, 27);
             tc_fence_after();
             if (elect_one()) {

@@ -35,6 +35,13 @@ int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, i
 int tc_net_debug_layer(TcNet* n, const float* x, const float* ptab, int layer, float* u_next, float* gate, int B, int L,
                        cudaStream_t st);
 
+// backward pass (bf16 mode): g_x = (d eps / d x)^T g_eps at (x, ptab) for B <= bchunk waveforms; the forward is recomputed
+// with the activations the backward needs kept (tanh / sigmoid of every layer: ~1 KB per position per layer).
+// eps_out may be null (eps_scratch, device fp32 (B, L), is then used for the recomputed eps).
+int tc_net_vjp(TcNet* n, const float* x, const float* ptab, const float* g_eps, float* g_x, float* eps_out, float* eps_scratch,
+               int B, int L, int bchunk, cudaStream_t st);
+size_t tc_net_bwd_bytes_per_waveform(const TcNet* n, int L);
+
 // per-launch CUDA-event timing of k1_layer ([0]) and k2_head ([1]); read synchronises on the recorded events
 void tc_net_profile(TcNet* n, bool on);
 int tc_net_debug_counters(TcNet* n, long long* host16x256);

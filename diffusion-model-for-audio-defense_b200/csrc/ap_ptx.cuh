@@ -137,6 +137,9 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
                ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void st_global_v4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // two fp32 -> packed bf16x2 (lo in bits [0,16), hi in bits [16,32)), round to nearest even
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t d;

@@ -434,6 +434,39 @@ extern "C" int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* 
   return AP_OK;
 }
 
+// Vector-Jacobian product of the network: g_x = (d eps_theta(x, t) / d x)^T g_eps (what autograd computes through the
+// reference's WaveNet when an attack calls loss.backward(), robustness_eval/white_box_attack.py:438).  bf16 mode.
+extern "C" int ap_diffwave_eps_vjp(ap_diffwave_t h, const float* x, float t, const float* g_eps, float* g_x, float* eps_out,
+                                   int B, int L, void* stream) {
+  AP_REQUIRE(h && x && g_eps && g_x, "ap_diffwave_eps_vjp: null argument");
+  AP_REQUIRE(B > 0 && L > 0, "ap_diffwave_eps_vjp: B and L must be positive (got %d, %d)", B, L);
+  if (h->mode != AP_MODE_BF16 && h->mode != AP_MODE_BF16X3)
+    return fail(AP_ERR_STATE, "ap_diffwave_eps_vjp: the backward pass exists in AP_MODE_BF16 and AP_MODE_BF16X3 only");
+  AP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // sub-batches sized so that the saved activations stay below ~24 GB
+  const size_t per = tc_net_bwd_bytes_per_waveform(h->tc, L);
+  long long bchunk = static_cast<long long>((24ull << 30) / per);
+  if (bchunk < 1) bchunk = 1;
+  if (bchunk > B) bchunk = B;
+  if (h->tc_chunk < bchunk || h->tc_L != L) {
+    int rc = ap_diffwave_reserve(h, static_cast<int>(bchunk), L);
+    if (rc != AP_OK) return rc;
+  }
+  const size_t nb = static_cast<size_t>(bchunk) * L * sizeof(float);
+  if (h->eps_buf.bytes < nb) AP_CUDA(h->eps_buf.alloc(nb));
+  int rc = step_embedding(h, t, st);
+  if (rc != AP_OK) return rc;
+  for (int b0 = 0; b0 < B; b0 += static_cast<int>(bchunk)) {
+    const int bn = B - b0 < bchunk ? B - b0 : static_cast<int>(bchunk);
+    const size_t off = static_cast<size_t>(b0) * L;
+    rc = tc_net_vjp(h->tc, x + off, h->ptab.as<float>(), g_eps + off, g_x + off, eps_out ? eps_out + off : nullptr,
+                    h->eps_buf.as<float>(), bn, L, static_cast<int>(bchunk), st);
+    if (rc != AP_OK) return rc;
+  }
+  return AP_OK;
+}
+
 extern "C" int ap_diffwave_purify_ddpm(ap_diffwave_t h, const float* x0, float* out, int t_star, const float* coef4,
                                        const float* z, uint64_t seed, uint64_t offset, int B, int L, void* stream) {
   AP_REQUIRE(h && x0 && out && coef4, "ap_diffwave_purify_ddpm: null argument");

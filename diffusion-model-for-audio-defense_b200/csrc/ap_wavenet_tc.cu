@@ -187,6 +187,9 @@ struct K1Params {
   const float* p_next;  // [256]
   const uint16_t* u_in; // [chunk][L][256] this layer's input (also read through tmUin as the GEMM-1 A operand)
   uint16_t* u_out;      // [chunk][L][256] next layer's input
+  uint16_t* ts_out;     // SAVE kernels (backward pass): [N][ts_chunk][L][512] bf16, the gate's local derivatives
+                        // d o / d a_t | d o / d a_s of every layer
+  int ts_chunk;
   long long* dbg;       // optional [gridDim.x][16] wait-cycle counters (development aid), or null
   // hi/lo split mode (DT = 2): offset of the lo plane in the third coordinate of the U / O tensor maps and in the rows of
   // the Wd / Wr maps (0 otherwise); the lo plane of u_in / u_out starts u_plane * L * 256 elements after the hi plane
@@ -205,7 +208,7 @@ struct K1Params {
 // registers until GEMM-2 of the previous tile has finished reading the 64 KB staging tile.  The residual epilogue does
 // not touch shared memory: u is read and u' written with 32-byte-per-thread global accesses (full sectors), which
 // takes its four 64 KB passes off the shared-memory crossbar (the resource that bounds this kernel).
-template <class G, int HSEL>
+template <class G, int HSEL, bool SAVE>
 __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p, const uint32_t tmem,
                                             const Tiles<G::CG>& tiles, const CUtensorMap* tmO, const uint32_t c2_addr) {
   constexpr int DT = G::DT;
@@ -238,6 +241,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);   // accumulators are in registers: the region is free again
     uint32_t pk[2][4][4];
     uint32_t pl[G::SPLIT ? 2 : 1][4][4];   // lo plane (split mode)
+    uint32_t tsk[2][4];                    // SAVE: packed tanh / sigmoid of the current 8 channels
 #pragma unroll
     for (int gq = 0; gq < 2; ++gq)
 #pragma unroll
@@ -248,13 +252,18 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
           const int cb = J * 256 + HSEL * 64 + gq * 32 + c0;
           if constexpr (G::SPLIT) {
             // fp32-class gate: exp-based tanh / sigmoid (MUFU.TANH is good to ~2^-11 only); p.bd holds HALF the sigmoid bias
-            const float o0 = tanh_exp(__uint_as_float(ta[gq][c0]) + p.bd[cb]) *
-                             sigmoid_exp(fmaf(2.f, p.bd[cb + 128], __uint_as_float(sg[gq][c0])));
-            const float o1 = tanh_exp(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]) *
-                             sigmoid_exp(fmaf(2.f, p.bd[cb + 129], __uint_as_float(sg[gq][c0 + 1])));
+            const float t0 = tanh_exp(__uint_as_float(ta[gq][c0]) + p.bd[cb]);
+            const float t1 = tanh_exp(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]);
+            const float g0 = sigmoid_exp(fmaf(2.f, p.bd[cb + 128], __uint_as_float(sg[gq][c0])));
+            const float g1 = sigmoid_exp(fmaf(2.f, p.bd[cb + 129], __uint_as_float(sg[gq][c0 + 1])));
+            const float o0 = t0 * g0, o1 = t1 * g1;
             const uint32_t hi = pack_bf16x2(o0, o1);
             pk[gq][i][e] = hi;
             pl[gq][i][e] = pack_bf16x2(o0 - bf16_lo(hi), o1 - bf16_hi(hi));
+            if constexpr (SAVE) {   // local derivatives of the gate (see the bf16 branch)
+              tsk[0][e] = pack_bf16x2(g0 * fmaf(-t0, t0, 1.f), g1 * fmaf(-t1, t1, 1.f));
+              tsk[1][e] = pack_bf16x2(t0 * g0 * (1.f - g0), t1 * g1 * (1.f - g1));
+            }
           } else {
             const float t0 = tanh_approx(__uint_as_float(ta[gq][c0]) + p.bd[cb]);
             const float t1 = tanh_approx(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]);
@@ -266,6 +275,21 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
 #else
             pk[gq][i][e] = pack2<DT>(t0 * fmaf(s0, 0.5f, 0.5f), t1 * fmaf(s1, 0.5f, 0.5f));
 #endif
+            if constexpr (SAVE) {
+              // the gate's local derivatives d o / d a_t = S (1 - T^2) and d o / d a_s = T S (1 - S), taken in fp32 here:
+              // recomputing them from bf16-rounded T, S loses all precision where the gate saturates (1 - T^2 << 1)
+              const float g0 = fmaf(s0, 0.5f, 0.5f), g1 = fmaf(s1, 0.5f, 0.5f);
+              tsk[0][e] = pack2<DT>(g0 * fmaf(-t0, t0, 1.f), g1 * fmaf(-t1, t1, 1.f));
+              tsk[1][e] = pack2<DT>(t0 * g0 * (1.f - g0), t1 * g1 * (1.f - g1));
+            }
+          }
+          if constexpr (SAVE) {
+            if (e == 3 && valid && l0 + row < p.L) {
+              uint16_t* td = p.ts_out + ((static_cast<size_t>(p.layer) * p.ts_chunk + b) * p.L + l0 + row) * 512 + J * 128 +
+                             HSEL * 64 + gq * 32 + i * 8;
+              st_global_v4(td, make_uint4(tsk[0][0], tsk[0][1], tsk[0][2], tsk[0][3]));
+              st_global_v4(td + 256, make_uint4(tsk[1][0], tsk[1][1], tsk[1][2], tsk[1][3]));
+            }
           }
         }
     // the staging tile still holds o of the previous tile until its GEMM-2 (the NEXT job, g + 1) has completed
@@ -400,7 +424,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
   }
 }
 
-template <int CG, int DT>
+template <int CG, int DT, bool SAVE = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k1_layer(const __grid_constant__ CUtensorMap tmUin,
          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWd,
@@ -532,8 +556,8 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
     // ======================================================================================= epilogue (8 warps)
     const uint32_t c2_addr = cx.base + G::BIAS_OFF;
     setmaxnreg_inc<200>();
-    if (((warp - EPI_WARP0) >> 2) == 0) k1_epilogue<G, 0>(cx, p, tmem, tiles, &tmO, c2_addr);
-    else k1_epilogue<G, 1>(cx, p, tmem, tiles, &tmO, c2_addr);
+    if (((warp - EPI_WARP0) >> 2) == 0) k1_epilogue<G, 0, SAVE>(cx, p, tmem, tiles, &tmO, c2_addr);
+    else k1_epilogue<G, 1, SAVE>(cx, p, tmem, tiles, &tmO, c2_addr);
   }
   tc_epilogue_teardown<CG>(tmem);
 }
@@ -545,6 +569,7 @@ struct K2Params {
   const float* bf2;      // [1]
   float* eps;            // [B][L]
   int o_plane, ws_plane, wf_plane;   // hi/lo split mode (DT = 2): offsets of the lo planes in the O / Ws / Wf tensor maps
+  uint32_t* mask_out;                // SAVE kernels (backward pass): [B][L][8] bit c of the row = (head pre-activation c > 0)
   // per-channel vectors in the kernel-parameter constant bank (constant operands of the epilogue FMAs):
   float bskip_scaled[256];   // (sum over layers of the skip-conv biases) * sqrt(1/N)
   float bf1[256];            // final_conv.0 bias
@@ -553,7 +578,7 @@ struct K2Params {
 enum { BAR2_S_READY = BAR_OUT_READY };
 
 // epilogue of k2 for the column half HSEL (channels HSEL*128 .. +127)
-template <class G, int HSEL>
+template <class G, int HSEL, bool SAVE>
 __device__ __forceinline__ void k2_epilogue(const Ctx<G>& cx, const K2Params& p, const uint32_t tmem,
                                             const Tiles<G::CG>& tiles, float* s_part) {
   constexpr int DT = G::DT;
@@ -604,14 +629,22 @@ __device__ __forceinline__ void k2_epilogue(const Ctx<G>& cx, const K2Params& p,
     mbar_wait(cx.bar(BAR_ACC_FULL + 1), ti & 1, 29);
     tc_fence_after();
     float dot = 0.f;
+    uint32_t mw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int gq = 0; gq < 4; ++gq) {
       uint32_t acc[32];
       tmem_ld_32x32b_x32(lane_addr + 256 + HSEL * 128 + gq * 32, acc);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
-        dot = fmaf(fmaxf(__uint_as_float(acc[e]) + p.bf1[HSEL * 128 + gq * 32 + e], 0.f), p.wf2[HSEL * 128 + gq * 32 + e], dot);
+      for (int e = 0; e < 32; ++e) {
+        const float pre = __uint_as_float(acc[e]) + p.bf1[HSEL * 128 + gq * 32 + e];
+        dot = fmaf(fmaxf(pre, 0.f), p.wf2[HSEL * 128 + gq * 32 + e], dot);
+        if constexpr (SAVE) mw[gq] |= (pre > 0.f ? 1u : 0u) << e;
+      }
+    }
+    if constexpr (SAVE) {
+      if (valid && l0 + row < p.L)
+        st_global_v4(p.mask_out + (static_cast<size_t>(b) * p.L + l0 + row) * 8 + HSEL * 4, make_uint4(mw[0], mw[1], mw[2], mw[3]));
     }
     tc_fence_before();
     __syncwarp();
@@ -623,7 +656,7 @@ __device__ __forceinline__ void k2_epilogue(const Ctx<G>& cx, const K2Params& p,
   }
 }
 
-template <int CG, int DT>
+template <int CG, int DT, bool SAVE = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWs,
         const __grid_constant__ CUtensorMap tmWf, const __grid_constant__ K2Params p) {
@@ -709,10 +742,209 @@ k2_head(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtenso
       }
     }
   } else if (warp >= EPI_WARP0) {
-    if (((warp - EPI_WARP0) >> 2) == 0) k2_epilogue<G, 0>(cx, p, tmem, tiles, s_part);
-    else k2_epilogue<G, 1>(cx, p, tmem, tiles, s_part);
+    if (((warp - EPI_WARP0) >> 2) == 0) k2_epilogue<G, 0, SAVE>(cx, p, tmem, tiles, s_part);
+    else k2_epilogue<G, 1, SAVE>(cx, p, tmem, tiles, s_part);
   }
   tc_epilogue_teardown<CG>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------ backward (VJP wrt x)
+// g_x = (d eps / d x)^T g_eps for the bf16 network: the reference's DiffWave.forward is differentiable (white-box attacks
+// call loss.backward() through the purifier, robustness_eval/white_box_attack.py:438); this is the same chain rule as
+// autograd over WaveNet.py:75-97,120-135,164-172, as three streaming tcgen05 GEMMs per layer pass:
+//   MODE 0 (head)      g_s  = (g_pre . Wf) * sqrt(1/N)                      g_pre = relu'(y) * w2 * g_eps   (K = 256)
+//   MODE 1 (layer, 1)  g_o  = g_s . Ws_n + g_u' . Wr_n * sqrt(.5)           (K = 512; K = 256 for the last layer)
+//                      g_a  = [ g_o * S (1 - T^2) | g_o * T S (1 - S) ]        (the two local derivatives are saved by k1<SAVE>)
+//   MODE 2 (layer, 2)  g_u  = sum_tap g_a[l - (tap-1) d] . Wd_tap^T + sqrt(.5) g_u'   (K = 3 * 512: the transposed dilated conv)
+// Gradients travel between the kernels as bf16 channels-last tensors (TMA sources of the next GEMM), accumulate in fp32.
+struct KbParams {
+  int n_tiles, tiles_per_sample, L, dilation, last;
+  int nkb;             // K blocks per tap: 4 (head, last layer's MODE 1) or 8
+  int b_row0;          // first row of this layer's weights in the B tensor map
+  float scale;         // MODE 0: sqrt(1/N)
+  const uint16_t* ts;  // MODE 1: [chunk][L][512] d o / d a_t | d o / d a_s of this layer's gate
+  const uint16_t* g_next;  // MODE 2: [chunk][L][256] g_u of layer n+1 (unused when last)
+  uint16_t* out;       // MODE 0: g_s [..][256]; MODE 1: g_a [..][512]; MODE 2: g_u [..][256]
+};
+
+template <class G, int MODE, int HSEL>
+__device__ __forceinline__ void kb_epilogue(const Ctx<G>& cx, const KbParams& p, const uint32_t tmem, const Tiles<G::CG>& tiles) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q4 = warp & 3;
+  const int row = q4 * 32 + lane;
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+  const float sqrt_half = 0.70710678118654752440f;
+  uint32_t ti = 0;
+  for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+    const bool valid = tile < p.n_tiles;
+    const int b = valid ? tile / p.tiles_per_sample : 0;
+    const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : 0;
+    const bool live = valid && l0 + row < p.L;
+    const size_t pos = static_cast<size_t>(b) * p.L + (live ? l0 + row : 0);
+    const uint32_t r = ti & 1;
+    mbar_wait(cx.bar(BAR_ACC_FULL + r), (ti >> 1) & 1, 60);
+    tc_fence_after();
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(lane_addr + r * 256 + HSEL * 128 + gq * 32, acc);
+      tmem_ld_wait();
+      if (gq == 3) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
+      }
+      const int ch = HSEL * 128 + gq * 32;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {       // 16 channels = 32 bytes of bf16
+        uint32_t o0[8], o1[8];
+        if constexpr (MODE == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o0[e] = pack_bf16x2(__uint_as_float(acc[i * 16 + 2 * e]) * p.scale, __uint_as_float(acc[i * 16 + 2 * e + 1]) * p.scale);
+          if (live) st_global_v8(p.out + pos * C + ch + i * 16, o0);
+        } else if constexpr (MODE == 1) {
+          uint32_t tv[8], sv[8];
+          if (live) {
+            ld_global_v8(p.ts + pos * 512 + ch + i * 16, tv);
+            ld_global_v8(p.ts + pos * 512 + 256 + ch + i * 16, sv);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float g0 = __uint_as_float(acc[i * 16 + 2 * e]), g1 = __uint_as_float(acc[i * 16 + 2 * e + 1]);
+            o0[e] = pack_bf16x2(g0 * bf16_lo(tv[e]), g1 * bf16_hi(tv[e]));          // d/d a_t
+            o1[e] = pack_bf16x2(g0 * bf16_lo(sv[e]), g1 * bf16_hi(sv[e]));          // d/d a_s
+          }
+          if (live) {
+            st_global_v8(p.out + pos * 512 + ch + i * 16, o0);
+            st_global_v8(p.out + pos * 512 + 256 + ch + i * 16, o1);
+          }
+        } else {
+          uint32_t gv[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (live && !p.last) ld_global_v8(p.g_next + pos * C + ch + i * 16, gv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o0[e] = pack_bf16x2(fmaf(bf16_lo(gv[e]), sqrt_half, __uint_as_float(acc[i * 16 + 2 * e])),
+                                fmaf(bf16_hi(gv[e]), sqrt_half, __uint_as_float(acc[i * 16 + 2 * e + 1])));
+          if (live) st_global_v8(p.out + pos * C + ch + i * 16, o0);
+        }
+      }
+    }
+  }
+}
+
+// tmA0: MODE 0 g_pre, MODE 1 g_s, MODE 2 g_a (512 channels); tmA1: MODE 1 g_u of layer n+1; tmB: the transposed weights
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_bwd(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ KbParams p) {
+  using G = Geo<2, 2, 0>;
+  constexpr int CG = 2;
+  Ctx<G> cx;
+  uint8_t* gen;
+  const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
+  if (threadIdx.x == 0) prefetch_tmap(&tmA0), prefetch_tmap(&tmA1), prefetch_tmap(&tmB);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  const Tiles<CG> tiles(p.n_tiles, cx.rank);
+  const int oob_l0 = p.tiles_per_sample * TILE_M;
+  const int ntap = MODE == 2 ? 3 : 1;
+
+  if (warp == 0) {
+    RingPos<G::NSTAGE> it;
+    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride) {
+      const bool valid = tile < p.n_tiles;
+      const int b = valid ? tile / p.tiles_per_sample : 0;
+      const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+      for (int tap = 0; tap < ntap; ++tap)
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const uint32_t s = it.s, ph = it.ph;
+          cx.wait_empty(s, ph, 61);
+          if (elect_one()) {
+            cx.arm(s, G::STAGE_BYTES);
+            const int row = !valid ? oob_l0 : (MODE == 2 ? l0 - (tap - 1) * p.dilation : l0);
+            if (MODE == 1 && kb >= 4) cx.load_a(s, &tmA1, (kb - 4) * 64, row, b);
+            else cx.load_a(s, &tmA0, kb * 64, row, b);
+            cx.load_b(s, &tmB, (tap * p.nkb + kb) * 64, p.b_row0);
+          }
+          __syncwarp();
+        }
+    }
+  } else if (warp == 1) {
+    if (cx.rank == 0) {
+      RingPos<G::NSTAGE> it;
+      uint32_t ti = 0;
+      const int nk = ntap * p.nkb;
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+        const uint32_t r = ti & 1;
+        mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((ti >> 1) & 1) ^ 1, 62);
+        tc_fence_after();
+        for (int k = 0; k < nk; ++k, ++it) {
+          const uint32_t s = it.s, ph = it.ph;
+          mbar_wait(cx.bar(BAR_FULL + s), ph, 63);
+          tc_fence_after();
+          if (elect_one()) {
+            cx.mma_kblock(tmem + r * 256, cx.stage_a(s), cx.stage_b(s), k == 0);
+            cx.commit(BAR_EMPTY + s);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) cx.commit(BAR_ACC_FULL + r);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    if (((warp - EPI_WARP0) >> 2) == 0) kb_epilogue<G, MODE, 0>(cx, p, tmem, tiles);
+    else kb_epilogue<G, MODE, 1>(cx, p, tmem, tiles);
+  }
+  tc_epilogue_teardown<CG>(tmem);
+}
+
+// g_pre[m][c] = mask(m, c) ? g_eps[m] * w2[c] : 0   (bf16; backward of eps = w2 . relu(pre) + b2, WaveNet.py:161-162)
+__global__ void __launch_bounds__(256) gpre_kernel(const float* __restrict__ g_eps, const uint32_t* __restrict__ mask,
+                                                    const float* __restrict__ w2, uint4* __restrict__ g_pre, long long M) {
+  __shared__ float sw[C];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[i] = w2[i];
+  __syncthreads();
+  const long long total = M * (C / 8);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i >> 5;
+    const int c = static_cast<int>(i & 31) * 8;
+    const float g = g_eps[m];
+    const uint32_t bits = mask[m * 8 + (c >> 5)] >> (c & 31);
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      pk[e] = pack_bf16x2((bits >> (2 * e)) & 1u ? g * sw[c + 2 * e] : 0.f, (bits >> (2 * e + 1)) & 1u ? g * sw[c + 2 * e + 1] : 0.f);
+    g_pre[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// g_x[m] = sum_c g_u0[m][c] * w[c] * [w[c] x[m] + b[c] > 0]   (backward of u0 = relu(w x + b) + p0, WaveNet.py:147,13-19);
+// one warp per position, 8 channels per lane
+__global__ void __launch_bounds__(256) gx_kernel(const uint4* __restrict__ g_u0, const float* __restrict__ x,
+                                                  const float* __restrict__ w, const float* __restrict__ b,
+                                                  float* __restrict__ g_x, long long M) {
+  const int lane = threadIdx.x & 31;
+  float wv[8], bv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) wv[e] = w[lane * 8 + e], bv[e] = b[lane * 8 + e];
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long m = warp0; m < M; m += nwarps) {
+    const float xv = x[m];
+    const uint4 g = g_u0[m * 32 + lane];
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (fmaf(wv[2 * e], xv, bv[2 * e]) > 0.f) acc = fmaf(bf16_lo(gw[e]), wv[2 * e], acc);
+      if (fmaf(wv[2 * e + 1], xv, bv[2 * e + 1]) > 0.f) acc = fmaf(bf16_hi(gw[e]), wv[2 * e + 1], acc);
+    }
+    for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) g_x[m] = acc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ init conv (bf16 out)
@@ -891,7 +1123,14 @@ struct TcNet {
   CUtensorMap tmWd_s, tmWr_s, tmWs_s, tmWf_s;              // over both planes, box of 128 rows (CTA pairs only)
   int dt = 0;                                              // 0: bf16, 1: fp16, 2: bf16 hi/lo split (bf16x3)
   bool ws_split = false;                                   // layout of the reserved workspace (two planes per tensor)
-  DevBuf br, bf2, init_w, init_b;                          // fp32 vectors
+  // backward pass (bf16 mode): transposed weights, saved activations and gradient buffers for bchunk waveforms
+  DevBuf wb, wdt, wft;                                     // [N][256][512], [N][256][1536], [256][256] bf16, K-major
+  CUtensorMap tmWb, tmWdT, tmWfT;
+  DevBuf ts, mask, g_pre, g_s, g_a, g_u[2];
+  CUtensorMap tmGpre, tmGs, tmGa, tmGu[2];
+  int bchunk = 0, bL = 0;
+  bool bwd_attr = false;
+  DevBuf br, bf2, init_w, init_b, wf2_dev;                 // fp32 vectors
   std::vector<float> bskip_host, bf1_host, wf2_host;       // k2's per-channel vectors (kernel params)
   std::vector<float> bd_host;                              // [N][512] dilated-conv biases in k1's packed order (kernel params)
   DevBuf u0, u1, o;
@@ -1026,11 +1265,34 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
   TRY(upload_bf16(n->wr_s, to_split(wr_f)));
   TRY(upload_bf16(n->ws_s, to_split(ws_f)));
   TRY(upload_bf16(n->wf_s, to_split(wf_f)));
+  {  // backward operands (see k_bwd): Wb[n][o][k] = Ws_n[k][o] (k < 256) | Wr_n[k-256][o] * sqrt(.5);
+     // WdT[n][c][tap*512 + oc] = Wd_n[oc][c][tap];  WfT[c][o] = Wf[o][c]
+    std::vector<uint16_t> wb(static_cast<size_t>(N) * C * 512), wdt(static_cast<size_t>(N) * C * 1536), wft(static_cast<size_t>(C) * C);
+    const float sh = static_cast<float>(std::sqrt(0.5));
+    for (int l = 0; l < N; ++l) {
+      const float* const* w = weights + 6 + 8 * l;
+      for (int o = 0; o < C; ++o)
+        for (int k = 0; k < C; ++k) {
+          wb[(static_cast<size_t>(l) * C + o) * 512 + k] = f32_to_bf16_rne(w[6][static_cast<size_t>(k) * C + o]);
+          wb[(static_cast<size_t>(l) * C + o) * 512 + 256 + k] = f32_to_bf16_rne(w[4][static_cast<size_t>(k) * C + o] * sh);
+        }
+      for (int c = 0; c < C; ++c)
+        for (int tap = 0; tap < 3; ++tap)
+          for (int oc = 0; oc < 512; ++oc)
+            wdt[(static_cast<size_t>(l) * C + c) * 1536 + tap * 512 + oc] = f32_to_bf16_rne(w[2][(static_cast<size_t>(oc) * C + c) * 3 + tap]);
+    }
+    for (int c = 0; c < C; ++c)
+      for (int o = 0; o < C; ++o) wft[static_cast<size_t>(c) * C + o] = f32_to_bf16_rne(tail[0][static_cast<size_t>(o) * C + c]);
+    TRY(upload_bf16(n->wb, wb));
+    TRY(upload_bf16(n->wdt, wdt));
+    TRY(upload_bf16(n->wft, wft));
+  }
   n->bd_host = bd;
   TRY(upload_f32(n->br, br));
   n->bskip_host = bskip;
   n->bf1_host.assign(tail[1], tail[1] + C);
   n->wf2_host.assign(tail[2], tail[2] + C);
+  TRY(upload_f32(n->wf2_dev, n->wf2_host));
   TRY(upload_f32(n->bf2, std::vector<float>(tail[3], tail[3] + 1)));
   TRY(upload_f32(n->init_w, std::vector<float>(weights[0], weights[0] + C)));
   TRY(upload_f32(n->init_b, std::vector<float>(weights[1], weights[1] + C)));
@@ -1060,6 +1322,10 @@ int tc_net_create(TcNet** out, const ap_wavenet_cfg& cfg, const float* const* we
     TRY(encode_bf16(&n->tmWr_s, n->wr_s.p, 2, s2, bw2));
     TRY(encode_bf16(&n->tmWs_s, n->ws_s.p, 2, s2, bw2));
     TRY(encode_bf16(&n->tmWf_s, n->wf_s.p, 2, s3, bw2));
+    const uint64_t b1[2] = {512, static_cast<uint64_t>(N) * 256}, b2[2] = {1536, static_cast<uint64_t>(N) * 256};
+    TRY(encode_bf16(&n->tmWb, n->wb.p, 2, b1, bw2));
+    TRY(encode_bf16(&n->tmWdT, n->wdt.p, 2, b2, bw2));
+    TRY(encode_bf16(&n->tmWfT, n->wft.p, 2, d3, bw2));
     const char* env = std::getenv("AP_TC_PAIR");
     if (env && env[0] == '0') n->pair = false;
     if (const char* e2 = std::getenv("AP_TC_DEBUG_LAYER")) n->dbg_layer = std::atoi(e2);
@@ -1131,7 +1397,8 @@ static cudaError_t launch_pair(Kernel kernel, int grid, int smem, cudaStream_t s
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int L, int layers, cudaStream_t st) {
+static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int L, int layers, cudaStream_t st,
+                         bool save = false) {
   using namespace tc;
   const long long M = static_cast<long long>(B) * L;
   {
@@ -1162,12 +1429,17 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     p.b_res = n->br.as<float>() + static_cast<size_t>(l) * C;
     p.p_next = ptab + static_cast<size_t>(l + 1) * C;
     p.dbg = (l == n->dbg_layer) ? n->dbg.as<long long>() : nullptr;
+    p.ts_out = save ? n->ts.as<uint16_t>() : nullptr, p.ts_chunk = n->bchunk;
     p.u_plane = p.o_plane = p.wd_plane = p.wr_plane = 0;
     if (n->dt == 2) p.u_plane = n->chunk, p.o_plane = n->N * n->chunk, p.wd_plane = n->N * 512, p.wr_plane = n->N * 256;
     cudaEvent_t e0 = prof_event(n, 0), e1 = e0 ? prof_event(n, 0) : nullptr;
     if (e1) cudaEventRecord(e0, st);
     const CUtensorMap& ui = n->tmU[l & 1];
-    if (n->dt == 2)
+    if (save && n->dt == 2)
+      AP_CUDA(launch_pair(k1_layer<2, 2, true>, pair_grid(n_tiles), Geo<2, 1, 2>::SMEM_BYTES, st, ui, n->tmO, n->tmWd_s, n->tmWr_s, p));
+    else if (save)
+      AP_CUDA(launch_pair(k1_layer<2, 0, true>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2, n->tmWr2, p));
+    else if (n->dt == 2)
       AP_CUDA(launch_pair(k1_layer<2, 2>, pair_grid(n_tiles), Geo<2, 1, 2>::SMEM_BYTES, st, ui, n->tmO, n->tmWd_s, n->tmWr_s, p));
     else if (n->pair && n->dt == 0)
       AP_CUDA(launch_pair(k1_layer<2, 0>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2, n->tmWr2, p));
@@ -1183,15 +1455,20 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
   return AP_OK;
 }
 
+static int tc_net_eps_impl(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st, bool save);
 int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st) {
+  return tc_net_eps_impl(n, x, ptab, eps, B, L, st, false);
+}
+static int tc_net_eps_impl(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st, bool save) {
   using namespace tc;
   if (B > n->chunk || L != n->L || n->ws_split != (n->dt == 2))
     return fail(AP_ERR_STATE, "tc_net_eps: workspace reserved for chunk %d x L %d (%s layout)", n->chunk, n->L,
                 n->ws_split ? "split" : "single-plane");
-  int rc = tc_run_layers(n, x, ptab, B, L, n->N, st);
+  int rc = tc_run_layers(n, x, ptab, B, L, n->N, st, save);
   if (rc != AP_OK) return rc;
   const int tps = ceil_div(L, TILE_M), n_tiles = tps * B;
   K2Params p;
+  p.mask_out = save ? n->mask.as<uint32_t>() : nullptr;
   p.n_tiles = n_tiles, p.tiles_per_sample = tps, p.L = L, p.num_layers = n->N, p.chunk_alloc = n->chunk;
   p.scale = static_cast<float>(std::sqrt(1.0 / n->N));
   p.bf2 = n->bf2.as<float>();
@@ -1202,7 +1479,11 @@ int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, i
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   cudaEvent_t e0 = prof_event(n, 1), e1 = e0 ? prof_event(n, 1) : nullptr;
   if (e1) cudaEventRecord(e0, st);
-  if (n->dt == 2)
+  if (save && n->dt == 2)
+    AP_CUDA(launch_pair(k2_head<2, 2, true>, pair_grid(n_tiles), Geo<2, 2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs_s, n->tmWf_s, p));
+  else if (save)
+    AP_CUDA(launch_pair(k2_head<2, 0, true>, pair_grid(n_tiles), Geo<2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs2, n->tmWf2, p));
+  else if (n->dt == 2)
     AP_CUDA(launch_pair(k2_head<2, 2>, pair_grid(n_tiles), Geo<2, 2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs_s, n->tmWf_s, p));
   else if (n->pair && n->dt == 0)
     AP_CUDA(launch_pair(k2_head<2, 0>, pair_grid(n_tiles), Geo<2, 2>::SMEM_BYTES, st, n->tmO, n->tmWs2, n->tmWf2, p));
@@ -1214,6 +1495,95 @@ int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, i
     k2_head<1, 1><<<grid, NTHREADS, Geo<1, 2>::SMEM_BYTES, st>>>(n->tmO, n->tmWs_h, n->tmWf_h, p);
   if (e1) cudaEventRecord(e1, st);
   AP_LAUNCH_CHECK();
+  return AP_OK;
+}
+
+// ---- backward: g_x = (d eps / d x)^T g_eps at (x, ptab); also returns eps when eps_out != nullptr.  bf16 pair mode only.
+static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
+  using namespace tc;
+  if (n->bchunk == chunk && n->bL == L) return AP_OK;
+  const size_t pos = static_cast<size_t>(chunk) * L;
+  for (DevBuf* d : {&n->ts, &n->mask, &n->g_pre, &n->g_s, &n->g_a, &n->g_u[0], &n->g_u[1]}) d->release();
+  AP_CUDA(n->ts.alloc(pos * 512 * 2 * n->N));
+  AP_CUDA(n->mask.alloc(pos * 8 * 4));
+  AP_CUDA(n->g_pre.alloc(pos * 256 * 2));
+  AP_CUDA(n->g_s.alloc(pos * 256 * 2));
+  AP_CUDA(n->g_a.alloc(pos * 512 * 2));
+  AP_CUDA(n->g_u[0].alloc(pos * 256 * 2));
+  AP_CUDA(n->g_u[1].alloc(pos * 256 * 2));
+  const uint64_t d256[3] = {256, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk)};
+  const uint64_t d512[3] = {512, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk)};
+  const uint32_t bx[3] = {64, 128, 1};
+  int rc = encode_bf16(&n->tmGpre, n->g_pre.p, 3, d256, bx);
+  if (rc == AP_OK) rc = encode_bf16(&n->tmGs, n->g_s.p, 3, d256, bx);
+  if (rc == AP_OK) rc = encode_bf16(&n->tmGa, n->g_a.p, 3, d512, bx);
+  if (rc == AP_OK) rc = encode_bf16(&n->tmGu[0], n->g_u[0].p, 3, d256, bx);
+  if (rc == AP_OK) rc = encode_bf16(&n->tmGu[1], n->g_u[1].p, 3, d256, bx);
+  if (rc != AP_OK) return rc;
+  if (!n->bwd_attr) {
+    AP_CUDA(cudaFuncSetAttribute(k_bwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k2_head<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2, 2>::SMEM_BYTES));
+    n->bwd_attr = true;
+  }
+  n->bchunk = chunk, n->bL = L;
+  return AP_OK;
+}
+
+size_t tc_net_bwd_bytes_per_waveform(const TcNet* n, int L) {
+  return static_cast<size_t>(L) * (static_cast<size_t>(n->N) * 1024 + 32 + 512 + 512 + 1024 + 1024);
+}
+
+int tc_net_vjp(TcNet* n, const float* x, const float* ptab, const float* g_eps, float* g_x, float* eps_out, float* eps_scratch,
+               int B, int L, int bchunk, cudaStream_t st) {
+  using namespace tc;
+  if (n->dt == 1) return fail(AP_ERR_STATE, "backward pass: bf16 / bf16x3 modes only");
+  if (B > n->chunk || L != n->L || n->ws_split != (n->dt == 2)) return fail(AP_ERR_STATE, "tc_net_vjp: forward workspace mismatch");
+  if (B > bchunk) return fail(AP_ERR_STATE, "tc_net_vjp: batch %d exceeds the backward chunk %d", B, bchunk);
+  int rc = tc_bwd_reserve(n, bchunk, L);
+  if (rc != AP_OK) return rc;
+  // forward, keeping tanh / sigmoid of every layer and the head's ReLU mask
+  rc = tc_net_eps_impl(n, x, ptab, eps_out ? eps_out : eps_scratch, B, L, st, true);
+  if (rc != AP_OK) return rc;
+  const long long M = static_cast<long long>(B) * L;
+  const int tps = ceil_div(L, TILE_M), n_tiles = tps * B, grid = pair_grid(n_tiles), smem = Geo<2, 2>::SMEM_BYTES;
+  {
+    long long blocks = ceil_div_ll(M * (C / 8), 256);
+    const long long cap = static_cast<long long>(num_sms()) * 8;
+    gpre_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, st>>>(g_eps, n->mask.as<uint32_t>(), n->wf2_dev.as<float>(),
+                                                                                    n->g_pre.as<uint4>(), M);
+    AP_LAUNCH_CHECK();
+  }
+  KbParams p{};
+  p.n_tiles = n_tiles, p.tiles_per_sample = tps, p.L = L, p.dilation = 1, p.last = 0;
+  p.nkb = 4, p.b_row0 = 0, p.scale = static_cast<float>(std::sqrt(1.0 / n->N));
+  p.ts = nullptr, p.g_next = nullptr, p.out = n->g_s.as<uint16_t>();
+  AP_CUDA(launch_pair(k_bwd<0>, grid, smem, st, n->tmGpre, n->tmGpre, n->tmWfT, p));
+  AP_LAUNCH_CHECK();
+  for (int l = n->N - 1; l >= 0; --l) {
+    const bool last = l == n->N - 1;
+    // g_u of layer l+1 lives in g_u[(l+1) & 1]; this layer writes g_u[l & 1]
+    p.last = last, p.nkb = last ? 4 : 8, p.b_row0 = l * 256;
+    p.ts = n->ts.as<uint16_t>() + static_cast<size_t>(l) * n->bchunk * L * 512;
+    p.out = n->g_a.as<uint16_t>();
+    AP_CUDA(launch_pair(k_bwd<1>, grid, smem, st, n->tmGs, n->tmGu[(l + 1) & 1], n->tmWb, p));
+    AP_LAUNCH_CHECK();
+    p.nkb = 8, p.dilation = 1 << (l % n->cfg.dilation_cycle);
+    p.g_next = n->g_u[(l + 1) & 1].as<uint16_t>(), p.out = n->g_u[l & 1].as<uint16_t>();
+    AP_CUDA(launch_pair(k_bwd<2>, grid, smem, st, n->tmGa, n->tmGa, n->tmWdT, p));
+    AP_LAUNCH_CHECK();
+  }
+  {
+    long long blocks = ceil_div_ll(M * 32, 256);
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    gx_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, st>>>(n->g_u[0].as<uint4>(), x, n->init_w.as<float>(),
+                                                                                  n->init_b.as<float>(), g_x, M);
+    AP_LAUNCH_CHECK();
+  }
   return AP_OK;
 }
 

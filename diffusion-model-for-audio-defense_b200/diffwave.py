@@ -72,12 +72,35 @@ def wavenet_weight_list(state_dict: dict, cfg: dict) -> list:
     return [np.ascontiguousarray(a) for a in out]
 
 
+def _wants_grad(x) -> bool:
+    return isinstance(x, torch.Tensor) and x.requires_grad and torch.is_grad_enabled()
+
+
+class _EpsVJP(torch.autograd.Function):
+    """eps_theta(x, t) with a backward pass through the CUDA kernels (``ap_diffwave_eps_vjp``): the reference's WaveNet is
+    an ordinary autograd module, and white-box attacks differentiate through it (robustness_eval/white_box_attack.py:438).
+    Only the input is kept; the backward call recomputes the forward with the activations it needs."""
+
+    @staticmethod
+    def forward(ctx, x, net, t):
+        xd = x.detach().to(torch.float32).contiguous()
+        ctx.net, ctx.t = net, float(t)
+        ctx.save_for_backward(xd)
+        return net.eps(xd, float(t))
+
+    @staticmethod
+    def backward(ctx, g):
+        (xd,) = ctx.saved_tensors
+        return ctx.net.eps_vjp(xd, ctx.t, g), None, None
+
+
 def _check_wave(x: torch.Tensor, what: str) -> torch.Tensor:
     if not isinstance(x, torch.Tensor):
         raise TypeError(f"{what}: expected a torch.Tensor, got {type(x)}")
     if x.requires_grad and torch.is_grad_enabled():
-        raise AudioPureError(f"{what}: audiopure_b200 is inference-only; got an input that requires grad "
-                             "(wrap the call in torch.no_grad() or detach the input)")
+        raise AudioPureError(f"{what}: this entry point is inference-only; got an input that requires grad (gradients "
+                             "flow through WaveNet.eps / WaveNet(...) / DiffWave.forward / RevDiffWave.forward in the "
+                             "bf16 and bf16x3 modes; otherwise wrap the call in torch.no_grad() or detach the input)")
     if not x.is_cuda:
         raise AudioPureError(f"{what}: input must be a CUDA tensor (there is no CPU path)")
     return x.detach().to(torch.float32).contiguous()
@@ -126,7 +149,11 @@ class WaveNet(torch.nn.Module):
 
     # -- forward --------------------------------------------------------------------------------------------------
     def eps(self, x: torch.Tensor, t: float, out: torch.Tensor | None = None) -> torch.Tensor:
-        """eps_theta(x, t) with the same diffusion step t for every row."""
+        """eps_theta(x, t) with the same diffusion step t for every row.  Differentiable wrt x (bf16 mode)."""
+        if out is None and _wants_grad(x):
+            if not x.is_cuda:
+                raise AudioPureError("WaveNet: input must be a CUDA tensor (there is no CPU path)")
+            return _EpsVJP.apply(x, self, float(t))
         x = _check_wave(x, "WaveNet")
         assert x.ndim == 3 and x.shape[1] == 1, x.shape
         B, _, L = x.shape
@@ -136,6 +163,18 @@ class WaveNet(torch.nn.Module):
             _lib.check(self._lib.ap_diffwave_eps(self._handle, x.data_ptr(), float(t), out.data_ptr(), B, L,
                                                  _lib.stream_ptr()), "ap_diffwave_eps")
         return out
+
+    def eps_vjp(self, x: torch.Tensor, t: float, g_eps: torch.Tensor) -> torch.Tensor:
+        """g_x = (d eps_theta(x, t) / d x)^T g_eps (the backward of ``eps``)."""
+        x = _check_wave(x, "WaveNet.eps_vjp")
+        g = g_eps.detach().to(torch.float32).contiguous()
+        assert x.ndim == 3 and x.shape[1] == 1 and g.shape == x.shape, (x.shape, g.shape)
+        B, _, L = x.shape
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(self._lib.ap_diffwave_eps_vjp(self._handle, x.data_ptr(), float(t), g.data_ptr(), gx.data_ptr(), None, B, L,
+                                                     _lib.stream_ptr()), "ap_diffwave_eps_vjp")
+        return gx
 
     def forward(self, input_data):
         audio, diffusion_steps = input_data
@@ -224,9 +263,44 @@ class DiffWave(torch.nn.Module):
     # -- reference API --------------------------------------------------------------------------------------------
     def forward(self, waveforms: Union[torch.Tensor, np.ndarray]):
         waveforms = self._as_tensor(waveforms)
+        if _wants_grad(waveforms):
+            return self._forward_autograd(waveforms)
         output = self._diffusion(waveforms)
         output = self._reverse(output)
         return output
+
+    def _randn(self, shape, device) -> torch.Tensor:
+        """A standard-normal tensor from the same stream the fused update kernels would consume (noise='philox': the
+        Philox counters of this draw; noise='torch': torch.normal on the CPU generator like the reference)."""
+        z, zp, seed, off = self._noise_args(shape, device)
+        if z is not None:
+            return z
+        zero = torch.zeros(tuple(shape), device=device, dtype=torch.float32)
+        out = torch.empty_like(zero)
+        n = int(np.prod(shape))
+        with torch.cuda.device(device):   # 0 * 0 + 1 * z
+            _lib.check(self._lib.ap_diffuse(zero.data_ptr(), 0.0, 1.0, None, seed, off, out.data_ptr(), shape[0], n // shape[0],
+                                            _lib.stream_ptr()), "ap_diffuse")
+        return out
+
+    def _forward_autograd(self, x_0: torch.Tensor) -> torch.Tensor:
+        """``forward`` for an input that requires grad (diffwave_ddpm.py:36-104 is differentiable in the reference).  The
+        network and its backward run in the CUDA kernels (``_EpsVJP``); the per-step affine updates are torch ops so that
+        autograd chains them.  Same noise order as the inference path: z_diffuse, z_{t*-1}, ..., z_1."""
+        _, _, Alpha_bar, _ = self._tables()
+        assert x_0.ndim == 3
+        if not x_0.is_cuda:
+            raise AudioPureError("DiffWave: input must be a CUDA tensor (there is no CPU path)")
+        t_star = self.reverse_timestep
+        a, b = float(torch.sqrt(Alpha_bar[t_star - 1])), float(torch.sqrt(1 - Alpha_bar[t_star - 1]))
+        x = a * x_0.to(torch.float32) + b * self._randn(x_0.shape, x_0.device)
+        for t in range(t_star - 1, -1, -1):
+            eps = self.model.eps(x, float(t))
+            c_eps, sqrt_alpha, sigma = self._ddpm_coefficients(t)
+            x = (x - c_eps * eps) / sqrt_alpha
+            if t > 0:
+                x = x + sigma * self._randn(x.shape, x.device)
+        return x
 
     def _diffusion(self, x_0):
         x_0 = self._as_tensor(x_0)

@@ -96,6 +96,8 @@ class RevDiffWave(torch.nn.Module):
     def audio_editing_sample(self, audio):
         assert isinstance(audio, torch.Tensor)
         assert audio.ndim == 3, audio.ndim
+        if audio.requires_grad and torch.is_grad_enabled():
+            return self._audio_editing_sample_autograd(audio.to(self.device))
         x0 = _check_wave(audio.to(self.device), "RevDiffWave")
         B, L = x0.shape[0], int(np.prod(x0.shape[1:]))
         dw = self.model
@@ -127,6 +129,36 @@ class RevDiffWave(torch.nn.Module):
                 with torch.cuda.device(x.device):
                     _lib.check(self._lib.ap_sde_step(x.data_ptr(), eps.data_ptr(), coef, zp, seed, off, B, L,
                                                      _lib.stream_ptr()), "ap_sde_step")
+            x0 = x
+            xs.append(x0)
+        return torch.cat(xs, dim=0)
+
+    def _audio_editing_sample_autograd(self, x0):
+        """The same Euler-Maruyama chain for an input that requires grad (the reference differentiates it with
+        torchsde.sdeint_adjoint, diffwave_sde.py:200-203): network + backward in the CUDA kernels, the affine step in torch
+        ops (discretise-then-differentiate: the exact gradient of the computed output)."""
+        dw = self.model
+        xs = []
+        x0 = x0.to(torch.float32)
+        for _ in range(self.args.sample_step):
+            total_noise_levels = self.args.t
+            if self.args.rand_t:
+                total_noise_levels = self.args.t + np.random.randint(-self.args.t_delta, self.args.t_delta)
+            a = (1 - self.betas).cumprod(dim=0)
+            sa, sb = float(a[total_noise_levels - 1].sqrt()), float((1.0 - a[total_noise_levels - 1]).sqrt())
+            e = torch.randn_like(x0) if self.noise == "torch" else dw._randn(x0.shape, x0.device)
+            x = sa * x0 + sb * e
+            for s, ds in euler_schedule(self.args.t, self.T):
+                d, c = self.rev_vpsde.step_coefficients(s, ds)
+                eps = dw.model.eps(x, float(d))
+                f = 0.5 * c.beta * x - c.diff2 * eps / c.sqrt_1mab        # -(drift - g^2 score), score = -eps / sqrt(1 - abar)
+                x = x + f * c.dt
+                if self.noise == "torch":
+                    z = torch.randn(x.shape, device=x.device) if c.g != 0.0 else None
+                else:
+                    z = dw._randn(x.shape, x.device)
+                if z is not None and c.g != 0.0:
+                    x = x + c.g * c.sqrt_dt * z
             x0 = x
             xs.append(x0)
         return torch.cat(xs, dim=0)

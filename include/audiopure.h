@@ -93,6 +93,16 @@ int ap_diffwave_reserve(ap_diffwave_t h, int chunk, int L);
  * (DiffWave.compute_eps_t, diffwave_ddpm.py:166-172).  x, eps: device (B, L). */
 int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* eps, int B, int L, void* stream);
 
+/* Vector-Jacobian product of the network wrt its input: g_x = (d eps_theta(x, t) / d x)^T g_eps -- what autograd computes
+ * through WaveNet_Speech_Commands.forward (WaveNet.py:164-172) when a white-box attack back-propagates through the purifier
+ * (DiffWave.forward is differentiable, diffwave_ddpm.py:36-47; robustness_eval/white_box_attack.py:438).  x, g_eps, g_x
+ * (and eps_out, optional: the network output at x) are device fp32 (B, L).  AP_MODE_BF16 or AP_MODE_BF16X3 (the forward
+ * in the handle's mode, the backward GEMMs with bf16 operands); the forward is recomputed with the gate's two local
+ * derivatives of every layer kept (~0.6 GB per 1 s waveform), in sub-batches bounded to ~24 GB.  The head's ReLU makes the
+ * gradient discontinuous in the forward values: with a bf16 forward ~1 % of its masks differ from an fp32 forward's. */
+int ap_diffwave_eps_vjp(ap_diffwave_t h, const float* x, float t, const float* g_eps, float* g_x, float* eps_out, int B,
+                        int L, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Per-step updates (HBM-bound elementwise kernels; in-kernel Philox4x32-10 + Box-Muller when z == NULL)
  * Noise element i of a call uses Philox counter (offset + i/4), key = seed; callers advance `offset` by

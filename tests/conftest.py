@@ -17,3 +17,10 @@ def golden():
     import numpy as np
     path = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
     return dict(np.load(path))
+
+
+@pytest.fixture(scope="session")
+def golden_grad():
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "reference_golden_grad.npz")
+    return dict(np.load(path))

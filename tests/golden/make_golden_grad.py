@@ -1,0 +1,69 @@
+"""Golden GRADIENTS from the unmodified reference (autograd through WaveNet_Speech_Commands / DiffWave.forward), for the
+backward pass of the CUDA path (ap_diffwave_eps_vjp).  Same shim and synthetic weights as make_golden.py.
+
+    python tests/golden/make_golden_grad.py        # in the build container; writes reference_golden_grad.npz
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as mg  # noqa: E402
+from make_golden import REF, NoiseInjector, synthetic, to_torch_sd  # noqa: E402
+
+
+def main():
+    mg.install_shim()
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    from diffusion_models.diffwave_ddpm import DiffWave
+    from diffusion_models.DiffWave_Unconditional.WaveNet import WaveNet_Speech_Commands
+    from diffusion_models.DiffWave_Unconditional.util import calc_diffusion_hyperparams
+
+    cfg = json.load(open(os.path.join(REF, "configs", "config.json")))
+    hp = calc_diffusion_hyperparams(**cfg["diffusion_config"])
+    net = WaveNet_Speech_Commands(**cfg["wavenet_config"]).eval()
+    net.load_state_dict(to_torch_sd(synthetic.wavenet_state_dict(seed=0)))
+    for p in net.parameters():
+        p.requires_grad_(False)
+    out = {}
+
+    # ---- VJP of the network: g_x = (d eps / d x)^T g_eps at t = 7 and t = 65
+    x = torch.from_numpy(synthetic.synthetic_waveforms(2, 1024, seed=1234))
+    g_eps = torch.from_numpy(synthetic.host_noise((2, 1, 1024), 4242, 0))
+    out["vjp_g_eps"] = g_eps.numpy()
+    for t in (7.0, 65.0):
+        xr = x.clone().requires_grad_(True)
+        eps = net((xr, t * torch.ones(2, 1)))
+        (gx,) = torch.autograd.grad(eps, xr, g_eps)
+        out[f"vjp_gx_L1024_t{int(t)}"] = gx.numpy()
+    # ragged length: zero padding at both ends with every dilation
+    x3 = torch.from_numpy(synthetic.synthetic_waveforms(1, 3001, seed=77))
+    g3 = torch.from_numpy(synthetic.host_noise((1, 1, 3001), 4243, 0))
+    out["vjp_g_eps_L3001"] = g3.numpy()
+    xr = x3.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad(net((xr, 7.0 * torch.ones(1, 1))), xr, g3)
+    out["vjp_gx_L3001_t7"] = gx.numpy()
+
+    # ---- gradient through the whole purifier (DiffWave.forward, t* = 2, injected noise): d <w, purified> / d x
+    dw = DiffWave(model=net, diffusion_hyperparams=hp, reverse_timestep=2).eval()
+    w = torch.from_numpy(synthetic.host_noise((2, 1, 1024), 4244, 0))
+    out["ddpm_grad_w"] = w.numpy()
+    xr = x.clone().requires_grad_(True)
+    with NoiseInjector(2024) as inj:
+        y = dw(xr)
+        assert inj.i == 2
+    (gx,) = torch.autograd.grad((y * w).sum(), xr)
+    out["ddpm_t2_purified"] = y.detach().numpy()
+    out["ddpm_t2_grad_L1024"] = gx.numpy()
+    np.savez_compressed(os.path.join(HERE, "reference_golden_grad.npz"), **out)
+    for k, v in out.items():
+        print(k, v.shape, float(np.abs(v).max()))
+
+
+if __name__ == "__main__":
+    main()

@@ -240,12 +240,68 @@ def test_full_size_batch_properties(ap, sd_full):
         assert torch.equal(eps_full, eps_one)                            # network output is batch independent, bit for bit
 
 
-def test_inference_only_and_cpu_inputs_raise(ap, diffwave):
+def test_inference_only_entry_points_and_cpu_inputs_raise(ap, diffwave):
+    """gradients flow through WaveNet / DiffWave.forward (backward-pass tests below); the other entry points refuse an
+    input that requires grad instead of silently dropping the gradient, and there is no CPU path"""
     x = torch.zeros(1, 1, 256, device="cuda", requires_grad=True)
     with pytest.raises(ap.AudioPureError):
-        diffwave.model.eps(x, 1.0)
+        diffwave.one_shot_denoise(x)
     with pytest.raises(ap.AudioPureError):
         diffwave.model.eps(torch.zeros(1, 1, 256), 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------- backward pass
+# Gradient tolerances.  The backward GEMMs use bf16 operands (their own rounding costs ~1 %).  The head's ReLU makes the
+# gradient a discontinuous function of the forward values: a bf16 forward (skip sum off by ~0.8 %) flips ~1 % of the
+# ReLU masks relative to the fp32 reference, which alone moves the gradient by 7-8 % (reproduced on the CPU by perturbing
+# the oracle's skip sum by 0.8 %).  With the bf16x3 forward the masks agree and only the backward's rounding remains.
+TOL_GRAD = {"bf16x3": 2e-2, "bf16": 1.5e-1}
+
+
+@pytest.mark.parametrize("key,L,B,t,seed,gkey", [("vjp_gx_L1024_t7", 1024, 2, 7.0, 1234, "vjp_g_eps"),
+                                                 ("vjp_gx_L1024_t65", 1024, 2, 65.0, 1234, "vjp_g_eps"),
+                                                 ("vjp_gx_L3001_t7", 3001, 1, 7.0, 77, "vjp_g_eps_L3001")])
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_wavenet_vjp_vs_reference_autograd(ap, golden_grad, sd_full, key, L, B, t, seed, gkey, mode):
+    """g_x = (d eps / d x)^T g_eps from the CUDA backward kernels vs autograd through the unmodified reference WaveNet
+    (tests/golden/make_golden_grad.py)."""
+    net = ap.WaveNet(sd_full, mode=mode, **synthetic.DEFAULT_WAVENET_CONFIG)
+    x = cuda(synthetic.synthetic_waveforms(B, L, seed=seed)).requires_grad_(True)
+    g = cuda(golden_grad[gkey])
+    eps = net((x, t * torch.ones(B, 1)))
+    assert eps.requires_grad
+    (gx,) = torch.autograd.grad(eps, x, g)
+    err = rel_l2(gx, golden_grad[key])
+    print(f"{key} {mode}: gradient rel-L2 {err:.3e}")
+    assert err < TOL_GRAD[mode]
+    # direct C-ABI call: linear in g_eps
+    gx2 = net.eps_vjp(x.detach(), t, 2.0 * g)
+    assert rel_l2(gx2, 2.0 * gx) < 1e-2
+
+
+def test_vjp_modes_without_a_backward_raise(ap, sd_full):
+    x = cuda(synthetic.synthetic_waveforms(1, 256, seed=1))
+    for mode in ("fp32", "fp16"):
+        with pytest.raises(ap.AudioPureError):
+            ap.WaveNet(sd_full, mode=mode, **synthetic.DEFAULT_WAVENET_CONFIG).eps_vjp(x, 3.0, torch.ones_like(x))
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_ddpm_purifier_gradient_vs_reference_autograd(diffwave, golden_grad, mode):
+    """d <w, DiffWave.forward(x)> / d x through two network evaluations, with the reference's injected noise."""
+    diffwave.model.set_mode(mode)
+    diffwave.reverse_timestep = 2
+    x = cuda(synthetic.synthetic_waveforms(2, 1024, seed=1234)).requires_grad_(True)
+    with TorchNormalInjector(2024) as inj:
+        y = diffwave(x)
+        assert inj.i == 2
+    assert rel_l2(y.detach(), golden_grad["ddpm_t2_purified"]) < TOL[mode]
+    (gx,) = torch.autograd.grad((y * cuda(golden_grad["ddpm_grad_w"])).sum(), x)
+    err = rel_l2(gx, golden_grad["ddpm_t2_grad_L1024"])
+    print(f"ddpm_t2 gradient {mode}: rel-L2 {err:.3e}")
+    # the purifier's Jacobian is close to a scaled identity: d eps / d x enters with c_eps ~ 0.012 per step
+    assert err < 0.1 * TOL_GRAD[mode]
+    diffwave.model.set_mode("bf16")
 
 
 # ---------------------------------------------------------------------------------------------------- purifier

@@ -186,3 +186,21 @@ def test_reffwave(golden, sd_full, hp):
     x = synthetic.synthetic_waveforms(2, 1024, seed=1234)
     y = orc.reffwave_forward(sd_full, x, hp, 5, 2, noise_list(2029, 2, x.shape)).numpy()
     assert rel_l2(y, golden["reffwave_t5_re2_L1024"]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------- gradients
+def test_oracle_autograd_matches_reference_gradients(golden_grad, sd_full, hp):
+    """The oracle is differentiable (torch ops); its autograd gradients are the checker of the CUDA backward pass
+    (ap_diffwave_eps_vjp).  Pinned here to gradients of the unmodified reference (tests/golden/make_golden_grad.py)."""
+    x = torch.from_numpy(synthetic.synthetic_waveforms(2, 1024, seed=1234))
+    g = torch.from_numpy(golden_grad["vjp_g_eps"])
+    xr = x.clone().requires_grad_(True)
+    eps = orc.wavenet_forward(sd_full, xr, 7.0 * torch.ones(2, 1))
+    (gx,) = torch.autograd.grad(eps, xr, g)
+    assert rel_l2(gx.numpy(), golden_grad["vjp_gx_L1024_t7"]) < 2e-5
+    # whole purifier: d <w, DiffWave.forward(x)> / d x with the reference's noise order
+    xr = x.clone().requires_grad_(True)
+    y = orc.ddpm_forward(sd_full, xr, hp, 2, noise_list(2024, 2, (2, 1, 1024)))
+    assert rel_l2(y.detach().numpy(), golden_grad["ddpm_t2_purified"]) < 1e-5
+    (gx,) = torch.autograd.grad((y * torch.from_numpy(golden_grad["ddpm_grad_w"])).sum(), xr)
+    assert rel_l2(gx.numpy(), golden_grad["ddpm_t2_grad_L1024"]) < 2e-5

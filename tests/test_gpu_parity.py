@@ -371,6 +371,37 @@ def test_sde_purifier_vs_oracle(ap, orc, sd_full, mode, t_star):
     assert err < (2e-5 if mode == "fp32" else 1e-2)
 
 
+def test_sde_purifier_gradient_vs_oracle_autograd(ap, orc, sd_full):
+    """RevDiffWave.forward is differentiable (the reference uses torchsde.sdeint_adjoint): gradient of <w, purified> through
+    the Euler-Maruyama chain (t* = 2) vs autograd over the oracle's restatement, same injected noise."""
+    import argparse
+    t_star = 2
+    args = argparse.Namespace(ddpm_path=None, ddpm_config=CONFIG_JSON, t=t_star, score_type="guided_diffusion", rand_t=False,
+                              t_delta=0, use_bm=False, sample_step=1)
+    rdw = ap.RevDiffWave(args, state_dict=sd_full, noise="torch", mode="bf16x3")
+    x = synthetic.synthetic_waveforms(2, 1024, seed=21)
+    w = synthetic.host_noise(x.shape, 77, 0)
+    n_steps = len(orc.sde_euler_schedule(t_star))
+    zs = [synthetic.host_noise(x.shape, 3000 + t_star, i) for i in range(1 + n_steps)]
+    xo = torch.from_numpy(x).requires_grad_(True)
+    yo = orc.sde_purify(sd_full, xo, t_star, orc.NoiseSource(zs))
+    (g_want,) = torch.autograd.grad((yo * torch.from_numpy(w)).sum(), xo)
+    it = iter(zs)
+    orig_like, orig_randn = torch.randn_like, torch.randn
+    torch.randn_like = lambda t, **kw: cuda(next(it))
+    torch.randn = lambda *a, **kw: cuda(next(it))
+    try:
+        xg = cuda(x).requires_grad_(True)
+        got = rdw(xg)
+    finally:
+        torch.randn_like, torch.randn = orig_like, orig_randn
+    assert rel_l2(got.detach(), yo.detach().numpy()) < 1e-5
+    (g_got,) = torch.autograd.grad((got * cuda(w)).sum(), xg)
+    err = rel_l2(g_got, g_want.numpy())
+    print(f"sde t*={t_star} gradient (bf16x3 forward): rel-L2 {err:.3e}")
+    assert err < 2e-3
+
+
 # ---------------------------------------------------------------------------------------------------- mel + classifiers
 def test_mel_vs_torchaudio_golden(ap, golden):
     xm = cuda(synthetic.synthetic_waveforms(2, 16000, seed=99))

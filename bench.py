@@ -297,7 +297,7 @@ def run_ours(args):
                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
                         "traffic": 24.38e6 * avg_wf if args.mode != "bf16x3" else None,
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum = 3.120e9 B for a 128-waveform launch "
-                                          "(profiles/r01_k1_v5_ncu_full_summary.txt; algorithmic 3.146e9 B), scaled to this "
+                                          "(profiles/r01_k1_v6_ncu_full_summary.txt; algorithmic 3.146e9 B), scaled to this "
                                           "run's waveforms per launch" if args.mode != "bf16x3" else "no ncu capture of the split kernel",
                         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                         "mma_flops_per_algorithmic_flop": 3 if args.mode == "bf16x3" else 1,

@@ -304,6 +304,25 @@ def test_ddpm_purifier_gradient_vs_reference_autograd(diffwave, golden_grad, mod
     diffwave.model.set_mode("bf16")
 
 
+def test_vjp_sub_batches_and_mode_switches(ap, sd_full):
+    """48 x 1 s waveforms exceed the 24 GB bound on saved activations (0.62 GB each): the backward runs in sub-batches
+    (38 + 10) and must equal the per-row results; switching bf16 <-> bf16x3 re-lays the workspace (one / two planes)."""
+    net = ap.WaveNet(sd_full, mode="bf16", **synthetic.DEFAULT_WAVENET_CONFIG)
+    x = cuda(synthetic.synthetic_waveforms(48, 16000, seed=5))
+    g = torch.randn(x.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    e0 = net.eps(x[40:], 9.0)
+    gx_all = net.eps_vjp(x, 9.0, g)
+    gx_tail = net.eps_vjp(x[40:].contiguous(), 9.0, g[40:].contiguous())
+    assert torch.isfinite(gx_all).all() and torch.equal(gx_all[40:], gx_tail)
+    net.set_mode("bf16x3")
+    e3 = net.eps(x[40:], 9.0)
+    assert rel_l2(e0, e3) < 2.5e-2 and not torch.equal(e0, e3)      # bf16 vs fp32-class eps at full length: 1.6e-2
+    gx3 = net.eps_vjp(x[40:].contiguous(), 9.0, g[40:].contiguous())
+    assert rel_l2(gx_tail, gx3) < 0.2
+    net.set_mode("bf16")
+    assert torch.equal(net.eps(x[40:], 9.0), e0)
+
+
 # ---------------------------------------------------------------------------------------------------- purifier
 @pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16", "bf16x3"])
 def test_ddpm_purifier_vs_reference_golden(diffwave, golden, mode):

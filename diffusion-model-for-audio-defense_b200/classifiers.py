@@ -63,12 +63,12 @@ class _Classifier(torch.nn.Module):
         return "tf32" if self._lib.ap_classifier_get_mode(self._handle) == _lib.AP_MODE_TF32 else "fp32"
 
     def __del__(self):
-        h, self._handle = getattr(self, "_handle", None), None
-        if h:
-            try:
+        try:   # may run during interpreter shutdown, when torch's Module.__setattr__ no longer works
+            h = self.__dict__.pop("_handle", None)
+            if h:
                 self._lib.ap_classifier_destroy(h)
-            except Exception:
-                pass
+        except Exception:
+            pass
 
 
 def _strip(sd: dict) -> dict:

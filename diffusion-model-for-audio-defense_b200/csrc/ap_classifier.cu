@@ -461,7 +461,11 @@ static int forward_resnext(ap_classifier_t h, const float* spec, float* logits, 
   const int H0 = 32, W0 = 32;
   int maxc = 64;
   for (auto& b : h->blocks) maxc = std::max(maxc, std::max(b->D, b->cout));
-  const int chunk = 64;
+  static const int chunk = [] {   // images per pass through the five activation buffers (AP_CLS_CHUNK overrides)
+    const char* e = std::getenv("AP_CLS_CHUNK");
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : 256;   // 64 -> 256 images: 15.8 -> 13.6 ms per 512 images (fewer ragged waves in the 8x8 stage)
+  }();
   const size_t need = static_cast<size_t>(std::min(B, chunk)) * H0 * W0 * maxc;
   if (need > h->buf_elems) h->plans.clear();     // buffers move: the tensor maps must be re-encoded
   int rc = ensure_ws(h, need);

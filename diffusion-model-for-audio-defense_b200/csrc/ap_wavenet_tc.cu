@@ -70,7 +70,7 @@ template <int CG_, int KIND, int DT_ = 0> struct Geo {
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
   static_assert(NSTAGE <= 5, "barrier table holds at most 5 stages");
 };
-enum { BAR_FULL = 0, BAR_EMPTY = 5, BAR_ACC_FULL = 10, BAR_ACC_EMPTY = 12, BAR_OUT_READY = 14, BAR_UC_FULL = 17, BAR_COUNT = 18 };
+enum { BAR_FULL = 0, BAR_EMPTY = 5, BAR_ACC_FULL = 10, BAR_ACC_EMPTY = 12, BAR_OUT_READY = 14, BAR_COUNT = 16 };
 
 // position in the TMA ring: stage index and phase parity (no division in the producer / MMA-issue loops)
 template <int NSTAGE> struct RingPos {
@@ -146,8 +146,7 @@ template <class G> __device__ __forceinline__ uint32_t tc_prologue(Ctx<G>& cx, u
       mbar_init(cx.bar(BAR_ACC_FULL + i), 1);
       mbar_init(cx.bar(BAR_ACC_EMPTY + i), 8 * CG);
     }
-    for (int i = 0; i < 3; ++i) mbar_init(cx.bar(BAR_OUT_READY + i), out_ready_count * CG);
-    mbar_init(cx.bar(BAR_UC_FULL), 1);
+    for (int i = 0; i < 2; ++i) mbar_init(cx.bar(BAR_OUT_READY + i), out_ready_count * CG);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -269,12 +268,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
             const float t1 = tanh_approx(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]);
             const float s0 = tanh_approx(fmaf(__uint_as_float(sg[gq][c0]), 0.5f, p.bd[cb + 128]));
             const float s1 = tanh_approx(fmaf(__uint_as_float(sg[gq][c0 + 1]), 0.5f, p.bd[cb + 129]));
-#ifdef AP_ABLATE_NO_MATH
-            pk[gq][i][e] = ta[gq][c0] ^ sg[gq][c0 + 1];
-            (void)t0, (void)t1, (void)s0, (void)s1;
-#else
             pk[gq][i][e] = pack2<DT>(t0 * fmaf(s0, 0.5f, 0.5f), t1 * fmaf(s1, 0.5f, 0.5f));
-#endif
             if constexpr (SAVE) {
               // the gate's local derivatives d o / d a_t = S (1 - T^2) and d o / d a_s = T S (1 - S), taken in fp32 here:
               // recomputing them from bf16-rounded T, S loses all precision where the gate saturates (1 - T^2 << 1)
@@ -316,11 +310,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     fence_proxy_async_smem();
     named_bar_sync(1, EPI_THREADS);
     if (etid == 0) {
-#ifdef AP_ABLATE_NO_OSTORE
-      if (false) {
-#else
       if (valid) {
-#endif
         tma_store_3d(tmO, cx.out_kb(2 * J), (2 * J) * 64, l0, p.layer * p.chunk_alloc + b);
         tma_store_3d(tmO, cx.out_kb(2 * J + 1), (2 * J + 1) * 64, l0, p.layer * p.chunk_alloc + b);
         if constexpr (G::SPLIT) {
@@ -337,11 +327,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
   // ---- residual epilogue: u' = (u + r) * sqrt(.5) + (b_res * sqrt(.5) + p_next) -> bf16, global -> registers -> global
   auto residual = [&](bool valid, int b, int l0) {
     const uint32_t r = g & 1;
-#ifdef AP_ABLATE_NO_RESID_IO
-    const bool live = false;
-#else
     const bool live = valid && l0 + row < p.L;
-#endif
     const size_t goff = (static_cast<size_t>(b) * p.L + (live ? l0 + row : 0)) * C + HSEL * 128;
     const size_t lo_off = static_cast<size_t>(p.u_plane) * p.L * C;     // split mode: the lo plane
     uint32_t uu[G::SPLIT ? 1 : 8][8];

@@ -205,12 +205,12 @@ class WaveNet(torch.nn.Module):
         return u, g
 
     def __del__(self):
-        h, self._handle = getattr(self, "_handle", None), None
-        if h:
-            try:
+        try:   # may run during interpreter shutdown, when torch's Module.__setattr__ no longer works
+            h = self.__dict__.pop("_handle", None)
+            if h:
                 self._lib.ap_diffwave_destroy(h)
-            except Exception:
-                pass
+        except Exception:
+            pass
 
 
 class DiffWave(torch.nn.Module):

@@ -46,12 +46,12 @@ class MelSpectrogramDB(torch.nn.Module):
         return self
 
     def __del__(self):
-        h, self._handle = getattr(self, "_handle", None), None
-        if h:
-            try:
+        try:   # may run during interpreter shutdown, when torch's Module.__setattr__ no longer works
+            h = self.__dict__.pop("_handle", None)
+            if h:
                 self._lib.ap_mel_destroy(h)
-            except Exception:
-                pass
+        except Exception:
+            pass
 
 
 def sc09_transform(device=None) -> MelSpectrogramDB:

@@ -68,9 +68,11 @@ SIGNATURES = {
     "ap_mel_destroy": (None, [_vp]),
     "ap_mel_frames": (_i, [_vp, _i]),
     "ap_mel_db": (_i, [_vp, _fp, _fp, _i, _i, _vp]),
+    "ap_mel_vjp": (_i, [_vp, _fp, _fp, _fp, _i, _i, _vp]),
     "ap_classifier_create": (_i, [_PP, C.POINTER(ClassifierCfg), _PP, _i, _i]),
     "ap_classifier_destroy": (None, [_vp]),
     "ap_classifier_forward": (_i, [_vp, _fp, _fp, _i, _i, _vp]),
+    "ap_classifier_vjp": (_i, [_vp, _fp, _fp, _fp, _i, _i, _vp]),
     "ap_classifier_set_mode": (_i, [_vp, _i]),
     "ap_classifier_get_mode": (_i, [_vp]),
     "ap_vote_counts": (_i, [_fp, _i, _i, _vp, _vp]),

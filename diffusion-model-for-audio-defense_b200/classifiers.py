@@ -23,8 +23,30 @@ def _np32(t) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(t, dtype=np.float32))
 
 
+class _ClassifierVJP(torch.autograd.Function):
+    """classifier forward with a backward pass through ``ap_classifier_vjp`` (ResNeXt)."""
+
+    @staticmethod
+    def forward(ctx, x, mod, B, in_len):
+        xd = x.detach().to(torch.float32).contiguous()
+        ctx.mod, ctx.B, ctx.in_len = mod, B, in_len
+        ctx.save_for_backward(xd)
+        return mod._run(xd, B, in_len)
+
+    @staticmethod
+    def backward(ctx, g):
+        (xd,) = ctx.saved_tensors
+        gx = torch.empty_like(xd)
+        gl = g.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(xd.device):
+            _lib.check(ctx.mod._lib.ap_classifier_vjp(ctx.mod._handle, xd.data_ptr(), gl.data_ptr(), gx.data_ptr(), ctx.B,
+                                                      ctx.in_len, _lib.stream_ptr()), "ap_classifier_vjp")
+        return gx, None, None, None
+
+
 class _Classifier(torch.nn.Module):
     kind = -1
+    differentiable = False      # ResNeXt has a backward pass (ap_classifier_vjp)
 
     def _create(self, cfg: "_lib.ClassifierCfg", weights, device):
         self._lib = _lib.load()
@@ -41,7 +63,9 @@ class _Classifier(torch.nn.Module):
         if not x.is_cuda:
             raise _lib.AudioPureError(f"{type(self).__name__}: input must be a CUDA tensor (there is no CPU path)")
         if x.requires_grad and torch.is_grad_enabled():
-            raise _lib.AudioPureError(f"{type(self).__name__}: inference-only (input requires grad)")
+            if not self.differentiable:
+                raise _lib.AudioPureError(f"{type(self).__name__}: inference-only (input requires grad)")
+            return _ClassifierVJP.apply(x, self, B, in_len)
         x = x.detach().to(torch.float32).contiguous()
         out = torch.empty(B, self.num_classes, device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
@@ -76,6 +100,8 @@ def _strip(sd: dict) -> dict:
 
 
 class ResNeXtClassifier(_Classifier):
+    differentiable = True
+
     def __init__(self, state_dict: dict, nlabels=10, cardinality=8, depth=29, base_width=64, widen_factor=4,
                  in_channels=1, device=None):
         super().__init__()

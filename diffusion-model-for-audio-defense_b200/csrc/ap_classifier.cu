@@ -73,6 +73,8 @@ struct ConvLayer {
   int Cin = 0, Cout = 0, kh = 1, kw = 1, stride = 1, pad = 0, groups = 1;
   int Cg = 0, Ng = 0, Ngp = 0, K = 0;
   DevBuf w, bias;
+  std::vector<float> wf_host;   // folded torch-layout weights [Cout][Cin/groups][kh][kw], kept when `keep_host` (backward pass)
+  bool keep_host = false;
   ConvTc tc;            // TF32 tensor-core twin (weights [Cout][K] K-major), built when the shape allows
   bool has_tc = false;
   // w_t: torch [Cout][Cin/groups][kh][kw]; optional BatchNorm(eval) folded: scale = gamma/sqrt(var+eps), shift = beta - mean*scale
@@ -100,6 +102,7 @@ struct ConvLayer {
     }
     AP_CUDA(w.upload(wp.data(), wp.size() * sizeof(float)));
     AP_CUDA(bias.upload(bp.data(), bp.size() * sizeof(float)));
+    if (keep_host) wf_host = wf;
     // structural part of conv_tc_supported (the spatial part is checked when the layer is bound to buffers)
     if (want_tc && Cg % 32 == 0 && (Ng == 64 || Ng == 128 || Ng % 256 == 0)) {
       int rc = tc.init(cin, cout, kh, kw, stride, pad, groups, wf.data(), bp.data());
@@ -126,6 +129,60 @@ struct ConvLayer {
     return AP_OK;
   }
 };
+
+// Data-gradient twin of a convolution: g_x = conv(g_y [zero-upsampled by the stride], W^T rotated 180 degrees), stride 1,
+// padding k - 1 - pad, same groups.  `L` must have kept its folded weights (keep_host).
+static int init_dgrad(ConvLayer& T, const ConvLayer& L) {
+  if (L.wf_host.empty()) return fail(AP_ERR_STATE, "init_dgrad: the forward layer did not keep its weights");
+  const int Cg = L.Cg, Ng = L.Ng, kh = L.kh, kw = L.kw;
+  std::vector<float> wt(static_cast<size_t>(L.Cin) * Ng * kh * kw);
+  for (int g = 0; g < L.groups; ++g)
+    for (int c = 0; c < Cg; ++c)
+      for (int n = 0; n < Ng; ++n)
+        for (int r = 0; r < kh; ++r)
+          for (int q = 0; q < kw; ++q)
+            wt[((static_cast<size_t>(g * Cg + c) * Ng + n) * kh + r) * kw + q] =
+                L.wf_host[((static_cast<size_t>(g * Ng + n) * Cg + c) * kh + (kh - 1 - r)) * kw + (kw - 1 - q)];
+  return T.init(L.Cout, L.Cin, kh, kw, 1, kh - 1 - L.pad, L.groups, wt.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// g[i] = act[i] > 0 ? g[i] : 0      (backward of ReLU, from the saved activation)
+__global__ void __launch_bounds__(256) relu_mask_kernel(float4* __restrict__ g, const float4* __restrict__ act, long long n4) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = g[i];
+    const float4 a = act[i];
+    v.x = a.x > 0.f ? v.x : 0.f, v.y = a.y > 0.f ? v.y : 0.f, v.z = a.z > 0.f ? v.z : 0.f, v.w = a.w > 0.f ? v.w : 0.f;
+    g[i] = v;
+  }
+}
+// up[b][2i][2j][c] = g[b][i][j][c], zero elsewhere   (NHWC; gradient of a stride-2 convolution before its dgrad)
+__global__ void __launch_bounds__(256) upsample2_kernel(const float4* __restrict__ g, float4* __restrict__ up, int B, int Ho, int Wo,
+                                                        int C4) {
+  const long long total = static_cast<long long>(B) * (2 * Ho) * (2 * Wo) * C4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4);
+    long long t = i / C4;
+    const int w = static_cast<int>(t % (2 * Wo));
+    t /= 2 * Wo;
+    const int hh = static_cast<int>(t % (2 * Ho));
+    const long long b = t / (2 * Ho);
+    up[i] = ((hh | w) & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : g[((b * Ho + (hh >> 1)) * Wo + (w >> 1)) * C4 + c];
+  }
+}
+// backward of avg_pool(P positions) + linear: g_y[b][p][c] = (sum_k fc_w[k][c] g_logits[b][k]) / P
+__global__ void __launch_bounds__(256) pool_fc_bwd_kernel(const float* __restrict__ g_logits, const float* __restrict__ fw, int Kc,
+                                                          int Cc, int P, float* __restrict__ g_y) {
+  const int b = blockIdx.x;
+  const float inv = 1.f / static_cast<float>(P);
+  for (int c = threadIdx.x; c < Cc; c += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < Kc; ++k) acc = fmaf(fw[k * Cc + c], g_logits[b * Kc + k], acc);
+    acc *= inv;
+    for (int pp = 0; pp < P; ++pp) g_y[(static_cast<long long>(b) * P + pp) * Cc + c] = acc;
+  }
+}
 
 // global average pool over P positions + linear: logits[b][k] = fc_b[k] + sum_c fc_w[k][c] * mean_p x[b][p][c]
 __global__ void __launch_bounds__(256) pool_fc_kernel(const float* __restrict__ x, int P, int Cc, const float* __restrict__ fw,
@@ -329,8 +386,9 @@ using namespace ap;
 
 struct Bottleneck {
   ConvLayer reduce, conv, expand, shortcut;
+  ConvLayer t_reduce, t_conv, t_expand, t_shortcut;   // data-gradient twins (built by the first ap_classifier_vjp call)
   bool has_shortcut = false;
-  int stride = 1, D = 0, cout = 0;
+  int stride = 1, D = 0, cout = 0, cin = 0;
 };
 
 struct ConvStep {   // one convolution of the ResNeXt forward bound to workspace buffers
@@ -368,6 +426,12 @@ struct ap_classifier_s {
   DevBuf buf[5];
   size_t buf_elems = 0;
   int chunk = 0;
+  // backward pass (ResNeXt): transposed stem, the tape of saved activations and five gradient buffers for `bwd_bn` images
+  ConvLayer t_stem;
+  bool bwd_ready = false;
+  int bwd_bn = 0;
+  DevBuf tape_x0, gbuf[5];
+  std::vector<std::unique_ptr<DevBuf>> tape;   // per block: r, c, y
 };
 
 static int ensure_ws(ap_classifier_t h, size_t elems) {
@@ -388,6 +452,7 @@ static int create_resnext(ap_classifier_t h, const float* const* w, int n_weight
     for (int b = 0; b < block_depth; ++b) expected += 15 + ((b == 0 && stages[s] != stages[s + 1]) ? 5 : 0);
   AP_REQUIRE(n_weights == expected, "ap_classifier_create: ResNeXt expects %d weight tensors, got %d", expected, n_weights);
   int i = 0;
+  h->stem.keep_host = true;
   int rc = h->stem.init(c.in_channels, 64, 3, 3, 1, 1, 1, w[0], nullptr, w[1], w[2], w[3], w[4]);
   if (rc != AP_OK) return rc;
   i = 5;
@@ -398,7 +463,8 @@ static int create_resnext(ap_classifier_t h, const float* const* w, int n_weight
       const int stride = (b == 0 && s > 0) ? 2 : 1;
       const double width_ratio = cout / (c.widen_factor * 64.0);
       const int D = c.cardinality * static_cast<int>(c.base_width * width_ratio);
-      blk->stride = stride, blk->D = D, blk->cout = cout;
+      blk->stride = stride, blk->D = D, blk->cout = cout, blk->cin = cin;
+      blk->reduce.keep_host = blk->conv.keep_host = blk->expand.keep_host = blk->shortcut.keep_host = true;
       rc = blk->reduce.init(cin, D, 1, 1, 1, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4], true);
       if (rc == AP_OK)
         rc = blk->conv.init(D, D, 3, 3, stride, 1, c.cardinality, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9], true);
@@ -494,6 +560,128 @@ static int forward_resnext(ap_classifier_t h, const float* spec, float* logits, 
     pool_fc_kernel<<<bn, 256, smem, st>>>(h->buf[last_out].as<float>(), 64, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(),
                                           h->cfg.num_classes, logits + static_cast<size_t>(b0) * h->cfg.num_classes, 0);
     AP_LAUNCH_CHECK();
+  }
+  return AP_OK;
+}
+
+// ---- backward of the ResNeXt forward: g_spec = (d logits / d spec)^T g_logits (autograd over resnext.py:56-64,134-142 with
+//      BatchNorm in eval mode).  The forward is recomputed on the fp32 FFMA path with every ReLU output kept (the tape);
+//      each convolution's data gradient is the forward convolution of the (zero-upsampled, for stride 2) output gradient with
+//      the transposed, 180-degree-rotated folded weights.
+static int vjp_resnext(ap_classifier_t h, const float* spec, const float* g_logits, float* g_spec, int B, cudaStream_t st) {
+  const int H0 = 32, W0 = 32, chunk = 32;
+  if (!h->bwd_ready) {
+    int rc = init_dgrad(h->t_stem, h->stem);
+    for (auto& b : h->blocks) {
+      if (rc == AP_OK) rc = init_dgrad(b->t_reduce, b->reduce);
+      if (rc == AP_OK) rc = init_dgrad(b->t_conv, b->conv);
+      if (rc == AP_OK) rc = init_dgrad(b->t_expand, b->expand);
+      if (rc == AP_OK && b->has_shortcut) rc = init_dgrad(b->t_shortcut, b->shortcut);
+    }
+    if (rc != AP_OK) return rc;
+    h->bwd_ready = true;
+  }
+  const int bn_max = std::min(B, chunk);
+  if (bn_max > h->bwd_bn) {   // (re)allocate the tape and the gradient buffers
+    size_t max_e = static_cast<size_t>(H0) * W0 * 64;
+    int H = H0, W = W0;
+    h->tape.clear();
+    AP_CUDA(h->tape_x0.alloc(static_cast<size_t>(bn_max) * H0 * W0 * 64 * sizeof(float)));
+    for (auto& b : h->blocks) {
+      const int Ho = (H - 1) / b->stride + 1, Wo = (W - 1) / b->stride + 1;
+      const size_t er = static_cast<size_t>(H) * W * b->D, ec = static_cast<size_t>(Ho) * Wo * b->D,
+                   ey = static_cast<size_t>(Ho) * Wo * b->cout, ex = static_cast<size_t>(H) * W * std::max(b->cin, b->cout);
+      max_e = std::max(std::max(max_e, er), std::max(std::max(ec, ey), ex));
+      for (size_t e : {er, ec, ey}) {
+        auto d = std::make_unique<DevBuf>();
+        AP_CUDA(d->alloc(e * bn_max * sizeof(float)));
+        h->tape.push_back(std::move(d));
+      }
+      H = Ho, W = Wo;
+    }
+    for (auto& g : h->gbuf) AP_CUDA(g.alloc(max_e * bn_max * sizeof(float)));
+    h->bwd_bn = bn_max;
+  }
+  auto grid_for = [](long long work) {
+    long long b = ceil_div_ll(work, 256);
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    return static_cast<unsigned>(b < cap ? (b > 0 ? b : 1) : cap);
+  };
+  auto mask = [&](float* g, const float* act, size_t elems) -> int {
+    relu_mask_kernel<<<grid_for(static_cast<long long>(elems / 4)), 256, 0, st>>>(reinterpret_cast<float4*>(g),
+                                                                                  reinterpret_cast<const float4*>(act),
+                                                                                  static_cast<long long>(elems / 4));
+    AP_LAUNCH_CHECK();
+    return AP_OK;
+  };
+  auto upsample = [&](const float* g, float* up, int bn, int Ho, int Wo, int Cc) -> int {
+    upsample2_kernel<<<grid_for(static_cast<long long>(bn) * 4 * Ho * Wo * (Cc / 4)), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(up), bn, Ho, Wo, Cc / 4);
+    AP_LAUNCH_CHECK();
+    return AP_OK;
+  };
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    // ---- forward with the tape
+    float* x0 = h->tape_x0.as<float>();
+    int rc = h->stem.run(spec + static_cast<size_t>(b0) * H0 * W0, bn, H0, W0, x0, nullptr, 1, st);
+    if (rc != AP_OK) return rc;
+    const float* x = x0;
+    int H = H0, W = W0;
+    for (size_t i = 0; i < h->blocks.size(); ++i) {
+      Bottleneck& b = *h->blocks[i];
+      float *r = h->tape[3 * i]->as<float>(), *c = h->tape[3 * i + 1]->as<float>(), *y = h->tape[3 * i + 2]->as<float>();
+      const int Ho = (H - 1) / b.stride + 1, Wo = (W - 1) / b.stride + 1;
+      rc = b.reduce.run(x, bn, H, W, r, nullptr, 1, st);
+      if (rc == AP_OK) rc = b.conv.run(r, bn, H, W, c, nullptr, 1, st);
+      const float* res = x;
+      if (rc == AP_OK && b.has_shortcut) {
+        rc = b.shortcut.run(x, bn, H, W, h->gbuf[4].as<float>(), nullptr, 0, st);
+        res = h->gbuf[4].as<float>();
+      }
+      if (rc == AP_OK) rc = b.expand.run(c, bn, Ho, Wo, y, res, 1, st);
+      if (rc != AP_OK) return rc;
+      x = y, H = Ho, W = Wo;
+    }
+    // ---- backward
+    float *GA = h->gbuf[0].as<float>(), *GB = h->gbuf[1].as<float>(), *GC = h->gbuf[2].as<float>(), *GD = h->gbuf[3].as<float>(),
+          *GE = h->gbuf[4].as<float>();
+    pool_fc_bwd_kernel<<<bn, 256, 0, st>>>(g_logits + static_cast<size_t>(b0) * h->cfg.num_classes, h->fc_w.as<float>(),
+                                           h->cfg.num_classes, h->feat, H * W, GA);
+    AP_LAUNCH_CHECK();
+    for (int i = static_cast<int>(h->blocks.size()) - 1; i >= 0; --i) {
+      Bottleneck& b = *h->blocks[i];
+      const float *r = h->tape[3 * i]->as<float>(), *c = h->tape[3 * i + 1]->as<float>(), *y = h->tape[3 * i + 2]->as<float>();
+      const int Ho = H, Wo = W, Hi = H * b.stride, Wi = W * b.stride;
+      const size_t npix_o = static_cast<size_t>(bn) * Ho * Wo, npix_i = static_cast<size_t>(bn) * Hi * Wi;
+      rc = mask(GA, y, npix_o * b.cout);                                          // through the block's final ReLU
+      if (rc == AP_OK) rc = b.t_expand.run(GA, bn, Ho, Wo, GB, nullptr, 0, st);   // -> d c
+      if (rc == AP_OK) rc = mask(GB, c, npix_o * b.D);
+      const float* src = GB;
+      if (rc == AP_OK && b.stride == 2) {
+        rc = upsample(GB, GC, bn, Ho, Wo, b.D);
+        src = GC;
+      }
+      if (rc == AP_OK) rc = b.t_conv.run(src, bn, Hi, Wi, GD, nullptr, 0, st);    // -> d r
+      if (rc == AP_OK) rc = mask(GD, r, npix_i * b.D);
+      const float* res = GA;                                                      // identity shortcut
+      if (rc == AP_OK && b.has_shortcut) {
+        const float* ssrc = GA;
+        if (b.stride == 2) {
+          rc = upsample(GA, GC, bn, Ho, Wo, b.cout);
+          ssrc = GC;
+        }
+        if (rc == AP_OK) rc = b.t_shortcut.run(ssrc, bn, Hi, Wi, GE, nullptr, 0, st);
+        res = GE;
+      }
+      if (rc == AP_OK) rc = b.t_reduce.run(GD, bn, Hi, Wi, GB, res, 0, st);       // d x = reduce^T(d r) + shortcut path
+      if (rc != AP_OK) return rc;
+      std::swap(GA, GB);
+      H = Hi, W = Wi;
+    }
+    rc = mask(GA, x0, static_cast<size_t>(bn) * H0 * W0 * 64);
+    if (rc == AP_OK) rc = h->t_stem.run(GA, bn, H0, W0, g_spec + static_cast<size_t>(b0) * H0 * W0, nullptr, 0, st);
+    if (rc != AP_OK) return rc;
   }
   return AP_OK;
 }
@@ -758,6 +946,17 @@ extern "C" int ap_classifier_forward(ap_classifier_t h, const float* input, floa
     case AP_CLS_RESNET: return forward_resnet(h, input, logits, B, 32, in_len, st);
     default: return forward_kws(h, input, logits, B, in_len, st);
   }
+}
+
+// g_input = (d logits / d input)^T g_logits.  ResNeXt only (the SC09 default victim, adaptive_attack_eval.py:21).
+extern "C" int ap_classifier_vjp(ap_classifier_t h, const float* input, const float* g_logits, float* g_input, int B, int in_len,
+                                 void* stream) {
+  AP_REQUIRE(h && input && g_logits && g_input, "ap_classifier_vjp: null argument");
+  AP_REQUIRE(B > 0, "ap_classifier_vjp: B must be positive");
+  if (h->cfg.kind != AP_CLS_RESNEXT) return fail(AP_ERR_STATE, "ap_classifier_vjp: the backward pass exists for ResNeXt only");
+  AP_REQUIRE(in_len == 32, "ap_classifier_vjp: ResNeXt input is (B, 1, 32, 32)");
+  AP_CUDA(cudaSetDevice(h->device));
+  return vjp_resnext(h, input, g_logits, g_input, B, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ap_classifier_set_mode(ap_classifier_t h, int mode) {

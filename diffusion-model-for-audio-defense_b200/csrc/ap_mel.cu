@@ -67,6 +67,88 @@ __global__ void __launch_bounds__(256) mel_db_kernel(const float* __restrict__ p
   }
 }
 
+// ---- backward (VJP wrt the waveform)
+// forward epilogue that keeps the spectrum: reim[m][col] in the basis' column order (tile t = [re 64t.. | im 64t..])
+struct ReImEpi {
+  float* reim;
+  int ld;   // = ncols
+  __device__ __forceinline__ void store(int, int m, int n0, int tx, const float (&lo)[4], const float (&hi)[4], int) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      reim[static_cast<long long>(m) * ld + n0 + tx * 4 + j] = lo[j];
+      reim[static_cast<long long>(m) * ld + n0 + 64 + tx * 4 + j] = hi[j];
+    }
+  }
+};
+// one warp per (b, f) row: mel power from the kept spectrum, g_mel = g_spec * (10 / ln 10) / melpow (0 where the clamp at
+// 1e-10 is active), g_P[k] = sum_mel g_mel fb[k][mel], and in place reim <- 2 * (re, im) * g_P = d loss / d (re, im)
+__global__ void __launch_bounds__(256) mel_bwd_kernel(float* __restrict__ reim, int ld, int n_freq, const float* __restrict__ fb,
+                                                      int n_mels, int frames, long long rows, const float* __restrict__ g_spec) {
+  extern __shared__ float sm[];   // per warp: n_mels gradients
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* gm = sm + wib * n_mels;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long m = warp; m < rows; m += nwarps) {
+    float* pr = reim + m * ld;
+    const long long b = m / frames;
+    const int f = static_cast<int>(m - b * frames);
+    for (int mel = lane; mel < n_mels; mel += 32) {
+      float acc = 0.f;
+      for (int k = 0; k < n_freq; ++k) {
+        const int col = (k >> 6) * 128 + (k & 63);
+        const float re = pr[col], im = pr[col + 64];
+        acc = fmaf(fmaf(re, re, im * im), fb[k * n_mels + mel], acc);
+      }
+      gm[mel] = acc > 1e-10f ? g_spec[(b * n_mels + mel) * frames + f] * (4.342944819032518f / acc) : 0.f;
+    }
+    __syncwarp();
+    for (int k = lane; k < n_freq; k += 32) {
+      float gp = 0.f;
+      for (int mel = 0; mel < n_mels; ++mel) gp = fmaf(gm[mel], fb[k * n_mels + mel], gp);
+      const int col = (k >> 6) * 128 + (k & 63);
+      pr[col] *= 2.f * gp;
+      pr[col + 64] *= 2.f * gp;
+    }
+    __syncwarp();
+  }
+}
+// A operand of the second GEMM: plain row-major rows (the padded columns of `reim` beyond n_freq hold zeros: basis columns
+// there are zero, so the forward wrote zeros)
+struct RowLoader {
+  const float* a;
+  int ld;
+  __device__ __forceinline__ float4 load4(int, int m, int k, int M, int K) const {
+    if (m >= M || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return *reinterpret_cast<const float4*>(a + static_cast<long long>(m) * ld + k);
+  }
+};
+// g_frames[m][n] -> overlap-add into g_wav at i = f*hop + n - pad (reflect padding folds the mirrored samples back)
+struct OverlapAddEpi {
+  float* g_wav;
+  int L, frames, hop, pad, reflect, n_fft;
+  __device__ __forceinline__ void put(int m, int n, float v) const {
+    if (n >= n_fft) return;
+    const int b = m / frames, f = m - b * frames;
+    int i = f * hop + n - pad;
+    if (i < 0) {
+      if (!reflect) return;
+      i = -i;
+    } else if (i >= L) {
+      if (!reflect) return;
+      i = 2 * (L - 1) - i;
+    }
+    if (i >= 0 && i < L) atomicAdd(g_wav + static_cast<long long>(b) * L + i, v);
+  }
+  __device__ __forceinline__ void store(int, int m, int n0, int tx, const float (&lo)[4], const float (&hi)[4], int) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      put(m, n0 + tx * 4 + j, lo[j]);
+      put(m, n0 + 64 + tx * 4 + j, hi[j]);
+    }
+  }
+};
+
 }  // namespace ap
 
 using namespace ap;
@@ -77,6 +159,11 @@ struct ap_mel_s {
   int n_freq = 0, ncols = 0, ld_power = 0;
   DevBuf basis, fb, power;
   long long power_rows = 0;
+  // backward pass: transposed basis [ncols][n_fft padded to 128] and the kept spectrum
+  std::vector<float> basis_host;
+  DevBuf basis_t, reim;
+  int ld_t = 0;
+  long long reim_rows = 0;
 };
 
 static double hz_to_mel(double f, bool slaney) {
@@ -134,6 +221,7 @@ extern "C" int ap_mel_create(ap_mel_t* out, const ap_mel_cfg* cfg, int device) {
       fb[static_cast<size_t>(k) * cfg->n_mels + m] = static_cast<float>(v);
     }
   }
+  h->basis_host = basis;
   cudaError_t e = h->basis.upload(basis.data(), basis.size() * sizeof(float));
   if (e == cudaSuccess) e = h->fb.upload(fb.data(), fb.size() * sizeof(float));
   if (e != cudaSuccess) {
@@ -174,5 +262,45 @@ extern "C" int ap_mel_db(ap_mel_t h, const float* wav, float* spec, int B, int L
   mel_db_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(h->power.as<float>(), h->ld_power, h->n_freq,
                                                                h->fb.as<float>(), h->cfg.n_mels, frames, rows, spec);
   AP_LAUNCH_CHECK();
+  return AP_OK;
+}
+
+// g_wav = (d spec / d wav)^T g_spec: backward of power spectrogram -> mel -> 10 log10 (what autograd computes through
+// torchaudio's MelSpectrogram + AmplitudeToDB).  wav, g_wav: device (B, L); g_spec: device (B, n_mels, frames).
+extern "C" int ap_mel_vjp(ap_mel_t h, const float* wav, const float* g_spec, float* g_wav, int B, int L, void* stream) {
+  AP_REQUIRE(h && wav && g_spec && g_wav, "ap_mel_vjp: null argument");
+  AP_REQUIRE(B > 0 && L > 0, "ap_mel_vjp: B and L must be positive (got %d, %d)", B, L);
+  AP_REQUIRE(!h->cfg.reflect_pad || L > h->cfg.n_fft / 2, "ap_mel_vjp: reflect padding needs L > n_fft/2");
+  AP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = h->cfg.n_fft, frames = 1 + L / h->cfg.hop_length;
+  const long long rows = static_cast<long long>(B) * frames;
+  AP_REQUIRE(rows < (1ll << 30), "ap_mel_vjp: batch too large");
+  if (!h->basis_t.p) {   // [ncols][ld_t]: basis transposed, N contiguous and padded to a multiple of 128 columns
+    h->ld_t = ((N + 127) / 128) * 128;
+    std::vector<float> bt(static_cast<size_t>(h->ncols) * h->ld_t, 0.f);
+    for (int n = 0; n < N; ++n)
+      for (int c = 0; c < h->ncols; ++c) bt[static_cast<size_t>(c) * h->ld_t + n] = h->basis_host[static_cast<size_t>(n) * h->ncols + c];
+    AP_CUDA(h->basis_t.upload(bt.data(), bt.size() * sizeof(float)));
+  }
+  if (rows > h->reim_rows) {
+    AP_CUDA(h->reim.alloc(static_cast<size_t>(rows) * h->ncols * sizeof(float)));
+    h->reim_rows = rows;
+  }
+  FrameLoader al{wav, L, frames, h->cfg.hop_length, N / 2, h->cfg.reflect_pad};
+  ReImEpi ep{h->reim.as<float>(), h->ncols};
+  AP_CUDA(sgemm::launch(al, h->basis.as<float>(), h->ncols, 0, 1, static_cast<int>(rows), h->ncols, N, ep, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  long long blocks = ceil_div_ll(rows * 32, 256);
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  mel_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 8 * h->cfg.n_mels * sizeof(float), st>>>(
+      h->reim.as<float>(), h->ncols, h->n_freq, h->fb.as<float>(), h->cfg.n_mels, frames, rows, g_spec);
+  AP_LAUNCH_CHECK();
+  AP_CUDA(cudaMemsetAsync(g_wav, 0, static_cast<size_t>(B) * L * sizeof(float), st));
+  RowLoader gl{h->reim.as<float>(), h->ncols};
+  OverlapAddEpi oe{g_wav, L, frames, h->cfg.hop_length, N / 2, h->cfg.reflect_pad, N};
+  AP_CUDA(sgemm::launch(gl, h->basis_t.as<float>(), h->ld_t, 0, 1, static_cast<int>(rows), h->ld_t, h->ncols, oe, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return AP_OK;
 }

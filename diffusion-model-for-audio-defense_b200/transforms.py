@@ -12,6 +12,22 @@ from . import _lib
 __all__ = ["MelSpectrogramDB", "sc09_transform", "kws_transform"]
 
 
+class _MelVJP(torch.autograd.Function):
+    """log-mel with a backward pass through ``ap_mel_vjp`` (torchaudio's transform is an autograd module in the reference)."""
+
+    @staticmethod
+    def forward(ctx, wav, mod):
+        x = wav.detach().to(torch.float32).contiguous()
+        ctx.mod = mod
+        ctx.save_for_backward(x)
+        return mod._db(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ctx.mod.vjp(x, g).reshape(x.shape), None
+
+
 class MelSpectrogramDB(torch.nn.Module):
     def __init__(self, sample_rate=16000, n_fft=400, hop_length=None, n_mels=128, norm=None, pad_mode="reflect",
                  mel_scale="htk", device=None):
@@ -32,7 +48,11 @@ class MelSpectrogramDB(torch.nn.Module):
     def forward(self, wav: torch.Tensor) -> torch.Tensor:
         if not wav.is_cuda:
             raise _lib.AudioPureError("MelSpectrogramDB: input must be a CUDA tensor (there is no CPU path)")
-        x = wav.detach().to(torch.float32).contiguous()
+        if wav.requires_grad and torch.is_grad_enabled():
+            return _MelVJP.apply(wav, self)
+        return self._db(wav.detach().to(torch.float32).contiguous())
+
+    def _db(self, x: torch.Tensor) -> torch.Tensor:
         lead = x.shape[:-1]
         L = x.shape[-1]
         B = int(x.numel() // L)
@@ -40,6 +60,18 @@ class MelSpectrogramDB(torch.nn.Module):
         out = torch.empty(*lead, self.n_mels, frames, device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
             _lib.check(self._lib.ap_mel_db(self._handle, x.data_ptr(), out.data_ptr(), B, L, _lib.stream_ptr()), "ap_mel_db")
+        return out
+
+    def vjp(self, wav: torch.Tensor, g_spec: torch.Tensor) -> torch.Tensor:
+        """g_wav = (d spec / d wav)^T g_spec."""
+        x = wav.detach().to(torch.float32).contiguous()
+        g = g_spec.detach().to(torch.float32).contiguous()
+        L = x.shape[-1]
+        B = int(x.numel() // L)
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(self._lib.ap_mel_vjp(self._handle, x.data_ptr(), g.data_ptr(), out.data_ptr(), B, L, _lib.stream_ptr()),
+                       "ap_mel_vjp")
         return out
 
     def cuda(self, device=None):   # the drivers call .cuda() on transforms (acoustic_system.py:39-40)

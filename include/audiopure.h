@@ -156,6 +156,10 @@ void ap_mel_destroy(ap_mel_t h);
 int ap_mel_frames(ap_mel_t h, int L); /* 1 + L / hop */
 /* wav: device (B, L); spec: device (B, n_mels, frames) */
 int ap_mel_db(ap_mel_t h, const float* wav, float* spec, int B, int L, void* stream);
+/* Vector-Jacobian product wrt the waveform: g_wav = (d spec / d wav)^T g_spec, the backward of torchaudio's
+ * MelSpectrogram + AmplitudeToDB (power 2, 10 log10 with the 1e-10 clamp) as autograd computes it.  wav, g_wav: device
+ * (B, L); g_spec: device (B, n_mels, frames). */
+int ap_mel_vjp(ap_mel_t h, const float* wav, const float* g_spec, float* g_wav, int B, int L, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Classifiers (replace Classifier(spec) at acoustic_system.py:49 / certified_robust.py:30)
@@ -181,6 +185,12 @@ int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cfg* cfg, con
 void ap_classifier_destroy(ap_classifier_t h);
 /* input: device (B, 1, 32, 32) spectrogram (ResNeXt, ResNet; in_len = 32), (B, L) waveform (M5; in_len = L) or (B, 32, W) (KWS; in_len = W) */
 int ap_classifier_forward(ap_classifier_t h, const float* input, float* logits, int B, int in_len, void* stream);
+/* Vector-Jacobian product wrt the input: g_input = (d logits / d input)^T g_logits, what autograd computes through
+ * CifarResNeXt.forward (models/resnext.py:134-142, BatchNorm in eval mode) when an attack back-propagates the loss
+ * (robustness_eval/white_box_attack.py:438).  ResNeXt only; fp32 (the forward is recomputed with every ReLU output kept,
+ * 32 images at a time).  input, g_input: device (B, 1, 32, 32); g_logits: device (B, num_classes). */
+int ap_classifier_vjp(ap_classifier_t h, const float* input, const float* g_logits, float* g_input, int B, int in_len,
+                      void* stream);
 /* AP_MODE_TF32 (default for ResNeXt: tensor-core convolutions) or AP_MODE_FP32 (every convolution on the FFMA path) */
 int ap_classifier_set_mode(ap_classifier_t h, int mode);
 int ap_classifier_get_mode(ap_classifier_t h);

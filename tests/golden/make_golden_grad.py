@@ -60,6 +60,49 @@ def main():
     (gx,) = torch.autograd.grad((y * w).sum(), xr)
     out["ddpm_t2_purified"] = y.detach().numpy()
     out["ddpm_t2_grad_L1024"] = gx.numpy()
+    # ---- mel front ends (torchaudio autograd): g_wav for a seeded g_spec
+    import torchaudio
+    xm = torch.from_numpy(synthetic.synthetic_waveforms(2, 16000, seed=99))
+    mel_sc = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=2048, hop_length=512, n_mels=32,
+                                                  norm="slaney", pad_mode="constant", mel_scale="slaney")
+    mel_kws = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_mels=32)
+    todb = torchaudio.transforms.AmplitudeToDB(stype="power")
+    for name, mel in (("sc09", mel_sc), ("kws", mel_kws)):
+        xr = xm.clone().requires_grad_(True)
+        spec = todb(mel(xr))
+        g = torch.from_numpy(synthetic.host_noise(tuple(spec.shape), 4250, 0))
+        (gx,) = torch.autograd.grad(spec, xr, g)
+        out[f"mel_{name}_g_spec"] = g.numpy()
+        out[f"mel_{name}_grad"] = gx.numpy()
+
+    # ---- ResNeXt-29 8x64 (eval mode): g_spec for a seeded g_logits, on the reference's own mel features
+    from models.resnext import CifarResNeXt
+    rx = CifarResNeXt(nlabels=10, in_channels=1).eval()
+    rx.load_state_dict(to_torch_sd(synthetic.resnext_state_dict(seed=0)))
+    for p in rx.parameters():
+        p.requires_grad_(False)
+    with torch.no_grad():
+        spec0 = todb(mel_sc(xm))
+    sr = spec0.clone().requires_grad_(True)
+    gl = torch.from_numpy(synthetic.host_noise((2, 10), 4251, 0))
+    (gs,) = torch.autograd.grad(rx(sr), sr, gl)
+    out["resnext_in_spec"] = spec0.numpy()
+    out["resnext_g_logits"] = gl.numpy()
+    out["resnext_grad"] = gs.numpy()
+
+    # ---- end to end: d CrossEntropy(AcousticSystem(x), y) / d x through DDPM t*=2 -> mel -> ResNeXt, one 1 s clip
+    from acoustic_system import AcousticSystem
+    transform = lambda w: todb(mel_sc(w))
+    dw.reverse_timestep = 2
+    system = AcousticSystem(classifier=rx, transform=transform, defender=dw, defense_type="wave")
+    x1 = torch.from_numpy(synthetic.synthetic_waveforms(1, 16000, seed=1234)).requires_grad_(True)
+    with NoiseInjector(2027) as inj:
+        logits = system(x1)
+    loss = torch.nn.functional.cross_entropy(logits, torch.tensor([3]))
+    (gx,) = torch.autograd.grad(loss, x1)
+    out["system_logits"] = logits.detach().numpy()
+    out["system_loss_grad"] = gx.numpy()
+
     np.savez_compressed(os.path.join(HERE, "reference_golden_grad.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, float(np.abs(v).max()))

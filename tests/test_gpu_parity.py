@@ -651,3 +651,47 @@ def test_cuda_graph_capture_and_replay(ap, sd_full, B):
         dw._offset = 0
         system(x)
     print(f"B={B}: eager {timeit(eager):.2f} ms, graph replay {timeit(g.replay):.2f} ms per query batch")
+
+
+# ---------------------------------------------------------------------------------------------------- end-to-end gradients
+@pytest.mark.parametrize("name", ["sc09", "kws"])
+def test_mel_vjp_vs_torchaudio_autograd(ap, golden_grad, name):
+    tr = ap.sc09_transform() if name == "sc09" else ap.kws_transform()
+    x = cuda(synthetic.synthetic_waveforms(2, 16000, seed=99)).requires_grad_(True)
+    spec = tr(x)
+    assert spec.requires_grad
+    (gx,) = torch.autograd.grad(spec, x, cuda(golden_grad[f"mel_{name}_g_spec"]))
+    err = rel_l2(gx, golden_grad[f"mel_{name}_grad"])
+    print(f"mel {name} gradient: rel-L2 {err:.3e}")
+    assert err < 1e-4
+
+
+def test_resnext_vjp_vs_reference_autograd(ap, golden_grad):
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    spec = cuda(golden_grad["resnext_in_spec"]).requires_grad_(True)
+    logits = rx(spec)
+    (gs,) = torch.autograd.grad(logits, spec, cuda(golden_grad["resnext_g_logits"]))
+    err = rel_l2(gs, golden_grad["resnext_grad"])
+    print(f"ResNeXt gradient: rel-L2 {err:.3e}")
+    assert err < 1e-3
+    m5 = ap.M5Classifier(synthetic.m5_state_dict(seed=0))
+    with pytest.raises(ap.AudioPureError):      # no backward pass for M5 / KWS / ResNet: refuse rather than drop the gradient
+        m5(cuda(synthetic.synthetic_waveforms(1, 16000, seed=1)).requires_grad_(True))
+
+
+def test_acoustic_system_loss_gradient_vs_reference_autograd(ap, golden_grad, sd_full):
+    """d CrossEntropy(AcousticSystem(x), y) / d x through DDPM t* = 2 -> log-mel -> ResNeXt: the white-box attack gradient
+    (robustness_eval/white_box_attack.py:430-438), every stage on the CUDA backward kernels."""
+    dw = ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=2, state_dict=sd_full, noise="torch", mode="bf16x3")
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    system = ap.AcousticSystem(classifier=rx, transform=ap.sc09_transform(), defender=dw, defense_type="wave")
+    x = cuda(synthetic.synthetic_waveforms(1, 16000, seed=1234)).requires_grad_(True)
+    with TorchNormalInjector(2027) as inj:
+        logits = system(x)
+        assert inj.i == 2
+    assert np.abs(logits.detach().cpu().numpy() - golden_grad["system_logits"]).max() < 5e-3
+    loss = torch.nn.functional.cross_entropy(logits, torch.tensor([3], device="cuda"))
+    (gx,) = torch.autograd.grad(loss, x)
+    err = rel_l2(gx, golden_grad["system_loss_grad"])
+    print(f"AcousticSystem loss gradient (bf16x3 purifier, tf32 classifier forward / fp32 backward): rel-L2 {err:.3e}")
+    assert err < 2e-2

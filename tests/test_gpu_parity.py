@@ -695,3 +695,27 @@ def test_acoustic_system_loss_gradient_vs_reference_autograd(ap, golden_grad, sd
     err = rel_l2(gx, golden_grad["system_loss_grad"])
     print(f"AcousticSystem loss gradient (bf16x3 purifier, tf32 classifier forward / fp32 backward): rel-L2 {err:.3e}")
     assert err < 2e-2
+
+
+def test_pgd_steps_through_the_defended_system_raise_the_loss(ap, sd_full):
+    """The reference's white-box attack loop (robustness_eval/white_box_attack.py:430-447: loss.backward(), delta += lr * sign(grad),
+    clamp to eps) run against the defended system on the CUDA path: fixed Philox noise (seed reset every step, as an attacker with
+    a fixed defender draw), L_inf eps = 0.002, 4 steps -- the loss on the true label must go up."""
+    dw = ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=1, state_dict=sd_full, noise="philox", seed=11, mode="bf16")
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    system = ap.AcousticSystem(classifier=rx, transform=ap.sc09_transform(), defender=dw, defense_type="wave")
+    x = cuda(synthetic.synthetic_waveforms(2, 16000, seed=321))
+    with torch.no_grad():
+        dw._offset = 0
+        y = system(x).argmax(1)
+    delta = torch.zeros_like(x, requires_grad=True)
+    eps, lr, losses = 2e-3, 5e-4, []
+    for _ in range(5):
+        dw._offset = 0
+        loss = torch.nn.functional.cross_entropy(system(x + delta), y)
+        losses.append(float(loss))
+        (grad,) = torch.autograd.grad(loss, delta)
+        assert torch.isfinite(grad).all() and float(grad.abs().max()) > 0
+        delta.data = (delta.data + lr * grad.sign()).clamp_(-eps, eps)
+    print("PGD losses:", [f"{v:.4f}" for v in losses])
+    assert losses[-1] > losses[0]

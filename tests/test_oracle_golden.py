@@ -204,3 +204,16 @@ def test_oracle_autograd_matches_reference_gradients(golden_grad, sd_full, hp):
     assert rel_l2(y.detach().numpy(), golden_grad["ddpm_t2_purified"]) < 1e-5
     (gx,) = torch.autograd.grad((y * torch.from_numpy(golden_grad["ddpm_grad_w"])).sum(), xr)
     assert rel_l2(gx.numpy(), golden_grad["ddpm_t2_grad_L1024"]) < 2e-5
+
+
+def test_oracle_mel_and_resnext_gradients_match_reference(golden_grad):
+    """torchaudio / CifarResNeXt autograd gradients (golden) vs autograd over the oracle's restatements."""
+    xm = torch.from_numpy(synthetic.synthetic_waveforms(2, 16000, seed=99))
+    for name, kw in (("sc09", orc.MEL_SC09), ("kws", orc.MEL_KWS)):
+        xr = xm.clone().requires_grad_(True)
+        (gx,) = torch.autograd.grad(orc.mel_db(xr, **kw), xr, torch.from_numpy(golden_grad[f"mel_{name}_g_spec"]))
+        assert rel_l2(gx.numpy(), golden_grad[f"mel_{name}_grad"]) < 1e-4, name
+    sr = torch.from_numpy(golden_grad["resnext_in_spec"]).requires_grad_(True)
+    logits = orc.resnext_forward(synthetic.resnext_state_dict(seed=0), sr)
+    (gs,) = torch.autograd.grad(logits, sr, torch.from_numpy(golden_grad["resnext_g_logits"]))
+    assert rel_l2(gs.numpy(), golden_grad["resnext_grad"]) < 1e-4

@@ -153,6 +153,7 @@ class ResNetClassifier(_Classifier):
 
 
 class M5Classifier(_Classifier):
+    differentiable = True
     def __init__(self, state_dict: dict, n_input=1, first_kernel_size=160, n_output=10, stride=16, n_channel=32,
                  device=None):
         super().__init__()

@@ -22,10 +22,10 @@ namespace ap {
 // in: NHWC [B][H][W][Ctot]; group z uses channels [z*Cg, (z+1)*Cg); k = (r*kw + s)*Cg + c
 template <bool VEC> struct Conv2dLoader {
   const float* in;
-  int H, W, Ctot, Cg, kh, kw, stride, pad, Ho, Wo;
+  int H, W, Ctot, Cg, kh, kw, stride, pad, pad_h, Ho, Wo;   // pad: width padding; pad_h: height padding (0 for 1 x k kernels)
   __device__ __forceinline__ float one(int z, int b, int oh, int ow, int k) const {
     const int rs = k / Cg, c = k - rs * Cg, r = rs / kw, s = rs - r * kw;
-    const int ih = oh * stride + r - pad, iw = ow * stride + s - pad;
+    const int ih = oh * stride + r - pad_h, iw = ow * stride + s - pad;
     if (ih < 0 || ih >= H || iw < 0 || iw >= W) return 0.f;
     return in[((static_cast<long long>(b) * H + ih) * W + iw) * Ctot + z * Cg + c];
   }
@@ -34,7 +34,7 @@ template <bool VEC> struct Conv2dLoader {
     const int b = m / (Ho * Wo), rem = m - b * (Ho * Wo), oh = rem / Wo, ow = rem - oh * Wo;
     if (VEC) {
       const int rs = k / Cg, c = k - rs * Cg, r = rs / kw, s = rs - r * kw;
-      const int ih = oh * stride + r - pad, iw = ow * stride + s - pad;
+      const int ih = oh * stride + r - pad_h, iw = ow * stride + s - pad;
       if (ih < 0 || ih >= H || iw < 0 || iw >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
       return *reinterpret_cast<const float4*>(in + ((static_cast<long long>(b) * H + ih) * W + iw) * Ctot + z * Cg + c);
     }
@@ -112,16 +112,17 @@ struct ConvLayer {
     return AP_OK;
   }
   int run(const float* in, int B, int H, int W, float* out, const float* residual, int relu, cudaStream_t st) const {
-    const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    const int pad_h = kh == 1 ? 0 : pad;   // 1 x k kernels (conv1d as a height-1 image) pad the width only
+    const int Ho = (H + 2 * pad_h - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
     const long long M = static_cast<long long>(B) * Ho * Wo;
     if (M >= (1ll << 31)) return fail(AP_ERR_INVALID, "conv: too many output pixels");
     ConvEpi ep{out, bias.as<float>(), residual, Cout, Ng, relu};
     cudaError_t e;
     if (Cg % 4 == 0) {
-      Conv2dLoader<true> al{in, H, W, Cin, Cg, kh, kw, stride, pad, Ho, Wo};
+      Conv2dLoader<true> al{in, H, W, Cin, Cg, kh, kw, stride, pad, pad_h, Ho, Wo};
       e = sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
     } else {
-      Conv2dLoader<false> al{in, H, W, Cin, Cg, kh, kw, stride, pad, Ho, Wo};
+      Conv2dLoader<false> al{in, H, W, Cin, Cg, kh, kw, stride, pad, pad_h, Ho, Wo};
       e = sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
     }
     if (e != cudaSuccess) return fail(AP_ERR_CUDA, "conv launch: %s", cudaGetErrorString(e));
@@ -143,7 +144,7 @@ static int init_dgrad(ConvLayer& T, const ConvLayer& L) {
           for (int q = 0; q < kw; ++q)
             wt[((static_cast<size_t>(g * Cg + c) * Ng + n) * kh + r) * kw + q] =
                 L.wf_host[((static_cast<size_t>(g * Ng + n) * Cg + c) * kh + (kh - 1 - r)) * kw + (kw - 1 - q)];
-  return T.init(L.Cout, L.Cin, kh, kw, 1, kh - 1 - L.pad, L.groups, wt.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+  return T.init(L.Cout, L.Cin, kh, kw, 1, kw - 1 - L.pad, L.groups, wt.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 // g[i] = act[i] > 0 ? g[i] : 0      (backward of ReLU, from the saved activation)
@@ -181,6 +182,65 @@ __global__ void __launch_bounds__(256) pool_fc_bwd_kernel(const float* __restric
     for (int k = 0; k < Kc; ++k) acc = fmaf(fw[k * Cc + c], g_logits[b * Kc + k], acc);
     acc *= inv;
     for (int pp = 0; pp < P; ++pp) g_y[(static_cast<long long>(b) * P + pp) * Cc + c] = acc;
+  }
+}
+
+// 1-D zero-upsampling: up[b][i*s][c] = g[b][i][c] (i < lo), zero elsewhere; lu >= (lo-1)*s + 1   (stride-s conv1d dgrad input)
+__global__ void __launch_bounds__(256) upsample1d_kernel(const float* __restrict__ g, float* __restrict__ up, int B, int lo, int lu,
+                                                         int s, int Cc) {
+  const long long total = static_cast<long long>(B) * lu * Cc;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cc);
+    const long long t = i / Cc;
+    const int l = static_cast<int>(t % lu);
+    const long long b = t / lu;
+    const int q = l / s;
+    up[i] = (l - q * s == 0 && q < lo) ? g[(b * lo + q) * Cc + c] : 0.f;
+  }
+}
+// backward of max_pool1d(4, 4) after ReLU: the gradient goes to the first maximum of each window if it is positive
+__global__ void __launch_bounds__(256) maxpool4_relu_bwd_kernel(const float* __restrict__ g_p, const float* __restrict__ a,
+                                                                float* __restrict__ g_a, int B, int lo, int Cc) {
+  const int lp = lo / 4;
+  const long long total = static_cast<long long>(B) * lo * Cc;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cc);
+    const long long t = i / Cc;
+    const int l = static_cast<int>(t % lo);
+    const long long b = t / lo;
+    const int w = l / 4, j = l - 4 * w;
+    float out = 0.f;
+    if (w < lp) {
+      const float* p = a + ((b * lo + 4 * w) * Cc) + c;
+      int arg = 0;
+      float m = p[0];
+      for (int q = 1; q < 4; ++q)
+        if (p[q * Cc] > m) m = p[q * Cc], arg = q;
+      if (arg == j && m > 0.f) out = g_p[(b * lp + w) * Cc + c];
+    }
+    g_a[i] = out;
+  }
+}
+// backward of avg-pool(P) + linear + log_softmax: g_z = g_out - softmax * sum(g_out); g_x[b][p][c] = (fc_w^T g_z)[c] / P
+__global__ void __launch_bounds__(256) logsoftmax_pool_fc_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ logp,
+                                                                     const float* __restrict__ fw, int Kc, int Cc, int P,
+                                                                     float* __restrict__ g_x) {
+  __shared__ float gz[64];
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int k = 0; k < Kc; ++k) sum += g_out[b * Kc + k];
+    for (int k = 0; k < Kc; ++k) gz[k] = g_out[b * Kc + k] - expf(logp[b * Kc + k]) * sum;
+  }
+  __syncthreads();
+  const float inv = 1.f / static_cast<float>(P);
+  for (int c = threadIdx.x; c < Cc; c += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < Kc; ++k) acc = fmaf(fw[k * Cc + c], gz[k], acc);
+    acc *= inv;
+    for (int pp = 0; pp < P; ++pp) g_x[(static_cast<long long>(b) * P + pp) * Cc + c] = acc;
   }
 }
 
@@ -418,7 +478,7 @@ struct ap_classifier_s {
   };
   std::vector<std::unique_ptr<ResBlock>> resblocks;
   // M5
-  ConvLayer m5conv[4];
+  ConvLayer m5conv[4], m5conv_t[4];   // forward layers and their data-gradient twins
   // KWS
   std::vector<std::unique_ptr<DevBuf>> kws_bufs;
   KwsWeights kws{};
@@ -808,6 +868,7 @@ static int create_m5(ap_classifier_t h, const float* const* w, int n_weights) {
   const int cin[4] = {1, n, n, 2 * n}, cout[4] = {n, n, 2 * n, 2 * n}, ks[4] = {c.m5_first_kernel, 3, 3, 3};
   for (int i = 0; i < 4; ++i) {
     const float* const* p = w + 6 * i;
+    h->m5conv[i].keep_host = true;
     int rc = h->m5conv[i].init(cin[i], cout[i], 1, ks[i], i == 0 ? c.m5_stride : 1, 0, 1, p[0], p[1], p[2], p[3], p[4], p[5]);
     if (rc != AP_OK) return rc;
   }
@@ -849,6 +910,91 @@ static int forward_m5(ap_classifier_t h, const float* wav, float* out, int B, in
     pool_fc_kernel<<<bn, 256, smem, st>>>(in, len, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(), h->cfg.num_classes,
                                           out + static_cast<size_t>(b0) * h->cfg.num_classes, 1);   // M5Net.py:35-38
     AP_LAUNCH_CHECK();
+  }
+  return AP_OK;
+}
+
+// ---- backward of the M5 forward (autograd over M5Net.py:21-38, BatchNorm in eval mode): g_wav = (d logp / d wav)^T g_logp
+static int vjp_m5(ap_classifier_t h, const float* wav, const float* g_out, float* g_wav, int B, int L, cudaStream_t st) {
+  const int chunk = 64, n = h->cfg.m5_channels, K = h->cfg.num_classes;
+  AP_REQUIRE(K <= 64, "M5 backward: at most 64 classes");
+  if (!h->bwd_ready) {
+    for (int i = 0; i < 4; ++i) {
+      int rc = init_dgrad(h->m5conv_t[i], h->m5conv[i]);
+      if (rc != AP_OK) return rc;
+    }
+    h->bwd_ready = true;
+  }
+  int len[5], lo[4];
+  len[0] = L;
+  for (int i = 0; i < 4; ++i) {
+    lo[i] = (len[i] - h->m5conv[i].kw) / h->m5conv[i].stride + 1;
+    AP_REQUIRE(lo[i] >= 4, "M5: sequence too short at conv%d", i + 1);
+    len[i + 1] = lo[i] / 4;
+  }
+  const int bn_max = std::min(B, chunk);
+  // elements per image of the largest buffer: the zero-upsampled gradient of the strided first convolution, (L - k + 1) x n
+  const size_t big = static_cast<size_t>(L) * std::max(n, 2);
+  if (bn_max > h->bwd_bn) {
+    h->tape.clear();
+    for (int i = 0; i < 4; ++i) {   // conv + BN + ReLU outputs
+      auto d = std::make_unique<DevBuf>();
+      AP_CUDA(d->alloc(static_cast<size_t>(bn_max) * lo[i] * h->m5conv[i].Cout * sizeof(float)));
+      h->tape.push_back(std::move(d));
+    }
+    for (auto& g : h->gbuf) AP_CUDA(g.alloc(big * bn_max * sizeof(float)));
+    h->bwd_bn = bn_max;
+  }
+  auto grid_for = [](long long work) {
+    long long b = ceil_div_ll(work, 256);
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    return static_cast<unsigned>(b < cap ? (b > 0 ? b : 1) : cap);
+  };
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    float *P0 = h->gbuf[0].as<float>(), *GA = h->gbuf[1].as<float>(), *GB = h->gbuf[2].as<float>(), *LP = h->gbuf[3].as<float>();
+    // forward with the tape
+    const float* in = wav + static_cast<size_t>(b0) * L;
+    for (int i = 0; i < 4; ++i) {
+      const ConvLayer& cv = h->m5conv[i];
+      float* a = h->tape[i]->as<float>();
+      int rc = cv.run(in, bn, 1, len[i], a, nullptr, 1, st);
+      if (rc != AP_OK) return rc;
+      maxpool4_kernel<<<grid_for(static_cast<long long>(bn) * len[i + 1] * cv.Cout), 256, 0, st>>>(a, P0, bn, lo[i], cv.Cout);
+      AP_LAUNCH_CHECK();
+      in = P0;   // the pooled tensor is consumed by the next convolution before it is overwritten
+      if (i < 3) {   // ping-pong the pooled buffers
+        std::swap(P0, GA);
+      }
+    }
+    const size_t smem = sizeof(float) * (h->feat + K);
+    pool_fc_kernel<<<bn, 256, smem, st>>>(in, len[4], h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(), K, LP, 1);
+    AP_LAUNCH_CHECK();
+    // backward
+    float* g = h->gbuf[0].as<float>();
+    float* t1 = h->gbuf[1].as<float>();
+    logsoftmax_pool_fc_bwd_kernel<<<bn, 256, 0, st>>>(g_out + static_cast<size_t>(b0) * K, LP, h->fc_w.as<float>(), K, h->feat, len[4], g);
+    AP_LAUNCH_CHECK();
+    for (int i = 3; i >= 0; --i) {
+      const ConvLayer& cv = h->m5conv[i];
+      const float* a = h->tape[i]->as<float>();
+      // g: (bn, len[i+1], Cout) -> t1: (bn, lo[i], Cout) through max-pool + ReLU
+      maxpool4_relu_bwd_kernel<<<grid_for(static_cast<long long>(bn) * lo[i] * cv.Cout), 256, 0, st>>>(g, a, t1, bn, lo[i], cv.Cout);
+      AP_LAUNCH_CHECK();
+      const float* src = t1;
+      int lsrc = lo[i];
+      if (cv.stride > 1) {   // zero-upsample to length len - k + 1 (stride-1 geometry of the transposed convolution)
+        lsrc = len[i] - cv.kw + 1;
+        upsample1d_kernel<<<grid_for(static_cast<long long>(bn) * lsrc * cv.Cout), 256, 0, st>>>(t1, GB, bn, lo[i], lsrc, cv.stride, cv.Cout);
+        AP_LAUNCH_CHECK();
+        src = GB;
+      } else if (lo[i] + cv.kw - 1 != len[i]) {
+        return fail(AP_ERR_STATE, "M5 backward: unexpected geometry");
+      }
+      float* dst = i == 0 ? g_wav + static_cast<size_t>(b0) * L : g;
+      int rc = h->m5conv_t[i].run(src, bn, 1, lsrc, dst, nullptr, 0, st);   // -> (bn, len[i], Cin)
+      if (rc != AP_OK) return rc;
+    }
   }
   return AP_OK;
 }
@@ -948,14 +1094,16 @@ extern "C" int ap_classifier_forward(ap_classifier_t h, const float* input, floa
   }
 }
 
-// g_input = (d logits / d input)^T g_logits.  ResNeXt only (the SC09 default victim, adaptive_attack_eval.py:21).
+// g_input = (d logits / d input)^T g_logits.  ResNeXt (the SC09 default victim, adaptive_attack_eval.py:21) and M5.
 extern "C" int ap_classifier_vjp(ap_classifier_t h, const float* input, const float* g_logits, float* g_input, int B, int in_len,
                                  void* stream) {
   AP_REQUIRE(h && input && g_logits && g_input, "ap_classifier_vjp: null argument");
   AP_REQUIRE(B > 0, "ap_classifier_vjp: B must be positive");
-  if (h->cfg.kind != AP_CLS_RESNEXT) return fail(AP_ERR_STATE, "ap_classifier_vjp: the backward pass exists for ResNeXt only");
-  AP_REQUIRE(in_len == 32, "ap_classifier_vjp: ResNeXt input is (B, 1, 32, 32)");
+  if (h->cfg.kind != AP_CLS_RESNEXT && h->cfg.kind != AP_CLS_M5)
+    return fail(AP_ERR_STATE, "ap_classifier_vjp: the backward pass exists for ResNeXt and M5 only");
   AP_CUDA(cudaSetDevice(h->device));
+  if (h->cfg.kind == AP_CLS_M5) return vjp_m5(h, input, g_logits, g_input, B, in_len, static_cast<cudaStream_t>(stream));
+  AP_REQUIRE(in_len == 32, "ap_classifier_vjp: ResNeXt input is (B, 1, 32, 32)");
   return vjp_resnext(h, input, g_logits, g_input, B, static_cast<cudaStream_t>(stream));
 }
 

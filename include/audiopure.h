@@ -186,9 +186,10 @@ void ap_classifier_destroy(ap_classifier_t h);
 /* input: device (B, 1, 32, 32) spectrogram (ResNeXt, ResNet; in_len = 32), (B, L) waveform (M5; in_len = L) or (B, 32, W) (KWS; in_len = W) */
 int ap_classifier_forward(ap_classifier_t h, const float* input, float* logits, int B, int in_len, void* stream);
 /* Vector-Jacobian product wrt the input: g_input = (d logits / d input)^T g_logits, what autograd computes through
- * CifarResNeXt.forward (models/resnext.py:134-142, BatchNorm in eval mode) when an attack back-propagates the loss
- * (robustness_eval/white_box_attack.py:438).  ResNeXt only; fp32 (the forward is recomputed with every ReLU output kept,
- * 32 images at a time).  input, g_input: device (B, 1, 32, 32); g_logits: device (B, num_classes). */
+ * CifarResNeXt.forward (models/resnext.py:134-142) or M5.forward (audio_models/M5/M5Net.py:21-38), BatchNorm in eval mode,
+ * when an attack back-propagates the loss (robustness_eval/white_box_attack.py:438).  ResNeXt and M5 only; fp32 (the forward is
+ * recomputed with every ReLU output kept, 32 / 64 inputs at a time).  input, g_input: device (B, 1, 32, 32) or (B, L);
+ * g_logits: device (B, num_classes). */
 int ap_classifier_vjp(ap_classifier_t h, const float* input, const float* g_logits, float* g_input, int B, int in_len,
                       void* stream);
 /* AP_MODE_TF32 (default for ResNeXt: tensor-core convolutions) or AP_MODE_FP32 (every convolution on the FFMA path) */

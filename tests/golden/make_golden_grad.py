@@ -90,6 +90,17 @@ def main():
     out["resnext_g_logits"] = gl.numpy()
     out["resnext_grad"] = gs.numpy()
 
+    # ---- M5 raw-waveform classifier (eval mode): g_wav for a seeded g_logp
+    sys.path.insert(0, os.path.join(REF, "audio_models", "M5"))
+    from M5Net import M5
+    m5 = M5(n_input=1, first_kernel_size=160, n_output=10).eval()
+    m5.load_state_dict(to_torch_sd(synthetic.m5_state_dict(seed=0)))
+    xr = xm.clone().requires_grad_(True)
+    gl5 = torch.from_numpy(synthetic.host_noise((2, 10), 4252, 0))
+    (g5,) = torch.autograd.grad(m5(xr), xr, gl5)
+    out["m5_g_logp"] = gl5.numpy()
+    out["m5_grad"] = g5.numpy()
+
     # ---- end to end: d CrossEntropy(AcousticSystem(x), y) / d x through DDPM t*=2 -> mel -> ResNeXt, one 1 s clip
     from acoustic_system import AcousticSystem
     transform = lambda w: todb(mel_sc(w))

@@ -674,9 +674,18 @@ def test_resnext_vjp_vs_reference_autograd(ap, golden_grad):
     err = rel_l2(gs, golden_grad["resnext_grad"])
     print(f"ResNeXt gradient: rel-L2 {err:.3e}")
     assert err < 1e-3
+    kws = ap.KWSClassifier(synthetic.kws_state_dict(seed=0))
+    with pytest.raises(ap.AudioPureError):      # no backward pass for KWS / ResNet: refuse rather than drop the gradient
+        kws(torch.zeros(1, 1, 32, 81, device="cuda", requires_grad=True))
+
+
+def test_m5_vjp_vs_reference_autograd(ap, golden_grad):
     m5 = ap.M5Classifier(synthetic.m5_state_dict(seed=0))
-    with pytest.raises(ap.AudioPureError):      # no backward pass for M5 / KWS / ResNet: refuse rather than drop the gradient
-        m5(cuda(synthetic.synthetic_waveforms(1, 16000, seed=1)).requires_grad_(True))
+    x = cuda(synthetic.synthetic_waveforms(2, 16000, seed=99)).requires_grad_(True)
+    (gx,) = torch.autograd.grad(m5(x), x, cuda(golden_grad["m5_g_logp"]))
+    err = rel_l2(gx, golden_grad["m5_grad"])
+    print(f"M5 gradient: rel-L2 {err:.3e}")
+    assert err < 1e-4
 
 
 def test_acoustic_system_loss_gradient_vs_reference_autograd(ap, golden_grad, sd_full):

@@ -56,6 +56,8 @@ SIGNATURES = {
     "ap_diffwave_reserve": (_i, [_vp, _i, _i]),
     "ap_diffwave_eps": (_i, [_vp, _fp, _f, _fp, _i, _i, _vp]),
     "ap_diffwave_eps_vjp": (_i, [_vp, _fp, _f, _fp, _fp, _fp, _i, _i, _vp]),
+    "ap_diffwave_eps_save": (_i, [_vp, _fp, _f, _fp, _i, _i, _vp, C.POINTER(C.c_ulonglong)]),
+    "ap_diffwave_eps_vjp_saved": (_i, [_vp, C.c_ulonglong, _fp, _fp, _fp, _i, _i, _vp]),
     "ap_noise_offset_stride": (_u64, [_i, _i]),
     "ap_diffuse": (_i, [_fp, _f, _f, _fp, _u64, _u64, _fp, _i, _i, _vp]),
     "ap_ddpm_step": (_i, [_fp, _fp, _f, _f, _f, _fp, _u64, _u64, _i, _i, _vp]),

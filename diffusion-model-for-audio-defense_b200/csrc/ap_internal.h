@@ -41,6 +41,12 @@ int tc_net_debug_layer(TcNet* n, const float* x, const float* ptab, int layer, f
 int tc_net_vjp(TcNet* n, const float* x, const float* ptab, const float* g_eps, float* g_x, float* eps_out, float* eps_scratch,
                int B, int L, int bchunk, cudaStream_t st);
 size_t tc_net_bwd_bytes_per_waveform(const TcNet* n, int L);
+// the two halves of tc_net_vjp: a forward that keeps the backward's inputs (token = generation of the saved state) and the
+// backward from that state
+int tc_net_eps_save(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, int bchunk, cudaStream_t st,
+                    unsigned long long* token);
+bool tc_net_saved_state_is(const TcNet* n, unsigned long long token, int B, int L);
+int tc_net_backward(TcNet* n, const float* x, const float* g_eps, float* g_x, int B, int L, cudaStream_t st);
 
 // per-launch CUDA-event timing of k1_layer ([0]) and k2_head ([1]); read synchronises on the recorded events
 void tc_net_profile(TcNet* n, bool on);

@@ -434,6 +434,8 @@ extern "C" int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* 
   return AP_OK;
 }
 
+static long long vjp_chunk(ap_diffwave_t h, int B, int L);
+
 // Vector-Jacobian product of the network: g_x = (d eps_theta(x, t) / d x)^T g_eps (what autograd computes through the
 // reference's WaveNet when an attack calls loss.backward(), robustness_eval/white_box_attack.py:438).  bf16 mode.
 extern "C" int ap_diffwave_eps_vjp(ap_diffwave_t h, const float* x, float t, const float* g_eps, float* g_x, float* eps_out,
@@ -444,11 +446,7 @@ extern "C" int ap_diffwave_eps_vjp(ap_diffwave_t h, const float* x, float t, con
     return fail(AP_ERR_STATE, "ap_diffwave_eps_vjp: the backward pass exists in AP_MODE_BF16 and AP_MODE_BF16X3 only");
   AP_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // sub-batches sized so that the saved activations stay below ~24 GB
-  const size_t per = tc_net_bwd_bytes_per_waveform(h->tc, L);
-  long long bchunk = static_cast<long long>((24ull << 30) / per);
-  if (bchunk < 1) bchunk = 1;
-  if (bchunk > B) bchunk = B;
+  const long long bchunk = vjp_chunk(h, B, L);
   if (h->tc_chunk < bchunk || h->tc_L != L) {
     int rc = ap_diffwave_reserve(h, static_cast<int>(bchunk), L);
     if (rc != AP_OK) return rc;
@@ -465,6 +463,46 @@ extern "C" int ap_diffwave_eps_vjp(ap_diffwave_t h, const float* x, float t, con
     if (rc != AP_OK) return rc;
   }
   return AP_OK;
+}
+
+static long long vjp_chunk(ap_diffwave_t h, int B, int L) {   // sub-batch keeping the saved activations below ~24 GB
+  const size_t per = tc_net_bwd_bytes_per_waveform(h->tc, L);
+  long long bchunk = static_cast<long long>((24ull << 30) / per);
+  if (bchunk < 1) bchunk = 1;
+  return bchunk > B ? B : bchunk;
+}
+
+// Forward that keeps the backward's inputs: eps = eps_theta(x, t) and *token identifies the saved state.  A following
+// ap_diffwave_eps_vjp_saved(token) skips the recomputation; the state is overwritten by the next saving forward (including the
+// recomputation inside ap_diffwave_eps_vjp), so in a chain of evaluations only the last one can be reused -- which is the first
+// one the backward pass visits.  Returns AP_ERR_STATE when B exceeds the backward sub-batch (use ap_diffwave_eps then).
+extern "C" int ap_diffwave_eps_save(ap_diffwave_t h, const float* x, float t, float* eps, int B, int L, void* stream,
+                                    unsigned long long* token) {
+  AP_REQUIRE(h && x && eps && token, "ap_diffwave_eps_save: null argument");
+  AP_REQUIRE(B > 0 && L > 0, "ap_diffwave_eps_save: B and L must be positive (got %d, %d)", B, L);
+  *token = 0;
+  if (h->mode != AP_MODE_BF16 && h->mode != AP_MODE_BF16X3)
+    return fail(AP_ERR_STATE, "ap_diffwave_eps_save: AP_MODE_BF16 and AP_MODE_BF16X3 only");
+  AP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long bchunk = vjp_chunk(h, B, L);
+  if (B > bchunk) return fail(AP_ERR_STATE, "ap_diffwave_eps_save: batch %d exceeds the backward sub-batch %lld", B, bchunk);
+  if (h->tc_chunk < B || h->tc_L != L) {
+    int rc = ap_diffwave_reserve(h, B, L);
+    if (rc != AP_OK) return rc;
+  }
+  int rc = step_embedding(h, t, st);
+  if (rc != AP_OK) return rc;
+  return tc_net_eps_save(h->tc, x, h->ptab.as<float>(), eps, B, L, static_cast<int>(bchunk), st, token);
+}
+
+extern "C" int ap_diffwave_eps_vjp_saved(ap_diffwave_t h, unsigned long long token, const float* x, const float* g_eps, float* g_x,
+                                         int B, int L, void* stream) {
+  AP_REQUIRE(h && x && g_eps && g_x, "ap_diffwave_eps_vjp_saved: null argument");
+  AP_REQUIRE(h->tc, "ap_diffwave_eps_vjp_saved: no tensor-core network");
+  if (!tc_net_saved_state_is(h->tc, token, B, L)) return fail(AP_ERR_STATE, "ap_diffwave_eps_vjp_saved: the saved state is stale");
+  AP_CUDA(cudaSetDevice(h->device));
+  return tc_net_backward(h->tc, x, g_eps, g_x, B, L, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ap_diffwave_purify_ddpm(ap_diffwave_t h, const float* x0, float* out, int t_star, const float* coef4,

@@ -1116,6 +1116,8 @@ struct TcNet {
   CUtensorMap tmGpre, tmGs, tmGa, tmGu[2];
   int bchunk = 0, bL = 0;
   bool bwd_attr = false;
+  unsigned long long save_gen = 0;   // generation of the saved forward state (tokens of ap_diffwave_eps_save)
+  int save_B = 0, save_dt = 0;
   DevBuf br, bf2, init_w, init_b, wf2_dev;                 // fp32 vectors
   std::vector<float> bskip_host, bf1_host, wf2_host;       // k2's per-channel vectors (kernel params)
   std::vector<float> bd_host;                              // [N][512] dilated-conv biases in k1's packed order (kernel params)
@@ -1490,6 +1492,7 @@ static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
   if (n->bchunk == chunk && n->bL == L) return AP_OK;
   const size_t pos = static_cast<size_t>(chunk) * L;
   for (DevBuf* d : {&n->ts, &n->mask, &n->g_pre, &n->g_s, &n->g_a, &n->g_u[0], &n->g_u[1]}) d->release();
+  n->save_B = 0, ++n->save_gen;
   AP_CUDA(n->ts.alloc(pos * 512 * 2 * n->N));
   AP_CUDA(n->mask.alloc(pos * 8 * 4));
   AP_CUDA(n->g_pre.alloc(pos * 256 * 2));
@@ -1524,17 +1527,32 @@ size_t tc_net_bwd_bytes_per_waveform(const TcNet* n, int L) {
   return static_cast<size_t>(L) * (static_cast<size_t>(n->N) * 1024 + 32 + 512 + 512 + 1024 + 1024);
 }
 
-int tc_net_vjp(TcNet* n, const float* x, const float* ptab, const float* g_eps, float* g_x, float* eps_out, float* eps_scratch,
-               int B, int L, int bchunk, cudaStream_t st) {
+// forward that keeps what the backward needs (the gate's local derivatives of every layer, the head's ReLU mask); returns a
+// token identifying the saved state (any later saving forward, re-reservation or mode change invalidates it)
+int tc_net_eps_save(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, int bchunk, cudaStream_t st,
+                    unsigned long long* token) {
   using namespace tc;
   if (n->dt == 1) return fail(AP_ERR_STATE, "backward pass: bf16 / bf16x3 modes only");
-  if (B > n->chunk || L != n->L || n->ws_split != (n->dt == 2)) return fail(AP_ERR_STATE, "tc_net_vjp: forward workspace mismatch");
-  if (B > bchunk) return fail(AP_ERR_STATE, "tc_net_vjp: batch %d exceeds the backward chunk %d", B, bchunk);
+  if (B > n->chunk || L != n->L || n->ws_split != (n->dt == 2)) return fail(AP_ERR_STATE, "tc_net_eps_save: forward workspace mismatch");
+  if (B > bchunk) return fail(AP_ERR_STATE, "tc_net_eps_save: batch %d exceeds the backward chunk %d", B, bchunk);
   int rc = tc_bwd_reserve(n, bchunk, L);
   if (rc != AP_OK) return rc;
-  // forward, keeping tanh / sigmoid of every layer and the head's ReLU mask
-  rc = tc_net_eps_impl(n, x, ptab, eps_out ? eps_out : eps_scratch, B, L, st, true);
+  n->save_B = 0;
+  rc = tc_net_eps_impl(n, x, ptab, eps, B, L, st, true);
   if (rc != AP_OK) return rc;
+  n->save_B = B, n->save_dt = n->dt;
+  if (token) *token = ++n->save_gen;
+  else ++n->save_gen;
+  return AP_OK;
+}
+bool tc_net_saved_state_is(const TcNet* n, unsigned long long token, int B, int L) {
+  return token != 0 && token == n->save_gen && n->save_B == B && n->bL == L && n->save_dt == n->dt;
+}
+
+// backward from the saved state of the last tc_net_eps_save (same x)
+int tc_net_backward(TcNet* n, const float* x, const float* g_eps, float* g_x, int B, int L, cudaStream_t st) {
+  using namespace tc;
+  if (n->save_B != B || n->bL != L) return fail(AP_ERR_STATE, "tc_net_backward: no saved forward state for this batch");
   const long long M = static_cast<long long>(B) * L;
   const int tps = ceil_div(L, TILE_M), n_tiles = tps * B, grid = pair_grid(n_tiles), smem = Geo<2, 2>::SMEM_BYTES;
   {
@@ -1571,6 +1589,13 @@ int tc_net_vjp(TcNet* n, const float* x, const float* ptab, const float* g_eps, 
     AP_LAUNCH_CHECK();
   }
   return AP_OK;
+}
+
+int tc_net_vjp(TcNet* n, const float* x, const float* ptab, const float* g_eps, float* g_x, float* eps_out, float* eps_scratch,
+               int B, int L, int bchunk, cudaStream_t st) {
+  int rc = tc_net_eps_save(n, x, ptab, eps_out ? eps_out : eps_scratch, B, L, bchunk, st, nullptr);
+  if (rc != AP_OK) return rc;
+  return tc_net_backward(n, x, g_eps, g_x, B, L, st);
 }
 
 // debug: run init + layers [0, layer] and return u_{layer+1} and o_layer as fp32 (B, L, 256)

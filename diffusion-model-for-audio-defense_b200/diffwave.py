@@ -82,16 +82,22 @@ class _EpsVJP(torch.autograd.Function):
     Only the input is kept; the backward call recomputes the forward with the activations it needs."""
 
     @staticmethod
-    def forward(ctx, x, net, t):
+    def forward(ctx, x, net, t, keep):
         xd = x.detach().to(torch.float32).contiguous()
         ctx.net, ctx.t = net, float(t)
         ctx.save_for_backward(xd)
-        return net.eps(xd, float(t))
+        # keep: run the forward that keeps the backward's inputs (token 0: nothing kept -- batch too large, or not asked)
+        eps, ctx.token = net._eps_save(xd, float(t)) if keep else (net.eps(xd, float(t)), 0)
+        return eps
 
     @staticmethod
     def backward(ctx, g):
         (xd,) = ctx.saved_tensors
-        return ctx.net.eps_vjp(xd, ctx.t, g), None, None
+        if ctx.token:     # the last saving forward of the handle is the first one the backward pass reaches
+            gx = ctx.net._eps_vjp_saved(ctx.token, xd, g)
+            if gx is not None:
+                return gx, None, None, None
+        return ctx.net.eps_vjp(xd, ctx.t, g), None, None, None
 
 
 def _check_wave(x: torch.Tensor, what: str) -> torch.Tensor:
@@ -148,12 +154,14 @@ class WaveNet(torch.nn.Module):
         _lib.check(self._lib.ap_diffwave_reserve(self._handle, int(chunk), int(length)), "ap_diffwave_reserve")
 
     # -- forward --------------------------------------------------------------------------------------------------
-    def eps(self, x: torch.Tensor, t: float, out: torch.Tensor | None = None) -> torch.Tensor:
-        """eps_theta(x, t) with the same diffusion step t for every row.  Differentiable wrt x (bf16 mode)."""
+    def eps(self, x: torch.Tensor, t: float, out: torch.Tensor | None = None, keep_for_backward: bool = True) -> torch.Tensor:
+        """eps_theta(x, t) with the same diffusion step t for every row.  Differentiable wrt x (bf16 / bf16x3 modes).
+        ``keep_for_backward``: for an input that requires grad, keep the backward's inputs during this forward (the handle
+        holds ONE such state, so a chain of evaluations passes True only for its last one -- the first to be differentiated)."""
         if out is None and _wants_grad(x):
             if not x.is_cuda:
                 raise AudioPureError("WaveNet: input must be a CUDA tensor (there is no CPU path)")
-            return _EpsVJP.apply(x, self, float(t))
+            return _EpsVJP.apply(x, self, float(t), bool(keep_for_backward))
         x = _check_wave(x, "WaveNet")
         assert x.ndim == 3 and x.shape[1] == 1, x.shape
         B, _, L = x.shape
@@ -163,6 +171,27 @@ class WaveNet(torch.nn.Module):
             _lib.check(self._lib.ap_diffwave_eps(self._handle, x.data_ptr(), float(t), out.data_ptr(), B, L,
                                                  _lib.stream_ptr()), "ap_diffwave_eps")
         return out
+
+    def _eps_save(self, x: torch.Tensor, t: float):
+        """(eps, token): forward that keeps the backward's inputs when the batch fits (token != 0), else the plain forward."""
+        B, _, L = x.shape
+        out = torch.empty_like(x)
+        token = C.c_ulonglong(0)
+        with torch.cuda.device(x.device):
+            rc = self._lib.ap_diffwave_eps_save(self._handle, x.data_ptr(), float(t), out.data_ptr(), B, L, _lib.stream_ptr(),
+                                                C.byref(token))
+        if rc != 0:
+            return self.eps(x, t), 0
+        return out, int(token.value)
+
+    def _eps_vjp_saved(self, token: int, x: torch.Tensor, g_eps: torch.Tensor):
+        g = g_eps.detach().to(torch.float32).contiguous()
+        B, _, L = x.shape
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            rc = self._lib.ap_diffwave_eps_vjp_saved(self._handle, C.c_ulonglong(token), x.data_ptr(), g.data_ptr(), gx.data_ptr(),
+                                                     B, L, _lib.stream_ptr())
+        return gx if rc == 0 else None
 
     def eps_vjp(self, x: torch.Tensor, t: float, g_eps: torch.Tensor) -> torch.Tensor:
         """g_x = (d eps_theta(x, t) / d x)^T g_eps (the backward of ``eps``)."""
@@ -295,7 +324,7 @@ class DiffWave(torch.nn.Module):
         a, b = float(torch.sqrt(Alpha_bar[t_star - 1])), float(torch.sqrt(1 - Alpha_bar[t_star - 1]))
         x = a * x_0.to(torch.float32) + b * self._randn(x_0.shape, x_0.device)
         for t in range(t_star - 1, -1, -1):
-            eps = self.model.eps(x, float(t))
+            eps = self.model.eps(x, float(t), keep_for_backward=(t == 0))
             c_eps, sqrt_alpha, sigma = self._ddpm_coefficients(t)
             x = (x - c_eps * eps) / sqrt_alpha
             if t > 0:

@@ -148,9 +148,10 @@ class RevDiffWave(torch.nn.Module):
             sa, sb = float(a[total_noise_levels - 1].sqrt()), float((1.0 - a[total_noise_levels - 1]).sqrt())
             e = torch.randn_like(x0) if self.noise == "torch" else dw._randn(x0.shape, x0.device)
             x = sa * x0 + sb * e
-            for s, ds in euler_schedule(self.args.t, self.T):
+            sched = list(euler_schedule(self.args.t, self.T))
+            for i, (s, ds) in enumerate(sched):
                 d, c = self.rev_vpsde.step_coefficients(s, ds)
-                eps = dw.model.eps(x, float(d))
+                eps = dw.model.eps(x, float(d), keep_for_backward=(i == len(sched) - 1))
                 f = 0.5 * c.beta * x - c.diff2 * eps / c.sqrt_1mab        # -(drift - g^2 score), score = -eps / sqrt(1 - abar)
                 x = x + f * c.dt
                 if self.noise == "torch":

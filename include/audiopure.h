@@ -102,6 +102,14 @@ int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* eps, int B,
  * gradient discontinuous in the forward values: with a bf16 forward ~1 % of its masks differ from an fp32 forward's. */
 int ap_diffwave_eps_vjp(ap_diffwave_t h, const float* x, float t, const float* g_eps, float* g_x, float* eps_out, int B,
                         int L, void* stream);
+/* The same in two halves, for callers that know at forward time that a backward will follow (autograd): a forward that keeps
+ * the backward's inputs and returns a token, and the backward from that state.  Any later saving forward on the handle
+ * (including the recomputation inside ap_diffwave_eps_vjp) overwrites the state: a stale token gives AP_ERR_STATE and the
+ * caller falls back to ap_diffwave_eps_vjp.  ap_diffwave_eps_save returns AP_ERR_STATE when B exceeds the ~24 GB sub-batch. */
+int ap_diffwave_eps_save(ap_diffwave_t h, const float* x, float t, float* eps, int B, int L, void* stream,
+                         unsigned long long* token);
+int ap_diffwave_eps_vjp_saved(ap_diffwave_t h, unsigned long long token, const float* x, const float* g_eps, float* g_x, int B,
+                              int L, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Per-step updates (HBM-bound elementwise kernels; in-kernel Philox4x32-10 + Box-Muller when z == NULL)

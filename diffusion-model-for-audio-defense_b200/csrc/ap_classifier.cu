@@ -133,7 +133,7 @@ struct ConvLayer {
 
 // Data-gradient twin of a convolution: g_x = conv(g_y [zero-upsampled by the stride], W^T rotated 180 degrees), stride 1,
 // padding k - 1 - pad, same groups.  `L` must have kept its folded weights (keep_host).
-static int init_dgrad(ConvLayer& T, const ConvLayer& L) {
+static int init_dgrad(ConvLayer& T, const ConvLayer& L, bool want_tc = false) {
   if (L.wf_host.empty()) return fail(AP_ERR_STATE, "init_dgrad: the forward layer did not keep its weights");
   const int Cg = L.Cg, Ng = L.Ng, kh = L.kh, kw = L.kw;
   std::vector<float> wt(static_cast<size_t>(L.Cin) * Ng * kh * kw);
@@ -144,7 +144,7 @@ static int init_dgrad(ConvLayer& T, const ConvLayer& L) {
           for (int q = 0; q < kw; ++q)
             wt[((static_cast<size_t>(g * Cg + c) * Ng + n) * kh + r) * kw + q] =
                 L.wf_host[((static_cast<size_t>(g * Ng + n) * Cg + c) * kh + (kh - 1 - r)) * kw + (kw - 1 - q)];
-  return T.init(L.Cout, L.Cin, kh, kw, 1, kw - 1 - L.pad, L.groups, wt.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+  return T.init(L.Cout, L.Cin, kh, kw, 1, kw - 1 - L.pad, L.groups, wt.data(), nullptr, nullptr, nullptr, nullptr, nullptr, want_tc);
 }
 
 // g[i] = act[i] > 0 ? g[i] : 0      (backward of ReLU, from the saved activation)
@@ -633,10 +633,10 @@ static int vjp_resnext(ap_classifier_t h, const float* spec, const float* g_logi
   if (!h->bwd_ready) {
     int rc = init_dgrad(h->t_stem, h->stem);
     for (auto& b : h->blocks) {
-      if (rc == AP_OK) rc = init_dgrad(b->t_reduce, b->reduce);
-      if (rc == AP_OK) rc = init_dgrad(b->t_conv, b->conv);
-      if (rc == AP_OK) rc = init_dgrad(b->t_expand, b->expand);
-      if (rc == AP_OK && b->has_shortcut) rc = init_dgrad(b->t_shortcut, b->shortcut);
+      if (rc == AP_OK) rc = init_dgrad(b->t_reduce, b->reduce, true);
+      if (rc == AP_OK) rc = init_dgrad(b->t_conv, b->conv, true);
+      if (rc == AP_OK) rc = init_dgrad(b->t_expand, b->expand, true);
+      if (rc == AP_OK && b->has_shortcut) rc = init_dgrad(b->t_shortcut, b->shortcut, true);
     }
     if (rc != AP_OK) return rc;
     h->bwd_ready = true;
@@ -680,9 +680,28 @@ static int vjp_resnext(ap_classifier_t h, const float* spec, const float* g_logi
     AP_LAUNCH_CHECK();
     return AP_OK;
   };
+  // AP_MODE_TF32: the recomputed forward and the data-gradient convolutions run on the tcgen05 kind::tf32 kernel wherever the
+  // shape allows (outputs rounded to tf32 for the next layer, like the inference path); AP_MODE_FP32: everything on FFMA
+  // (a ReLU network's gradient is discontinuous in the forward values: the tf32 forward flips ~0.1 % of the masks per layer
+  // relative to an fp32 forward, which moves the gradient by ~6 %; AP_CLS_VJP_FWD_FP32=1 keeps the recomputed forward on
+  // FFMA so that tests can check the tensor-core data-gradient kernels alone against fp32 autograd)
+  const bool tc_bwd = h->mode == AP_MODE_TF32;
+  const char* env_fwd = std::getenv("AP_CLS_VJP_FWD_FP32");
+  const bool tc_fwd = tc_bwd && !(env_fwd && env_fwd[0] == '1');
+  bool use_tc = tc_fwd;
+  int bn = 0;
+  auto conv = [&](const ConvLayer& Lr, const float* in, int Hh, int Ww, float* out, const float* res, int relu) -> int {
+    if (use_tc && Lr.has_tc && conv_tc_supported(Lr.Cin, Lr.Cout, Lr.groups, Hh, Ww, Lr.kh, Lr.kw, Lr.stride, Lr.pad)) {
+      ConvTcBinding bnd;
+      int rc = Lr.tc.bind(&bnd, in, bn, Hh, Ww, out, res, relu, 1);
+      return rc != AP_OK ? rc : Lr.tc.run(bnd, st);
+    }
+    return Lr.run(in, bn, Hh, Ww, out, res, relu, st);
+  };
   for (int b0 = 0; b0 < B; b0 += chunk) {
-    const int bn = std::min(chunk, B - b0);
+    bn = std::min(chunk, B - b0);
     // ---- forward with the tape
+    use_tc = tc_fwd;
     float* x0 = h->tape_x0.as<float>();
     int rc = h->stem.run(spec + static_cast<size_t>(b0) * H0 * W0, bn, H0, W0, x0, nullptr, 1, st);
     if (rc != AP_OK) return rc;
@@ -692,18 +711,19 @@ static int vjp_resnext(ap_classifier_t h, const float* spec, const float* g_logi
       Bottleneck& b = *h->blocks[i];
       float *r = h->tape[3 * i]->as<float>(), *c = h->tape[3 * i + 1]->as<float>(), *y = h->tape[3 * i + 2]->as<float>();
       const int Ho = (H - 1) / b.stride + 1, Wo = (W - 1) / b.stride + 1;
-      rc = b.reduce.run(x, bn, H, W, r, nullptr, 1, st);
-      if (rc == AP_OK) rc = b.conv.run(r, bn, H, W, c, nullptr, 1, st);
+      rc = conv(b.reduce, x, H, W, r, nullptr, 1);
+      if (rc == AP_OK) rc = conv(b.conv, r, H, W, c, nullptr, 1);
       const float* res = x;
       if (rc == AP_OK && b.has_shortcut) {
-        rc = b.shortcut.run(x, bn, H, W, h->gbuf[4].as<float>(), nullptr, 0, st);
+        rc = conv(b.shortcut, x, H, W, h->gbuf[4].as<float>(), nullptr, 0);
         res = h->gbuf[4].as<float>();
       }
-      if (rc == AP_OK) rc = b.expand.run(c, bn, Ho, Wo, y, res, 1, st);
+      if (rc == AP_OK) rc = conv(b.expand, c, Ho, Wo, y, res, 1);
       if (rc != AP_OK) return rc;
       x = y, H = Ho, W = Wo;
     }
     // ---- backward
+    use_tc = tc_bwd;
     float *GA = h->gbuf[0].as<float>(), *GB = h->gbuf[1].as<float>(), *GC = h->gbuf[2].as<float>(), *GD = h->gbuf[3].as<float>(),
           *GE = h->gbuf[4].as<float>();
     pool_fc_bwd_kernel<<<bn, 256, 0, st>>>(g_logits + static_cast<size_t>(b0) * h->cfg.num_classes, h->fc_w.as<float>(),
@@ -715,14 +735,14 @@ static int vjp_resnext(ap_classifier_t h, const float* spec, const float* g_logi
       const int Ho = H, Wo = W, Hi = H * b.stride, Wi = W * b.stride;
       const size_t npix_o = static_cast<size_t>(bn) * Ho * Wo, npix_i = static_cast<size_t>(bn) * Hi * Wi;
       rc = mask(GA, y, npix_o * b.cout);                                          // through the block's final ReLU
-      if (rc == AP_OK) rc = b.t_expand.run(GA, bn, Ho, Wo, GB, nullptr, 0, st);   // -> d c
+      if (rc == AP_OK) rc = conv(b.t_expand, GA, Ho, Wo, GB, nullptr, 0);   // -> d c
       if (rc == AP_OK) rc = mask(GB, c, npix_o * b.D);
       const float* src = GB;
       if (rc == AP_OK && b.stride == 2) {
         rc = upsample(GB, GC, bn, Ho, Wo, b.D);
         src = GC;
       }
-      if (rc == AP_OK) rc = b.t_conv.run(src, bn, Hi, Wi, GD, nullptr, 0, st);    // -> d r
+      if (rc == AP_OK) rc = conv(b.t_conv, src, Hi, Wi, GD, nullptr, 0);    // -> d r
       if (rc == AP_OK) rc = mask(GD, r, npix_i * b.D);
       const float* res = GA;                                                      // identity shortcut
       if (rc == AP_OK && b.has_shortcut) {
@@ -731,10 +751,10 @@ static int vjp_resnext(ap_classifier_t h, const float* spec, const float* g_logi
           rc = upsample(GA, GC, bn, Ho, Wo, b.cout);
           ssrc = GC;
         }
-        if (rc == AP_OK) rc = b.t_shortcut.run(ssrc, bn, Hi, Wi, GE, nullptr, 0, st);
+        if (rc == AP_OK) rc = conv(b.t_shortcut, ssrc, Hi, Wi, GE, nullptr, 0);
         res = GE;
       }
-      if (rc == AP_OK) rc = b.t_reduce.run(GD, bn, Hi, Wi, GB, res, 0, st);       // d x = reduce^T(d r) + shortcut path
+      if (rc == AP_OK) rc = conv(b.t_reduce, GD, Hi, Wi, GB, res, 0);       // d x = reduce^T(d r) + shortcut path
       if (rc != AP_OK) return rc;
       std::swap(GA, GB);
       H = Hi, W = Wi;

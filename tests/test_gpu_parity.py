@@ -666,14 +666,21 @@ def test_mel_vjp_vs_torchaudio_autograd(ap, golden_grad, name):
     assert err < 1e-4
 
 
-def test_resnext_vjp_vs_reference_autograd(ap, golden_grad):
-    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+@pytest.mark.parametrize("mode", ["fp32", "tf32-bwd", "tf32"])
+def test_resnext_vjp_vs_reference_autograd(ap, golden_grad, mode, monkeypatch):
+    """fp32: FFMA forward recompute and data-gradient convolutions.  tf32 (the default mode): both on the tcgen05 kernel --
+    the gradient of the tf32 forward, whose ReLU masks differ from the fp32 forward's in ~0.1 % of the units per layer: a ReLU
+    network's gradient is discontinuous in the forward values, and that alone moves it by ~6 %.  tf32-bwd keeps the recomputed
+    forward in fp32 (AP_CLS_VJP_FWD_FP32=1) and so checks the tensor-core data-gradient kernels alone."""
+    if mode == "tf32-bwd":
+        monkeypatch.setenv("AP_CLS_VJP_FWD_FP32", "1")
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0)).set_mode("fp32" if mode == "fp32" else "tf32")
     spec = cuda(golden_grad["resnext_in_spec"]).requires_grad_(True)
     logits = rx(spec)
     (gs,) = torch.autograd.grad(logits, spec, cuda(golden_grad["resnext_g_logits"]))
     err = rel_l2(gs, golden_grad["resnext_grad"])
-    print(f"ResNeXt gradient: rel-L2 {err:.3e}")
-    assert err < 1e-3
+    print(f"ResNeXt gradient ({mode}): rel-L2 {err:.3e}")
+    assert err < {"fp32": 1e-5, "tf32-bwd": 5e-3, "tf32": 1.5e-1}[mode]
     kws = ap.KWSClassifier(synthetic.kws_state_dict(seed=0))
     with pytest.raises(ap.AudioPureError):      # no backward pass for KWS / ResNet: refuse rather than drop the gradient
         kws(torch.zeros(1, 1, 32, 81, device="cuda", requires_grad=True))
@@ -692,7 +699,7 @@ def test_acoustic_system_loss_gradient_vs_reference_autograd(ap, golden_grad, sd
     """d CrossEntropy(AcousticSystem(x), y) / d x through DDPM t* = 2 -> log-mel -> ResNeXt: the white-box attack gradient
     (robustness_eval/white_box_attack.py:430-438), every stage on the CUDA backward kernels."""
     dw = ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=2, state_dict=sd_full, noise="torch", mode="bf16x3")
-    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0)).set_mode("fp32")   # tf32 forward: ReLU-mask flips (see above)
     system = ap.AcousticSystem(classifier=rx, transform=ap.sc09_transform(), defender=dw, defense_type="wave")
     x = cuda(synthetic.synthetic_waveforms(1, 16000, seed=1234)).requires_grad_(True)
     with TorchNormalInjector(2027) as inj:
@@ -702,7 +709,7 @@ def test_acoustic_system_loss_gradient_vs_reference_autograd(ap, golden_grad, sd
     loss = torch.nn.functional.cross_entropy(logits, torch.tensor([3], device="cuda"))
     (gx,) = torch.autograd.grad(loss, x)
     err = rel_l2(gx, golden_grad["system_loss_grad"])
-    print(f"AcousticSystem loss gradient (bf16x3 purifier, tf32 classifier forward / fp32 backward): rel-L2 {err:.3e}")
+    print(f"AcousticSystem loss gradient (bf16x3 purifier, fp32 classifier): rel-L2 {err:.3e}")
     assert err < 2e-2
 
 

@@ -729,7 +729,7 @@ def test_pgd_steps_through_the_defended_system_raise_the_loss(ap, sd_full):
     for _ in range(5):
         dw._offset = 0
         loss = torch.nn.functional.cross_entropy(system(x + delta), y)
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         (grad,) = torch.autograd.grad(loss, delta)
         assert torch.isfinite(grad).all() and float(grad.abs().max()) > 0
         delta.data = (delta.data + lr * grad.sign()).clamp_(-eps, eps)

@@ -192,6 +192,7 @@ struct ap_diffwave_s {
   // bf16 tensor-core network
   TcNet* tc = nullptr;
   int tc_chunk = 0, tc_L = 0;
+  bool user_reserved = false;   // the workspace size was chosen by ap_diffwave_reserve: implicit calls do not change it
 };
 
 static int upload(DevBuf& d, const std::vector<float>& v) {
@@ -325,8 +326,14 @@ extern "C" int ap_diffwave_set_mode(ap_diffwave_t h, int mode) {
 }
 extern "C" int ap_diffwave_get_mode(ap_diffwave_t h) { return h ? h->mode : AP_ERR_INVALID; }
 
+static int reserve_ws(ap_diffwave_t h, int chunk, int L);
 extern "C" int ap_diffwave_reserve(ap_diffwave_t h, int chunk, int L) {
   AP_REQUIRE(h && chunk > 0 && L > 0, "ap_diffwave_reserve: bad arguments");
+  int rc = reserve_ws(h, chunk, L);
+  if (rc == AP_OK) h->user_reserved = true;
+  return rc;
+}
+static int reserve_ws(ap_diffwave_t h, int chunk, int L) {
   AP_CUDA(cudaSetDevice(h->device));
   if (h->mode != AP_MODE_FP32) {
     if (h->tc_chunk == chunk && h->tc_L == L) return AP_OK;
@@ -410,7 +417,7 @@ extern "C" int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* 
   const bool tc = h->mode != AP_MODE_FP32;
   int chunk = tc ? h->tc_chunk : h->chunk;
   const int curL = tc ? h->tc_L : h->L;
-  if (chunk == 0 || curL != L) {
+  {
     // default chunk: bounded workspace (fp32: 4 * 4 B * 256 ch per position; bf16: ~2.5 KB per position incl. gate history)
     // bf16: 148 waveforms of 1 s = 18500 tiles = 125 full rounds over 74 CTA pairs (no ragged last wave)
     // bf16x3: two planes per tensor, so half as many waveforms in the same workspace
@@ -418,9 +425,13 @@ extern "C" int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* 
     long long want = budget_positions / L;
     if (want < 1) want = 1;
     if (want > B) want = B;
-    int rc = ap_diffwave_reserve(h, static_cast<int>(want), L);
-    if (rc != AP_OK) return rc;
-    chunk = static_cast<int>(want);
+    // an implicitly sized workspace grows with the batch (e.g. after a small backward pass); an explicit reserve is kept
+    if (chunk == 0 || curL != L || (!h->user_reserved && chunk < want)) {
+      int rc = reserve_ws(h, static_cast<int>(want), L);
+      if (rc != AP_OK) return rc;
+      if (chunk == 0 || curL != L) h->user_reserved = false;
+      chunk = static_cast<int>(want);
+    }
   }
   int rc = step_embedding(h, t, st);
   if (rc != AP_OK) return rc;
@@ -448,8 +459,9 @@ extern "C" int ap_diffwave_eps_vjp(ap_diffwave_t h, const float* x, float t, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long bchunk = vjp_chunk(h, B, L);
   if (h->tc_chunk < bchunk || h->tc_L != L) {
-    int rc = ap_diffwave_reserve(h, static_cast<int>(bchunk), L);
+    int rc = reserve_ws(h, static_cast<int>(bchunk), L);
     if (rc != AP_OK) return rc;
+    h->user_reserved = false;
   }
   const size_t nb = static_cast<size_t>(bchunk) * L * sizeof(float);
   if (h->eps_buf.bytes < nb) AP_CUDA(h->eps_buf.alloc(nb));
@@ -488,8 +500,9 @@ extern "C" int ap_diffwave_eps_save(ap_diffwave_t h, const float* x, float t, fl
   const long long bchunk = vjp_chunk(h, B, L);
   if (B > bchunk) return fail(AP_ERR_STATE, "ap_diffwave_eps_save: batch %d exceeds the backward sub-batch %lld", B, bchunk);
   if (h->tc_chunk < B || h->tc_L != L) {
-    int rc = ap_diffwave_reserve(h, B, L);
+    int rc = reserve_ws(h, B, L);
     if (rc != AP_OK) return rc;
+    h->user_reserved = false;
   }
   int rc = step_embedding(h, t, st);
   if (rc != AP_OK) return rc;
@@ -537,8 +550,9 @@ extern "C" int ap_diffwave_debug_layer(ap_diffwave_t h, const float* x, float t,
   AP_REQUIRE(B > 0 && L > 0 && layer >= 0 && layer < h->cfg.num_res_layers, "ap_diffwave_debug_layer: bad arguments");
   AP_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = ap_diffwave_reserve(h, B, L);
+  int rc = reserve_ws(h, B, L);
   if (rc != AP_OK) return rc;
+  h->user_reserved = false;
   rc = step_embedding(h, t, st);
   if (rc != AP_OK) return rc;
   if (h->mode != AP_MODE_FP32) return tc_net_debug_layer(h->tc, x, h->ptab.as<float>(), layer, u_next, gate, B, L, st);

@@ -173,6 +173,7 @@ class M5Classifier(_Classifier):
 
 
 class KWSClassifier(_Classifier):
+    differentiable = True
     def __init__(self, state_dict: dict, in_size=32, hidden_size=64, num_classes=4, device=None):
         super().__init__()
         sd = _strip(state_dict)

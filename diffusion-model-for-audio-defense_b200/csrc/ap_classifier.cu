@@ -438,6 +438,250 @@ __global__ void __launch_bounds__(256) kws_kernel(const float* __restrict__ spec
   }
 }
 
+// ---- backward of the KWS forward (autograd over audio_models/RCNN_KWS/model.py:5-113): one CTA per sample recomputes the
+//      forward with the gate values of every GRU step kept in a global scratch area, then runs attention / BPTT / separable
+//      convolution backward.  g_spec = (d logp / d spec)^T g_out.
+struct KwsScratch {   // offsets (floats) into the per-sample scratch block
+  int dw, x0, x1, x2, sv, th, att, ctx, lg, g_x2, g_x1, g_x0, g_dw, total;
+};
+__host__ __device__ inline KwsScratch kws_scratch(int I, int W1, int T, int H, int K) {
+  KwsScratch s;
+  int o = 0;
+  s.dw = o, o += I * W1;
+  s.x0 = o, o += T * H;
+  s.x1 = o, o += T * 2 * H;
+  s.x2 = o, o += T * 2 * H;
+  s.sv = o, o += 2 * 2 * T * 5 * H;     // [layer][dir][step]{r, z, n, h_prev, gh_n}[H]
+  s.th = o, o += T * 2 * H;             // tanh(Wx x_t + b)
+  s.att = o, o += T;
+  s.ctx = o, o += 2 * H;
+  s.lg = o, o += K;
+  s.g_x2 = o, o += T * 2 * H;
+  s.g_x1 = o, o += T * 2 * H;
+  s.g_x0 = o, o += T * H;
+  s.g_dw = o, o += I * W1;
+  s.total = (o + 3) & ~3;
+  return s;
+}
+
+__global__ void __launch_bounds__(256) kws_vjp_kernel(const float* __restrict__ spec, int Wf, int in_size, int H, int num_classes,
+                                                      KwsWeights w, const float* __restrict__ g_out, float* __restrict__ scratch,
+                                                      float* __restrict__ g_spec) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int W1 = (Wf - 5) / 2 + 1, T = (W1 - 1) / 8 + 1;
+  const KwsScratch so = kws_scratch(in_size, W1, T, H, num_classes);
+  float* S = scratch + static_cast<long long>(b) * so.total;
+  float *dw = S + so.dw, *x0 = S + so.x0, *x1 = S + so.x1, *x2 = S + so.x2, *sv = S + so.sv, *th = S + so.th, *att = S + so.att,
+        *ctx = S + so.ctx, *lg = S + so.lg, *g_x2 = S + so.g_x2, *g_x1 = S + so.g_x1, *g_x0 = S + so.g_x0, *g_dw = S + so.g_dw;
+  float* hbuf = sm;                 // [2][H]   hidden state (forward) / carried gradient (backward)
+  float* gi = hbuf + 2 * H;         // [2][3H]
+  float* gh = gi + 2 * 3 * H;       // [2][3H]
+  float* red = gh + 2 * 3 * H;      // [64] small reductions
+  const float* sp = spec + static_cast<long long>(b) * in_size * Wf;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  // ------------------------------------------------------------------ forward (as kws_kernel), keeping the gate values
+  for (int i = tid; i < in_size * W1; i += nt) {
+    const int c = i / W1, t = i - c * W1;
+    float acc = w.dw_b[c];
+    for (int k = 0; k < 5; ++k) acc = fmaf(w.dw_w[c * 5 + k], sp[c * Wf + 2 * t + k], acc);
+    dw[i] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < T * H; i += nt) {
+    const int t = i / H, o = i - t * H;
+    float acc = w.pw_b[o];
+    for (int c = 0; c < in_size; ++c) acc = fmaf(w.pw_w[o * in_size + c], dw[c * W1 + 8 * t], acc);
+    x0[i] = acc;
+  }
+  __syncthreads();
+  {
+    const float* xin = x0;
+    int in_l = H;
+    float* xout = x1;
+    for (int layer = 0; layer < 2; ++layer) {
+      for (int i = tid; i < 2 * H; i += nt) hbuf[i] = 0.f;
+      __syncthreads();
+      for (int step = 0; step < T; ++step) {
+        for (int i = tid; i < 2 * 3 * H; i += nt) {
+          const int dir = i / (3 * H), g = i - dir * 3 * H;
+          const int t = dir ? T - 1 - step : step;
+          const float* wih = w.gru[layer][dir][0] + static_cast<long long>(g) * in_l;
+          const float* whh = w.gru[layer][dir][1] + static_cast<long long>(g) * H;
+          float a = w.gru[layer][dir][2][g], c = w.gru[layer][dir][3][g];
+          for (int k = 0; k < in_l; ++k) a = fmaf(wih[k], xin[t * in_l + k], a);
+          for (int k = 0; k < H; ++k) c = fmaf(whh[k], hbuf[dir * H + k], c);
+          gi[i] = a, gh[i] = c;
+        }
+        __syncthreads();
+        for (int i = tid; i < 2 * H; i += nt) {
+          const int dir = i / H, j = i - dir * H;
+          const int t = dir ? T - 1 - step : step;
+          const float* a = gi + dir * 3 * H;
+          const float* c = gh + dir * 3 * H;
+          const float r = sigm(a[j] + c[j]), z = sigm(a[H + j] + c[H + j]);
+          const float n = tanhf(a[2 * H + j] + r * c[2 * H + j]);
+          const float hp = hbuf[i];
+          const float hn = (1.f - z) * n + z * hp;
+          float* q = sv + (((layer * 2 + dir) * T + step) * 5) * H + j;
+          q[0] = r, q[H] = z, q[2 * H] = n, q[3 * H] = hp, q[4 * H] = c[2 * H + j];
+          hbuf[i] = hn;
+          xout[t * 2 * H + dir * H + j] = hn;
+        }
+        __syncthreads();
+      }
+      xin = xout, in_l = 2 * H, xout = x2;
+    }
+  }
+  const float* xf = x2;
+  for (int t = warp; t < T; t += nt >> 5) {
+    float acc = 0.f;
+    for (int o = lane; o < 2 * H; o += 32) {
+      float d = w.wx_b[o];
+      for (int k = 0; k < 2 * H; ++k) d = fmaf(w.wx_w[o * 2 * H + k], xf[t * 2 * H + k], d);
+      const float tv = tanhf(d);
+      th[t * 2 * H + o] = tv;
+      acc = fmaf(w.vt_w[o], tv, acc);
+    }
+    for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) att[t] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float mx = att[0];
+    for (int t = 1; t < T; ++t) mx = fmaxf(mx, att[t]);
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) att[t] = expf(att[t] - mx), s += att[t];
+    for (int t = 0; t < T; ++t) att[t] /= s;
+  }
+  __syncthreads();
+  for (int j = tid; j < 2 * H; j += nt) {
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc = fmaf(att[t], xf[t * 2 * H + j], acc);
+    ctx[j] = acc;
+  }
+  __syncthreads();
+  for (int k = warp; k < num_classes; k += nt >> 5) {
+    float acc = 0.f;
+    for (int j = lane; j < 2 * H; j += 32) acc = fmaf(w.u_w[k * 2 * H + j], ctx[j], acc);
+    for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) lg[k] = acc;
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ backward
+  // log_softmax: g_lg = g_out - softmax * sum(g_out)      (red[0..K) = g_lg)
+  if (tid == 0) {
+    float mx = lg[0];
+    for (int k = 1; k < num_classes; ++k) mx = fmaxf(mx, lg[k]);
+    float s = 0.f, gs = 0.f;
+    for (int k = 0; k < num_classes; ++k) s += expf(lg[k] - mx), gs += g_out[b * num_classes + k];
+    for (int k = 0; k < num_classes; ++k) red[k] = g_out[b * num_classes + k] - expf(lg[k] - mx) / s * gs;
+  }
+  __syncthreads();
+  // g_ctx = U^T g_lg  (kept in gi[0..2H))
+  float* g_ctx = gi;
+  for (int j = tid; j < 2 * H; j += nt) {
+    float acc = 0.f;
+    for (int k = 0; k < num_classes; ++k) acc = fmaf(w.u_w[k * 2 * H + j], red[k], acc);
+    g_ctx[j] = acc;
+  }
+  __syncthreads();
+  // g_att[t] = g_ctx . x_t   (gh[0..T)); g_x2[t] = att[t] * g_ctx
+  float* g_att = gh;
+  for (int t = warp; t < T; t += nt >> 5) {
+    float acc = 0.f;
+    for (int j = lane; j < 2 * H; j += 32) {
+      acc = fmaf(g_ctx[j], xf[t * 2 * H + j], acc);
+      g_x2[t * 2 * H + j] = att[t] * g_ctx[j];
+    }
+    for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) g_att[t] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {   // softmax over time: g_e = att * (g_att - sum att g_att)   (in place in g_att)
+    float dot = 0.f;
+    for (int t = 0; t < T; ++t) dot = fmaf(att[t], g_att[t], dot);
+    for (int t = 0; t < T; ++t) g_att[t] = att[t] * (g_att[t] - dot);
+  }
+  __syncthreads();
+  // e_t = Vt . tanh(d_t), d_t = Wx x_t + b:  g_d[t][o] = g_e[t] Vt[o] (1 - th^2)  (overwrites th);  g_x2[t] += Wx^T g_d[t]
+  for (int i = tid; i < T * 2 * H; i += nt) {
+    const int t = i / (2 * H), o = i - t * 2 * H;
+    const float tv = th[i];
+    th[i] = g_att[t] * w.vt_w[o] * (1.f - tv * tv);
+  }
+  __syncthreads();
+  for (int i = tid; i < T * 2 * H; i += nt) {
+    const int t = i / (2 * H), k = i - t * 2 * H;
+    float acc = 0.f;
+    for (int o = 0; o < 2 * H; ++o) acc = fmaf(w.wx_w[o * 2 * H + k], th[t * 2 * H + o], acc);
+    g_x2[i] += acc;
+  }
+  for (int i = tid; i < T * 2 * H; i += nt) g_x1[i] = 0.f;
+  for (int i = tid; i < T * H; i += nt) g_x0[i] = 0.f;
+  __syncthreads();
+  // GRU layers, back-propagation through time (both directions in parallel, steps in reverse order)
+  for (int layer = 1; layer >= 0; --layer) {
+    const int in_l = layer == 0 ? H : 2 * H;
+    const float* g_y = layer == 1 ? g_x2 : g_x1;       // gradient wrt this layer's outputs
+    float* g_in = layer == 1 ? g_x1 : g_x0;            // gradient wrt this layer's inputs (accumulated)
+    for (int i = tid; i < 2 * H; i += nt) hbuf[i] = 0.f;   // carried d loss / d h
+    __syncthreads();
+    for (int step = T - 1; step >= 0; --step) {
+      for (int i = tid; i < 2 * H; i += nt) {
+        const int dir = i / H, j = i - dir * H;
+        const int t = dir ? T - 1 - step : step;
+        const float* q = sv + (((layer * 2 + dir) * T + step) * 5) * H + j;
+        const float r = q[0], z = q[H], n = q[2 * H], hp = q[3 * H], ghn = q[4 * H];
+        const float gh_tot = hbuf[i] + g_y[t * 2 * H + dir * H + j];
+        const float g_an = gh_tot * (1.f - z) * (1.f - n * n);
+        const float g_ar = g_an * ghn * r * (1.f - r);
+        const float g_az = gh_tot * (hp - n) * z * (1.f - z);
+        float* a = gi + dir * 3 * H;
+        float* c = gh + dir * 3 * H;
+        a[j] = g_ar, a[H + j] = g_az, a[2 * H + j] = g_an;
+        c[j] = g_ar, c[H + j] = g_az, c[2 * H + j] = g_an * r;
+        hbuf[i] = gh_tot * z;                               // direct path to h_prev; the W_hh path is added below
+      }
+      __syncthreads();
+      for (int i = tid; i < 2 * H; i += nt) {               // d h_prev += W_hh^T g_gh
+        const int dir = i / H, j = i - dir * H;
+        const float* whh = w.gru[layer][dir][1];
+        const float* c = gh + dir * 3 * H;
+        float acc = 0.f;
+        for (int g = 0; g < 3 * H; ++g) acc = fmaf(whh[static_cast<long long>(g) * H + j], c[g], acc);
+        hbuf[i] += acc;
+      }
+      for (int i = tid; i < 2 * in_l; i += nt) {            // d x_t += W_ih^T g_gi (the two directions may hit the same t)
+        const int dir = i / in_l, k = i - dir * in_l;
+        const int t = dir ? T - 1 - step : step;
+        const float* wih = w.gru[layer][dir][0];
+        const float* a = gi + dir * 3 * H;
+        float acc = 0.f;
+        for (int g = 0; g < 3 * H; ++g) acc = fmaf(wih[static_cast<long long>(g) * in_l + k], a[g], acc);
+        atomicAdd(g_in + t * in_l + k, acc);
+      }
+      __syncthreads();
+    }
+  }
+  // separable convolution: x0[t][o] = pw_b[o] + sum_c pw_w[o][c] dw[c][8 t];  dw[c][t'] = dw_b[c] + sum_k dw_w[c][k] spec[c][2 t' + k]
+  for (int i = tid; i < in_size * T; i += nt) {
+    const int c = i / T, t = i - c * T;
+    float acc = 0.f;
+    for (int o = 0; o < H; ++o) acc = fmaf(w.pw_w[o * in_size + c], g_x0[t * H + o], acc);
+    g_dw[c * W1 + 8 * t] = acc;
+  }
+  float* gs = g_spec + static_cast<long long>(b) * in_size * Wf;
+  for (int i = tid; i < in_size * Wf; i += nt) gs[i] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < in_size * T * 5; i += nt) {       // windows of different t do not overlap (16 columns apart, 5 wide)
+    const int c = i / (T * 5), rem = i - c * T * 5, t = rem / 5, k = rem - t * 5;
+    gs[c * Wf + 16 * t + k] = w.dw_w[c * 5 + k] * g_dw[c * W1 + 8 * t];
+  }
+}
+
 // NCHW with C == 1 is already NHWC; this transposes (B, C, W) -> (B, W, C) for the M5 input when C > 1 (unused: C == 1)
 
 }  // namespace ap
@@ -1068,6 +1312,21 @@ static int forward_kws(ap_classifier_t h, const float* spec, float* out, int B, 
   return AP_OK;
 }
 
+static int vjp_kws(ap_classifier_t h, const float* spec, const float* g_out, float* g_spec, int B, int Wf, cudaStream_t st) {
+  const int I = h->cfg.kws_in_size, H = h->cfg.kws_hidden, K = h->cfg.num_classes;
+  AP_REQUIRE(Wf >= 5, "KWS: need at least 5 spectrogram frames (got %d)", Wf);
+  AP_REQUIRE(K <= 64, "KWS backward: at most 64 classes");
+  const int W1 = (Wf - 5) / 2 + 1, T = (W1 - 1) / 8 + 1;
+  AP_REQUIRE(T <= 6 * H, "KWS backward: spectrogram too long (%d frames)", Wf);   // g_att lives in a [2][3H] scratch row
+  const KwsScratch so = kws_scratch(I, W1, T, H, K);
+  const size_t need = static_cast<size_t>(B) * so.total * sizeof(float);
+  if (h->gbuf[0].bytes < need) AP_CUDA(h->gbuf[0].alloc(need));
+  const size_t smem = sizeof(float) * (2 * H + 2 * 2 * 3 * H + 64);
+  kws_vjp_kernel<<<B, 256, smem, st>>>(spec, Wf, I, H, K, h->kws, g_out, h->gbuf[0].as<float>(), g_spec);
+  AP_LAUNCH_CHECK();
+  return AP_OK;
+}
+
 extern "C" int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cfg* cfg, const float* const* weights,
                                     int n_weights, int device) {
   AP_REQUIRE(out && cfg && weights, "ap_classifier_create: null argument");
@@ -1114,14 +1373,15 @@ extern "C" int ap_classifier_forward(ap_classifier_t h, const float* input, floa
   }
 }
 
-// g_input = (d logits / d input)^T g_logits.  ResNeXt (the SC09 default victim, adaptive_attack_eval.py:21) and M5.
+// g_input = (d logits / d input)^T g_logits.  ResNeXt (the SC09 default victim, adaptive_attack_eval.py:21), M5 and RCNN_KWS.
 extern "C" int ap_classifier_vjp(ap_classifier_t h, const float* input, const float* g_logits, float* g_input, int B, int in_len,
                                  void* stream) {
   AP_REQUIRE(h && input && g_logits && g_input, "ap_classifier_vjp: null argument");
   AP_REQUIRE(B > 0, "ap_classifier_vjp: B must be positive");
-  if (h->cfg.kind != AP_CLS_RESNEXT && h->cfg.kind != AP_CLS_M5)
-    return fail(AP_ERR_STATE, "ap_classifier_vjp: the backward pass exists for ResNeXt and M5 only");
+  if (h->cfg.kind != AP_CLS_RESNEXT && h->cfg.kind != AP_CLS_M5 && h->cfg.kind != AP_CLS_KWS)
+    return fail(AP_ERR_STATE, "ap_classifier_vjp: the backward pass exists for ResNeXt, M5 and RCNN_KWS only");
   AP_CUDA(cudaSetDevice(h->device));
+  if (h->cfg.kind == AP_CLS_KWS) return vjp_kws(h, input, g_logits, g_input, B, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_M5) return vjp_m5(h, input, g_logits, g_input, B, in_len, static_cast<cudaStream_t>(stream));
   AP_REQUIRE(in_len == 32, "ap_classifier_vjp: ResNeXt input is (B, 1, 32, 32)");
   return vjp_resnext(h, input, g_logits, g_input, B, static_cast<cudaStream_t>(stream));

@@ -101,6 +101,22 @@ def main():
     out["m5_g_logp"] = gl5.numpy()
     out["m5_grad"] = g5.numpy()
 
+    # ---- RCNN_KWS (eval mode) on the reference's KWS mel features: g_spec for a seeded g_logp
+    import importlib.util
+    kspec = importlib.util.spec_from_file_location("rcnn_kws_model", os.path.join(REF, "audio_models", "RCNN_KWS", "model.py"))
+    kmod = importlib.util.module_from_spec(kspec)
+    kspec.loader.exec_module(kmod)
+    kws = kmod.KWSModel(in_size=32).eval()
+    kws.load_state_dict(to_torch_sd(synthetic.kws_state_dict(seed=0)))
+    with torch.no_grad():
+        spec_k = todb(mel_kws(xm))
+    skr = spec_k.clone().requires_grad_(True)
+    glk = torch.from_numpy(synthetic.host_noise((2, 4), 4253, 0))
+    (gk,) = torch.autograd.grad(kws(skr), skr, glk)
+    out["kws_in_spec"] = spec_k.numpy()
+    out["kws_g_logp"] = glk.numpy()
+    out["kws_grad"] = gk.numpy()
+
     # ---- end to end: d CrossEntropy(AcousticSystem(x), y) / d x through DDPM t*=2 -> mel -> ResNeXt, one 1 s clip
     from acoustic_system import AcousticSystem
     transform = lambda w: todb(mel_sc(w))

@@ -681,9 +681,20 @@ def test_resnext_vjp_vs_reference_autograd(ap, golden_grad, mode, monkeypatch):
     err = rel_l2(gs, golden_grad["resnext_grad"])
     print(f"ResNeXt gradient ({mode}): rel-L2 {err:.3e}")
     assert err < {"fp32": 1e-5, "tf32-bwd": 5e-3, "tf32": 1.5e-1}[mode]
+    rn = ap.ResNetClassifier(synthetic.resnet_state_dict(depth=34, seed=0), depth=34)
+    with pytest.raises(ap.AudioPureError):      # no backward pass for the ResNet family: refuse rather than drop the gradient
+        rn(torch.zeros(1, 1, 32, 32, device="cuda", requires_grad=True))
+
+
+def test_kws_vjp_vs_reference_autograd(ap, golden_grad):
+    """separable conv -> 2-layer bidirectional GRU -> additive attention -> log_softmax: back-propagation through time in one
+    CTA per sample vs autograd through the reference's KWSModel"""
     kws = ap.KWSClassifier(synthetic.kws_state_dict(seed=0))
-    with pytest.raises(ap.AudioPureError):      # no backward pass for KWS / ResNet: refuse rather than drop the gradient
-        kws(torch.zeros(1, 1, 32, 81, device="cuda", requires_grad=True))
+    spec = cuda(golden_grad["kws_in_spec"]).requires_grad_(True)
+    (gs,) = torch.autograd.grad(kws(spec), spec, cuda(golden_grad["kws_g_logp"]))
+    err = rel_l2(gs, golden_grad["kws_grad"])
+    print(f"RCNN_KWS gradient: rel-L2 {err:.3e}")
+    assert err < 1e-4
 
 
 def test_m5_vjp_vs_reference_autograd(ap, golden_grad):

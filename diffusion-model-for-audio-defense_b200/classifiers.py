@@ -127,6 +127,7 @@ class ResNeXtClassifier(_Classifier):
 
 class ResNetClassifier(_Classifier):
     """torchvision-style ResNet-18/34/50/101/152 with ``in_channels`` (models/resnet.py:103-220) on (B,1,32,32) input."""
+    differentiable = True
     LAYERS = {18: (False, (2, 2, 2, 2)), 34: (False, (3, 4, 6, 3)), 50: (True, (3, 4, 6, 3)), 101: (True, (3, 4, 23, 3)),
               152: (True, (3, 8, 36, 3))}
 

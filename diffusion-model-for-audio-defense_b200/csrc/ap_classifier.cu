@@ -319,6 +319,41 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const float* __restri
   }
 }
 
+// backward of MaxPool2d(3, 2, 1): each input position gathers the gradient of the (at most four) windows whose FIRST maximum
+// (row-major scan, like torch) it is
+__global__ void __launch_bounds__(256) maxpool3x3s2_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ in,
+                                                               float* __restrict__ g_in, int B, int H, int W, int Cc) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = static_cast<long long>(B) * H * W * Cc;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cc);
+    long long t = i / Cc;
+    const int iw = static_cast<int>(t % W);
+    t /= W;
+    const int ih = static_cast<int>(t % H);
+    const long long b = t / H;
+    float acc = 0.f;
+    for (int oh = (ih + 1) / 2 - 1; oh <= (ih + 1) / 2; ++oh) {       // windows with 2 oh - 1 <= ih <= 2 oh + 1
+      if (oh < 0 || oh >= Ho || ih < 2 * oh - 1 || ih > 2 * oh + 1) continue;
+      for (int ow = (iw + 1) / 2 - 1; ow <= (iw + 1) / 2; ++ow) {
+        if (ow < 0 || ow >= Wo || iw < 2 * ow - 1 || iw > 2 * ow + 1) continue;
+        float m = -INFINITY;
+        int ar = -1, as = -1;
+        for (int r = 0; r < 3; ++r)
+          for (int q = 0; q < 3; ++q) {
+            const int jh = 2 * oh + r - 1, jw = 2 * ow + q - 1;
+            if (jh < 0 || jh >= H || jw < 0 || jw >= W) continue;
+            const float v = in[((b * H + jh) * W + jw) * Cc + c];
+            if (v > m) m = v, ar = jh, as = jw;
+          }
+        if (ar == ih && as == iw) acc += g_out[((b * Ho + oh) * Wo + ow) * Cc + c];
+      }
+    }
+    g_in[i] = acc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- KWS (RCNN + attention)
 // One CTA per sample; everything lives in shared memory (W <= 512 spectrogram frames).
 struct KwsWeights {
@@ -717,8 +752,9 @@ struct ap_classifier_s {
   // ResNet family
   struct ResBlock {
     ConvLayer c1, c2, c3, down;
+    ConvLayer t_c1, t_c2, t_c3, t_down;   // data-gradient twins (backward pass)
     bool bottleneck = false, has_down = false;
-    int stride = 1, cout = 0;
+    int stride = 1, cout = 0, cin = 0, planes = 0;
   };
   std::vector<std::unique_ptr<ResBlock>> resblocks;
   // M5
@@ -1034,6 +1070,7 @@ static int create_resnet(ap_classifier_t h, const float* const* w, int n_weights
       inpl = planes * exp;
     }
   AP_REQUIRE(n_weights == expected, "ap_classifier_create: ResNet-%d expects %d weight tensors, got %d", c.depth, expected, n_weights);
+  h->stem.keep_host = true;
   int rc = h->stem.init(1, 64, 7, 7, 2, 3, 1, w[0], nullptr, w[1], w[2], w[3], w[4]);
   if (rc != AP_OK) return rc;
   int i = 5;
@@ -1042,7 +1079,8 @@ static int create_resnet(ap_classifier_t h, const float* const* w, int n_weights
     for (int b = 0; b < counts[l]; ++b) {
       auto blk = std::make_unique<ap_classifier_s::ResBlock>();
       const int planes = 64 << l, stride = (b == 0 && l > 0) ? 2 : 1;
-      blk->bottleneck = bott, blk->stride = stride, blk->cout = planes * exp;
+      blk->bottleneck = bott, blk->stride = stride, blk->cout = planes * exp, blk->cin = inpl, blk->planes = planes;
+      blk->c1.keep_host = blk->c2.keep_host = blk->c3.keep_host = blk->down.keep_host = true;
       if (bott) {
         rc = blk->c1.init(inpl, planes, 1, 1, 1, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
         if (rc == AP_OK) rc = blk->c2.init(planes, planes, 3, 3, stride, 1, 1, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9]);
@@ -1118,6 +1156,160 @@ static int forward_resnet(ap_classifier_t h, const float* spec, float* logits, i
     pool_fc_kernel<<<bn, 256, smem, st>>>(x, 1, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(), h->cfg.num_classes,
                                           logits + static_cast<size_t>(b0) * h->cfg.num_classes, 0);   // AvgPool2d(1) + fc, :156-158
     AP_LAUNCH_CHECK();
+  }
+  return AP_OK;
+}
+
+// ---- backward of the ResNet forward (autograd over models/resnet.py:140-160, BatchNorm in eval mode), fp32 on the FFMA path
+static int vjp_resnet(ap_classifier_t h, const float* spec, const float* g_logits, float* g_spec, int B, int H0, int W0,
+                      cudaStream_t st) {
+  auto half = [](int v) { return (v - 1) / 2 + 1; };
+  const int H1 = half(H0), W1 = half(W0), H2 = half(H1), W2 = half(W1);
+  AP_REQUIRE(H0 == 2 * H1 && W0 == 2 * W1 && half(half(half(H2))) == 1 && half(half(half(W2))) == 1,
+             "ResNet backward: input %dx%d does not reduce to 1x1 by exact halvings", H0, W0);
+  const int chunk = 64;
+  if (!h->bwd_ready) {
+    int rc = init_dgrad(h->t_stem, h->stem);
+    for (auto& b : h->resblocks) {
+      if (rc == AP_OK) rc = init_dgrad(b->t_c1, b->c1);
+      if (rc == AP_OK) rc = init_dgrad(b->t_c2, b->c2);
+      if (rc == AP_OK && b->bottleneck) rc = init_dgrad(b->t_c3, b->c3);
+      if (rc == AP_OK && b->has_down) rc = init_dgrad(b->t_down, b->down);
+    }
+    if (rc != AP_OK) return rc;
+    h->bwd_ready = true;
+  }
+  const int bn_max = std::min(B, chunk);
+  if (bn_max > h->bwd_bn) {
+    h->tape.clear();
+    size_t max_e = static_cast<size_t>(H0) * W0 * 64;    // the zero-upsampled stem gradient
+    AP_CUDA(h->tape_x0.alloc(static_cast<size_t>(bn_max) * H1 * W1 * 64 * sizeof(float)));     // stem conv + ReLU output
+    auto add = [&](size_t e) -> int {
+      auto d = std::make_unique<DevBuf>();
+      AP_CUDA(d->alloc(e * bn_max * sizeof(float)));
+      h->tape.push_back(std::move(d));
+      max_e = std::max(max_e, e);
+      return AP_OK;
+    };
+    int rc = add(static_cast<size_t>(H2) * W2 * 64);       // tape[0]: pooled stem output = input of the first block
+    int H = H2, W = W2;
+    for (auto& b : h->resblocks) {
+      const int Ho = (H - 1) / b->stride + 1, Wo = (W - 1) / b->stride + 1;
+      if (rc == AP_OK) rc = add(static_cast<size_t>(b->bottleneck ? H * W : Ho * Wo) * b->planes);     // c1 output
+      if (rc == AP_OK) rc = add(static_cast<size_t>(Ho) * Wo * b->planes);                              // c2 output (bottleneck)
+      if (rc == AP_OK) rc = add(static_cast<size_t>(Ho) * Wo * b->cout);                                // block output
+      max_e = std::max(max_e, static_cast<size_t>(H) * W * std::max(b->cin, std::max(b->cout, b->planes)));
+      if (rc != AP_OK) return rc;
+      H = Ho, W = Wo;
+    }
+    for (auto& g : h->gbuf) AP_CUDA(g.alloc(max_e * bn_max * sizeof(float)));
+    h->bwd_bn = bn_max;
+  }
+  auto grid_for = [](long long work) {
+    long long b = ceil_div_ll(work, 256);
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    return static_cast<unsigned>(b < cap ? (b > 0 ? b : 1) : cap);
+  };
+  int bn = 0;
+  auto mask = [&](float* g, const float* act, size_t elems) -> int {
+    relu_mask_kernel<<<grid_for(static_cast<long long>(elems / 4)), 256, 0, st>>>(reinterpret_cast<float4*>(g),
+                                                                                  reinterpret_cast<const float4*>(act),
+                                                                                  static_cast<long long>(elems / 4));
+    AP_LAUNCH_CHECK();
+    return AP_OK;
+  };
+  auto upsample = [&](const float* g, float* up, int Ho, int Wo, int Cc) -> int {
+    upsample2_kernel<<<grid_for(static_cast<long long>(bn) * 4 * Ho * Wo * (Cc / 4)), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(up), bn, Ho, Wo, Cc / 4);
+    AP_LAUNCH_CHECK();
+    return AP_OK;
+  };
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    bn = std::min(chunk, B - b0);
+    // ---- forward with the tape
+    float* y1s = h->tape_x0.as<float>();
+    int rc = h->stem.run(spec + static_cast<size_t>(b0) * H0 * W0, bn, H0, W0, y1s, nullptr, 1, st);
+    if (rc != AP_OK) return rc;
+    float* x = h->tape[0]->as<float>();
+    maxpool3x3s2_kernel<<<grid_for(static_cast<long long>(bn) * H2 * W2 * 64), 256, 0, st>>>(y1s, x, bn, H1, W1, 64);
+    AP_LAUNCH_CHECK();
+    int H = H2, W = W2;
+    for (size_t i = 0; i < h->resblocks.size(); ++i) {
+      auto& b = *h->resblocks[i];
+      float *a1 = h->tape[1 + 3 * i]->as<float>(), *a2 = h->tape[2 + 3 * i]->as<float>(), *y = h->tape[3 + 3 * i]->as<float>();
+      const int Ho = (H - 1) / b.stride + 1, Wo = (W - 1) / b.stride + 1;
+      const float* res = x;
+      if (b.has_down) {
+        rc = b.down.run(x, bn, H, W, h->gbuf[4].as<float>(), nullptr, 0, st);
+        if (rc != AP_OK) return rc;
+        res = h->gbuf[4].as<float>();
+      }
+      if (b.bottleneck) {
+        rc = b.c1.run(x, bn, H, W, a1, nullptr, 1, st);
+        if (rc == AP_OK) rc = b.c2.run(a1, bn, H, W, a2, nullptr, 1, st);
+        if (rc == AP_OK) rc = b.c3.run(a2, bn, Ho, Wo, y, res, 1, st);
+      } else {
+        rc = b.c1.run(x, bn, H, W, a1, nullptr, 1, st);
+        if (rc == AP_OK) rc = b.c2.run(a1, bn, Ho, Wo, y, res, 1, st);
+      }
+      if (rc != AP_OK) return rc;
+      x = y, H = Ho, W = Wo;
+    }
+    // ---- backward
+    float *GA = h->gbuf[0].as<float>(), *GB = h->gbuf[1].as<float>(), *GC = h->gbuf[2].as<float>(), *GD = h->gbuf[3].as<float>(),
+          *GE = h->gbuf[4].as<float>();
+    pool_fc_bwd_kernel<<<bn, 256, 0, st>>>(g_logits + static_cast<size_t>(b0) * h->cfg.num_classes, h->fc_w.as<float>(),
+                                           h->cfg.num_classes, h->feat, H * W, GA);
+    AP_LAUNCH_CHECK();
+    for (int i = static_cast<int>(h->resblocks.size()) - 1; i >= 0; --i) {
+      auto& b = *h->resblocks[i];
+      const float *a1 = h->tape[1 + 3 * i]->as<float>(), *a2 = h->tape[2 + 3 * i]->as<float>(), *y = h->tape[3 + 3 * i]->as<float>();
+      const int Ho = H, Wo = W, Hi = H * b.stride, Wi = W * b.stride;
+      const size_t npo = static_cast<size_t>(bn) * Ho * Wo, npi = static_cast<size_t>(bn) * Hi * Wi;
+      rc = mask(GA, y, npo * b.cout);
+      const float* res = GA;                                    // identity shortcut
+      if (rc == AP_OK && b.has_down) {                          // shortcut path first: it borrows GC for the upsampled gradient
+        const float* ssrc = GA;
+        if (b.stride == 2) {
+          rc = upsample(GA, GC, Ho, Wo, b.cout);
+          ssrc = GC;
+        }
+        if (rc == AP_OK) rc = b.t_down.run(ssrc, bn, Hi, Wi, GE, nullptr, 0, st);
+        res = GE;
+      }
+      if (b.bottleneck) {
+        if (rc == AP_OK) rc = b.t_c3.run(GA, bn, Ho, Wo, GB, nullptr, 0, st);
+        if (rc == AP_OK) rc = mask(GB, a2, npo * b.planes);
+        const float* src = GB;
+        if (rc == AP_OK && b.stride == 2) {
+          rc = upsample(GB, GC, Ho, Wo, b.planes);
+          src = GC;
+        }
+        if (rc == AP_OK) rc = b.t_c2.run(src, bn, Hi, Wi, GD, nullptr, 0, st);
+        if (rc == AP_OK) rc = mask(GD, a1, npi * b.planes);
+        if (rc == AP_OK) rc = b.t_c1.run(GD, bn, Hi, Wi, GB, res, 0, st);
+      } else {
+        if (rc == AP_OK) rc = b.t_c2.run(GA, bn, Ho, Wo, GB, nullptr, 0, st);
+        if (rc == AP_OK) rc = mask(GB, a1, npo * b.planes);
+        const float* src = GB;
+        if (rc == AP_OK && b.stride == 2) {
+          rc = upsample(GB, GC, Ho, Wo, b.planes);
+          src = GC;
+        }
+        if (rc == AP_OK) rc = b.t_c1.run(src, bn, Hi, Wi, GD, res, 0, st);
+        if (rc == AP_OK) std::swap(GB, GD);                     // the block's input gradient is in GB either way
+      }
+      if (rc != AP_OK) return rc;
+      std::swap(GA, GB);
+      H = Hi, W = Wi;
+    }
+    // stem: max-pool, ReLU, 7x7 stride-2 convolution
+    maxpool3x3s2_bwd_kernel<<<grid_for(static_cast<long long>(bn) * H1 * W1 * 64), 256, 0, st>>>(GA, y1s, GB, bn, H1, W1, 64);
+    AP_LAUNCH_CHECK();
+    rc = mask(GB, y1s, static_cast<size_t>(bn) * H1 * W1 * 64);
+    if (rc == AP_OK) rc = upsample(GB, GC, H1, W1, 64);
+    if (rc == AP_OK) rc = h->t_stem.run(GC, bn, H0, W0, g_spec + static_cast<size_t>(b0) * H0 * W0, nullptr, 0, st);
+    if (rc != AP_OK) return rc;
   }
   return AP_OK;
 }
@@ -1378,9 +1570,8 @@ extern "C" int ap_classifier_vjp(ap_classifier_t h, const float* input, const fl
                                  void* stream) {
   AP_REQUIRE(h && input && g_logits && g_input, "ap_classifier_vjp: null argument");
   AP_REQUIRE(B > 0, "ap_classifier_vjp: B must be positive");
-  if (h->cfg.kind != AP_CLS_RESNEXT && h->cfg.kind != AP_CLS_M5 && h->cfg.kind != AP_CLS_KWS)
-    return fail(AP_ERR_STATE, "ap_classifier_vjp: the backward pass exists for ResNeXt, M5 and RCNN_KWS only");
   AP_CUDA(cudaSetDevice(h->device));
+  if (h->cfg.kind == AP_CLS_RESNET) return vjp_resnet(h, input, g_logits, g_input, B, in_len, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_KWS) return vjp_kws(h, input, g_logits, g_input, B, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_M5) return vjp_m5(h, input, g_logits, g_input, B, in_len, static_cast<cudaStream_t>(stream));
   AP_REQUIRE(in_len == 32, "ap_classifier_vjp: ResNeXt input is (B, 1, 32, 32)");

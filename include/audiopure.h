@@ -196,7 +196,7 @@ int ap_classifier_forward(ap_classifier_t h, const float* input, float* logits, 
 /* Vector-Jacobian product wrt the input: g_input = (d logits / d input)^T g_logits, what autograd computes through
  * CifarResNeXt.forward (models/resnext.py:134-142) or M5.forward (audio_models/M5/M5Net.py:21-38), BatchNorm in eval mode,
  * or KWSModel.forward (audio_models/RCNN_KWS/model.py:90-113), when an attack back-propagates the loss
- * (robustness_eval/white_box_attack.py:438).  ResNeXt, M5 and RCNN_KWS; the forward is recomputed with what the backward needs
+ * (robustness_eval/white_box_attack.py:438).  Every classifier kind; the forward is recomputed with what the backward needs
  * kept (ReLU outputs / GRU gate values).  input, g_input: device (B, 1, 32, 32), (B, L) or (B, 32, W);
  * g_logits: device (B, num_classes). */
 int ap_classifier_vjp(ap_classifier_t h, const float* input, const float* g_logits, float* g_input, int B, int in_len,

@@ -90,6 +90,15 @@ def main():
     out["resnext_g_logits"] = gl.numpy()
     out["resnext_grad"] = gs.numpy()
 
+    # ---- ResNet family (BasicBlock and Bottleneck variants, eval mode) on the same mel features
+    from models.resnet import resnet34, resnet50
+    for depth, ctor in ((34, resnet34), (50, resnet50)):
+        rn = ctor(num_classes=10, in_channels=1).eval()
+        rn.load_state_dict(to_torch_sd(synthetic.resnet_state_dict(depth=depth, seed=0)))
+        sr = spec0.clone().requires_grad_(True)
+        (gr,) = torch.autograd.grad(rn(sr), sr, gl)
+        out[f"resnet{depth}_grad"] = gr.numpy()
+
     # ---- M5 raw-waveform classifier (eval mode): g_wav for a seeded g_logp
     sys.path.insert(0, os.path.join(REF, "audio_models", "M5"))
     from M5Net import M5

@@ -681,9 +681,16 @@ def test_resnext_vjp_vs_reference_autograd(ap, golden_grad, mode, monkeypatch):
     err = rel_l2(gs, golden_grad["resnext_grad"])
     print(f"ResNeXt gradient ({mode}): rel-L2 {err:.3e}")
     assert err < {"fp32": 1e-5, "tf32-bwd": 5e-3, "tf32": 1.5e-1}[mode]
-    rn = ap.ResNetClassifier(synthetic.resnet_state_dict(depth=34, seed=0), depth=34)
-    with pytest.raises(ap.AudioPureError):      # no backward pass for the ResNet family: refuse rather than drop the gradient
-        rn(torch.zeros(1, 1, 32, 32, device="cuda", requires_grad=True))
+
+
+@pytest.mark.parametrize("depth", [34, 50])
+def test_resnet_vjp_vs_reference_autograd(ap, golden_grad, depth):
+    rn = ap.ResNetClassifier(synthetic.resnet_state_dict(depth=depth, seed=0), depth=depth)
+    spec = cuda(golden_grad["resnext_in_spec"]).requires_grad_(True)
+    (gs,) = torch.autograd.grad(rn(spec), spec, cuda(golden_grad["resnext_g_logits"]))
+    err = rel_l2(gs, golden_grad[f"resnet{depth}_grad"])
+    print(f"ResNet-{depth} gradient: rel-L2 {err:.3e}")
+    assert err < 1e-4
 
 
 def test_kws_vjp_vs_reference_autograd(ap, golden_grad):

@@ -302,6 +302,15 @@ __device__ __forceinline__ float tanh_exp(float x) {
   const float e = __expf(2.f * fminf(fmaxf(x, -40.f), 40.f));
   return 1.f - __fdividef(2.f, 1.f + e);
 }
+// tanh(a) * sigmoid(s) with one reciprocal: (E - 1) / ((E + 1)(1 + F)), E = e^{2a}, F = e^{-s}.  a is clamped above so
+// that E + 1 stays finite; E -> 0 gives -1 / (1 + F), F -> inf gives 0.  Absolute error ~2e-7 (checked against float64).
+__device__ __forceinline__ float gate_exp(float a, float s) {
+  float E, F, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E) : "f"(fminf(a, 20.f) * 2.885390081777927f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(F) : "f"(s * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((E + 1.f) * (1.f + F)));
+  return (E - 1.f) * r;
+}
 __device__ __forceinline__ float sigmoid_exp(float x) {
   return __fdividef(1.f, 1.f + __expf(-fminf(fmaxf(x, -80.f), 80.f)));
 }

@@ -61,16 +61,19 @@ template <int CG_, int KIND, int DT_ = 0> struct Geo {
   static constexpr int B_ROWS = 256 / CG;
   static constexpr int B_BYTES = B_ROWS * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = CG == 1 ? (SPLIT ? 2 : 3) : (SPLIT ? 3 : 5);
+  // bf16x3: k2_head stages both planes of the skip sum (128 KB, 3-stage ring); k1_split issues GEMM-2 in two K halves through
+  // one 64 KB tile and keeps the 5-stage ring
+  static constexpr bool WIDE_STAGING = SPLIT && KIND == 2;
+  static constexpr int NSTAGE = CG == 1 ? (SPLIT ? 2 : 3) : (WIDE_STAGING ? 3 : 5);
   static constexpr int OUT_OFF = NSTAGE * STAGE_BYTES;
-  static constexpr int BIAS_OFF = OUT_OFF + (SPLIT ? 2 : 1) * OUT_BYTES;
+  static constexpr int BIAS_OFF = OUT_OFF + (WIDE_STAGING || (SPLIT && CG == 1) ? 2 : 1) * OUT_BYTES;
   static constexpr int BAR_OFF = BIAS_OFF + 1024;   // k1: c2[256]; k2: 128 partial dots
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + slack to align the base to 1024 B
   static constexpr uint32_t IDESC = DT_ == 1 ? umma_idesc_f16_f32(128 * CG, 256) : umma_idesc_bf16_f32(128 * CG, 256);
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
   static_assert(NSTAGE <= 5, "barrier table holds at most 5 stages");
 };
-enum { BAR_FULL = 0, BAR_EMPTY = 5, BAR_ACC_FULL = 10, BAR_ACC_EMPTY = 12, BAR_OUT_READY = 14, BAR_COUNT = 16 };
+enum { BAR_FULL = 0, BAR_EMPTY = 5, BAR_ACC_FULL = 10, BAR_ACC_EMPTY = 12, BAR_OUT_READY = 14, BAR_G2A_DONE = 16, BAR_COUNT = 17 };
 
 // position in the TMA ring: stage index and phase parity (no division in the producer / MMA-issue loops)
 template <int NSTAGE> struct RingPos {
@@ -147,6 +150,7 @@ template <class G> __device__ __forceinline__ uint32_t tc_prologue(Ctx<G>& cx, u
       mbar_init(cx.bar(BAR_ACC_EMPTY + i), 8 * CG);
     }
     for (int i = 0; i < 2; ++i) mbar_init(cx.bar(BAR_OUT_READY + i), out_ready_count * CG);
+    mbar_init(cx.bar(BAR_G2A_DONE), 1);   // k1_split: first half of GEMM-2 done
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -186,6 +190,7 @@ struct K1Params {
   const float* p_next;  // [256]
   const uint16_t* u_in; // [chunk][L][256] this layer's input (also read through tmUin as the GEMM-1 A operand)
   uint16_t* u_out;      // [chunk][L][256] next layer's input
+  uint16_t* o_out;      // k1_split: [2 planes][N][chunk][L][256] gate outputs (written from registers)
   uint16_t* ts_out;     // SAVE kernels (backward pass): [N][ts_chunk][L][512] bf16, the gate's local derivatives
                         // d o / d a_t | d o / d a_s of every layer
   int ts_chunk;
@@ -544,6 +549,298 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
     setmaxnreg_inc<200>();
     if (((warp - EPI_WARP0) >> 2) == 0) k1_epilogue<G, 0, SAVE>(cx, p, tmem, tiles, &tmO, c2_addr);
     else k1_epilogue<G, 1, SAVE>(cx, p, tmem, tiles, &tmO, c2_addr);
+  }
+  tc_epilogue_teardown<CG>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------ k1 for the bf16x3 mode
+// Same math as k1_layer with three MMAs per K step (Geo::NCOMBO) and both bf16 planes of every tensor.  Keeping o_hi AND o_lo
+// of a whole tile staged for GEMM-2 would cost 128 KB of shared memory (a 3-stage ring); instead GEMM-2 is issued in two
+// K halves -- G2a after the gate epilogue of chunk 0 (o channels 0..127), G2b after chunk 1 -- through one 64 KB staging
+// tile (hi K-blocks in slots 0-1, lo in 2-3), which leaves the 5-stage ring of the bf16 kernel.  TMEM region X (columns
+// 0..255) holds the GEMM-2 accumulator across both halves, region Y (256..511) every GEMM-1 chunk in turn (the gate epilogue
+// frees it as soon as the accumulators are in registers).  Job order of the MMA warp per tile t:
+//   G1c0(t) -> Y | G2b(t-1) -> X | G1c1(t) -> Y | G2a(t) -> X          epilogue: gate c0(t), residual(t-1), gate c1(t)
+static_assert(BAR_COUNT * 8 + 8 <= 256, "barrier area");
+
+template <class G, int HSEL, bool SAVE>
+__device__ __forceinline__ void k1s_epilogue(const Ctx<G>& cx, const K1Params& p, const uint32_t tmem, const Tiles<G::CG>& tiles,
+                                             const uint32_t c2_addr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q4 = warp & 3, etid = threadIdx.x - EPI_WARP0 * 32;
+  const int row = q4 * 32 + lane;
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+  const uint32_t row_off = row * 128, sw = row & 7;
+  const float sqrt_half = 0.70710678118654752440f;
+  const int oob_l0 = p.tiles_per_sample * TILE_M;
+  const size_t lo_u = static_cast<size_t>(p.u_plane) * p.L * C, lo_o = static_cast<size_t>(p.o_plane) * p.L * C;
+  uint32_t k = 0;   // gate jobs done (phase of the Y-region barriers)
+
+  auto gate = [&](auto jc, uint32_t ti, bool valid, int b, int l0) {
+    constexpr int J = decltype(jc)::value;
+    mbar_wait(cx.bar(BAR_ACC_FULL + 1), k & 1, 70);
+    tc_fence_after();
+    uint32_t ta[2][32], sg[2][32];
+#pragma unroll
+    for (int gq = 0; gq < 2; ++gq) {
+      tmem_ld_32x32b_x32(lane_addr + 256 + HSEL * 64 + gq * 32, ta[gq]);
+      tmem_ld_32x32b_x32(lane_addr + 256 + 128 + HSEL * 64 + gq * 32, sg[gq]);
+    }
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 1);
+    const bool live = valid && l0 + row < p.L;
+    const size_t pos = static_cast<size_t>(b) * p.L + (live ? l0 + row : 0);
+    uint32_t pk[2][4][4], pl[2][4][4], tsk[2][4];
+#pragma unroll
+    for (int gq = 0; gq < 2; ++gq)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c0 = i * 8 + 2 * e;
+          const int cb = J * 256 + HSEL * 64 + gq * 32 + c0;
+          // fp32-class gate (MUFU.TANH is good to ~2^-11 only); p.bd holds HALF the sigmoid bias
+          const float a0 = __uint_as_float(ta[gq][c0]) + p.bd[cb], a1 = __uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1];
+          const float s0 = fmaf(2.f, p.bd[cb + 128], __uint_as_float(sg[gq][c0]));
+          const float s1 = fmaf(2.f, p.bd[cb + 129], __uint_as_float(sg[gq][c0 + 1]));
+          float o0, o1;
+          if constexpr (SAVE) {   // tanh and sigmoid separately: the backward pass keeps the gate's local derivatives
+            const float t0 = tanh_exp(a0), t1 = tanh_exp(a1), g0 = sigmoid_exp(s0), g1 = sigmoid_exp(s1);
+            o0 = t0 * g0, o1 = t1 * g1;
+            tsk[0][e] = pack_bf16x2(g0 * fmaf(-t0, t0, 1.f), g1 * fmaf(-t1, t1, 1.f));
+            tsk[1][e] = pack_bf16x2(t0 * g0 * (1.f - g0), t1 * g1 * (1.f - g1));
+          } else {                // one quotient: tanh(a) sigmoid(s) = (E - 1) / ((E + 1)(1 + F)), E = e^{2a}, F = e^{-s}
+            o0 = gate_exp(a0, s0), o1 = gate_exp(a1, s1);
+          }
+          const uint32_t hi = pack_bf16x2(o0, o1);
+          pk[gq][i][e] = hi;
+          pl[gq][i][e] = pack_bf16x2(o0 - bf16_lo(hi), o1 - bf16_hi(hi));
+        }
+        if constexpr (SAVE) {
+          if (live) {
+            uint16_t* td = p.ts_out + ((static_cast<size_t>(p.layer) * p.ts_chunk + b) * p.L + l0 + row) * 512 + J * 128 + HSEL * 64 +
+                           gq * 32 + i * 8;
+            st_global_v4(td, make_uint4(tsk[0][0], tsk[0][1], tsk[0][2], tsk[0][3]));
+            st_global_v4(td + 256, make_uint4(tsk[1][0], tsk[1][1], tsk[1][2], tsk[1][3]));
+          }
+        }
+      }
+    // O (both planes) straight from registers: 4 x 32 bytes per thread and plane
+    if (live) {
+      uint16_t* od = p.o_out + (static_cast<size_t>(p.layer) * p.chunk_alloc * p.L + pos) * C + J * 128 + HSEL * 64;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const uint32_t (&q0)[4] = pk[v >> 1][(v & 1) * 2], (&q1)[4] = pk[v >> 1][(v & 1) * 2 + 1];
+        const uint32_t h8[8] = {q0[0], q0[1], q0[2], q0[3], q1[0], q1[1], q1[2], q1[3]};
+        st_global_v8(od + v * 16, h8);
+        const uint32_t (&r0)[4] = pl[v >> 1][(v & 1) * 2], (&r1)[4] = pl[v >> 1][(v & 1) * 2 + 1];
+        const uint32_t l8[8] = {r0[0], r0[1], r0[2], r0[3], r1[0], r1[1], r1[2], r1[3]};
+        st_global_v8(od + lo_o + v * 16, l8);
+      }
+    }
+    if (!p.last) {
+      // the staging tile is free once the GEMM-2 half that read it has completed: G2b of the previous tile before chunk 0,
+      // G2a of this tile before chunk 1
+      if (J == 0) {
+        if (ti > 0) mbar_wait(cx.bar(BAR_ACC_FULL + 0), (ti - 1) & 1, 71);
+      } else {
+        mbar_wait(cx.bar(BAR_G2A_DONE), ti & 1, 72);
+      }
+      tc_fence_after();
+      const uint32_t hi_base = cx.out_kb(HSEL) + row_off, lo_base = cx.out_kb(2 + HSEL) + row_off;
+#pragma unroll
+      for (int gq = 0; gq < 2; ++gq)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          st_shared_v4(hi_base + (((gq * 4 + i) ^ sw) << 4), make_uint4(pk[gq][i][0], pk[gq][i][1], pk[gq][i][2], pk[gq][i][3]));
+          st_shared_v4(lo_base + (((gq * 4 + i) ^ sw) << 4), make_uint4(pl[gq][i][0], pl[gq][i][1], pl[gq][i][2], pl[gq][i][3]));
+        }
+      fence_proxy_async_smem();
+      named_bar_sync(1, EPI_THREADS);
+      if (etid == 0) cx.arrive_leader(BAR_OUT_READY + J);
+    }
+    ++k;
+  };
+
+  auto residual = [&](uint32_t t_idx, bool valid, int b, int l0) {
+    const bool live = valid && l0 + row < p.L;
+    const size_t goff = (static_cast<size_t>(b) * p.L + (live ? l0 + row : 0)) * C + HSEL * 128;
+    mbar_wait(cx.bar(BAR_ACC_FULL + 0), t_idx & 1, 73);
+    tc_fence_after();
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(lane_addr + HSEL * 128 + gq * 32, acc);
+      tmem_ld_wait();
+      if (gq == 3) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 0);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int ch = HSEL * 128 + gq * 32 + i * 16;
+        uint32_t pk[8], pl[8], uh[8], ul[8];
+        if (live) {
+          ld_global_v8(p.u_in + goff + (gq * 2 + i) * 16, uh);
+          ld_global_v8(p.u_in + lo_u + goff + (gq * 2 + i) * 16, ul);
+        }
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const uint4 cv = ld_shared_v4(c2_addr + (ch + e4 * 4) * 4);
+          const float cc[4] = {__uint_as_float(cv.x), __uint_as_float(cv.y), __uint_as_float(cv.z), __uint_as_float(cv.w)};
+          const int a0 = i * 16 + e4 * 4;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float u0 = bf16_lo(uh[e4 * 2 + h]) + bf16_lo(ul[e4 * 2 + h]);
+            const float u1 = bf16_hi(uh[e4 * 2 + h]) + bf16_hi(ul[e4 * 2 + h]);
+            const float v0 = fmaf(u0 + __uint_as_float(acc[a0 + 2 * h]), sqrt_half, cc[2 * h]);
+            const float v1 = fmaf(u1 + __uint_as_float(acc[a0 + 2 * h + 1]), sqrt_half, cc[2 * h + 1]);
+            const uint32_t hi = pack_bf16x2(v0, v1);
+            pk[e4 * 2 + h] = hi;
+            pl[e4 * 2 + h] = pack_bf16x2(v0 - bf16_lo(hi), v1 - bf16_hi(hi));
+          }
+        }
+        if (live) {
+          st_global_v8(p.u_out + goff + (gq * 2 + i) * 16, pk);
+          st_global_v8(p.u_out + lo_u + goff + (gq * 2 + i) * 16, pl);
+        }
+      }
+    }
+  };
+
+  uint32_t ti = 0;
+  bool pvalid = false;
+  int pb = 0, pl0 = 0;
+  for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+    const bool valid = tile < p.n_tiles;
+    const int b = valid ? tile / p.tiles_per_sample : 0;
+    const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+    gate(std::integral_constant<int, 0>{}, ti, valid, b, l0);
+    if (!p.last && ti > 0) residual(ti - 1, pvalid, pb, pl0);
+    gate(std::integral_constant<int, 1>{}, ti, valid, b, l0);
+    pvalid = valid, pb = b, pl0 = l0;
+  }
+  if (!p.last && ti > 0) residual(ti - 1, pvalid, pb, pl0);
+}
+
+template <bool SAVE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k1_split(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUtensorMap tmWd,
+         const __grid_constant__ CUtensorMap tmWr, const __grid_constant__ K1Params p) {
+  using G = Geo<2, 1, 2>;
+  constexpr int CG = 2;
+  Ctx<G> cx;
+  uint8_t* gen;
+  const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
+  {
+    float* s_c2 = reinterpret_cast<float*>(gen + G::BIAS_OFF);
+    for (int i = threadIdx.x; i < C; i += NTHREADS) s_c2[i] = fmaf(p.b_res[i], 0.70710678118654752440f, p.p_next[i]);
+  }
+  if (threadIdx.x == 0) prefetch_tmap(&tmUin), prefetch_tmap(&tmWd), prefetch_tmap(&tmWr);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  const Tiles<CG> tiles(p.n_tiles, cx.rank);
+  const int oob_l0 = p.tiles_per_sample * TILE_M;
+
+  if (warp < EPI_WARP0) setmaxnreg_dec<96>();
+  if (warp == 0) {
+    // ======================================================================================= TMA producer
+    RingPos<G::NSTAGE> it;
+    uint32_t ti = 0;
+    auto load_g1 = [&](int j, bool valid, int b, int l0) {
+      for (int tap = 0; tap < 3; ++tap)
+        for (int kb = 0; kb < 4; ++kb)
+          for (int cmb = 0; cmb < 3; ++cmb, ++it) {
+            const uint32_t s = it.s, ph = it.ph;
+            cx.wait_empty(s, ph, 74);
+            if (elect_one()) {
+              cx.arm(s, G::STAGE_BYTES);
+              cx.load_a(s, &tmUin, kb * 64, valid ? l0 + (tap - 1) * p.dilation : oob_l0, b + (cmb == 1 ? p.u_plane : 0));
+              cx.load_b(s, &tmWd, tap * C + kb * 64, (p.layer * 2 + j) * 256 + (cmb == 2 ? p.wd_plane : 0));
+            }
+            __syncwarp();
+          }
+    };
+    auto load_wr = [&](int pass) {   // res-conv weights of K-blocks 2 pass, 2 pass + 1
+      for (int kbp = 0; kbp < 2; ++kbp)
+        for (int cmb = 0; cmb < 3; ++cmb, ++it) {
+          const uint32_t s = it.s, ph = it.ph;
+          cx.wait_empty(s, ph, 75);
+          if (elect_one()) {
+            cx.arm(s, G::B_BYTES);
+            cx.load_b(s, &tmWr, (pass * 2 + kbp) * 64, p.layer * 256 + (cmb == 2 ? p.wr_plane : 0));
+          }
+          __syncwarp();
+        }
+    };
+    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+      const bool valid = tile < p.n_tiles;
+      const int b = valid ? tile / p.tiles_per_sample : 0;
+      const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+      load_g1(0, valid, b, l0);
+      if (!p.last && ti > 0) load_wr(1);
+      load_g1(1, valid, b, l0);
+      if (!p.last) load_wr(0);
+    }
+    if (!p.last && ti > 0) load_wr(1);
+  } else if (warp == 1) {
+    // ======================================================================================= MMA issuer (leader CTA)
+    if (cx.rank == 0) {
+      RingPos<G::NSTAGE> it;
+      uint32_t k = 0, ti = 0;
+      auto gemm1 = [&]() {
+        mbar_wait(cx.bar(BAR_ACC_EMPTY + 1), (k & 1) ^ 1, 76);
+        tc_fence_after();
+        for (int kblk = 0; kblk < 36; ++kblk, ++it) {
+          const uint32_t s = it.s, ph = it.ph;
+          mbar_wait(cx.bar(BAR_FULL + s), ph, 77);
+          tc_fence_after();
+          if (elect_one()) {
+            cx.mma_kblock(tmem + 256, cx.stage_a(s), cx.stage_b(s), kblk == 0);
+            cx.commit(BAR_EMPTY + s);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) cx.commit(BAR_ACC_FULL + 1);
+        __syncwarp();
+        ++k;
+      };
+      auto gemm2_half = [&](uint32_t t_idx, int pass) {
+        if (pass == 0) {   // a new accumulation: region X must have been drained by the residual epilogue of tile t-1
+          mbar_wait(cx.bar(BAR_ACC_EMPTY + 0), (t_idx & 1) ^ 1, 78);
+        }
+        mbar_wait(cx.bar(BAR_OUT_READY + pass), t_idx & 1, 79);
+        tc_fence_after();
+        for (int kbp = 0; kbp < 2; ++kbp)
+          for (int cmb = 0; cmb < 3; ++cmb, ++it) {
+            const uint32_t s = it.s, ph = it.ph;
+            mbar_wait(cx.bar(BAR_FULL + s), ph, 80);
+            tc_fence_after();
+            if (elect_one()) {
+              cx.mma_kblock(tmem, cx.out_kb((cmb == 1 ? 2 : 0) + kbp), cx.stage_b(s), pass == 0 && kbp == 0 && cmb == 0);
+              cx.commit(BAR_EMPTY + s);
+            }
+            __syncwarp();
+          }
+        if (elect_one()) cx.commit(pass == 0 ? BAR_G2A_DONE : BAR_ACC_FULL + 0);
+        __syncwarp();
+      };
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+        gemm1();
+        if (!p.last && ti > 0) gemm2_half(ti - 1, 1);
+        gemm1();
+        if (!p.last) gemm2_half(ti, 0);
+      }
+      if (!p.last && ti > 0) gemm2_half(ti - 1, 1);
+    }
+  } else if (warp >= EPI_WARP0) {
+    setmaxnreg_inc<200>();
+    const uint32_t c2_addr = cx.base + G::BIAS_OFF;
+    if (((warp - EPI_WARP0) >> 2) == 0) k1s_epilogue<G, 0, SAVE>(cx, p, tmem, tiles, c2_addr);
+    else k1s_epilogue<G, 1, SAVE>(cx, p, tmem, tiles, c2_addr);
   }
   tc_epilogue_teardown<CG>(tmem);
 }
@@ -1362,7 +1659,7 @@ int tc_net_reserve(TcNet* n, int chunk, int L) {
     AP_CUDA(cudaFuncSetAttribute(k2_head<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k2_head<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
-    AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_split<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k2_head<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2, 2>::SMEM_BYTES));
     n->attr_set = true;
   }
@@ -1413,6 +1710,7 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     p.chunk_alloc = n->chunk, p.last = (l == n->N - 1), p.L = L;
     p.u_in = (l & 1) ? n->u1.as<uint16_t>() : n->u0.as<uint16_t>();
     p.u_out = (l & 1) ? n->u0.as<uint16_t>() : n->u1.as<uint16_t>();
+    p.o_out = n->o.as<uint16_t>();
     std::memcpy(p.bd, n->bd_host.data() + static_cast<size_t>(l) * 512, sizeof(p.bd));
     p.b_res = n->br.as<float>() + static_cast<size_t>(l) * C;
     p.p_next = ptab + static_cast<size_t>(l + 1) * C;
@@ -1424,11 +1722,11 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     if (e1) cudaEventRecord(e0, st);
     const CUtensorMap& ui = n->tmU[l & 1];
     if (save && n->dt == 2)
-      AP_CUDA(launch_pair(k1_layer<2, 2, true>, pair_grid(n_tiles), Geo<2, 1, 2>::SMEM_BYTES, st, ui, n->tmO, n->tmWd_s, n->tmWr_s, p));
+      AP_CUDA(launch_pair(k1_split<true>, pair_grid(n_tiles), Geo<2, 1, 2>::SMEM_BYTES, st, ui, n->tmWd_s, n->tmWr_s, p));
     else if (save)
       AP_CUDA(launch_pair(k1_layer<2, 0, true>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2, n->tmWr2, p));
     else if (n->dt == 2)
-      AP_CUDA(launch_pair(k1_layer<2, 2>, pair_grid(n_tiles), Geo<2, 1, 2>::SMEM_BYTES, st, ui, n->tmO, n->tmWd_s, n->tmWr_s, p));
+      AP_CUDA(launch_pair(k1_split<false>, pair_grid(n_tiles), Geo<2, 1, 2>::SMEM_BYTES, st, ui, n->tmWd_s, n->tmWr_s, p));
     else if (n->pair && n->dt == 0)
       AP_CUDA(launch_pair(k1_layer<2, 0>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2, n->tmWr2, p));
     else if (n->pair)
@@ -1515,7 +1813,7 @@ static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
     AP_CUDA(cudaFuncSetAttribute(k_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k2_head<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
-    AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k1_split<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k2_head<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2, 2>::SMEM_BYTES));
     n->bwd_attr = true;
   }

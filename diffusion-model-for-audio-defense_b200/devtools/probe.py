@@ -17,7 +17,7 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     chunk = int(sys.argv[2]) if len(sys.argv) > 2 else B
     sd = synthetic.wavenet_state_dict(seed=0)
-    net = ap.WaveNet(sd, mode="bf16", **synthetic.DEFAULT_WAVENET_CONFIG)
+    net = ap.WaveNet(sd, mode=os.environ.get("AP_PROBE_MODE", "bf16"), **synthetic.DEFAULT_WAVENET_CONFIG)
     lib = _lib.load()
     L = 16000
     x = torch.from_numpy(synthetic.synthetic_waveforms(B, L, seed=1)).cuda()

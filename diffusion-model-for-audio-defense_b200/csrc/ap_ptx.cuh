@@ -302,6 +302,54 @@ __device__ __forceinline__ float tanh_exp(float x) {
   const float e = __expf(2.f * fminf(fmaxf(x, -40.f), 40.f));
   return 1.f - __fdividef(2.f, 1.f + e);
 }
+// packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 on sm_100): two independent fp32 operations per instruction
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void up2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// v -> (bf16x2 hi, bf16x2 lo) with lo = bf16(v - float(hi)) for a pair of values
+__device__ __forceinline__ void split_bf16x2(f32x2 v, uint32_t& hi, uint32_t& lo) {
+  float v0, v1;
+  up2(v, v0, v1);
+  hi = pack_bf16x2(v0, v1);
+  float r0, r1;
+  up2(fma2(pk2(bf16_lo(hi), bf16_hi(hi)), pk2(-1.f, -1.f), v), r0, r1);
+  lo = pack_bf16x2(r0, r1);
+}
+// the gate of two channels at once: tanh(a) * sigmoid(s) = (E - 1) / ((E + 1)(1 + F)), E = e^{2a}, F = e^{-s} (see gate_exp)
+__device__ __forceinline__ f32x2 gate_exp2(f32x2 a, f32x2 s) {
+  float a0, a1, x0, x1, y0, y1, E0, E1, F0, F1, r0, r1;
+  up2(a, a0, a1);
+  up2(mul2(pk2(fminf(a0, 20.f), fminf(a1, 20.f)), pk2(2.885390081777927f, 2.885390081777927f)), x0, x1);
+  up2(mul2(s, pk2(-1.4426950408889634f, -1.4426950408889634f)), y0, y1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E0) : "f"(x0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E1) : "f"(x1));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(F0) : "f"(y0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(F1) : "f"(y1));
+  const f32x2 E = pk2(E0, E1), one = pk2(1.f, 1.f);
+  up2(mul2(add2(E, one), add2(pk2(F0, F1), one)), x0, x1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(x0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(x1));
+  return mul2(add2(E, pk2(-1.f, -1.f)), pk2(r0, r1));
+}
 // tanh(a) * sigmoid(s) with one reciprocal: (E - 1) / ((E + 1)(1 + F)), E = e^{2a}, F = e^{-s}.  a is clamped above so
 // that E + 1 stays finite; E -> 0 gives -1 / (1 + F), F -> inf gives 0.  Absolute error ~2e-7 (checked against float64).
 __device__ __forceinline__ float gate_exp(float a, float s) {

@@ -605,18 +605,16 @@ __device__ __forceinline__ void k1s_epilogue(const Ctx<G>& cx, const K1Params& p
           const float a0 = __uint_as_float(ta[gq][c0]) + p.bd[cb], a1 = __uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1];
           const float s0 = fmaf(2.f, p.bd[cb + 128], __uint_as_float(sg[gq][c0]));
           const float s1 = fmaf(2.f, p.bd[cb + 129], __uint_as_float(sg[gq][c0 + 1]));
-          float o0, o1;
+          f32x2 o2;
           if constexpr (SAVE) {   // tanh and sigmoid separately: the backward pass keeps the gate's local derivatives
             const float t0 = tanh_exp(a0), t1 = tanh_exp(a1), g0 = sigmoid_exp(s0), g1 = sigmoid_exp(s1);
-            o0 = t0 * g0, o1 = t1 * g1;
+            o2 = pk2(t0 * g0, t1 * g1);
             tsk[0][e] = pack_bf16x2(g0 * fmaf(-t0, t0, 1.f), g1 * fmaf(-t1, t1, 1.f));
             tsk[1][e] = pack_bf16x2(t0 * g0 * (1.f - g0), t1 * g1 * (1.f - g1));
-          } else {                // one quotient: tanh(a) sigmoid(s) = (E - 1) / ((E + 1)(1 + F)), E = e^{2a}, F = e^{-s}
-            o0 = gate_exp(a0, s0), o1 = gate_exp(a1, s1);
+          } else {                // one quotient per channel, two channels per instruction (packed fp32x2 arithmetic)
+            o2 = gate_exp2(pk2(a0, a1), pk2(s0, s1));
           }
-          const uint32_t hi = pack_bf16x2(o0, o1);
-          pk[gq][i][e] = hi;
-          pl[gq][i][e] = pack_bf16x2(o0 - bf16_lo(hi), o1 - bf16_hi(hi));
+          split_bf16x2(o2, pk[gq][i][e], pl[gq][i][e]);
         }
         if constexpr (SAVE) {
           if (live) {
@@ -694,13 +692,11 @@ __device__ __forceinline__ void k1s_epilogue(const Ctx<G>& cx, const K1Params& p
           const int a0 = i * 16 + e4 * 4;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const float u0 = bf16_lo(uh[e4 * 2 + h]) + bf16_lo(ul[e4 * 2 + h]);
-            const float u1 = bf16_hi(uh[e4 * 2 + h]) + bf16_hi(ul[e4 * 2 + h]);
-            const float v0 = fmaf(u0 + __uint_as_float(acc[a0 + 2 * h]), sqrt_half, cc[2 * h]);
-            const float v1 = fmaf(u1 + __uint_as_float(acc[a0 + 2 * h + 1]), sqrt_half, cc[2 * h + 1]);
-            const uint32_t hi = pack_bf16x2(v0, v1);
-            pk[e4 * 2 + h] = hi;
-            pl[e4 * 2 + h] = pack_bf16x2(v0 - bf16_lo(hi), v1 - bf16_hi(hi));
+            const uint32_t wh = uh[e4 * 2 + h], wl = ul[e4 * 2 + h];
+            const f32x2 u2 = add2(pk2(bf16_lo(wh), bf16_hi(wh)), pk2(bf16_lo(wl), bf16_hi(wl)));
+            const f32x2 r2 = pk2(__uint_as_float(acc[a0 + 2 * h]), __uint_as_float(acc[a0 + 2 * h + 1]));
+            const f32x2 v2 = fma2(add2(u2, r2), pk2(sqrt_half, sqrt_half), pk2(cc[2 * h], cc[2 * h + 1]));
+            split_bf16x2(v2, pk[e4 * 2 + h], pl[e4 * 2 + h]);
           }
         }
         if (live) {

@@ -244,7 +244,6 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     __syncwarp();
     if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);   // accumulators are in registers: the region is free again
     uint32_t pk[2][4][4];
-    uint32_t pl[G::SPLIT ? 2 : 1][4][4];   // lo plane (split mode)
     uint32_t tsk[2][4];                    // SAVE: packed tanh / sigmoid of the current 8 channels
 #pragma unroll
     for (int gq = 0; gq < 2; ++gq)
@@ -254,21 +253,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
         for (int e = 0; e < 4; ++e) {
           const int c0 = i * 8 + 2 * e;
           const int cb = J * 256 + HSEL * 64 + gq * 32 + c0;
-          if constexpr (G::SPLIT) {
-            // fp32-class gate: exp-based tanh / sigmoid (MUFU.TANH is good to ~2^-11 only); p.bd holds HALF the sigmoid bias
-            const float t0 = tanh_exp(__uint_as_float(ta[gq][c0]) + p.bd[cb]);
-            const float t1 = tanh_exp(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]);
-            const float g0 = sigmoid_exp(fmaf(2.f, p.bd[cb + 128], __uint_as_float(sg[gq][c0])));
-            const float g1 = sigmoid_exp(fmaf(2.f, p.bd[cb + 129], __uint_as_float(sg[gq][c0 + 1])));
-            const float o0 = t0 * g0, o1 = t1 * g1;
-            const uint32_t hi = pack_bf16x2(o0, o1);
-            pk[gq][i][e] = hi;
-            pl[gq][i][e] = pack_bf16x2(o0 - bf16_lo(hi), o1 - bf16_hi(hi));
-            if constexpr (SAVE) {   // local derivatives of the gate (see the bf16 branch)
-              tsk[0][e] = pack_bf16x2(g0 * fmaf(-t0, t0, 1.f), g1 * fmaf(-t1, t1, 1.f));
-              tsk[1][e] = pack_bf16x2(t0 * g0 * (1.f - g0), t1 * g1 * (1.f - g1));
-            }
-          } else {
+          {
             const float t0 = tanh_approx(__uint_as_float(ta[gq][c0]) + p.bd[cb]);
             const float t1 = tanh_approx(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]);
             const float s0 = tanh_approx(fmaf(__uint_as_float(sg[gq][c0]), 0.5f, p.bd[cb + 128]));
@@ -308,9 +293,6 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         st_shared_v4(kb_base + (((gq * 4 + i) ^ sw) << 4), make_uint4(pk[gq][i][0], pk[gq][i][1], pk[gq][i][2], pk[gq][i][3]));
-        if constexpr (G::SPLIT)   // lo plane: K-blocks 4..7 of the staging tile
-          st_shared_v4(kb_base + 4 * A_BYTES + (((gq * 4 + i) ^ sw) << 4),
-                       make_uint4(pl[gq][i][0], pl[gq][i][1], pl[gq][i][2], pl[gq][i][3]));
       }
     fence_proxy_async_smem();
     named_bar_sync(1, EPI_THREADS);
@@ -318,10 +300,6 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
       if (valid) {
         tma_store_3d(tmO, cx.out_kb(2 * J), (2 * J) * 64, l0, p.layer * p.chunk_alloc + b);
         tma_store_3d(tmO, cx.out_kb(2 * J + 1), (2 * J + 1) * 64, l0, p.layer * p.chunk_alloc + b);
-        if constexpr (G::SPLIT) {
-          tma_store_3d(tmO, cx.out_kb(4 + 2 * J), (2 * J) * 64, l0, p.o_plane + p.layer * p.chunk_alloc + b);
-          tma_store_3d(tmO, cx.out_kb(4 + 2 * J + 1), (2 * J + 1) * 64, l0, p.o_plane + p.layer * p.chunk_alloc + b);
-        }
       }
       bulk_commit();                                       // always a group (possibly empty): wait_group counts stay uniform
       cx.arrive_leader(BAR_OUT_READY + J);
@@ -334,13 +312,10 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     const uint32_t r = g & 1;
     const bool live = valid && l0 + row < p.L;
     const size_t goff = (static_cast<size_t>(b) * p.L + (live ? l0 + row : 0)) * C + HSEL * 128;
-    const size_t lo_off = static_cast<size_t>(p.u_plane) * p.L * C;     // split mode: the lo plane
-    uint32_t uu[G::SPLIT ? 1 : 8][8];
-    if constexpr (!G::SPLIT) {
-      if (live) {
+    uint32_t uu[8][8];
+    if (live) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) ld_global_v8(p.u_in + goff + v * 16, uu[v]);
-      }
+      for (int v = 0; v < 8; ++v) ld_global_v8(p.u_in + goff + v * 16, uu[v]);
     }
     w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 10);
     tc_fence_after();
@@ -357,13 +332,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
 #pragma unroll
       for (int i = 0; i < 2; ++i) {                        // 16 channels = one 32-byte access (per plane)
         const int ch = HSEL * 128 + gq * 32 + i * 16;
-        uint32_t pk[8], pl[8], uh[8], ul[8];
-        if constexpr (G::SPLIT) {
-          if (live) {
-            ld_global_v8(p.u_in + goff + (gq * 2 + i) * 16, uh);
-            ld_global_v8(p.u_in + lo_off + goff + (gq * 2 + i) * 16, ul);
-          }
-        }
+        uint32_t pk[8];
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4) {
           const uint4 cv = ld_shared_v4(c2_addr + (ch + e4 * 4) * 4);   // warp-uniform address: broadcast
@@ -371,25 +340,13 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
           const int a0 = i * 16 + e4 * 4;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            float u0, u1;
-            if constexpr (G::SPLIT) {
-              u0 = bf16_lo(uh[e4 * 2 + h]) + bf16_lo(ul[e4 * 2 + h]);
-              u1 = bf16_hi(uh[e4 * 2 + h]) + bf16_hi(ul[e4 * 2 + h]);
-            } else {
-              u0 = unpack_lo<DT>(uu[gq * 2 + i][e4 * 2 + h]);
-              u1 = unpack_hi<DT>(uu[gq * 2 + i][e4 * 2 + h]);
-            }
+            const float u0 = unpack_lo<DT>(uu[gq * 2 + i][e4 * 2 + h]), u1 = unpack_hi<DT>(uu[gq * 2 + i][e4 * 2 + h]);
             const float v0 = fmaf(u0 + __uint_as_float(acc[a0 + 2 * h]), sqrt_half, cc[2 * h]);
             const float v1 = fmaf(u1 + __uint_as_float(acc[a0 + 2 * h + 1]), sqrt_half, cc[2 * h + 1]);
-            const uint32_t hi = pack2<DT>(v0, v1);
-            pk[e4 * 2 + h] = hi;
-            if constexpr (G::SPLIT) pl[e4 * 2 + h] = pack_bf16x2(v0 - bf16_lo(hi), v1 - bf16_hi(hi));
+            pk[e4 * 2 + h] = pack2<DT>(v0, v1);
           }
         }
-        if (live) {
-          st_global_v8(p.u_out + goff + (gq * 2 + i) * 16, pk);
-          if constexpr (G::SPLIT) st_global_v8(p.u_out + lo_off + goff + (gq * 2 + i) * 16, pl);
-        }
+        if (live) st_global_v8(p.u_out + goff + (gq * 2 + i) * 16, pk);
       }
     }
     ++g;
@@ -421,6 +378,7 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWd,
          const __grid_constant__ CUtensorMap tmWr, const __grid_constant__ K1Params p) {
   using G = Geo<CG, 1, DT>;
+  static_assert(!G::SPLIT, "the bf16x3 mode has its own layer kernel (k1_split)");
   Ctx<G> cx;
   uint8_t* gen;
   const uint32_t tmem = tc_prologue<G>(cx, gen, 1);

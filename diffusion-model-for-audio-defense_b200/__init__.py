@@ -17,6 +17,7 @@ _LAZY = {
     "create_model": "classifiers",
     "AcousticSystem": "acoustic_system",
     "RobustCertificate": "certify", "certify_dataset": "certify",
+    "EOT": "blackbox", "NES": "blackbox", "QueryLoss": "blackbox", "resolve_loss": "blackbox", "resolve_prediction": "blackbox",
     "AudioPureError": "_lib",
 }
 

@@ -79,6 +79,11 @@ SIGNATURES = {
     "ap_classifier_get_mode": (_i, [_vp]),
     "ap_vote_counts": (_i, [_fp, _i, _i, _vp, _vp]),
     "ap_argmax": (_i, [_fp, _i, _i, _vp, _vp]),
+    "ap_nes_noise_blocks": (_u64, [_i, _i, _i]),
+    "ap_nes_perturb": (_i, [_fp, _f, _fp, _u64, _u64, _i, _fp, _i, _i, _i, _vp]),
+    "ap_nes_gradient": (_i, [_fp, _fp, _u64, _u64, _i, _f, _i, _fp, _i, _i, _i, _vp]),
+    "ap_query_loss": (_i, [_fp, _vp, _i, _i, _i, _i, _f, _i, _fp, _vp, _vp]),
+    "ap_query_loss_vjp": (_i, [_fp, _vp, _fp, _i, _i, _i, _i, _f, _i, _fp, _vp]),
     "ap_selftest_umma": (_i, [_vp, _vp, _fp, _i, _vp]),
     "ap_diffwave_debug_layer": (_i, [_vp, _fp, _f, _i, _fp, _fp, _i, _i, _vp]),
     "ap_diffwave_profile": (_i, [_vp, _i]),

@@ -213,6 +213,37 @@ int ap_vote_counts(const float* logits, int B, int K, long long* counts, void* s
 int ap_argmax(const float* logits, int B, int K, int* pred, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Black-box query serving: the NES gradient estimator FAKEBOB runs around the defended system
+ * (robustness_eval/_NES.py:14-56, called from black_box_attack.py:186-190) and the per-query loss / decision of the
+ * EOT wrapper (_EOT.py:39-42, _utils.py:113-125).  S = samples_per_draw_batch_size (even), H = S / 2, R = S + first.
+ *
+ * ap_nes_perturb:  out (A, R, L) <- the query batch of one NES draw (_NES.py:18-25):
+ *     out[a, 0]             = x[a]                         (only when first = 1: the un-noised query of draw 0)
+ *     out[a, first + j]     = z[a, j] * sigma + x[a]       j < H
+ *     out[a, first + H + j] = (-z[a, j]) * sigma + x[a]
+ *   z_or_null: device (A, H, L) noise, or NULL for Philox normals (element e = lane e % 4 of block offset + e / 4;
+ *   a draw consumes ap_nes_noise_blocks(A, S, L) blocks).
+ * ap_nes_gradient: grad (A, L) (+)= scale * sum_j (loss[a, first + j] - loss[a, first + H + j]) * z[a, j]
+ *   = scale * S * torch.mean(loss * noise, 1) of _NES.py:47,51 with the noise REGENERATED from the same (seed, offset)
+ *   instead of read back from HBM.  loss: device (A, R).  accumulate = 0 overwrites grad, 1 adds to it.
+ * ap_query_loss:   loss[b] = CrossEntropyLoss(reduction='none') (AP_LOSS_ENTROPY; resolve_loss task 'SCR',
+ *   _utils.py:116-117) or score_real + confidence - max_other (AP_LOSS_MARGIN; SEC4SR_MarginLoss CSI branch,
+ *   _utils.py:73-84; other - real when targeted; max(., 0) when clip); pred[b] = argmax (first index on ties).
+ *   labels: device int64 (B); loss / pred may be NULL (not both).  A label outside [0, K) yields NaN.
+ * ------------------------------------------------------------------------------------------------------------- */
+enum { AP_LOSS_ENTROPY = 0, AP_LOSS_MARGIN = 1 };
+uint64_t ap_nes_noise_blocks(int A, int S, int L);
+int ap_nes_perturb(const float* x, float sigma, const float* z_or_null, uint64_t seed, uint64_t offset, int first,
+                   float* out, int A, int S, int L, void* stream);
+int ap_nes_gradient(const float* loss, const float* z_or_null, uint64_t seed, uint64_t offset, int first, float scale,
+                    int accumulate, float* grad, int A, int S, int L, void* stream);
+int ap_query_loss(const float* scores, const long long* labels, int B, int K, int kind, int targeted, float confidence,
+                  int clip, float* loss, int* pred, void* stream);
+/* g_scores (B, K) = g_loss[b] * d loss[b] / d scores[b, :]  (EOT with use_grad=True, _EOT.py:43-44) */
+int ap_query_loss_vjp(const float* scores, const long long* labels, const float* g_loss, int B, int K, int kind,
+                      int targeted, float confidence, int clip, float* g_scores, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Self tests of the tcgen05/TMA building blocks (used by tests/ and smoke): run a single-tile UMMA GEMM
  * D[128x256] = A[128xK] * B[256xK]^T (bf16 in, fp32 out) through TMA + TMEM and write D to `d_out` (device, 128*256).
  * a_bf16 / b_bf16: device, K-major, raw bf16 bits.  K must be a multiple of 64.

@@ -556,3 +556,75 @@ def smooth_counts(logits_fn, x, n: int, sigma: float, batch_size: int, noise, nu
         pred = logits_fn(x_in, t_star).max(1)[1]
         counts += np.bincount(pred.numpy(), minlength=num_classes)
     return counts
+
+
+# ---------------------------------------------------------------------------------------------- black-box queries (§8f-3)
+def query_loss(scores, labels, kind: str = "Entropy", targeted: bool = False, confidence: float = 0.0,
+               clip_max: bool = True):
+    """Per-query loss.  'Entropy': nn.CrossEntropyLoss(reduction='none'), what resolve_loss returns for task 'SCR'
+    (robustness_eval/_utils.py:113-117).  'Margin': the closed-set branch of SEC4SR_MarginLoss
+    (_utils.py:66-84: real + confidence - other, other + confidence - real when targeted; clip at 0, :98-99)."""
+    s = _t(scores, torch.float32)
+    y = torch.as_tensor(np.asarray(labels), dtype=torch.int64)
+    if kind == "Entropy":
+        lse = torch.logsumexp(s, dim=1)
+        return lse - s.gather(1, y[:, None])[:, 0]
+    onehot = F.one_hot(y, s.shape[1]).to(s.dtype)
+    real = (onehot * s).sum(1)
+    other = ((1 - onehot) * s - onehot * 10000).max(1)[0]
+    loss = other + confidence - real if targeted else real + confidence - other
+    return loss.clamp_min(0) if clip_max else loss
+
+
+def eot_scores(model_fn, loss_fn, x, y, eot_size: int = 1, eot_batch: int = 1):
+    """_EOT.py:18-69 without gradients: average scores / loss over eot_size evaluations of a stochastic model, plus the
+    per-query list of argmax decisions.  model_fn: (n,1,L) -> (n,K)."""
+    n = x.shape[0]
+    nb = eot_size // eot_batch
+    scores = loss = None
+    decisions = [[] for _ in range(n)]
+    for _ in range(nb):
+        s = model_fn(x.repeat(eot_batch, 1, 1))
+        l = loss_fn(s, y.repeat(eot_batch))
+        sm, lm = s.view(eot_batch, n, -1).mean(0), l.view(eot_batch, n).mean(0)
+        scores, loss = (sm, lm) if scores is None else (scores + sm, loss + lm)
+        d = s.max(1)[1].view(eot_batch, n).numpy()
+        for i in range(n):
+            decisions[i] += list(d[:, i])
+    return scores / nb, loss / nb, decisions
+
+
+def nes_gradient(model_fn, loss_fn, x, y, samples_per_draw: int, batch: int, sigma: float, noise, eot_size: int = 1,
+                 eot_batch: int = 1):
+    """_NES.py:14-56.  x (A,1,L); noise(shape) -> (A, batch/2, 1, L) standard normals for each of the
+    samples_per_draw // batch draws.  Returns (mean_loss (A,), grad (A,1,L), adver_loss (A,), adver_score (A,K),
+    predict (A,)) plus the list of query batches (for the perturbation kernel's parity test)."""
+    from collections import Counter
+    x = _t(x, torch.float32)
+    y = torch.as_tensor(np.asarray(y), dtype=torch.int64)
+    A, C, N = x.shape
+    nb = samples_per_draw // batch
+    eot_nb = eot_size // eot_batch
+    queries = []
+    grad = mean_loss = adver_loss = adver_score = predict = None
+    for i in range(nb):
+        z = _t(noise((A, batch // 2, C, N)), torch.float32)
+        z = torch.cat((z, -z), 1)                                           # antithetic pairs, :20
+        if i == 0:
+            z = torch.cat((torch.zeros_like(x).unsqueeze(1), z), 1)         # the un-noised query rides along, :21-22
+        q = (z * sigma + x.unsqueeze(1)).view(-1, C, N)                     # :23-24
+        queries.append(q)
+        R = z.shape[1]
+        scores, loss, dec = eot_scores(model_fn, loss_fn, q, y.repeat_interleave(R), eot_size, eot_batch)
+        loss = (loss / eot_nb).view(A, R)                                   # second division by the EOT batch count, :35
+        scores = (scores / eot_nb).view(A, R, -1)
+        if i == 0:
+            adver_loss, adver_score = loss[:, 0], scores[:, 0]
+            loss, z = loss[:, 1:], z[:, 1:]
+            predict = np.array([Counter(d).most_common(1)[0][0] for d in dec]).reshape(A, -1)[:, 0]
+            grad = (loss[:, :, None, None] * z).mean(1)
+            mean_loss = loss.mean(1)
+        else:
+            grad = grad + (loss[:, :, None, None] * z).mean(1)
+            mean_loss = mean_loss + loss.mean(1)
+    return mean_loss / nb, grad / sigma / nb, adver_loss, adver_score, predict, queries

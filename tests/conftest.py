@@ -24,3 +24,10 @@ def golden_grad():
     import numpy as np
     path = os.path.join(ROOT, "tests", "golden", "reference_golden_grad.npz")
     return dict(np.load(path))
+
+
+@pytest.fixture(scope="session")
+def golden_blackbox():
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "reference_golden_blackbox.npz")
+    return dict(np.load(path))

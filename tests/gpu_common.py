@@ -43,3 +43,17 @@ class TorchNormalInjector:
 
     def __exit__(self, *a):
         torch.normal = self._orig
+
+
+class ToyDefendedModel:
+    """The stochastic stand-in model of tests/golden/make_golden_blackbox.py: scores = tanh((x + 0.05 e) W) * 4 with e
+    popped from a fixed host-noise list.  Works on whatever device x lives on (torch ops: test scaffolding only)."""
+
+    def __init__(self, L, K=10, seed=900):
+        self.W = torch.from_numpy(synthetic.host_noise((L, K), 777, 0) * np.float32(4.0 / np.sqrt(L)))
+        self.seed, self.i = seed, 0
+
+    def __call__(self, x):
+        e = torch.from_numpy(synthetic.host_noise(tuple(x.shape), self.seed, self.i)).to(x.device)
+        self.i += 1
+        return torch.tanh((x + 0.05 * e)[:, 0, :] @ self.W.to(x.device)) * 4

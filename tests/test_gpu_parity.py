@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_common import CONFIG_JSON, TorchNormalInjector, cuda, rel_l2, synthetic
+from gpu_common import CONFIG_JSON, TorchNormalInjector, ToyDefendedModel, cuda, rel_l2, synthetic
 
 pytestmark = pytest.mark.gpu
 
@@ -753,3 +753,142 @@ def test_pgd_steps_through_the_defended_system_raise_the_loss(ap, sd_full):
         delta.data = (delta.data + lr * grad.sign()).clamp_(-eps, eps)
     print("PGD losses:", [f"{v:.4f}" for v in losses])
     assert losses[-1] > losses[0]
+
+
+# ------------------------------------------------------------------------------------ black-box query serving (section 8f-3)
+def test_query_loss_kernels_vs_reference_golden(ap, golden_blackbox):
+    """ap_query_loss / ap_query_loss_vjp vs nn.CrossEntropyLoss(reduction='none') and SEC4SR_MarginLoss of the reference
+    (robustness_eval/_utils.py:30-125), values and gradients (EOT backpropagates ones, _EOT.py:43-44)."""
+    from audiopure_b200.blackbox import QueryLoss, resolve_loss
+    g = golden_blackbox
+    y = cuda(g["loss_labels"])
+    loss_fn, sign = resolve_loss("Margin", False, 0.5, "SCR", None, False)
+    assert sign == 1 and resolve_loss("Entropy", True)[1] == -1
+    s = cuda(g["loss_scores"]).requires_grad_(True)
+    l = loss_fn(s, y)
+    l.backward(torch.ones_like(l))
+    np.testing.assert_allclose(l.detach().cpu().numpy(), g["loss_entropy"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(s.grad.cpu().numpy(), g["loss_entropy_grad"], rtol=0, atol=1e-6)
+    _, dec = loss_fn.loss_and_decision(s.detach(), y)
+    assert np.array_equal(dec.cpu().numpy(), g["loss_decision"])          # includes a tied row: first index wins
+    for targeted in (0, 1):
+        for clip in (0, 1):
+            m = QueryLoss("Margin", bool(targeted), 0.5, bool(clip))
+            s = cuda(g["loss_scores"]).requires_grad_(True)
+            l = m(s, y)
+            l.backward(torch.ones_like(l))
+            assert np.array_equal(l.detach().cpu().numpy(), g[f"loss_margin_t{targeted}_c{clip}"])
+            assert np.array_equal(s.grad.cpu().numpy(), g[f"loss_margin_t{targeted}_c{clip}_grad"])
+    bad = loss_fn(cuda(g["loss_scores"][:2]), torch.tensor([-1, 10], device="cuda"))
+    assert torch.isnan(bad).all()                                         # out-of-range label: NaN, never an OOB read
+
+
+class _RandnInjector:
+    """torch.randn(size, device=...) -> host noise popped in call order (what make_golden_blackbox.py fed the reference)."""
+
+    def __init__(self, seed):
+        self.seed, self.i, self._orig = seed, 0, torch.randn
+
+    def __enter__(self):
+        def fake(size, device=None, **kw):
+            z = synthetic.host_noise(tuple(size), self.seed, self.i)
+            self.i += 1
+            return torch.from_numpy(z).to(device)
+        torch.randn = fake
+        return self
+
+    def __exit__(self, *a):
+        torch.randn = self._orig
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_nes_vs_reference_golden(ap, golden_blackbox, name):
+    """NES + EOT on the CUDA kernels vs robustness_eval._NES.NES / _EOT.EOT of the reference around the same stand-in
+    model and the same injected noise: the query batches bit for bit, scores / losses to fp32 rounding, the estimate to
+    the conditioning of the estimator (loss differences of ~sigma divided by sigma).  'b' has a ragged length (1001:
+    scalar path), EOT 4 x 2 and a single draw."""
+    from audiopure_b200.blackbox import EOT, NES, QueryLoss
+    g = golden_blackbox
+    A, L, spd, bs, es, eb = (int(v) for v in g[f"nes_{name}_cfg"])
+    sigma = float(g[f"nes_{name}_sigma"])
+    toy, seen = ToyDefendedModel(L), []
+
+    def model(x):
+        seen.append(x.detach().clone())
+        return toy(x)
+
+    nes = NES(spd, bs, sigma, EOT(model, QueryLoss("Entropy"), es, eb, False), noise="torch")
+    with _RandnInjector(4000) as inj:
+        mean_loss, grad, adver_loss, adver_score, predict = nes(cuda(g[f"nes_{name}_x"]), cuda(g[f"nes_{name}_y"]))
+        assert inj.i == spd // bs
+    per_draw = es // eb
+    for i in range(spd // bs):
+        q = seen[i * per_draw]
+        assert np.array_equal(q[: q.shape[0] // eb].cpu().numpy(), g[f"nes_{name}_queries{i}"])
+    np.testing.assert_allclose(adver_score.cpu().numpy(), g[f"nes_{name}_adver_score"], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(adver_loss.cpu().numpy(), g[f"nes_{name}_adver_loss"], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(mean_loss.cpu().numpy(), g[f"nes_{name}_mean_loss"], rtol=0, atol=5e-6)
+    assert np.array_equal(np.asarray(predict), g[f"nes_{name}_predict"])
+    err = rel_l2(grad, g[f"nes_{name}_grad"])
+    print(f"NES[{name}] gradient estimate vs reference: rel-L2 {err:.2e}")
+    assert grad.shape == (A, 1, L) and err < 2e-4       # measured 2e-6
+
+
+@pytest.mark.parametrize("A,S,L,first", [(2, 8, 1024, 1), (3, 6, 1001, 0), (1, 200, 16000, 1)])
+def test_nes_kernels_exact_arithmetic_and_philox_regeneration(ap, A, S, L, first):
+    """ap_nes_gradient against float64 numpy on given losses and noise; and the Philox path: the noise the perturbation
+    kernel adds is the stream ap_randn produces at the same (seed, offset), and the gradient kernel regenerates exactly it."""
+    from audiopure_b200 import _lib
+    lib = _lib.load()
+    H, R = S // 2, S + first
+    x = cuda(synthetic.synthetic_waveforms(A, L, seed=9)[:, 0])
+    z = cuda(synthetic.host_noise((A, H, L), 123, 0))
+    loss = cuda(synthetic.host_noise((A, R), 124, 0))
+    st = _lib.stream_ptr()
+    ref = (1.0 / S) * np.einsum("aj,ajn->an", (loss[:, first:first + H] - loss[:, first + H:]).cpu().numpy().astype(np.float64),
+                                z.cpu().numpy().astype(np.float64))
+    grad = torch.full((A, L), 7.0, device="cuda")
+    _lib.check(lib.ap_nes_gradient(loss.data_ptr(), z.data_ptr(), 0, 0, first, 1.0 / S, 0, grad.data_ptr(), A, S, L, st))
+    assert rel_l2(grad, ref) < 1e-6
+    _lib.check(lib.ap_nes_gradient(loss.data_ptr(), z.data_ptr(), 0, 0, first, 1.0 / S, 1, grad.data_ptr(), A, S, L, st))
+    assert rel_l2(grad, 2 * ref) < 1e-6                                    # accumulate = 1 adds to the previous draw
+    # in-kernel noise
+    seed, off, sigma = 77, 12345, 0.05
+    out = torch.empty(A, R, L, device="cuda")
+    _lib.check(lib.ap_nes_perturb(x.data_ptr(), sigma, None, seed, off, first, out.data_ptr(), A, S, L, st))
+    zr = torch.empty(A, H, L, device="cuda")
+    _lib.check(lib.ap_randn(zr.data_ptr(), zr.numel(), seed, off, st))
+    assert int(lib.ap_nes_noise_blocks(A, S, L)) == (A * H * L + 3) // 4
+    assert torch.equal(out[:, first:first + H], zr * sigma + x[:, None])
+    assert torch.equal(out[:, first + H:], (-zr) * sigma + x[:, None])
+    if first:
+        assert torch.equal(out[:, 0], x)
+    g_philox, g_given = torch.empty(A, L, device="cuda"), torch.empty(A, L, device="cuda")
+    _lib.check(lib.ap_nes_gradient(loss.data_ptr(), None, seed, off, first, 0.5, 0, g_philox.data_ptr(), A, S, L, st))
+    _lib.check(lib.ap_nes_gradient(loss.data_ptr(), zr.data_ptr(), 0, 0, first, 0.5, 0, g_given.data_ptr(), A, S, L, st))
+    assert torch.equal(g_philox, g_given)
+    with pytest.raises(ap.AudioPureError):
+        _lib.check(lib.ap_nes_perturb(x.data_ptr(), sigma, None, seed, off, first, out.data_ptr(), A, 7, L, st))
+
+
+def test_nes_estimate_aligns_with_the_autograd_gradient(ap):
+    """Property at full size: around the (deterministic) log-mel + ResNeXt system, the NES estimate from 2000 Philox
+    queries of one 16000-sample clip correlates with the exact gradient of the same loss from the CUDA backward kernels --
+    two independent paths to the same quantity.  For a linear loss the expected cosine is sqrt(S / (S + L)) = 0.33."""
+    from audiopure_b200.blackbox import EOT, NES, QueryLoss, _PhiloxStream
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0)).set_mode("fp32")
+    system = ap.AcousticSystem(classifier=rx, transform=ap.sc09_transform(), defender=None)
+    x = cuda(synthetic.synthetic_waveforms(1, 16000, seed=4321))
+    y = torch.tensor([3], device="cuda")
+    loss_fn = QueryLoss("Entropy")
+    xr = x.clone().requires_grad_(True)
+    loss = loss_fn(system(xr), y)
+    (g_true,) = torch.autograd.grad(loss.sum(), xr)
+    loss = loss.detach()
+    nes = NES(2000, 200, 0.001, EOT(system, loss_fn, 1, 1, False), stream=_PhiloxStream(seed=5))
+    mean_loss, g_nes, adver_loss, adver_score, predict = nes(x, y)
+    cos = float((g_nes * g_true).sum() / (g_nes.norm() * g_true.norm()))
+    print(f"NES (2000 queries) vs autograd gradient: cosine {cos:.3f}, |g_nes| {float(g_nes.norm()):.3e}, |g| {float(g_true.norm()):.3e}")
+    assert abs(float(adver_loss[0]) - float(loss[0])) < 1e-4 and abs(float(mean_loss[0]) - float(loss[0])) < 1e-2
+    assert int(predict[0]) == int(adver_score.argmax(1)[0])
+    assert cos > 0.15                                   # measured 0.25; unrelated directions give |cos| ~ 1 / sqrt(L) = 0.008

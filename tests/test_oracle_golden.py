@@ -217,3 +217,34 @@ def test_oracle_mel_and_resnext_gradients_match_reference(golden_grad):
     logits = orc.resnext_forward(synthetic.resnext_state_dict(seed=0), sr)
     (gs,) = torch.autograd.grad(logits, sr, torch.from_numpy(golden_grad["resnext_g_logits"]))
     assert rel_l2(gs.numpy(), golden_grad["resnext_grad"]) < 1e-4
+
+
+def test_query_losses_match_reference(golden_blackbox):
+    g = golden_blackbox
+    s, y = g["loss_scores"], g["loss_labels"]
+    np.testing.assert_allclose(orc.query_loss(s, y, "Entropy").numpy(), g["loss_entropy"], rtol=0, atol=2e-6)
+    for targeted in (0, 1):
+        for clip in (0, 1):
+            out = orc.query_loss(s, y, "Margin", bool(targeted), 0.5, bool(clip)).numpy()
+            assert np.array_equal(out, g[f"loss_margin_t{targeted}_c{clip}"])
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_nes_estimator_matches_reference(golden_blackbox, name):
+    """oracle nes_gradient / eot_scores vs robustness_eval._NES.NES + _EOT.EOT around the same stand-in model."""
+    from gpu_common import ToyDefendedModel
+    g = golden_blackbox
+    A, L, spd, bs, es, eb = (int(v) for v in g[f"nes_{name}_cfg"])
+    sigma = float(g[f"nes_{name}_sigma"])
+    draws = iter(range(1000))
+    mean_loss, grad, adver_loss, adver_score, predict, queries = orc.nes_gradient(
+        ToyDefendedModel(L), lambda s, y: orc.query_loss(s, y, "Entropy"), g[f"nes_{name}_x"], g[f"nes_{name}_y"], spd, bs,
+        sigma, lambda shape: synthetic.host_noise(shape, 4000, next(draws)), es, eb)
+    for i, q in enumerate(queries):
+        assert np.array_equal(q.numpy(), g[f"nes_{name}_queries{i}"])
+    np.testing.assert_allclose(adver_score.numpy(), g[f"nes_{name}_adver_score"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(adver_loss.numpy(), g[f"nes_{name}_adver_loss"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(mean_loss.numpy(), g[f"nes_{name}_mean_loss"], rtol=0, atol=2e-6)
+    assert np.array_equal(predict, g[f"nes_{name}_predict"])
+    # the estimate divides loss differences of ~sigma by sigma: 1e-7 of loss rounding is ~1e-4 of the gradient
+    assert rel_l2(grad.numpy(), g[f"nes_{name}_grad"]) < 2e-3

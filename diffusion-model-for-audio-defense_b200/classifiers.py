@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["ResNeXtClassifier", "ResNetClassifier", "M5Classifier", "KWSClassifier", "create_model"]
+__all__ = ["ResNeXtClassifier", "ResNetClassifier", "VGGClassifier", "M5Classifier", "KWSClassifier", "create_model"]
 
 
 def _np32(t) -> np.ndarray:
@@ -153,6 +153,39 @@ class ResNetClassifier(_Classifier):
         return self._run(spec, spec.shape[0], 32)
 
 
+class VGGClassifier(_Classifier):
+    """VGG-11/13/16/19 with batch norm and ``in_channels`` (models/vgg.py:32-95; ``vgg19_bn`` is the SC09 factory's fallback
+    and one of ``--classifier_model``'s choices, adaptive_attack_eval.py:21) on (B,1,32,32) input."""
+    differentiable = True
+    CFG = {11: [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+           13: [64, 64, "M", 128, 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+           16: [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"],
+           19: [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]}
+
+    def __init__(self, state_dict: dict, depth: int = 19, num_classes=10, in_channels=1, device=None):
+        super().__init__()
+        sd = _strip(state_dict)
+        w, i = [], 0
+        for v in self.CFG[depth]:                       # make_layers (vgg.py:69-82): conv, BatchNorm, ReLU | MaxPool
+            if v == "M":
+                i += 1
+                continue
+            c, b = f"features.{i}", f"features.{i + 1}"
+            if b + ".running_mean" not in sd:
+                raise NotImplementedError("VGGClassifier: only the batch-norm variants (vgg*_bn) have a kernel path")
+            w += [sd[c + ".weight"], sd[c + ".bias"], sd[b + ".weight"], sd[b + ".bias"], sd[b + ".running_mean"],
+                  sd[b + ".running_var"]]
+            i += 3
+        for j in (0, 3, 6):
+            w += [sd[f"classifier.{j}.weight"], sd[f"classifier.{j}.bias"]]
+        cfg = _lib.ClassifierCfg(_lib.AP_CLS_VGG, num_classes, 0, depth, 0, 0, in_channels, 0, 0, 0, 0, 0)
+        self._create(cfg, w, device)
+
+    def forward(self, spec: torch.Tensor) -> torch.Tensor:
+        assert spec.ndim == 4 and tuple(spec.shape[1:]) == (1, 32, 32), f"expected (B,1,32,32), got {tuple(spec.shape)}"
+        return self._run(spec, spec.shape[0], 32)
+
+
 class M5Classifier(_Classifier):
     differentiable = True
     def __init__(self, state_dict: dict, n_input=1, first_kernel_size=160, n_output=10, stride=16, n_channel=32,
@@ -212,6 +245,10 @@ def create_model(path: str, device=None):
         depth = {v: k for k, v in ResNetClassifier.LAYERS.items()}[(bottleneck, counts)]
         return ResNetClassifier(sd, depth=depth, num_classes=model.fc.out_features, in_channels=model.conv1.in_channels,
                                 device=device)
+    if name == "VGG":
+        convs = sum(1 for m in model.features if type(m).__name__ == "Conv2d")
+        return VGGClassifier(sd, depth=convs + 3, num_classes=model.classifier[6].out_features,
+                             in_channels=model.features[0].in_channels, device=device)
     if name == "M5":
         return M5Classifier(sd, first_kernel_size=model.conv1.kernel_size[0], n_output=model.fc1.out_features,
                             stride=model.conv1.stride[0], n_channel=model.conv1.out_channels, device=device)

@@ -297,6 +297,52 @@ __global__ void __launch_bounds__(256) maxpool4_kernel(const float* __restrict__
 }
 
 // MaxPool2d(kernel 3, stride 2, padding 1) over NHWC [B][H][W][C] -> [B][Ho][Wo][C]   (torchvision ResNet stem, resnet.py:112)
+// MaxPool2d(kernel 2, stride 2) on NHWC (models/vgg.py:73), H and W even
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W,
+                                                         int C4) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * C4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4);
+    long long t = i / C4;
+    const int ow = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const long long b = t / Ho;
+    const float4* p = in + ((b * H + 2 * oh) * W + 2 * ow) * C4 + c;
+    const float4 v0 = p[0], v1 = p[C4], v2 = p[static_cast<long long>(W) * C4], v3 = p[static_cast<long long>(W + 1) * C4];
+    out[i] = make_float4(fmaxf(fmaxf(v0.x, v1.x), fmaxf(v2.x, v3.x)), fmaxf(fmaxf(v0.y, v1.y), fmaxf(v2.y, v3.y)),
+                         fmaxf(fmaxf(v0.z, v1.z), fmaxf(v2.z, v3.z)), fmaxf(fmaxf(v0.w, v1.w), fmaxf(v2.w, v3.w)));
+  }
+}
+// its backward: the window's gradient goes to the first maximal element in (row, column) scan order, like torch
+__global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ in,
+                                                             float* __restrict__ g_in, int B, int H, int W, int Cc) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * Cc;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cc);
+    long long t = i / Cc;
+    const int ow = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const long long b = t / Ho;
+    const long long base = ((b * H + 2 * oh) * W + 2 * ow) * Cc + c;
+    const long long off[4] = {0, Cc, static_cast<long long>(W) * Cc, static_cast<long long>(W + 1) * Cc};
+    float m = in[base];
+    int arg = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      const float v = in[base + off[q]];
+      if (v > m) m = v, arg = q;
+    }
+    const float g = g_out[i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g_in[base + off[q]] = q == arg ? g : 0.f;
+  }
+}
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H,
                                                            int W, int Cc) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
@@ -759,6 +805,10 @@ struct ap_classifier_s {
   std::vector<std::unique_ptr<ResBlock>> resblocks;
   // M5
   ConvLayer m5conv[4], m5conv_t[4];   // forward layers and their data-gradient twins
+  // VGG (batch-norm variants): `vgg_plan` lists output channels per convolution, -1 for a max-pool; three fully connected layers
+  std::vector<int> vgg_plan;
+  std::vector<std::unique_ptr<ConvLayer>> vgg_conv, vgg_conv_t;
+  ConvLayer vgg_fc[3], vgg_fc_t[3];
   // KWS
   std::vector<std::unique_ptr<DevBuf>> kws_bufs;
   KwsWeights kws{};
@@ -1314,6 +1364,190 @@ static int vjp_resnet(ap_classifier_t h, const float* spec, const float* g_logit
   return AP_OK;
 }
 
+// ---- VGG-11/13/16/19 with batch norm (models/vgg.py:32-95; the SC09 factory builds vgg19_bn, models/__init__.py:44-45).
+// state_dict order: features.{i}.{weight,bias} + BatchNorm {weight,bias,running_mean,running_var} per convolution, then
+// classifier.{0,3,6}.{weight,bias}.  Every 3x3 convolution folds its bias and BatchNorm; Dropout is the identity in eval mode;
+// on a 32x32 input the five pools leave a 1x1 map, so the three Linear layers are 1x1 convolutions on it.
+static int create_vgg(ap_classifier_t h, const float* const* w, int n_weights) {
+  const ap_classifier_cfg& c = h->cfg;
+  static const int A[] = {64, -1, 128, -1, 256, 256, -1, 512, 512, -1, 512, 512, -1, 0};
+  static const int Bc[] = {64, 64, -1, 128, 128, -1, 256, 256, -1, 512, 512, -1, 512, 512, -1, 0};
+  static const int D[] = {64, 64, -1, 128, 128, -1, 256, 256, 256, -1, 512, 512, 512, -1, 512, 512, 512, -1, 0};
+  static const int E[] = {64, 64, -1, 128, 128, -1, 256, 256, 256, 256, -1, 512, 512, 512, 512, -1, 512, 512, 512, 512, -1, 0};
+  const int* plan = c.depth == 11 ? A : c.depth == 13 ? Bc : c.depth == 16 ? D : c.depth == 19 ? E : nullptr;
+  AP_REQUIRE(plan, "ap_classifier_create: VGG depth must be 11/13/16/19 (got %d)", c.depth);
+  AP_REQUIRE(c.in_channels == 1, "ap_classifier_create: VGG in_channels must be 1 (NCHW == NHWC)");
+  int n_conv = 0;
+  for (const int* q = plan; *q; ++q) {
+    h->vgg_plan.push_back(*q);
+    n_conv += *q > 0;
+  }
+  AP_REQUIRE(n_weights == 6 * n_conv + 6, "ap_classifier_create: VGG-%d (batch norm) expects %d weight tensors, got %d", c.depth,
+             6 * n_conv + 6, n_weights);
+  int i = 0, cin = 1;
+  for (int v : h->vgg_plan) {
+    if (v < 0) continue;
+    auto L = std::make_unique<ConvLayer>();
+    L->keep_host = true;
+    int rc = L->init(cin, v, 3, 3, 1, 1, 1, w[i], w[i + 1], w[i + 2], w[i + 3], w[i + 4], w[i + 5]);
+    if (rc != AP_OK) return rc;
+    h->vgg_conv.push_back(std::move(L));
+    i += 6, cin = v;
+  }
+  const int dims[4] = {512, 4096, 4096, c.num_classes};
+  for (int j = 0; j < 3; ++j) {
+    h->vgg_fc[j].keep_host = true;
+    int rc = h->vgg_fc[j].init(dims[j], dims[j + 1], 1, 1, 1, 0, 1, w[i], w[i + 1], nullptr, nullptr, nullptr, nullptr);
+    if (rc != AP_OK) return rc;
+    i += 2;
+  }
+  h->feat = 512;
+  return AP_OK;
+}
+
+static unsigned vgg_grid(long long work) {
+  long long b = ceil_div_ll(work, 256);
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<unsigned>(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+static int forward_vgg(ap_classifier_t h, const float* spec, float* logits, int B, int H0, int W0, cudaStream_t st) {
+  AP_REQUIRE(H0 == 32 && W0 == 32, "VGG: the classifier head needs a 1x1 final map, i.e. a 32x32 input (got %dx%d)", H0, W0);
+  const int chunk = 256;
+  int rc = ensure_ws(h, static_cast<size_t>(std::min(B, chunk)) * H0 * W0 * 64);
+  if (rc != AP_OK) return rc;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    const float* x = spec + static_cast<size_t>(b0) * H0 * W0;
+    float* nxt[2] = {h->buf[0].as<float>(), h->buf[1].as<float>()};
+    int H = H0, W = W0, C = 1, which = 0;
+    size_t ci = 0;
+    for (int v : h->vgg_plan) {
+      float* y = nxt[which];
+      if (v > 0) {
+        rc = h->vgg_conv[ci++]->run(x, bn, H, W, y, nullptr, 1, st);                                     // vgg.py:75-78
+        if (rc != AP_OK) return rc;
+        C = v;
+      } else {
+        maxpool2x2_kernel<<<vgg_grid(static_cast<long long>(bn) * (H / 2) * (W / 2) * (C / 4)), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), bn, H, W, C / 4);
+        AP_LAUNCH_CHECK();
+        H /= 2, W /= 2;
+      }
+      x = y, which ^= 1;
+    }
+    for (int j = 0; j < 3; ++j) {                                                                        // vgg.py:36-44
+      float* y = j == 2 ? logits + static_cast<size_t>(b0) * h->cfg.num_classes : nxt[which];
+      rc = h->vgg_fc[j].run(x, bn, 1, 1, y, nullptr, j < 2, st);
+      if (rc != AP_OK) return rc;
+      x = y, which ^= 1;
+    }
+  }
+  return AP_OK;
+}
+
+// backward of forward_vgg (autograd over models/vgg.py:49-53, BatchNorm / Dropout in eval mode), fp32 on the FFMA path:
+// the forward is recomputed with every layer output kept, then walked in reverse
+static int vjp_vgg(ap_classifier_t h, const float* spec, const float* g_logits, float* g_spec, int B, int H0, int W0,
+                   cudaStream_t st) {
+  AP_REQUIRE(H0 == 32 && W0 == 32, "VGG backward: input must be 32x32 (got %dx%d)", H0, W0);
+  const int chunk = 64;
+  const size_t n_layers = h->vgg_plan.size();
+  if (!h->bwd_ready) {
+    for (auto& L : h->vgg_conv) {
+      auto T = std::make_unique<ConvLayer>();
+      int rc = init_dgrad(*T, *L);
+      if (rc != AP_OK) return rc;
+      h->vgg_conv_t.push_back(std::move(T));
+    }
+    for (int j = 0; j < 3; ++j) {
+      int rc = init_dgrad(h->vgg_fc_t[j], h->vgg_fc[j]);
+      if (rc != AP_OK) return rc;
+    }
+    h->bwd_ready = true;
+  }
+  const int bn_max = std::min(B, chunk);
+  if (bn_max > h->bwd_bn) {
+    h->tape.clear();
+    int H = H0, W = W0, C = 1;
+    size_t max_e = 4096;
+    for (int v : h->vgg_plan) {
+      if (v > 0) C = v;
+      else H /= 2, W /= 2;
+      const size_t e = static_cast<size_t>(H) * W * C;
+      auto d = std::make_unique<DevBuf>();
+      AP_CUDA(d->alloc(e * bn_max * sizeof(float)));
+      h->tape.push_back(std::move(d));
+      max_e = std::max(max_e, e);
+    }
+    for (int j = 0; j < 2; ++j) {
+      auto d = std::make_unique<DevBuf>();
+      AP_CUDA(d->alloc(static_cast<size_t>(4096) * bn_max * sizeof(float)));
+      h->tape.push_back(std::move(d));
+    }
+    for (int j = 0; j < 2; ++j) AP_CUDA(h->gbuf[j].alloc(max_e * bn_max * sizeof(float)));
+    h->bwd_bn = bn_max;
+  }
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    // ---- forward with the tape
+    const float* x = spec + static_cast<size_t>(b0) * H0 * W0;
+    int H = H0, W = W0, C = 1, rc = AP_OK;
+    size_t ci = 0;
+    for (size_t l = 0; l < n_layers; ++l) {
+      float* y = h->tape[l]->as<float>();
+      const int v = h->vgg_plan[l];
+      if (v > 0) {
+        rc = h->vgg_conv[ci++]->run(x, bn, H, W, y, nullptr, 1, st);
+        if (rc != AP_OK) return rc;
+        C = v;
+      } else {
+        maxpool2x2_kernel<<<vgg_grid(static_cast<long long>(bn) * (H / 2) * (W / 2) * (C / 4)), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), bn, H, W, C / 4);
+        AP_LAUNCH_CHECK();
+        H /= 2, W /= 2;
+      }
+      x = y;
+    }
+    float *f1 = h->tape[n_layers]->as<float>(), *f2 = h->tape[n_layers + 1]->as<float>();
+    rc = h->vgg_fc[0].run(x, bn, 1, 1, f1, nullptr, 1, st);
+    if (rc == AP_OK) rc = h->vgg_fc[1].run(f1, bn, 1, 1, f2, nullptr, 1, st);
+    if (rc != AP_OK) return rc;
+    // ---- backward
+    float *GA = h->gbuf[0].as<float>(), *GB = h->gbuf[1].as<float>();
+    auto mask = [&](float* g, const float* act, size_t elems) -> int {
+      relu_mask_kernel<<<vgg_grid(static_cast<long long>(elems / 4)), 256, 0, st>>>(
+          reinterpret_cast<float4*>(g), reinterpret_cast<const float4*>(act), static_cast<long long>(elems / 4));
+      AP_LAUNCH_CHECK();
+      return AP_OK;
+    };
+    rc = h->vgg_fc_t[2].run(g_logits + static_cast<size_t>(b0) * h->cfg.num_classes, bn, 1, 1, GA, nullptr, 0, st);
+    if (rc == AP_OK) rc = mask(GA, f2, static_cast<size_t>(bn) * 4096);
+    if (rc == AP_OK) rc = h->vgg_fc_t[1].run(GA, bn, 1, 1, GB, nullptr, 0, st);
+    if (rc == AP_OK) rc = mask(GB, f1, static_cast<size_t>(bn) * 4096);
+    if (rc == AP_OK) rc = h->vgg_fc_t[0].run(GB, bn, 1, 1, GA, nullptr, 0, st);      // gradient of the pooled 1x1x512 features
+    if (rc != AP_OK) return rc;
+    for (int l = static_cast<int>(n_layers) - 1; l >= 0; --l) {
+      const int v = h->vgg_plan[l];
+      const float* in_act = l > 0 ? h->tape[l - 1]->as<float>() : nullptr;          // input of layer l
+      if (v > 0) {
+        --ci;
+        rc = mask(GA, h->tape[l]->as<float>(), static_cast<size_t>(bn) * H * W * C);
+        float* dst = l == 0 ? g_spec + static_cast<size_t>(b0) * H0 * W0 : GB;
+        if (rc == AP_OK) rc = h->vgg_conv_t[ci]->run(GA, bn, H, W, dst, nullptr, 0, st);
+        if (rc != AP_OK) return rc;
+        C = h->vgg_conv[ci]->Cin;
+      } else {
+        maxpool2x2_bwd_kernel<<<vgg_grid(static_cast<long long>(bn) * H * W * C), 256, 0, st>>>(GA, in_act, GB, bn, 2 * H, 2 * W, C);
+        AP_LAUNCH_CHECK();
+        H *= 2, W *= 2;
+      }
+      std::swap(GA, GB);
+    }
+  }
+  return AP_OK;
+}
+
 // ---- M5: state_dict order conv{i}.weight, conv{i}.bias, bn{i}.{weight,bias,running_mean,running_var} (i=1..4), fc1.weight, fc1.bias
 static int create_m5(ap_classifier_t h, const float* const* w, int n_weights) {
   const ap_classifier_cfg& c = h->cfg;
@@ -1540,6 +1774,7 @@ extern "C" int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cf
     case AP_CLS_M5: rc = create_m5(h, weights, n_weights); break;
     case AP_CLS_RESNET: rc = create_resnet(h, weights, n_weights); break;
     case AP_CLS_KWS: rc = create_kws(h, weights, n_weights); break;
+    case AP_CLS_VGG: rc = create_vgg(h, weights, n_weights); break;
     default: rc = fail(AP_ERR_INVALID, "ap_classifier_create: unknown classifier kind %d", cfg->kind);
   }
   if (rc != AP_OK) {
@@ -1561,6 +1796,7 @@ extern "C" int ap_classifier_forward(ap_classifier_t h, const float* input, floa
     case AP_CLS_RESNEXT: return forward_resnext(h, input, logits, B, st);
     case AP_CLS_M5: return forward_m5(h, input, logits, B, in_len, st);
     case AP_CLS_RESNET: return forward_resnet(h, input, logits, B, 32, in_len, st);
+    case AP_CLS_VGG: return forward_vgg(h, input, logits, B, 32, in_len, st);
     default: return forward_kws(h, input, logits, B, in_len, st);
   }
 }
@@ -1572,6 +1808,7 @@ extern "C" int ap_classifier_vjp(ap_classifier_t h, const float* input, const fl
   AP_REQUIRE(B > 0, "ap_classifier_vjp: B must be positive");
   AP_CUDA(cudaSetDevice(h->device));
   if (h->cfg.kind == AP_CLS_RESNET) return vjp_resnet(h, input, g_logits, g_input, B, in_len, in_len, static_cast<cudaStream_t>(stream));
+  if (h->cfg.kind == AP_CLS_VGG) return vjp_vgg(h, input, g_logits, g_input, B, in_len, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_KWS) return vjp_kws(h, input, g_logits, g_input, B, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_M5) return vjp_m5(h, input, g_logits, g_input, B, in_len, static_cast<cudaStream_t>(stream));
   AP_REQUIRE(in_len == 32, "ap_classifier_vjp: ResNeXt input is (B, 1, 32, 32)");

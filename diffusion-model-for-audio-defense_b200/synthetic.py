@@ -159,6 +159,30 @@ def resnet_state_dict(depth: int = 34, seed: int = 0, num_classes: int = 10, in_
     return sd
 
 
+VGG_CFG = {11: [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+           13: [64, 64, "M", 128, 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+           16: [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"],
+           19: [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]}
+
+
+def vgg_state_dict(depth: int = 19, seed: int = 0, num_classes: int = 10, in_channels: int = 1):
+    """vgg*_bn state dict (models/vgg.py:32-95): conv weight + bias, BN with non-trivial running stats, three Linear layers."""
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    i, cin = 0, in_channels
+    for v in VGG_CFG[depth]:
+        if v == "M":
+            i += 1
+            continue
+        _conv2d(sd, seed, f"features.{i}", v, cin, 3, 3)
+        sd[f"features.{i}.bias"] = _normal(seed, f"features.{i}.bias", (v,), 0.1)
+        _bn(sd, seed, f"features.{i + 1}", v)
+        i, cin = i + 3, v
+    _linear(sd, seed, "classifier.0", 4096, 512, gain=2.0)
+    _linear(sd, seed, "classifier.3", 4096, 4096, gain=2.0)
+    _linear(sd, seed, "classifier.6", num_classes, 4096, gain=4.0)
+    return sd
+
+
 def m5_state_dict(seed: int = 0, n_input=1, first_kernel_size=160, n_output=10, n_channel=32):
     """M5 state dict (M5Net.py:4-20)."""
     sd: "OrderedDict[str, np.ndarray]" = OrderedDict()

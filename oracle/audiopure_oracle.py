@@ -449,6 +449,33 @@ def resnet_forward(sd, spec, depth=34, dtype=torch.float32):
 # --------------------------------------------------------------------------------------
 # a17  M5                                            audio_models/M5/M5Net.py:21-38
 # --------------------------------------------------------------------------------------
+VGG_CFG = {11: [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+           13: [64, 64, "M", 128, 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+           16: [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"],
+           19: [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]}
+
+
+def vgg_forward(sd, spec, depth=19, dtype=torch.float32):
+    """VGG with batch norm in eval mode (models/vgg.py:49-53, make_layers :69-82): [conv3x3 + BN + ReLU | maxpool 2x2]*,
+    flatten (1x1 map for a 32x32 input), Linear-ReLU-(Dropout)-Linear-ReLU-(Dropout)-Linear."""
+    x = _t(spec, dtype)
+    i = 0
+    for v in VGG_CFG[depth]:
+        if v == "M":
+            x = F.max_pool2d(x, 2, 2)
+            i += 1
+            continue
+        x = F.conv2d(x, _t(sd[f"features.{i}.weight"], dtype), _t(sd[f"features.{i}.bias"], dtype), padding=1)
+        x = F.relu(_bn_eval(sd, f"features.{i + 1}", x, dtype))
+        i += 3
+    x = x.reshape(x.shape[0], -1)
+    for j in (0, 3, 6):
+        x = F.linear(x, _t(sd[f"classifier.{j}.weight"], dtype), _t(sd[f"classifier.{j}.bias"], dtype))
+        if j < 6:
+            x = F.relu(x)
+    return x
+
+
 def m5_forward(sd, wave, stride=16, dtype=torch.float32):
     w = lambda k: _t(sd[k], dtype)
     x = _t(wave, dtype)

@@ -31,3 +31,10 @@ def golden_blackbox():
     import numpy as np
     path = os.path.join(ROOT, "tests", "golden", "reference_golden_blackbox.npz")
     return dict(np.load(path))
+
+
+@pytest.fixture(scope="session")
+def golden_vgg():
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "reference_golden_vgg.npz")
+    return dict(np.load(path))

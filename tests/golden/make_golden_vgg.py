@@ -1,0 +1,46 @@
+"""Golden logits and input gradients of the reference's VGG classifiers (audio_models/ConvNets_SpeechCommands/models/vgg.py,
+built through the reference factory models.create_model) on the mel features already pinned in reference_golden*.npz.
+
+    python tests/golden/make_golden_vgg.py        # in the build container; writes reference_golden_vgg.npz
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as mg  # noqa: E402
+from make_golden import synthetic, to_torch_sd  # noqa: E402
+
+
+def main():
+    mg.install_shim()
+    torch.set_num_threads(os.cpu_count())
+    import models
+    from models.vgg import vgg11_bn
+    g = dict(np.load(os.path.join(HERE, "reference_golden.npz")))
+    gg = dict(np.load(os.path.join(HERE, "reference_golden_grad.npz")))
+    out = {}
+    # the factory's fallback IS vgg19_bn (models/__init__.py:44-45) -- and 'resnet18' falls through to it as well (:18-21)
+    for name, key, depth in (("vgg19_bn", "vgg19", 19), ("resnet18", None, 19), ("vgg11_bn", "vgg11", 11)):
+        net = (vgg11_bn(num_classes=10, in_channels=1) if depth == 11 else models.create_model(name, 10, 1)).eval()
+        assert type(net).__name__ == "VGG"
+        if key is None:
+            continue
+        net.load_state_dict(to_torch_sd(synthetic.vgg_state_dict(depth=depth, seed=0)))
+        for p in net.parameters():
+            p.requires_grad_(False)
+        with torch.no_grad():
+            out[f"{key}_logits"] = net(torch.from_numpy(g["mel_sc09"])).numpy()
+        sr = torch.from_numpy(gg["resnext_in_spec"]).clone().requires_grad_(True)
+        (gs,) = torch.autograd.grad(net(sr), sr, torch.from_numpy(gg["resnext_g_logits"]))
+        out[f"{key}_grad"] = gs.numpy()
+    path = os.path.join(HERE, "reference_golden_vgg.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: (v.shape, float(np.abs(v).max())) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -892,3 +892,28 @@ def test_nes_estimate_aligns_with_the_autograd_gradient(ap):
     assert abs(float(adver_loss[0]) - float(loss[0])) < 1e-4 and abs(float(mean_loss[0]) - float(loss[0])) < 1e-2
     assert int(predict[0]) == int(adver_score.argmax(1)[0])
     assert cos > 0.15                                   # measured 0.25; unrelated directions give |cos| ~ 1 / sqrt(L) = 0.008
+
+
+# ------------------------------------------------------------------------------------ VGG classifiers (section 8f-4)
+@pytest.mark.parametrize("depth", [11, 19])
+def test_vgg_vs_reference_golden(ap, golden, golden_grad, golden_vgg, depth):
+    """vgg11_bn / vgg19_bn (models/vgg.py:32-95; `--classifier_model vgg19_bn`, adaptive_attack_eval.py:21) on the CUDA
+    path: logits, top-1 and the input gradient against the unmodified reference; a batch that spans two chunks of the
+    backward (64 + 6) must reproduce the single-image results."""
+    vg = ap.VGGClassifier(synthetic.vgg_state_dict(depth=depth, seed=0), depth=depth)
+    logits = vg(cuda(golden["mel_sc09"])).cpu().numpy()
+    want = golden_vgg[f"vgg{depth}_logits"]
+    assert np.abs(logits - want).max() < 1e-3 * max(1.0, np.abs(want).max())
+    assert (logits.argmax(1) == want.argmax(1)).all()
+    spec = cuda(golden_grad["resnext_in_spec"]).requires_grad_(True)
+    g_logits = cuda(golden_grad["resnext_g_logits"])
+    (gs,) = torch.autograd.grad(vg(spec), spec, g_logits)
+    err = rel_l2(gs, golden_vgg[f"vgg{depth}_grad"])
+    print(f"VGG-{depth} logits max err {np.abs(logits - want).max():.2e}, gradient rel-L2 {err:.3e}")
+    assert err < 1e-4
+    big = spec.detach().repeat(35, 1, 1, 1).requires_grad_(True)                # 70 images
+    out = vg(big)
+    (gb,) = torch.autograd.grad(out, big, g_logits.repeat(35, 1))
+    assert torch.allclose(out[-2:], vg(spec.detach()), atol=1e-5) and rel_l2(gb[-2:], gs) < 1e-5
+    with pytest.raises(ap.AudioPureError):
+        vg.set_mode("tf32")

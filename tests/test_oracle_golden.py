@@ -248,3 +248,15 @@ def test_nes_estimator_matches_reference(golden_blackbox, name):
     assert np.array_equal(predict, g[f"nes_{name}_predict"])
     # the estimate divides loss differences of ~sigma by sigma: 1e-7 of loss rounding is ~1e-4 of the gradient
     assert rel_l2(grad.numpy(), g[f"nes_{name}_grad"]) < 2e-3
+
+
+@pytest.mark.parametrize("depth", [11, 19])
+def test_vgg_family(golden, golden_grad, golden_vgg, depth):
+    """oracle vgg_forward (logits and autograd input gradient) vs the reference's vgg11_bn / vgg19_bn (models/vgg.py)."""
+    sd = synthetic.vgg_state_dict(depth=depth, seed=0)
+    logits = orc.vgg_forward(sd, golden["mel_sc09"], depth=depth).numpy()
+    want = golden_vgg[f"vgg{depth}_logits"]
+    assert np.abs(logits - want).max() < 1e-4 * max(1.0, np.abs(want).max())
+    spec = torch.from_numpy(golden_grad["resnext_in_spec"]).clone().requires_grad_(True)
+    (gs,) = torch.autograd.grad(orc.vgg_forward(sd, spec, depth=depth), spec, torch.from_numpy(golden_grad["resnext_g_logits"]))
+    assert rel_l2(gs.numpy(), golden_vgg[f"vgg{depth}_grad"]) < 1e-4

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["ResNeXtClassifier", "ResNetClassifier", "VGGClassifier", "M5Classifier", "KWSClassifier", "create_model"]
+__all__ = ["ResNeXtClassifier", "ResNetClassifier", "VGGClassifier", "WideResNetClassifier", "M5Classifier", "KWSClassifier", "create_model"]
 
 
 def _np32(t) -> np.ndarray:
@@ -186,6 +186,32 @@ class VGGClassifier(_Classifier):
         return self._run(spec, spec.shape[0], 32)
 
 
+class WideResNetClassifier(_Classifier):
+    """WideResNet-depth-widen_factor with ``in_channels`` (models/wideresnet.py:15-92; ``wideresnet28_10`` is one of
+    ``--classifier_model``'s choices, adaptive_attack_eval.py:21) on (B,1,32,32) input.  Dropout (``wideresnet28_10D``) is the
+    identity in eval mode."""
+    differentiable = True
+
+    def __init__(self, state_dict: dict, depth: int = 28, widen_factor: int = 10, num_classes=10, in_channels=1, device=None):
+        super().__init__()
+        sd = _strip(state_dict)
+        bn = lambda p: [sd[p + ".weight"], sd[p + ".bias"], sd[p + ".running_mean"], sd[p + ".running_var"]]
+        w = [sd["conv1.weight"]]
+        for s in (1, 2, 3):
+            for b in range((depth - 4) // 6):
+                p = f"block{s}.layer.{b}"
+                w += [*bn(p + ".bn1"), sd[p + ".conv1.weight"], *bn(p + ".bn2"), sd[p + ".conv2.weight"]]
+                if p + ".convShortcut.weight" in sd:
+                    w.append(sd[p + ".convShortcut.weight"])
+        w += [*bn("bn1"), sd["fc.weight"], sd["fc.bias"]]
+        cfg = _lib.ClassifierCfg(_lib.AP_CLS_WRN, num_classes, 0, depth, 0, widen_factor, in_channels, 0, 0, 0, 0, 0)
+        self._create(cfg, w, device)
+
+    def forward(self, spec: torch.Tensor) -> torch.Tensor:
+        assert spec.ndim == 4 and tuple(spec.shape[1:]) == (1, 32, 32), f"expected (B,1,32,32), got {tuple(spec.shape)}"
+        return self._run(spec, spec.shape[0], 32)
+
+
 class M5Classifier(_Classifier):
     differentiable = True
     def __init__(self, state_dict: dict, n_input=1, first_kernel_size=160, n_output=10, stride=16, n_channel=32,
@@ -249,6 +275,10 @@ def create_model(path: str, device=None):
         convs = sum(1 for m in model.features if type(m).__name__ == "Conv2d")
         return VGGClassifier(sd, depth=convs + 3, num_classes=model.classifier[6].out_features,
                              in_channels=model.features[0].in_channels, device=device)
+    if name == "WideResNet":
+        n = len(model.block1.layer)
+        return WideResNetClassifier(sd, depth=6 * n + 4, widen_factor=model.nChannels // 64, num_classes=model.fc.out_features,
+                                    in_channels=model.conv1.in_channels, device=device)
     if name == "M5":
         return M5Classifier(sd, first_kernel_size=model.conv1.kernel_size[0], n_output=model.fc1.out_features,
                             stride=model.conv1.stride[0], n_channel=model.conv1.out_channels, device=device)

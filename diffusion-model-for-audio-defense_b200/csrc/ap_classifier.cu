@@ -297,6 +297,35 @@ __global__ void __launch_bounds__(256) maxpool4_kernel(const float* __restrict__
 }
 
 // MaxPool2d(kernel 3, stride 2, padding 1) over NHWC [B][H][W][C] -> [B][Ho][Wo][C]   (torchvision ResNet stem, resnet.py:112)
+// y = relu(x * scale[c] + shift[c]) on NHWC: a pre-activation BatchNorm (eval) + ReLU that cannot fold into a convolution
+// because it acts on a residual sum (models/wideresnet.py:31-35,87)
+__global__ void __launch_bounds__(256) bn_relu_kernel(const float4* __restrict__ x, const float4* __restrict__ scale,
+                                                      const float4* __restrict__ shift, float4* __restrict__ y, long long n4,
+                                                      int C4) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4);
+    const float4 v = x[i], a = scale[c], b = shift[c];
+    y[i] = make_float4(fmaxf(fmaf(v.x, a.x, b.x), 0.f), fmaxf(fmaf(v.y, a.y, b.y), 0.f), fmaxf(fmaf(v.z, a.z, b.z), 0.f),
+                       fmaxf(fmaf(v.w, a.w, b.w), 0.f));
+  }
+}
+// its backward: g_x = (act > 0 ? g_act * scale[c] : 0) + skip   (skip: the identity-shortcut gradient, or null)
+__global__ void __launch_bounds__(256) bn_relu_bwd_kernel(const float4* g_act, const float4* __restrict__ act,
+                                                          const float4* __restrict__ scale, const float4* skip, float4* g_x,
+                                                          long long n4, int C4) {   // g_x may alias g_act (same index only)
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4);
+    const float4 g = g_act[i], a = act[i], sc = scale[c];
+    float4 o = skip ? skip[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    o.x += a.x > 0.f ? g.x * sc.x : 0.f;
+    o.y += a.y > 0.f ? g.y * sc.y : 0.f;
+    o.z += a.z > 0.f ? g.z * sc.z : 0.f;
+    o.w += a.w > 0.f ? g.w * sc.w : 0.f;
+    g_x[i] = o;
+  }
+}
 // MaxPool2d(kernel 2, stride 2) on NHWC (models/vgg.py:73), H and W even
 __global__ void __launch_bounds__(256) maxpool2x2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W,
                                                          int C4) {
@@ -805,6 +834,15 @@ struct ap_classifier_s {
   std::vector<std::unique_ptr<ResBlock>> resblocks;
   // M5
   ConvLayer m5conv[4], m5conv_t[4];   // forward layers and their data-gradient twins
+  // WideResNet: pre-activation blocks; bn1 of every block (and the final BatchNorm) as device scale / shift vectors
+  struct WrnBlock {
+    ConvLayer c1, c2, sc, t_c1, t_c2, t_sc;
+    DevBuf scale, shift;
+    bool equal = true;
+    int stride = 1, cin = 0, cout = 0;
+  };
+  std::vector<std::unique_ptr<WrnBlock>> wrn;
+  DevBuf wrn_scale, wrn_shift;   // final BatchNorm
   // VGG (batch-norm variants): `vgg_plan` lists output channels per convolution, -1 for a max-pool; three fully connected layers
   std::vector<int> vgg_plan;
   std::vector<std::unique_ptr<ConvLayer>> vgg_conv, vgg_conv_t;
@@ -1548,6 +1586,230 @@ static int vjp_vgg(ap_classifier_t h, const float* spec, const float* g_logits, 
   return AP_OK;
 }
 
+// ---- WideResNet-d-k (models/wideresnet.py:15-92; `wideresnet28_10` is a --classifier_model choice, adaptive_attack_eval.py:21).
+// Weights: conv1.weight; per block bn1.{weight,bias,running_mean,running_var}, conv1.weight, bn2.{...}, conv2.weight,
+// [convShortcut.weight]; bn1.{...}; fc.weight, fc.bias.  bn2 folds into conv1 (ReLU in its epilogue); bn1 acts on the residual sum
+// and runs as bn_relu_kernel.  A block whose width changes feeds relu(bn1(x)) to BOTH the convolutions and the shortcut (:31-32,39).
+static int bn_vectors(DevBuf& scale, DevBuf& shift, const float* const* w, int C) {
+  std::vector<float> a(C), b(C);
+  for (int c = 0; c < C; ++c) {
+    a[c] = w[0][c] / std::sqrt(w[3][c] + 1e-5f);
+    b[c] = w[1][c] - w[2][c] * a[c];
+  }
+  AP_CUDA(scale.upload(a.data(), sizeof(float) * C));
+  AP_CUDA(shift.upload(b.data(), sizeof(float) * C));
+  return AP_OK;
+}
+
+static int create_wrn(ap_classifier_t h, const float* const* w, int n_weights) {
+  const ap_classifier_cfg& c = h->cfg;
+  AP_REQUIRE(c.depth >= 10 && (c.depth - 4) % 6 == 0, "ap_classifier_create: WideResNet depth must be 6n + 4 (got %d)", c.depth);
+  AP_REQUIRE(c.widen_factor >= 1 && c.widen_factor <= 16, "ap_classifier_create: WideResNet widen_factor %d out of range", c.widen_factor);
+  AP_REQUIRE(c.in_channels == 1, "ap_classifier_create: WideResNet in_channels must be 1 (NCHW == NHWC)");
+  const int n = (c.depth - 4) / 6;
+  const int ch[4] = {16, 16 * c.widen_factor, 32 * c.widen_factor, 64 * c.widen_factor};
+  int expected = 1 + 4 + 2;
+  for (int s = 0; s < 3; ++s)
+    for (int b = 0; b < n; ++b) expected += 10 + ((b == 0 && ch[s] != ch[s + 1]) ? 1 : 0);
+  AP_REQUIRE(n_weights == expected, "ap_classifier_create: WideResNet-%d-%d expects %d weight tensors, got %d", c.depth,
+             c.widen_factor, expected, n_weights);
+  h->stem.keep_host = true;
+  int rc = h->stem.init(1, 16, 3, 3, 1, 1, 1, w[0], nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc != AP_OK) return rc;
+  int i = 1;
+  for (int s = 0; s < 3; ++s)
+    for (int b = 0; b < n; ++b) {
+      auto blk = std::make_unique<ap_classifier_s::WrnBlock>();
+      blk->cin = b == 0 ? ch[s] : ch[s + 1], blk->cout = ch[s + 1], blk->stride = (b == 0 && s > 0) ? 2 : 1;
+      blk->equal = blk->cin == blk->cout;
+      blk->c1.keep_host = blk->c2.keep_host = blk->sc.keep_host = true;
+      rc = bn_vectors(blk->scale, blk->shift, w + i, blk->cin);
+      if (rc == AP_OK) rc = blk->c1.init(blk->cin, blk->cout, 3, 3, blk->stride, 1, 1, w[i + 4], nullptr, w[i + 5], w[i + 6], w[i + 7], w[i + 8]);
+      if (rc == AP_OK) rc = blk->c2.init(blk->cout, blk->cout, 3, 3, 1, 1, 1, w[i + 9], nullptr, nullptr, nullptr, nullptr, nullptr);
+      i += 10;
+      if (rc == AP_OK && !blk->equal) {
+        rc = blk->sc.init(blk->cin, blk->cout, 1, 1, blk->stride, 0, 1, w[i], nullptr, nullptr, nullptr, nullptr, nullptr);
+        i += 1;
+      }
+      if (rc != AP_OK) return rc;
+      h->wrn.push_back(std::move(blk));
+    }
+  rc = bn_vectors(h->wrn_scale, h->wrn_shift, w + i, ch[3]);
+  if (rc != AP_OK) return rc;
+  h->feat = ch[3];
+  AP_CUDA(h->fc_w.upload(w[i + 4], sizeof(float) * c.num_classes * h->feat));
+  AP_CUDA(h->fc_b.upload(w[i + 5], sizeof(float) * c.num_classes));
+  return AP_OK;
+}
+
+static int wrn_bn_relu(const float* x, const DevBuf& scale, const DevBuf& shift, float* y, long long elems, int C, cudaStream_t st) {
+  bn_relu_kernel<<<vgg_grid(elems / 4), 256, 0, st>>>(reinterpret_cast<const float4*>(x), scale.as<float4>(), shift.as<float4>(),
+                                                      reinterpret_cast<float4*>(y), elems / 4, C / 4);
+  AP_LAUNCH_CHECK();
+  return AP_OK;
+}
+
+// One pass over `bn` images.  tape == nullptr: inference (activations ping-pong through buf[0..4]);
+// otherwise a_l = relu(bn1(x_l)) and h_l = relu(bn2(conv1(a_l))) of every block and the final relu(bn(x)) are kept in tape[2l], [2l+1], [2n].
+static int wrn_pass(ap_classifier_t h, const float* spec, float* logits, int bn, std::vector<std::unique_ptr<DevBuf>>* tape,
+                    cudaStream_t st) {
+  float* x = h->buf[0].as<float>();
+  float* xo = h->buf[1].as<float>();
+  int rc = h->stem.run(spec, bn, 32, 32, x, nullptr, 0, st);                                               // wideresnet.py:83
+  if (rc != AP_OK) return rc;
+  int H = 32, W = 32;
+  for (size_t l = 0; l < h->wrn.size(); ++l) {
+    auto& b = *h->wrn[l];
+    float* a = tape ? (*tape)[2 * l]->as<float>() : h->buf[2].as<float>();
+    float* hh = tape ? (*tape)[2 * l + 1]->as<float>() : h->buf[3].as<float>();
+    const int Ho = H / b.stride, Wo = W / b.stride;
+    rc = wrn_bn_relu(x, b.scale, b.shift, a, static_cast<long long>(bn) * H * W * b.cin, b.cin, st);       // :31-34
+    const float* res = x;
+    if (rc == AP_OK && !b.equal) {
+      rc = b.sc.run(a, bn, H, W, h->buf[4].as<float>(), nullptr, 0, st);                                   // :39
+      res = h->buf[4].as<float>();
+    }
+    if (rc == AP_OK) rc = b.c1.run(a, bn, H, W, hh, nullptr, 1, st);                                       // :35
+    if (rc == AP_OK) rc = b.c2.run(hh, bn, Ho, Wo, xo, res, 0, st);                                        // :38-39
+    if (rc != AP_OK) return rc;
+    std::swap(x, xo);
+    H = Ho, W = Wo;
+  }
+  float* f = tape ? (*tape)[2 * h->wrn.size()]->as<float>() : xo;
+  rc = wrn_bn_relu(x, h->wrn_scale, h->wrn_shift, f, static_cast<long long>(bn) * H * W * h->feat, h->feat, st);   // :87
+  if (rc != AP_OK) return rc;
+  const size_t smem = sizeof(float) * (h->feat + h->cfg.num_classes);
+  pool_fc_kernel<<<bn, 256, smem, st>>>(f, H * W, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(), h->cfg.num_classes, logits, 0);
+  AP_LAUNCH_CHECK();                                                                                       // :88-90
+  return AP_OK;
+}
+
+static int forward_wrn(ap_classifier_t h, const float* spec, float* logits, int B, int H0, int W0, cudaStream_t st) {
+  AP_REQUIRE(H0 == 32 && W0 == 32, "WideResNet: avg_pool2d(8) + view needs a 32x32 input (got %dx%d)", H0, W0);
+  const int chunk = 128;
+  int rc = ensure_ws(h, static_cast<size_t>(std::min(B, chunk)) * 32 * 32 * std::max(16, h->wrn[0]->cout));
+  if (rc != AP_OK) return rc;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    rc = wrn_pass(h, spec + static_cast<size_t>(b0) * 1024, logits + static_cast<size_t>(b0) * h->cfg.num_classes, bn, nullptr, st);
+    if (rc != AP_OK) return rc;
+  }
+  return AP_OK;
+}
+
+// backward of the WideResNet forward (autograd over models/wideresnet.py:30-39,82-90, BatchNorm in eval mode), fp32 FFMA path
+static int vjp_wrn(ap_classifier_t h, const float* spec, const float* g_logits, float* g_spec, int B, int H0, int W0,
+                   cudaStream_t st) {
+  AP_REQUIRE(H0 == 32 && W0 == 32, "WideResNet backward: input must be 32x32 (got %dx%d)", H0, W0);
+  const int chunk = 32;
+  const size_t nb = h->wrn.size();
+  if (!h->bwd_ready) {
+    int rc = init_dgrad(h->t_stem, h->stem);
+    for (auto& b : h->wrn) {
+      if (rc == AP_OK) rc = init_dgrad(b->t_c1, b->c1);
+      if (rc == AP_OK) rc = init_dgrad(b->t_c2, b->c2);
+      if (rc == AP_OK && !b->equal) rc = init_dgrad(b->t_sc, b->sc);
+    }
+    if (rc != AP_OK) return rc;
+    h->bwd_ready = true;
+  }
+  const int bn_max = std::min(B, chunk);
+  int rc = ensure_ws(h, static_cast<size_t>(bn_max) * 32 * 32 * std::max(16, h->wrn[0]->cout));
+  if (rc != AP_OK) return rc;
+  size_t widest = 0;    // largest gradient tensor per image: a stride-2 block's zero-upsampled gradient is (2H, 2W, cout)
+  for (int H = 32; auto& b : h->wrn) {
+    widest = std::max(widest, static_cast<size_t>(H) * H * std::max(b->cin, b->cout));
+    H /= b->stride;
+  }
+  if (bn_max > h->bwd_bn) {
+    h->tape.clear();
+    int H = 32;
+    auto add = [&](size_t e) -> int {
+      auto d = std::make_unique<DevBuf>();
+      AP_CUDA(d->alloc(e * bn_max * sizeof(float)));
+      h->tape.push_back(std::move(d));
+      return AP_OK;
+    };
+    for (auto& b : h->wrn) {
+      rc = add(static_cast<size_t>(H) * H * b->cin);
+      H /= b->stride;
+      if (rc == AP_OK) rc = add(static_cast<size_t>(H) * H * b->cout);
+      if (rc != AP_OK) return rc;
+    }
+    rc = add(static_cast<size_t>(H) * H * h->feat);
+    if (rc != AP_OK) return rc;
+    for (auto& g : h->gbuf) AP_CUDA(g.alloc(widest * bn_max * sizeof(float)));
+    AP_CUDA(h->tape_x0.alloc(sizeof(float) * bn_max * h->cfg.num_classes));     // logits of the recomputed forward (unused)
+    h->bwd_bn = bn_max;
+  }
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    rc = wrn_pass(h, spec + static_cast<size_t>(b0) * 1024, h->tape_x0.as<float>(), bn, &h->tape, st);
+    if (rc != AP_OK) return rc;
+    // G: gradient of the current block's output; T1..T4: scratch with fixed roles (g_h, upsampled g_h, upsampled G, shortcut gradient)
+    float *G = h->gbuf[0].as<float>(), *T1 = h->gbuf[1].as<float>(), *T2 = h->gbuf[2].as<float>(), *T3 = h->gbuf[3].as<float>(),
+          *T4 = h->gbuf[4].as<float>();
+    int H = 8, W = 8;
+    auto bwd_act = [&](float* g_act, const float* act, const DevBuf& scale, const float* skip, long long elems, int C) -> int {
+      bn_relu_bwd_kernel<<<vgg_grid(elems / 4), 256, 0, st>>>(reinterpret_cast<const float4*>(g_act),
+                                                              reinterpret_cast<const float4*>(act), scale.as<float4>(),
+                                                              reinterpret_cast<const float4*>(skip), reinterpret_cast<float4*>(g_act),
+                                                              elems / 4, C / 4);
+      AP_LAUNCH_CHECK();
+      return AP_OK;
+    };
+    auto upsample = [&](const float* g, float* up, int Ho, int Wo, int Cc) -> int {
+      upsample2_kernel<<<vgg_grid(static_cast<long long>(bn) * 4 * Ho * Wo * (Cc / 4)), 256, 0, st>>>(
+          reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(up), bn, Ho, Wo, Cc / 4);
+      AP_LAUNCH_CHECK();
+      return AP_OK;
+    };
+    // head: avg_pool2d(8) + fc, then the final BatchNorm + ReLU (in place)
+    pool_fc_bwd_kernel<<<bn, 256, 0, st>>>(g_logits + static_cast<size_t>(b0) * h->cfg.num_classes, h->fc_w.as<float>(),
+                                           h->cfg.num_classes, h->feat, H * W, G);
+    AP_LAUNCH_CHECK();
+    rc = bwd_act(G, h->tape[2 * nb]->as<float>(), h->wrn_scale, nullptr, static_cast<long long>(bn) * H * W * h->feat, h->feat);
+    if (rc != AP_OK) return rc;
+    for (int l = static_cast<int>(nb) - 1; l >= 0; --l) {
+      auto& b = *h->wrn[l];
+      const float *a = h->tape[2 * l]->as<float>(), *hh = h->tape[2 * l + 1]->as<float>();
+      const int Hi = H * b.stride, Wi = W * b.stride;
+      const long long npo = static_cast<long long>(bn) * H * W;
+      rc = b.t_c2.run(G, bn, H, W, T1, nullptr, 0, st);                         // g_h = conv2^T G, then the ReLU of bn2
+      if (rc != AP_OK) return rc;
+      relu_mask_kernel<<<vgg_grid(npo * b.cout / 4), 256, 0, st>>>(reinterpret_cast<float4*>(T1), reinterpret_cast<const float4*>(hh),
+                                                                   npo * b.cout / 4);
+      AP_LAUNCH_CHECK();
+      const float* res = nullptr;                                               // what reaches `a` through the shortcut convolution
+      if (!b.equal) {
+        const float* src = G;
+        if (b.stride == 2) {
+          rc = upsample(G, T3, H, W, b.cout);
+          src = T3;
+        }
+        if (rc == AP_OK) rc = b.t_sc.run(src, bn, Hi, Wi, T4, nullptr, 0, st);
+        res = T4;
+      }
+      const float* src = T1;
+      float* g_a = T2;
+      if (rc == AP_OK && b.stride == 2) {
+        rc = upsample(T1, T2, H, W, b.cout);
+        src = T2, g_a = T1;
+      }
+      if (rc == AP_OK) rc = b.t_c1.run(src, bn, Hi, Wi, g_a, res, 0, st);       // g_a = conv1^T g_h (+ shortcut part)
+      // x feeds bn1 + ReLU -> a, and for an equal-width block also the identity shortcut (+ G); in place in g_a
+      if (rc == AP_OK) rc = bwd_act(g_a, a, b.scale, b.equal ? G : nullptr, static_cast<long long>(bn) * Hi * Wi * b.cin, b.cin);
+      if (rc != AP_OK) return rc;
+      if (g_a == T1) std::swap(G, T1);
+      else std::swap(G, T2);
+      H = Hi, W = Wi;
+    }
+    rc = h->t_stem.run(G, bn, 32, 32, g_spec + static_cast<size_t>(b0) * 1024, nullptr, 0, st);
+    if (rc != AP_OK) return rc;
+  }
+  return AP_OK;
+}
+
 // ---- M5: state_dict order conv{i}.weight, conv{i}.bias, bn{i}.{weight,bias,running_mean,running_var} (i=1..4), fc1.weight, fc1.bias
 static int create_m5(ap_classifier_t h, const float* const* w, int n_weights) {
   const ap_classifier_cfg& c = h->cfg;
@@ -1775,6 +2037,7 @@ extern "C" int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cf
     case AP_CLS_RESNET: rc = create_resnet(h, weights, n_weights); break;
     case AP_CLS_KWS: rc = create_kws(h, weights, n_weights); break;
     case AP_CLS_VGG: rc = create_vgg(h, weights, n_weights); break;
+    case AP_CLS_WRN: rc = create_wrn(h, weights, n_weights); break;
     default: rc = fail(AP_ERR_INVALID, "ap_classifier_create: unknown classifier kind %d", cfg->kind);
   }
   if (rc != AP_OK) {
@@ -1797,6 +2060,7 @@ extern "C" int ap_classifier_forward(ap_classifier_t h, const float* input, floa
     case AP_CLS_M5: return forward_m5(h, input, logits, B, in_len, st);
     case AP_CLS_RESNET: return forward_resnet(h, input, logits, B, 32, in_len, st);
     case AP_CLS_VGG: return forward_vgg(h, input, logits, B, 32, in_len, st);
+    case AP_CLS_WRN: return forward_wrn(h, input, logits, B, 32, in_len, st);
     default: return forward_kws(h, input, logits, B, in_len, st);
   }
 }
@@ -1808,6 +2072,7 @@ extern "C" int ap_classifier_vjp(ap_classifier_t h, const float* input, const fl
   AP_REQUIRE(B > 0, "ap_classifier_vjp: B must be positive");
   AP_CUDA(cudaSetDevice(h->device));
   if (h->cfg.kind == AP_CLS_RESNET) return vjp_resnet(h, input, g_logits, g_input, B, in_len, in_len, static_cast<cudaStream_t>(stream));
+  if (h->cfg.kind == AP_CLS_WRN) return vjp_wrn(h, input, g_logits, g_input, B, in_len, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_VGG) return vjp_vgg(h, input, g_logits, g_input, B, in_len, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_KWS) return vjp_kws(h, input, g_logits, g_input, B, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_M5) return vjp_m5(h, input, g_logits, g_input, B, in_len, static_cast<cudaStream_t>(stream));

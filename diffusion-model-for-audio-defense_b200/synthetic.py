@@ -183,6 +183,26 @@ def vgg_state_dict(depth: int = 19, seed: int = 0, num_classes: int = 10, in_cha
     return sd
 
 
+def wideresnet_state_dict(depth: int = 28, widen_factor: int = 10, seed: int = 0, num_classes: int = 10, in_channels: int = 1):
+    """WideResNet state dict (models/wideresnet.py:53-80), BN with non-trivial running stats."""
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    ch = [16, 16 * widen_factor, 32 * widen_factor, 64 * widen_factor]
+    _conv2d(sd, seed, "conv1", ch[0], in_channels, 3, 3)
+    for s in range(3):
+        for b in range((depth - 4) // 6):
+            p = f"block{s + 1}.layer.{b}"
+            cin = ch[s] if b == 0 else ch[s + 1]
+            _bn(sd, seed, p + ".bn1", cin)
+            _conv2d(sd, seed, p + ".conv1", ch[s + 1], cin, 3, 3)
+            _bn(sd, seed, p + ".bn2", ch[s + 1])
+            _conv2d(sd, seed, p + ".conv2", ch[s + 1], ch[s + 1], 3, 3)
+            if cin != ch[s + 1]:
+                _conv2d(sd, seed, p + ".convShortcut", ch[s + 1], cin, 1, 1)
+    _bn(sd, seed, "bn1", ch[3])
+    _linear(sd, seed, "fc", num_classes, ch[3], gain=4.0)
+    return sd
+
+
 def m5_state_dict(seed: int = 0, n_input=1, first_kernel_size=160, n_output=10, n_channel=32):
     """M5 state dict (M5Net.py:4-20)."""
     sd: "OrderedDict[str, np.ndarray]" = OrderedDict()

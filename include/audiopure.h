@@ -177,6 +177,7 @@ int ap_mel_vjp(ap_mel_t h, const float* wav, const float* g_spec, float* g_wav, 
 #define AP_CLS_KWS 2     /* KWSModel, audio_models/RCNN_KWS/model.py:66-113 : (B,1,32,W) -> (B,4) log-probs */
 #define AP_CLS_RESNET 3  /* ResNet-18/34/50/101/152, models/resnet.py:103-220 : (B,1,32,32) -> (B,num_classes) logits; `depth` selects */
 #define AP_CLS_VGG 4     /* VGG-11/13/16/19 with batch norm, models/vgg.py:32-95 : (B,1,32,32) -> (B,num_classes) logits; `depth` selects */
+#define AP_CLS_WRN 5     /* WideResNet-depth-widen_factor, models/wideresnet.py:15-92 : (B,1,32,32) -> (B,num_classes) logits */
 typedef struct {
   int kind;
   int num_classes;

@@ -476,6 +476,29 @@ def vgg_forward(sd, spec, depth=19, dtype=torch.float32):
     return x
 
 
+def wideresnet_forward(sd, spec, depth=28, widen_factor=10, dtype=torch.float32):
+    """WideResNet in eval mode (models/wideresnet.py:30-39 block, :82-90 net).  A block whose width changes replaces x by
+    relu(bn1(x)) for both the convolutions and the 1x1 shortcut; an equal-width block keeps x for the identity shortcut.
+    BatchNorm goes through F.batch_norm like the reference's nn.BatchNorm2d: with these random weights a single ReLU whose
+    pre-activation changes sign under a differently rounded normalisation moves the input gradient by ~1e-3 (measured:
+    3 such flips among 6e6 units with the (x - m) / sqrt(v + eps) * w + b form, none with F.batch_norm, vs float64)."""
+    w = lambda k: _t(sd[k], dtype)
+    bn = lambda p, x: F.batch_norm(x, w(p + ".running_mean"), w(p + ".running_var"), w(p + ".weight"), w(p + ".bias"), False, 0.0, 1e-5)
+    x = F.conv2d(_t(spec, dtype), w("conv1.weight"), padding=1)
+    for s in range(3):
+        for b in range((depth - 4) // 6):
+            p = f"block{s + 1}.layer.{b}"
+            stride = 2 if (b == 0 and s > 0) else 1
+            a = F.relu(bn(p + ".bn1", x))
+            h = F.relu(bn(p + ".bn2", F.conv2d(a, w(p + ".conv1.weight"), stride=stride, padding=1)))
+            h = F.conv2d(h, w(p + ".conv2.weight"), padding=1)
+            short = F.conv2d(a, w(p + ".convShortcut.weight"), stride=stride) if p + ".convShortcut.weight" in sd else x
+            x = short + h
+    x = F.relu(bn("bn1", x))
+    x = F.avg_pool2d(x, 8).reshape(x.shape[0], -1)
+    return F.linear(x, w("fc.weight"), w("fc.bias"))
+
+
 def m5_forward(sd, wave, stride=16, dtype=torch.float32):
     w = lambda k: _t(sd[k], dtype)
     x = _t(wave, dtype)

@@ -1,5 +1,5 @@
-"""Golden logits and input gradients of the reference's VGG classifiers (audio_models/ConvNets_SpeechCommands/models/vgg.py,
-built through the reference factory models.create_model) on the mel features already pinned in reference_golden*.npz.
+"""Golden logits and input gradients of the reference's VGG and WideResNet classifiers
+(audio_models/ConvNets_SpeechCommands/models/{vgg,wideresnet}.py, built through the reference factory models.create_model) on the mel features already pinned in reference_golden*.npz.
 
     python tests/golden/make_golden_vgg.py        # in the build container; writes reference_golden_vgg.npz
 """
@@ -30,6 +30,19 @@ def main():
         if key is None:
             continue
         net.load_state_dict(to_torch_sd(synthetic.vgg_state_dict(depth=depth, seed=0)))
+        for p in net.parameters():
+            p.requires_grad_(False)
+        with torch.no_grad():
+            out[f"{key}_logits"] = net(torch.from_numpy(g["mel_sc09"])).numpy()
+        sr = torch.from_numpy(gg["resnext_in_spec"]).clone().requires_grad_(True)
+        (gs,) = torch.autograd.grad(net(sr), sr, torch.from_numpy(gg["resnext_g_logits"]))
+        out[f"{key}_grad"] = gs.numpy()
+    # WideResNet-28-10 through the factory (models/__init__.py:29-30) and a narrow WRN-16-1 (equal-width first block)
+    from models.wideresnet import WideResNet
+    for key, depth, k in (("wrn28_10", 28, 10), ("wrn16_1", 16, 1)):
+        net = (models.create_model("wideresnet28_10", 10, 1) if depth == 28 else
+               WideResNet(depth=depth, widen_factor=k, dropRate=0, num_classes=10, in_channels=1)).eval()
+        net.load_state_dict(to_torch_sd(synthetic.wideresnet_state_dict(depth=depth, widen_factor=k, seed=0)))
         for p in net.parameters():
             p.requires_grad_(False)
         with torch.no_grad():

@@ -917,3 +917,27 @@ def test_vgg_vs_reference_golden(ap, golden, golden_grad, golden_vgg, depth):
     assert torch.allclose(out[-2:], vg(spec.detach()), atol=1e-5) and rel_l2(gb[-2:], gs) < 1e-5
     with pytest.raises(ap.AudioPureError):
         vg.set_mode("tf32")
+
+
+@pytest.mark.parametrize("key,depth,k", [("wrn28_10", 28, 10), ("wrn16_1", 16, 1)])
+def test_wideresnet_vs_reference_golden(ap, golden, golden_grad, golden_vgg, key, depth, k):
+    """WideResNet-28-10 (`--classifier_model wideresnet28_10`, adaptive_attack_eval.py:21; models/wideresnet.py:15-92) and a
+    narrow WRN-16-1 (equal-width first block) on the CUDA path: logits, top-1 and the input gradient against the unmodified
+    reference; a batch that spans two chunks of the backward (32 + 4) must reproduce the two-image results."""
+    wr = ap.WideResNetClassifier(synthetic.wideresnet_state_dict(depth=depth, widen_factor=k, seed=0), depth=depth, widen_factor=k)
+    logits = wr(cuda(golden["mel_sc09"])).cpu().numpy()
+    want = golden_vgg[f"{key}_logits"]
+    assert np.abs(logits - want).max() < 1e-3 * max(1.0, np.abs(want).max())
+    assert (logits.argmax(1) == want.argmax(1)).all()
+    spec = cuda(golden_grad["resnext_in_spec"]).requires_grad_(True)
+    g_logits = cuda(golden_grad["resnext_g_logits"])
+    (gs,) = torch.autograd.grad(wr(spec), spec, g_logits)
+    err = rel_l2(gs, golden_vgg[f"{key}_grad"])
+    print(f"{key} logits max err {np.abs(logits - want).max():.2e} (max |logit| {np.abs(want).max():.1f}), gradient rel-L2 {err:.3e}")
+    # WRN-28-10 with these random weights: one ReLU whose pre-activation changes sign under a differently rounded fp32
+    # normalisation moves the gradient by ~1e-3 (oracle/audiopure_oracle.py::wideresnet_forward measured 3 flips = 2.4e-3)
+    assert err < (5e-3 if key == "wrn28_10" else 1e-4)      # measured 3.0e-4 / 7.4e-7
+    big = spec.detach().repeat(18, 1, 1, 1).requires_grad_(True)                # 36 images
+    out = wr(big)
+    (gb,) = torch.autograd.grad(out, big, g_logits.repeat(18, 1))
+    assert torch.allclose(out[-2:], wr(spec.detach()), rtol=1e-5, atol=1e-4) and rel_l2(gb[-2:], gs) < 1e-5

@@ -260,3 +260,16 @@ def test_vgg_family(golden, golden_grad, golden_vgg, depth):
     spec = torch.from_numpy(golden_grad["resnext_in_spec"]).clone().requires_grad_(True)
     (gs,) = torch.autograd.grad(orc.vgg_forward(sd, spec, depth=depth), spec, torch.from_numpy(golden_grad["resnext_g_logits"]))
     assert rel_l2(gs.numpy(), golden_vgg[f"vgg{depth}_grad"]) < 1e-4
+
+
+@pytest.mark.parametrize("key,depth,k", [("wrn28_10", 28, 10), ("wrn16_1", 16, 1)])
+def test_wideresnet_family(golden, golden_grad, golden_vgg, key, depth, k):
+    """oracle wideresnet_forward (logits and autograd input gradient) vs the reference's WideResNet (models/wideresnet.py)."""
+    sd = synthetic.wideresnet_state_dict(depth=depth, widen_factor=k, seed=0)
+    logits = orc.wideresnet_forward(sd, golden["mel_sc09"], depth=depth, widen_factor=k).numpy()
+    want = golden_vgg[f"{key}_logits"]
+    assert np.abs(logits - want).max() < 1e-4 * max(1.0, np.abs(want).max())
+    spec = torch.from_numpy(golden_grad["resnext_in_spec"]).clone().requires_grad_(True)
+    (gs,) = torch.autograd.grad(orc.wideresnet_forward(sd, spec, depth=depth, widen_factor=k), spec,
+                                torch.from_numpy(golden_grad["resnext_g_logits"]))
+    assert rel_l2(gs.numpy(), golden_vgg[f"{key}_grad"]) < 1e-4

@@ -13,7 +13,7 @@ _LAZY = {
     "create_diffwave_model": "diffwave",
     "RevDiffWave": "diffwave_sde", "RevVPSDE": "diffwave_sde",
     "MelSpectrogramDB": "transforms", "sc09_transform": "transforms", "kws_transform": "transforms",
-    "ResNeXtClassifier": "classifiers", "ResNetClassifier": "classifiers", "VGGClassifier": "classifiers", "WideResNetClassifier": "classifiers", "M5Classifier": "classifiers", "KWSClassifier": "classifiers",
+    "ResNeXtClassifier": "classifiers", "ResNetClassifier": "classifiers", "VGGClassifier": "classifiers", "WideResNetClassifier": "classifiers", "DenseNetClassifier": "classifiers", "M5Classifier": "classifiers", "KWSClassifier": "classifiers",
     "create_model": "classifiers",
     "AcousticSystem": "acoustic_system",
     "RobustCertificate": "certify", "certify_dataset": "certify",

@@ -13,7 +13,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AP_LIB_PATH") or os.path.join(_PKG_DIR, "libaudiopure_b200.so")
 
 AP_MODE_BF16, AP_MODE_FP32, AP_MODE_TF32, AP_MODE_FP16, AP_MODE_BF16X3 = 0, 1, 2, 3, 4
-AP_CLS_RESNEXT, AP_CLS_M5, AP_CLS_KWS, AP_CLS_RESNET, AP_CLS_VGG, AP_CLS_WRN = 0, 1, 2, 3, 4, 5
+AP_CLS_RESNEXT, AP_CLS_M5, AP_CLS_KWS, AP_CLS_RESNET, AP_CLS_VGG, AP_CLS_WRN, AP_CLS_DENSENET = 0, 1, 2, 3, 4, 5, 6
 
 
 class AudioPureError(RuntimeError):

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["ResNeXtClassifier", "ResNetClassifier", "VGGClassifier", "WideResNetClassifier", "M5Classifier", "KWSClassifier", "create_model"]
+__all__ = ["ResNeXtClassifier", "ResNetClassifier", "VGGClassifier", "WideResNetClassifier", "DenseNetClassifier", "M5Classifier", "KWSClassifier", "create_model"]
 
 
 def _np32(t) -> np.ndarray:
@@ -212,6 +212,34 @@ class WideResNetClassifier(_Classifier):
         return self._run(spec, spec.shape[0], 32)
 
 
+class DenseNetClassifier(_Classifier):
+    """DenseNet-BC-depth-growthRate with ``in_channels`` (models/densenet.py:15-147; ``densenet_bc_100_12`` is one of
+    ``--classifier_model``'s choices, adaptive_attack_eval.py:21) on (B,1,32,32) input.  Bottleneck blocks only (the factory
+    builds nothing else, models/__init__.py:37-42)."""
+    differentiable = True
+
+    def __init__(self, state_dict: dict, depth: int = 100, growth_rate: int = 12, compression_rate: int = 2, num_classes=10,
+                 in_channels=1, device=None):
+        super().__init__()
+        sd = _strip(state_dict)
+        bn = lambda p: [sd[p + ".weight"], sd[p + ".bias"], sd[p + ".running_mean"], sd[p + ".running_var"]]
+        n = (depth - 4) // 6
+        w = [sd["conv1.weight"]]
+        for s in (1, 2, 3):
+            for l in range(n):
+                p = f"dense{s}.{l}"
+                w += [*bn(p + ".bn1"), sd[p + ".conv1.weight"], *bn(p + ".bn2"), sd[p + ".conv2.weight"]]
+            if s < 3:
+                w += [*bn(f"trans{s}.bn1"), sd[f"trans{s}.conv1.weight"]]
+        w += [*bn("bn"), sd["fc.weight"], sd["fc.bias"]]
+        cfg = _lib.ClassifierCfg(_lib.AP_CLS_DENSENET, num_classes, 0, depth, growth_rate, compression_rate, in_channels, 0, 0, 0, 0, 0)
+        self._create(cfg, w, device)
+
+    def forward(self, spec: torch.Tensor) -> torch.Tensor:
+        assert spec.ndim == 4 and tuple(spec.shape[1:]) == (1, 32, 32), f"expected (B,1,32,32), got {tuple(spec.shape)}"
+        return self._run(spec, spec.shape[0], 32)
+
+
 class M5Classifier(_Classifier):
     differentiable = True
     def __init__(self, state_dict: dict, n_input=1, first_kernel_size=160, n_output=10, stride=16, n_channel=32,
@@ -279,6 +307,12 @@ def create_model(path: str, device=None):
         n = len(model.block1.layer)
         return WideResNetClassifier(sd, depth=6 * n + 4, widen_factor=model.nChannels // 64, num_classes=model.fc.out_features,
                                     in_channels=model.conv1.in_channels, device=device)
+    if name == "DenseNet":
+        n = len(model.dense1)
+        growth = model.growthRate
+        comp = round(model.trans1.conv1.in_channels / model.trans1.conv1.out_channels)
+        return DenseNetClassifier(sd, depth=6 * n + 4, growth_rate=growth, compression_rate=comp,
+                                  num_classes=model.fc.out_features, in_channels=model.conv1.in_channels, device=device)
     if name == "M5":
         return M5Classifier(sd, first_kernel_size=model.conv1.kernel_size[0], n_output=model.fc1.out_features,
                             stride=model.conv1.stride[0], n_channel=model.conv1.out_channels, device=device)

@@ -112,17 +112,22 @@ struct ConvLayer {
     return AP_OK;
   }
   int run(const float* in, int B, int H, int W, float* out, const float* residual, int relu, cudaStream_t st) const {
+    return run_strided(in, Cin, B, H, W, out, Cout, residual, relu, st);
+  }
+  // in / out are channel slices of wider NHWC tensors: pixel strides in_ctot / out_ctot floats (DenseNet's concatenation)
+  int run_strided(const float* in, int in_ctot, int B, int H, int W, float* out, int out_ctot, const float* residual, int relu,
+                  cudaStream_t st) const {
     const int pad_h = kh == 1 ? 0 : pad;   // 1 x k kernels (conv1d as a height-1 image) pad the width only
     const int Ho = (H + 2 * pad_h - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
     const long long M = static_cast<long long>(B) * Ho * Wo;
     if (M >= (1ll << 31)) return fail(AP_ERR_INVALID, "conv: too many output pixels");
-    ConvEpi ep{out, bias.as<float>(), residual, Cout, Ng, relu};
+    ConvEpi ep{out, bias.as<float>(), residual, out_ctot, Ng, relu};
     cudaError_t e;
-    if (Cg % 4 == 0) {
-      Conv2dLoader<true> al{in, H, W, Cin, Cg, kh, kw, stride, pad, pad_h, Ho, Wo};
+    if (Cg % 4 == 0 && in_ctot % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+      Conv2dLoader<true> al{in, H, W, in_ctot, Cg, kh, kw, stride, pad, pad_h, Ho, Wo};
       e = sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
     } else {
-      Conv2dLoader<false> al{in, H, W, Cin, Cg, kh, kw, stride, pad, pad_h, Ho, Wo};
+      Conv2dLoader<false> al{in, H, W, in_ctot, Cg, kh, kw, stride, pad, pad_h, Ho, Wo};
       e = sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
     }
     if (e != cudaSuccess) return fail(AP_ERR_CUDA, "conv launch: %s", cudaGetErrorString(e));
@@ -324,6 +329,73 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_kernel(const float4* g_act, c
     o.z += a.z > 0.f ? g.z * sc.z : 0.f;
     o.w += a.w > 0.f ? g.w * sc.w : 0.f;
     g_x[i] = o;
+  }
+}
+// DenseNet: pre-activation BatchNorm + ReLU of a channel PREFIX of the concatenated tensor x (pixel stride xs floats) into
+// a compact tensor y (pixel stride C4 * 4); scale / shift are zero on layout-padding channels  (models/densenet.py:27-28)
+__global__ void __launch_bounds__(256) bn_relu_prefix_kernel(const float* __restrict__ x, int xs, const float4* __restrict__ scale,
+                                                             const float4* __restrict__ shift, float4* __restrict__ y,
+                                                             long long npix, int C4) {
+  const long long total = npix * C4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4);
+    const long long pix = i / C4;
+    const float4 v = *reinterpret_cast<const float4*>(x + pix * xs + 4 * c), a = scale[c], b = shift[c];
+    y[i] = make_float4(fmaxf(fmaf(v.x, a.x, b.x), 0.f), fmaxf(fmaf(v.y, a.y, b.y), 0.f), fmaxf(fmaf(v.z, a.z, b.z), 0.f),
+                       fmaxf(fmaf(v.w, a.w, b.w), 0.f));
+  }
+}
+// its backward, with the ReLU mask recomputed from x: gx[prefix] (+)= (x * scale + shift > 0) ? g * scale : 0
+__global__ void __launch_bounds__(256) bn_relu_prefix_bwd_kernel(const float4* __restrict__ g, const float* __restrict__ x, int xs,
+                                                                 const float4* __restrict__ scale, const float4* __restrict__ shift,
+                                                                 float* __restrict__ gx, long long npix, int C4, int accumulate) {
+  const long long total = npix * C4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4);
+    const long long pix = i / C4;
+    const float4 v = *reinterpret_cast<const float4*>(x + pix * xs + 4 * c), a = scale[c], b = shift[c], gg = g[i];
+    float4* dst = reinterpret_cast<float4*>(gx + pix * xs + 4 * c);
+    float4 o = accumulate ? *dst : make_float4(0.f, 0.f, 0.f, 0.f);
+    o.x += fmaf(v.x, a.x, b.x) > 0.f ? gg.x * a.x : 0.f;
+    o.y += fmaf(v.y, a.y, b.y) > 0.f ? gg.y * a.y : 0.f;
+    o.z += fmaf(v.z, a.z, b.z) > 0.f ? gg.z * a.z : 0.f;
+    o.w += fmaf(v.w, a.w, b.w) > 0.f ? gg.w * a.w : 0.f;
+    *dst = o;
+  }
+}
+// avg_pool2d(2) of a compact (B, H, W, cs) tensor into the first C channels of a (B, H/2, W/2, os) tensor (densenet.py:70),
+// and its backward (every input pixel receives a quarter of its window's gradient)
+__global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__ in, int cs, float* __restrict__ out, int os, int B,
+                                                       int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    long long t = i / C;
+    const int ow = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const long long b = t / Ho;
+    const float* p = in + ((b * H + 2 * oh) * W + 2 * ow) * cs + c;
+    out[((b * Ho + oh) * Wo + ow) * os + c] = (p[0] + p[cs] + p[static_cast<long long>(W) * cs] + p[static_cast<long long>(W + 1) * cs]) * 0.25f;
+  }
+}
+__global__ void __launch_bounds__(256) avgpool2_bwd_kernel(const float* __restrict__ g_out, int os, float* __restrict__ g_in, int cs,
+                                                           int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * H * W * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    long long t = i / C;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int hh = static_cast<int>(t % H);
+    const long long b = t / H;
+    g_in[((b * H + hh) * W + w) * cs + c] = 0.25f * g_out[((b * Ho + (hh >> 1)) * Wo + (w >> 1)) * os + c];
   }
 }
 // MaxPool2d(kernel 2, stride 2) on NHWC (models/vgg.py:73), H and W even
@@ -843,6 +915,24 @@ struct ap_classifier_s {
   };
   std::vector<std::unique_ptr<WrnBlock>> wrn;
   DevBuf wrn_scale, wrn_shift;   // final BatchNorm
+  // DenseNet-BC: three dense blocks; each keeps its concatenated activations in ONE (B, H, W, stride) tensor whose first
+  // C0p = round4(C0) channels are the block input (padding channels stay zero) followed by `growth` channels per layer
+  struct DnLayer {
+    DevBuf scale, shift;                 // bn1 over the layer's input prefix, in the physical channel layout
+    ConvLayer c1, c2, t_c1, t_c2;        // 1x1 (bn2 folded, ReLU) and 3x3; data-gradient twins
+    int cp = 0, off = 0;                 // physical input channels; where this layer's `growth` outputs go
+  };
+  struct DnBlock {
+    int C0 = 0, C0p = 0, stride = 0, H = 0;
+    std::vector<std::unique_ptr<DnLayer>> layers;
+    DevBuf t_scale, t_shift;             // transition after the block (blocks 0, 1) or the final BatchNorm (block 2)
+    ConvLayer t_conv, t_conv_t;
+    int t_cout = 0;
+  };
+  std::vector<std::unique_ptr<DnBlock>> dn;
+  int dn_growth = 0, dn_mid = 0;
+  DevBuf dn_x[3], dn_gx[3], dn_a, dn_h, dn_t;
+  size_t dn_elems = 0;
   // VGG (batch-norm variants): `vgg_plan` lists output channels per convolution, -1 for a max-pool; three fully connected layers
   std::vector<int> vgg_plan;
   std::vector<std::unique_ptr<ConvLayer>> vgg_conv, vgg_conv_t;
@@ -1810,6 +1900,257 @@ static int vjp_wrn(ap_classifier_t h, const float* spec, const float* g_logits, 
   return AP_OK;
 }
 
+// ---- DenseNet-BC-depth-growth (models/densenet.py:15-147; `densenet_bc_100_12` is a --classifier_model choice,
+// adaptive_attack_eval.py:21).  cfg.base_width = growthRate, cfg.widen_factor = compressionRate.
+// Weights: conv1.weight; per dense layer bn1.{weight,bias,running_mean,running_var}, conv1.weight, bn2.{...}, conv2.weight;
+// after dense1 / dense2 the transition's bn1.{...}, conv1.weight; bn.{...}; fc.weight, fc.bias.
+// torch.cat((x, out), 1) (:36) never copies here: every dense block owns one NHWC tensor of its final width, each layer's 3x3
+// convolution writes its `growth` channels straight into its slice, and each layer's BatchNorm reads a channel prefix.
+static std::vector<float> dn_phys(const float* src, int rows, int Cl, int C0, int C0p) {
+  const int cp = Cl + (C0p - C0);
+  std::vector<float> out(static_cast<size_t>(rows) * cp, 0.f);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < Cl; ++c) out[static_cast<size_t>(r) * cp + (c < C0 ? c : c + (C0p - C0))] = src[static_cast<size_t>(r) * Cl + c];
+  return out;
+}
+static int dn_bn(DevBuf& scale, DevBuf& shift, const float* const* w, int Cl, int C0, int C0p) {
+  std::vector<float> a(Cl), b(Cl);
+  for (int c = 0; c < Cl; ++c) {
+    a[c] = w[0][c] / std::sqrt(w[3][c] + 1e-5f);
+    b[c] = w[1][c] - w[2][c] * a[c];
+  }
+  const std::vector<float> ap = dn_phys(a.data(), 1, Cl, C0, C0p), bp = dn_phys(b.data(), 1, Cl, C0, C0p);
+  AP_CUDA(scale.upload(ap.data(), sizeof(float) * ap.size()));
+  AP_CUDA(shift.upload(bp.data(), sizeof(float) * bp.size()));
+  return AP_OK;
+}
+
+static int create_dn(ap_classifier_t h, const float* const* w, int n_weights) {
+  const ap_classifier_cfg& c = h->cfg;
+  const int g = c.base_width, comp = c.widen_factor;
+  AP_REQUIRE(c.depth >= 10 && (c.depth - 4) % 6 == 0, "ap_classifier_create: DenseNet-BC depth must be 6n + 4 (got %d)", c.depth);
+  AP_REQUIRE(g >= 4 && g % 4 == 0 && g <= 64, "ap_classifier_create: DenseNet growthRate must be a multiple of 4 in [4, 64] (got %d)", g);
+  AP_REQUIRE(comp >= 1 && comp <= 4, "ap_classifier_create: DenseNet compressionRate %d out of range", comp);
+  AP_REQUIRE(c.in_channels == 1, "ap_classifier_create: DenseNet in_channels must be 1 (NCHW == NHWC)");
+  const int n = (c.depth - 4) / 6;
+  AP_REQUIRE(n_weights == 1 + 30 * n + 10 + 6, "ap_classifier_create: DenseNet-BC-%d-%d expects %d weight tensors, got %d", c.depth, g,
+             1 + 30 * n + 16, n_weights);
+  h->dn_growth = g, h->dn_mid = 4 * g;
+  int C = 2 * g, i = 1, rc;
+  h->stem.keep_host = true;
+  rc = h->stem.init(1, C, 3, 3, 1, 1, 1, w[0], nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc != AP_OK) return rc;
+  for (int blk = 0; blk < 3; ++blk) {
+    auto B = std::make_unique<ap_classifier_s::DnBlock>();
+    B->C0 = C, B->C0p = (C + 3) / 4 * 4, B->stride = B->C0p + g * n, B->H = 32 >> blk;
+    for (int l = 0; l < n; ++l) {
+      auto L = std::make_unique<ap_classifier_s::DnLayer>();
+      const int Cl = C + g * l;
+      L->cp = B->C0p + g * l, L->off = L->cp;
+      rc = dn_bn(L->scale, L->shift, w + i, Cl, B->C0, B->C0p);
+      if (rc != AP_OK) return rc;
+      const std::vector<float> w1 = dn_phys(w[i + 4], 4 * g, Cl, B->C0, B->C0p);
+      L->c1.keep_host = L->c2.keep_host = true;
+      rc = L->c1.init(L->cp, 4 * g, 1, 1, 1, 0, 1, w1.data(), nullptr, w[i + 5], w[i + 6], w[i + 7], w[i + 8]);
+      if (rc == AP_OK) rc = L->c2.init(4 * g, g, 3, 3, 1, 1, 1, w[i + 9], nullptr, nullptr, nullptr, nullptr, nullptr);
+      if (rc != AP_OK) return rc;
+      B->layers.push_back(std::move(L));
+      i += 10;
+    }
+    C += g * n;
+    rc = dn_bn(B->t_scale, B->t_shift, w + i, C, B->C0, B->C0p);
+    if (rc != AP_OK) return rc;
+    if (blk < 2) {                                                                  // Transition, densenet.py:56-71
+      B->t_cout = C / comp;
+      const std::vector<float> wt = dn_phys(w[i + 4], B->t_cout, C, B->C0, B->C0p);
+      B->t_conv.keep_host = true;
+      rc = B->t_conv.init(B->stride, B->t_cout, 1, 1, 1, 0, 1, wt.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+      if (rc != AP_OK) return rc;
+      i += 5;
+      C = B->t_cout;
+    } else {                                                                        // bn, relu, avgpool(8), fc: :139-144
+      const std::vector<float> fw = dn_phys(w[i + 4], c.num_classes, C, B->C0, B->C0p);
+      h->feat = B->stride;
+      AP_CUDA(h->fc_w.upload(fw.data(), sizeof(float) * fw.size()));
+      AP_CUDA(h->fc_b.upload(w[i + 5], sizeof(float) * c.num_classes));
+    }
+    h->dn.push_back(std::move(B));
+  }
+  return AP_OK;
+}
+
+static int dn_ensure(ap_classifier_t h, int bn, bool bwd) {
+  const size_t need = static_cast<size_t>(bn);
+  if (need > h->dn_elems) {
+    size_t a_max = 0;
+    for (int blk = 0; blk < 3; ++blk) {
+      auto& B = *h->dn[blk];
+      AP_CUDA(h->dn_x[blk].alloc(need * B.H * B.H * B.stride * sizeof(float)));
+      h->dn_gx[blk].release();
+      a_max = std::max(a_max, static_cast<size_t>(B.H) * B.H * B.stride);
+    }
+    AP_CUDA(h->dn_a.alloc(need * a_max * sizeof(float)));
+    AP_CUDA(h->dn_h.alloc(need * 1024 * h->dn_mid * sizeof(float)));
+    AP_CUDA(h->dn_t.alloc(need * 1024 * ((h->dn[0]->t_cout + 3) / 4 * 4) * sizeof(float)));
+    h->dn_elems = need;
+    h->bwd_bn = 0;
+  }
+  if (bwd && bn > h->bwd_bn) {
+    h->tape.clear();
+    for (int blk = 0; blk < 3; ++blk) {
+      auto& B = *h->dn[blk];
+      AP_CUDA(h->dn_gx[blk].alloc(h->dn_elems * B.H * B.H * B.stride * sizeof(float)));
+      for (size_t l = 0; l < B.layers.size(); ++l) {
+        auto d = std::make_unique<DevBuf>();
+        AP_CUDA(d->alloc(h->dn_elems * B.H * B.H * h->dn_mid * sizeof(float)));
+        h->tape.push_back(std::move(d));
+      }
+    }
+    AP_CUDA(h->tape_x0.alloc(sizeof(float) * h->dn_elems * h->cfg.num_classes));
+    h->bwd_bn = static_cast<int>(h->dn_elems);
+  }
+  return AP_OK;
+}
+
+static int dn_prefix(const float* x, int xs, const DevBuf& scale, const DevBuf& shift, float* y, long long npix, int cp, cudaStream_t st) {
+  bn_relu_prefix_kernel<<<vgg_grid(npix * (cp / 4)), 256, 0, st>>>(x, xs, scale.as<float4>(), shift.as<float4>(),
+                                                                   reinterpret_cast<float4*>(y), npix, cp / 4);
+  AP_LAUNCH_CHECK();
+  return AP_OK;
+}
+
+// One pass over `bn` images; with `tape`, the bottleneck activation relu(bn2(conv1(.))) of every dense layer is kept.
+static int dn_pass(ap_classifier_t h, const float* spec, float* logits, int bn, bool tape, cudaStream_t st) {
+  const int g = h->dn_growth, mid = h->dn_mid;
+  for (int blk = 0; blk < 3; ++blk)
+    AP_CUDA(cudaMemsetAsync(h->dn_x[blk].p, 0, static_cast<size_t>(bn) * h->dn[blk]->H * h->dn[blk]->H * h->dn[blk]->stride * sizeof(float), st));
+  int rc = h->stem.run_strided(spec, 1, bn, 32, 32, h->dn_x[0].as<float>(), h->dn[0]->stride, nullptr, 0, st);   // densenet.py:134
+  if (rc != AP_OK) return rc;
+  float* A = h->dn_a.as<float>();
+  size_t ti = 0;
+  for (int blk = 0; blk < 3; ++blk) {
+    auto& B = *h->dn[blk];
+    float* X = h->dn_x[blk].as<float>();
+    const int H = B.H;
+    const long long npix = static_cast<long long>(bn) * H * H;
+    for (auto& Lp : B.layers) {                                                      // Bottleneck.forward, :26-36
+      auto& L = *Lp;
+      float* h1 = tape ? h->tape[ti++]->as<float>() : h->dn_h.as<float>();
+      rc = dn_prefix(X, B.stride, L.scale, L.shift, A, npix, L.cp, st);
+      if (rc == AP_OK) rc = L.c1.run_strided(A, L.cp, bn, H, H, h1, mid, nullptr, 1, st);
+      if (rc == AP_OK) rc = L.c2.run_strided(h1, mid, bn, H, H, X + L.off, B.stride, nullptr, 0, st);
+      if (rc != AP_OK) return rc;
+    }
+    rc = dn_prefix(X, B.stride, B.t_scale, B.t_shift, A, npix, B.stride, st);
+    if (rc != AP_OK) return rc;
+    if (blk < 2) {                                                                   // Transition.forward, :65-71
+      const int cs = (B.t_cout + 3) / 4 * 4;
+      rc = B.t_conv.run_strided(A, B.stride, bn, H, H, h->dn_t.as<float>(), cs, nullptr, 0, st);
+      if (rc != AP_OK) return rc;
+      avgpool2_kernel<<<vgg_grid(npix / 4 * B.t_cout), 256, 0, st>>>(h->dn_t.as<float>(), cs, h->dn_x[blk + 1].as<float>(),
+                                                                     h->dn[blk + 1]->stride, bn, H, H, B.t_cout);
+      AP_LAUNCH_CHECK();
+    } else {
+      const size_t smem = sizeof(float) * (h->feat + h->cfg.num_classes);
+      pool_fc_kernel<<<bn, 256, smem, st>>>(A, H * H, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(), h->cfg.num_classes, logits, 0);
+      AP_LAUNCH_CHECK();
+    }
+  }
+  (void)g;
+  return AP_OK;
+}
+
+static int forward_dn(ap_classifier_t h, const float* spec, float* logits, int B, int H0, int W0, cudaStream_t st) {
+  AP_REQUIRE(H0 == 32 && W0 == 32, "DenseNet: AvgPool2d(8) + view needs a 32x32 input (got %dx%d)", H0, W0);
+  const int chunk = 128;
+  int rc = dn_ensure(h, std::min(B, chunk), false);
+  if (rc != AP_OK) return rc;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    rc = dn_pass(h, spec + static_cast<size_t>(b0) * 1024, logits + static_cast<size_t>(b0) * h->cfg.num_classes, bn, false, st);
+    if (rc != AP_OK) return rc;
+  }
+  return AP_OK;
+}
+
+// backward of the DenseNet forward (autograd over models/densenet.py:26-36,65-71,133-146, BatchNorm in eval mode).  The
+// gradient of a block's concatenated tensor lives in one tensor of the same layout: walking the layers in reverse, the slice a
+// layer wrote has by then received the contributions of every later reader.
+static int vjp_dn(ap_classifier_t h, const float* spec, const float* g_logits, float* g_spec, int B, int H0, int W0, cudaStream_t st) {
+  AP_REQUIRE(H0 == 32 && W0 == 32, "DenseNet backward: input must be 32x32 (got %dx%d)", H0, W0);
+  const int chunk = 32, mid = h->dn_mid;
+  if (!h->bwd_ready) {
+    int rc = init_dgrad(h->t_stem, h->stem);
+    for (auto& Bk : h->dn) {
+      for (auto& L : Bk->layers) {
+        if (rc == AP_OK) rc = init_dgrad(L->t_c1, L->c1);
+        if (rc == AP_OK) rc = init_dgrad(L->t_c2, L->c2);
+      }
+      if (rc == AP_OK && Bk->t_cout) rc = init_dgrad(Bk->t_conv_t, Bk->t_conv);
+    }
+    if (rc != AP_OK) return rc;
+    h->bwd_ready = true;
+  }
+  int rc = dn_ensure(h, std::min(B, chunk), true);
+  if (rc != AP_OK) return rc;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    rc = dn_pass(h, spec + static_cast<size_t>(b0) * 1024, h->tape_x0.as<float>(), bn, true, st);
+    if (rc != AP_OK) return rc;
+    float *A = h->dn_a.as<float>(), *Hb = h->dn_h.as<float>(), *T = h->dn_t.as<float>();
+    auto prefix_bwd = [&](const float* g, const float* x, int xs, const DevBuf& scale, const DevBuf& shift, float* gx, long long npix,
+                          int cp, int accumulate) -> int {
+      bn_relu_prefix_bwd_kernel<<<vgg_grid(npix * (cp / 4)), 256, 0, st>>>(reinterpret_cast<const float4*>(g), x, xs, scale.as<float4>(),
+                                                                          shift.as<float4>(), gx, npix, cp / 4, accumulate);
+      AP_LAUNCH_CHECK();
+      return AP_OK;
+    };
+    {   // head: AvgPool2d(8) + fc, then the final BatchNorm + ReLU
+      auto& Bk = *h->dn[2];
+      pool_fc_bwd_kernel<<<bn, 256, 0, st>>>(g_logits + static_cast<size_t>(b0) * h->cfg.num_classes, h->fc_w.as<float>(),
+                                             h->cfg.num_classes, h->feat, Bk.H * Bk.H, A);
+      AP_LAUNCH_CHECK();
+      rc = prefix_bwd(A, h->dn_x[2].as<float>(), Bk.stride, Bk.t_scale, Bk.t_shift, h->dn_gx[2].as<float>(),
+                      static_cast<long long>(bn) * Bk.H * Bk.H, Bk.stride, 0);
+      if (rc != AP_OK) return rc;
+    }
+    size_t ti = h->tape.size();
+    for (int blk = 2; blk >= 0; --blk) {
+      auto& Bk = *h->dn[blk];
+      const int H = Bk.H;
+      const long long npix = static_cast<long long>(bn) * H * H;
+      float *X = h->dn_x[blk].as<float>(), *GX = h->dn_gx[blk].as<float>();
+      for (int l = static_cast<int>(Bk.layers.size()) - 1; l >= 0; --l) {
+        auto& L = *Bk.layers[l];
+        const float* h1 = h->tape[--ti]->as<float>();
+        rc = L.t_c2.run_strided(GX + L.off, Bk.stride, bn, H, H, Hb, mid, nullptr, 0, st);
+        if (rc != AP_OK) return rc;
+        relu_mask_kernel<<<vgg_grid(npix * mid / 4), 256, 0, st>>>(reinterpret_cast<float4*>(Hb), reinterpret_cast<const float4*>(h1),
+                                                                   npix * mid / 4);
+        AP_LAUNCH_CHECK();
+        rc = L.t_c1.run_strided(Hb, mid, bn, H, H, A, L.cp, nullptr, 0, st);
+        if (rc == AP_OK) rc = prefix_bwd(A, X, Bk.stride, L.scale, L.shift, GX, npix, L.cp, 1);
+        if (rc != AP_OK) return rc;
+      }
+      if (blk > 0) {   // through the transition that produced this block's input
+        auto& P = *h->dn[blk - 1];
+        const int Hp = P.H, cs = (P.t_cout + 3) / 4 * 4;
+        const long long npp = static_cast<long long>(bn) * Hp * Hp;
+        avgpool2_bwd_kernel<<<vgg_grid(npp * P.t_cout), 256, 0, st>>>(GX, Bk.stride, T, cs, bn, Hp, Hp, P.t_cout);
+        AP_LAUNCH_CHECK();
+        rc = P.t_conv_t.run_strided(T, cs, bn, Hp, Hp, A, P.stride, nullptr, 0, st);
+        if (rc == AP_OK)
+          rc = prefix_bwd(A, h->dn_x[blk - 1].as<float>(), P.stride, P.t_scale, P.t_shift, h->dn_gx[blk - 1].as<float>(), npp, P.stride, 0);
+        if (rc != AP_OK) return rc;
+      }
+    }
+    rc = h->t_stem.run_strided(h->dn_gx[0].as<float>(), h->dn[0]->stride, bn, 32, 32, g_spec + static_cast<size_t>(b0) * 1024, 1,
+                               nullptr, 0, st);
+    if (rc != AP_OK) return rc;
+  }
+  return AP_OK;
+}
+
 // ---- M5: state_dict order conv{i}.weight, conv{i}.bias, bn{i}.{weight,bias,running_mean,running_var} (i=1..4), fc1.weight, fc1.bias
 static int create_m5(ap_classifier_t h, const float* const* w, int n_weights) {
   const ap_classifier_cfg& c = h->cfg;
@@ -2038,6 +2379,7 @@ extern "C" int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cf
     case AP_CLS_KWS: rc = create_kws(h, weights, n_weights); break;
     case AP_CLS_VGG: rc = create_vgg(h, weights, n_weights); break;
     case AP_CLS_WRN: rc = create_wrn(h, weights, n_weights); break;
+    case AP_CLS_DENSENET: rc = create_dn(h, weights, n_weights); break;
     default: rc = fail(AP_ERR_INVALID, "ap_classifier_create: unknown classifier kind %d", cfg->kind);
   }
   if (rc != AP_OK) {
@@ -2061,6 +2403,7 @@ extern "C" int ap_classifier_forward(ap_classifier_t h, const float* input, floa
     case AP_CLS_RESNET: return forward_resnet(h, input, logits, B, 32, in_len, st);
     case AP_CLS_VGG: return forward_vgg(h, input, logits, B, 32, in_len, st);
     case AP_CLS_WRN: return forward_wrn(h, input, logits, B, 32, in_len, st);
+    case AP_CLS_DENSENET: return forward_dn(h, input, logits, B, 32, in_len, st);
     default: return forward_kws(h, input, logits, B, in_len, st);
   }
 }
@@ -2072,6 +2415,7 @@ extern "C" int ap_classifier_vjp(ap_classifier_t h, const float* input, const fl
   AP_REQUIRE(B > 0, "ap_classifier_vjp: B must be positive");
   AP_CUDA(cudaSetDevice(h->device));
   if (h->cfg.kind == AP_CLS_RESNET) return vjp_resnet(h, input, g_logits, g_input, B, in_len, in_len, static_cast<cudaStream_t>(stream));
+  if (h->cfg.kind == AP_CLS_DENSENET) return vjp_dn(h, input, g_logits, g_input, B, in_len, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_WRN) return vjp_wrn(h, input, g_logits, g_input, B, in_len, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_VGG) return vjp_vgg(h, input, g_logits, g_input, B, in_len, in_len, static_cast<cudaStream_t>(stream));
   if (h->cfg.kind == AP_CLS_KWS) return vjp_kws(h, input, g_logits, g_input, B, in_len, static_cast<cudaStream_t>(stream));

@@ -203,6 +203,36 @@ def wideresnet_state_dict(depth: int = 28, widen_factor: int = 10, seed: int = 0
     return sd
 
 
+def densenet_state_dict(depth: int = 100, growth_rate: int = 12, compression_rate: int = 2, seed: int = 0, num_classes: int = 10,
+                        in_channels: int = 1):
+    """DenseNet-BC state dict (models/densenet.py:74-123, Bottleneck blocks), BN with non-trivial running stats.  Convolutions
+    are drawn with std sqrt(1 / fan_in): the reference's fan-out rule amplifies every 48 -> 12 convolution ~3x without trained
+    BatchNorm statistics, which over 48 concatenated layers overflows any useful dynamic range (logits ~ 4e7)."""
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    n, g = (depth - 4) // 6, growth_rate
+
+    def conv(name, cout, cin, k):
+        sd[name + ".weight"] = _normal(seed, name + ".weight", (cout, cin, k, k), np.sqrt(1.0 / (cin * k * k)))
+
+    C = 2 * g
+    conv("conv1", C, in_channels, 3)
+    for s in (1, 2, 3):
+        for l in range(n):
+            p = f"dense{s}.{l}"
+            _bn(sd, seed, p + ".bn1", C)
+            conv(p + ".conv1", 4 * g, C, 1)
+            _bn(sd, seed, p + ".bn2", 4 * g)
+            conv(p + ".conv2", g, 4 * g, 3)
+            C += g
+        if s < 3:
+            _bn(sd, seed, f"trans{s}.bn1", C)
+            conv(f"trans{s}.conv1", C // compression_rate, C, 1)
+            C = C // compression_rate
+    _bn(sd, seed, "bn", C)
+    _linear(sd, seed, "fc", num_classes, C, gain=4.0)
+    return sd
+
+
 def m5_state_dict(seed: int = 0, n_input=1, first_kernel_size=160, n_output=10, n_channel=32):
     """M5 state dict (M5Net.py:4-20)."""
     sd: "OrderedDict[str, np.ndarray]" = OrderedDict()

@@ -178,6 +178,8 @@ int ap_mel_vjp(ap_mel_t h, const float* wav, const float* g_spec, float* g_wav, 
 #define AP_CLS_RESNET 3  /* ResNet-18/34/50/101/152, models/resnet.py:103-220 : (B,1,32,32) -> (B,num_classes) logits; `depth` selects */
 #define AP_CLS_VGG 4     /* VGG-11/13/16/19 with batch norm, models/vgg.py:32-95 : (B,1,32,32) -> (B,num_classes) logits; `depth` selects */
 #define AP_CLS_WRN 5     /* WideResNet-depth-widen_factor, models/wideresnet.py:15-92 : (B,1,32,32) -> (B,num_classes) logits */
+#define AP_CLS_DENSENET 6 /* DenseNet-BC-depth-growth, models/densenet.py:15-147 : (B,1,32,32) -> (B,num_classes) logits;
+                           * base_width = growthRate, widen_factor = compressionRate */
 typedef struct {
   int kind;
   int num_classes;

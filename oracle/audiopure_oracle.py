@@ -499,6 +499,24 @@ def wideresnet_forward(sd, spec, depth=28, widen_factor=10, dtype=torch.float32)
     return F.linear(x, w("fc.weight"), w("fc.bias"))
 
 
+def densenet_forward(sd, spec, depth=100, dtype=torch.float32):
+    """DenseNet-BC in eval mode (models/densenet.py:26-36 bottleneck, :65-71 transition, :133-146 net).  F.batch_norm as in
+    wideresnet_forward (same sensitivity of the input gradient to single ReLU sign changes)."""
+    w = lambda k: _t(sd[k], dtype)
+    bn = lambda p, x: F.batch_norm(x, w(p + ".running_mean"), w(p + ".running_var"), w(p + ".weight"), w(p + ".bias"), False, 0.0, 1e-5)
+    x = F.conv2d(_t(spec, dtype), w("conv1.weight"), padding=1)
+    for s in (1, 2, 3):
+        for l in range((depth - 4) // 6):
+            p = f"dense{s}.{l}"
+            out = F.conv2d(F.relu(bn(p + ".bn1", x)), w(p + ".conv1.weight"))
+            out = F.conv2d(F.relu(bn(p + ".bn2", out)), w(p + ".conv2.weight"), padding=1)
+            x = torch.cat((x, out), 1)
+        if s < 3:
+            x = F.avg_pool2d(F.conv2d(F.relu(bn(f"trans{s}.bn1", x)), w(f"trans{s}.conv1.weight")), 2)
+    x = F.avg_pool2d(F.relu(bn("bn", x)), 8).reshape(x.shape[0], -1)
+    return F.linear(x, w("fc.weight"), w("fc.bias"))
+
+
 def m5_forward(sd, wave, stride=16, dtype=torch.float32):
     w = lambda k: _t(sd[k], dtype)
     x = _t(wave, dtype)

@@ -1,5 +1,5 @@
-"""Golden logits and input gradients of the reference's VGG and WideResNet classifiers
-(audio_models/ConvNets_SpeechCommands/models/{vgg,wideresnet}.py, built through the reference factory models.create_model) on the mel features already pinned in reference_golden*.npz.
+"""Golden logits and input gradients of the reference's VGG, WideResNet and DenseNet classifiers
+(audio_models/ConvNets_SpeechCommands/models/{vgg,wideresnet,densenet}.py, built through the reference factory models.create_model) on the mel features already pinned in reference_golden*.npz.
 
     python tests/golden/make_golden_vgg.py        # in the build container; writes reference_golden_vgg.npz
 """
@@ -43,6 +43,20 @@ def main():
         net = (models.create_model("wideresnet28_10", 10, 1) if depth == 28 else
                WideResNet(depth=depth, widen_factor=k, dropRate=0, num_classes=10, in_channels=1)).eval()
         net.load_state_dict(to_torch_sd(synthetic.wideresnet_state_dict(depth=depth, widen_factor=k, seed=0)))
+        for p in net.parameters():
+            p.requires_grad_(False)
+        with torch.no_grad():
+            out[f"{key}_logits"] = net(torch.from_numpy(g["mel_sc09"])).numpy()
+        sr = torch.from_numpy(gg["resnext_in_spec"]).clone().requires_grad_(True)
+        (gs,) = torch.autograd.grad(net(sr), sr, torch.from_numpy(gg["resnext_g_logits"]))
+        out[f"{key}_grad"] = gs.numpy()
+    # DenseNet-BC-100-12 through the factory (models/__init__.py:37-38) and a shallow BC-22-12 whose third block starts at 33
+    # channels (an input width that is not a multiple of 4)
+    from models.densenet import DenseNet
+    for key, depth in (("densenet100_12", 100), ("densenet22_12", 22)):
+        net = (models.create_model("densenet_bc_100_12", 10, 1) if depth == 100 else
+               DenseNet(depth=depth, growthRate=12, compressionRate=2, num_classes=10, in_channels=1)).eval()
+        net.load_state_dict(to_torch_sd(synthetic.densenet_state_dict(depth=depth, growth_rate=12, seed=0)))
         for p in net.parameters():
             p.requires_grad_(False)
         with torch.no_grad():

@@ -941,3 +941,26 @@ def test_wideresnet_vs_reference_golden(ap, golden, golden_grad, golden_vgg, key
     out = wr(big)
     (gb,) = torch.autograd.grad(out, big, g_logits.repeat(18, 1))
     assert torch.allclose(out[-2:], wr(spec.detach()), rtol=1e-5, atol=1e-4) and rel_l2(gb[-2:], gs) < 1e-5
+
+
+@pytest.mark.parametrize("key,depth", [("densenet100_12", 100), ("densenet22_12", 22)])
+def test_densenet_vs_reference_golden(ap, golden, golden_grad, golden_vgg, key, depth):
+    """DenseNet-BC-100-12 (`--classifier_model densenet_bc_100_12`, adaptive_attack_eval.py:21; models/densenet.py:15-147) and
+    a shallow BC-22-12 whose third dense block starts at 33 channels (layout padding inside the concatenated tensor) on the
+    CUDA path: logits, top-1 and the input gradient against the unmodified reference; a batch that spans two chunks of the
+    backward (32 + 4) must reproduce the two-image results."""
+    dn = ap.DenseNetClassifier(synthetic.densenet_state_dict(depth=depth, growth_rate=12, seed=0), depth=depth, growth_rate=12)
+    logits = dn(cuda(golden["mel_sc09"])).cpu().numpy()
+    want = golden_vgg[f"{key}_logits"]
+    assert np.abs(logits - want).max() < 1e-3 * max(1.0, np.abs(want).max())
+    assert (logits.argmax(1) == want.argmax(1)).all()
+    spec = cuda(golden_grad["resnext_in_spec"]).requires_grad_(True)
+    g_logits = cuda(golden_grad["resnext_g_logits"])
+    (gs,) = torch.autograd.grad(dn(spec), spec, g_logits)
+    err = rel_l2(gs, golden_vgg[f"{key}_grad"])
+    print(f"{key} logits max err {np.abs(logits - want).max():.2e} (max |logit| {np.abs(want).max():.1f}), gradient rel-L2 {err:.3e}")
+    assert err < 5e-3                      # single ReLU sign changes under different fp32 rounding, see the WideResNet test
+    big = spec.detach().repeat(18, 1, 1, 1).requires_grad_(True)                # 36 images
+    out = dn(big)
+    (gb,) = torch.autograd.grad(out, big, g_logits.repeat(18, 1))
+    assert torch.allclose(out[-2:], dn(spec.detach()), rtol=1e-5, atol=1e-4) and rel_l2(gb[-2:], gs) < 1e-5

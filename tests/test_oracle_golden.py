@@ -273,3 +273,15 @@ def test_wideresnet_family(golden, golden_grad, golden_vgg, key, depth, k):
     (gs,) = torch.autograd.grad(orc.wideresnet_forward(sd, spec, depth=depth, widen_factor=k), spec,
                                 torch.from_numpy(golden_grad["resnext_g_logits"]))
     assert rel_l2(gs.numpy(), golden_vgg[f"{key}_grad"]) < 1e-4
+
+
+@pytest.mark.parametrize("key,depth", [("densenet100_12", 100), ("densenet22_12", 22)])
+def test_densenet_family(golden, golden_grad, golden_vgg, key, depth):
+    """oracle densenet_forward (logits and autograd input gradient) vs the reference's DenseNet-BC (models/densenet.py)."""
+    sd = synthetic.densenet_state_dict(depth=depth, growth_rate=12, seed=0)
+    logits = orc.densenet_forward(sd, golden["mel_sc09"], depth=depth).numpy()
+    want = golden_vgg[f"{key}_logits"]
+    assert np.abs(logits - want).max() < 1e-4 * max(1.0, np.abs(want).max())
+    spec = torch.from_numpy(golden_grad["resnext_in_spec"]).clone().requires_grad_(True)
+    (gs,) = torch.autograd.grad(orc.densenet_forward(sd, spec, depth=depth), spec, torch.from_numpy(golden_grad["resnext_g_logits"]))
+    assert rel_l2(gs.numpy(), golden_vgg[f"{key}_grad"]) < 1e-4

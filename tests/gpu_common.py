@@ -57,3 +57,93 @@ class ToyDefendedModel:
         e = torch.from_numpy(synthetic.host_noise(tuple(x.shape), self.seed, self.i)).to(x.device)
         self.i += 1
         return torch.tanh((x + 0.05 * e)[:, 0, :] @ self.W.to(x.device)) * 4
+
+
+# ---- stand-ins for the reference's pickled classifier modules (create_model.py:8-16 unpickles WHOLE modules; the GPU box has
+# no reference checkout, so these carry the class names, attributes and state_dict keys that loader dispatches on)
+from types import SimpleNamespace as _NS  # noqa: E402
+
+
+class _PickledStandIn(torch.nn.Module):
+    def __init__(self, sd, **attrs):
+        super().__init__()
+        self._sd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+        for k, v in attrs.items():
+            object.__setattr__(self, k, v)
+
+    def state_dict(self, *a, **k):
+        return dict(self._sd)
+
+
+class CifarResNeXt(_PickledStandIn):
+    pass
+
+
+class ResNet(_PickledStandIn):
+    pass
+
+
+class Bottleneck:          # type(model.layer1[0]).__name__ decides BasicBlock vs Bottleneck
+    pass
+
+
+class BasicBlock:
+    pass
+
+
+class VGG(_PickledStandIn):
+    pass
+
+
+class Conv2d:
+    def __init__(self, in_channels=1):
+        self.in_channels = in_channels
+
+
+class WideResNet(_PickledStandIn):
+    pass
+
+
+class DenseNet(_PickledStandIn):
+    pass
+
+
+class M5(_PickledStandIn):
+    pass
+
+
+class DataParallelStandIn(torch.nn.Module):      # `.module` is unwrapped by the loader (create_model.py:12-13)
+    def __init__(self, module):
+        super().__init__()
+        object.__setattr__(self, "module", module)
+
+
+def pickled_classifier(kind):
+    """(stand-in module, directly constructed classifier factory) for one create_model branch."""
+    import audiopure_b200 as ap
+    if kind == "resnext":
+        sd = synthetic.resnext_state_dict(seed=0)
+        return (CifarResNeXt(sd, nlabels=10, cardinality=8, depth=29, base_width=64, widen_factor=4, conv_1_3x3=_NS(in_channels=1)),
+                lambda: ap.ResNeXtClassifier(sd))
+    if kind == "resnet50":
+        sd = synthetic.resnet_state_dict(depth=50, seed=0)
+        layers = {f"layer{i + 1}": [Bottleneck()] * n for i, n in enumerate((3, 4, 6, 3))}
+        return (ResNet(sd, fc=_NS(out_features=10), conv1=_NS(in_channels=1), **layers), lambda: ap.ResNetClassifier(sd, depth=50))
+    if kind == "vgg19":
+        sd = synthetic.vgg_state_dict(depth=19, seed=0)
+        feats = [Conv2d(1) if v != "M" else None for v in synthetic.VGG_CFG[19]]
+        return (VGG(sd, features=feats, classifier={6: _NS(out_features=10)}), lambda: ap.VGGClassifier(sd, depth=19))
+    if kind == "wrn16_4":
+        sd = synthetic.wideresnet_state_dict(depth=16, widen_factor=4, seed=0)
+        return (WideResNet(sd, block1=_NS(layer=[0, 0]), nChannels=256, fc=_NS(out_features=10), conv1=_NS(in_channels=1)),
+                lambda: ap.WideResNetClassifier(sd, depth=16, widen_factor=4))
+    if kind == "densenet22":
+        sd = synthetic.densenet_state_dict(depth=22, growth_rate=12, seed=0)
+        return (DenseNet(sd, dense1=[0, 0, 0], growthRate=12, trans1=_NS(conv1=_NS(in_channels=60, out_channels=30)),
+                         fc=_NS(out_features=10), conv1=_NS(in_channels=1)),
+                lambda: ap.DenseNetClassifier(sd, depth=22, growth_rate=12))
+    if kind == "m5":
+        sd = synthetic.m5_state_dict(seed=0)
+        return (M5(sd, conv1=_NS(kernel_size=(160,), stride=(16,), out_channels=32), fc1=_NS(out_features=10)),
+                lambda: ap.M5Classifier(sd))
+    raise KeyError(kind)

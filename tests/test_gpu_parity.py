@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_common import CONFIG_JSON, TorchNormalInjector, ToyDefendedModel, cuda, rel_l2, synthetic
+from gpu_common import (CONFIG_JSON, DataParallelStandIn, TorchNormalInjector, ToyDefendedModel, cuda, pickled_classifier, rel_l2,
+                        synthetic)
 
 pytestmark = pytest.mark.gpu
 
@@ -964,3 +965,19 @@ def test_densenet_vs_reference_golden(ap, golden, golden_grad, golden_vgg, key, 
     out = dn(big)
     (gb,) = torch.autograd.grad(out, big, g_logits.repeat(18, 1))
     assert torch.allclose(out[-2:], dn(spec.detach()), rtol=1e-5, atol=1e-4) and rel_l2(gb[-2:], gs) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["resnext", "resnet50", "vgg19", "wrn16_4", "densenet22", "m5"])
+def test_create_model_rebuilds_pickled_modules(ap, golden, tmp_path, kind):
+    """create_model (audio_models/ConvNets_SpeechCommands/create_model.py:8-16): torch.load of a WHOLE pickled module,
+    `.module` unwrapped when it was saved from DataParallel, rebuilt on the CUDA kernels from its state dict.  Stand-in classes
+    carry the reference's class names and the attributes the loader dispatches on."""
+    module, direct = pickled_classifier(kind)
+    path = str(tmp_path / f"{kind}-best-acc.pth")
+    torch.save(DataParallelStandIn(module) if kind in ("resnext", "vgg19") else module, path)
+    clf = ap.create_model(path)
+    x = cuda(synthetic.synthetic_waveforms(2, 16000, seed=3)) if kind == "m5" else cuda(golden["mel_sc09"])
+    assert type(clf) is type(direct()) and torch.equal(clf(x), direct()(x))
+    with pytest.raises(NotImplementedError):
+        torch.save(torch.nn.Linear(2, 2), path)
+        ap.create_model(path)

@@ -398,6 +398,30 @@ __global__ void __launch_bounds__(256) avgpool2_bwd_kernel(const float* __restri
     g_in[((b * H + hh) * W + w) * cs + c] = 0.25f * g_out[((b * Ho + (hh >> 1)) * Wo + (w >> 1)) * os + c];
   }
 }
+// Data gradient of a strided single-input-channel conv1d (M5's first layer: k = 160, stride 16, 1 -> 32 channels):
+//   g_x[b][n] = sum_{i : 0 <= n - i s < k} sum_c g_y[b][i][c] * w[c][n - i s]
+// The generic dgrad twin would run an implicit GEMM with ONE useful output column of its 128-wide tile over a 16x
+// zero-upsampled gradient (263 ms for 512 clips); here each thread owns one sample n and walks its <= k / s windows.
+__global__ void __launch_bounds__(256) conv1d_cin1_dgrad_kernel(const float* __restrict__ g_y, const float* __restrict__ w,
+                                                                float* __restrict__ g_x, int L, int lo, int k, int s, int Cc) {
+  extern __shared__ float ws[];   // [c][j]
+  for (int i = threadIdx.x; i < Cc * k; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const float* gy = g_y + static_cast<long long>(b) * lo * Cc;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < L; n += gridDim.x * blockDim.x) {
+    int i_hi = n / s;
+    if (i_hi > lo - 1) i_hi = lo - 1;
+    int i_lo = n - k + 1 <= 0 ? 0 : (n - k + s) / s;      // ceil((n - k + 1) / s)
+    float acc = 0.f;
+    for (int i = i_lo; i <= i_hi; ++i) {
+      const int j = n - i * s;
+      const float* row = gy + static_cast<long long>(i) * Cc;
+      for (int c = 0; c < Cc; ++c) acc = fmaf(row[c], ws[c * k + j], acc);
+    }
+    g_x[static_cast<long long>(b) * L + n] = acc;
+  }
+}
 // MaxPool2d(kernel 2, stride 2) on NHWC (models/vgg.py:73), H and W even
 __global__ void __launch_bounds__(256) maxpool2x2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W,
                                                          int C4) {
@@ -906,6 +930,7 @@ struct ap_classifier_s {
   std::vector<std::unique_ptr<ResBlock>> resblocks;
   // M5
   ConvLayer m5conv[4], m5conv_t[4];   // forward layers and their data-gradient twins
+  DevBuf m5_w0;                       // first layer's folded weights [c][j] for conv1d_cin1_dgrad_kernel
   // WideResNet: pre-activation blocks; bn1 of every block (and the final BatchNorm) as device scale / shift vectors
   struct WrnBlock {
     ConvLayer c1, c2, sc, t_c1, t_c2, t_sc;
@@ -2213,6 +2238,10 @@ static int vjp_m5(ap_classifier_t h, const float* wav, const float* g_out, float
   AP_REQUIRE(K <= 64, "M5 backward: at most 64 classes");
   if (!h->bwd_ready) {
     for (int i = 0; i < 4; ++i) {
+      if (i == 0 && h->m5conv[0].Cin == 1) {   // dedicated kernel, see conv1d_cin1_dgrad_kernel
+        AP_CUDA(h->m5_w0.upload(h->m5conv[0].wf_host.data(), h->m5conv[0].wf_host.size() * sizeof(float)));
+        continue;
+      }
       int rc = init_dgrad(h->m5conv_t[i], h->m5conv[i]);
       if (rc != AP_OK) return rc;
     }
@@ -2274,6 +2303,14 @@ static int vjp_m5(ap_classifier_t h, const float* wav, const float* g_out, float
       // g: (bn, len[i+1], Cout) -> t1: (bn, lo[i], Cout) through max-pool + ReLU
       maxpool4_relu_bwd_kernel<<<grid_for(static_cast<long long>(bn) * lo[i] * cv.Cout), 256, 0, st>>>(g, a, t1, bn, lo[i], cv.Cout);
       AP_LAUNCH_CHECK();
+      if (i == 0 && h->m5_w0.p) {
+        const size_t smem = static_cast<size_t>(cv.Cout) * cv.kw * sizeof(float);
+        dim3 grid(static_cast<unsigned>(std::min(ceil_div(L, 256), 64)), static_cast<unsigned>(bn));
+        conv1d_cin1_dgrad_kernel<<<grid, 256, smem, st>>>(t1, h->m5_w0.as<float>(), g_wav + static_cast<size_t>(b0) * L, L, lo[0],
+                                                         cv.kw, cv.stride, cv.Cout);
+        AP_LAUNCH_CHECK();
+        continue;
+      }
       const float* src = t1;
       int lsrc = lo[i];
       if (cv.stride > 1) {   // zero-upsample to length len - k + 1 (stride-1 geometry of the transposed convolution)

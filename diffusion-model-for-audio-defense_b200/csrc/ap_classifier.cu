@@ -104,7 +104,7 @@ struct ConvLayer {
     AP_CUDA(bias.upload(bp.data(), bp.size() * sizeof(float)));
     if (keep_host) wf_host = wf;
     // structural part of conv_tc_supported (the spatial part is checked when the layer is bound to buffers)
-    if (want_tc && Cg % 32 == 0 && (Ng == 64 || Ng == 128 || Ng % 256 == 0)) {
+    if (want_tc && Cg % 32 == 0 && conv_tc_n_tile(Ng) != 0) {
       int rc = tc.init(cin, cout, kh, kw, stride, pad, groups, wf.data(), bp.data());
       if (rc != AP_OK) return rc;
       has_tc = true;
@@ -304,15 +304,22 @@ __global__ void __launch_bounds__(256) maxpool4_kernel(const float* __restrict__
 // MaxPool2d(kernel 3, stride 2, padding 1) over NHWC [B][H][W][C] -> [B][Ho][Wo][C]   (torchvision ResNet stem, resnet.py:112)
 // y = relu(x * scale[c] + shift[c]) on NHWC: a pre-activation BatchNorm (eval) + ReLU that cannot fold into a convolution
 // because it acts on a residual sum (models/wideresnet.py:31-35,87)
+__device__ __forceinline__ float round_tf32_rne(float x) {   // what the tensor-core path's consumers expect (ap_conv_tc.cu)
+  uint32_t u = __float_as_uint(x);
+  u = (u + 0x00000fffu + ((u >> 13) & 1u)) & 0xffffe000u;
+  return __uint_as_float(u);
+}
 __global__ void __launch_bounds__(256) bn_relu_kernel(const float4* __restrict__ x, const float4* __restrict__ scale,
                                                       const float4* __restrict__ shift, float4* __restrict__ y, long long n4,
-                                                      int C4) {
+                                                      int C4, int round_out) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C4);
     const float4 v = x[i], a = scale[c], b = shift[c];
-    y[i] = make_float4(fmaxf(fmaf(v.x, a.x, b.x), 0.f), fmaxf(fmaf(v.y, a.y, b.y), 0.f), fmaxf(fmaf(v.z, a.z, b.z), 0.f),
-                       fmaxf(fmaf(v.w, a.w, b.w), 0.f));
+    float4 o = make_float4(fmaxf(fmaf(v.x, a.x, b.x), 0.f), fmaxf(fmaf(v.y, a.y, b.y), 0.f), fmaxf(fmaf(v.z, a.z, b.z), 0.f),
+                           fmaxf(fmaf(v.w, a.w, b.w), 0.f));
+    if (round_out) o = make_float4(round_tf32_rne(o.x), round_tf32_rne(o.y), round_tf32_rne(o.z), round_tf32_rne(o.w));
+    y[i] = o;
   }
 }
 // its backward: g_x = (act > 0 ? g_act * scale[c] : 0) + skip   (skip: the identity-shortcut gradient, or null)
@@ -915,6 +922,15 @@ struct ap_classifier_s {
   int mode = AP_MODE_FP32;                        // AP_MODE_TF32: tensor-core convolutions where the shape allows
   unsigned tc_mask = 7;                           // bit 0: 1x1, bit 1: 3x3 stride 1, bit 2: strided (AP_CLS_TC_MASK, bisecting aid)
   std::map<int, std::vector<ConvStep>> plans;     // keyed by the number of images in the chunk
+  struct TcSlot {   // one convolution of a VGG / WideResNet pass bound to the buffers it was last run on
+    const float* in = nullptr;
+    float* out = nullptr;
+    const float* res = nullptr;
+    int relu = -1, bn = 0;
+    bool tc = false;
+    ConvTcBinding bnd;
+  };
+  std::vector<TcSlot> tc_slots;
   // ResNeXt
   ConvLayer stem;
   std::vector<std::unique_ptr<Bottleneck>> blocks;
@@ -1517,6 +1533,23 @@ static int vjp_resnet(ap_classifier_t h, const float* spec, const float* g_logit
   return AP_OK;
 }
 
+// A convolution of a VGG / WideResNet inference pass: tf32 tensor cores when the classifier is in AP_MODE_TF32 and the layer
+// has a tensor-core twin for this geometry, else the fp32 FFMA implicit GEMM.  Slot `si` caches the tensor maps of the buffers the
+// convolution ran on last time (they are re-encoded when a buffer moved or the chunk size changed).
+static int conv_auto(ap_classifier_t h, size_t si, const ConvLayer& L, const float* in, int bn, int H, int W, float* out,
+                     const float* res, int relu, int round_out, cudaStream_t st) {
+  if (h->mode != AP_MODE_TF32 || !L.has_tc || !conv_tc_supported(L.Cin, L.Cout, L.groups, H, W, L.kh, L.kw, L.stride, L.pad))
+    return L.run(in, bn, H, W, out, res, relu, st);
+  if (h->tc_slots.size() <= si) h->tc_slots.resize(si + 1);
+  auto& s = h->tc_slots[si];
+  if (!s.tc || s.in != in || s.out != out || s.res != res || s.relu != relu || s.bn != bn) {
+    int rc = L.tc.bind(&s.bnd, in, bn, H, W, out, res, relu, round_out);
+    if (rc != AP_OK) return rc;
+    s.in = in, s.out = out, s.res = res, s.relu = relu, s.bn = bn, s.tc = true;
+  }
+  return L.tc.run(s.bnd, st);
+}
+
 // ---- VGG-11/13/16/19 with batch norm (models/vgg.py:32-95; the SC09 factory builds vgg19_bn, models/__init__.py:44-45).
 // state_dict order: features.{i}.{weight,bias} + BatchNorm {weight,bias,running_mean,running_var} per convolution, then
 // classifier.{0,3,6}.{weight,bias}.  Every 3x3 convolution folds its bias and BatchNorm; Dropout is the identity in eval mode;
@@ -1542,7 +1575,7 @@ static int create_vgg(ap_classifier_t h, const float* const* w, int n_weights) {
     if (v < 0) continue;
     auto L = std::make_unique<ConvLayer>();
     L->keep_host = true;
-    int rc = L->init(cin, v, 3, 3, 1, 1, 1, w[i], w[i + 1], w[i + 2], w[i + 3], w[i + 4], w[i + 5]);
+    int rc = L->init(cin, v, 3, 3, 1, 1, 1, w[i], w[i + 1], w[i + 2], w[i + 3], w[i + 4], w[i + 5], true);
     if (rc != AP_OK) return rc;
     h->vgg_conv.push_back(std::move(L));
     i += 6, cin = v;
@@ -1550,7 +1583,7 @@ static int create_vgg(ap_classifier_t h, const float* const* w, int n_weights) {
   const int dims[4] = {512, 4096, 4096, c.num_classes};
   for (int j = 0; j < 3; ++j) {
     h->vgg_fc[j].keep_host = true;
-    int rc = h->vgg_fc[j].init(dims[j], dims[j + 1], 1, 1, 1, 0, 1, w[i], w[i + 1], nullptr, nullptr, nullptr, nullptr);
+    int rc = h->vgg_fc[j].init(dims[j], dims[j + 1], 1, 1, 1, 0, 1, w[i], w[i + 1], nullptr, nullptr, nullptr, nullptr, true);
     if (rc != AP_OK) return rc;
     i += 2;
   }
@@ -1578,9 +1611,9 @@ static int forward_vgg(ap_classifier_t h, const float* spec, float* logits, int 
     for (int v : h->vgg_plan) {
       float* y = nxt[which];
       if (v > 0) {
-        rc = h->vgg_conv[ci++]->run(x, bn, H, W, y, nullptr, 1, st);                                     // vgg.py:75-78
+        rc = conv_auto(h, ci, *h->vgg_conv[ci], x, bn, H, W, y, nullptr, 1, 1, st);                      // vgg.py:75-78
         if (rc != AP_OK) return rc;
-        C = v;
+        ++ci, C = v;
       } else {
         maxpool2x2_kernel<<<vgg_grid(static_cast<long long>(bn) * (H / 2) * (W / 2) * (C / 4)), 256, 0, st>>>(
             reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), bn, H, W, C / 4);
@@ -1591,7 +1624,7 @@ static int forward_vgg(ap_classifier_t h, const float* spec, float* logits, int 
     }
     for (int j = 0; j < 3; ++j) {                                                                        // vgg.py:36-44
       float* y = j == 2 ? logits + static_cast<size_t>(b0) * h->cfg.num_classes : nxt[which];
-      rc = h->vgg_fc[j].run(x, bn, 1, 1, y, nullptr, j < 2, st);
+      rc = conv_auto(h, ci + j, h->vgg_fc[j], x, bn, 1, 1, y, nullptr, j < 2, 1, st);
       if (rc != AP_OK) return rc;
       x = y, which ^= 1;
     }
@@ -1739,11 +1772,12 @@ static int create_wrn(ap_classifier_t h, const float* const* w, int n_weights) {
       blk->equal = blk->cin == blk->cout;
       blk->c1.keep_host = blk->c2.keep_host = blk->sc.keep_host = true;
       rc = bn_vectors(blk->scale, blk->shift, w + i, blk->cin);
-      if (rc == AP_OK) rc = blk->c1.init(blk->cin, blk->cout, 3, 3, blk->stride, 1, 1, w[i + 4], nullptr, w[i + 5], w[i + 6], w[i + 7], w[i + 8]);
-      if (rc == AP_OK) rc = blk->c2.init(blk->cout, blk->cout, 3, 3, 1, 1, 1, w[i + 9], nullptr, nullptr, nullptr, nullptr, nullptr);
+      if (rc == AP_OK)
+        rc = blk->c1.init(blk->cin, blk->cout, 3, 3, blk->stride, 1, 1, w[i + 4], nullptr, w[i + 5], w[i + 6], w[i + 7], w[i + 8], true);
+      if (rc == AP_OK) rc = blk->c2.init(blk->cout, blk->cout, 3, 3, 1, 1, 1, w[i + 9], nullptr, nullptr, nullptr, nullptr, nullptr, true);
       i += 10;
       if (rc == AP_OK && !blk->equal) {
-        rc = blk->sc.init(blk->cin, blk->cout, 1, 1, blk->stride, 0, 1, w[i], nullptr, nullptr, nullptr, nullptr, nullptr);
+        rc = blk->sc.init(blk->cin, blk->cout, 1, 1, blk->stride, 0, 1, w[i], nullptr, nullptr, nullptr, nullptr, nullptr, true);
         i += 1;
       }
       if (rc != AP_OK) return rc;
@@ -1757,9 +1791,10 @@ static int create_wrn(ap_classifier_t h, const float* const* w, int n_weights) {
   return AP_OK;
 }
 
-static int wrn_bn_relu(const float* x, const DevBuf& scale, const DevBuf& shift, float* y, long long elems, int C, cudaStream_t st) {
+static int wrn_bn_relu(const float* x, const DevBuf& scale, const DevBuf& shift, float* y, long long elems, int C, int round_out,
+                       cudaStream_t st) {
   bn_relu_kernel<<<vgg_grid(elems / 4), 256, 0, st>>>(reinterpret_cast<const float4*>(x), scale.as<float4>(), shift.as<float4>(),
-                                                      reinterpret_cast<float4*>(y), elems / 4, C / 4);
+                                                      reinterpret_cast<float4*>(y), elems / 4, C / 4, round_out);
   AP_LAUNCH_CHECK();
   return AP_OK;
 }
@@ -1778,20 +1813,23 @@ static int wrn_pass(ap_classifier_t h, const float* spec, float* logits, int bn,
     float* a = tape ? (*tape)[2 * l]->as<float>() : h->buf[2].as<float>();
     float* hh = tape ? (*tape)[2 * l + 1]->as<float>() : h->buf[3].as<float>();
     const int Ho = H / b.stride, Wo = W / b.stride;
-    rc = wrn_bn_relu(x, b.scale, b.shift, a, static_cast<long long>(bn) * H * W * b.cin, b.cin, st);       // :31-34
+    // the recomputed forward of the backward pass (tape) stays on the fp32 path: its ReLU masks must match an fp32 forward
+    const bool tc = !tape && h->mode == AP_MODE_TF32;
+    rc = wrn_bn_relu(x, b.scale, b.shift, a, static_cast<long long>(bn) * H * W * b.cin, b.cin, tc, st);   // :31-34
     const float* res = x;
     if (rc == AP_OK && !b.equal) {
-      rc = b.sc.run(a, bn, H, W, h->buf[4].as<float>(), nullptr, 0, st);                                   // :39
+      rc = tc ? conv_auto(h, 3 * l, b.sc, a, bn, H, W, h->buf[4].as<float>(), nullptr, 0, 0, st)
+              : b.sc.run(a, bn, H, W, h->buf[4].as<float>(), nullptr, 0, st);                              // :39
       res = h->buf[4].as<float>();
     }
-    if (rc == AP_OK) rc = b.c1.run(a, bn, H, W, hh, nullptr, 1, st);                                       // :35
-    if (rc == AP_OK) rc = b.c2.run(hh, bn, Ho, Wo, xo, res, 0, st);                                        // :38-39
+    if (rc == AP_OK) rc = tc ? conv_auto(h, 3 * l + 1, b.c1, a, bn, H, W, hh, nullptr, 1, 1, st) : b.c1.run(a, bn, H, W, hh, nullptr, 1, st);   // :35
+    if (rc == AP_OK) rc = tc ? conv_auto(h, 3 * l + 2, b.c2, hh, bn, Ho, Wo, xo, res, 0, 0, st) : b.c2.run(hh, bn, Ho, Wo, xo, res, 0, st);     // :38-39
     if (rc != AP_OK) return rc;
     std::swap(x, xo);
     H = Ho, W = Wo;
   }
   float* f = tape ? (*tape)[2 * h->wrn.size()]->as<float>() : xo;
-  rc = wrn_bn_relu(x, h->wrn_scale, h->wrn_shift, f, static_cast<long long>(bn) * H * W * h->feat, h->feat, st);   // :87
+  rc = wrn_bn_relu(x, h->wrn_scale, h->wrn_shift, f, static_cast<long long>(bn) * H * W * h->feat, h->feat, 0, st);   // :87
   if (rc != AP_OK) return rc;
   const size_t smem = sizeof(float) * (h->feat + h->cfg.num_classes);
   pool_fc_kernel<<<bn, 256, smem, st>>>(f, H * W, h->feat, h->fc_w.as<float>(), h->fc_b.as<float>(), h->cfg.num_classes, logits, 0);
@@ -2414,8 +2452,14 @@ extern "C" int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cf
     case AP_CLS_M5: rc = create_m5(h, weights, n_weights); break;
     case AP_CLS_RESNET: rc = create_resnet(h, weights, n_weights); break;
     case AP_CLS_KWS: rc = create_kws(h, weights, n_weights); break;
-    case AP_CLS_VGG: rc = create_vgg(h, weights, n_weights); break;
-    case AP_CLS_WRN: rc = create_wrn(h, weights, n_weights); break;
+    case AP_CLS_VGG:   // tf32 by default, as for ResNeXt: what cuDNN runs for the reference's convolutions on this GPU
+      rc = create_vgg(h, weights, n_weights);
+      h->mode = AP_MODE_TF32;
+      break;
+    case AP_CLS_WRN:
+      rc = create_wrn(h, weights, n_weights);
+      h->mode = AP_MODE_TF32;
+      break;
     case AP_CLS_DENSENET: rc = create_dn(h, weights, n_weights); break;
     default: rc = fail(AP_ERR_INVALID, "ap_classifier_create: unknown classifier kind %d", cfg->kind);
   }
@@ -2464,8 +2508,9 @@ extern "C" int ap_classifier_vjp(ap_classifier_t h, const float* input, const fl
 extern "C" int ap_classifier_set_mode(ap_classifier_t h, int mode) {
   AP_REQUIRE(h, "ap_classifier_set_mode: null handle");
   AP_REQUIRE(mode == AP_MODE_FP32 || mode == AP_MODE_TF32, "ap_classifier_set_mode: mode must be AP_MODE_FP32 or AP_MODE_TF32");
-  AP_REQUIRE(mode == AP_MODE_FP32 || h->cfg.kind == AP_CLS_RESNEXT, "ap_classifier_set_mode: only ResNeXt has tensor-core convolutions");
-  if (mode != h->mode) h->plans.clear();
+  AP_REQUIRE(mode == AP_MODE_FP32 || h->cfg.kind == AP_CLS_RESNEXT || h->cfg.kind == AP_CLS_VGG || h->cfg.kind == AP_CLS_WRN,
+             "ap_classifier_set_mode: only ResNeXt, VGG and WideResNet have tensor-core convolutions");
+  if (mode != h->mode) h->plans.clear(), h->tc_slots.clear();
   h->mode = mode;
   return AP_OK;
 }

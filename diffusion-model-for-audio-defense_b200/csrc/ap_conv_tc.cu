@@ -198,12 +198,20 @@ static inline float host_round_tf32(float x) {
   return y;
 }
 
+// Output channels per tile (the UMMA N): 256 where it divides the group width, the whole group for 64 / 128, and 160 for
+// WideResNet's 160 / 320 / 640-channel layers (any multiple of 32 up to 256 is a legal N for M = 128; the epilogue works in
+// 32-column slabs).  0: no tensor-core tile for this width.
+int conv_tc_n_tile(int Ng) {
+  if (Ng > 0 && Ng % 256 == 0) return 256;
+  if (Ng == 64 || Ng == 128) return Ng;
+  if (Ng > 0 && Ng % 160 == 0) return 160;
+  return 0;
+}
+
 bool conv_tc_supported(int Cin, int Cout, int groups, int H, int W, int kh, int kw, int stride, int pad) {
   if (groups <= 0 || Cin % groups || Cout % groups) return false;
   const int Cg = Cin / groups, Ng = Cout / groups;
-  if (Cg % 32 || Ng % 64) return false;
-  if (Ng > 256 && Ng % 256) return false;
-  if (Ng < 256 && Ng != 64 && Ng != 128) return false;
+  if (Cg % 32 || conv_tc_n_tile(Ng) == 0) return false;
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
   if (Wo <= 0 || Ho <= 0 || Wo > 128 || 128 % Wo) return false;
   const int rows = 128 / Wo;                       // output rows per 128-pixel tile
@@ -214,7 +222,8 @@ bool conv_tc_supported(int Cin, int Cout, int groups, int H, int W, int kh, int 
 int ConvTc::init(int cin, int cout, int kh_, int kw_, int stride_, int pad_, int groups_, const float* w_folded /*[Cout][Cg][kh][kw]*/,
                  const float* bias_folded) {
   Cin = cin, Cout = cout, kh = kh_, kw = kw_, stride = stride_, pad = pad_, groups = groups_;
-  Cg = cin / groups, Ng = cout / groups, NT = Ng >= 256 ? 256 : Ng, K = kh * kw * Cg;
+  Cg = cin / groups, Ng = cout / groups, NT = conv_tc_n_tile(Ng), K = kh * kw * Cg;
+  if (NT == 0 || Cg % 32) return fail(AP_ERR_INVALID, "ConvTc: no tensor-core tile for %d -> %d channels per group", Cg, Ng);
   std::vector<float> wp(static_cast<size_t>(cout) * K);
   for (int o = 0; o < cout; ++o)
     for (int c = 0; c < Cg; ++c)

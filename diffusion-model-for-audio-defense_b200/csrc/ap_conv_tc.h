@@ -22,6 +22,7 @@ struct ConvTcBinding {   // one convolution bound to concrete activation buffers
   CUtensorMap tmA, tmOut, tmRes;
   ConvTcParams p;
 };
+int conv_tc_n_tile(int Ng);   // output channels per tensor-core tile for a group width, 0 if none
 bool conv_tc_supported(int Cin, int Cout, int groups, int H, int W, int kh, int kw, int stride, int pad);
 
 struct ConvTc {

@@ -901,7 +901,7 @@ def test_vgg_vs_reference_golden(ap, golden, golden_grad, golden_vgg, depth):
     """vgg11_bn / vgg19_bn (models/vgg.py:32-95; `--classifier_model vgg19_bn`, adaptive_attack_eval.py:21) on the CUDA
     path: logits, top-1 and the input gradient against the unmodified reference; a batch that spans two chunks of the
     backward (64 + 6) must reproduce the single-image results."""
-    vg = ap.VGGClassifier(synthetic.vgg_state_dict(depth=depth, seed=0), depth=depth)
+    vg = ap.VGGClassifier(synthetic.vgg_state_dict(depth=depth, seed=0), depth=depth).set_mode("fp32")
     logits = vg(cuda(golden["mel_sc09"])).cpu().numpy()
     want = golden_vgg[f"vgg{depth}_logits"]
     assert np.abs(logits - want).max() < 1e-3 * max(1.0, np.abs(want).max())
@@ -916,8 +916,12 @@ def test_vgg_vs_reference_golden(ap, golden, golden_grad, golden_vgg, depth):
     out = vg(big)
     (gb,) = torch.autograd.grad(out, big, g_logits.repeat(35, 1))
     assert torch.allclose(out[-2:], vg(spec.detach()), atol=1e-5) and rel_l2(gb[-2:], gs) < 1e-5
-    with pytest.raises(ap.AudioPureError):
-        vg.set_mode("tf32")
+    # tf32 tensor-core convolutions (what cuDNN runs for the reference on this GPU by default): 10-bit mantissa operands
+    lt = vg.set_mode("tf32")(cuda(golden["mel_sc09"])).cpu().numpy()
+    print(f"VGG-{depth} tf32 logits max err {np.abs(lt - want).max():.2e}")
+    assert np.abs(lt - want).max() < 2e-2 * max(1.0, np.abs(want).max()) and (lt.argmax(1) == want.argmax(1)).all()
+    big_t = vg(big.detach())                                                     # 70 images: several images per tile + a ragged tail
+    assert torch.allclose(big_t[-2:], torch.from_numpy(lt).cuda(), atol=1e-5) and torch.allclose(big_t[:2], big_t[-2:], atol=1e-5)
 
 
 @pytest.mark.parametrize("key,depth,k", [("wrn28_10", 28, 10), ("wrn16_1", 16, 1)])
@@ -926,6 +930,7 @@ def test_wideresnet_vs_reference_golden(ap, golden, golden_grad, golden_vgg, key
     narrow WRN-16-1 (equal-width first block) on the CUDA path: logits, top-1 and the input gradient against the unmodified
     reference; a batch that spans two chunks of the backward (32 + 4) must reproduce the two-image results."""
     wr = ap.WideResNetClassifier(synthetic.wideresnet_state_dict(depth=depth, widen_factor=k, seed=0), depth=depth, widen_factor=k)
+    wr.set_mode("fp32")
     logits = wr(cuda(golden["mel_sc09"])).cpu().numpy()
     want = golden_vgg[f"{key}_logits"]
     assert np.abs(logits - want).max() < 1e-3 * max(1.0, np.abs(want).max())
@@ -942,6 +947,12 @@ def test_wideresnet_vs_reference_golden(ap, golden, golden_grad, golden_vgg, key
     out = wr(big)
     (gb,) = torch.autograd.grad(out, big, g_logits.repeat(18, 1))
     assert torch.allclose(out[-2:], wr(spec.detach()), rtol=1e-5, atol=1e-4) and rel_l2(gb[-2:], gs) < 1e-5
+    # tf32 tensor-core convolutions (N = 160 tiles for the 160 / 320 / 640-channel layers of WRN-28-10; WRN-16-1 has none)
+    lt = wr.set_mode("tf32")(cuda(golden["mel_sc09"])).cpu().numpy()
+    print(f"{key} tf32 logits max err {np.abs(lt - want).max():.2e} (max |logit| {np.abs(want).max():.1f})")
+    assert np.abs(lt - want).max() < 2e-2 * max(1.0, np.abs(want).max()) and (lt.argmax(1) == want.argmax(1)).all()
+    big_t = wr(big.detach())
+    assert torch.allclose(big_t[-2:], torch.from_numpy(lt).cuda(), rtol=1e-5, atol=1e-4)
 
 
 @pytest.mark.parametrize("key,depth", [("densenet100_12", 100), ("densenet22_12", 22)])
@@ -965,6 +976,8 @@ def test_densenet_vs_reference_golden(ap, golden, golden_grad, golden_vgg, key, 
     out = dn(big)
     (gb,) = torch.autograd.grad(out, big, g_logits.repeat(18, 1))
     assert torch.allclose(out[-2:], dn(spec.detach()), rtol=1e-5, atol=1e-4) and rel_l2(gb[-2:], gs) < 1e-5
+    with pytest.raises(ap.AudioPureError):
+        dn.set_mode("tf32")
 
 
 @pytest.mark.parametrize("kind", ["resnext", "resnet50", "vgg19", "wrn16_4", "densenet22", "m5"])

@@ -56,7 +56,12 @@ class ToyDefendedModel:
     def __call__(self, x):
         e = torch.from_numpy(synthetic.host_noise(tuple(x.shape), self.seed, self.i)).to(x.device)
         self.i += 1
-        return torch.tanh((x + 0.05 * e)[:, 0, :] @ self.W.to(x.device)) * 4
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False          # the stand-in must be an fp32 function on every device
+        try:
+            return torch.tanh((x + 0.05 * e)[:, 0, :] @ self.W.to(x.device)) * 4
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 # ---- stand-ins for the reference's pickled classifier modules (create_model.py:8-16 unpickles WHOLE modules; the GPU box has

@@ -36,6 +36,7 @@ def test_vs_pytorch_eager_on_the_same_gpu():
             cache[key] = torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype)
         return cache[key]
 
+    tf32_flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = True
     import torchaudio
@@ -60,6 +61,7 @@ def test_vs_pytorch_eager_on_the_same_gpu():
         t_eager = time.perf_counter() - t0
     finally:
         orc._t, orc.step_embedding = orig_t, orig_se
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_flags     # later tests use fp32 torch ops
 
     # ---- hand-written path, same inputs and the same host noise
     dw = ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=t_star, state_dict=sd, noise="torch")

@@ -1533,12 +1533,20 @@ static int vjp_resnet(ap_classifier_t h, const float* spec, const float* g_logit
   return AP_OK;
 }
 
-// A convolution of a VGG / WideResNet inference pass: tf32 tensor cores when the classifier is in AP_MODE_TF32 and the layer
+// The recomputed forward of a VGG / WideResNet backward pass runs on the tensor cores in AP_MODE_TF32 (the gradient is then that of
+// the tf32 network: its ReLU masks differ from an fp32 forward's in a few units, which moves the input gradient by a few per cent,
+// see DESIGN.md "Backward pass") unless AP_CLS_VJP_FWD_FP32=1 keeps it on the fp32 path, as for ResNeXt.
+static bool tape_on_tensor_cores(const ap_classifier_s* h) {
+  const char* e = std::getenv("AP_CLS_VJP_FWD_FP32");   // read per call, like vjp_resnext
+  return h->mode == AP_MODE_TF32 && !(e && std::atoi(e) != 0);
+}
+
+// A convolution of a VGG / WideResNet pass: tf32 tensor cores when the classifier is in AP_MODE_TF32 and the layer
 // has a tensor-core twin for this geometry, else the fp32 FFMA implicit GEMM.  Slot `si` caches the tensor maps of the buffers the
 // convolution ran on last time (they are re-encoded when a buffer moved or the chunk size changed).
 static int conv_auto(ap_classifier_t h, size_t si, const ConvLayer& L, const float* in, int bn, int H, int W, float* out,
-                     const float* res, int relu, int round_out, cudaStream_t st) {
-  if (h->mode != AP_MODE_TF32 || !L.has_tc || !conv_tc_supported(L.Cin, L.Cout, L.groups, H, W, L.kh, L.kw, L.stride, L.pad))
+                     const float* res, int relu, int round_out, cudaStream_t st, bool allow_tc = true) {
+  if (!allow_tc || h->mode != AP_MODE_TF32 || !L.has_tc || !conv_tc_supported(L.Cin, L.Cout, L.groups, H, W, L.kh, L.kw, L.stride, L.pad))
     return L.run(in, bn, H, W, out, res, relu, st);
   if (h->tc_slots.size() <= si) h->tc_slots.resize(si + 1);
   auto& s = h->tc_slots[si];
@@ -1639,15 +1647,17 @@ static int vjp_vgg(ap_classifier_t h, const float* spec, const float* g_logits, 
   AP_REQUIRE(H0 == 32 && W0 == 32, "VGG backward: input must be 32x32 (got %dx%d)", H0, W0);
   const int chunk = 64;
   const size_t n_layers = h->vgg_plan.size();
+  const size_t NS = h->vgg_conv.size() + 3;     // tensor-map slots: [0, NS) inference, [NS, 2 NS) recomputed forward, [2 NS, 3 NS) backward
+  const bool tape_tc = tape_on_tensor_cores(h);
   if (!h->bwd_ready) {
     for (auto& L : h->vgg_conv) {
       auto T = std::make_unique<ConvLayer>();
-      int rc = init_dgrad(*T, *L);
+      int rc = init_dgrad(*T, *L, true);
       if (rc != AP_OK) return rc;
       h->vgg_conv_t.push_back(std::move(T));
     }
     for (int j = 0; j < 3; ++j) {
-      int rc = init_dgrad(h->vgg_fc_t[j], h->vgg_fc[j]);
+      int rc = init_dgrad(h->vgg_fc_t[j], h->vgg_fc[j], true);
       if (rc != AP_OK) return rc;
     }
     h->bwd_ready = true;
@@ -1684,9 +1694,9 @@ static int vjp_vgg(ap_classifier_t h, const float* spec, const float* g_logits, 
       float* y = h->tape[l]->as<float>();
       const int v = h->vgg_plan[l];
       if (v > 0) {
-        rc = h->vgg_conv[ci++]->run(x, bn, H, W, y, nullptr, 1, st);
+        rc = conv_auto(h, NS + ci, *h->vgg_conv[ci], x, bn, H, W, y, nullptr, 1, 1, st, tape_tc);
         if (rc != AP_OK) return rc;
-        C = v;
+        ++ci, C = v;
       } else {
         maxpool2x2_kernel<<<vgg_grid(static_cast<long long>(bn) * (H / 2) * (W / 2) * (C / 4)), 256, 0, st>>>(
             reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), bn, H, W, C / 4);
@@ -1696,8 +1706,8 @@ static int vjp_vgg(ap_classifier_t h, const float* spec, const float* g_logits, 
       x = y;
     }
     float *f1 = h->tape[n_layers]->as<float>(), *f2 = h->tape[n_layers + 1]->as<float>();
-    rc = h->vgg_fc[0].run(x, bn, 1, 1, f1, nullptr, 1, st);
-    if (rc == AP_OK) rc = h->vgg_fc[1].run(f1, bn, 1, 1, f2, nullptr, 1, st);
+    rc = conv_auto(h, NS + ci, h->vgg_fc[0], x, bn, 1, 1, f1, nullptr, 1, 1, st, tape_tc);
+    if (rc == AP_OK) rc = conv_auto(h, NS + ci + 1, h->vgg_fc[1], f1, bn, 1, 1, f2, nullptr, 1, 1, st, tape_tc);
     if (rc != AP_OK) return rc;
     // ---- backward
     float *GA = h->gbuf[0].as<float>(), *GB = h->gbuf[1].as<float>();
@@ -1709,9 +1719,9 @@ static int vjp_vgg(ap_classifier_t h, const float* spec, const float* g_logits, 
     };
     rc = h->vgg_fc_t[2].run(g_logits + static_cast<size_t>(b0) * h->cfg.num_classes, bn, 1, 1, GA, nullptr, 0, st);
     if (rc == AP_OK) rc = mask(GA, f2, static_cast<size_t>(bn) * 4096);
-    if (rc == AP_OK) rc = h->vgg_fc_t[1].run(GA, bn, 1, 1, GB, nullptr, 0, st);
+    if (rc == AP_OK) rc = conv_auto(h, 2 * NS + ci + 1, h->vgg_fc_t[1], GA, bn, 1, 1, GB, nullptr, 0, 0, st);
     if (rc == AP_OK) rc = mask(GB, f1, static_cast<size_t>(bn) * 4096);
-    if (rc == AP_OK) rc = h->vgg_fc_t[0].run(GB, bn, 1, 1, GA, nullptr, 0, st);      // gradient of the pooled 1x1x512 features
+    if (rc == AP_OK) rc = conv_auto(h, 2 * NS + ci, h->vgg_fc_t[0], GB, bn, 1, 1, GA, nullptr, 0, 0, st);   // gradient of the pooled 1x1x512 features
     if (rc != AP_OK) return rc;
     for (int l = static_cast<int>(n_layers) - 1; l >= 0; --l) {
       const int v = h->vgg_plan[l];
@@ -1720,7 +1730,7 @@ static int vjp_vgg(ap_classifier_t h, const float* spec, const float* g_logits, 
         --ci;
         rc = mask(GA, h->tape[l]->as<float>(), static_cast<size_t>(bn) * H * W * C);
         float* dst = l == 0 ? g_spec + static_cast<size_t>(b0) * H0 * W0 : GB;
-        if (rc == AP_OK) rc = h->vgg_conv_t[ci]->run(GA, bn, H, W, dst, nullptr, 0, st);
+        if (rc == AP_OK) rc = conv_auto(h, 2 * NS + ci, *h->vgg_conv_t[ci], GA, bn, H, W, dst, nullptr, 0, 0, st);
         if (rc != AP_OK) return rc;
         C = h->vgg_conv[ci]->Cin;
       } else {
@@ -1813,17 +1823,17 @@ static int wrn_pass(ap_classifier_t h, const float* spec, float* logits, int bn,
     float* a = tape ? (*tape)[2 * l]->as<float>() : h->buf[2].as<float>();
     float* hh = tape ? (*tape)[2 * l + 1]->as<float>() : h->buf[3].as<float>();
     const int Ho = H / b.stride, Wo = W / b.stride;
-    // the recomputed forward of the backward pass (tape) stays on the fp32 path: its ReLU masks must match an fp32 forward
-    const bool tc = !tape && h->mode == AP_MODE_TF32;
+    const bool tc = h->mode == AP_MODE_TF32 && (!tape || tape_on_tensor_cores(h));
+    const size_t sb = tape ? 3 * h->wrn.size() : 0;       // tensor-map slots of the recomputed forward follow the inference ones
     rc = wrn_bn_relu(x, b.scale, b.shift, a, static_cast<long long>(bn) * H * W * b.cin, b.cin, tc, st);   // :31-34
     const float* res = x;
     if (rc == AP_OK && !b.equal) {
-      rc = tc ? conv_auto(h, 3 * l, b.sc, a, bn, H, W, h->buf[4].as<float>(), nullptr, 0, 0, st)
+      rc = tc ? conv_auto(h, sb + 3 * l, b.sc, a, bn, H, W, h->buf[4].as<float>(), nullptr, 0, 0, st)
               : b.sc.run(a, bn, H, W, h->buf[4].as<float>(), nullptr, 0, st);                              // :39
       res = h->buf[4].as<float>();
     }
-    if (rc == AP_OK) rc = tc ? conv_auto(h, 3 * l + 1, b.c1, a, bn, H, W, hh, nullptr, 1, 1, st) : b.c1.run(a, bn, H, W, hh, nullptr, 1, st);   // :35
-    if (rc == AP_OK) rc = tc ? conv_auto(h, 3 * l + 2, b.c2, hh, bn, Ho, Wo, xo, res, 0, 0, st) : b.c2.run(hh, bn, Ho, Wo, xo, res, 0, st);     // :38-39
+    if (rc == AP_OK) rc = tc ? conv_auto(h, sb + 3 * l + 1, b.c1, a, bn, H, W, hh, nullptr, 1, 1, st) : b.c1.run(a, bn, H, W, hh, nullptr, 1, st);   // :35
+    if (rc == AP_OK) rc = tc ? conv_auto(h, sb + 3 * l + 2, b.c2, hh, bn, Ho, Wo, xo, res, 0, 0, st) : b.c2.run(hh, bn, Ho, Wo, xo, res, 0, st);     // :38-39
     if (rc != AP_OK) return rc;
     std::swap(x, xo);
     H = Ho, W = Wo;
@@ -1859,9 +1869,9 @@ static int vjp_wrn(ap_classifier_t h, const float* spec, const float* g_logits, 
   if (!h->bwd_ready) {
     int rc = init_dgrad(h->t_stem, h->stem);
     for (auto& b : h->wrn) {
-      if (rc == AP_OK) rc = init_dgrad(b->t_c1, b->c1);
-      if (rc == AP_OK) rc = init_dgrad(b->t_c2, b->c2);
-      if (rc == AP_OK && !b->equal) rc = init_dgrad(b->t_sc, b->sc);
+      if (rc == AP_OK) rc = init_dgrad(b->t_c1, b->c1, true);
+      if (rc == AP_OK) rc = init_dgrad(b->t_c2, b->c2, true);
+      if (rc == AP_OK && !b->equal) rc = init_dgrad(b->t_sc, b->sc, true);
     }
     if (rc != AP_OK) return rc;
     h->bwd_ready = true;
@@ -1928,7 +1938,8 @@ static int vjp_wrn(ap_classifier_t h, const float* spec, const float* g_logits, 
       const float *a = h->tape[2 * l]->as<float>(), *hh = h->tape[2 * l + 1]->as<float>();
       const int Hi = H * b.stride, Wi = W * b.stride;
       const long long npo = static_cast<long long>(bn) * H * W;
-      rc = b.t_c2.run(G, bn, H, W, T1, nullptr, 0, st);                         // g_h = conv2^T G, then the ReLU of bn2
+      const size_t sb = 6 * nb + 3 * static_cast<size_t>(l);                    // tensor-map slots of this block's three twins
+      rc = conv_auto(h, sb, b.t_c2, G, bn, H, W, T1, nullptr, 0, 0, st);         // g_h = conv2^T G, then the ReLU of bn2
       if (rc != AP_OK) return rc;
       relu_mask_kernel<<<vgg_grid(npo * b.cout / 4), 256, 0, st>>>(reinterpret_cast<float4*>(T1), reinterpret_cast<const float4*>(hh),
                                                                    npo * b.cout / 4);
@@ -1940,7 +1951,7 @@ static int vjp_wrn(ap_classifier_t h, const float* spec, const float* g_logits, 
           rc = upsample(G, T3, H, W, b.cout);
           src = T3;
         }
-        if (rc == AP_OK) rc = b.t_sc.run(src, bn, Hi, Wi, T4, nullptr, 0, st);
+        if (rc == AP_OK) rc = conv_auto(h, sb + 1, b.t_sc, src, bn, Hi, Wi, T4, nullptr, 0, 0, st);
         res = T4;
       }
       const float* src = T1;
@@ -1949,7 +1960,7 @@ static int vjp_wrn(ap_classifier_t h, const float* spec, const float* g_logits, 
         rc = upsample(T1, T2, H, W, b.cout);
         src = T2, g_a = T1;
       }
-      if (rc == AP_OK) rc = b.t_c1.run(src, bn, Hi, Wi, g_a, res, 0, st);       // g_a = conv1^T g_h (+ shortcut part)
+      if (rc == AP_OK) rc = conv_auto(h, sb + 2, b.t_c1, src, bn, Hi, Wi, g_a, res, 0, 0, st);   // g_a = conv1^T g_h (+ shortcut part)
       // x feeds bn1 + ReLU -> a, and for an equal-width block also the identity shortcut (+ G); in place in g_a
       if (rc == AP_OK) rc = bwd_act(g_a, a, b.scale, b.equal ? G : nullptr, static_cast<long long>(bn) * Hi * Wi * b.cin, b.cin);
       if (rc != AP_OK) return rc;

@@ -897,7 +897,7 @@ def test_nes_estimate_aligns_with_the_autograd_gradient(ap):
 
 # ------------------------------------------------------------------------------------ VGG classifiers (section 8f-4)
 @pytest.mark.parametrize("depth", [11, 19])
-def test_vgg_vs_reference_golden(ap, golden, golden_grad, golden_vgg, depth):
+def test_vgg_vs_reference_golden(ap, golden, golden_grad, golden_vgg, depth, monkeypatch):
     """vgg11_bn / vgg19_bn (models/vgg.py:32-95; `--classifier_model vgg19_bn`, adaptive_attack_eval.py:21) on the CUDA
     path: logits, top-1 and the input gradient against the unmodified reference; a batch that spans two chunks of the
     backward (64 + 6) must reproduce the single-image results."""
@@ -922,10 +922,19 @@ def test_vgg_vs_reference_golden(ap, golden, golden_grad, golden_vgg, depth):
     assert np.abs(lt - want).max() < 2e-2 * max(1.0, np.abs(want).max()) and (lt.argmax(1) == want.argmax(1)).all()
     big_t = vg(big.detach())                                                     # 70 images: several images per tile + a ragged tail
     assert torch.allclose(big_t[-2:], torch.from_numpy(lt).cuda(), atol=1e-5) and torch.allclose(big_t[:2], big_t[-2:], atol=1e-5)
+    # the tf32-mode gradient is the gradient of the tf32 network (tensor-core forward tape and data-gradient convolutions)
+    (gt,) = torch.autograd.grad(vg(spec), spec, g_logits)
+    (gbt,) = torch.autograd.grad(vg(big), big, g_logits.repeat(35, 1))
+    err_t = rel_l2(gt, golden_vgg[f"vgg{depth}_grad"])
+    monkeypatch.setenv("AP_CLS_VJP_FWD_FP32", "1")          # fp32 forward tape, tensor-core data-gradient convolutions only
+    (gtb,) = torch.autograd.grad(vg(spec), spec, g_logits)
+    err_tb = rel_l2(gtb, golden_vgg[f"vgg{depth}_grad"])
+    print(f"VGG-{depth} gradient rel-L2: tf32 {err_t:.3e}, tf32 backward on an fp32 forward {err_tb:.3e}")
+    assert err_t < 0.3 and err_tb < 2e-2 and rel_l2(gbt[-2:], gt) < 1e-5       # measured 0.13 / 6e-3 (VGG-19)
 
 
 @pytest.mark.parametrize("key,depth,k", [("wrn28_10", 28, 10), ("wrn16_1", 16, 1)])
-def test_wideresnet_vs_reference_golden(ap, golden, golden_grad, golden_vgg, key, depth, k):
+def test_wideresnet_vs_reference_golden(ap, golden, golden_grad, golden_vgg, key, depth, k, monkeypatch):
     """WideResNet-28-10 (`--classifier_model wideresnet28_10`, adaptive_attack_eval.py:21; models/wideresnet.py:15-92) and a
     narrow WRN-16-1 (equal-width first block) on the CUDA path: logits, top-1 and the input gradient against the unmodified
     reference; a batch that spans two chunks of the backward (32 + 4) must reproduce the two-image results."""
@@ -953,6 +962,16 @@ def test_wideresnet_vs_reference_golden(ap, golden, golden_grad, golden_vgg, key
     assert np.abs(lt - want).max() < 2e-2 * max(1.0, np.abs(want).max()) and (lt.argmax(1) == want.argmax(1)).all()
     big_t = wr(big.detach())
     assert torch.allclose(big_t[-2:], torch.from_numpy(lt).cuda(), rtol=1e-5, atol=1e-4)
+    # the tf32-mode gradient is the gradient of the tf32 network (tensor-core forward tape and data-gradient convolutions);
+    # ReLU units whose sign differs from the fp32 forward move it by per cents (cf. the ResNeXt tf32 gradient test)
+    (gt,) = torch.autograd.grad(wr(spec), spec, g_logits)
+    (gbt,) = torch.autograd.grad(wr(big), big, g_logits.repeat(18, 1))
+    err_t = rel_l2(gt, golden_vgg[f"{key}_grad"])
+    monkeypatch.setenv("AP_CLS_VJP_FWD_FP32", "1")          # fp32 forward tape, tensor-core data-gradient convolutions only
+    (gtb,) = torch.autograd.grad(wr(spec), spec, g_logits)
+    err_tb = rel_l2(gtb, golden_vgg[f"{key}_grad"])
+    print(f"{key} gradient rel-L2: tf32 {err_t:.3e}, tf32 backward on an fp32 forward {err_tb:.3e}")
+    assert err_t < 0.5 and err_tb < 2e-2 and rel_l2(gbt[-2:], gt) < 1e-5
 
 
 @pytest.mark.parametrize("key,depth", [("densenet100_12", 100), ("densenet22_12", 22)])

@@ -77,7 +77,7 @@ class _Classifier(torch.nn.Module):
         return self
 
     def set_mode(self, mode: str):
-        """'tf32' (tensor-core convolutions, default for ResNeXt, VGG and WideResNet) or 'fp32' (FFMA everywhere)."""
+        """'tf32' (tensor-core convolutions, default for ResNeXt, ResNet, VGG and WideResNet) or 'fp32' (FFMA everywhere)."""
         m = {"fp32": _lib.AP_MODE_FP32, "tf32": _lib.AP_MODE_TF32}[mode]
         _lib.check(self._lib.ap_classifier_set_mode(self._handle, m), "ap_classifier_set_mode")
         return self

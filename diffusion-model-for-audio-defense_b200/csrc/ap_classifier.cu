@@ -1265,6 +1265,31 @@ static int vjp_resnext(ap_classifier_t h, const float* spec, const float* g_logi
   return AP_OK;
 }
 
+// The recomputed forward of a VGG / WideResNet backward pass runs on the tensor cores in AP_MODE_TF32 (the gradient is then that of
+// the tf32 network: its ReLU masks differ from an fp32 forward's in a few units, which moves the input gradient by a few per cent,
+// see DESIGN.md "Backward pass") unless AP_CLS_VJP_FWD_FP32=1 keeps it on the fp32 path, as for ResNeXt.
+static bool tape_on_tensor_cores(const ap_classifier_s* h) {
+  const char* e = std::getenv("AP_CLS_VJP_FWD_FP32");   // read per call, like vjp_resnext
+  return h->mode == AP_MODE_TF32 && !(e && std::atoi(e) != 0);
+}
+
+// A convolution of a VGG / WideResNet pass: tf32 tensor cores when the classifier is in AP_MODE_TF32 and the layer
+// has a tensor-core twin for this geometry, else the fp32 FFMA implicit GEMM.  Slot `si` caches the tensor maps of the buffers the
+// convolution ran on last time (they are re-encoded when a buffer moved or the chunk size changed).
+static int conv_auto(ap_classifier_t h, size_t si, const ConvLayer& L, const float* in, int bn, int H, int W, float* out,
+                     const float* res, int relu, int round_out, cudaStream_t st, bool allow_tc = true) {
+  if (!allow_tc || h->mode != AP_MODE_TF32 || !L.has_tc || !conv_tc_supported(L.Cin, L.Cout, L.groups, H, W, L.kh, L.kw, L.stride, L.pad))
+    return L.run(in, bn, H, W, out, res, relu, st);
+  if (h->tc_slots.size() <= si) h->tc_slots.resize(si + 1);
+  auto& s = h->tc_slots[si];
+  if (!s.tc || s.in != in || s.out != out || s.res != res || s.relu != relu || s.bn != bn) {
+    int rc = L.tc.bind(&s.bnd, in, bn, H, W, out, res, relu, round_out);
+    if (rc != AP_OK) return rc;
+    s.in = in, s.out = out, s.res = res, s.relu = relu, s.bn = bn, s.tc = true;
+  }
+  return L.tc.run(s.bnd, st);
+}
+
 // ---- ResNet family (models/resnet.py:103-220): state_dict order conv1.weight, bn1.{w,b,mean,var}, then per block
 //      conv1, bn1, conv2, bn2, [conv3, bn3,] [downsample.0.weight, downsample.1.{...}], finally fc.weight, fc.bias
 static int create_resnet(ap_classifier_t h, const float* const* w, int n_weights) {
@@ -1301,18 +1326,18 @@ static int create_resnet(ap_classifier_t h, const float* const* w, int n_weights
       blk->bottleneck = bott, blk->stride = stride, blk->cout = planes * exp, blk->cin = inpl, blk->planes = planes;
       blk->c1.keep_host = blk->c2.keep_host = blk->c3.keep_host = blk->down.keep_host = true;
       if (bott) {
-        rc = blk->c1.init(inpl, planes, 1, 1, 1, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
-        if (rc == AP_OK) rc = blk->c2.init(planes, planes, 3, 3, stride, 1, 1, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9]);
-        if (rc == AP_OK) rc = blk->c3.init(planes, planes * 4, 1, 1, 1, 0, 1, w[i + 10], nullptr, w[i + 11], w[i + 12], w[i + 13], w[i + 14]);
+        rc = blk->c1.init(inpl, planes, 1, 1, 1, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4], true);
+        if (rc == AP_OK) rc = blk->c2.init(planes, planes, 3, 3, stride, 1, 1, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9], true);
+        if (rc == AP_OK) rc = blk->c3.init(planes, planes * 4, 1, 1, 1, 0, 1, w[i + 10], nullptr, w[i + 11], w[i + 12], w[i + 13], w[i + 14], true);
         i += 15;
       } else {
-        rc = blk->c1.init(inpl, planes, 3, 3, stride, 1, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
-        if (rc == AP_OK) rc = blk->c2.init(planes, planes, 3, 3, 1, 1, 1, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9]);
+        rc = blk->c1.init(inpl, planes, 3, 3, stride, 1, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4], true);
+        if (rc == AP_OK) rc = blk->c2.init(planes, planes, 3, 3, 1, 1, 1, w[i + 5], nullptr, w[i + 6], w[i + 7], w[i + 8], w[i + 9], true);
         i += 10;
       }
       if (rc == AP_OK && b == 0 && (stride != 1 || inpl != planes * exp)) {
         blk->has_down = true;
-        rc = blk->down.init(inpl, planes * exp, 1, 1, stride, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4]);
+        rc = blk->down.init(inpl, planes * exp, 1, 1, stride, 0, 1, w[i], nullptr, w[i + 1], w[i + 2], w[i + 3], w[i + 4], true);
         i += 5;
       }
       if (rc != AP_OK) return rc;
@@ -1351,22 +1376,24 @@ static int forward_resnet(ap_classifier_t h, const float* spec, float* logits, i
       AP_LAUNCH_CHECK();
     }
     int H = H2, W = W2;
+    size_t si = 0;                                  // tensor-map slots: four per block
     for (auto& blk : h->resblocks) {
       const int Ho = (H - 1) / blk->stride + 1, Wo = (W - 1) / blk->stride + 1;
       const float* res = x;
       if (blk->has_down) {
-        rc = blk->down.run(x, bn, H, W, sc, nullptr, 0, st);
+        rc = conv_auto(h, si + 3, blk->down, x, bn, H, W, sc, nullptr, 0, 1, st);
         if (rc != AP_OK) return rc;
         res = sc;
       }
       if (blk->bottleneck) {
-        rc = blk->c1.run(x, bn, H, W, y1, nullptr, 1, st);
-        if (rc == AP_OK) rc = blk->c2.run(y1, bn, H, W, y2, nullptr, 1, st);
-        if (rc == AP_OK) rc = blk->c3.run(y2, bn, Ho, Wo, xo, res, 1, st);
+        rc = conv_auto(h, si, blk->c1, x, bn, H, W, y1, nullptr, 1, 1, st);
+        if (rc == AP_OK) rc = conv_auto(h, si + 1, blk->c2, y1, bn, H, W, y2, nullptr, 1, 1, st);
+        if (rc == AP_OK) rc = conv_auto(h, si + 2, blk->c3, y2, bn, Ho, Wo, xo, res, 1, 1, st);
       } else {
-        rc = blk->c1.run(x, bn, H, W, y1, nullptr, 1, st);
-        if (rc == AP_OK) rc = blk->c2.run(y1, bn, Ho, Wo, xo, res, 1, st);
+        rc = conv_auto(h, si, blk->c1, x, bn, H, W, y1, nullptr, 1, 1, st);
+        if (rc == AP_OK) rc = conv_auto(h, si + 1, blk->c2, y1, bn, Ho, Wo, xo, res, 1, 1, st);
       }
+      si += 4;
       if (rc != AP_OK) return rc;
       std::swap(x, xo);
       H = Ho, W = Wo;
@@ -1387,13 +1414,15 @@ static int vjp_resnet(ap_classifier_t h, const float* spec, const float* g_logit
   AP_REQUIRE(H0 == 2 * H1 && W0 == 2 * W1 && half(half(half(H2))) == 1 && half(half(half(W2))) == 1,
              "ResNet backward: input %dx%d does not reduce to 1x1 by exact halvings", H0, W0);
   const int chunk = 64;
+  const size_t NS = 4 * h->resblocks.size();   // tensor-map slots: [0, NS) inference, [NS, 2 NS) recomputed forward, [2 NS, 3 NS) backward
+  const bool tape_tc = tape_on_tensor_cores(h);
   if (!h->bwd_ready) {
     int rc = init_dgrad(h->t_stem, h->stem);
     for (auto& b : h->resblocks) {
-      if (rc == AP_OK) rc = init_dgrad(b->t_c1, b->c1);
-      if (rc == AP_OK) rc = init_dgrad(b->t_c2, b->c2);
-      if (rc == AP_OK && b->bottleneck) rc = init_dgrad(b->t_c3, b->c3);
-      if (rc == AP_OK && b->has_down) rc = init_dgrad(b->t_down, b->down);
+      if (rc == AP_OK) rc = init_dgrad(b->t_c1, b->c1, true);
+      if (rc == AP_OK) rc = init_dgrad(b->t_c2, b->c2, true);
+      if (rc == AP_OK && b->bottleneck) rc = init_dgrad(b->t_c3, b->c3, true);
+      if (rc == AP_OK && b->has_down) rc = init_dgrad(b->t_down, b->down, true);
     }
     if (rc != AP_OK) return rc;
     h->bwd_ready = true;
@@ -1458,18 +1487,19 @@ static int vjp_resnet(ap_classifier_t h, const float* spec, const float* g_logit
       float *a1 = h->tape[1 + 3 * i]->as<float>(), *a2 = h->tape[2 + 3 * i]->as<float>(), *y = h->tape[3 + 3 * i]->as<float>();
       const int Ho = (H - 1) / b.stride + 1, Wo = (W - 1) / b.stride + 1;
       const float* res = x;
+      const size_t sf = NS + 4 * i;                 // tensor-map slots of the recomputed forward
       if (b.has_down) {
-        rc = b.down.run(x, bn, H, W, h->gbuf[4].as<float>(), nullptr, 0, st);
+        rc = conv_auto(h, sf + 3, b.down, x, bn, H, W, h->gbuf[4].as<float>(), nullptr, 0, 1, st, tape_tc);
         if (rc != AP_OK) return rc;
         res = h->gbuf[4].as<float>();
       }
       if (b.bottleneck) {
-        rc = b.c1.run(x, bn, H, W, a1, nullptr, 1, st);
-        if (rc == AP_OK) rc = b.c2.run(a1, bn, H, W, a2, nullptr, 1, st);
-        if (rc == AP_OK) rc = b.c3.run(a2, bn, Ho, Wo, y, res, 1, st);
+        rc = conv_auto(h, sf, b.c1, x, bn, H, W, a1, nullptr, 1, 1, st, tape_tc);
+        if (rc == AP_OK) rc = conv_auto(h, sf + 1, b.c2, a1, bn, H, W, a2, nullptr, 1, 1, st, tape_tc);
+        if (rc == AP_OK) rc = conv_auto(h, sf + 2, b.c3, a2, bn, Ho, Wo, y, res, 1, 1, st, tape_tc);
       } else {
-        rc = b.c1.run(x, bn, H, W, a1, nullptr, 1, st);
-        if (rc == AP_OK) rc = b.c2.run(a1, bn, Ho, Wo, y, res, 1, st);
+        rc = conv_auto(h, sf, b.c1, x, bn, H, W, a1, nullptr, 1, 1, st, tape_tc);
+        if (rc == AP_OK) rc = conv_auto(h, sf + 1, b.c2, a1, bn, Ho, Wo, y, res, 1, 1, st, tape_tc);
       }
       if (rc != AP_OK) return rc;
       x = y, H = Ho, W = Wo;
@@ -1485,6 +1515,7 @@ static int vjp_resnet(ap_classifier_t h, const float* spec, const float* g_logit
       const float *a1 = h->tape[1 + 3 * i]->as<float>(), *a2 = h->tape[2 + 3 * i]->as<float>(), *y = h->tape[3 + 3 * i]->as<float>();
       const int Ho = H, Wo = W, Hi = H * b.stride, Wi = W * b.stride;
       const size_t npo = static_cast<size_t>(bn) * Ho * Wo, npi = static_cast<size_t>(bn) * Hi * Wi;
+      const size_t sb = 2 * NS + 4 * static_cast<size_t>(i);   // tensor-map slots of this block's data-gradient twins
       rc = mask(GA, y, npo * b.cout);
       const float* res = GA;                                    // identity shortcut
       if (rc == AP_OK && b.has_down) {                          // shortcut path first: it borrows GC for the upsampled gradient
@@ -1493,29 +1524,29 @@ static int vjp_resnet(ap_classifier_t h, const float* spec, const float* g_logit
           rc = upsample(GA, GC, Ho, Wo, b.cout);
           ssrc = GC;
         }
-        if (rc == AP_OK) rc = b.t_down.run(ssrc, bn, Hi, Wi, GE, nullptr, 0, st);
+        if (rc == AP_OK) rc = conv_auto(h, sb + 3, b.t_down, ssrc, bn, Hi, Wi, GE, nullptr, 0, 0, st);
         res = GE;
       }
       if (b.bottleneck) {
-        if (rc == AP_OK) rc = b.t_c3.run(GA, bn, Ho, Wo, GB, nullptr, 0, st);
+        if (rc == AP_OK) rc = conv_auto(h, sb + 2, b.t_c3, GA, bn, Ho, Wo, GB, nullptr, 0, 0, st);
         if (rc == AP_OK) rc = mask(GB, a2, npo * b.planes);
         const float* src = GB;
         if (rc == AP_OK && b.stride == 2) {
           rc = upsample(GB, GC, Ho, Wo, b.planes);
           src = GC;
         }
-        if (rc == AP_OK) rc = b.t_c2.run(src, bn, Hi, Wi, GD, nullptr, 0, st);
+        if (rc == AP_OK) rc = conv_auto(h, sb + 1, b.t_c2, src, bn, Hi, Wi, GD, nullptr, 0, 0, st);
         if (rc == AP_OK) rc = mask(GD, a1, npi * b.planes);
-        if (rc == AP_OK) rc = b.t_c1.run(GD, bn, Hi, Wi, GB, res, 0, st);
+        if (rc == AP_OK) rc = conv_auto(h, sb, b.t_c1, GD, bn, Hi, Wi, GB, res, 0, 0, st);
       } else {
-        if (rc == AP_OK) rc = b.t_c2.run(GA, bn, Ho, Wo, GB, nullptr, 0, st);
+        if (rc == AP_OK) rc = conv_auto(h, sb + 1, b.t_c2, GA, bn, Ho, Wo, GB, nullptr, 0, 0, st);
         if (rc == AP_OK) rc = mask(GB, a1, npo * b.planes);
         const float* src = GB;
         if (rc == AP_OK && b.stride == 2) {
           rc = upsample(GB, GC, Ho, Wo, b.planes);
           src = GC;
         }
-        if (rc == AP_OK) rc = b.t_c1.run(src, bn, Hi, Wi, GD, res, 0, st);
+        if (rc == AP_OK) rc = conv_auto(h, sb, b.t_c1, src, bn, Hi, Wi, GD, res, 0, 0, st);
         if (rc == AP_OK) std::swap(GB, GD);                     // the block's input gradient is in GB either way
       }
       if (rc != AP_OK) return rc;
@@ -1531,31 +1562,6 @@ static int vjp_resnet(ap_classifier_t h, const float* spec, const float* g_logit
     if (rc != AP_OK) return rc;
   }
   return AP_OK;
-}
-
-// The recomputed forward of a VGG / WideResNet backward pass runs on the tensor cores in AP_MODE_TF32 (the gradient is then that of
-// the tf32 network: its ReLU masks differ from an fp32 forward's in a few units, which moves the input gradient by a few per cent,
-// see DESIGN.md "Backward pass") unless AP_CLS_VJP_FWD_FP32=1 keeps it on the fp32 path, as for ResNeXt.
-static bool tape_on_tensor_cores(const ap_classifier_s* h) {
-  const char* e = std::getenv("AP_CLS_VJP_FWD_FP32");   // read per call, like vjp_resnext
-  return h->mode == AP_MODE_TF32 && !(e && std::atoi(e) != 0);
-}
-
-// A convolution of a VGG / WideResNet pass: tf32 tensor cores when the classifier is in AP_MODE_TF32 and the layer
-// has a tensor-core twin for this geometry, else the fp32 FFMA implicit GEMM.  Slot `si` caches the tensor maps of the buffers the
-// convolution ran on last time (they are re-encoded when a buffer moved or the chunk size changed).
-static int conv_auto(ap_classifier_t h, size_t si, const ConvLayer& L, const float* in, int bn, int H, int W, float* out,
-                     const float* res, int relu, int round_out, cudaStream_t st, bool allow_tc = true) {
-  if (!allow_tc || h->mode != AP_MODE_TF32 || !L.has_tc || !conv_tc_supported(L.Cin, L.Cout, L.groups, H, W, L.kh, L.kw, L.stride, L.pad))
-    return L.run(in, bn, H, W, out, res, relu, st);
-  if (h->tc_slots.size() <= si) h->tc_slots.resize(si + 1);
-  auto& s = h->tc_slots[si];
-  if (!s.tc || s.in != in || s.out != out || s.res != res || s.relu != relu || s.bn != bn) {
-    int rc = L.tc.bind(&s.bnd, in, bn, H, W, out, res, relu, round_out);
-    if (rc != AP_OK) return rc;
-    s.in = in, s.out = out, s.res = res, s.relu = relu, s.bn = bn, s.tc = true;
-  }
-  return L.tc.run(s.bnd, st);
 }
 
 // ---- VGG-11/13/16/19 with batch norm (models/vgg.py:32-95; the SC09 factory builds vgg19_bn, models/__init__.py:44-45).
@@ -2461,7 +2467,10 @@ extern "C" int ap_classifier_create(ap_classifier_t* out, const ap_classifier_cf
       break;
     }
     case AP_CLS_M5: rc = create_m5(h, weights, n_weights); break;
-    case AP_CLS_RESNET: rc = create_resnet(h, weights, n_weights); break;
+    case AP_CLS_RESNET:
+      rc = create_resnet(h, weights, n_weights);
+      h->mode = AP_MODE_TF32;
+      break;
     case AP_CLS_KWS: rc = create_kws(h, weights, n_weights); break;
     case AP_CLS_VGG:   // tf32 by default, as for ResNeXt: what cuDNN runs for the reference's convolutions on this GPU
       rc = create_vgg(h, weights, n_weights);
@@ -2519,8 +2528,9 @@ extern "C" int ap_classifier_vjp(ap_classifier_t h, const float* input, const fl
 extern "C" int ap_classifier_set_mode(ap_classifier_t h, int mode) {
   AP_REQUIRE(h, "ap_classifier_set_mode: null handle");
   AP_REQUIRE(mode == AP_MODE_FP32 || mode == AP_MODE_TF32, "ap_classifier_set_mode: mode must be AP_MODE_FP32 or AP_MODE_TF32");
-  AP_REQUIRE(mode == AP_MODE_FP32 || h->cfg.kind == AP_CLS_RESNEXT || h->cfg.kind == AP_CLS_VGG || h->cfg.kind == AP_CLS_WRN,
-             "ap_classifier_set_mode: only ResNeXt, VGG and WideResNet have tensor-core convolutions");
+  AP_REQUIRE(mode == AP_MODE_FP32 || h->cfg.kind == AP_CLS_RESNEXT || h->cfg.kind == AP_CLS_RESNET || h->cfg.kind == AP_CLS_VGG ||
+                 h->cfg.kind == AP_CLS_WRN,
+             "ap_classifier_set_mode: only ResNeXt, ResNet, VGG and WideResNet have tensor-core convolutions");
   if (mode != h->mode) h->plans.clear(), h->tc_slots.clear();
   h->mode = mode;
   return AP_OK;

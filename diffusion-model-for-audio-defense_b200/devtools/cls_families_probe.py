@@ -36,7 +36,7 @@ def timed(fn, n=3):
 out = {"batch": B}
 for name, (ctor, gflop, kind) in FAMILIES.items():
     clf = ctor()
-    if name in ("vgg19_bn", "wideresnet28_10") and os.environ.get("AP_PROBE_TF32", "1") == "1":
+    if name in ("vgg19_bn", "wideresnet28_10", "resnet34") and os.environ.get("AP_PROBE_TF32", "1") == "1":
         clf.set_mode("tf32")
     x = torch.randn(B, 1, 32, 32, device="cuda") if kind == "spec" else torch.randn(B, 1, 16000, device="cuda") * 0.1
 

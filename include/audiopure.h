@@ -205,7 +205,7 @@ int ap_classifier_forward(ap_classifier_t h, const float* input, float* logits, 
  * g_logits: device (B, num_classes). */
 int ap_classifier_vjp(ap_classifier_t h, const float* input, const float* g_logits, float* g_input, int B, int in_len,
                       void* stream);
-/* AP_MODE_TF32 (default for ResNeXt, VGG and WideResNet: tensor-core convolutions where a tile shape exists, in the forward pass,
+/* AP_MODE_TF32 (default for ResNeXt, ResNet, VGG and WideResNet: tensor-core convolutions where a tile shape exists, in the forward pass,
  * the recomputed forward of ap_classifier_vjp (AP_CLS_VJP_FWD_FP32=1 keeps that one on the fp32 path) and the data gradients) or AP_MODE_FP32 (every convolution on the FFMA path) */
 int ap_classifier_set_mode(ap_classifier_t h, int mode);
 int ap_classifier_get_mode(ap_classifier_t h);

@@ -123,12 +123,15 @@ struct ConvLayer {
     if (M >= (1ll << 31)) return fail(AP_ERR_INVALID, "conv: too many output pixels");
     ConvEpi ep{out, bias.as<float>(), residual, out_ctot, Ng, relu};
     cudaError_t e;
+    const bool narrow = Ng <= 16;   // 128 x 16 tiles instead of 128 x 128: DenseNet's growth convolutions, 1-channel data gradients
     if (Cg % 4 == 0 && in_ctot % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
       Conv2dLoader<true> al{in, H, W, in_ctot, Cg, kh, kw, stride, pad, pad_h, Ho, Wo};
-      e = sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
+      e = narrow ? sgemm::launch_n16(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st)
+                 : sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
     } else {
       Conv2dLoader<false> al{in, H, W, in_ctot, Cg, kh, kw, stride, pad, pad_h, Ho, Wo};
-      e = sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
+      e = narrow ? sgemm::launch_n16(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st)
+                 : sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
     }
     if (e != cudaSuccess) return fail(AP_ERR_CUDA, "conv launch: %s", cudaGetErrorString(e));
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -75,6 +75,30 @@ def test_compute_entry_points_fail_loudly_without_gpu(lib):
                    res_channels=64, skip_channels=64, num_res_layers=2)
 
 
+def test_blackbox_host_logic_and_argument_checks(lib):
+    """Host side of the black-box query path (no compute): argument validation of the NES / loss entry points, the noise-block
+    accounting, resolve_loss / resolve_prediction semantics (robustness_eval/_utils.py:103-136), and CPU tensors refused."""
+    import audiopure_b200 as ap
+    from audiopure_b200.blackbox import EOT, NES, QueryLoss, resolve_loss, resolve_prediction
+    assert lib.ap_nes_noise_blocks(3, 8, 1001) == (3 * 4 * 1001 + 3) // 4
+    one = C.c_void_p(16)                                                   # never dereferenced: validation comes first
+    assert lib.ap_nes_perturb(one, 0.1, None, 0, 0, 1, one, 2, 7, 100, None) == -1      # odd samples_per_draw_batch
+    assert b"even" in lib.ap_last_error()
+    assert lib.ap_nes_perturb(None, 0.1, None, 0, 0, 1, one, 2, 8, 100, None) == -1
+    assert lib.ap_nes_gradient(one, None, 0, 0, 2, 1.0, 0, one, 2, 8, 100, None) == -1  # first must be 0 or 1
+    assert lib.ap_query_loss(one, one, 4, 10, 7, 0, 0.0, 0, one, None, None) == -1      # unknown loss kind
+    assert lib.ap_query_loss(one, one, 0, 10, 0, 0, 0.0, 0, one, None, None) == 0       # empty batch is a no-op
+    loss, sign = resolve_loss("Margin", targeted=True, task="SCR")
+    assert isinstance(loss, QueryLoss) and loss.kind == 0 and sign == -1   # the reference returns cross entropy for 'SCR'
+    with pytest.raises(NotImplementedError):
+        resolve_loss("Entropy", task="SV")
+    assert list(resolve_prediction([[3, 1, 3], [2, 5, 5, 2], [7]])) == [3, 2, 7]        # majority, first seen wins a tie
+    with pytest.raises(ap.AudioPureError):
+        QueryLoss("Entropy")(torch.zeros(2, 10), torch.zeros(2, dtype=torch.long))      # CPU tensors: no CPU path
+    with pytest.raises(ap.AudioPureError):
+        NES(8, 8, 0.001, EOT(lambda x: x, loss, 1, 1, False))(torch.zeros(1, 1, 16), torch.zeros(1, dtype=torch.long))
+
+
 def test_hyperparams_and_sde_schedule_match_oracle(golden):
     import audiopure_oracle as orc
     from audiopure_b200.diffwave import calc_diffusion_hyperparams

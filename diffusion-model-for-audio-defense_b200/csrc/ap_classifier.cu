@@ -2296,7 +2296,8 @@ static int vjp_m5(ap_classifier_t h, const float* wav, const float* g_out, float
   AP_REQUIRE(K <= 64, "M5 backward: at most 64 classes");
   if (!h->bwd_ready) {
     for (int i = 0; i < 4; ++i) {
-      if (i == 0 && h->m5conv[0].Cin == 1) {   // dedicated kernel, see conv1d_cin1_dgrad_kernel
+      // dedicated kernel (see conv1d_cin1_dgrad_kernel) when its weight tile fits the default 48 KB of dynamic shared memory
+      if (i == 0 && h->m5conv[0].Cin == 1 && h->m5conv[0].wf_host.size() * sizeof(float) <= 48 * 1024) {
         AP_CUDA(h->m5_w0.upload(h->m5conv[0].wf_host.data(), h->m5conv[0].wf_host.size() * sizeof(float)));
         continue;
       }

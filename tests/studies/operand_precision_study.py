@@ -9,6 +9,9 @@ residual stream) and the B operand (the folded dilated-conv weights) of GEMM-1 r
   fp8_tensor      : e4m3, one scale per activation tensor and one per output channel of the weights,
   fp8_channel     : e4m3, one activation scale per input channel (foldable into the weights) and per-output-channel weight scales,
   fp8_w_only      : e4m3 weights, bf16 activations,
+  fp8_skip        : GEMM-1 in bf16, but the gate output o and the skip weights of the K = 9216 skip GEMM (k2_head) in e4m3 -- o is
+                    in (-1, 1) and is the tensor k1 writes and k2 re-reads (38 GB per 128 waveforms), so storing it in 8 bits would
+                    halve that traffic,
 and reports, against the fp32 forward: rel-L2 of eps at t = 65 and t = 1, and of the one-shot x0 estimate at t* = 66.
 
     python tests/studies/operand_precision_study.py            # ~1 min on CPU; prints one JSON line
@@ -44,7 +47,7 @@ def quantise(u, wd, mode):
     """(A operand u (B,C,L), B operand wd (2C,C,3)) as GEMM-1 would see them."""
     if mode == "fp32":
         return u, wd
-    if mode == "bf16":
+    if mode in ("bf16", "fp8_skip"):
         return q_bf16(u), q_bf16(wd)
     w_scale = wd.abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-30) / E4M3_MAX          # per output channel
     if mode == "fp8_w_only":
@@ -77,7 +80,11 @@ def wavenet(sd, audio, t, mode):
         a = F.conv1d(uq, wq, w(p + ".dilated_conv_layer.conv.bias"), dilation=d, padding=d)
         o = torch.tanh(a[:, :C]) * torch.sigmoid(a[:, C:])
         h = (u + F.conv1d(o, wn(p + ".res_conv"), w(p + ".res_conv.bias"))) * math.sqrt(0.5)
-        skip_total = skip_total + F.conv1d(o, wn(p + ".skip_conv"), w(p + ".skip_conv.bias"))
+        ws, os_ = wn(p + ".skip_conv"), o
+        if mode == "fp8_skip":
+            ws = q_e4m3(ws, ws.abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-30) / E4M3_MAX)
+            os_ = q_e4m3(o, torch.tensor(1.0 / E4M3_MAX * 1.0))          # |o| < 1: a fixed scale, no amax pass
+        skip_total = skip_total + F.conv1d(os_, ws, w(p + ".skip_conv.bias"))
     s = skip_total * math.sqrt(1.0 / 36)
     y = torch.relu(F.conv1d(s, wn("final_conv.0.conv"), w("final_conv.0.conv.bias")))
     return F.conv1d(y, w("final_conv.2.conv.weight"), w("final_conv.2.conv.bias"))
@@ -102,7 +109,7 @@ def main():
         ref65, ref1 = wavenet(sd, xt, 65.0, "fp32"), wavenet(sd, x1, 1.0, "fp32")
         assert rel(orc.wavenet_forward(sd, xt, 65.0 * torch.ones(B, 1)), ref65) < 1e-6               # same function as the oracle
         x0_ref = orc.predict_x0_from_eps(hp, xt, 65, ref65)
-        for mode in ("bf16", "fp8_w_only", "fp8_channel", "fp8_tensor"):
+        for mode in ("bf16", "fp8_skip", "fp8_w_only", "fp8_channel", "fp8_tensor"):
             e65, e1 = wavenet(sd, xt, 65.0, mode), wavenet(sd, x1, 1.0, mode)
             out[mode] = {"eps_rel_l2_t65": rel(e65, ref65), "eps_rel_l2_t1": rel(e1, ref1),
                          "one_shot_x0_rel_l2_t66": rel(orc.predict_x0_from_eps(hp, xt, 65, e65), x0_ref)}

@@ -65,6 +65,8 @@ SIGNATURES = {
     "ap_predict_x0": (_i, [_fp, _fp, _f, _f, _fp, _i, _i, _vp]),
     "ap_smooth_inputs": (_i, [_fp, _f, _f, _fp, _u64, _u64, _fp, _i, _i, _vp]),
     "ap_randn": (_i, [_fp, _u64, _u64, _u64, _vp]),
+    "ap_diffwave_smooth_denoise": (_i, [_vp, _fp, _f, _f, _fp, _u64, _u64, _vp, _f, _f, _f, _fp, _i, _i, _vp]),
+    "ap_u64_add": (_i, [_vp, _u64, _vp]),
     "ap_diffwave_purify_ddpm": (_i, [_vp, _fp, _fp, _i, _vp, _fp, _u64, _u64, _i, _i, _vp]),
     "ap_mel_create": (_i, [_PP, C.POINTER(MelCfg), _i]),
     "ap_mel_destroy": (None, [_vp]),
@@ -77,7 +79,7 @@ SIGNATURES = {
     "ap_classifier_vjp": (_i, [_vp, _fp, _fp, _fp, _i, _i, _vp]),
     "ap_classifier_set_mode": (_i, [_vp, _i]),
     "ap_classifier_get_mode": (_i, [_vp]),
-    "ap_vote_counts": (_i, [_fp, _i, _i, _vp, _vp]),
+    "ap_vote_counts": (_i, [_fp, _i, _i, _vp, _i, _vp]),
     "ap_argmax": (_i, [_fp, _i, _i, _vp, _vp]),
     "ap_nes_noise_blocks": (_u64, [_i, _i, _i]),
     "ap_nes_perturb": (_i, [_fp, _f, _fp, _u64, _u64, _i, _fp, _i, _i, _i, _vp]),
@@ -116,6 +118,45 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().ap_last_error()
         raise AudioPureError(f"{what or 'audiopure call'} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+_STREAM_IDS = {"diffwave": 0x4449464657415645, "certify": 0x4345525449465921, "nes": 0x4E45535155455259}
+_instances = 0
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return x ^ (x >> 31)
+
+
+def philox_key(consumer: str, seed) -> int:
+    """Philox key of one noise consumer ('diffwave', 'certify', 'nes').
+
+    The reference draws the defender's diffusion noise, the smoothing noise and an attacker's NES probes from independent
+    RNG streams.  Here every consumer owns a counter-based Philox4x32-10 stream; its 64-bit key is
+    ``splitmix64(seed) ^ consumer_id``, so the same user seed never makes two KINDS of consumer walk the same blocks.
+    ``seed=None`` (the default of the host classes) derives a fresh key per object:
+    ``splitmix64(torch.initial_seed() + 2^32 * rank + instance_index)`` -- reproducible under ``torch.manual_seed``, distinct
+    across the objects of one process and across the ranks of a torch.distributed job.  Pass an explicit seed (bench.py uses
+    ``2024 + rank``) to pin a stream; certification shards ONE stream across ranks by offset, not by key (certify.py)."""
+    global _instances
+    if seed is None:
+        import torch
+        rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank = torch.distributed.get_rank()
+        seed = (int(torch.initial_seed()) + (rank << 32) + _instances) & 0xFFFFFFFFFFFFFFFF
+        _instances += 1
+    return _splitmix64(int(seed) & 0xFFFFFFFFFFFFFFFF) ^ _STREAM_IDS[consumer]
+
+
+def check_device(x, device_index: int, what: str) -> None:
+    """The C side launches on the handle's device with the caller's stream: a tensor on another GPU is an error here, not an
+    'invalid resource handle' from the driver later."""
+    if x.is_cuda and x.device.index != device_index:
+        raise AudioPureError(f"{what}: input is on cuda:{x.device.index} but the handle was created on cuda:{device_index}")
 
 
 def launch_count() -> int:

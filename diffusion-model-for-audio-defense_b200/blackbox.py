@@ -167,8 +167,8 @@ class _PhiloxStream:
     """Process-wide counter for the in-kernel noise: FAKEBOB builds a fresh ``NES`` per iteration
     (black_box_attack.py:187), so the offset cannot live on the NES object."""
 
-    def __init__(self, seed: int = 0):
-        self.seed, self.offset = int(seed), 0
+    def __init__(self, seed: int | None = None):
+        self.seed, self.offset = _lib.philox_key("nes", seed), 0
 
     def take(self, blocks: int) -> int:
         off = self.offset

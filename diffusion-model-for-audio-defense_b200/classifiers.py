@@ -55,6 +55,7 @@ class _Classifier(torch.nn.Module):
         dev = device if isinstance(device, int) else (torch.device(device).index or 0)
         self._weights = [_np32(w) for w in weights]
         self._handle = C.c_void_p()
+        self.device_index = dev
         _lib.check(self._lib.ap_classifier_create(C.byref(self._handle), C.byref(cfg), _lib.ptr_array(self._weights),
                                                   len(self._weights), dev), "ap_classifier_create")
         self.num_classes = cfg.num_classes
@@ -62,6 +63,7 @@ class _Classifier(torch.nn.Module):
     def _run(self, x: torch.Tensor, B: int, in_len: int) -> torch.Tensor:
         if not x.is_cuda:
             raise _lib.AudioPureError(f"{type(self).__name__}: input must be a CUDA tensor (there is no CPU path)")
+        _lib.check_device(x, self.device_index, type(self).__name__)
         if x.requires_grad and torch.is_grad_enabled():
             if not self.differentiable:
                 raise _lib.AudioPureError(f"{type(self).__name__}: inference-only (input requires grad)")

@@ -998,6 +998,7 @@ struct ap_classifier_s {
 
 static int ensure_ws(ap_classifier_t h, size_t elems) {
   if (elems <= h->buf_elems) return AP_OK;
+  h->buf_elems = 0;   // alloc() releases the old buffers first: a failure must not leave the old size behind
   for (auto& b : h->buf) AP_CUDA(b.alloc(elems * sizeof(float)));
   h->buf_elems = elems;
   return AP_OK;

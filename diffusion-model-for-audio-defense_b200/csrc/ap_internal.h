@@ -19,6 +19,18 @@ int sde_step(float* x, const float* eps, const ap_sde_coef& c, const float* z, u
 int predict_x0(const float* xt, const float* eps, float a, float b, float* x0, long long n, cudaStream_t st);
 int vote(const float* logits, int B, int K, long long* counts, int* pred, cudaStream_t st);
 
+// Fused certification front end (RobustCertificate.smooth_predict + DiffWave.one_shot_denoise, certified_robust.py:44-54 and
+// diffwave_ddpm.py:174-205): the network's first kernel builds the noisy copies x_in[b] = scale * (x + sigma * z[b]) of ONE
+// input x (L) itself (and parks them in the output buffer), its last kernel turns eps into x0 = a * x_in - b * eps in place.
+struct SmoothSrc {
+  const float* x1;             // device (L): the input every row is a noisy copy of
+  float sigma, scale;          // x_in = scale * (x1 + sigma * z)
+  const float* z;              // device (B, L) host-generated N(0,1) noise, or null: Philox(seed) block offset + e / 4, lane e % 4
+  uint64_t seed, offset;
+  const uint64_t* offset_dev;  // optional device word added to `offset` (a captured CUDA graph replays with a moving offset)
+  float a, b;                  // sqrt(1 / abar_t), sqrt(1 / abar_t - 1)
+};
+
 // ap_wavenet_tc.cu : the bf16 tensor-core (tcgen05 / TMEM / TMA) DiffWave network, C == S == 256 only.
 //   weights: the ap_diffwave_create list (host fp32, weight-norm folded).
 struct TcNet;
@@ -31,6 +43,8 @@ size_t tc_net_workspace_bytes(const TcNet* n);
 // eps[b, l] for b < B <= chunk.  ptab: device fp32 [num_layers + 1][256] step-embedding projections (row n = fc_t of
 // layer n applied to the embedding; the extra last row is zero).  x, eps: device fp32 (B, L).
 int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st);
+// x0[b, :] for b < B <= chunk: the fused smoothing-input + one-shot-denoise form (x0 also serves as the x_in scratch)
+int tc_net_smooth_denoise(TcNet* n, const SmoothSrc& src, const float* ptab, float* x0, int B, int L, cudaStream_t st);
 // debug: run init + layers [0, layer]; returns u_{layer+1} and o_layer converted to fp32 (B, L, 256); either may be null
 int tc_net_debug_layer(TcNet* n, const float* x, const float* ptab, int layer, float* u_next, float* gate, int B, int L,
                        cudaStream_t st);

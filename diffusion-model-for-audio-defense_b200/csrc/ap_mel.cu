@@ -249,6 +249,7 @@ extern "C" int ap_mel_db(ap_mel_t h, const float* wav, float* spec, int B, int L
   const long long rows = static_cast<long long>(B) * frames;
   AP_REQUIRE(rows < (1ll << 30), "ap_mel_db: batch too large");
   if (rows > h->power_rows) {
+    h->power_rows = 0;   // alloc() releases the old buffer first
     AP_CUDA(h->power.alloc(static_cast<size_t>(rows) * h->ld_power * sizeof(float)));
     h->power_rows = rows;
   }
@@ -284,6 +285,7 @@ extern "C" int ap_mel_vjp(ap_mel_t h, const float* wav, const float* g_spec, flo
     AP_CUDA(h->basis_t.upload(bt.data(), bt.size() * sizeof(float)));
   }
   if (rows > h->reim_rows) {
+    h->reim_rows = 0;
     AP_CUDA(h->reim.alloc(static_cast<size_t>(rows) * h->ncols * sizeof(float)));
     h->reim_rows = rows;
   }

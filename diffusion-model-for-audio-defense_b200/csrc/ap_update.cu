@@ -310,8 +310,9 @@ int ap_randn(float* out, uint64_t n, uint64_t seed, uint64_t offset, void* strea
   return launch_ew(op, static_cast<long long>(n), aligned16(out), NOISE_PHILOX, nullptr, seed, offset,
                    static_cast<cudaStream_t>(stream));
 }
-int ap_vote_counts(const float* logits, int B, int K, long long* counts, void* stream) {
+int ap_vote_counts(const float* logits, int B, int K, long long* counts, int counts_len, void* stream) {
   AP_REQUIRE(logits && counts && B >= 0 && K > 0 && K <= 4096, "ap_vote_counts: bad arguments");
+  AP_REQUIRE(K <= counts_len, "ap_vote_counts: %d classes do not fit a count vector of %d entries", K, counts_len);
   return vote(logits, B, K, counts, nullptr, static_cast<cudaStream_t>(stream));
 }
 int ap_argmax(const float* logits, int B, int K, int* pred, void* stream) {

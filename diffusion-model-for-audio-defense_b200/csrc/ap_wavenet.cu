@@ -5,6 +5,7 @@
 // Activation layout (both modes): channels-last [waveform][position][channel], so a dilated tap is a contiguous
 // channel vector at position l +- d and the implicit GEMM has positions as rows (M) and channels as K.
 #include <cmath>
+#include <cstdlib>
 
 #include "ap_common.cuh"
 #include "ap_internal.h"
@@ -337,17 +338,26 @@ static int reserve_ws(ap_diffwave_t h, int chunk, int L) {
   AP_CUDA(cudaSetDevice(h->device));
   if (h->mode != AP_MODE_FP32) {
     if (h->tc_chunk == chunk && h->tc_L == L) return AP_OK;
+    h->tc_chunk = 0, h->tc_L = 0;            // the old buffers are released first: nothing may describe them if this fails
     int rc = tc_net_reserve(h->tc, chunk, L);
     if (rc != AP_OK) return rc;
     h->tc_chunk = chunk, h->tc_L = L;
     return AP_OK;
   }
   if (h->chunk == chunk && h->L == L) return AP_OK;
+  h->chunk = 0, h->L = 0;
   const size_t n = static_cast<size_t>(chunk) * L * h->cfg.res_channels * sizeof(float);
-  AP_CUDA(h->u0.alloc(n));
-  AP_CUDA(h->u1.alloc(n));
-  AP_CUDA(h->outb.alloc(n));
-  AP_CUDA(h->skip.alloc(n));
+  h->u0.release(), h->u1.release(), h->outb.release(), h->skip.release();
+  cudaError_t e = h->u0.alloc(n);
+  if (e == cudaSuccess) e = h->u1.alloc(n);
+  if (e == cudaSuccess) e = h->outb.alloc(n);
+  if (e == cudaSuccess) e = h->skip.alloc(n);
+  if (e != cudaSuccess) {
+    h->u0.release(), h->u1.release(), h->outb.release(), h->skip.release();
+    (void)cudaGetLastError();
+    return fail(AP_ERR_CUDA, "DiffWave fp32 workspace: %.2f GB for %d waveforms of length %d -> %s", 4.0 * n / 1e9, chunk, L,
+                cudaGetErrorString(e));
+  }
   h->chunk = chunk, h->L = L;
   return AP_OK;
 }
@@ -409,31 +419,57 @@ static int eps_fp32_chunk(ap_diffwave_t h, const float* x, float* eps, int B, in
   return AP_OK;
 }
 
+// Workspace for a batch of B waveforms of length L in the current mode: keeps an explicit ap_diffwave_reserve, otherwise
+// (re)sizes the implicit one.  Returns the chunk (waveforms per pass) in *chunk_out.
+static int ensure_workspace(ap_diffwave_t h, int B, int L, int* chunk_out) {
+  const bool tc = h->mode != AP_MODE_FP32;
+  int chunk = tc ? h->tc_chunk : h->chunk;
+  const int curL = tc ? h->tc_L : h->L;
+  // default chunk.  Workspace per position: fp32 4 tensors * 256 ch * 4 B = 4 KB; bf16 (N + 2) tensors * 256 ch * 2 B
+  // = 19.4 KB for 36 layers (the gate output of EVERY layer is kept for k2_head); bf16x3 twice that (two planes).
+  // bf16: 148 waveforms of 1 s = 18500 tiles = 125 full rounds over 74 CTA pairs (no ragged last wave) = 46 GB;
+  // bf16x3: half as many waveforms in the same bytes.  On top of that shape heuristic the implicit workspace is bounded
+  // by HALF of the device memory that is free right now (plus what this handle already holds) and by
+  // AP_DIFFWAVE_WORKSPACE_GB if set, so a shared or smaller GPU gets a smaller chunk instead of an allocation failure.
+  const long long budget_positions = tc ? (h->mode == AP_MODE_BF16X3 ? 74ll : 148ll) * 16000 : (1ll << 18);
+  long long want = budget_positions / L;
+  if (want > B) want = B;
+  if (chunk == 0 || curL != L || (!h->user_reserved && chunk < want)) {
+    const int N = h->cfg.num_res_layers;
+    const double per_wave = tc ? (h->mode == AP_MODE_BF16X3 ? 2.0 : 1.0) * L * 512.0 * (N + 2) : L * 4096.0;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const double held = tc ? static_cast<double>(tc_net_workspace_bytes(h->tc))
+                             : static_cast<double>(h->u0.bytes + h->u1.bytes + h->outb.bytes + h->skip.bytes);
+      double budget = 0.5 * (static_cast<double>(free_b) + held);
+      if (const char* env = std::getenv("AP_DIFFWAVE_WORKSPACE_GB")) {
+        const double cap = std::atof(env) * 1e9;
+        if (cap > 0 && cap < budget) budget = cap;
+      }
+      const long long fit = static_cast<long long>(budget / per_wave);
+      if (want > fit) want = fit;
+    }
+    if (want < 1) want = 1;
+    // an implicitly sized workspace grows with the batch (e.g. after a small backward pass); an explicit reserve is kept
+    int rc = reserve_ws(h, static_cast<int>(want), L);
+    if (rc != AP_OK) return rc;
+    if (chunk == 0 || curL != L) h->user_reserved = false;
+    chunk = static_cast<int>(want);
+  }
+  *chunk_out = chunk;
+  return AP_OK;
+}
+
 extern "C" int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* eps, int B, int L, void* stream) {
   AP_REQUIRE(h && x && eps, "ap_diffwave_eps: null argument");
   AP_REQUIRE(B > 0 && L > 0, "ap_diffwave_eps: B and L must be positive (got %d, %d)", B, L);
   AP_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool tc = h->mode != AP_MODE_FP32;
-  int chunk = tc ? h->tc_chunk : h->chunk;
-  const int curL = tc ? h->tc_L : h->L;
-  {
-    // default chunk: bounded workspace (fp32: 4 * 4 B * 256 ch per position; bf16: ~2.5 KB per position incl. gate history)
-    // bf16: 148 waveforms of 1 s = 18500 tiles = 125 full rounds over 74 CTA pairs (no ragged last wave)
-    // bf16x3: two planes per tensor, so half as many waveforms in the same workspace
-    const long long budget_positions = tc ? (h->mode == AP_MODE_BF16X3 ? 74ll : 148ll) * 16000 : (1ll << 18);
-    long long want = budget_positions / L;
-    if (want < 1) want = 1;
-    if (want > B) want = B;
-    // an implicitly sized workspace grows with the batch (e.g. after a small backward pass); an explicit reserve is kept
-    if (chunk == 0 || curL != L || (!h->user_reserved && chunk < want)) {
-      int rc = reserve_ws(h, static_cast<int>(want), L);
-      if (rc != AP_OK) return rc;
-      if (chunk == 0 || curL != L) h->user_reserved = false;
-      chunk = static_cast<int>(want);
-    }
-  }
-  int rc = step_embedding(h, t, st);
+  int chunk = 0;
+  int rc = ensure_workspace(h, B, L, &chunk);
+  if (rc != AP_OK) return rc;
+  rc = step_embedding(h, t, st);
   if (rc != AP_OK) return rc;
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int bn = B - b0 < chunk ? B - b0 : chunk;
@@ -442,6 +478,51 @@ extern "C" int ap_diffwave_eps(ap_diffwave_t h, const float* x, float t, float* 
     rc = tc ? tc_net_eps(h->tc, xc, h->ptab.as<float>(), ec, bn, L, st) : eps_fp32_chunk(h, xc, ec, bn, L, st);
     if (rc != AP_OK) return rc;
   }
+  return AP_OK;
+}
+
+// Certification front end in one call: x0[b] = a * x_in[b] - b * eps_theta(x_in[b], t), x_in[b] = scale * (x + sigma * z[b]).
+// Tensor-core modes with L % 4 == 0: the noisy copies are built inside the network's init kernel and x0 is formed in
+// k2_head's epilogue (no separate smoothing-input / predict-x0 passes over HBM).  Otherwise (fp32 FFMA mode, ragged L) the
+// same result is computed by the unfused sequence ap_smooth_inputs -> ap_diffwave_eps -> ap_predict_x0.
+extern "C" int ap_diffwave_smooth_denoise(ap_diffwave_t h, const float* x, float sigma, float scale, const float* z,
+                                          uint64_t seed, uint64_t offset, const uint64_t* offset_dev, float t,
+                                          float sqrt_recip_ab, float sqrt_recipm1_ab, float* x0, int B, int L, void* stream) {
+  AP_REQUIRE(h && x && x0, "ap_diffwave_smooth_denoise: null argument");
+  AP_REQUIRE(B > 0 && L > 0, "ap_diffwave_smooth_denoise: B and L must be positive (got %d, %d)", B, L);
+  AP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fused = h->mode != AP_MODE_FP32 && L % 4 == 0;
+  if (!fused) {
+    AP_REQUIRE(!offset_dev, "ap_diffwave_smooth_denoise: a device-resident noise offset needs a tensor-core mode and L %% 4 == 0");
+    const size_t nb = static_cast<size_t>(B) * L * sizeof(float);
+    if (h->eps_buf.bytes < nb) AP_CUDA(h->eps_buf.alloc(nb));
+    int rc = ap_smooth_inputs(x, sigma, scale, z, seed, offset, x0, B, L, stream);
+    if (rc != AP_OK) return rc;
+    rc = ap_diffwave_eps(h, x0, t, h->eps_buf.as<float>(), B, L, stream);
+    if (rc != AP_OK) return rc;
+    return predict_x0(x0, h->eps_buf.as<float>(), sqrt_recip_ab, sqrt_recipm1_ab, x0, static_cast<long long>(B) * L, st);
+  }
+  int chunk = 0;
+  int rc = ensure_workspace(h, B, L, &chunk);
+  if (rc != AP_OK) return rc;
+  rc = step_embedding(h, t, st);
+  if (rc != AP_OK) return rc;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bn = B - b0 < chunk ? B - b0 : chunk;
+    const size_t e0 = static_cast<size_t>(b0) * L;   // a multiple of 4: element e of the call is lane e % 4 of block offset + e / 4
+    SmoothSrc src{x, sigma, scale, z ? z + e0 : nullptr, seed, offset + e0 / 4, offset_dev, sqrt_recip_ab, sqrt_recipm1_ab};
+    rc = tc_net_smooth_denoise(h->tc, src, h->ptab.as<float>(), x0 + e0, bn, L, st);
+    if (rc != AP_OK) return rc;
+  }
+  return AP_OK;
+}
+
+__global__ void u64_add_kernel(unsigned long long* p, unsigned long long inc) { *p += inc; }
+extern "C" int ap_u64_add(uint64_t* dev, uint64_t inc, void* stream) {
+  AP_REQUIRE(dev, "ap_u64_add: null pointer");
+  u64_add_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(dev), inc);
+  AP_LAUNCH_CHECK();
   return AP_OK;
 }
 

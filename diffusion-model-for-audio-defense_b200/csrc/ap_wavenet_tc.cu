@@ -27,6 +27,7 @@
 #include "ap_common.cuh"
 #include "ap_conv_tc.h"
 #include "ap_internal.h"
+#include "ap_philox.cuh"
 #include "ap_ptx.cuh"
 
 namespace ap {
@@ -807,6 +808,9 @@ struct K2Params {
   float* eps;            // [B][L]
   int o_plane, ws_plane, wf_plane;   // hi/lo split mode (DT = 2): offsets of the lo planes in the O / Ws / Wf tensor maps
   uint32_t* mask_out;                // SAVE kernels (backward pass): [B][L][8] bit c of the row = (head pre-activation c > 0)
+  // fused one-shot denoise (certification): p.eps holds x_in on entry and receives x0 = x0_a * x_in - x0_b * eps
+  int fuse_x0;
+  float x0_a, x0_b;
   // per-channel vectors in the kernel-parameter constant bank (constant operands of the epilogue FMAs):
   float bskip_scaled[256];   // (sum over layers of the skip-conv biases) * sqrt(1/N)
   float bf1[256];            // final_conv.0 bias
@@ -888,7 +892,12 @@ __device__ __forceinline__ void k2_epilogue(const Ctx<G>& cx, const K2Params& p,
     if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 1);
     if (HSEL == 1) s_part[row] = dot;
     named_bar_sync(1, EPI_THREADS);
-    if (HSEL == 0 && valid && l0 + row < p.L) p.eps[static_cast<size_t>(b) * p.L + l0 + row] = dot + s_part[row] + p.bf2[0];
+    if (HSEL == 0 && valid && l0 + row < p.L) {
+      float* dst = p.eps + static_cast<size_t>(b) * p.L + l0 + row;
+      const float e = dot + s_part[row] + p.bf2[0];
+      // _predict_x0_from_eps (diffwave_ddpm.py:195-205) in PredictX0Op's rounding order
+      *dst = p.fuse_x0 ? __fsub_rn(__fmul_rn(p.x0_a, *dst), __fmul_rn(p.x0_b, e)) : e;
+    }
     named_bar_sync(1, EPI_THREADS);   // s_part is rewritten by the next tile
   }
 }
@@ -1207,6 +1216,68 @@ __global__ void __launch_bounds__(256) init_h16_kernel(const float* __restrict__
       pk[e] = pack2<DT>(v0, v1);
     }
     u[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// Certification front end fused into the init conv: a block walks 1024 consecutive positions e = b * L + l of the (B, L) batch.
+// Phase 1: thread i draws the Philox block of positions [e0 + 4 i, +4) -- or reads the caller's noise -- and forms
+//          x_in = scale * (x1[l] + sigma * z) in SmoothOp's rounding order (ap_update.cu); x_in goes to shared memory and to
+//          `xin_out` (the x0 output buffer, which k2_head's epilogue reads back and overwrites).
+// Phase 2: the 1024 x 256 channels-last tile of u0 = bf16(relu(w x_in + b) + p0) (hi / lo planes in split mode).
+// Requires (B * L) % 4 == 0 handling of the tail by element count; the Philox block of element e is offset + e / 4.
+template <int DT>
+__global__ void __launch_bounds__(256) init_smooth_kernel(const SmoothSrc src, const float* __restrict__ w, const float* __restrict__ b,
+                                                           const float* __restrict__ p0, uint4* __restrict__ u, long long lo_off,
+                                                           float* __restrict__ xin_out, long long M, int L) {
+  __shared__ float sw[C], sb[C], sp[C];
+  __shared__ __align__(16) float sx[1024];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[i] = w[i], sb[i] = b[i], sp[i] = p0[i];
+  const uint64_t off = src.offset + (src.offset_dev ? *src.offset_dev : 0ull);
+  for (long long e0 = static_cast<long long>(blockIdx.x) * 1024; e0 < M; e0 += static_cast<long long>(gridDim.x) * 1024) {
+    __syncthreads();                                       // sw/sb/sp visible; previous tile's sx consumed
+    {
+      const long long e = e0 + 4 * threadIdx.x;
+      if (e < M) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        const int cnt = M - e >= 4 ? 4 : static_cast<int>(M - e);
+        if (src.z) {
+          for (int j = 0; j < cnt; ++j) z[j] = src.z[e + j];
+        } else {
+          normal4(off + static_cast<uint64_t>(e >> 2), src.seed, z);
+        }
+        float xi[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xv = j < cnt ? src.x1[(e + j) % L] : 0.f;
+          xi[j] = __fmul_rn(src.scale, __fadd_rn(xv, __fmul_rn(src.sigma, z[j])));
+          sx[4 * threadIdx.x + j] = xi[j];
+          if (j < cnt) xin_out[e + j] = xi[j];
+        }
+      }
+    }
+    __syncthreads();
+    const long long npos = M - e0 < 1024 ? M - e0 : 1024;
+    for (long long i = threadIdx.x; i < npos * 32; i += blockDim.x) {
+      const int c = static_cast<int>(i & 31) * 8;
+      const float xv = sx[i >> 5];
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v0, v1;
+        if (DT == 2) {   // the roundings of init_split_kernel
+          v0 = __fadd_rn(fmaxf(__fadd_rn(__fmul_rn(sw[c + 2 * k], xv), sb[c + 2 * k]), 0.f), sp[c + 2 * k]);
+          v1 = __fadd_rn(fmaxf(__fadd_rn(__fmul_rn(sw[c + 2 * k + 1], xv), sb[c + 2 * k + 1]), 0.f), sp[c + 2 * k + 1]);
+          ph[k] = pack_bf16x2(v0, v1);
+          pl[k] = pack_bf16x2(v0 - bf16_lo(ph[k]), v1 - bf16_hi(ph[k]));
+        } else {         // the roundings of init_h16_kernel
+          v0 = fmaxf(fmaf(sw[c + 2 * k], xv, sb[c + 2 * k]), 0.f) + sp[c + 2 * k];
+          v1 = fmaxf(fmaf(sw[c + 2 * k + 1], xv, sb[c + 2 * k + 1]), 0.f) + sp[c + 2 * k + 1];
+          ph[k] = pack2<DT == 1 ? 1 : 0>(v0, v1);
+        }
+      }
+      u[e0 * 32 + i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      if (DT == 2) u[lo_off + e0 * 32 + i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
   }
 }
 
@@ -1592,18 +1663,32 @@ int tc_net_reserve(TcNet* n, int chunk, int L) {
   using namespace tc;
   const int planes = n->dt == 2 ? 2 : 1;   // split mode: hi plane [chunk] followed by the lo plane [chunk]
   const size_t per = static_cast<size_t>(planes) * chunk * L * C * sizeof(uint16_t);
+  // the old buffers go first (two workspaces do not fit): from here on nothing -- sizes, tensor maps, the saved backward
+  // state -- may describe them, so a failed allocation leaves an EMPTY workspace rather than dangling pointers
+  n->chunk = 0, n->L = 0, n->save_B = 0;
+  std::memset(n->tmU, 0, sizeof(n->tmU)), std::memset(&n->tmO, 0, sizeof(n->tmO));
   n->u0.release(), n->u1.release(), n->o.release();
-  AP_CUDA(n->u0.alloc(per));
-  AP_CUDA(n->u1.alloc(per));
-  AP_CUDA(n->o.alloc(per * n->N));
-  n->chunk = chunk, n->L = L, n->ws_split = planes == 2;
+  cudaError_t e = n->u0.alloc(per);
+  if (e == cudaSuccess) e = n->u1.alloc(per);
+  if (e == cudaSuccess) e = n->o.alloc(per * n->N);
+  if (e != cudaSuccess) {
+    n->u0.release(), n->u1.release(), n->o.release();
+    (void)cudaGetLastError();
+    return fail(AP_ERR_CUDA, "DiffWave workspace: %.2f GB for %d waveforms of length %d (%d layers, %s) -> %s; lower it with "
+                "ap_diffwave_reserve or AP_DIFFWAVE_WORKSPACE_GB", per * (n->N + 2.0) / 1e9, chunk, L, n->N,
+                planes == 2 ? "bf16x3" : "bf16", cudaGetErrorString(e));
+  }
   const uint64_t du[3] = {256, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk) * planes};
   const uint64_t dO[3] = {256, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk) * n->N * planes};
   const uint32_t bx[3] = {64, 128, 1};
   int rc = encode_bf16(&n->tmU[0], n->u0.p, 3, du, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmU[1], n->u1.p, 3, du, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmO, n->o.p, 3, dO, bx);
-  if (rc != AP_OK) return rc;
+  if (rc != AP_OK) {
+    n->u0.release(), n->u1.release(), n->o.release();
+    return rc;
+  }
+  n->chunk = chunk, n->L = L, n->ws_split = planes == 2;   // committed only now: allocations and encodes succeeded
   if (!n->attr_set) {
     AP_CUDA(cudaFuncSetAttribute(k1_layer<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 1>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k2_head<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1, 2>::SMEM_BYTES));
@@ -1637,10 +1722,23 @@ static cudaError_t launch_pair(Kernel kernel, int grid, int smem, cudaStream_t s
 }
 
 static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int L, int layers, cudaStream_t st,
-                         bool save = false) {
+                         bool save = false, const SmoothSrc* smooth = nullptr, float* xin_out = nullptr) {
   using namespace tc;
   const long long M = static_cast<long long>(B) * L;
-  {
+  if (smooth) {
+    long long blocks = ceil_div_ll(M, 1024);
+    const long long cap = static_cast<long long>(num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    const long long lo_off = static_cast<long long>(n->chunk) * L * (C / 8);
+    const unsigned g = static_cast<unsigned>(blocks);
+    if (n->dt == 2)
+      init_smooth_kernel<2><<<g, 256, 0, st>>>(*smooth, n->init_w.as<float>(), n->init_b.as<float>(), ptab, n->u0.as<uint4>(), lo_off, xin_out, M, L);
+    else if (n->dt == 0)
+      init_smooth_kernel<0><<<g, 256, 0, st>>>(*smooth, n->init_w.as<float>(), n->init_b.as<float>(), ptab, n->u0.as<uint4>(), 0, xin_out, M, L);
+    else
+      init_smooth_kernel<1><<<g, 256, 0, st>>>(*smooth, n->init_w.as<float>(), n->init_b.as<float>(), ptab, n->u0.as<uint4>(), 0, xin_out, M, L);
+    AP_LAUNCH_CHECK();
+  } else {
     long long blocks = ceil_div_ll(M * (C / 8), 256);
     const long long cap = static_cast<long long>(num_sms()) * 8;
     if (blocks > cap) blocks = cap;
@@ -1695,20 +1793,26 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
   return AP_OK;
 }
 
-static int tc_net_eps_impl(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st, bool save);
+static int tc_net_eps_impl(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st, bool save,
+                           const SmoothSrc* smooth = nullptr);
 int tc_net_eps(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st) {
   return tc_net_eps_impl(n, x, ptab, eps, B, L, st, false);
 }
-static int tc_net_eps_impl(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st, bool save) {
+int tc_net_smooth_denoise(TcNet* n, const SmoothSrc& src, const float* ptab, float* x0, int B, int L, cudaStream_t st) {
+  return tc_net_eps_impl(n, nullptr, ptab, x0, B, L, st, false, &src);
+}
+static int tc_net_eps_impl(TcNet* n, const float* x, const float* ptab, float* eps, int B, int L, cudaStream_t st, bool save,
+                           const SmoothSrc* smooth) {
   using namespace tc;
   if (B > n->chunk || L != n->L || n->ws_split != (n->dt == 2))
     return fail(AP_ERR_STATE, "tc_net_eps: workspace reserved for chunk %d x L %d (%s layout)", n->chunk, n->L,
                 n->ws_split ? "split" : "single-plane");
-  int rc = tc_run_layers(n, x, ptab, B, L, n->N, st, save);
+  int rc = tc_run_layers(n, x, ptab, B, L, n->N, st, save, smooth, eps);
   if (rc != AP_OK) return rc;
   const int tps = ceil_div(L, TILE_M), n_tiles = tps * B;
   K2Params p;
   p.mask_out = save ? n->mask.as<uint32_t>() : nullptr;
+  p.fuse_x0 = smooth != nullptr, p.x0_a = smooth ? smooth->a : 0.f, p.x0_b = smooth ? smooth->b : 0.f;
   p.n_tiles = n_tiles, p.tiles_per_sample = tps, p.L = L, p.num_layers = n->N, p.chunk_alloc = n->chunk;
   p.scale = static_cast<float>(std::sqrt(1.0 / n->N));
   p.bf2 = n->bf2.as<float>();
@@ -1743,15 +1847,22 @@ static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
   using namespace tc;
   if (n->bchunk == chunk && n->bL == L) return AP_OK;
   const size_t pos = static_cast<size_t>(chunk) * L;
-  for (DevBuf* d : {&n->ts, &n->mask, &n->g_pre, &n->g_s, &n->g_a, &n->g_u[0], &n->g_u[1]}) d->release();
+  DevBuf* bufs[7] = {&n->ts, &n->mask, &n->g_pre, &n->g_s, &n->g_a, &n->g_u[0], &n->g_u[1]};
+  const size_t sizes[7] = {pos * 512 * 2 * n->N, pos * 8 * 4, pos * 256 * 2, pos * 256 * 2, pos * 512 * 2, pos * 256 * 2, pos * 256 * 2};
+  n->bchunk = 0, n->bL = 0;                 // nothing describes the released buffers if an allocation below fails
   n->save_B = 0, ++n->save_gen;
-  AP_CUDA(n->ts.alloc(pos * 512 * 2 * n->N));
-  AP_CUDA(n->mask.alloc(pos * 8 * 4));
-  AP_CUDA(n->g_pre.alloc(pos * 256 * 2));
-  AP_CUDA(n->g_s.alloc(pos * 256 * 2));
-  AP_CUDA(n->g_a.alloc(pos * 512 * 2));
-  AP_CUDA(n->g_u[0].alloc(pos * 256 * 2));
-  AP_CUDA(n->g_u[1].alloc(pos * 256 * 2));
+  for (DevBuf* d : bufs) d->release();
+  for (int i = 0; i < 7; ++i) {
+    cudaError_t e = bufs[i]->alloc(sizes[i]);
+    if (e != cudaSuccess) {
+      for (DevBuf* d : bufs) d->release();
+      (void)cudaGetLastError();
+      size_t total = 0;
+      for (size_t s : sizes) total += s;
+      return fail(AP_ERR_CUDA, "DiffWave backward workspace: %.2f GB for %d waveforms of length %d -> %s", total / 1e9, chunk, L,
+                  cudaGetErrorString(e));
+    }
+  }
   const uint64_t d256[3] = {256, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk)};
   const uint64_t d512[3] = {512, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk)};
   const uint32_t bx[3] = {64, 128, 1};
@@ -1760,7 +1871,10 @@ static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
   if (rc == AP_OK) rc = encode_bf16(&n->tmGa, n->g_a.p, 3, d512, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmGu[0], n->g_u[0].p, 3, d256, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmGu[1], n->g_u[1].p, 3, d256, bx);
-  if (rc != AP_OK) return rc;
+  if (rc != AP_OK) {
+    for (DevBuf* d : bufs) d->release();
+    return rc;
+  }
   if (!n->bwd_attr) {
     AP_CUDA(cudaFuncSetAttribute(k_bwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));

@@ -161,8 +161,10 @@ class WaveNet(torch.nn.Module):
         if out is None and _wants_grad(x):
             if not x.is_cuda:
                 raise AudioPureError("WaveNet: input must be a CUDA tensor (there is no CPU path)")
+            _lib.check_device(x, self.device_index, "WaveNet")
             return _EpsVJP.apply(x, self, float(t), bool(keep_for_backward))
         x = _check_wave(x, "WaveNet")
+        _lib.check_device(x, self.device_index, "WaveNet")
         assert x.ndim == 3 and x.shape[1] == 1, x.shape
         B, _, L = x.shape
         if out is None:
@@ -196,6 +198,7 @@ class WaveNet(torch.nn.Module):
     def eps_vjp(self, x: torch.Tensor, t: float, g_eps: torch.Tensor) -> torch.Tensor:
         """g_x = (d eps_theta(x, t) / d x)^T g_eps (the backward of ``eps``)."""
         x = _check_wave(x, "WaveNet.eps_vjp")
+        _lib.check_device(x, self.device_index, "WaveNet.eps_vjp")
         g = g_eps.detach().to(torch.float32).contiguous()
         assert x.ndim == 3 and x.shape[1] == 1 and g.shape == x.shape, (x.shape, g.shape)
         B, _, L = x.shape
@@ -245,13 +248,14 @@ class WaveNet(torch.nn.Module):
 class DiffWave(torch.nn.Module):
     """Reference ``DiffWave`` surface (diffwave_ddpm.py:16-249).
 
-    ``noise='philox'`` (default) draws the Gaussian noise inside the update kernels (counter-based Philox4x32-10, seeded by
-    ``seed``; successive draws advance an internal offset).  ``noise='torch'`` draws it exactly as the reference does --
+    ``noise='philox'`` (default) draws the Gaussian noise inside the update kernels (counter-based Philox4x32-10; the key is
+    derived from ``seed`` by ``_lib.philox_key`` -- ``None`` gives every object, and every rank, its own stream; successive
+    draws advance an internal offset).  ``noise='torch'`` draws it exactly as the reference does --
     ``torch.normal(0, 1, size=...)`` on the CPU generator, copied to the device -- which is what the parity tests use.
     """
 
     def __init__(self, model: WaveNet, diffusion_hyperparams: dict, reverse_timestep: int = 200, grad_enable=True,
-                 noise: str = "philox", seed: int = 0):
+                 noise: str = "philox", seed: int | None = None):
         super().__init__()
         self.model = model
         self.diffusion_hyperparams = diffusion_hyperparams
@@ -260,7 +264,7 @@ class DiffWave(torch.nn.Module):
         self.grad_enable = grad_enable
         assert noise in ("philox", "torch")
         self.noise = noise
-        self.seed = int(seed)
+        self.seed = _lib.philox_key("diffwave", seed)   # per-consumer Philox key (see _lib.philox_key)
         self._offset = 0
         self._lib = _lib.load()
 
@@ -481,7 +485,7 @@ class ReffWave(DiffWave):
     ``x <- one_shot_denoise(diffusion(x))`` at the fixed ``reverse_timestep``."""
 
     def __init__(self, model: WaveNet, diffusion_hyperparams: dict, reverse_timestep: int = 200, num_re: int = 5,
-                 noise: str = "philox", seed: int = 0):
+                 noise: str = "philox", seed: int | None = None):
         super().__init__(model, diffusion_hyperparams, reverse_timestep=reverse_timestep, noise=noise, seed=seed)
         self.num_re = num_re
 
@@ -497,7 +501,7 @@ class ReffWave(DiffWave):
 
 
 def create_diffwave_model(model_path, config_path, reverse_timestep=25, state_dict: dict | None = None,
-                          noise: str = "philox", seed: int = 0, mode: str | None = None, device=None) -> DiffWave:
+                          noise: str = "philox", seed: int | None = None, mode: str | None = None, device=None) -> DiffWave:
     """diffwave_ddpm.py:395-411: JSON config + ``torch.load(model_path)['model_state_dict']`` -> DiffWave.
     ``state_dict`` may be given directly (synthetic weights; the reference checkpoints are not in its tree)."""
     with open(config_path) as f:

@@ -74,17 +74,34 @@ class RevVPSDE(torch.nn.Module):
 class RevDiffWave(torch.nn.Module):
     """``RevDiffWave(args)``: args.{ddpm_path, ddpm_config, t, score_type, rand_t, t_delta, use_bm, sample_step}
     (diffwave_sde.py:136-217).  ``state_dict`` / ``noise`` / ``seed`` / ``mode`` are extensions for synthetic weights and
-    parity tests; ``noise='torch'`` draws e with ``torch.randn_like`` and the Brownian increments with ``torch.randn``."""
+    parity tests; ``noise='torch'`` draws e with ``torch.randn_like`` and one Brownian increment per Euler step with
+    ``torch.randn`` (also for a step whose diffusion coefficient is 0, as torchsde's Brownian interval does).
 
-    def __init__(self, args, device=None, state_dict=None, noise: str = "philox", seed: int = 0, mode=None):
+    Gradient (an input that requires grad): the reference evaluates the network inside the drift under ``torch.no_grad()``
+    (``DiffWave.compute_eps_t`` is decorated, diffwave_ddpm.py:166, and RevVPSDE.rvpsde_fn calls it, diffwave_sde.py:94), so what
+    ``sdeint_adjoint`` differentiates is the affine part of the drift with eps held constant.  That is the default here
+    (``grad_through_eps=False``); ``grad_through_eps=True`` is the opt-in exact gradient of the computed chain, with the
+    network's backward pass on the CUDA kernels.
+
+    ``args.use_bm=True`` raises: the explicit ``torchsde.BrownianInterval`` object of diffwave_sde.py:199-201 is not reproduced
+    (with ``use_bm=False`` torchsde builds the same kind of interval itself, so the increments have the same law)."""
+
+    def __init__(self, args, device=None, state_dict=None, noise: str = "philox", seed: int | None = None, mode=None,
+                 grad_through_eps: bool = False):
         super().__init__()
         self.args = args
+        if getattr(args, "use_bm", False):
+            raise NotImplementedError("RevDiffWave: args.use_bm=True (an explicit torchsde.BrownianInterval, "
+                                      "diffwave_sde.py:199-201) is not supported; use_bm=False draws Brownian increments of "
+                                      "the same law")
         if device is None:
-            device = torch.device("cuda")
-        self.device = device
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cuda")
+        self.device = torch.device(device)
+        self.grad_through_eps = bool(grad_through_eps)
         audio_shape = (1, 16000)
         model = create_diffwave_model(model_path=getattr(args, "ddpm_path", None), config_path=args.ddpm_config,
-                                      reverse_timestep=args.t, state_dict=state_dict, noise=noise, seed=seed, mode=mode)
+                                      reverse_timestep=args.t, state_dict=state_dict, noise=noise, seed=seed, mode=mode,
+                                      device=self.device)
         self.T = 200
         self.model = model
         self.rev_vpsde = RevVPSDE(model=model, score_type=args.score_type, beta_min=0.0001 * self.T,
@@ -122,8 +139,8 @@ class RevDiffWave(torch.nn.Module):
                 d, coef = self.rev_vpsde.step_coefficients(s, ds)
                 dw.model.eps(x, float(d), out=eps)
                 if self.noise == "torch":
-                    z = torch.randn(x.shape, device=x.device) if coef.g != 0.0 else None
-                    zp, seed, off = (z.data_ptr() if z is not None else None), 0, 0
+                    z = torch.randn(x.shape, device=x.device)
+                    zp, seed, off = z.data_ptr(), 0, 0
                 else:
                     z, zp, seed, off = dw._noise_args(x.shape, x.device)
                 with torch.cuda.device(x.device):
@@ -135,8 +152,9 @@ class RevDiffWave(torch.nn.Module):
 
     def _audio_editing_sample_autograd(self, x0):
         """The same Euler-Maruyama chain for an input that requires grad (the reference differentiates it with
-        torchsde.sdeint_adjoint, diffwave_sde.py:200-203): network + backward in the CUDA kernels, the affine step in torch
-        ops (discretise-then-differentiate: the exact gradient of the computed output)."""
+        torchsde.sdeint_adjoint, diffwave_sde.py:200-203): the affine step in torch ops (discretise-then-differentiate), the
+        network on the CUDA kernels -- as a constant of the differentiation by default, like the reference's no-grad
+        ``compute_eps_t``; with ``grad_through_eps`` through ``_EpsVJP`` (the exact gradient of the computed output)."""
         dw = self.model
         xs = []
         x0 = x0.to(torch.float32)
@@ -151,14 +169,15 @@ class RevDiffWave(torch.nn.Module):
             sched = list(euler_schedule(self.args.t, self.T))
             for i, (s, ds) in enumerate(sched):
                 d, c = self.rev_vpsde.step_coefficients(s, ds)
-                eps = dw.model.eps(x, float(d), keep_for_backward=(i == len(sched) - 1))
+                if self.grad_through_eps:
+                    eps = dw.model.eps(x, float(d), keep_for_backward=(i == len(sched) - 1))
+                else:
+                    with torch.no_grad():
+                        eps = dw.model.eps(x.detach(), float(d))
                 f = 0.5 * c.beta * x - c.diff2 * eps / c.sqrt_1mab        # -(drift - g^2 score), score = -eps / sqrt(1 - abar)
                 x = x + f * c.dt
-                if self.noise == "torch":
-                    z = torch.randn(x.shape, device=x.device) if c.g != 0.0 else None
-                else:
-                    z = dw._randn(x.shape, x.device)
-                if z is not None and c.g != 0.0:
+                z = torch.randn(x.shape, device=x.device) if self.noise == "torch" else dw._randn(x.shape, x.device)
+                if c.g != 0.0:
                     x = x + c.g * c.sqrt_dt * z
             x0 = x
             xs.append(x0)

@@ -43,11 +43,13 @@ class MelSpectrogramDB(torch.nn.Module):
         cfg = _lib.MelCfg(sample_rate, n_fft, hop_length, n_mels, int(norm == "slaney"), int(mel_scale == "slaney"),
                           int(pad_mode == "reflect"))
         self._handle = C.c_void_p()
+        self.device_index = dev
         _lib.check(self._lib.ap_mel_create(C.byref(self._handle), C.byref(cfg), dev), "ap_mel_create")
 
     def forward(self, wav: torch.Tensor) -> torch.Tensor:
         if not wav.is_cuda:
             raise _lib.AudioPureError("MelSpectrogramDB: input must be a CUDA tensor (there is no CPU path)")
+        _lib.check_device(wav, self.device_index, "MelSpectrogramDB")
         if wav.requires_grad and torch.is_grad_enabled():
             return _MelVJP.apply(wav, self)
         return self._db(wav.detach().to(torch.float32).contiguous())

@@ -139,6 +139,19 @@ int ap_predict_x0(const float* xt, const float* eps, float sqrt_recip_ab, float 
  * RobustCertificate.smooth_predict builds (certified_robust.py:44-54).  x: device (L), out: device (B, L). */
 int ap_smooth_inputs(const float* x, float sigma, float scale, const float* z_or_null, uint64_t seed, uint64_t offset,
                      float* out, int B, int L, void* stream);
+/* The certification front end in ONE call (RobustCertificate.smooth_predict's input construction, certified_robust.py:44-54,
+ * followed by DiffWave.one_shot_denoise, diffwave_ddpm.py:174-205): for b < B
+ *     x_in[b,:] = scale * (x[:] + sigma * z[b,:]) ;  x0[b,:] = sqrt_recip_ab * x_in[b,:] - sqrt_recipm1_ab * eps_theta(x_in[b,:], t)
+ * x: device (L), x0: device (B, L).  In the tensor-core modes with L % 4 == 0 the noisy copies are built inside the network's
+ * first kernel and x0 is formed in the epilogue of its last one; otherwise the unfused kernels run (same values either way:
+ * ap_smooth_inputs -> ap_diffwave_eps -> ap_predict_x0).  Noise element e = b * L + l uses Philox block offset + e / 4.
+ * offset_dev: optional device word ADDED to `offset`, so that a captured CUDA graph of a micro-batch can be replayed with a
+ * moving noise offset (advance it on the stream with ap_u64_add); NULL = `offset` alone. */
+int ap_diffwave_smooth_denoise(ap_diffwave_t h, const float* x, float sigma, float scale, const float* z_or_null,
+                               uint64_t seed, uint64_t offset, const uint64_t* offset_dev, float t, float sqrt_recip_ab,
+                               float sqrt_recipm1_ab, float* x0, int B, int L, void* stream);
+/* *dev += inc, enqueued on `stream` (one thread) */
+int ap_u64_add(uint64_t* dev, uint64_t inc, void* stream);
 /* standard-normal fill (diagnostics / statistical tests of the in-kernel RNG) */
 int ap_randn(float* out, uint64_t n, uint64_t seed, uint64_t offset, void* stream);
 
@@ -212,9 +225,10 @@ int ap_classifier_get_mode(ap_classifier_t h);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Votes (replaces the argmax + per-class .sum().item() loop of smooth_predict, certified_robust.py:59-67)
- * counts: device int64[K], ACCUMULATED (caller zeroes it); ties resolve to the lowest class index like torch.max.
+ * counts: device int64[counts_len], ACCUMULATED (caller zeroes it); K = logits.shape[-1] must not exceed counts_len (the
+ * reference sizes counts from output.shape[-1], certified_robust.py:60-63); ties resolve to the lowest class index like torch.max.
  * ------------------------------------------------------------------------------------------------------------- */
-int ap_vote_counts(const float* logits, int B, int K, long long* counts, void* stream);
+int ap_vote_counts(const float* logits, int B, int K, long long* counts, int counts_len, void* stream);
 int ap_argmax(const float* logits, int B, int K, int* pred, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

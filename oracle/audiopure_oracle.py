@@ -285,26 +285,40 @@ def sde_step_coefficients(tab, s: torch.Tensor):
     return {"d": d, "beta": beta, "sqrt_1m_ab": tab["sqrt_1m_alphas_cumprod"][d], "g": scale * torch.sqrt(beta)}
 
 
-def sde_purify(sd, x0, t_star: int, noise, T: int = 200, eps_fn=None, **wn_kw):
-    """RevDiffWave.audio_editing_sample with sample_step=1, rand_t=False (diffwave_sde.py:166-211).
+def sde_purify(sd, x0, t_star: int, noise, T: int = 200, eps_fn=None, sample_step: int = 1, noise_level=None,
+               grad_through_eps: bool = False, **wn_kw):
+    """RevDiffWave.audio_editing_sample (diffwave_sde.py:166-211): ``sample_step`` chained rounds, outputs concatenated on the
+    batch dimension (:182,:211); ``noise_level`` = the (rand_t-jittered) diffusion level of :185-190, default t_star -- the
+    solver span always uses t_star (:193-196).
 
-    noise order: e (diffusion), then one N(0,1) tensor per Euler step (dW = sqrt(ds) * z).
+    noise order per round: e (diffusion), then one N(0,1) tensor per Euler step (dW = sqrt(ds) * z).
+    The network evaluation inside the drift is a constant for autograd, as in the reference (``compute_eps_t`` is
+    ``@torch.no_grad()``, diffwave_ddpm.py:166, called at diffwave_sde.py:94); ``grad_through_eps=True`` differentiates it.
     """
     x0 = _t(x0, torch.float32)
     tab = sde_tables(T, 0.0001 * T, 0.02 * T)
     eps_fn = eps_fn or (lambda xx, tt: wavenet_forward(sd, xx, tt * torch.ones(xx.shape[0], 1), **wn_kw))
     a = (1 - tab["discrete_betas"]).cumprod(dim=0)             # :189
-    e = noise(x0.shape)
-    x = x0 * a[t_star - 1].sqrt() + e * (1.0 - a[t_star - 1]).sqrt()   # :190
-    for s, ds in sde_euler_schedule(t_star, T):
-        c = sde_step_coefficients(tab, s)
-        eps = eps_fn(x, c["d"]).to(torch.float32)              # compute_eps_t(x, disc_steps[0])   :94
-        drift = -0.5 * c["beta"] * x                            # vpsde_fn                          :80
-        score = -eps / c["sqrt_1m_ab"]                          #                                   :98
-        rdrift = drift - c["beta"] * score                      # diffusion**2 == beta              :103
-        f = -rdrift                                             #                                   :124
-        x = x + f * ds + c["g"] * torch.sqrt(ds) * noise(x.shape)
-    return x
+    level = t_star if noise_level is None else noise_level
+    xs = []
+    for _ in range(sample_step):
+        e = noise(x0.shape)
+        x = x0 * a[level - 1].sqrt() + e * (1.0 - a[level - 1]).sqrt()   # :190
+        for s, ds in sde_euler_schedule(t_star, T):
+            c = sde_step_coefficients(tab, s)
+            if grad_through_eps:
+                eps = eps_fn(x, c["d"]).to(torch.float32)
+            else:
+                with torch.no_grad():
+                    eps = eps_fn(x.detach(), c["d"]).to(torch.float32)      # compute_eps_t(x, disc_steps[0])   :94
+            drift = -0.5 * c["beta"] * x                            # vpsde_fn                          :80
+            score = -eps / c["sqrt_1m_ab"]                          #                                   :98
+            rdrift = drift - torch.sqrt(c["beta"]) ** 2 * score     # diffusion[:, None] ** 2 * score   :103
+            f = -rdrift                                             #                                   :124
+            x = x + f * ds + c["g"] * torch.sqrt(ds) * noise(x.shape)
+        x0 = x
+        xs.append(x0)
+    return torch.cat(xs, dim=0)
 
 
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,279 @@
+"""GPU parity at the BASELINE shapes (run with ``-m gpu`` on a B200): the CUDA path, called through the C ABI, against golden
+pack v2 -- outputs of the UNMODIFIED reference at L = 16 000 / 32 000 (tests/golden/make_golden_v2.py) and of the reference's own
+RevDiffWave (tests/golden/make_golden_sde.py).
+
+Tolerances (BASELINE.json north_star + VERDICT r01 item 1):
+  eps at L = 16 000:   bf16 <= 1e-2, bf16x3 <= 1e-4, fp32 <= 2e-5          (rel-L2, the strong metric)
+  one-shot x0_hat:     bf16 <= 1e-2, bf16x3 <= 2e-5, fp32 <= 1e-5
+  top-1 over 32 clips: 32/32 in fp32; in bf16 (tf32 classifier) every clip whose reference margin exceeds MARGIN must agree,
+                       and the agreement is printed as k/32.
+"""
+import argparse
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_common import CONFIG_JSON, TorchNormalInjector, cuda, rel_l2, synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL_EPS = {"fp32": 2e-5, "bf16": 1e-2, "bf16x3": 1e-4}
+TOL_X0 = {"fp32": 1e-5, "bf16": 1e-2, "bf16x3": 2e-5}
+TOL_WAVE = {"fp32": 1e-5, "bf16": 1e-2, "bf16x3": 1e-5}
+MARGIN = 0.05          # reference top-1 margin (logit units) above which the bf16 / tf32 pipeline must agree
+SIGMAS = ((0.25, 34), (0.5, 66), (1.0, 117))
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ap():
+    import audiopure_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def sd_full():
+    return synthetic.wavenet_state_dict(seed=0)
+
+
+@pytest.fixture(scope="module")
+def diffwave(ap, sd_full):
+    return ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=2, state_dict=sd_full, noise="torch")
+
+
+@pytest.fixture(scope="module")
+def resnext_centred(ap, golden_v2):
+    sd = synthetic.resnext_state_dict(seed=0)
+    sd["classifier.bias"] = golden_v2["resnext_centred_bias"]
+    return ap.ResNeXtClassifier(sd)
+
+
+def margins(logits):
+    s = np.sort(logits, axis=1)
+    return s[:, -1] - s[:, -2]
+
+
+# ------------------------------------------------------------------------------------------------ eps at the benchmark length
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("t", [1, 65, 116])
+def test_eps_at_L16000(diffwave, golden_v2, mode, t):
+    diffwave.model.set_mode(mode)
+    x = cuda(synthetic.synthetic_waveforms(2, 16000, seed=1234))
+    eps = diffwave.model((x, float(t) * torch.ones(2, 1)))
+    err = rel_l2(eps, golden_v2[f"eps_L16000_t{t}"])
+    print(f"eps L=16000 t={t} {mode}: rel-L2 {err:.3e} (tol {TOL_EPS[mode]:.0e})")
+    assert err < TOL_EPS[mode]
+
+
+# ------------------------------------------------------------------------------------------------ smoothing-level inputs
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("sigma,t_star", SIGMAS)
+def test_one_shot_on_smoothing_inputs(ap, diffwave, resnext_centred, golden_v2, mode, sigma, t_star):
+    """certified_robust.py:44-54: x_in = sqrt(abar*) (x + sigma z) -> one_shot_denoise -> mel -> classifier, 8 draws."""
+    diffwave.model.set_mode(mode)
+    resnext_centred.set_mode("fp32" if mode == "fp32" else "tf32")
+    seed = 3000 + int(sigma * 100)
+    x1 = torch.from_numpy(synthetic.synthetic_waveforms(2, 16000, seed=1234))[0:1]
+    tr = ap.sc09_transform()
+    want_lg = golden_v2[f"smooth_logits_sigma{sigma}"]
+    got = []
+    for b in range(2):
+        delta = torch.from_numpy(synthetic.host_noise((4, 1, 16000), seed, b)) * sigma + 0
+        x_in = (1 / (1 + sigma ** 2)) ** 0.5 * (x1.repeat(4, 1, 1) + delta)
+        diffwave.reverse_timestep = t_star
+        x0 = diffwave.one_shot_denoise(x_in.cuda())
+        if b == 0:
+            err = rel_l2(x0[:2], golden_v2[f"smooth_x0_sigma{sigma}"])
+            print(f"one-shot x0 sigma={sigma} t*={t_star} {mode}: rel-L2 {err:.3e} (tol {TOL_X0[mode]:.0e})")
+            assert err < TOL_X0[mode]
+        got.append(resnext_centred(tr(x0)).cpu().numpy())
+    got = np.concatenate(got)
+    agree = got.argmax(1) == want_lg.argmax(1)
+    print(f"  logits max diff {np.abs(got - want_lg).max():.3e}; top-1 {int(agree.sum())}/8")
+    if mode == "fp32":
+        assert agree.all() and np.abs(got - want_lg).max() < 5e-3
+    else:
+        assert agree[margins(want_lg) > MARGIN].all()
+    # the same draws through RobustCertificate.smooth_predict (noise drawn exactly like the reference: torch.normal on the CPU)
+    rc = ap.RobustCertificate(classifier=resnext_centred, transform=tr, denoiser=diffwave, noise="torch", distributed=False)
+    with TorchNormalInjector(seed) as inj:
+        counts = rc.smooth_predict(x1.cuda(), num_sampling=8, sigma=sigma, batch_size=4)
+        assert inj.i == 2
+    assert diffwave.reverse_timestep == t_star
+    if mode == "fp32" or (margins(want_lg) > MARGIN).all():
+        assert np.array_equal(counts.numpy(), golden_v2[f"smooth_counts_sigma{sigma}"])
+    diffwave.reverse_timestep = 2
+
+
+# ------------------------------------------------------------------------------------------------ top-1 over 32 clips
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+def test_top1_over_32_clips(ap, diffwave, resnext_centred, trained_checkpoints, golden_v2, mode):
+    """DDPM t* = 2 -> mel -> ResNeXt (and -> the TRAINED M5) on 32 clips with the reference's noise: top-1 agreement k/32."""
+    diffwave.model.set_mode(mode)
+    diffwave.reverse_timestep = 2
+    resnext_centred.set_mode("fp32" if mode == "fp32" else "tf32")
+    m5 = ap.M5Classifier(trained_checkpoints["m5"])
+    tr = ap.sc09_transform()
+    x32 = torch.from_numpy(synthetic.synthetic_waveforms(32, 16000, seed=4321))
+    pur = []
+    with TorchNormalInjector(2040) as inj:
+        for i in range(0, 32, 8):
+            pur.append(diffwave(x32[i:i + 8].cuda()))
+        assert inj.i == 8
+    pur = torch.cat(pur)
+    err = rel_l2(pur[:2], golden_v2["top1_purified_first2"])
+    want, want5 = golden_v2["top1_logits"], golden_v2["top1_m5_logprobs"]
+    got, got5 = resnext_centred(tr(pur)).cpu().numpy(), m5(pur).cpu().numpy()
+    agree, agree5 = got.argmax(1) == want.argmax(1), got5.argmax(1) == want5.argmax(1)
+    big = margins(want) > MARGIN
+    print(f"top-1 {mode}: purified rel-L2 {err:.3e}; ResNeXt {int(agree.sum())}/32 (margin>{MARGIN}: {int(agree[big].sum())}/"
+          f"{int(big.sum())}), logits max diff {np.abs(got - want).max():.3e}; trained M5 {int(agree5.sum())}/32, "
+          f"log-prob max diff {np.abs(got5 - want5).max():.3e}; classes seen {sorted(set(want.argmax(1).tolist()))}")
+    assert err < TOL_WAVE[mode]
+    if mode == "fp32":
+        assert agree.all() and agree5.all()
+        assert np.abs(got - want).max() < 5e-3 and np.abs(got5 - want5).max() < 5e-3
+    else:
+        assert agree[big].all()
+        assert agree5[margins(want5) > MARGIN].all()
+
+
+# ------------------------------------------------------------------------------------------------ KWS at 2 s, trained checkpoints
+def test_kws_two_second_clips_trained_checkpoint(ap, diffwave, trained_checkpoints, golden_v2):
+    tr = ap.kws_transform()
+    kws = ap.KWSClassifier(trained_checkpoints["kws"])
+    xk = torch.from_numpy(synthetic.synthetic_waveforms(16, 32000, seed=555))
+    mel = tr(xk.cuda())
+    assert tuple(mel.shape) == (16, 1, 32, 161)
+    dmel = float(np.abs(mel[:2].cpu().numpy() - golden_v2["kws2s_mel"]).max())
+    lp = kws(mel).cpu().numpy()
+    want = golden_v2["kws2s_logprobs"]
+    print(f"KWS 2 s: mel max|dB diff| {dmel:.2e}; log-prob max diff {np.abs(lp - want).max():.3e}; top-1 "
+          f"{int((lp.argmax(1) == want.argmax(1)).sum())}/16")
+    assert dmel < 2e-3 and np.abs(lp - want).max() < 5e-3 and (lp.argmax(1) == want.argmax(1)).all()
+    # BASELINE configs[4]: DDPM t* = 2 at L = 32 000 -> KWS mel -> RCNN_KWS
+    for mode in ("fp32", "bf16"):
+        diffwave.model.set_mode(mode)
+        diffwave.reverse_timestep = 2
+        with TorchNormalInjector(2041) as inj:
+            pk = diffwave(xk[:2].cuda())
+            assert inj.i == 2
+        err = rel_l2(pk[:1], golden_v2["kws2s_purified_first1"])
+        lpp = kws(tr(pk)).cpu().numpy()
+        wantp = golden_v2["kws2s_purified_logprobs"]
+        print(f"  purified at L=32000 {mode}: rel-L2 {err:.3e}; log-prob max diff {np.abs(lpp - wantp).max():.3e}")
+        assert err < TOL_WAVE[mode]
+        assert (lpp.argmax(1) == wantp.argmax(1))[margins(wantp) > MARGIN].all()
+        if mode == "fp32":
+            assert np.abs(lpp - wantp).max() < 5e-3
+
+
+def test_trained_m5_and_create_model_on_the_reference_pickle(ap, trained_checkpoints, golden_v2):
+    """create_model.py:8-16 on the reference's OWN pickled M5 module (tests/golden/m5_k160_vanilla_best_acc.pth, a byte copy of
+    audio_models/M5/checkpoints/kernel_size=160/vanilla-best-acc.pth).  The GPU box has no reference checkout, so the class the
+    pickle names (M5Net.M5) is registered as an empty nn.Module subclass: unpickling restores the real torch sub-modules."""
+    x5 = cuda(synthetic.synthetic_waveforms(16, 16000, seed=556))
+    want = golden_v2["m5_trained_logprobs"]
+    direct = ap.M5Classifier(trained_checkpoints["m5"])(x5).cpu().numpy()
+    mod = types.ModuleType("M5Net")
+    mod.M5 = type("M5", (torch.nn.Module,), {})
+    sys.modules["M5Net"] = mod
+    try:
+        model = ap.create_model(os.path.join(GOLDEN_DIR, "m5_k160_vanilla_best_acc.pth"))
+    finally:
+        del sys.modules["M5Net"]
+    assert type(model).__name__ == "M5Classifier" and model.num_classes == 10
+    got = model(x5).cpu().numpy()
+    print(f"trained M5: log-prob max diff {np.abs(got - want).max():.3e}; top-1 {int((got.argmax(1) == want.argmax(1)).sum())}/16")
+    assert np.array_equal(got, direct)
+    assert np.abs(got - want).max() < 5e-3 and (got.argmax(1) == want.argmax(1)).all()
+
+
+# ------------------------------------------------------------------------------------------------ reverse-SDE purifier
+class RandnInjector:
+    """torch.randn_like / torch.randn -> host noise in call order, on the GPU (what make_golden_sde.py fed the reference)."""
+
+    def __init__(self, seed):
+        self.seed, self.i = seed, 0
+
+    def __enter__(self):
+        self._like, self._randn = torch.randn_like, torch.randn
+
+        def nxt(shape):
+            z = cuda(synthetic.host_noise(tuple(shape), self.seed, self.i))
+            self.i += 1
+            return z
+        torch.randn_like = lambda t, **kw: nxt(t.shape)
+        torch.randn = lambda *size, **kw: nxt(size[0] if len(size) == 1 and not isinstance(size[0], int) else size)
+        return self
+
+    def __exit__(self, *a):
+        torch.randn_like, torch.randn = self._like, self._randn
+
+
+def _rev(ap, sd_full, t, mode, **kw):
+    a = dict(ddpm_path=None, ddpm_config=CONFIG_JSON, t=t, score_type="guided_diffusion", rand_t=False, t_delta=15, use_bm=False,
+             sample_step=1)
+    a.update(kw)
+    return ap.RevDiffWave(argparse.Namespace(**a), state_dict=sd_full, noise="torch", mode=mode)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_sde_values_vs_reference_revdiffwave(ap, sd_full, golden_sde, mode):
+    tol = 2e-5 if mode == "fp32" else 1e-2
+    x = cuda(synthetic.synthetic_waveforms(1, 16000, seed=21))
+    for t, seed, key in ((3, 3103, "t3_out"), (7, 3107, "t7_out")):
+        with torch.no_grad(), RandnInjector(seed):
+            y = _rev(ap, sd_full, t, mode)(x)
+        err = rel_l2(y, golden_sde[key])
+        print(f"sde t*={t} {mode}: rel-L2 {err:.3e}")
+        assert err < tol
+    with torch.no_grad(), RandnInjector(3202) as inj:
+        y = _rev(ap, sd_full, 2, mode, sample_step=2)(x)
+        assert inj.i == int(golden_sde["ss2_noise_draws"])
+    assert tuple(y.shape) == (2, 1, 16000) and rel_l2(y, golden_sde["ss2_out"]) < tol
+    np.random.seed(11)
+    with torch.no_grad(), RandnInjector(3304):
+        y = _rev(ap, sd_full, 4, mode, rand_t=True, t_delta=3)(x)
+    assert rel_l2(y, golden_sde["randt_out"]) < tol
+
+
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3"])
+def test_sde_gradient_matches_the_reference_semantics(ap, sd_full, golden_sde, mode):
+    """The reference's compute_eps_t is @torch.no_grad() (diffwave_ddpm.py:166) and RevVPSDE.rvpsde_fn calls it
+    (diffwave_sde.py:94): the gradient that reaches a white-box attack through the SDE purifier holds eps constant.  Default
+    RevDiffWave reproduces it (rel-L2 <= 1e-5 in every arithmetic mode -- the gradient does not depend on the network's
+    precision); grad_through_eps=True is a different, opt-in quantity."""
+    w = cuda(golden_sde["w"])
+    x = cuda(synthetic.synthetic_waveforms(1, 16000, seed=21))
+    xg = x.clone().requires_grad_(True)
+    with RandnInjector(3103):
+        y = _rev(ap, sd_full, 3, mode)(xg)
+    (g,) = torch.autograd.grad((y * w[:1]).sum(), xg)
+    err = rel_l2(g, golden_sde["t3_grad"])
+    print(f"sde t*=3 gradient (eps detached, {mode}): rel-L2 {err:.3e}")
+    assert err < 1e-5
+    xg = x.clone().requires_grad_(True)
+    with RandnInjector(3202):
+        y = _rev(ap, sd_full, 2, mode, sample_step=2)(xg)
+    (g,) = torch.autograd.grad((y * w).sum(), xg)
+    err = rel_l2(g, golden_sde["ss2_grad"])
+    print(f"sde sample_step=2 gradient (eps detached, {mode}): rel-L2 {err:.3e}")
+    assert err < 1e-5
+    # opt-in: the exact gradient of the computed chain (through the network) is a different vector
+    rdw = _rev(ap, sd_full, 3, mode)
+    rdw.grad_through_eps = True
+    xg = x.clone().requires_grad_(True)
+    with RandnInjector(3103):
+        y = rdw(xg)
+    (g2,) = torch.autograd.grad((y * w[:1]).sum(), xg)
+    assert rel_l2(g2, golden_sde["t3_grad"]) > 1e-3
+
+
+def test_sde_use_bm_raises(ap, sd_full):
+    with pytest.raises(NotImplementedError):
+        _rev(ap, sd_full, 2, "bf16", use_bm=True)

@@ -118,8 +118,9 @@ def test_vote_counts(ap):
     logits[7, 3] = logits[7, 8] = 9.0     # tie -> lowest index
     counts = torch.zeros(10, dtype=torch.int64, device="cuda")
     lc = logits.cuda()
-    _lib.check(lib.ap_vote_counts(lc.data_ptr(), 1001, 10, counts.data_ptr(), _lib.stream_ptr()))
-    _lib.check(lib.ap_vote_counts(lc.data_ptr(), 1001, 10, counts.data_ptr(), _lib.stream_ptr()))   # accumulates
+    _lib.check(lib.ap_vote_counts(lc.data_ptr(), 1001, 10, counts.data_ptr(), 10, _lib.stream_ptr()))
+    _lib.check(lib.ap_vote_counts(lc.data_ptr(), 1001, 10, counts.data_ptr(), 10, _lib.stream_ptr()))   # accumulates
+    assert lib.ap_vote_counts(lc.data_ptr(), 1001, 10, counts.data_ptr(), 9, _lib.stream_ptr()) == -1   # K > len(counts)
     ref = torch.bincount(logits.max(1)[1], minlength=10)
     assert torch.equal(counts.cpu(), 2 * ref) and int(counts.sum()) == 2002
 
@@ -214,7 +215,7 @@ def test_error_paths(ap, diffwave):
     assert lib.ap_diffwave_eps(diffwave.model._handle, x.data_ptr(), 1.0, x.data_ptr(), 0, 256, None) == -1      # B == 0
     assert b"positive" in lib.ap_last_error()
     assert lib.ap_diffwave_eps(None, x.data_ptr(), 1.0, x.data_ptr(), 2, 256, None) == -1                          # null handle
-    assert lib.ap_vote_counts(x.data_ptr(), 4, 0, x.data_ptr(), None) == -1                                       # K == 0
+    assert lib.ap_vote_counts(x.data_ptr(), 4, 0, x.data_ptr(), 10, None) == -1                                       # K == 0
     with pytest.raises(_lib.AudioPureError):
         ap.MelSpectrogramDB(n_fft=2048, hop_length=512, n_mels=32, pad_mode="reflect")(torch.zeros(1, 1, 512, device="cuda"))
     with pytest.raises(AssertionError):
@@ -392,19 +393,20 @@ def test_sde_purifier_vs_oracle(ap, orc, sd_full, mode, t_star):
 
 
 def test_sde_purifier_gradient_vs_oracle_autograd(ap, orc, sd_full):
-    """RevDiffWave.forward is differentiable (the reference uses torchsde.sdeint_adjoint): gradient of <w, purified> through
-    the Euler-Maruyama chain (t* = 2) vs autograd over the oracle's restatement, same injected noise."""
+    """The OPT-IN exact gradient of the Euler-Maruyama chain (``grad_through_eps=True``: back-propagation through the network,
+    which the reference does not do -- its compute_eps_t is no_grad; the default, reference-faithful gradient is pinned to the
+    reference in test_gpu_golden_v2.py): gradient of <w, purified> (t* = 2) vs autograd over the oracle, same injected noise."""
     import argparse
     t_star = 2
     args = argparse.Namespace(ddpm_path=None, ddpm_config=CONFIG_JSON, t=t_star, score_type="guided_diffusion", rand_t=False,
                               t_delta=0, use_bm=False, sample_step=1)
-    rdw = ap.RevDiffWave(args, state_dict=sd_full, noise="torch", mode="bf16x3")
+    rdw = ap.RevDiffWave(args, state_dict=sd_full, noise="torch", mode="bf16x3", grad_through_eps=True)
     x = synthetic.synthetic_waveforms(2, 1024, seed=21)
     w = synthetic.host_noise(x.shape, 77, 0)
     n_steps = len(orc.sde_euler_schedule(t_star))
     zs = [synthetic.host_noise(x.shape, 3000 + t_star, i) for i in range(1 + n_steps)]
     xo = torch.from_numpy(x).requires_grad_(True)
-    yo = orc.sde_purify(sd_full, xo, t_star, orc.NoiseSource(zs))
+    yo = orc.sde_purify(sd_full, xo, t_star, orc.NoiseSource(zs), grad_through_eps=True)
     (g_want,) = torch.autograd.grad((yo * torch.from_numpy(w)).sum(), xo)
     it = iter(zs)
     orig_like, orig_randn = torch.randn_like, torch.randn

@@ -285,3 +285,96 @@ def test_densenet_family(golden, golden_grad, golden_vgg, key, depth):
     spec = torch.from_numpy(golden_grad["resnext_in_spec"]).clone().requires_grad_(True)
     (gs,) = torch.autograd.grad(orc.densenet_forward(sd, spec, depth=depth), spec, torch.from_numpy(golden_grad["resnext_g_logits"]))
     assert rel_l2(gs.numpy(), golden_vgg[f"{key}_grad"]) < 1e-4
+
+
+# ================================================================================================ golden pack v2 (BASELINE shapes)
+def test_v2_wavenet_at_benchmark_length(golden_v2, sd_full):
+    """eps at L = 16 000 (every dilation up to 2048 reads real samples, not only padding), t = 65."""
+    x = synthetic.synthetic_waveforms(2, 16000, seed=1234)
+    eps = orc.wavenet_forward(sd_full, x, 65.0 * torch.ones(2, 1)).numpy()
+    assert rel_l2(eps, golden_v2["eps_L16000_t65"]) < 2e-5
+
+
+def test_v2_one_shot_on_smoothing_level_input(golden_v2, sd_full, hp):
+    """certified_robust.py:44-54 at sigma = 1.0 (t* = 117): x0_hat of sqrt(abar*) (x + sigma z)."""
+    sigma, t_star = 1.0, 117
+    assert orc.compute_t_star(hp, sigma) == t_star
+    x1 = torch.from_numpy(synthetic.synthetic_waveforms(2, 16000, seed=1234))[0:1]
+    z = torch.from_numpy(synthetic.host_noise((4, 1, 16000), 3000 + int(sigma * 100), 0))
+    x_in = (1 / (1 + sigma ** 2)) ** 0.5 * (x1.repeat(4, 1, 1) + z * sigma)
+    x0 = orc.one_shot_denoise(sd_full, x_in[:2], hp, t_star).numpy()
+    assert rel_l2(x0, golden_v2["smooth_x0_sigma1.0"]) < 1e-5
+
+
+def test_v2_classifiers_on_purified_clips(golden_v2, trained_checkpoints):
+    """mel -> ResNeXt (centred bias) and the TRAINED M5 on the reference's purified clips: logits, top-1."""
+    pur = golden_v2["top1_purified_first2"]
+    rx = synthetic.resnext_state_dict(seed=0)
+    rx["classifier.bias"] = golden_v2["resnext_centred_bias"]
+    lg = orc.resnext_forward(rx, orc.mel_db(pur, **orc.MEL_SC09)).numpy()
+    assert np.abs(lg - golden_v2["top1_logits"][:2]).max() < 2e-3
+    assert (lg.argmax(1) == golden_v2["top1_logits"][:2].argmax(1)).all()
+    lp = orc.m5_forward(trained_checkpoints["m5"], pur).numpy()
+    assert np.abs(lp - golden_v2["top1_m5_logprobs"][:2]).max() < 1e-3
+    assert len(set(golden_v2["top1_logits"].argmax(1).tolist())) >= 5        # the 32-clip top-1 golden is not unanimous
+    assert len(set(golden_v2["top1_m5_logprobs"].argmax(1).tolist())) >= 5
+
+
+def test_v2_trained_m5_and_kws_at_two_seconds(golden_v2, trained_checkpoints):
+    xk = synthetic.synthetic_waveforms(16, 32000, seed=555)
+    mel = orc.mel_db(xk, **orc.MEL_KWS).numpy()
+    assert mel.shape == (16, 1, 32, 161)
+    assert np.abs(mel[:2] - golden_v2["kws2s_mel"]).max() < 2e-3
+    lp = orc.kws_forward(trained_checkpoints["kws"], mel).numpy()
+    assert np.abs(lp - golden_v2["kws2s_logprobs"]).max() < 2e-3
+    assert (lp.argmax(1) == golden_v2["kws2s_logprobs"].argmax(1)).all()
+    x5 = synthetic.synthetic_waveforms(16, 16000, seed=556)
+    l5 = orc.m5_forward(trained_checkpoints["m5"], x5).numpy()
+    assert np.abs(l5 - golden_v2["m5_trained_logprobs"]).max() < 1e-3
+    assert (l5.argmax(1) == golden_v2["m5_trained_logprobs"].argmax(1)).all()
+
+
+def test_create_model_unpickles_the_reference_m5_checkpoint(golden_v2):
+    """create_model.py:8-16 loads a WHOLE pickled module; the vendored file is the reference's own M5 checkpoint.  Here (CPU) only
+    the unpickle + state-dict extraction is exercised; the -m gpu twin runs it through classifiers.create_model."""
+    import types
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "m5_k160_vanilla_best_acc.pth")
+    mod = types.ModuleType("M5Net")
+    mod.M5 = type("M5", (torch.nn.Module,), {})
+    sys.modules["M5Net"] = mod
+    try:
+        model = torch.load(path, map_location="cpu", weights_only=False)
+    finally:
+        del sys.modules["M5Net"]
+    assert type(model).__name__ == "M5" and model.conv1.kernel_size == (160,) and model.conv1.stride == (16,)
+    sd = {k: v.numpy() for k, v in model.state_dict().items()}
+    x5 = synthetic.synthetic_waveforms(16, 16000, seed=556)
+    assert np.abs(orc.m5_forward(sd, x5).numpy() - golden_v2["m5_trained_logprobs"]).max() < 1e-3
+
+
+# ================================================================================================ SDE purifier vs the reference's RevDiffWave
+def _noise(seed, n, shape):
+    return orc.NoiseSource([synthetic.host_noise(shape, seed, i) for i in range(n)])
+
+
+def test_sde_oracle_vs_reference_revdiffwave(golden_sde, sd_full):
+    """value and gradient of the reference's RevDiffWave.audio_editing_sample (its f / g / level / chaining code; only the Euler
+    stepping loop is a restatement): t* = 3, sample_step = 1.  eps is a constant of the differentiation (no_grad in the reference)."""
+    x = torch.from_numpy(synthetic.synthetic_waveforms(1, 16000, seed=21)).requires_grad_(True)
+    w = torch.from_numpy(golden_sde["w"])
+    y = orc.sde_purify(sd_full, x, 3, _noise(3103, int(golden_sde["t3_noise_draws"]), (1, 1, 16000)))
+    assert rel_l2(y.detach().numpy(), golden_sde["t3_out"]) < 1e-5
+    (g,) = torch.autograd.grad((y * w[:1]).sum(), x)
+    assert rel_l2(g.numpy(), golden_sde["t3_grad"]) < 1e-6
+
+
+def test_sde_oracle_sample_step_and_rand_t(golden_sde, sd_full):
+    x = torch.from_numpy(synthetic.synthetic_waveforms(1, 16000, seed=21)).requires_grad_(True)
+    w = torch.from_numpy(golden_sde["w"])
+    y = orc.sde_purify(sd_full, x, 2, _noise(3202, int(golden_sde["ss2_noise_draws"]), (1, 1, 16000)), sample_step=2)
+    assert y.shape == (2, 1, 16000) and rel_l2(y.detach().numpy(), golden_sde["ss2_out"]) < 1e-5
+    (g,) = torch.autograd.grad((y * w).sum(), x)
+    assert rel_l2(g.numpy(), golden_sde["ss2_grad"]) < 1e-6
+    with torch.no_grad():
+        yr = orc.sde_purify(sd_full, x.detach(), 4, _noise(3304, 5, (1, 1, 16000)), noise_level=int(golden_sde["randt_level"]))
+    assert rel_l2(yr.numpy(), golden_sde["randt_out"]) < 1e-5

@@ -359,6 +359,45 @@ __device__ __forceinline__ float gate_exp(float a, float s) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((E + 1.f) * (1.f + F)));
   return (E - 1.f) * r;
 }
+// ---- the gate WITHOUT transcendental-pipe exponentials.  ncu on k1_layer: the XU pipe (MUFU.TANH x 2 per gate channel plus the
+// F2FP packs) is 97.5 % busy -- the layer kernel is bound by it, not by the tensor pipe (79 %).  2^x is therefore evaluated on
+// the FMA / ALU pipes: x = j + f with j = round(x), |f| <= 0.5 (magic-number rounding), 2^f by a minimax polynomial of degree
+// DEG in packed fp32x2 arithmetic, 2^j by adding j into the exponent field.  Relative error 7.5e-5 (DEG 3), 2.6e-6 (DEG 4),
+// 7.5e-8 (DEG 5).  One MUFU.RCP per channel remains:
+//     tanh(a) sigmoid(s) = (E - 1) / ((E + 1)(1 + F)),  E = 2^(2 log2e a),  F = 2^(-log2e s)
+// max abs error of the gate vs float64: 3.7e-5 (DEG 3; MUFU.TANH's 2^-11 gives 7e-4), 1.3e-6 (DEG 4), < 1e-7 (DEG 5).
+template <int DEG> __host__ __device__ constexpr float ex2_coef(int k) {
+  return DEG == 3 ? (k == 0 ? 0.99992807f : k == 1 ? 0.69326099f : k == 2 ? 0.24261112f : 0.055171638f)
+       : DEG == 4 ? (k == 0 ? 0.99999926f : k == 1 ? 0.69312181f : k == 2 ? 0.24024745f : k == 3 ? 0.055917860f : 0.0095700983f)
+                  : (k == 0 ? 1.00000007f : k == 1 ? 0.69314697f : k == 2 ? 0.24022120f : k == 3 ? 0.055507133f
+                     : k == 4 ? 0.0096755413f : 0.0013276468f);
+}
+// 2^x for two values; x is clamped to [-64, 64] (the caller's quotient saturates long before)
+template <int DEG> __device__ __forceinline__ f32x2 ex2_poly2(f32x2 x) {
+  float x0, x1;
+  up2(x, x0, x1);
+  x = pk2(fminf(fmaxf(x0, -64.f), 64.f), fminf(fmaxf(x1, -64.f), 64.f));
+  const float M = 12582912.f;                                       // 1.5 * 2^23: x + M has round(x) in its low mantissa bits
+  const f32x2 r = add2(x, pk2(M, M));
+  const f32x2 f = fma2(add2(r, pk2(-M, -M)), pk2(-1.f, -1.f), x);   // x - round(x)
+  f32x2 p = pk2(ex2_coef<DEG>(DEG), ex2_coef<DEG>(DEG));
+#pragma unroll
+  for (int k = DEG - 1; k >= 0; --k) p = fma2(p, f, pk2(ex2_coef<DEG>(k), ex2_coef<DEG>(k)));
+  float p0, p1, r0, r1;
+  up2(p, p0, p1);
+  up2(r, r0, r1);
+  return pk2(__int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23)),
+             __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23)));
+}
+// the gate of two channels: x = 2 log2e (a_t + b_t), y = -log2e (a_s + b_s) (the caller folds scale and bias into one FFMA2)
+template <int DEG> __device__ __forceinline__ f32x2 gate_poly2(f32x2 x, f32x2 y) {
+  const f32x2 E = ex2_poly2<DEG>(x), F = ex2_poly2<DEG>(y), one = pk2(1.f, 1.f);
+  float d0, d1, r0, r1;
+  up2(mul2(add2(E, one), add2(F, one)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  return mul2(add2(E, pk2(-1.f, -1.f)), pk2(r0, r1));
+}
 __device__ __forceinline__ float sigmoid_exp(float x) {
   return __fdividef(1.f, 1.f + __expf(-fminf(fmaxf(x, -80.f), 80.f)));
 }

@@ -36,6 +36,22 @@ namespace tc {
 using namespace ptx;
 
 constexpr int C = 256;                      // channels (res == skip)
+// Gate variants (development switches, devtools/ab_compare.py).  MEASURED (r02, same box, sustained): evaluating the gate's
+// exponentials on the FMA pipe (gate_poly2: one MUFU.RCP per channel instead of two MUFU.TANH) makes k1_layer SLOWER
+// (1.72 -> 2.22 ms per 128 waveforms): a microbenchmark puts MUFU at 16 results/clk/SM, so the two tanh of a tile cost
+// 4096 of its 14336 clk -- the epilogue is bound by its instruction count / dependency chains, not by the XU pipe, and the
+// polynomial adds ~9 FMA-pipe + 6 ALU instructions per channel.  Kept for the record and for accuracy studies (3.7e-5 max
+// abs error vs 7e-4 for MUFU.TANH).
+#ifdef AP_GATE_POLY
+constexpr bool kGatePoly = true;
+#else
+constexpr bool kGatePoly = false;
+#endif
+#ifdef AP_SPLIT_GATE_POLY
+constexpr bool kSplitGatePoly = true;
+#else
+constexpr bool kSplitGatePoly = false;
+#endif
 constexpr int TILE_M = 128;                 // positions per tile (per CTA)
 constexpr int A_BYTES = TILE_M * 128;       // [128 rows][64 bf16]  SWIZZLE_128B
 constexpr int OUT_BYTES = 4 * A_BYTES;      // 4 K-blocks of [128][64] bf16 (gate output / skip-sum staging)
@@ -200,10 +216,18 @@ struct K1Params {
   // the Wd / Wr maps (0 otherwise); the lo plane of u_in / u_out starts u_plane * L * 256 elements after the hi plane
   int u_plane, o_plane, wd_plane, wr_plane;
   // dilated-conv biases in packed chunk order: [j][0..127] tanh bias of gate channel 128 j + c, [j][128..255] HALF the
-  // sigmoid bias of the same channel (sigmoid(s) = 0.5 tanh(0.5 s) + 0.5).  They live in the kernel-parameter constant
-  // bank, so the bias add is a constant operand of the FADD / FFMA: no shared-memory or shuffle traffic in the epilogue.
-  float bd[512];
+  // sigmoid bias of the same channel (sigmoid(s) = 0.5 tanh(0.5 s) + 0.5) -- the SAVE kernels and k1_split; for k1_layer's
+  // inference gate (gate_poly2) the host pre-scales them to 2 log2e b_t | -log2e b_s.  They live in the kernel-parameter
+  // constant bank, so the bias add is a constant operand of the FADD / FFMA: no shared-memory or shuffle traffic in the epilogue.
+  alignas(8) float bd[512];
 };
+
+// Development aid (AP_TC_DEBUG=1): SM-clock timestamps of the MMA jobs and the epilogue phases of tiles kTraceTile0.. of CTA 0,
+// rows 200.. of the debug table ([tile][32 slots]); devtools/probe.py prints the reconstructed timeline.
+constexpr uint32_t kTraceTile0 = 60, kTraceTiles = 3;
+__device__ __forceinline__ void trace(const K1Params& p, uint32_t ti, int slot) {
+  if (p.dbg && blockIdx.x == 0 && ti - kTraceTile0 < kTraceTiles) p.dbg[200 * 16 + (ti - kTraceTile0) * 32 + slot] = clock64();
+}
 
 // Order of the accumulation jobs of one CTA (pair), shared by the TMA producer, the MMA issuer and the epilogue warps:
 //   G1c0(0) G1c1(0) | G1c0(1) G2(0) G1c1(1) | G1c0(2) G2(1) G1c1(2) | ... | G2(T-1)
@@ -234,6 +258,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     const uint32_t r = g & 1;
     w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 9);
     tc_fence_after();
+    if (etid == 0) trace(p, ti, 8 + J * 8);
     uint32_t ta[2][32], sg[2][32];
 #pragma unroll
     for (int gq = 0; gq < 2; ++gq) {
@@ -244,6 +269,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     tc_fence_before();
     __syncwarp();
     if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);   // accumulators are in registers: the region is free again
+    if (etid == 0) trace(p, ti, 9 + J * 8);
     uint32_t pk[2][4][4];
     uint32_t tsk[2][4];                    // SAVE: packed tanh / sigmoid of the current 8 channels
 #pragma unroll
@@ -254,7 +280,17 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
         for (int e = 0; e < 4; ++e) {
           const int c0 = i * 8 + 2 * e;
           const int cb = J * 256 + HSEL * 64 + gq * 32 + c0;
-          {
+          if constexpr (!SAVE && kGatePoly) {
+            // exponentials on the FMA pipe, one MUFU.RCP per channel (gate_poly2; p.bd holds 2 log2e b_t | -log2e b_s here)
+            const float2 bt = reinterpret_cast<const float2*>(p.bd)[cb >> 1], bs = reinterpret_cast<const float2*>(p.bd)[(cb + 128) >> 1];
+            const f32x2 x = fma2(pk2(__uint_as_float(ta[gq][c0]), __uint_as_float(ta[gq][c0 + 1])),
+                                 pk2(2.885390081777927f, 2.885390081777927f), pk2(bt.x, bt.y));
+            const f32x2 y = fma2(pk2(__uint_as_float(sg[gq][c0]), __uint_as_float(sg[gq][c0 + 1])),
+                                 pk2(-1.4426950408889634f, -1.4426950408889634f), pk2(bs.x, bs.y));
+            float o0, o1;
+            up2(gate_poly2<3>(x, y), o0, o1);
+            pk[gq][i][e] = pack2<DT>(o0, o1);
+          } else {
             const float t0 = tanh_approx(__uint_as_float(ta[gq][c0]) + p.bd[cb]);
             const float t1 = tanh_approx(__uint_as_float(ta[gq][c0 + 1]) + p.bd[cb + 1]);
             const float s0 = tanh_approx(fmaf(__uint_as_float(sg[gq][c0]), 0.5f, p.bd[cb + 128]));
@@ -278,6 +314,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
           }
         }
     // the staging tile still holds o of the previous tile until its GEMM-2 (the NEXT job, g + 1) has completed
+    if (etid == 0) trace(p, ti, 10 + J * 8);
     if (etid == 0) {                                       // and the O store of chunk J of the previous tile has read it
       if (J == 0 && !p.last && ti > 0) {
         w_g2 += mbar_wait(cx.bar(BAR_ACC_FULL + ((g + 1) & 1)), ((g + 1) >> 1) & 1, 12);
@@ -304,14 +341,17 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
       }
       bulk_commit();                                       // always a group (possibly empty): wait_group counts stay uniform
       cx.arrive_leader(BAR_OUT_READY + J);
+      trace(p, ti, 11 + J * 8);
     }
     ++g;
   };
 
   // ---- residual epilogue: u' = (u + r) * sqrt(.5) + (b_res * sqrt(.5) + p_next) -> bf16, global -> registers -> global
+  uint32_t cur_ti = 0;
   auto residual = [&](bool valid, int b, int l0) {
     const uint32_t r = g & 1;
     const bool live = valid && l0 + row < p.L;
+    if (etid == 0) trace(p, cur_ti, 24);
     const size_t goff = (static_cast<size_t>(b) * p.L + (live ? l0 + row : 0)) * C + HSEL * 128;
     uint32_t uu[8][8];
     if (live) {
@@ -320,6 +360,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     }
     w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 10);
     tc_fence_after();
+    if (etid == 0) trace(p, cur_ti, 25);
 #pragma unroll
     for (int gq = 0; gq < 4; ++gq) {
       uint32_t acc[32];
@@ -329,6 +370,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
+        if (etid == 0) trace(p, cur_ti, 26);
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {                        // 16 channels = one 32-byte access (per plane)
@@ -350,6 +392,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
         if (live) st_global_v8(p.u_out + goff + (gq * 2 + i) * 16, pk);
       }
     }
+    if (etid == 0) trace(p, cur_ti, 27);
     ++g;
   };
 
@@ -360,6 +403,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     const bool valid = tile < p.n_tiles;
     const int b = valid ? tile / p.tiles_per_sample : 0;
     const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+    cur_ti = ti;
     gate(std::integral_constant<int, 0>{}, ti, valid, b, l0);
     if (!p.last && ti > 0) residual(pvalid, pb, pl0);
     gate(std::integral_constant<int, 1>{}, ti, valid, b, l0);
@@ -452,10 +496,13 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
       uint32_t g = 0, ti = 0;
       long long w_full = 0, w_acc = 0, w_out = 0;
       const long long t_start = clock64();
+      int tslot = 0;
       auto gemm1 = [&]() {
         const uint32_t r = g & 1;
+        if (lane == 0) trace(p, ti, tslot);
         w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 3);
         tc_fence_after();
+        if (lane == 0) trace(p, ti, tslot + 1);
         for (int kblk = 0; kblk < 12 * G::NCOMBO; ++kblk, ++it) {
           const uint32_t s = it.s, ph = it.ph;
           w_full += mbar_wait(cx.bar(BAR_FULL + s), ph, 4);
@@ -468,12 +515,15 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
         }
         if (elect_one()) cx.commit(BAR_ACC_FULL + r);
         __syncwarp();
+        if (lane == 0) trace(p, ti, tslot + 2);
         ++g;
       };
       auto gemm2 = [&](uint32_t t_idx) {
         const uint32_t r = g & 1;
+        if (lane == 0) trace(p, ti, 28);
         w_acc += mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 5);
         tc_fence_after();
+        if (lane == 0) trace(p, ti, 29);
         for (int kb = 0; kb < 4; ++kb) {
           if ((kb & 1) == 0) w_out += mbar_wait(cx.bar(BAR_OUT_READY + (kb >> 1)), t_idx & 1, 6);
           for (int cmb = 0; cmb < G::NCOMBO; ++cmb, ++it) {
@@ -489,11 +539,14 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
         }
         if (elect_one()) cx.commit(BAR_ACC_FULL + r);
         __syncwarp();
+        if (lane == 0) trace(p, ti, 30);
         ++g;
       };
       for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+        tslot = 0;
         gemm1();
         if (!p.last && ti > 0) gemm2(ti - 1);
+        tslot = 4;
         gemm1();
       }
       if (!p.last && ti > 0) gemm2(ti - 1);
@@ -570,6 +623,9 @@ __device__ __forceinline__ void k1s_epilogue(const Ctx<G>& cx, const K1Params& p
             o2 = pk2(t0 * g0, t1 * g1);
             tsk[0][e] = pack_bf16x2(g0 * fmaf(-t0, t0, 1.f), g1 * fmaf(-t1, t1, 1.f));
             tsk[1][e] = pack_bf16x2(t0 * g0 * (1.f - g0), t1 * g1 * (1.f - g1));
+          } else if (kSplitGatePoly) {  // one quotient per channel; both exponentials on the FMA pipe (degree-5 polynomial: 1e-7)
+            o2 = gate_poly2<5>(mul2(pk2(a0, a1), pk2(2.885390081777927f, 2.885390081777927f)),
+                               mul2(pk2(s0, s1), pk2(-1.4426950408889634f, -1.4426950408889634f)));
           } else {                // one quotient per channel, two channels per instruction (packed fp32x2 arithmetic)
             o2 = gate_exp2(pk2(a0, a1), pk2(s0, s1));
           }
@@ -1764,6 +1820,15 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     p.u_out = (l & 1) ? n->u0.as<uint16_t>() : n->u1.as<uint16_t>();
     p.o_out = n->o.as<uint16_t>();
     std::memcpy(p.bd, n->bd_host.data() + static_cast<size_t>(l) * 512, sizeof(p.bd));
+    if (!save && n->dt != 2 && tc::kGatePoly) {
+      // k1_layer's gate evaluates 2^(2 log2e (a_t + b_t)) and 2^(-log2e (a_s + b_s)) on the FMA pipe (gate_poly2): the biases
+      // travel pre-scaled, so that scale and bias are ONE packed FFMA.  bd_host holds b_t and HALF of b_s.
+      for (int j = 0; j < 2; ++j)
+        for (int c = 0; c < 128; ++c) {
+          p.bd[j * 256 + c] *= 2.885390081777927f;
+          p.bd[j * 256 + 128 + c] *= -2.f * 1.4426950408889634f;
+        }
+    }
     p.b_res = n->br.as<float>() + static_cast<size_t>(l) * C;
     p.p_next = ptab + static_cast<size_t>(l + 1) * C;
     p.dbg = (l == n->dbg_layer) ? n->dbg.as<long long>() : nullptr;

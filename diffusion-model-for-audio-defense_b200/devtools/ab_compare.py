@@ -21,7 +21,7 @@ def one(seconds):
     from audiopure_b200 import _lib, synthetic
     B, L = 512, 16000
     sd = synthetic.wavenet_state_dict(seed=0)
-    net = ap.WaveNet(sd, mode="bf16", **synthetic.DEFAULT_WAVENET_CONFIG)
+    net = ap.WaveNet(sd, mode=os.environ.get("AP_AB_MODE", "bf16"), **synthetic.DEFAULT_WAVENET_CONFIG)
     lib = _lib.load()
     x = torch.from_numpy(synthetic.synthetic_waveforms(B, L, seed=1)).cuda()
     out = torch.empty_like(x)

@@ -51,6 +51,17 @@ def main():
         for i, nm in enumerate(names):
             src = lead if nm.startswith("mma") or nm == "tiles" else act
             print(f"  {nm:20s} {src[:, i].mean():14.0f}")
+        tr = buf[200:].reshape(-1)[: 3 * 32].reshape(3, 32)
+        if tr.any():
+            names_t = {0: "G1c0 wait acc_empty", 1: "G1c0 issue start", 2: "G1c0 issued", 28: "G2 wait acc_empty", 29: "G2 issue start(after out_ready)",
+                       30: "G2 issued", 4: "G1c1 wait acc_empty", 5: "G1c1 issue start", 6: "G1c1 issued", 8: "gate0 acc_full", 9: "gate0 tmem loaded",
+                       10: "gate0 math done", 11: "gate0 staged", 24: "res begin(u loads issued)", 25: "res acc_full", 26: "res tmem loaded",
+                       27: "res done", 16: "gate1 acc_full", 17: "gate1 tmem loaded", 18: "gate1 math done", 19: "gate1 staged"}
+            t0 = tr[0][tr[0] > 0].min()
+            ev = sorted((int(tr[k, s] - t0), k, names_t[s]) for k in range(3) for s in names_t if tr[k, s] > 0)
+            print("timeline of CTA 0 (clk since the first event; tile index relative to tile 60):")
+            for clk, k, nm in ev:
+                print(f"  {clk:8d}  tile+{k}  {'MMA ' if nm.startswith('G') else 'EPI '} {nm}")
         t = lead[:, 6].mean()
         print(f"  per tile: mma_total {lead[:, 5].mean() / t:.0f} clk = ideal MMA 14336 (12288 for the last layer) + wait_full {lead[:, 2].mean() / t:.0f}"
               f" + wait_accempty {lead[:, 3].mean() / t:.0f} + wait_outready {lead[:, 4].mean() / t:.0f} + issue/other")

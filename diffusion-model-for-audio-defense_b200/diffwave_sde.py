@@ -87,7 +87,7 @@ class RevDiffWave(torch.nn.Module):
     (with ``use_bm=False`` torchsde builds the same kind of interval itself, so the increments have the same law)."""
 
     def __init__(self, args, device=None, state_dict=None, noise: str = "philox", seed: int | None = None, mode=None,
-                 grad_through_eps: bool = False):
+                 grad_through_eps: bool = False, diffwave: DiffWave | None = None):
         super().__init__()
         self.args = args
         if getattr(args, "use_bm", False):
@@ -99,9 +99,13 @@ class RevDiffWave(torch.nn.Module):
         self.device = torch.device(device)
         self.grad_through_eps = bool(grad_through_eps)
         audio_shape = (1, 16000)
-        model = create_diffwave_model(model_path=getattr(args, "ddpm_path", None), config_path=args.ddpm_config,
-                                      reverse_timestep=args.t, state_dict=state_dict, noise=noise, seed=seed, mode=mode,
-                                      device=self.device)
+        if diffwave is not None:      # share an existing DiffWave (one network handle / workspace for several purifiers)
+            model, noise = diffwave, diffwave.noise
+            model.reverse_timestep = args.t
+        else:
+            model = create_diffwave_model(model_path=getattr(args, "ddpm_path", None), config_path=args.ddpm_config,
+                                          reverse_timestep=args.t, state_dict=state_dict, noise=noise, seed=seed, mode=mode,
+                                          device=self.device)
         self.T = 200
         self.model = model
         self.rev_vpsde = RevVPSDE(model=model, score_type=args.score_type, beta_min=0.0001 * self.T,

@@ -129,6 +129,43 @@ def wavenet_forward(sd: dict, audio, steps, num_res_layers: int = 36, dilation_c
     return eps
 
 
+def wavenet_forward_bf16_dataflow(sd: dict, audio, steps, num_res_layers: int = 36, dilation_cycle: int = 12,
+                                  embed_dim_in: int = 128):
+    """``wavenet_forward`` with the ROUNDING POINTS of the product's bf16 tensor-core mode made explicit (fp32 accumulation
+    everywhere): the residual stream u is stored as bf16 after every block, every GEMM operand is bf16 -- u and the folded
+    weights of the dilated convolution, the gate output o (A operand of the res 1x1 and of the deferred skip GEMM) with the
+    res / skip weights, the scaled skip sum s with the head's 1x1 weights.  Not a reference function: it is the error budget
+    of bf16 OPERANDS for this network (DESIGN.md section 3 'Numerics'), used to tell rounding that is inherent to the mode
+    from kernel defects -- the CUDA path must agree with THIS function far more closely than either agrees with fp32."""
+    q = lambda x: x.to(torch.bfloat16).to(torch.float32)
+    w = lambda k: _t(sd[k], torch.float32)
+    wn = lambda p: fold_weight_norm(sd[p + ".weight_g"], sd[p + ".weight_v"], torch.float32)
+    x = _t(audio, torch.float32)
+    steps = _t(steps, torch.float32)
+    h = F.conv1d(x, wn("init_conv.0.conv"), w("init_conv.0.conv.bias"))
+    h = torch.maximum(h, torch.zeros_like(h))
+    emb = step_embedding(steps, embed_dim_in)
+    emb = _swish(F.linear(emb, w("residual_layer.fc_t1.weight"), w("residual_layer.fc_t1.bias")))
+    emb = _swish(F.linear(emb, w("residual_layer.fc_t2.weight"), w("residual_layer.fc_t2.bias")))
+    C = h.shape[1]
+    part = lambda n: F.linear(emb, w(f"residual_layer.residual_blocks.{n}.fc_t.weight"),
+                              w(f"residual_layer.residual_blocks.{n}.fc_t.bias")).reshape(-1, C, 1)
+    u = q(h + part(0))
+    skip_total = torch.zeros_like(h)
+    for n in range(num_res_layers):
+        p = f"residual_layer.residual_blocks.{n}"
+        d = 2 ** (n % dilation_cycle)
+        a = F.conv1d(u, q(wn(p + ".dilated_conv_layer.conv")), w(p + ".dilated_conv_layer.conv.bias"), dilation=d, padding=d)
+        o = q(torch.tanh(a[:, :C]) * torch.sigmoid(a[:, C:]))
+        res = F.conv1d(o, q(wn(p + ".res_conv")), w(p + ".res_conv.bias"))
+        skip_total = skip_total + F.conv1d(o, q(wn(p + ".skip_conv")), w(p + ".skip_conv.bias"))
+        if n + 1 < num_res_layers:
+            u = q((u + res) * math.sqrt(0.5) + part(n + 1))
+    s = q(skip_total * math.sqrt(1.0 / num_res_layers))
+    y = F.relu(F.conv1d(s, q(wn("final_conv.0.conv")), w("final_conv.0.conv.bias")))
+    return F.conv1d(y, w("final_conv.2.conv.weight"), w("final_conv.2.conv.bias"))
+
+
 # --------------------------------------------------------------------------------------
 # a7-a10  DiffWave DDPM purifier                     diffusion_models/diffwave_ddpm.py
 # --------------------------------------------------------------------------------------

@@ -81,16 +81,32 @@ template <int CG_, int KIND, int DT_ = 0> struct Geo {
   // bf16x3: k2_head stages both planes of the skip sum (128 KB, 3-stage ring); k1_split issues GEMM-2 in two K halves through
   // one 64 KB tile and keeps the 5-stage ring
   static constexpr bool WIDE_STAGING = SPLIT && KIND == 2;
-  static constexpr int NSTAGE = CG == 1 ? (SPLIT ? 2 : 3) : (WIDE_STAGING ? 3 : 5);
+  // k1_layer in pair mode moves the residual stream through shared memory with TMA (u sub-tiles in, u' sub-tiles out: two
+  // 16 KB buffers) instead of 32-byte-per-thread global accesses; that costs one ring stage (4 instead of 5).
+#ifdef AP_RES_DIRECT
+  static constexpr bool RES_STAGED = false;
+#else
+  static constexpr bool RES_STAGED = KIND == 1 && !SPLIT && CG == 2;
+#endif
+#ifdef AP_K1_NSTAGE   // development aid: ring depth experiments
+  static constexpr int NSTAGE = CG == 1 ? (SPLIT ? 2 : 3) : (WIDE_STAGING ? 3 : (RES_STAGED ? AP_K1_NSTAGE : 5));
+#else
+  static constexpr int NSTAGE = CG == 1 ? (SPLIT ? 2 : 3) : (WIDE_STAGING ? 3 : (RES_STAGED ? 4 : 5));
+#endif
   static constexpr int OUT_OFF = NSTAGE * STAGE_BYTES;
-  static constexpr int BIAS_OFF = OUT_OFF + (WIDE_STAGING || (SPLIT && CG == 1) ? 2 : 1) * OUT_BYTES;
+  static constexpr int RES_OFF = OUT_OFF + (WIDE_STAGING || (SPLIT && CG == 1) ? 2 : 1) * OUT_BYTES;
+  static constexpr int BIAS_OFF = RES_OFF + (RES_STAGED ? 2 * A_BYTES : 0);
   static constexpr int BAR_OFF = BIAS_OFF + 1024;   // k1: c2[256]; k2: 128 partial dots
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + slack to align the base to 1024 B
   static constexpr uint32_t IDESC = DT_ == 1 ? umma_idesc_f16_f32(128 * CG, 256) : umma_idesc_bf16_f32(128 * CG, 256);
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
   static_assert(NSTAGE <= 5, "barrier table holds at most 5 stages");
 };
-enum { BAR_FULL = 0, BAR_EMPTY = 5, BAR_ACC_FULL = 10, BAR_ACC_EMPTY = 12, BAR_OUT_READY = 14, BAR_G2A_DONE = 16, BAR_COUNT = 17 };
+enum { BAR_FULL = 0, BAR_EMPTY = 5, BAR_ACC_FULL = 10, BAR_ACC_EMPTY = 12, BAR_OUT_READY = 14, BAR_G2A_DONE = 16,
+       BAR_RES_FULL = 17,   // [2] u sub-tile landed in residual buffer i (loader warp's TMA)
+       BAR_RES_DONE = 19,   // [2] the 8 epilogue warps have overwritten buffer i with u' (-> storer warp)
+       BAR_RES_FREE = 21,   // [2] the TMA store of buffer i has read it (-> loader warp)
+       BAR_COUNT = 23 };
 
 // position in the TMA ring: stage index and phase parity (no division in the producer / MMA-issue loops)
 template <int NSTAGE> struct RingPos {
@@ -168,6 +184,11 @@ template <class G> __device__ __forceinline__ uint32_t tc_prologue(Ctx<G>& cx, u
     }
     for (int i = 0; i < 2; ++i) mbar_init(cx.bar(BAR_OUT_READY + i), out_ready_count * CG);
     mbar_init(cx.bar(BAR_G2A_DONE), 1);   // k1_split: first half of GEMM-2 done
+    for (int i = 0; i < 2; ++i) {          // k1_layer's staged residual (per CTA, not per pair)
+      mbar_init(cx.bar(BAR_RES_FULL + i), 1);
+      mbar_init(cx.bar(BAR_RES_DONE + i), 8);
+      mbar_init(cx.bar(BAR_RES_FREE + i), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -280,6 +301,10 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
         for (int e = 0; e < 4; ++e) {
           const int c0 = i * 8 + 2 * e;
           const int cb = J * 256 + HSEL * 64 + gq * 32 + c0;
+#ifdef AP_PROBE_NO_EPI   // roofline probe (wrong results): the epilogue keeps its protocol but does no arithmetic
+          pk[gq][i][e] = ta[gq][c0] ^ sg[gq][c0 + 1];
+          continue;
+#endif
           if constexpr (!SAVE && kGatePoly) {
             // exponentials on the FMA pipe, one MUFU.RCP per channel (gate_poly2; p.bd holds 2 log2e b_t | -log2e b_s here)
             const float2 bt = reinterpret_cast<const float2*>(p.bd)[cb >> 1], bs = reinterpret_cast<const float2*>(p.bd)[(cb + 128) >> 1];
@@ -325,6 +350,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
       w_bulk += clock64() - t0;
     }
     named_bar_sync(1, EPI_THREADS);
+    if (etid == 0) trace(p, ti, 12 + J * 8);
     const uint32_t kb_base = cx.out_kb(2 * J + HSEL) + row_off;
 #pragma unroll
     for (int gq = 0; gq < 2; ++gq)
@@ -335,10 +361,12 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     fence_proxy_async_smem();
     named_bar_sync(1, EPI_THREADS);
     if (etid == 0) {
+      trace(p, ti, 13 + J * 8);
       if (valid) {
         tma_store_3d(tmO, cx.out_kb(2 * J), (2 * J) * 64, l0, p.layer * p.chunk_alloc + b);
         tma_store_3d(tmO, cx.out_kb(2 * J + 1), (2 * J + 1) * 64, l0, p.layer * p.chunk_alloc + b);
       }
+      trace(p, ti, 14 + J * 8);
       bulk_commit();                                       // always a group (possibly empty): wait_group counts stay uniform
       cx.arrive_leader(BAR_OUT_READY + J);
       trace(p, ti, 11 + J * 8);
@@ -348,7 +376,87 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
 
   // ---- residual epilogue: u' = (u + r) * sqrt(.5) + (b_res * sqrt(.5) + p_next) -> bf16, global -> registers -> global
   uint32_t cur_ti = 0;
+  uint32_t rcount = 0;   // residual sub-tiles consumed so far: buffer rcount & 1, barrier phase (rcount >> 1) & 1
+  // ---- residual epilogue, staged (pair mode): u arrives in 16 KB sub-tiles [128 rows][64 ch] through TMA (loader warp), each
+  //      thread rewrites its row's 32 channels in place, the storer warp sends the sub-tile to u_out with a TMA store.  No global
+  //      accesses from the epilogue warps: the direct version's 32-byte-per-thread LDG / STG touched 32 cache lines per
+  //      instruction (4096 LSU wavefronts per tile) and held up every other memory instruction of the SM, TMA issue included.
+  auto residual_staged = [&]() {
+    const uint32_t r = g & 1;
+    if (etid == 0) trace(p, cur_ti, 24);
+    w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 10);
+    tc_fence_after();
+    if (etid == 0) trace(p, cur_ti, 25);
+    // all 128 accumulators of this thread's row into registers first: the TMEM region is free for the next MMA job at once,
+    // however long the sub-tile round trips (store -> buffer free -> load) of passes 2 and 3 take
+    uint32_t accs[4][32];
+#ifndef AP_RES_LATE_RELEASE
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) tmem_ld_32x32b_x32(lane_addr + r * 256 + pass * 64 + HSEL * 32, accs[pass]);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
+    if (etid == 0) trace(p, cur_ti, 26);
+#endif
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass, ++rcount) {
+      const uint32_t buf = rcount & 1;
+      const uint32_t (&acc)[32] = accs[pass];
+#ifdef AP_RES_LATE_RELEASE   // development aid: TMEM read pass by pass, released after the last pass (A/B in profiles/r02_ab_k1_variants.txt)
+      tmem_ld_32x32b_x32(lane_addr + r * 256 + pass * 64 + HSEL * 32, accs[pass]);
+      tmem_ld_wait();
+      if (pass == 3) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
+      }
+#endif
+      mbar_wait(cx.bar(BAR_RES_FULL + buf), (rcount >> 1) & 1, 13);
+      const uint32_t rb = cx.base + G::RES_OFF + buf * A_BYTES + row_off;
+#ifdef AP_PROBE_NO_EPI
+      if (acc[0] == 0x7fc12345u) st_shared_v4(rb, make_uint4(acc[1], acc[2], acc[3], acc[4]));
+      if (true) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cx.bar(BAR_RES_DONE + buf));
+        continue;
+      }
+#endif
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {                          // 8 channels = one 16-byte chunk of the swizzled row
+        const uint32_t addr = rb + (((HSEL * 4 + c) ^ sw) << 4);
+        const uint4 uv = ld_shared_v4(addr);
+        const uint32_t uw[4] = {uv.x, uv.y, uv.z, uv.w};
+        const int ch = pass * 64 + HSEL * 32 + c * 8;
+        uint32_t pk[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint4 cv = ld_shared_v4(c2_addr + (ch + h * 4) * 4);   // warp-uniform address: broadcast
+          const float cc[4] = {__uint_as_float(cv.x), __uint_as_float(cv.y), __uint_as_float(cv.z), __uint_as_float(cv.w)};
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const uint32_t w2 = uw[h * 2 + e];
+            const int a0 = c * 8 + h * 4 + e * 2;
+            const float v0 = fmaf(unpack_lo<DT>(w2) + __uint_as_float(acc[a0]), sqrt_half, cc[e * 2]);
+            const float v1 = fmaf(unpack_hi<DT>(w2) + __uint_as_float(acc[a0 + 1]), sqrt_half, cc[e * 2 + 1]);
+            pk[h * 2 + e] = pack2<DT>(v0, v1);
+          }
+        }
+        st_shared_v4(addr, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(cx.bar(BAR_RES_DONE + buf));
+    }
+    if (etid == 0) trace(p, cur_ti, 27);
+    ++g;
+  };
   auto residual = [&](bool valid, int b, int l0) {
+    if constexpr (G::RES_STAGED) {
+      residual_staged();
+      return;
+    }
     const uint32_t r = g & 1;
     const bool live = valid && l0 + row < p.L;
     if (etid == 0) trace(p, cur_ti, 24);
@@ -358,6 +466,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
 #pragma unroll
       for (int v = 0; v < 8; ++v) ld_global_v8(p.u_in + goff + v * 16, uu[v]);
     }
+    if (etid == 0) trace(p, cur_ti, 31);
     w_accfull += mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 10);
     tc_fence_after();
     if (etid == 0) trace(p, cur_ti, 25);
@@ -419,7 +528,7 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
 
 template <int CG, int DT, bool SAVE = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k1_layer(const __grid_constant__ CUtensorMap tmUin,
+k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUtensorMap tmUout,
          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWd,
          const __grid_constant__ CUtensorMap tmWr, const __grid_constant__ K1Params p) {
   using G = Geo<CG, 1, DT>;
@@ -432,7 +541,7 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
     for (int i = threadIdx.x; i < C; i += NTHREADS) s_c2[i] = fmaf(p.b_res[i], 0.70710678118654752440f, p.p_next[i]);
   }
   if (threadIdx.x == 0)
-    prefetch_tmap(&tmUin), prefetch_tmap(&tmO), prefetch_tmap(&tmWd), prefetch_tmap(&tmWr);
+    prefetch_tmap(&tmUin), prefetch_tmap(&tmUout), prefetch_tmap(&tmO), prefetch_tmap(&tmWd), prefetch_tmap(&tmWr);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -455,9 +564,13 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
               const uint32_t s = it.s, ph = it.ph;
               w_empty += cx.wait_empty(s, ph, 1);
               if (elect_one()) {
+#ifdef AP_PROBE_NO_TMA   // roofline probe (wrong results): no operand traffic, the MMAs run on whatever the ring holds
+                if (cx.rank == 0) mbar_arrive(cx.bar(BAR_FULL + s)); else mbar_arrive_cluster(cx.lbar(BAR_FULL + s));
+#else
                 cx.arm(s, G::STAGE_BYTES);
                 cx.load_a(s, &tmUin, kb * 64, valid ? l0 + (tap - 1) * p.dilation : oob_l0, b + (cmb == 1 ? p.u_plane : 0));
                 cx.load_b(s, &tmWd, tap * C + kb * 64, (p.layer * 2 + j) * 256 + (cmb == 2 ? p.wd_plane : 0));
+#endif
               }
               __syncwarp();
             }
@@ -468,8 +581,12 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
             const uint32_t s = it.s, ph = it.ph;
             w_empty += cx.wait_empty(s, ph, 2);
             if (elect_one()) {
+#ifdef AP_PROBE_NO_TMA
+              if (cx.rank == 0) mbar_arrive(cx.bar(BAR_FULL + s)); else mbar_arrive_cluster(cx.lbar(BAR_FULL + s));
+#else
               cx.arm(s, G::B_BYTES);
               cx.load_b(s, &tmWr, kb * 64, p.layer * 256 + (cmb == 2 ? p.wr_plane : 0));
+#endif
             }
             __syncwarp();
           }
@@ -554,6 +671,50 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin,
         long long* d = p.dbg + blockIdx.x * 16;
         d[2] = w_full, d[3] = w_acc, d[4] = w_out, d[5] = clock64() - t_start, d[6] = ti;
       }
+    }
+  } else if (warp == 2) {
+    // ======================================================================================= residual loader (staged residual)
+    // one 16 KB sub-tile [128 rows][64 channels] of this CTA's u tile per pass, into residual buffer (count & 1) once the storer
+    // has released it; runs ahead of the epilogue by up to two sub-tiles
+    if (G::RES_STAGED && !p.last) {
+      uint32_t rcount = 0;
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride) {
+        const bool valid = tile < p.n_tiles;
+        const int b = valid ? tile / p.tiles_per_sample : 0;
+        const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+        for (int pass = 0; pass < 4; ++pass, ++rcount) {
+          const uint32_t buf = rcount & 1;
+          mbar_wait(cx.bar(BAR_RES_FREE + buf), ((rcount >> 1) & 1) ^ 1, 14);
+          if (elect_one()) {
+            mbar_expect_tx(cx.bar(BAR_RES_FULL + buf), A_BYTES);
+            tma_load_3d(cx.base + G::RES_OFF + buf * A_BYTES, &tmUin, cx.bar(BAR_RES_FULL + buf), pass * 64, l0, b);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ======================================================================================= residual storer (staged residual)
+    if (G::RES_STAGED && !p.last) {
+      uint32_t rcount = 0;
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride) {
+        const bool valid = tile < p.n_tiles;
+        const int b = valid ? tile / p.tiles_per_sample : 0;
+        const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+        for (int pass = 0; pass < 4; ++pass, ++rcount) {
+          const uint32_t buf = rcount & 1;
+          mbar_wait(cx.bar(BAR_RES_DONE + buf), (rcount >> 1) & 1, 15);
+          if (elect_one()) {
+            if (valid) tma_store_3d(&tmUout, cx.base + G::RES_OFF + buf * A_BYTES, pass * 64, l0, b);   // rows >= L are clipped
+            bulk_commit();
+            bulk_wait_read<0>();                       // the store has read the buffer: the loader may refill it
+            mbar_arrive(cx.bar(BAR_RES_FREE + buf));
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) bulk_wait_all<0>();             // global writes of the last stores are complete before the CTA exits
+      __syncwarp();
     }
   } else if (warp >= EPI_WARP0) {
     // ======================================================================================= epilogue (8 warps)
@@ -1838,20 +1999,21 @@ static int tc_run_layers(TcNet* n, const float* x, const float* ptab, int B, int
     cudaEvent_t e0 = prof_event(n, 0), e1 = e0 ? prof_event(n, 0) : nullptr;
     if (e1) cudaEventRecord(e0, st);
     const CUtensorMap& ui = n->tmU[l & 1];
+    const CUtensorMap& uo = n->tmU[(l + 1) & 1];
     if (save && n->dt == 2)
       AP_CUDA(launch_pair(k1_split<true>, pair_grid(n_tiles), Geo<2, 1, 2>::SMEM_BYTES, st, ui, n->tmWd_s, n->tmWr_s, p));
     else if (save)
-      AP_CUDA(launch_pair(k1_layer<2, 0, true>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2, n->tmWr2, p));
+      AP_CUDA(launch_pair(k1_layer<2, 0, true>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, uo, n->tmO, n->tmWd2, n->tmWr2, p));
     else if (n->dt == 2)
       AP_CUDA(launch_pair(k1_split<false>, pair_grid(n_tiles), Geo<2, 1, 2>::SMEM_BYTES, st, ui, n->tmWd_s, n->tmWr_s, p));
     else if (n->pair && n->dt == 0)
-      AP_CUDA(launch_pair(k1_layer<2, 0>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2, n->tmWr2, p));
+      AP_CUDA(launch_pair(k1_layer<2, 0>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, uo, n->tmO, n->tmWd2, n->tmWr2, p));
     else if (n->pair)
-      AP_CUDA(launch_pair(k1_layer<2, 1>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, n->tmO, n->tmWd2_h, n->tmWr2_h, p));
+      AP_CUDA(launch_pair(k1_layer<2, 1>, pair_grid(n_tiles), Geo<2, 1>::SMEM_BYTES, st, ui, uo, n->tmO, n->tmWd2_h, n->tmWr2_h, p));
     else if (n->dt == 0)
-      k1_layer<1, 0><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(ui, n->tmO, n->tmWd, n->tmWr, p);
+      k1_layer<1, 0><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(ui, uo, n->tmO, n->tmWd, n->tmWr, p);
     else
-      k1_layer<1, 1><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(ui, n->tmO, n->tmWd_h, n->tmWr_h, p);
+      k1_layer<1, 1><<<grid, NTHREADS, Geo<1, 1>::SMEM_BYTES, st>>>(ui, uo, n->tmO, n->tmWd_h, n->tmWr_h, p);
     if (e1) cudaEventRecord(e1, st);
     AP_LAUNCH_CHECK();
   }

@@ -45,7 +45,8 @@ def main():
         _lib.check(lib.ap_diffwave_debug_counters(net._handle, buf.ctypes.data))
         names = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_accempty", "mma_wait_outready", "mma_total",
                  "tiles", "epi_wait_accfull", "epi_wait_g2", "epi_total", "epi_wait_bulk"]
-        act = buf[buf[:, 1] > 0]
+        cnt = buf[:200]
+        act = cnt[cnt[:, 1] > 0]
         lead = act[act[:, 5] > 0]
         print(f"active CTAs {len(act)}, MMA-issuing CTAs {len(lead)} (last k1 launch; cycles, mean over CTAs)")
         for i, nm in enumerate(names):
@@ -56,7 +57,8 @@ def main():
             names_t = {0: "G1c0 wait acc_empty", 1: "G1c0 issue start", 2: "G1c0 issued", 28: "G2 wait acc_empty", 29: "G2 issue start(after out_ready)",
                        30: "G2 issued", 4: "G1c1 wait acc_empty", 5: "G1c1 issue start", 6: "G1c1 issued", 8: "gate0 acc_full", 9: "gate0 tmem loaded",
                        10: "gate0 math done", 11: "gate0 staged", 24: "res begin(u loads issued)", 25: "res acc_full", 26: "res tmem loaded",
-                       27: "res done", 16: "gate1 acc_full", 17: "gate1 tmem loaded", 18: "gate1 math done", 19: "gate1 staged"}
+                       27: "res done", 31: "res u loads issued", 12: "gate0 barrier1 passed", 13: "gate0 barrier2 passed", 14: "gate0 tma stores issued",
+                       20: "gate1 barrier1 passed", 21: "gate1 barrier2 passed", 22: "gate1 tma stores issued", 16: "gate1 acc_full", 17: "gate1 tmem loaded", 18: "gate1 math done", 19: "gate1 staged"}
             t0 = tr[0][tr[0] > 0].min()
             ev = sorted((int(tr[k, s] - t0), k, names_t[s]) for k in range(3) for s in names_t if tr[k, s] > 0)
             print("timeline of CTA 0 (clk since the first event; tile index relative to tile 60):")

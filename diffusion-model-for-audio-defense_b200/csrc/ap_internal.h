@@ -62,6 +62,16 @@ int tc_net_eps_save(TcNet* n, const float* x, const float* ptab, float* eps, int
 bool tc_net_saved_state_is(const TcNet* n, unsigned long long token, int B, int L);
 int tc_net_backward(TcNet* n, const float* x, const float* g_eps, float* g_x, int B, int L, cudaStream_t st);
 
+// K4 on the tensor cores (ap_wavenet_tc.cu): windowed DFT as a tcgen05 GEMM (bf16 hi/lo split operands) with power -> mel ->
+// dB fused into the epilogue.  Eligible: zero padding, 32 mels, hop % 64 == 0, n_fft a multiple (<= 8) of hop, n_fft/2 % 128 == 0,
+// 32 frames per waveform (the SC09 front end: 2048 / 512 on 1 s clips).
+struct MelTc;
+bool mel_tc_eligible(const ap_mel_cfg& cfg, int L);
+int mel_tc_create(MelTc** out, const ap_mel_cfg& cfg);
+void mel_tc_destroy(MelTc* m);
+// wav: device (B, L); fb: device [n_freq][32]; spec: device (B, 32, 32)
+int mel_tc_forward(MelTc* m, const float* wav, const float* fb, float* spec, int B, int L, cudaStream_t st);
+
 // per-launch CUDA-event timing of k1_layer ([0]) and k2_head ([1]); read synchronises on the recorded events
 void tc_net_profile(TcNet* n, bool on);
 int tc_net_debug_counters(TcNet* n, long long* host16x256);

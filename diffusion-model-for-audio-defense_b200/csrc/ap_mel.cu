@@ -164,6 +164,10 @@ struct ap_mel_s {
   DevBuf basis_t, reim;
   int ld_t = 0;
   long long reim_rows = 0;
+  ap::MelTc* tc = nullptr;      // tensor-core forward (created on first eligible call)
+  ~ap_mel_s() {
+    if (tc) ap::mel_tc_destroy(tc);
+  }
 };
 
 static double hz_to_mel(double f, bool slaney) {
@@ -248,6 +252,13 @@ extern "C" int ap_mel_db(ap_mel_t h, const float* wav, float* spec, int B, int L
   const int frames = 1 + L / h->cfg.hop_length;
   const long long rows = static_cast<long long>(B) * frames;
   AP_REQUIRE(rows < (1ll << 30), "ap_mel_db: batch too large");
+  if (mel_tc_eligible(h->cfg, L)) {     // tcgen05 DFT GEMM with the power / filterbank / dB tail fused into its epilogue
+    if (!h->tc) {
+      int rc = mel_tc_create(&h->tc, h->cfg);
+      if (rc != AP_OK) return rc;
+    }
+    return mel_tc_forward(h->tc, wav, h->fb.as<float>(), spec, B, L, st);
+  }
   if (rows > h->power_rows) {
     h->power_rows = 0;   // alloc() releases the old buffer first
     AP_CUDA(h->power.alloc(static_cast<size_t>(rows) * h->ld_power * sizeof(float)));

@@ -1541,6 +1541,198 @@ __global__ void h16_to_f32_kernel(const uint16_t* __restrict__ in, float* __rest
     out[i] = unpack_lo<DT>(in[i]);
 }
 
+
+// ------------------------------------------------------------------------------------------------ K4: log-mel on the tensor cores
+// The windowed-DFT contraction of the log-mel front end (torchaudio MelSpectrogram + AmplitudeToDB, built at
+// certified_robustness_eval.py:85-87) as a tcgen05 GEMM with fp32-class accuracy and the whole tail fused into its epilogue:
+//     frames[(b, f)][n] . basis[n][cos k | -sin k]  ->  power = re^2 + im^2  ->  mel filterbank  ->  10 log10(max(., 1e-10))
+// so that the power spectrum never reaches HBM (the FFMA version wrote and re-read 262 KB per waveform).
+//  * A operand without im2col: with hop H and n_fft = Q H, frame f is the concatenation of Q consecutive H-sample blocks of the
+//    zero-padded waveform, frame[f][q H + r] = Xp[f + q][r].  One 3-D TMA box (64 r, 32 frames, 4 waveforms) of Xp at block
+//    offset q is therefore the [128 rows][64 k] A tile of K-block (q, r0) -- the same trick as the dilated taps of k1_layer.
+//  * fp32-class accuracy on bf16 tensor cores: Xp and the basis are kept as bf16 hi / lo planes and every product is
+//    accumulated as hi*hi + lo*hi + hi*lo (three MMAs per K step, as in AP_MODE_BF16X3): 2e-3 dB needs more than tf32's 10 bits.
+//  * N tile t = [cos bins 128 t .. +127 | -sin bins 128 t .. +127]; the sine row of bin 0 is identically zero, so it carries
+//    the Nyquist bin (n_fft / 2) instead: n_freq - 1 = 1024 bins = 8 tiles with nothing padded.
+//  * CTA pairs (cta_group::2, M = 256 = 8 waveforms x 32 frames); a pair walks the N tiles of its rows while every epilogue
+//    thread keeps the 32 mel sums of its row in registers: thread = row (TMEM lane), two column halves on the two warp groups.
+struct MelGeo {
+  static constexpr int CG = 2, DT = 0;
+  static constexpr int B_ROWS = 128, B_BYTES = B_ROWS * 128, STAGE_BYTES = A_BYTES + B_BYTES, NSTAGE = 5;
+  static constexpr int OUT_OFF = NSTAGE * STAGE_BYTES;     // filterbank rows of the current N tile: [129][32] fp32 (row 128: Nyquist)
+  static constexpr int RED_OFF = OUT_OFF + 129 * 32 * 4 + 128;   // mel sums of the upper column half: [128 rows][33] fp32
+  static constexpr int BIAS_OFF = RED_OFF + 128 * 33 * 4;
+  static constexpr int BAR_OFF = (BIAS_OFF + 255) / 256 * 256;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+  static constexpr uint32_t IDESC = umma_idesc_bf16_f32(256, 256);
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+};
+struct MelParams {
+  int n_tiles;        // CTA tiles of 128 rows = 4 waveforms x 32 frames
+  int B;              // waveforms with an output
+  int x_plane;        // offset of the lo plane in the third coordinate of the Xp tensor map (= padded batch)
+  int basis_plane;    // offset of the lo plane in the rows of the basis tensor map (= NT * 256)
+  int NT, KB, hop64;  // N tiles (n_freq - 1) / 128, K blocks n_fft / 64, K blocks per hop
+  const float* fb;    // [n_freq][32]
+  float* spec;        // [B][32 mels][32 frames]
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_mel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ MelParams p) {
+  using G = MelGeo;
+  Ctx<G> cx;
+  uint8_t* gen;
+  const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
+  if (threadIdx.x == 0) prefetch_tmap(&tmX), prefetch_tmap(&tmB);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Tiles<2> tiles(p.n_tiles, cx.rank);
+  const int stages_per_ntile = p.KB * 3;
+
+  if (warp == 0) {
+    // ======================================================================================= TMA producer
+    RingPos<G::NSTAGE> it;
+    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride) {
+      const int b0 = tile < p.n_tiles ? tile * 4 : 2 * p.x_plane;     // past the end: the whole box is zero-filled
+      for (int nt = 0; nt < p.NT; ++nt)
+        for (int kb = 0; kb < p.KB; ++kb)
+          for (int cmb = 0; cmb < 3; ++cmb, ++it) {    // (hi, hi), (lo, hi), (hi, lo)
+            const uint32_t s = it.s, ph = it.ph;
+            cx.wait_empty(s, ph, 90);
+            if (elect_one()) {
+              cx.arm(s, G::STAGE_BYTES);
+              cx.load_a(s, &tmX, (kb % p.hop64) * 64, kb / p.hop64, b0 + (cmb == 1 && tile < p.n_tiles ? p.x_plane : 0));
+              cx.load_b(s, &tmB, kb * 64, nt * 256 + (cmb == 2 ? p.basis_plane : 0));
+            }
+            __syncwarp();
+          }
+    }
+  } else if (warp == 1) {
+    // ======================================================================================= MMA issuer (leader CTA)
+    if (cx.rank == 0) {
+      RingPos<G::NSTAGE> it;
+      uint32_t g = 0;
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride)
+        for (int nt = 0; nt < p.NT; ++nt, ++g) {
+          const uint32_t r = g & 1;
+          mbar_wait(cx.bar(BAR_ACC_EMPTY + r), ((g >> 1) & 1) ^ 1, 91);
+          tc_fence_after();
+          for (int k = 0; k < stages_per_ntile; ++k, ++it) {
+            const uint32_t s = it.s, ph = it.ph;
+            mbar_wait(cx.bar(BAR_FULL + s), ph, 92);
+            tc_fence_after();
+            if (elect_one()) {
+              cx.mma_kblock(tmem + r * 256, cx.stage_a(s), cx.stage_b(s), k == 0);
+              cx.commit(BAR_EMPTY + s);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) cx.commit(BAR_ACC_FULL + r);
+          __syncwarp();
+        }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ======================================================================================= epilogue (8 warps)
+    const int hsel = (warp - EPI_WARP0) >> 2, q4 = warp & 3, etid = threadIdx.x - EPI_WARP0 * 32;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+    const uint32_t fb_addr = cx.base + G::OUT_OFF;
+    float* fb_s = reinterpret_cast<float*>(gen + G::OUT_OFF);
+    float* red = reinterpret_cast<float*>(gen + G::RED_OFF);
+    uint32_t g = 0;
+    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride) {
+      float mel[32];
+#pragma unroll
+      for (int m = 0; m < 32; ++m) mel[m] = 0.f;
+      for (int nt = 0; nt < p.NT; ++nt, ++g) {
+        const uint32_t r = g & 1;
+        named_bar_sync(1, EPI_THREADS);                    // the previous N tile's filterbank rows are no longer read
+        {
+          const float4* src = reinterpret_cast<const float4*>(p.fb + static_cast<size_t>(nt) * 128 * 32);
+          float4* dst = reinterpret_cast<float4*>(fb_s);
+          for (int i = etid; i < 128 * 8; i += EPI_THREADS) dst[i] = src[i];
+          if (nt == 0 && etid < 8)                          // the Nyquist bin's row (tile 0 carries it in the sine slot of bin 0)
+            dst[128 * 8 + etid] = reinterpret_cast<const float4*>(p.fb + static_cast<size_t>(p.NT) * 128 * 32)[etid];
+        }
+        named_bar_sync(1, EPI_THREADS);
+        mbar_wait(cx.bar(BAR_ACC_FULL + r), (g >> 1) & 1, 93);
+        tc_fence_after();
+#pragma unroll
+        for (int grp = 0; grp < 2; ++grp) {
+          uint32_t re[32], im[32];
+          tmem_ld_32x32b_x32(lane_addr + r * 256 + hsel * 64 + grp * 32, re);
+          tmem_ld_32x32b_x32(lane_addr + r * 256 + 128 + hsel * 64 + grp * 32, im);
+          tmem_ld_wait();
+          if (grp == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + r);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float c = __uint_as_float(re[j]), s = __uint_as_float(im[j]);
+            const int bin = hsel * 64 + grp * 32 + j;
+            const bool nyq = (nt == 0) & (bin == 0);
+            const float pw = nyq ? c * c : fmaf(c, c, s * s);
+            const uint32_t fr = fb_addr + bin * 128;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const uint4 w = ld_shared_v4(fr + v * 16);    // warp-uniform address: broadcast
+              mel[4 * v + 0] = fmaf(pw, __uint_as_float(w.x), mel[4 * v + 0]);
+              mel[4 * v + 1] = fmaf(pw, __uint_as_float(w.y), mel[4 * v + 1]);
+              mel[4 * v + 2] = fmaf(pw, __uint_as_float(w.z), mel[4 * v + 2]);
+              mel[4 * v + 3] = fmaf(pw, __uint_as_float(w.w), mel[4 * v + 3]);
+            }
+            if (nyq) {
+              const float pn = s * s;
+#pragma unroll
+              for (int m = 0; m < 32; ++m) mel[m] = fmaf(pn, fb_s[128 * 32 + m], mel[m]);
+            }
+          }
+        }
+      }
+      // combine the two column halves, dB, store spec[b][mel][frame] (a warp = the 32 frames of one waveform: coalesced)
+      named_bar_sync(1, EPI_THREADS);
+      if (hsel == 1) {
+#pragma unroll
+        for (int m = 0; m < 32; ++m) red[row * 33 + m] = mel[m];
+      }
+      named_bar_sync(1, EPI_THREADS);
+      if (hsel == 0 && tile < p.n_tiles) {
+        const int b = tile * 4 + q4;
+        if (b < p.B) {
+#pragma unroll
+          for (int m = 0; m < 32; ++m) {
+            const float v = mel[m] + red[row * 33 + m];
+            p.spec[(static_cast<size_t>(b) * 32 + m) * 32 + lane] = 10.0f * log10f(fmaxf(v, 1e-10f));
+          }
+        }
+      }
+    }
+  }
+  tc_epilogue_teardown<2>(tmem);
+}
+
+// zero-padded hop-sized blocks of the waveform as bf16 hi / lo planes: xp[plane][b][blk][r] = split(wav[b][(blk * hop + r) - pad])
+__global__ void __launch_bounds__(256) mel_prep_kernel(const float* __restrict__ wav, uint32_t* __restrict__ xp, long long plane_words,
+                                                        int B, int Bpad, int L, int hop, int nblk, int pad) {
+  const long long per_b = static_cast<long long>(nblk) * hop / 2, total = per_b * Bpad;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per_b);
+    const long long e = (i - b * per_b) * 2 - pad;          // sample index of the first element of the pair
+    float v0 = 0.f, v1 = 0.f;
+    if (b < B) {
+      const float* w = wav + static_cast<long long>(b) * L;
+      if (e >= 0 && e < L) v0 = w[e];
+      if (e + 1 >= 0 && e + 1 < L) v1 = w[e + 1];
+    }
+    const uint32_t hi = pack_bf16x2(v0, v1);
+    xp[i] = hi;
+    xp[plane_words + i] = pack_bf16x2(v0 - bf16_lo(hi), v1 - bf16_hi(hi));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ self test kernel
 // D[128 x 256] = A[128 x K] . B[256 x K]^T through the same TMA / UMMA / TMEM-load primitives (one CTA, one stage).
 __global__ void __launch_bounds__(128, 1)
@@ -2226,6 +2418,102 @@ int tc_net_debug_layer(TcNet* n, const float* x, const float* ptab, int layer, f
   return AP_OK;
 }
 
+
+// ================================================================================================ K4 on the tensor cores (host)
+struct MelTc {
+  int n_fft = 0, hop = 0, n_freq = 0, nblk = 0, NT = 0;
+  DevBuf basis, xp;           // bf16 hi plane followed by the lo plane
+  CUtensorMap tmB{}, tmX{};
+  int bpad = 0, L = 0;        // what xp / tmX are sized for
+  bool attr = false;
+};
+void mel_tc_destroy(MelTc* m) { delete m; }
+
+bool mel_tc_eligible(const ap_mel_cfg& c, int L) {
+  if (std::getenv("AP_MEL_FFMA")) return false;             // development aid: force the FFMA path
+  return !c.reflect_pad && c.n_mels == 32 && c.hop_length % 64 == 0 && c.n_fft % c.hop_length == 0 && c.n_fft / c.hop_length <= 8 &&
+         (c.n_fft / 2) % 128 == 0 && 1 + L / c.hop_length == 32;
+}
+
+// basis_rows(k, n): double-precision windowed DFT rows; the caller passes the window
+int mel_tc_create(MelTc** out, const ap_mel_cfg& c) {
+  using namespace tc;
+  *out = nullptr;
+  auto* m = new MelTc();
+  m->n_fft = c.n_fft, m->hop = c.hop_length, m->n_freq = c.n_fft / 2 + 1, m->NT = (c.n_fft / 2) / 128;
+  const int N = c.n_fft, rows = m->NT * 256;
+  const double PI = 3.14159265358979323846;
+  std::vector<uint16_t> b(static_cast<size_t>(2) * rows * N);
+  for (int t = 0; t < m->NT; ++t)
+    for (int j = 0; j < 256; ++j) {
+      const int k = t * 128 + (j & 127);
+      const bool sine = j >= 128, nyq = sine && k == 0;     // the (all-zero) sine row of bin 0 carries the Nyquist bin
+      uint16_t* hi = b.data() + static_cast<size_t>(t * 256 + j) * N;
+      uint16_t* lo = hi + static_cast<size_t>(rows) * N;
+      for (int n = 0; n < N; ++n) {
+        const double win = 0.5 - 0.5 * std::cos(2.0 * PI * n / N);          // periodic hann (torch.hann_window default)
+        const long long nk = (static_cast<long long>(n) * (nyq ? N / 2 : k)) % N;
+        const double ang = 2.0 * PI * static_cast<double>(nk) / N;
+        const float v = static_cast<float>(nyq ? win * std::cos(ang) : (sine ? -win * std::sin(ang) : win * std::cos(ang)));
+        hi[n] = f32_to_bf16_rne(v);
+        uint32_t hb = static_cast<uint32_t>(hi[n]) << 16;
+        float hf;
+        std::memcpy(&hf, &hb, 4);
+        lo[n] = f32_to_bf16_rne(v - hf);
+      }
+    }
+  cudaError_t e = m->basis.upload(b.data(), b.size() * sizeof(uint16_t));
+  if (e != cudaSuccess) {
+    delete m;
+    return fail(AP_ERR_CUDA, "mel basis upload: %s", cudaGetErrorString(e));
+  }
+  const uint64_t db[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(2 * rows)};
+  const uint32_t bb[2] = {64, 128};
+  int rc = encode_bf16(&m->tmB, m->basis.p, 2, db, bb);
+  if (rc != AP_OK) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return AP_OK;
+}
+
+int mel_tc_forward(MelTc* m, const float* wav, const float* fb, float* spec, int B, int L, cudaStream_t st) {
+  using namespace tc;
+  const int frames = 1 + L / m->hop, Q = m->n_fft / m->hop;
+  if (frames != 32) return fail(AP_ERR_STATE, "mel_tc_forward: 32 frames per waveform only");
+  const int bpad = (B + 7) / 8 * 8, nblk = frames + Q - 1;
+  if (bpad > m->bpad || L != m->L) {
+    m->bpad = 0;
+    const size_t words = static_cast<size_t>(bpad) * nblk * m->hop / 2;
+    AP_CUDA(m->xp.alloc(2 * words * sizeof(uint32_t)));
+    const uint64_t dx[3] = {static_cast<uint64_t>(m->hop), static_cast<uint64_t>(nblk), static_cast<uint64_t>(2 * bpad)};
+    const uint32_t bx[3] = {64, 32, 4};
+    int rc = encode_bf16(&m->tmX, m->xp.p, 3, dx, bx);
+    if (rc != AP_OK) return rc;
+    m->bpad = bpad, m->L = L, m->nblk = nblk;
+  }
+  if (!m->attr) {
+    AP_CUDA(cudaFuncSetAttribute(k_mel, cudaFuncAttributeMaxDynamicSharedMemorySize, MelGeo::SMEM_BYTES));
+    m->attr = true;
+  }
+  // the tensor map spans m->bpad waveforms; the lo plane starts m->bpad entries into its third dimension
+  const long long plane_words = static_cast<long long>(m->bpad) * nblk * m->hop / 2;
+  {
+    long long blocks = ceil_div_ll(plane_words, 256);
+    const long long cap = static_cast<long long>(num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    mel_prep_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(wav, m->xp.as<uint32_t>(), plane_words, B, m->bpad, L, m->hop, nblk,
+                                                                   m->n_fft / 2);
+    AP_LAUNCH_CHECK();
+  }
+  MelParams p;
+  p.n_tiles = (B + 3) / 4, p.B = B, p.x_plane = m->bpad, p.basis_plane = m->NT * 256;
+  p.NT = m->NT, p.KB = m->n_fft / 64, p.hop64 = m->hop / 64, p.fb = fb, p.spec = spec;
+  AP_CUDA(launch_pair(k_mel, pair_grid(p.n_tiles), MelGeo::SMEM_BYTES, st, m->tmX, m->tmB, p));
+  AP_LAUNCH_CHECK();
+  return AP_OK;
+}
 }  // namespace ap
 
 // ================================================================================================ C ABI: self test

@@ -288,3 +288,103 @@ def host_noise(shape, seed: int = 2024, index: int = 0) -> np.ndarray:
     """Host-generated standard-normal tensors handed identically to the oracle and the CUDA path."""
     rng = np.random.Generator(np.random.PCG64([seed, index]))
     return rng.standard_normal(shape).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ spectrogram UNet (Diffusion-Spec)
+DEFAULT_UNET_CONFIG = dict(  # improved_diffusion/script_util.py:12-33,85-127 (model_and_diffusion_defaults + create_model)
+    image_size=32, in_channels=1, model_channels=128, out_channels=1, num_res_blocks=3, attention_resolutions=(2, 4),
+    channel_mult=(1, 2, 2, 2), num_heads=4, num_heads_upsample=4, use_scale_shift_norm=True)
+
+
+def unet_structure(config: dict | None = None):
+    """The module walk of UNetModel.__init__ (improved_diffusion/unet.py:301-443) as a flat list of
+    ``(state-dict prefix, kind, cin, cout)`` with kind in {'conv_in', 'res', 'attn', 'down', 'up', 'out'}; 'res' of the
+    output path has cin = channels of the concatenated input.  Shared by the synthetic weights, the oracle and the
+    host module, so the three agree on names and order by construction."""
+    c = dict(DEFAULT_UNET_CONFIG)
+    if config:
+        c.update(config)
+    mc, nrb, mult, att = c["model_channels"], c["num_res_blocks"], c["channel_mult"], tuple(c["attention_resolutions"])
+    ops = [("input_blocks.0.0", "conv_in", c["in_channels"], mc)]
+    chans, ch, ds, idx = [mc], mc, 1, 1
+    for level, m in enumerate(mult):
+        for _ in range(nrb):
+            ops.append((f"input_blocks.{idx}.0", "res", ch, m * mc))
+            ch = m * mc
+            if ds in att:
+                ops.append((f"input_blocks.{idx}.1", "attn", ch, ch))
+            ops.append((f"input_blocks.{idx}", "push", ch, ch))
+            chans.append(ch)
+            idx += 1
+        if level != len(mult) - 1:
+            ops.append((f"input_blocks.{idx}.0", "down", ch, ch))
+            ops.append((f"input_blocks.{idx}", "push", ch, ch))
+            chans.append(ch)
+            idx += 1
+            ds *= 2
+    ops += [("middle_block.0", "res", ch, ch), ("middle_block.1", "attn", ch, ch), ("middle_block.2", "res", ch, ch)]
+    idx = 0
+    for level, m in list(enumerate(mult))[::-1]:
+        for i in range(nrb + 1):
+            skip = chans.pop()
+            ops.append((f"output_blocks.{idx}", "pop", skip, ch + skip))
+            ops.append((f"output_blocks.{idx}.0", "res", ch + skip, mc * m))
+            ch = mc * m
+            sub = 1
+            if ds in att:
+                ops.append((f"output_blocks.{idx}.{sub}", "attn", ch, ch))
+                sub += 1
+            if level and i == nrb:
+                ops.append((f"output_blocks.{idx}.{sub}", "up", ch, ch))
+                ds //= 2
+            idx += 1
+    ops.append(("out", "out", ch, c["out_channels"]))
+    return ops, c
+
+
+def unet_state_dict(seed: int = 0, config: dict | None = None) -> "OrderedDict[str, np.ndarray]":
+    """Seeded UNetModel state dict with the reference's keys.  The reference zero-initialises the second convolution of every
+    ResBlock, every attention output projection and the final convolution (``zero_module``), which makes eps == 0 for a
+    fresh model; they are re-randomised here (scaled down, as a trained model would have them small but non-zero)."""
+    ops, c = unet_structure(config)
+    mc = c["model_channels"]
+    ted = 4 * mc
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+
+    def conv(prefix, cout, cin, k, gain=1.0):
+        fan_in = cin * k * k
+        sd[prefix + ".weight"] = _normal(seed, prefix + ".weight", (cout, cin, k, k), gain * np.sqrt(1.0 / fan_in))
+        sd[prefix + ".bias"] = _uniform(seed, prefix + ".bias", (cout,), -1, 1) * np.float32(gain / np.sqrt(fan_in))
+
+    def gn(prefix, ch):
+        sd[prefix + ".weight"] = _uniform(seed, prefix + ".weight", (ch,), 0.5, 1.5)
+        sd[prefix + ".bias"] = _normal(seed, prefix + ".bias", (ch,), 0.1)
+
+    _linear(sd, seed, "time_embed.0", ted, mc)
+    _linear(sd, seed, "time_embed.2", ted, ted)
+    for prefix, kind, cin, cout in ops:
+        if kind == "conv_in":
+            conv(prefix, cout, cin, 3)
+        elif kind == "res":
+            gn(prefix + ".in_layers.0", cin)
+            conv(prefix + ".in_layers.2", cout, cin, 3)
+            _linear(sd, seed, prefix + ".emb_layers.1", 2 * cout if c["use_scale_shift_norm"] else cout, ted)
+            gn(prefix + ".out_layers.0", cout)
+            conv(prefix + ".out_layers.3", cout, cout, 3, gain=0.5)
+            if cin != cout:
+                conv(prefix + ".skip_connection", cout, cin, 1)
+        elif kind == "attn":
+            gn(prefix + ".norm", cin)
+            w = _normal(seed, prefix + ".qkv.weight", (3 * cin, cin, 1), np.sqrt(1.0 / cin))
+            sd[prefix + ".qkv.weight"] = w
+            sd[prefix + ".qkv.bias"] = _normal(seed, prefix + ".qkv.bias", (3 * cin,), 0.02)
+            sd[prefix + ".proj_out.weight"] = _normal(seed, prefix + ".proj_out.weight", (cin, cin, 1), 0.5 * np.sqrt(1.0 / cin))
+            sd[prefix + ".proj_out.bias"] = _normal(seed, prefix + ".proj_out.bias", (cin,), 0.02)
+        elif kind == "down":
+            conv(prefix + ".op", cout, cin, 3)
+        elif kind == "up":
+            conv(prefix + ".conv", cout, cin, 3)
+        elif kind == "out":
+            gn("out.0", cin)
+            conv("out.2", cout, cin, 3, gain=0.5)
+    return sd

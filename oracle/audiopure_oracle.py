@@ -677,6 +677,132 @@ def smooth_counts(logits_fn, x, n: int, sigma: float, batch_size: int, noise, nu
     return counts
 
 
+# --------------------------------------------------------------------------------------
+# §8(f)4  spectrogram-domain purifier ("Diffusion-Spec")
+#   UNet:  diffusion_models/Improved_Diffusion_Unconditional/improved_diffusion/unet.py:107-276,301-497, nn.py:12-21,93-121
+#   SDE :  diffusion_models/improved_diffusion_sde.py:47-226
+# --------------------------------------------------------------------------------------
+def unet_timestep_embedding(timesteps, dim: int, max_period: float = 10000.0):
+    """nn.py:103-121."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = timesteps[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def unet_forward(sd: dict, x, timesteps, ops, cfg):
+    """UNetModel.forward (unet.py:462-497) as plain torch ops over a weight dict; ``ops, cfg`` = synthetic.unet_structure()
+    (the module walk of UNetModel.__init__).  x (B, C, H, W), timesteps (B,) -> (B, out_channels, H, W)."""
+    w = lambda k: _t(sd[k], torch.float32)
+    silu = lambda v: v * torch.sigmoid(v)                                   # nn.py:12-14
+    gn = lambda v, p: F.group_norm(v.float(), 32, w(p + ".weight"), w(p + ".bias"), 1e-5)      # GroupNorm32, nn.py:17-19,100
+    heads = cfg["num_heads"]
+    emb = unet_timestep_embedding(_t(timesteps, torch.float32), cfg["model_channels"])
+    emb = F.linear(silu(F.linear(emb, w("time_embed.0.weight"), w("time_embed.0.bias"))), w("time_embed.2.weight"),
+                   w("time_embed.2.bias"))                                  # unet.py:335-339,476
+
+    def res(p, h):                                                          # ResBlock._forward, unet.py:183-197
+        y = F.conv2d(silu(gn(h, p + ".in_layers.0")), w(p + ".in_layers.2.weight"), w(p + ".in_layers.2.bias"), padding=1)
+        e = F.linear(silu(emb), w(p + ".emb_layers.1.weight"), w(p + ".emb_layers.1.bias"))[..., None, None]
+        if cfg["use_scale_shift_norm"]:
+            scale, shift = torch.chunk(e, 2, dim=1)
+            y = gn(y, p + ".out_layers.0") * (1 + scale) + shift
+        else:
+            y = gn(y + e, p + ".out_layers.0")
+        y = F.conv2d(silu(y), w(p + ".out_layers.3.weight"), w(p + ".out_layers.3.bias"), padding=1)
+        if p + ".skip_connection.weight" in sd:
+            h = F.conv2d(h, w(p + ".skip_connection.weight"), w(p + ".skip_connection.bias"))
+        return h + y
+
+    def attn(p, h):                                                         # AttentionBlock._forward + QKVAttention, :219-253
+        b, c, hh, ww = h.shape
+        xf = h.reshape(b, c, -1)
+        qkv = F.conv1d(gn(xf, p + ".norm"), w(p + ".qkv.weight"), w(p + ".qkv.bias"))
+        qkv = qkv.reshape(b * heads, -1, qkv.shape[2])
+        ch = qkv.shape[1] // 3
+        q, k, v = torch.split(qkv, ch, dim=1)
+        scale = 1 / math.sqrt(math.sqrt(ch))
+        wgt = torch.softmax(torch.einsum("bct,bcs->bts", q * scale, k * scale).float(), dim=-1)
+        a = torch.einsum("bts,bcs->bct", wgt, v).reshape(b, -1, xf.shape[2])
+        a = F.conv1d(a, w(p + ".proj_out.weight"), w(p + ".proj_out.bias"))
+        return (xf + a).reshape(b, c, hh, ww)
+
+    h = _t(x, torch.float32)
+    hs = []
+    for p, kind, cin, cout in ops:
+        if kind == "conv_in":
+            h = F.conv2d(h, w(p + ".weight"), w(p + ".bias"), padding=1)
+            hs.append(h)
+        elif kind == "res":
+            h = res(p, h)
+        elif kind == "attn":
+            h = attn(p, h)
+        elif kind == "push":
+            hs.append(h)
+        elif kind == "pop":
+            h = torch.cat([h, hs.pop()], dim=1)                             # unet.py:493
+        elif kind == "down":
+            h = F.conv2d(h, w(p + ".op.weight"), w(p + ".op.bias"), stride=2, padding=1)      # Downsample, :93-104
+        elif kind == "up":
+            h = F.conv2d(F.interpolate(h, scale_factor=2, mode="nearest"), w(p + ".conv.weight"), w(p + ".conv.bias"),
+                         padding=1)                                         # Upsample, :68-78
+        elif kind == "out":
+            h = F.conv2d(silu(gn(h, "out.0")), w("out.2.weight"), w("out.2.bias"), padding=1)  # unet.py:438-442
+    return h
+
+
+MEL_UPPER_BOUND, MEL_LOWER_BOUND = 38.22, -100.0                            # sc09_spectrogram_dataset.py:61-62
+
+
+def spec_sde_tables(N: int = 1000, beta_min: float = 0.1, beta_max: float = 20.0):
+    """RevVPSDE.__init__ of improved_diffusion_sde.py:48-76."""
+    betas = torch.linspace(beta_min / N, beta_max / N, N)
+    return {"N": N, "beta_0": beta_min, "beta_1": beta_max, "discrete_betas": betas}
+
+
+def spec_sde_schedule(t_star: int, dt: float = 1e-3):
+    """The fixed-step Euler grid of ``sdeint_adjoint(..., method='euler')`` over ts = linspace(1 - t*/1000, 1 - 1e-5, 2)
+    (improved_diffusion_sde.py:193-203); no dt is passed there, so torchsde's default dt = 1e-3 applies.
+    PARITY UNPINNED (torchsde absent): same restated loop as ``sde_euler_schedule``."""
+    ts = torch.linspace(1 - t_star * 1.0 / 1000, 1 - 1e-5, 2)
+    curr, t1, out = ts[0], ts[1], []
+    while bool(curr < t1):
+        nxt = torch.minimum(curr + dt, t1)
+        out.append((curr.clone(), (nxt - curr).clone()))
+        curr = nxt
+    return out
+
+
+def spec_sde_step_coefficients(tab, s: torch.Tensor):
+    """RevVPSDE.f / .g at solver time s (improved_diffusion_sde.py:82-139): continuous beta, continuous alpha_bar, no
+    discrete scale factor on the diffusion."""
+    tau = 1 - s
+    beta = tab["beta_0"] + tau * (tab["beta_1"] - tab["beta_0"])                                        # :84
+    ab = torch.exp(-0.5 * (tab["beta_1"] - tab["beta_0"]) * tau ** 2 - tab["beta_0"] * tau)             # :72
+    return {"d": int((tau.float() * tab["N"]).long()), "beta": beta, "neg_recip": -1.0 / torch.sqrt(1.0 - ab),
+            "g": torch.sqrt(beta)}
+
+
+def spec_sde_purify(sd, img, t_star: int, noise, ops, cfg, eps_fn=None):
+    """RevImprovedDiffusion.image_editing_sample, sample_step = 1, rand_t = False (improved_diffusion_sde.py:175-219):
+    standardise the dB mel-spectrogram to [-1, 1], diffuse to level t*, integrate the reverse VP-SDE with the UNet's eps,
+    map back.  noise order: e, then one N(0,1) tensor per Euler step."""
+    img = _t(img, torch.float32)
+    tab = spec_sde_tables()
+    eps_fn = eps_fn or (lambda xx, d: unet_forward(sd, xx, d * torch.ones(xx.shape[0]), ops, cfg))
+    x0 = 2 * (img - MEL_LOWER_BOUND) / (MEL_UPPER_BOUND - MEL_LOWER_BOUND) - 1                           # melspec_standardize
+    a = (1 - tab["discrete_betas"]).cumprod(dim=0)
+    x = x0 * a[t_star - 1].sqrt() + noise(x0.shape) * (1.0 - a[t_star - 1]).sqrt()                       # :190
+    for s, ds in spec_sde_schedule(t_star):
+        c = spec_sde_step_coefficients(tab, s)
+        eps = eps_fn(x, c["d"]).to(torch.float32)                                                        # :105
+        drift = -0.5 * c["beta"] * x                                                                     # :85
+        score = c["neg_recip"] * eps                                                                     # :110
+        rdrift = drift - torch.sqrt(c["beta"]) ** 2 * score                                              # :115
+        x = x + (-rdrift) * ds + c["g"] * torch.sqrt(ds) * noise(x.shape)
+    return (x + 1) * (MEL_UPPER_BOUND - MEL_LOWER_BOUND) / 2 + MEL_LOWER_BOUND                           # melspec_inv_standardize
+
+
 # ---------------------------------------------------------------------------------------------- black-box queries (§8f-3)
 def query_loss(scores, labels, kind: str = "Entropy", targeted: bool = False, confidence: float = 0.0,
                clip_max: bool = True):

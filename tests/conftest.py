@@ -64,3 +64,10 @@ def trained_checkpoints():
         fam, name = k.split(".", 1)
         out[fam][name] = raw[k]
     return out
+
+
+@pytest.fixture(scope="session")
+def golden_unet():
+    """the reference's spectrogram UNet and RevImprovedDiffusion (tests/golden/make_golden_unet.py)"""
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_unet.npz")))

@@ -378,3 +378,24 @@ def test_sde_oracle_sample_step_and_rand_t(golden_sde, sd_full):
     with torch.no_grad():
         yr = orc.sde_purify(sd_full, x.detach(), 4, _noise(3304, 5, (1, 1, 16000)), noise_level=int(golden_sde["randt_level"]))
     assert rel_l2(yr.numpy(), golden_sde["randt_out"]) < 1e-5
+
+
+# ================================================================================================ spectrogram-domain purifier (Diffusion-Spec)
+def test_unet_oracle_vs_reference(golden_unet):
+    ops, cfg = synthetic.unet_structure()
+    sd = synthetic.unet_state_dict(seed=0)
+    x = golden_unet["unet_x"]
+    with torch.no_grad():
+        e37 = orc.unet_forward(sd, x, 37 * torch.ones(3), ops, cfg).numpy()
+        e1 = orc.unet_forward(sd, x[:1], torch.ones(1), ops, cfg).numpy()
+    assert rel_l2(e37, golden_unet["unet_eps_t37"]) < 1e-5
+    assert rel_l2(e1, golden_unet["unet_eps_t1"]) < 1e-5
+
+
+def test_spec_sde_oracle_vs_reference_revimproveddiffusion(golden_unet):
+    ops, cfg = synthetic.unet_structure()
+    sd = synthetic.unet_state_dict(seed=0)
+    n = int(golden_unet["spec_noise_draws"])
+    with torch.no_grad():
+        y = orc.spec_sde_purify(sd, golden_unet["spec_in"], 2, _noise(5300, n, (2, 1, 32, 32)), ops, cfg).numpy()
+    assert rel_l2(y, golden_unet["spec_purified_t2"]) < 1e-5

@@ -16,6 +16,7 @@ _LAZY = {
     "ResNeXtClassifier": "classifiers", "ResNetClassifier": "classifiers", "VGGClassifier": "classifiers", "WideResNetClassifier": "classifiers", "DenseNetClassifier": "classifiers", "M5Classifier": "classifiers", "KWSClassifier": "classifiers",
     "create_model": "classifiers",
     "AcousticSystem": "acoustic_system",
+    "UNet": "improved_diffusion", "RevImprovedDiffusion": "improved_diffusion",
     "RobustCertificate": "certify", "certify_dataset": "certify",
     "EOT": "blackbox", "NES": "blackbox", "QueryLoss": "blackbox", "resolve_loss": "blackbox", "resolve_prediction": "blackbox",
     "AudioPureError": "_lib",

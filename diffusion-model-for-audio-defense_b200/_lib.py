@@ -40,6 +40,11 @@ class ClassifierCfg(C.Structure):
                                       "kws_hidden")]
 
 
+class UNetCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("image_size", "in_channels", "model_channels", "out_channels", "num_res_blocks", "num_heads",
+                                      "use_scale_shift_norm")]
+
+
 _vp, _fp, _i, _f, _u64 = C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_uint64   # device pointers travel as void*
 _PP = C.POINTER(C.c_void_p)
 
@@ -79,6 +84,9 @@ SIGNATURES = {
     "ap_classifier_vjp": (_i, [_vp, _fp, _fp, _fp, _i, _i, _vp]),
     "ap_classifier_set_mode": (_i, [_vp, _i]),
     "ap_classifier_get_mode": (_i, [_vp]),
+    "ap_unet_create": (_i, [_PP, C.POINTER(UNetCfg), _vp, _i, _PP, _i, _i]),
+    "ap_unet_destroy": (None, [_vp]),
+    "ap_unet_eps": (_i, [_vp, _fp, _f, _fp, _i, _vp]),
     "ap_vote_counts": (_i, [_fp, _i, _i, _vp, _i, _vp]),
     "ap_argmax": (_i, [_fp, _i, _i, _vp, _vp]),
     "ap_nes_noise_blocks": (_u64, [_i, _i, _i]),

@@ -16,7 +16,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libaudiopure_b200.so")
 STAMP = LIB_PATH + ".stamp"
-SOURCES = ["ap_update.cu", "ap_query.cu", "ap_wavenet.cu", "ap_wavenet_tc.cu", "ap_mel.cu", "ap_classifier.cu", "ap_conv_tc.cu"]
+SOURCES = ["ap_update.cu", "ap_query.cu", "ap_wavenet.cu", "ap_wavenet_tc.cu", "ap_mel.cu", "ap_classifier.cu", "ap_conv_tc.cu", "ap_unet.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -1,0 +1,135 @@
+// Convolution as an implicit GEMM over NHWC activations (FFMA path) with its optional TF32 tensor-core twin: shared by the
+// classifiers (ap_classifier.cu) and the spectrogram UNet (ap_unet.cu).
+#pragma once
+#include <cmath>
+#include <vector>
+
+#include "ap_common.cuh"
+#include "ap_conv_tc.h"
+#include "ap_internal.h"
+#include "ap_sgemm.cuh"
+
+namespace ap {
+
+// ---------------------------------------------------------------------------------------------- conv as implicit GEMM
+// in: NHWC [B][H][W][Ctot]; group z uses channels [z*Cg, (z+1)*Cg); k = (r*kw + s)*Cg + c
+template <bool VEC> struct Conv2dLoader {
+  const float* in;
+  int H, W, Ctot, Cg, kh, kw, stride, pad, pad_h, Ho, Wo;   // pad: width padding; pad_h: height padding (0 for 1 x k kernels)
+  __device__ __forceinline__ float one(int z, int b, int oh, int ow, int k) const {
+    const int rs = k / Cg, c = k - rs * Cg, r = rs / kw, s = rs - r * kw;
+    const int ih = oh * stride + r - pad_h, iw = ow * stride + s - pad;
+    if (ih < 0 || ih >= H || iw < 0 || iw >= W) return 0.f;
+    return in[((static_cast<long long>(b) * H + ih) * W + iw) * Ctot + z * Cg + c];
+  }
+  __device__ __forceinline__ float4 load4(int z, int m, int k, int M, int K) const {
+    if (m >= M || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const int b = m / (Ho * Wo), rem = m - b * (Ho * Wo), oh = rem / Wo, ow = rem - oh * Wo;
+    if (VEC) {
+      const int rs = k / Cg, c = k - rs * Cg, r = rs / kw, s = rs - r * kw;
+      const int ih = oh * stride + r - pad_h, iw = ow * stride + s - pad;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+      return *reinterpret_cast<const float4*>(in + ((static_cast<long long>(b) * H + ih) * W + iw) * Ctot + z * Cg + c);
+    }
+    float4 v;
+    v.x = one(z, b, oh, ow, k);
+    v.y = k + 1 < K ? one(z, b, oh, ow, k + 1) : 0.f;
+    v.z = k + 2 < K ? one(z, b, oh, ow, k + 2) : 0.f;
+    v.w = k + 3 < K ? one(z, b, oh, ow, k + 3) : 0.f;
+    return v;
+  }
+};
+// out[m][z*Ng + n] = act(acc + bias [+ residual])
+struct ConvEpi {
+  float* out;
+  const float* bias;
+  const float* residual;
+  int Ctot, Ng, relu;
+  __device__ __forceinline__ void put(int z, int m, int n, float acc) const {
+    if (n >= Ng) return;
+    const int ch = z * Ng + n;
+    const long long idx = static_cast<long long>(m) * Ctot + ch;
+    float v = acc + bias[ch];
+    if (residual) v += residual[idx];
+    out[idx] = relu ? fmaxf(v, 0.f) : v;
+  }
+  __device__ __forceinline__ void store(int z, int m, int n0, int tx, const float (&lo)[4], const float (&hi)[4], int) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      put(z, m, n0 + tx * 4 + j, lo[j]);
+      put(z, m, n0 + 64 + tx * 4 + j, hi[j]);
+    }
+  }
+};
+
+struct ConvLayer {
+  int Cin = 0, Cout = 0, kh = 1, kw = 1, stride = 1, pad = 0, groups = 1;
+  int Cg = 0, Ng = 0, Ngp = 0, K = 0;
+  DevBuf w, bias;
+  std::vector<float> wf_host;   // folded torch-layout weights [Cout][Cin/groups][kh][kw], kept when `keep_host` (backward pass)
+  bool keep_host = false;
+  ConvTc tc;            // TF32 tensor-core twin (weights [Cout][K] K-major), built when the shape allows
+  bool has_tc = false;
+  // w_t: torch [Cout][Cin/groups][kh][kw]; optional BatchNorm(eval) folded: scale = gamma/sqrt(var+eps), shift = beta - mean*scale
+  int init(int cin, int cout, int kh_, int kw_, int stride_, int pad_, int groups_, const float* w_t, const float* conv_bias,
+           const float* bn_w, const float* bn_b, const float* bn_m, const float* bn_v, bool want_tc = false) {
+    Cin = cin, Cout = cout, kh = kh_, kw = kw_, stride = stride_, pad = pad_, groups = groups_;
+    Cg = cin / groups, Ng = cout / groups, Ngp = ((Ng + 127) / 128) * 128, K = kh * kw * Cg;
+    std::vector<float> wp(static_cast<size_t>(groups) * K * Ngp, 0.f), bp(cout), wf(static_cast<size_t>(cout) * K);
+    for (int o = 0; o < cout; ++o) {
+      float scale = 1.f, shift = conv_bias ? conv_bias[o] : 0.f;
+      if (bn_w) {
+        scale = bn_w[o] / std::sqrt(bn_v[o] + 1e-5f);
+        shift = bn_b[o] + (shift - bn_m[o]) * scale;
+      }
+      bp[o] = shift;
+      const int g = o / Ng, n = o - g * Ng;
+      for (int c = 0; c < Cg; ++c)
+        for (int r = 0; r < kh; ++r)
+          for (int s = 0; s < kw; ++s)
+          {
+            const size_t ti = ((static_cast<size_t>(o) * Cg + c) * kh + r) * kw + s;
+            wf[ti] = w_t[ti] * scale;
+            wp[(static_cast<size_t>(g) * K + (r * kw + s) * Cg + c) * Ngp + n] = wf[ti];
+          }
+    }
+    AP_CUDA(w.upload(wp.data(), wp.size() * sizeof(float)));
+    AP_CUDA(bias.upload(bp.data(), bp.size() * sizeof(float)));
+    if (keep_host) wf_host = wf;
+    // structural part of conv_tc_supported (the spatial part is checked when the layer is bound to buffers)
+    if (want_tc && Cg % 32 == 0 && conv_tc_n_tile(Ng) != 0) {
+      int rc = tc.init(cin, cout, kh, kw, stride, pad, groups, wf.data(), bp.data());
+      if (rc != AP_OK) return rc;
+      has_tc = true;
+    }
+    return AP_OK;
+  }
+  int run(const float* in, int B, int H, int W, float* out, const float* residual, int relu, cudaStream_t st) const {
+    return run_strided(in, Cin, B, H, W, out, Cout, residual, relu, st);
+  }
+  // in / out are channel slices of wider NHWC tensors: pixel strides in_ctot / out_ctot floats (DenseNet's concatenation)
+  int run_strided(const float* in, int in_ctot, int B, int H, int W, float* out, int out_ctot, const float* residual, int relu,
+                  cudaStream_t st) const {
+    const int pad_h = kh == 1 ? 0 : pad;   // 1 x k kernels (conv1d as a height-1 image) pad the width only
+    const int Ho = (H + 2 * pad_h - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    const long long M = static_cast<long long>(B) * Ho * Wo;
+    if (M >= (1ll << 31)) return fail(AP_ERR_INVALID, "conv: too many output pixels");
+    ConvEpi ep{out, bias.as<float>(), residual, out_ctot, Ng, relu};
+    cudaError_t e;
+    const bool narrow = Ng <= 16;   // 128 x 16 tiles instead of 128 x 128: DenseNet's growth convolutions, 1-channel data gradients
+    if (Cg % 4 == 0 && in_ctot % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+      Conv2dLoader<true> al{in, H, W, in_ctot, Cg, kh, kw, stride, pad, pad_h, Ho, Wo};
+      e = narrow ? sgemm::launch_n16(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st)
+                 : sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
+    } else {
+      Conv2dLoader<false> al{in, H, W, in_ctot, Cg, kh, kw, stride, pad, pad_h, Ho, Wo};
+      e = narrow ? sgemm::launch_n16(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st)
+                 : sgemm::launch(al, w.as<float>(), Ngp, static_cast<long long>(K) * Ngp, groups, static_cast<int>(M), Ng, K, ep, st);
+    }
+    if (e != cudaSuccess) return fail(AP_ERR_CUDA, "conv launch: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return AP_OK;
+  }
+};
+
+}  // namespace ap

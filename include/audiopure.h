@@ -224,6 +224,34 @@ int ap_classifier_set_mode(ap_classifier_t h, int mode);
 int ap_classifier_get_mode(ap_classifier_t h);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Spectrogram-domain purifier ("Diffusion-Spec"): the UNet eps-network of RevImprovedDiffusion
+ * (diffusion_models/improved_diffusion_sde.py:140-226 builds it with create_model_and_diffusion; UNetModel.forward,
+ * Improved_Diffusion_Unconditional/improved_diffusion/unet.py:462-497).  The reverse-SDE update itself is ap_sde_step.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct ap_unet_s* ap_unet_t;
+typedef struct {
+  int image_size;     /* 32 */
+  int in_channels;    /* 1 */
+  int model_channels; /* 128 */
+  int out_channels;   /* 1 */
+  int num_res_blocks; /* 3 */
+  int num_heads;      /* 4 (64-channel heads) */
+  int use_scale_shift_norm; /* 1 */
+} ap_unet_cfg; /* == script_util.py model_and_diffusion_defaults / create_model */
+enum { AP_UNET_CONV_IN = 0, AP_UNET_RES = 1, AP_UNET_ATTN = 2, AP_UNET_PUSH = 3, AP_UNET_POP = 4, AP_UNET_DOWN = 5, AP_UNET_UP = 6,
+       AP_UNET_OUT = 7 };
+/* ops: the module walk of UNetModel.__init__ (unet.py:341-443) as n_ops rows {kind, cin, cout} (PUSH / POP = the skip-connection
+ * stack of forward(), :483-494; POP's cout = channels after th.cat).  weights: host fp32 pointers in the reference's state-dict
+ * order (time_embed.0.weight, .bias, time_embed.2.*, then per op: conv weight / bias; ResBlock: in_layers.0.{weight,bias},
+ * in_layers.2.{weight,bias}, emb_layers.1.{weight,bias}, out_layers.0.*, out_layers.3.*, [skip_connection.*]; AttentionBlock:
+ * norm.*, qkv.*, proj_out.*; out.0.*, out.2.*). */
+int ap_unet_create(ap_unet_t* out, const ap_unet_cfg* cfg, const int* ops, int n_ops, const float* const* weights,
+                   int n_weights, int device);
+void ap_unet_destroy(ap_unet_t h);
+/* eps = model(x, timesteps = t for every row).  x, eps: device fp32 (B, 1, image_size, image_size). */
+int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Votes (replaces the argmax + per-class .sum().item() loop of smooth_predict, certified_robust.py:59-67)
  * counts: device int64[counts_len], ACCUMULATED (caller zeroes it); K = logits.shape[-1] must not exceed counts_len (the
  * reference sizes counts from output.shape[-1], certified_robust.py:60-63); ties resolve to the lowest class index like torch.max.

@@ -302,3 +302,39 @@ def test_sde_gradient_matches_the_reference_semantics(ap, sd_full, golden_sde, m
 def test_sde_use_bm_raises(ap, sd_full):
     with pytest.raises(NotImplementedError):
         _rev(ap, sd_full, 2, "bf16", use_bm=True)
+
+
+# ------------------------------------------------------------------------------------------------ spectrogram-domain purifier
+def test_unet_eps_vs_reference(ap, golden_unet):
+    """UNetModel.forward (improved_diffusion/unet.py:462-497) on the CUDA kernels vs the unmodified reference, fp32."""
+    net = ap.UNet(synthetic.unet_state_dict(seed=0))
+    x = cuda(golden_unet["unet_x"])
+    e37 = net(x, torch.tensor([37, 37, 37]))
+    e1 = net(x[:1], torch.tensor([1]))
+    err37, err1 = rel_l2(e37, golden_unet["unet_eps_t37"]), rel_l2(e1, golden_unet["unet_eps_t1"])
+    print(f"UNet eps t=37: rel-L2 {err37:.3e}; t=1: {err1:.3e}")
+    assert err37 < 2e-5 and err1 < 2e-5
+    big = net(cuda(np.tile(golden_unet["unet_x"], (11, 1, 1, 1))), torch.full((33,), 37))       # batch independence, ragged sub-batches
+    assert rel_l2(big[30:33], golden_unet["unet_eps_t37"]) < 2e-5
+
+
+def test_rev_improved_diffusion_vs_reference(ap, golden_unet):
+    """RevImprovedDiffusion.image_editing_sample (improved_diffusion_sde.py:175-219) with the reference's noise, t = 2, and as the
+    'spec' defender of AcousticSystem (acoustic_system.py:43-47)."""
+    args = argparse.Namespace(ddpm_path=None, t=2, score_type="guided_diffusion", rand_t=False, t_delta=15, use_bm=False, sample_step=1)
+    rid = ap.RevImprovedDiffusion(args, state_dict=synthetic.unet_state_dict(seed=0), noise="torch")
+    spec = cuda(golden_unet["spec_in"])
+    with RandnInjector(5300) as inj:
+        y = rid(spec)
+        assert inj.i == int(golden_unet["spec_noise_draws"])
+    err = rel_l2(y, golden_unet["spec_purified_t2"])
+    print(f"Diffusion-Spec t*=2: purified spectrogram rel-L2 {err:.3e}")
+    assert err < 1e-5
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    system = ap.AcousticSystem(classifier=rx, transform=ap.sc09_transform(), defender=rid, defense_type="spec")
+    wav = cuda(synthetic.synthetic_waveforms(2, 16000, seed=9))
+    with RandnInjector(5301):
+        logits = system(wav)
+    assert tuple(logits.shape) == (2, 10) and torch.isfinite(logits).all()
+    with pytest.raises(Exception):
+        rid(spec.clone().requires_grad_(True))

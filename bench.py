@@ -81,6 +81,9 @@ def measured_peaks():
 
 
 def workload_name(workload, t_star, length, batch, sigma_in=None):
+    if workload == "spec":
+        return (f"SURVEY 8(f)4 Diffusion-Spec: SC09 log-mel -> spectrogram UNet (128 ch, 30 ResBlocks, 15 attention blocks) reverse-SDE "
+                f"t*={t_star} -> ResNeXt-29 8x64, batch {batch} x {length / 16000:g} s @ 16 kHz per GPU, random-init weights, tf32 convolutions")
     purifier = {"sc09": f"DDPM t*={t_star}", "sde": f"reverse-SDE (Euler-Maruyama) t*={t_star}",
                 "m5": f"DDPM t*={t_star}", "kws": f"DDPM t*={t_star}"}[workload]
     head = {"sc09": "SC09 log-mel + ResNeXt-29 8x64", "sde": "SC09 log-mel + ResNeXt-29 8x64", "m5": "M5 raw-waveform classifier",
@@ -249,13 +252,15 @@ class Harness:
     def system(self, workload, t_star):
         ap = self.ap
         self.dw.reverse_timestep = t_star
-        if workload == "sde":
-            ns = argparse.Namespace(ddpm_path=None, ddpm_config=self.cfg_json, t=t_star, score_type="guided_diffusion", rand_t=False,
-                                    t_delta=0, use_bm=False, sample_step=1)
-            defender = ap.RevDiffWave(ns, diffwave=self.dw)
-        else:
-            defender = self.dw
+        ns = argparse.Namespace(ddpm_path=None, ddpm_config=self.cfg_json, t=t_star, score_type="guided_diffusion", rand_t=False,
+                                t_delta=0, use_bm=False, sample_step=1)
         transform, classifier = self.classifier(workload if workload in ("m5", "kws") else "sc09")
+        if workload == "spec":      # Diffusion-Spec: the UNet reverse-SDE purifier acts on the log-mel spectrogram (defense_type 'spec')
+            if "spec" not in self._cls:
+                self._cls["spec"] = ap.RevImprovedDiffusion(ns, state_dict=self.synthetic.unet_state_dict(seed=0), seed=3024 + self.rank)
+            self._cls["spec"].args.t = t_star
+            return ap.AcousticSystem(classifier=classifier, transform=transform, defender=self._cls["spec"], defense_type="spec")
+        defender = ap.RevDiffWave(ns, diffwave=self.dw) if workload == "sde" else self.dw
         return ap.AcousticSystem(classifier=classifier, transform=transform, defender=defender, defense_type="wave")
 
     # -- timing ---------------------------------------------------------------------------------------------------
@@ -568,6 +573,8 @@ def run_ours(args):
             else:
                 leg("sde_t10_sigma1.0", workload="sde", t_star=10, batch=512, length=LENGTH, steps=st_, warmup=wu_, mode="bf16",
                     sigma_in=1.0)
+            if extras == "all":
+                leg("spec_sde_t2", workload="spec", t_star=2, batch=512, length=LENGTH, steps=st_, warmup=wu_, mode="bf16")
             leg("m5", workload="m5", t_star=2, batch=512, length=LENGTH, steps=3, warmup=wu_, mode="bf16", e2e=True)
             leg("kws_2s", workload="kws", t_star=2, batch=512, length=32000, steps=st_, warmup=wu_, mode="bf16", e2e=True)
             dw.model.set_mode(args.mode)

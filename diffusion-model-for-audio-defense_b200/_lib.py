@@ -86,6 +86,7 @@ SIGNATURES = {
     "ap_classifier_get_mode": (_i, [_vp]),
     "ap_unet_create": (_i, [_PP, C.POINTER(UNetCfg), _vp, _i, _PP, _i, _i]),
     "ap_unet_destroy": (None, [_vp]),
+    "ap_unet_set_mode": (_i, [_vp, _i]),
     "ap_unet_eps": (_i, [_vp, _fp, _f, _fp, _i, _vp]),
     "ap_vote_counts": (_i, [_fp, _i, _i, _vp, _i, _vp]),
     "ap_argmax": (_i, [_fp, _i, _i, _vp, _vp]),

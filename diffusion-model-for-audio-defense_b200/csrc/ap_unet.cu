@@ -30,7 +30,7 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v))
 // scale_shift: [2 C] for this block (scale = first C entries, shift = last C: th.chunk(emb_out, 2, dim=1), unet.py:190), or null.
 __global__ void __launch_bounds__(256) gn_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ gamma,
                                                  const float* __restrict__ beta, const float* __restrict__ scale_shift, int HW, int C,
-                                                 int cpg, int act) {
+                                                 int cpg, int act, int round_tf32) {
   const int b = blockIdx.x / 32, g = blockIdx.x % 32;
   const float* xb = x + static_cast<size_t>(b) * HW * C + g * cpg;
   float* ob = out + static_cast<size_t>(b) * HW * C + g * cpg;
@@ -72,7 +72,13 @@ __global__ void __launch_bounds__(256) gn_kernel(const float* __restrict__ x, fl
     const size_t idx = static_cast<size_t>(i / cpg) * C + c;
     float y = (xb[idx] - mean) * rstd * gamma[ch] + beta[ch];
     if (scale_shift) y = y * (1.f + scale_shift[ch]) + scale_shift[C + ch];
-    ob[idx] = act ? silu_f(y) : y;
+    y = act ? silu_f(y) : y;
+    if (round_tf32) {   // the tensor core truncates fp32 operands to tf32: round to nearest here instead
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(y));
+      y = __uint_as_float(r);
+    }
+    ob[idx] = y;
   }
 }
 
@@ -206,6 +212,7 @@ struct UOp {
 struct ap_unet_s {
   ap_unet_cfg cfg{};
   int device = 0;
+  int mode = AP_MODE_TF32;      // AP_MODE_TF32: tcgen05 kind::tf32 convolutions where a tile shape exists; AP_MODE_FP32: FFMA everywhere
   std::vector<std::unique_ptr<UOp>> ops;
   DevBuf te_w0, te_b0, te_w2, te_b2, emb_w, emb_b, emb_silu, ss;
   int ss_rows = 0;
@@ -254,7 +261,7 @@ extern "C" int ap_unet_create(ap_unet_t* out, const ap_unet_cfg* cfg, const int*
     if (op->kind == OP_CONV_IN || op->kind == OP_DOWN || op->kind == OP_UP) {
       const float *cw = next(), *cb = next();
       AP_REQUIRE(cb, "ap_unet_create: too few weights");
-      TRY(op->c1.init(ci, co, 3, 3, op->kind == OP_DOWN ? 2 : 1, 1, 1, cw, cb, nullptr, nullptr, nullptr, nullptr));
+      TRY(op->c1.init(ci, co, 3, 3, op->kind == OP_DOWN ? 2 : 1, 1, 1, cw, cb, nullptr, nullptr, nullptr, nullptr, true));
     } else if (op->kind == OP_RES) {
       const float *g1 = next(), *b1 = next(), *w1 = next(), *bb1 = next(), *ew = next(), *eb = next(), *g2 = next(), *b2 = next(),
                   *w2 = next(), *bb2 = next();
@@ -262,17 +269,17 @@ extern "C" int ap_unet_create(ap_unet_t* out, const ap_unet_cfg* cfg, const int*
       AP_REQUIRE(ci % 32 == 0 && co % 32 == 0, "ap_unet_create: channel counts must be multiples of 32 (GroupNorm32)");
       TRY(upload_vec(op->g1, g1, ci));
       TRY(upload_vec(op->b1, b1, ci));
-      TRY(op->c1.init(ci, co, 3, 3, 1, 1, 1, w1, bb1, nullptr, nullptr, nullptr, nullptr));
+      TRY(op->c1.init(ci, co, 3, 3, 1, 1, 1, w1, bb1, nullptr, nullptr, nullptr, nullptr, true));
       op->ss_off = static_cast<int>(emb_b.size());
       emb_w.insert(emb_w.end(), ew, ew + static_cast<size_t>(2 * co) * ted);
       emb_b.insert(emb_b.end(), eb, eb + 2 * co);
       TRY(upload_vec(op->g2, g2, co));
       TRY(upload_vec(op->b2, b2, co));
-      TRY(op->c2.init(co, co, 3, 3, 1, 1, 1, w2, bb2, nullptr, nullptr, nullptr, nullptr));
+      TRY(op->c2.init(co, co, 3, 3, 1, 1, 1, w2, bb2, nullptr, nullptr, nullptr, nullptr, true));
       if (ci != co) {
         const float *sw = next(), *sb = next();
         AP_REQUIRE(sb, "ap_unet_create: too few weights");
-        TRY(op->skip.init(ci, co, 1, 1, 1, 0, 1, sw, sb, nullptr, nullptr, nullptr, nullptr));
+        TRY(op->skip.init(ci, co, 1, 1, 1, 0, 1, sw, sb, nullptr, nullptr, nullptr, nullptr, true));
         op->has_skip = true;
       }
     } else if (op->kind == OP_ATTN) {
@@ -281,14 +288,14 @@ extern "C" int ap_unet_create(ap_unet_t* out, const ap_unet_cfg* cfg, const int*
       AP_REQUIRE(ci % cfg->num_heads == 0 && ci / cfg->num_heads == 64, "ap_unet_create: attention heads must be 64 channels wide");
       TRY(upload_vec(op->g1, g, ci));
       TRY(upload_vec(op->b1, b, ci));
-      TRY(op->c1.init(ci, 3 * ci, 1, 1, 1, 0, 1, qw, qb, nullptr, nullptr, nullptr, nullptr));
-      TRY(op->c2.init(ci, ci, 1, 1, 1, 0, 1, pw, pb, nullptr, nullptr, nullptr, nullptr));
+      TRY(op->c1.init(ci, 3 * ci, 1, 1, 1, 0, 1, qw, qb, nullptr, nullptr, nullptr, nullptr, true));
+      TRY(op->c2.init(ci, ci, 1, 1, 1, 0, 1, pw, pb, nullptr, nullptr, nullptr, nullptr, true));
     } else if (op->kind == OP_OUT) {
       const float *g = next(), *b = next(), *cw = next(), *cb = next();
       AP_REQUIRE(cb, "ap_unet_create: too few weights");
       TRY(upload_vec(op->g1, g, ci));
       TRY(upload_vec(op->b1, b, ci));
-      TRY(op->c1.init(ci, co, 3, 3, 1, 1, 1, cw, cb, nullptr, nullptr, nullptr, nullptr));
+      TRY(op->c1.init(ci, co, 3, 3, 1, 1, 1, cw, cb, nullptr, nullptr, nullptr, nullptr, true));
     } else {
       AP_REQUIRE(op->kind == OP_PUSH || op->kind == OP_POP, "ap_unet_create: unknown op kind %d", op->kind);
     }
@@ -326,6 +333,11 @@ extern "C" int ap_unet_create(ap_unet_t* out, const ap_unet_cfg* cfg, const int*
 }
 
 extern "C" void ap_unet_destroy(ap_unet_t h) { delete h; }
+extern "C" int ap_unet_set_mode(ap_unet_t h, int mode) {
+  AP_REQUIRE(h && (mode == AP_MODE_TF32 || mode == AP_MODE_FP32), "ap_unet_set_mode: AP_MODE_TF32 or AP_MODE_FP32");
+  h->mode = mode;
+  return AP_OK;
+}
 
 // eps[b] = UNet(x[b], t) with the same discrete step t for every sample (RevVPSDE.rvpsde_fn passes one step per Euler step,
 // improved_diffusion_sde.py:104-105).  x, eps: device fp32 (B, 1, S, S).
@@ -362,9 +374,18 @@ extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int
     std::vector<Act> stack;
     Act cur{const_cast<float*>(x) + static_cast<size_t>(b0) * S * S, S, 1};
     auto gn = [&](const Act& a, float* out, const DevBuf& g, const DevBuf& b, const float* ss, int act) -> int {
-      gn_kernel<<<bn * 32, 256, 0, st>>>(a.p, out, g.as<float>(), b.as<float>(), ss, a.H * a.H, a.C, a.C / 32, act);
+      gn_kernel<<<bn * 32, 256, 0, st>>>(a.p, out, g.as<float>(), b.as<float>(), ss, a.H * a.H, a.C, a.C / 32, act,
+                                         h->mode == AP_MODE_TF32);
       AP_LAUNCH_CHECK();
       return AP_OK;
+    };
+    auto conv = [&](const ConvLayer& L, const float* in, int H, float* out, const float* res) -> int {
+      if (h->mode == AP_MODE_TF32 && L.has_tc && conv_tc_supported(L.Cin, L.Cout, L.groups, H, H, L.kh, L.kw, L.stride, L.pad)) {
+        ConvTcBinding bnd;
+        int rcb = L.tc.bind(&bnd, in, bn, H, H, out, res, 0, 0);
+        return rcb != AP_OK ? rcb : L.tc.run(bnd, st);
+      }
+      return L.run(in, bn, H, H, out, res, 0, st);
     };
     int rc = AP_OK;
     for (auto& opp : h->ops) {
@@ -372,7 +393,7 @@ extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int
       const size_t px = static_cast<size_t>(bn) * cur.H * cur.H;
       if (op.kind == OP_CONV_IN) {
         float* o = alloc(px * op.cout);
-        rc = op.c1.run(cur.p, bn, cur.H, cur.H, o, nullptr, 0, st);
+        rc = conv(op.c1, cur.p, cur.H, o, nullptr);
         cur = {o, cur.H, op.cout};
         stack.push_back(cur);                              // hs.append(h) of input_blocks[0] (unet.py:483-485)
       } else if (op.kind == OP_RES) {
@@ -381,16 +402,16 @@ extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int
         float* n2 = alloc(px * op.cout);
         float* o = alloc(px * op.cout);
         rc = gn(cur, n1, op.g1, op.b1, nullptr, 1);                                             // in_layers: GN, SiLU
-        if (rc == AP_OK) rc = op.c1.run(n1, bn, cur.H, cur.H, y1, nullptr, 0, st);              //            conv
+        if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, y1, nullptr);              //            conv
         Act a1{y1, cur.H, op.cout};
         if (rc == AP_OK) rc = gn(a1, n2, op.g2, op.b2, h->ss.as<float>() + op.ss_off, 1);       // out_layers[0] * (1 + scale) + shift, SiLU
         const float* res = cur.p;
         if (rc == AP_OK && op.has_skip) {
           float* sk = alloc(px * op.cout);
-          rc = op.skip.run(cur.p, bn, cur.H, cur.H, sk, nullptr, 0, st);
+          rc = conv(op.skip, cur.p, cur.H, sk, nullptr);
           res = sk;
         }
-        if (rc == AP_OK) rc = op.c2.run(n2, bn, cur.H, cur.H, o, res, 0, st);                   // conv + skip_connection(x)
+        if (rc == AP_OK) rc = conv(op.c2, n2, cur.H, o, res);                   // conv + skip_connection(x)
         cur = {o, cur.H, op.cout};
       } else if (op.kind == OP_ATTN) {
         const int T = cur.H * cur.H, Cc = cur.C;
@@ -399,7 +420,7 @@ extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int
         float* av = alloc(px * Cc);
         float* o = alloc(px * Cc);
         rc = gn(cur, n1, op.g1, op.b1, nullptr, 0);
-        if (rc == AP_OK) rc = op.c1.run(n1, bn, cur.H, cur.H, qkv, nullptr, 0, st);
+        if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, qkv, nullptr);
         if (rc == AP_OK) {
           const size_t smem = static_cast<size_t>(2) * T * 64 * sizeof(float);
           static bool attr = false;
@@ -410,7 +431,7 @@ extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int
           AP_REQUIRE(T <= 256, "ap_unet_eps: attention over more than 256 positions is not supported");
           unet_attn_kernel<64><<<bn * heads, T < 256 ? ((T + 31) / 32) * 32 : 256, smem, st>>>(qkv, av, T, Cc, heads);
           AP_LAUNCH_CHECK();
-          rc = op.c2.run(av, bn, cur.H, cur.H, o, cur.p, 0, st);                                // proj_out + x
+          rc = conv(op.c2, av, cur.H, o, cur.p);                                // proj_out + x
         }
         cur = {o, cur.H, Cc};
       } else if (op.kind == OP_PUSH) {
@@ -429,7 +450,7 @@ extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int
       } else if (op.kind == OP_DOWN) {
         const int Ho = cur.H / 2;
         float* o = alloc(static_cast<size_t>(bn) * Ho * Ho * op.cout);
-        rc = op.c1.run(cur.p, bn, cur.H, cur.H, o, nullptr, 0, st);
+        rc = conv(op.c1, cur.p, cur.H, o, nullptr);
         cur = {o, Ho, op.cout};
       } else if (op.kind == OP_UP) {
         float* up = alloc(4 * px * op.cin);
@@ -437,12 +458,12 @@ extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int
         nearest_up2_kernel<<<grid_for_n(static_cast<long long>(px) * op.cin, 256), 256, 0, st>>>(
             reinterpret_cast<const float4*>(cur.p), reinterpret_cast<float4*>(up), bn, cur.H, cur.H, op.cin / 4);
         AP_LAUNCH_CHECK();
-        rc = op.c1.run(up, bn, 2 * cur.H, 2 * cur.H, o, nullptr, 0, st);
+        rc = conv(op.c1, up, 2 * cur.H, o, nullptr);
         cur = {o, 2 * cur.H, op.cout};
       } else if (op.kind == OP_OUT) {
         float* n1 = alloc(px * op.cin);
         rc = gn(cur, n1, op.g1, op.b1, nullptr, 1);
-        if (rc == AP_OK) rc = op.c1.run(n1, bn, cur.H, cur.H, eps + static_cast<size_t>(b0) * S * S, nullptr, 0, st);
+        if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, eps + static_cast<size_t>(b0) * S * S, nullptr);
       }
       if (rc != AP_OK) return rc;
       if (top > h->arena_floats) return fail(AP_ERR_STATE, "ap_unet_eps: activation arena overflow (%zu > %zu floats)", top, h->arena_floats);

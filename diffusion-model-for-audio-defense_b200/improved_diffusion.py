@@ -81,6 +81,12 @@ class UNet(torch.nn.Module):
         _lib.check(self._lib.ap_unet_create(C.byref(self._handle), C.byref(c), op_arr.ctypes.data, len(ops),
                                             _lib.ptr_array(self._weights), len(self._weights), self.device_index), "ap_unet_create")
 
+    def set_mode(self, mode: str) -> "UNet":
+        """'tf32' (default: tensor-core convolutions, the precision of the reference's cuDNN path) or 'fp32' (FFMA, parity mode)"""
+        _lib.check(self._lib.ap_unet_set_mode(self._handle, {"tf32": _lib.AP_MODE_TF32, "fp32": _lib.AP_MODE_FP32}[mode]),
+                   "ap_unet_set_mode")
+        return self
+
     def eps(self, x: torch.Tensor, t: float, out: torch.Tensor | None = None) -> torch.Tensor:
         if not x.is_cuda:
             raise _lib.AudioPureError("UNet: input must be a CUDA tensor (there is no CPU path)")

@@ -248,6 +248,9 @@ enum { AP_UNET_CONV_IN = 0, AP_UNET_RES = 1, AP_UNET_ATTN = 2, AP_UNET_PUSH = 3,
 int ap_unet_create(ap_unet_t* out, const ap_unet_cfg* cfg, const int* ops, int n_ops, const float* const* weights,
                    int n_weights, int device);
 void ap_unet_destroy(ap_unet_t h);
+/* AP_MODE_TF32 (default: every convolution with a tensor-core tile shape on tcgen05 kind::tf32 -- the precision of the reference's
+ * cuDNN path) or AP_MODE_FP32 (FFMA everywhere; the parity mode) */
+int ap_unet_set_mode(ap_unet_t h, int mode);
 /* eps = model(x, timesteps = t for every row).  x, eps: device fp32 (B, 1, image_size, image_size). */
 int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int B, void* stream);
 

@@ -309,6 +309,10 @@ def test_unet_eps_vs_reference(ap, golden_unet):
     """UNetModel.forward (improved_diffusion/unet.py:462-497) on the CUDA kernels vs the unmodified reference, fp32."""
     net = ap.UNet(synthetic.unet_state_dict(seed=0))
     x = cuda(golden_unet["unet_x"])
+    err_tf32 = rel_l2(net(x, torch.tensor([37, 37, 37])), golden_unet["unet_eps_t37"])      # default mode: tf32 tensor-core convolutions
+    print(f"UNet eps t=37, tf32 tensor-core convolutions: rel-L2 {err_tf32:.3e}")
+    assert err_tf32 < 5e-3
+    net.set_mode("fp32")
     e37 = net(x, torch.tensor([37, 37, 37]))
     e1 = net(x[:1], torch.tensor([1]))
     err37, err1 = rel_l2(e37, golden_unet["unet_eps_t37"]), rel_l2(e1, golden_unet["unet_eps_t1"])
@@ -323,6 +327,7 @@ def test_rev_improved_diffusion_vs_reference(ap, golden_unet):
     'spec' defender of AcousticSystem (acoustic_system.py:43-47)."""
     args = argparse.Namespace(ddpm_path=None, t=2, score_type="guided_diffusion", rand_t=False, t_delta=15, use_bm=False, sample_step=1)
     rid = ap.RevImprovedDiffusion(args, state_dict=synthetic.unet_state_dict(seed=0), noise="torch")
+    rid.model.set_mode("fp32")
     spec = cuda(golden_unet["spec_in"])
     with RandnInjector(5300) as inj:
         y = rid(spec)

@@ -611,10 +611,10 @@ def run_ours(args):
             roofline = {"kernel": "k1_layer (DiffWave residual block: tcgen05 implicit GEMM K=768/N=512 + K=256/N=256, fused "
                                   "gate / residual epilogues)", "bound": "tensor", "achieved": achieved,
                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
-                        "traffic": 24.245e6 * avg_wf if args.mode != "bf16x3" else None,
+                        "traffic": 24.430e6 * avg_wf if args.mode != "bf16x3" else None,
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel "
-                                          "(profiles/, 3.103e9 B for a 128-waveform launch; algorithmic 3.146e9 B), scaled to this "
-                                          "run's waveforms per launch" if args.mode != "bf16x3" else "see profiles/ for the split kernel",
+                                          "(profiles/r02_k1_staged_ncu_full_summary.txt: 3.127e9 B for a 128-waveform launch; algorithmic "
+                                          "3.146e9 B), scaled to this run's waveforms per launch" if args.mode != "bf16x3" else "see profiles/ for the split kernel",
                         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                         "mma_flops_per_algorithmic_flop": 3 if args.mode == "bf16x3" else 1,
                         "avg_launch_ms": k1_ms, "launches": int(prof_n[0]), "waveforms_per_launch": avg_wf,

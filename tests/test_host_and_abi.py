@@ -173,3 +173,42 @@ def test_vote_allreduce_world_size_2_gloo():
     [p.join(timeout=60) for p in procs]
     want = np.bincount(np.random.default_rng(123).integers(0, K, size=n), minlength=K).tolist()
     assert results[0] == want and results[1] == want
+
+
+def test_philox_keys_are_distinct_per_consumer_and_per_object():
+    """a defender's diffusion noise, the smoothing noise and an attacker's NES probes must not walk the same Philox
+    blocks for equal user seeds; default-seeded objects get their own streams."""
+    from audiopure_b200 import _lib
+    keys = {c: _lib.philox_key(c, 0) for c in ("diffwave", "certify", "nes")}
+    assert len(set(keys.values())) == 3 and all(0 <= k < 2 ** 64 for k in keys.values())
+    assert _lib.philox_key("diffwave", 7) == _lib.philox_key("diffwave", 7) != _lib.philox_key("diffwave", 8)
+    a, b = _lib.philox_key("diffwave", None), _lib.philox_key("diffwave", None)
+    assert a != b
+
+
+def test_unet_structure_matches_the_reference_walk():
+    """synthetic.unet_structure reproduces UNetModel.__init__'s module walk: 446 state-dict tensors for the default configuration
+    (checked key by key against the reference in tests/golden/make_golden_unet.py), a balanced skip-connection stack, 30 ResBlocks
+    and 15 attention blocks."""
+    from audiopure_b200 import synthetic
+    ops, cfg = synthetic.unet_structure()
+    kinds = [k for _, k, _, _ in ops]
+    assert kinds.count("res") == 30 and kinds.count("attn") == 15 and kinds.count("down") == 3 and kinds.count("up") == 3
+    assert kinds.count("push") + 1 == kinds.count("pop") == 16          # conv_in pushes implicitly
+    assert len(synthetic.unet_state_dict(seed=0)) == 446
+    depth = 1
+    for k in kinds:
+        depth += (k == "push") - (k == "pop")
+        assert depth >= 0
+    assert depth == 0
+
+
+def test_spec_and_wave_euler_schedules():
+    from audiopure_b200.diffwave_sde import euler_schedule
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import audiopure_oracle as orc
+    for t in (1, 3, 7, 10):
+        a, b = euler_schedule(t), orc.sde_euler_schedule(t)
+        assert len(a) == len(b) == t and all(float(x[0]) == float(y[0]) and float(x[1]) == float(y[1]) for x, y in zip(a, b))
+    s = orc.spec_sde_schedule(2)
+    assert len(s) == 2 and abs(float(s[0][1]) - 1e-3) < 1e-7

@@ -343,3 +343,75 @@ def test_rev_improved_diffusion_vs_reference(ap, golden_unet):
     assert tuple(logits.shape) == (2, 10) and torch.isfinite(logits).all()
     with pytest.raises(Exception):
         rid(spec.clone().requires_grad_(True))
+
+
+# ------------------------------------------------------------------------------------------------ fused certification front end
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "fp32"])
+def test_smooth_denoise_fused_equals_unfused(ap, diffwave, mode):
+    """ap_diffwave_smooth_denoise (noisy copies built in the init kernel, x0 in k2's epilogue) == ap_smooth_inputs ->
+    one_shot_denoise, bit for bit, with caller-supplied noise and with in-kernel Philox noise (same blocks)."""
+    from audiopure_b200 import _lib
+    lib = _lib.load()
+    diffwave.model.set_mode(mode)
+    diffwave.reverse_timestep = 66
+    B, L, sigma = 5, 4096, 0.5
+    scale = (1 / (1 + sigma ** 2)) ** 0.5
+    x1 = cuda(synthetic.synthetic_waveforms(1, L, seed=3))
+    ab = diffwave.diffusion_hyperparams["Alpha_bar"]
+    a, b = float((1 / ab).sqrt()[65]), float((1 / ab - 1).sqrt()[65])
+    st = _lib.stream_ptr()
+    for z in (cuda(synthetic.host_noise((B, 1, L), 11, 0)), None):
+        zp = z.data_ptr() if z is not None else None
+        x_in = torch.empty(B, 1, L, device="cuda")
+        _lib.check(lib.ap_smooth_inputs(x1.data_ptr(), sigma, scale, zp, 1234, 77, x_in.data_ptr(), B, L, st))
+        want = diffwave.one_shot_denoise(x_in)
+        got = torch.empty(B, 1, L, device="cuda")
+        _lib.check(lib.ap_diffwave_smooth_denoise(diffwave.model._handle, x1.data_ptr(), sigma, scale, zp, 1234, 77, None, 65.0, a, b,
+                                                  got.data_ptr(), B, L, st))
+        assert torch.equal(got, want), float((got - want).abs().max())
+    diffwave.reverse_timestep = 2
+
+
+def test_certify_graph_replay_equals_eager(ap, diffwave):
+    """The CUDA-graph micro-batch (device-resident Philox offset) draws the same noise blocks as the eager path: identical counts,
+    decisions and radii; certify() over two inputs == two single-input calls (the pipelining changes no value)."""
+    diffwave.model.set_mode("bf16")
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=1))
+    tr = ap.sc09_transform()
+    x = cuda(synthetic.synthetic_waveforms(2, 16000, seed=31)) * 0.9
+    y = torch.zeros(2, dtype=torch.int64, device="cuda")
+    res = {}
+    for use_graph in (True, False):
+        rc = ap.RobustCertificate(classifier=rx, transform=tr, denoiser=diffwave, seed=5, use_graph=use_graph, distributed=False)
+        c = rc.smooth_predict(x[:1], num_sampling=150, sigma=0.45, batch_size=64)           # 2 replays + a ragged eager batch
+        yp, r = rc.certify(x, y, sigma=0.45, n_0=20, n=130, batch_size=64)
+        res[use_graph] = (c, yp.cpu(), r.cpu())
+        assert int(c.sum()) == 150
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1]) and torch.equal(res[True][2], res[False][2])
+    rc = ap.RobustCertificate(classifier=rx, transform=tr, denoiser=diffwave, seed=5, distributed=False)
+    rc.smooth_predict(x[:1], num_sampling=150, sigma=0.45, batch_size=64)
+    y0, r0 = rc.certify(x[:1], y[:1], sigma=0.45, n_0=20, n=130, batch_size=64)
+    assert torch.equal(y0.cpu(), res[True][1][:1]) and torch.equal(r0.cpu(), res[True][2][:1])
+    diffwave.reverse_timestep = 2
+
+
+def test_certify_counts_sized_from_classifier_output(ap, diffwave, trained_checkpoints):
+    """the vote vector follows the classifier's output width (4 for RCNN_KWS), not a num_classes default of 10."""
+    diffwave.model.set_mode("bf16")
+    kws = ap.KWSClassifier(trained_checkpoints["kws"])
+    rc = ap.RobustCertificate(classifier=kws, transform=ap.kws_transform(), denoiser=diffwave, seed=1, distributed=False)
+    c = rc.smooth_predict(cuda(synthetic.synthetic_waveforms(1, 16000, seed=4)), num_sampling=24, sigma=0.25, batch_size=16)
+    assert tuple(c.shape) == (4,) and int(c.sum()) == 24
+    diffwave.reverse_timestep = 2
+
+
+@pytest.mark.parametrize("B", [1, 5, 13])
+def test_mel_tensor_core_path_ragged_batches(ap, B, monkeypatch):
+    """k_mel (tcgen05, CTA pairs of 8 waveforms) on batches that are not a multiple of 8 vs the FFMA path."""
+    x = cuda(synthetic.synthetic_waveforms(B, 16000, seed=70 + B))
+    tr = ap.sc09_transform()
+    got = tr(x).clone()
+    monkeypatch.setenv("AP_MEL_FFMA", "1")
+    want = ap.sc09_transform()(x)
+    assert got.shape == want.shape == (B, 1, 32, 32)
+    assert float((got - want).abs().max()) < 1e-3

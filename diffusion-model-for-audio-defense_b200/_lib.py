@@ -53,6 +53,7 @@ SIGNATURES = {
     "ap_last_error": (C.c_char_p, []),
     "ap_version": (_i, []),
     "ap_launch_count": (C.c_ulonglong, []),
+    "ap_alloc_generation": (C.c_ulonglong, []),
     "ap_fold_weight_norm": (_i, [_vp, _vp, _vp, _i, _i]),
     "ap_diffwave_create": (_i, [_PP, C.POINTER(WavenetCfg), _PP, _i, _i]),
     "ap_diffwave_destroy": (None, [_vp]),

@@ -53,6 +53,7 @@ class _Pipeline:
         self.x0 = None            # (batch, 1, L) noisy copies -> denoised copies
         self.offset_dev = None    # int64[1]: Philox block offset of the next micro-batch (advanced by the graph)
         self.votes = None         # int64[K] accumulated by the graph's vote kernel
+        self.generation = None    # ap_alloc_generation() right after the capture: the graph holds raw workspace pointers
 
 
 class RobustCertificate:
@@ -143,8 +144,9 @@ class RobustCertificate:
         mode = getattr(getattr(self.denoiser, "model", None), "mode", None)
         t_star = getattr(self.denoiser, "reverse_timestep", None)
         key = (x.device, L, batch, float(sigma), float(scale), t_star, mode, self.noise)
-        if p.key == key:
-            return p
+        if p.key == key and (p.graph is None or p.generation == self._lib.ap_alloc_generation()):
+            return p            # (a library workspace that moved since the capture -- another batch size, length or mode through
+                                #  the same handles -- invalidates the graph: fall through and capture again)
         p.key, p.graph, p.votes = key, None, None
         p.x1 = torch.empty(1, 1, L, device=x.device, dtype=torch.float32)
         p.x0 = torch.empty(batch, 1, L, device=x.device, dtype=torch.float32)
@@ -160,6 +162,7 @@ class RobustCertificate:
                 self._vote(lg, p)
                 _lib.check(self._lib.ap_u64_add(p.offset_dev.data_ptr(), (batch * L) // 4, _lib.stream_ptr()), "ap_u64_add")
             p.graph = g
+            p.generation = self._lib.ap_alloc_generation()
         return p
 
     def _enqueue_counts(self, x, num_sampling, sigma, batch_size):

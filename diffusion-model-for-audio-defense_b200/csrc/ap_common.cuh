@@ -15,6 +15,9 @@ namespace ap {
 
 extern thread_local std::string g_last_error;
 extern std::atomic<unsigned long long> g_launches;
+// bumped by every device (re)allocation or release of the library: a captured CUDA graph that replays the library's kernels holds
+// raw pointers into its workspaces and must be re-captured when this changes (ap_alloc_generation, certify.py)
+extern std::atomic<unsigned long long> g_alloc_generation;
 
 inline int fail(int code, const char* fmt, ...) {
   char buf[1024];
@@ -59,7 +62,10 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaFree(p);
+      g_alloc_generation.fetch_add(1, std::memory_order_relaxed);
+    }
     p = nullptr;
     bytes = 0;
   }
@@ -68,6 +74,7 @@ struct DevBuf {
     if (n == 0) return cudaSuccess;
     cudaError_t e = cudaMalloc(&p, n);
     if (e == cudaSuccess) bytes = n;
+    g_alloc_generation.fetch_add(1, std::memory_order_relaxed);
     return e;
   }
   cudaError_t upload(const void* host, size_t n) {

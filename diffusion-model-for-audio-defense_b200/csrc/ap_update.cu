@@ -10,6 +10,7 @@ namespace ap {
 
 thread_local std::string g_last_error;
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> g_alloc_generation{0};
 
 int select_device(int device) {
   int n = 0;
@@ -248,6 +249,7 @@ extern "C" {
 const char* ap_last_error(void) { return g_last_error.c_str(); }
 int ap_version(void) { return 100; }
 unsigned long long ap_launch_count(void) { return g_launches.load(); }
+unsigned long long ap_alloc_generation(void) { return g_alloc_generation.load(); }
 
 int ap_fold_weight_norm(const float* g, const float* v, float* w, int cout, int fan_in) {
   AP_REQUIRE(g && v && w && cout > 0 && fan_in > 0, "ap_fold_weight_norm: bad arguments");

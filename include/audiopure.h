@@ -49,6 +49,10 @@ const char* ap_last_error(void);
 int ap_version(void);
 /* number of kernels this library has launched since load (process-wide, all handles); bench.py's gpu_launches */
 unsigned long long ap_launch_count(void);
+/* changes whenever the library allocates or frees device memory (workspaces grow with the batch, the sequence length and the
+ * arithmetic mode): a CUDA graph captured around these entry points holds raw workspace pointers and must be re-captured when
+ * the value differs from the one read right after the capture */
+unsigned long long ap_alloc_generation(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Host helpers (no GPU needed)

@@ -415,3 +415,21 @@ def test_mel_tensor_core_path_ragged_batches(ap, B, monkeypatch):
     want = ap.sc09_transform()(x)
     assert got.shape == want.shape == (B, 1, 32, 32)
     assert float((got - want).abs().max()) < 1e-3
+
+
+def test_certify_graph_survives_a_moved_workspace(ap, sd_full):
+    """A captured micro-batch holds raw pointers into the DiffWave workspace; when another call re-sizes that workspace the graph
+    must be re-captured (ap_alloc_generation), not replayed on freed memory."""
+    dw = ap.create_diffwave_model(None, CONFIG_JSON, reverse_timestep=2, state_dict=sd_full, noise="philox", seed=3, mode="bf16")
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=1))
+    tr = ap.sc09_transform()
+    x = cuda(synthetic.synthetic_waveforms(1, 16000, seed=31)) * 0.9
+    rc = ap.RobustCertificate(classifier=rx, transform=tr, denoiser=dw, seed=5, distributed=False)
+    a = rc.smooth_predict(x, num_sampling=96, sigma=0.45, batch_size=32)
+    dw.reverse_timestep = 2
+    dw(cuda(synthetic.synthetic_waveforms(40, 16000, seed=2)))        # a larger batch: the implicit workspace grows and moves
+    rc2 = ap.RobustCertificate(classifier=rx, transform=tr, denoiser=dw, seed=5, distributed=False)
+    want = rc2.smooth_predict(x, num_sampling=96, sigma=0.45, batch_size=32)
+    rc._offset = 0                                                    # same Philox blocks as the first call
+    b = rc.smooth_predict(x, num_sampling=96, sigma=0.45, batch_size=32)
+    assert torch.equal(a, want) and torch.equal(b, want)

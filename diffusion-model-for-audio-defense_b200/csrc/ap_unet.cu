@@ -221,6 +221,7 @@ struct ap_unet_s {
   size_t arena_floats = 0;
   int cap_B = 0;
   size_t need_per_sample = 0;   // floats
+  bool attn_attr = false;
 };
 
 static int upload_vec(DevBuf& d, const float* p, size_t n) {
@@ -423,10 +424,9 @@ extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int
         if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, qkv, nullptr);
         if (rc == AP_OK) {
           const size_t smem = static_cast<size_t>(2) * T * 64 * sizeof(float);
-          static bool attr = false;
-          if (!attr) {
+          if (!h->attn_attr) {     // per handle, i.e. per device: function attributes belong to the device's context
             AP_CUDA(cudaFuncSetAttribute(unet_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 64 * 4));
-            attr = true;
+            h->attn_attr = true;
           }
           AP_REQUIRE(T <= 256, "ap_unet_eps: attention over more than 256 positions is not supported");
           unet_attn_kernel<64><<<bn * heads, T < 256 ? ((T + 31) / 32) * 32 : 256, smem, st>>>(qkv, av, T, Cc, heads);

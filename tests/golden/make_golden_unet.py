@@ -59,6 +59,23 @@ def main():
     with torch.no_grad(), RandnInjector(5300) as inj:
         out["spec_purified_t2"] = rid(spec.clone()).numpy()
         out["spec_noise_draws"] = np.array(inj.i)
+    # ---- gradients (the reference back-propagates through this UNet: no no_grad on the spectrogram path)
+    for prm in model.parameters():
+        prm.requires_grad_(False)
+    g_eps = torch.from_numpy(synthetic.host_noise((3, 1, 32, 32), 5400, 0))
+    out["unet_g_eps"] = g_eps.numpy()
+    xr = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad(model(xr, torch.tensor([37, 37, 37])), xr, g_eps)
+    out["unet_vjp_t37"] = gx.numpy()
+    for prm in rid.parameters():
+        prm.requires_grad_(False)
+    w = torch.from_numpy(synthetic.host_noise((2, 1, 32, 32), 5500, 0))
+    out["spec_grad_w"] = w.numpy()
+    sr = spec.clone().requires_grad_(True)
+    with RandnInjector(5300):
+        y = rid(sr)
+    (gs,) = torch.autograd.grad((y * w).sum(), sr)
+    out["spec_purified_grad_t2"] = gs.numpy()
     np.savez_compressed(os.path.join(HERE, "reference_golden_unet.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, float(np.abs(v).max()))

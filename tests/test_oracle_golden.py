@@ -399,3 +399,17 @@ def test_spec_sde_oracle_vs_reference_revimproveddiffusion(golden_unet):
     with torch.no_grad():
         y = orc.spec_sde_purify(sd, golden_unet["spec_in"], 2, _noise(5300, n, (2, 1, 32, 32)), ops, cfg).numpy()
     assert rel_l2(y, golden_unet["spec_purified_t2"]) < 1e-5
+
+
+def test_unet_oracle_gradients_vs_reference(golden_unet):
+    """the oracle is differentiable: its autograd gradients through the UNet and through the spectrogram purifier (which, unlike
+    the waveform purifier, the reference does NOT wrap in no_grad) match the reference's"""
+    ops, cfg = synthetic.unet_structure()
+    sd = synthetic.unet_state_dict(seed=0)
+    x = torch.from_numpy(golden_unet["unet_x"]).requires_grad_(True)
+    (gx,) = torch.autograd.grad(orc.unet_forward(sd, x, 37 * torch.ones(3), ops, cfg), x, torch.from_numpy(golden_unet["unet_g_eps"]))
+    assert rel_l2(gx.numpy(), golden_unet["unet_vjp_t37"]) < 1e-4
+    s = torch.from_numpy(golden_unet["spec_in"]).requires_grad_(True)
+    y = orc.spec_sde_purify(sd, s, 2, _noise(5300, int(golden_unet["spec_noise_draws"]), (2, 1, 32, 32)), ops, cfg)
+    (gs,) = torch.autograd.grad((y * torch.from_numpy(golden_unet["spec_grad_w"])).sum(), s)
+    assert rel_l2(gs.numpy(), golden_unet["spec_purified_grad_t2"]) < 1e-4

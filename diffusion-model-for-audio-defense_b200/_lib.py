@@ -89,6 +89,7 @@ SIGNATURES = {
     "ap_unet_destroy": (None, [_vp]),
     "ap_unet_set_mode": (_i, [_vp, _i]),
     "ap_unet_eps": (_i, [_vp, _fp, _f, _fp, _i, _vp]),
+    "ap_unet_eps_vjp": (_i, [_vp, _fp, _f, _fp, _fp, _fp, _i, _vp]),
     "ap_vote_counts": (_i, [_fp, _i, _i, _vp, _i, _vp]),
     "ap_argmax": (_i, [_fp, _i, _i, _vp, _vp]),
     "ap_nes_noise_blocks": (_u64, [_i, _i, _i]),

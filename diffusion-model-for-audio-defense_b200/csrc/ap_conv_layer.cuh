@@ -132,4 +132,20 @@ struct ConvLayer {
   }
 };
 
+// Data-gradient twin of a convolution: g_x = conv(g_y [zero-upsampled by the stride], W^T rotated 180 degrees), stride 1,
+// padding k - 1 - pad, same groups.  `L` must have kept its folded weights (keep_host).
+inline int init_dgrad(ConvLayer& T, const ConvLayer& L, bool want_tc = false) {
+  if (L.wf_host.empty()) return fail(AP_ERR_STATE, "init_dgrad: the forward layer did not keep its weights");
+  const int Cg = L.Cg, Ng = L.Ng, kh = L.kh, kw = L.kw;
+  std::vector<float> wt(static_cast<size_t>(L.Cin) * Ng * kh * kw);
+  for (int g = 0; g < L.groups; ++g)
+    for (int c = 0; c < Cg; ++c)
+      for (int n = 0; n < Ng; ++n)
+        for (int r = 0; r < kh; ++r)
+          for (int q = 0; q < kw; ++q)
+            wt[((static_cast<size_t>(g * Cg + c) * Ng + n) * kh + r) * kw + q] =
+                L.wf_host[((static_cast<size_t>(g * Ng + n) * Cg + c) * kh + (kh - 1 - r)) * kw + (kw - 1 - q)];
+  return T.init(L.Cout, L.Cin, kh, kw, 1, kw - 1 - L.pad, L.groups, wt.data(), nullptr, nullptr, nullptr, nullptr, nullptr, want_tc);
+}
+
 }  // namespace ap

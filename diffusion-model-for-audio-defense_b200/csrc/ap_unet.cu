@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <memory>
+#include <unordered_map>
 #include <vector>
 
 #include "ap_common.cuh"
@@ -187,6 +188,226 @@ __global__ void __launch_bounds__(256) concat_kernel(const float4* __restrict__ 
 }
 // NCHW (C == 1: same memory as NHWC) in / out is handled by the caller; nothing to do here.
 
+// ------------------------------------------------------------------------------------------------ backward kernels (VJP wrt x)
+// The reference back-propagates through this UNet (improved_diffusion_sde.py:104-105 calls the model without no_grad), so a
+// white-box attack on Diffusion-Spec needs g_x = (d eps / d x)^T g_eps.  Chain rule over the recorded forward (activations are
+// still in the arena): convolution data-gradient twins (transposed, 180-degree-rotated weights), and the kernels below.
+
+// backward of gn_kernel: y = act(z), z = ((x - mean) rstd gamma + beta) [(1 + scale) + shift]; statistics recomputed from x.
+//   dxhat = g_y act'(z) [(1 + scale)] gamma ;  g_x = rstd (dxhat - mean(dxhat) - xhat mean(dxhat xhat))   over the (sample, group)
+__global__ void __launch_bounds__(256) gn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     const float* __restrict__ scale_shift, int HW, int C, int cpg, int act, int accumulate) {
+  const int b = blockIdx.x / 32, g = blockIdx.x % 32;
+  const size_t off = static_cast<size_t>(b) * HW * C + g * cpg;
+  const float* xb = x + off;
+  const float* gb = gy + off;
+  float* ob = gx + off;
+  const int n = HW * cpg;
+  __shared__ float red[2][8];
+  __shared__ float s_a, s_b;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  auto block_sum2 = [&](float v0, float v1, float& o0, float& o1) {
+    for (int o = 16; o; o >>= 1) v0 += __shfl_xor_sync(0xffffffffu, v0, o), v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+    __syncthreads();
+    if (lane == 0) red[0][wid] = v0, red[1][wid] = v1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int i = 0; i < 8; ++i) t0 += red[0][i], t1 += red[1][i];
+      s_a = t0, s_b = t1;
+    }
+    __syncthreads();
+    o0 = s_a, o1 = s_b;
+  };
+  float s = 0.f, dummy;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += xb[static_cast<size_t>(i / cpg) * C + (i % cpg)];
+  float mean;
+  block_sum2(s, 0.f, mean, dummy);
+  mean /= n;
+  float v = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = xb[static_cast<size_t>(i / cpg) * C + (i % cpg)] - mean;
+    v = fmaf(d, d, v);
+  }
+  float var;
+  block_sum2(v, 0.f, var, dummy);
+  const float rstd = rsqrtf(var / n + 1e-5f);
+  auto dxhat_of = [&](int i, float& xhat) -> float {
+    const int c = i % cpg, ch = g * cpg + c;
+    const size_t idx = static_cast<size_t>(i / cpg) * C + c;
+    xhat = (xb[idx] - mean) * rstd;
+    float z = xhat * gamma[ch] + beta[ch];
+    float dz = gb[idx];
+    float mul = gamma[ch];
+    if (scale_shift) {
+      z = z * (1.f + scale_shift[ch]) + scale_shift[C + ch];
+      mul *= 1.f + scale_shift[ch];
+    }
+    if (act) {
+      const float sg = 1.f / (1.f + __expf(-z));
+      dz *= sg * (1.f + z * (1.f - sg));                    // d silu(z) / dz
+    }
+    return dz * mul;
+  };
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float xhat;
+    const float d = dxhat_of(i, xhat);
+    s1 += d, s2 = fmaf(d, xhat, s2);
+  }
+  float m1, m2;
+  block_sum2(s1, s2, m1, m2);
+  m1 /= n, m2 /= n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float xhat;
+    const float d = dxhat_of(i, xhat);
+    const size_t idx = static_cast<size_t>(i / cpg) * C + (i % cpg);
+    const float r = rstd * (d - m1 - xhat * m2);
+    ob[idx] = accumulate ? ob[idx] + r : r;
+  }
+}
+
+// backward of unet_attn_kernel.  One CTA per (sample, head), one thread per position.  Phase A (thread = query t): softmax row,
+// D_t = sum_s P g_P, g_S = P (g_P - D_t) -> g_q; P and g_S of the head go to global scratch [T][T].  Phase B (thread = key s):
+// g_k[s] = sc^2 sum_t g_S[t][s] q_t, g_v[s] = sum_t P[t][s] g_o[t].
+template <int CH> __global__ void __launch_bounds__(256) unet_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g_out,
+                                                                             float* __restrict__ g_qkv, float* __restrict__ Pm,
+                                                                             float* __restrict__ Gs, int T, int C, int heads) {
+  extern __shared__ float kv[];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const float* base = qkv + static_cast<size_t>(b) * T * 3 * C + h * 3 * CH;
+  const float* gob = g_out + static_cast<size_t>(b) * T * C + h * CH;
+  float* gq = g_qkv + static_cast<size_t>(b) * T * 3 * C + h * 3 * CH;
+  float* P = Pm + static_cast<size_t>(blockIdx.x) * T * T;
+  float* G = Gs + static_cast<size_t>(blockIdx.x) * T * T;
+  float* ks = kv;
+  float* vs = kv + static_cast<size_t>(T) * CH;
+  for (int i = threadIdx.x; i < T * CH; i += blockDim.x) {
+    const int s = i / CH, c = i - s * CH;
+    ks[i] = base[static_cast<size_t>(s) * 3 * C + CH + c];
+    vs[i] = base[static_cast<size_t>(s) * 3 * C + 2 * CH + c];
+  }
+  __syncthreads();
+  const float sc = rsqrtf(sqrtf(static_cast<float>(CH))), sc2 = sc * sc;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float q[CH], go[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) q[c] = base[static_cast<size_t>(t) * 3 * C + c], go[c] = gob[static_cast<size_t>(t) * C + c];
+    float m = -INFINITY, l = 0.f;
+    for (int s = 0; s < T; ++s) {
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) d = fmaf(q[c], ks[s * CH + c], d);
+      d *= sc2;
+      const float mn = fmaxf(m, d);
+      l = l * __expf(m - mn) + __expf(d - mn);
+      m = mn;
+    }
+    const float inv = 1.f / l;
+    float D = 0.f;
+    for (int s = 0; s < T; ++s) {
+      float d = 0.f, gp = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) d = fmaf(q[c], ks[s * CH + c], d), gp = fmaf(go[c], vs[s * CH + c], gp);
+      const float pw = __expf(d * sc2 - m) * inv;
+      P[static_cast<size_t>(t) * T + s] = pw;
+      G[static_cast<size_t>(t) * T + s] = gp;
+      D = fmaf(pw, gp, D);
+    }
+    float acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+    for (int s = 0; s < T; ++s) {
+      const float gs = P[static_cast<size_t>(t) * T + s] * (G[static_cast<size_t>(t) * T + s] - D);
+      G[static_cast<size_t>(t) * T + s] = gs;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = fmaf(gs, ks[s * CH + c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) gq[static_cast<size_t>(t) * 3 * C + c] = acc[c] * sc2;
+  }
+  __syncthreads();     // P and G of this head (written by this CTA) are complete
+  for (int s = threadIdx.x; s < T; s += blockDim.x) {
+    float gk[CH], gv[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) gk[c] = 0.f, gv[c] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float gs = G[static_cast<size_t>(t) * T + s], pw = P[static_cast<size_t>(t) * T + s];
+      const float* qt = base + static_cast<size_t>(t) * 3 * C;
+      const float* got = gob + static_cast<size_t>(t) * C;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) gk[c] = fmaf(gs, qt[c], gk[c]), gv[c] = fmaf(pw, got[c], gv[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      gq[static_cast<size_t>(s) * 3 * C + CH + c] = gk[c] * sc2;
+      gq[static_cast<size_t>(s) * 3 * C + 2 * CH + c] = gv[c];
+    }
+  }
+}
+
+// backward of nearest_up2_kernel: g_in[b][i][j][c] (+)= sum of the 2 x 2 block of g_out
+__global__ void __launch_bounds__(256) up2_bwd_kernel(const float4* __restrict__ g_out, float4* __restrict__ g_in, int B, int H, int W,
+                                                      int C4, int accumulate) {
+  const long long total = static_cast<long long>(B) * H * W * C4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4);
+    long long t = i / C4;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int hh = static_cast<int>(t % H);
+    const long long b = t / H;
+    float4 a = accumulate ? g_in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const float4 v = g_out[((b * 2 * H + 2 * hh + (d >> 1)) * 2 * W + 2 * w + (d & 1)) * C4 + c];
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    g_in[i] = a;
+  }
+}
+// backward of concat_kernel: g_a (+)= g_out[..., :C1], g_s (+)= g_out[..., C1:]
+__global__ void __launch_bounds__(256) split_bwd_kernel(const float4* __restrict__ g_out, float4* __restrict__ g_a, float4* __restrict__ g_s,
+                                                        long long pixels, int C1_4, int C2_4, int acc_a, int acc_s) {
+  const int Ct = C1_4 + C2_4;
+  const long long total = pixels * Ct;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Ct);
+    const long long px = i / Ct;
+    const float4 v = g_out[i];
+    float4* dst = c < C1_4 ? g_a + px * C1_4 + c : g_s + px * C2_4 + (c - C1_4);
+    if (c < C1_4 ? acc_a : acc_s) {
+      float4 o = *dst;
+      o.x += v.x, o.y += v.y, o.z += v.z, o.w += v.w;
+      *dst = o;
+    } else {
+      *dst = v;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] += src[i];
+}
+// up[b][2i][2j][c] = g[b][i][j][c], zero elsewhere (the gradient of a stride-2 convolution before its stride-1 data-gradient twin)
+__global__ void __launch_bounds__(256) zero_up2_kernel(const float4* __restrict__ g, float4* __restrict__ up, int B, int Ho, int Wo, int C4) {
+  const long long total = static_cast<long long>(B) * (2 * Ho) * (2 * Wo) * C4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4);
+    long long t = i / C4;
+    const int ow = static_cast<int>(t % (2 * Wo));
+    t /= 2 * Wo;
+    const int oh = static_cast<int>(t % (2 * Ho));
+    const long long b = t / (2 * Ho);
+    up[i] = ((oh | ow) & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : g[((b * Ho + (oh >> 1)) * Wo + (ow >> 1)) * C4 + c];
+  }
+}
+
 static int grid_for_n(long long n, int threads) {
   long long b = ceil_div_ll(n, threads);
   const long long cap = static_cast<long long>(num_sms()) * 8;
@@ -201,6 +422,7 @@ enum { OP_CONV_IN = 0, OP_RES = 1, OP_ATTN = 2, OP_PUSH = 3, OP_POP = 4, OP_DOWN
 
 namespace {
 struct UOp {
+  UOp() { c1.keep_host = c2.keep_host = skip.keep_host = true; }   // the backward pass builds data-gradient twins from the host copy
   int kind = 0, cin = 0, cout = 0;
   ConvLayer c1, c2, skip;      // res: in conv, out conv, skip 1x1 | attn: qkv (c1), proj (c2) | conv_in / down / up / out: c1
   bool has_skip = false;
@@ -222,6 +444,12 @@ struct ap_unet_s {
   int cap_B = 0;
   size_t need_per_sample = 0;   // floats
   bool attn_attr = false;
+  // backward pass: gradient arena, data-gradient twins of every convolution, scratch for the recomputed eps
+  DevBuf garena, eps_scratch;
+  size_t garena_floats = 0, need_grad_per_sample = 0;
+  int gcap_B = 0;
+  bool twins_ready = false;
+  std::unordered_map<const ConvLayer*, std::unique_ptr<ConvLayer>> twins;
 };
 
 static int upload_vec(DevBuf& d, const float* p, size_t n) {
@@ -328,6 +556,16 @@ extern "C" int ap_unet_create(ap_unet_t* out, const ap_unet_cfg* cfg, const int*
       }
     }
     h->need_per_sample = need + 64;
+    // gradients: one buffer per activation (<= the forward's arena), zero-upsampled gradients of the three stride-2 convolutions,
+    // and the attention scratch (P and g_S: 2 x heads x T x T per attention block)
+    size_t gneed = need;
+    int Hh = cfg->image_size;
+    for (auto& op : h->ops) {
+      if (op->kind == OP_DOWN) gneed += static_cast<size_t>(Hh) * Hh * op->cout, Hh /= 2;
+      else if (op->kind == OP_UP) Hh *= 2;
+      else if (op->kind == OP_ATTN) gneed += static_cast<size_t>(2) * cfg->num_heads * Hh * Hh * Hh * Hh;
+    }
+    h->need_grad_per_sample = gneed + 64;
   }
   *out = h.release();
   return AP_OK;
@@ -340,134 +578,330 @@ extern "C" int ap_unet_set_mode(ap_unet_t h, int mode) {
   return AP_OK;
 }
 
-// eps[b] = UNet(x[b], t) with the same discrete step t for every sample (RevVPSDE.rvpsde_fn passes one step per Euler step,
-// improved_diffusion_sde.py:104-105).  x, eps: device fp32 (B, 1, S, S).
-extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int B, void* stream) {
-  AP_REQUIRE(h && x && eps && B > 0, "ap_unet_eps: bad arguments");
-  AP_CUDA(cudaSetDevice(h->device));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int mc = h->cfg.model_channels, ted = 4 * mc, S = h->cfg.image_size, heads = h->cfg.num_heads;
-  // activations: sub-batches that keep the arena below ~8 GB
-  const size_t per = h->need_per_sample;
-  int chunk = static_cast<int>(std::max<size_t>(1, (static_cast<size_t>(2) << 30) / per));   // floats: 2 Gi floats = 8 GB
-  if (chunk > B) chunk = B;
-  if (h->cap_B < chunk) {
-    h->cap_B = 0;
-    AP_CUDA(h->arena.alloc(per * chunk * sizeof(float)));
-    h->cap_B = chunk, h->arena_floats = per * chunk;
-  }
+// ---- one recorded operation of a forward pass (the activations stay in the arena until the chunk is done)
+namespace {
+enum { T_CONV = 0, T_GN = 1, T_ATTN = 2, T_UP2 = 3, T_CONCAT = 4 };
+struct TapeEntry {
+  int kind = 0;
+  const ConvLayer* L = nullptr;       // T_CONV
+  const float* in = nullptr;
+  float* out = nullptr;
+  const float* res = nullptr;         // T_CONV: tensor added in the epilogue; T_CONCAT: the second input
+  int Hin = 0, Cin = 0, Cout = 0;     // spatial size of `in`; channels of in / out (T_CONCAT: C1 = Cin, C2 = Cout - Cin)
+  const DevBuf* gamma = nullptr;      // T_GN
+  const DevBuf* beta = nullptr;
+  const float* ss = nullptr;
+  int act = 0;
+};
+}  // namespace
+
+static int unet_time_path(ap_unet_t h, float t, cudaStream_t st) {
+  const int mc = h->cfg.model_channels, ted = 4 * mc;
   unet_time_embed_kernel<<<1, 512, sizeof(float) * (mc + ted), st>>>(t, mc, h->te_w0.as<float>(), h->te_b0.as<float>(),
                                                                      h->te_w2.as<float>(), h->te_b2.as<float>(), h->emb_silu.as<float>());
   AP_LAUNCH_CHECK();
   unet_emb_proj_kernel<<<ceil_div(h->ss_rows * 32, 256), 256, 0, st>>>(h->emb_silu.as<float>(), ted, h->emb_w.as<float>(),
                                                                        h->emb_b.as<float>(), h->ss_rows, h->ss.as<float>());
   AP_LAUNCH_CHECK();
-  for (int b0 = 0; b0 < B; b0 += chunk) {
-    const int bn = std::min(chunk, B - b0);
-    float* arena = h->arena.as<float>();
-    size_t top = 0;
-    auto alloc = [&](size_t n) {
-      float* p = arena + top;
-      top += (n + 3) & ~static_cast<size_t>(3);
-      return p;
-    };
-    struct Act { float* p; int H, C; };
-    std::vector<Act> stack;
-    Act cur{const_cast<float*>(x) + static_cast<size_t>(b0) * S * S, S, 1};
-    auto gn = [&](const Act& a, float* out, const DevBuf& g, const DevBuf& b, const float* ss, int act) -> int {
-      gn_kernel<<<bn * 32, 256, 0, st>>>(a.p, out, g.as<float>(), b.as<float>(), ss, a.H * a.H, a.C, a.C / 32, act,
-                                         h->mode == AP_MODE_TF32);
-      AP_LAUNCH_CHECK();
-      return AP_OK;
-    };
-    auto conv = [&](const ConvLayer& L, const float* in, int H, float* out, const float* res) -> int {
-      if (h->mode == AP_MODE_TF32 && L.has_tc && conv_tc_supported(L.Cin, L.Cout, L.groups, H, H, L.kh, L.kw, L.stride, L.pad)) {
-        ConvTcBinding bnd;
-        int rcb = L.tc.bind(&bnd, in, bn, H, H, out, res, 0, 0);
-        return rcb != AP_OK ? rcb : L.tc.run(bnd, st);
-      }
-      return L.run(in, bn, H, H, out, res, 0, st);
-    };
-    int rc = AP_OK;
-    for (auto& opp : h->ops) {
-      UOp& op = *opp;
-      const size_t px = static_cast<size_t>(bn) * cur.H * cur.H;
-      if (op.kind == OP_CONV_IN) {
-        float* o = alloc(px * op.cout);
-        rc = conv(op.c1, cur.p, cur.H, o, nullptr);
-        cur = {o, cur.H, op.cout};
-        stack.push_back(cur);                              // hs.append(h) of input_blocks[0] (unet.py:483-485)
-      } else if (op.kind == OP_RES) {
-        float* n1 = alloc(px * op.cin);
-        float* y1 = alloc(px * op.cout);
-        float* n2 = alloc(px * op.cout);
-        float* o = alloc(px * op.cout);
-        rc = gn(cur, n1, op.g1, op.b1, nullptr, 1);                                             // in_layers: GN, SiLU
-        if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, y1, nullptr);              //            conv
-        Act a1{y1, cur.H, op.cout};
-        if (rc == AP_OK) rc = gn(a1, n2, op.g2, op.b2, h->ss.as<float>() + op.ss_off, 1);       // out_layers[0] * (1 + scale) + shift, SiLU
-        const float* res = cur.p;
-        if (rc == AP_OK && op.has_skip) {
-          float* sk = alloc(px * op.cout);
-          rc = conv(op.skip, cur.p, cur.H, sk, nullptr);
-          res = sk;
-        }
-        if (rc == AP_OK) rc = conv(op.c2, n2, cur.H, o, res);                   // conv + skip_connection(x)
-        cur = {o, cur.H, op.cout};
-      } else if (op.kind == OP_ATTN) {
-        const int T = cur.H * cur.H, Cc = cur.C;
-        float* n1 = alloc(px * Cc);
-        float* qkv = alloc(px * 3 * Cc);
-        float* av = alloc(px * Cc);
-        float* o = alloc(px * Cc);
-        rc = gn(cur, n1, op.g1, op.b1, nullptr, 0);
-        if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, qkv, nullptr);
-        if (rc == AP_OK) {
-          const size_t smem = static_cast<size_t>(2) * T * 64 * sizeof(float);
-          if (!h->attn_attr) {     // per handle, i.e. per device: function attributes belong to the device's context
-            AP_CUDA(cudaFuncSetAttribute(unet_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 64 * 4));
-            h->attn_attr = true;
-          }
-          AP_REQUIRE(T <= 256, "ap_unet_eps: attention over more than 256 positions is not supported");
-          unet_attn_kernel<64><<<bn * heads, T < 256 ? ((T + 31) / 32) * 32 : 256, smem, st>>>(qkv, av, T, Cc, heads);
-          AP_LAUNCH_CHECK();
-          rc = conv(op.c2, av, cur.H, o, cur.p);                                // proj_out + x
-        }
-        cur = {o, cur.H, Cc};
-      } else if (op.kind == OP_PUSH) {
-        stack.push_back(cur);
-      } else if (op.kind == OP_POP) {
-        AP_REQUIRE(!stack.empty(), "ap_unet_eps: skip stack underflow");
-        const Act s = stack.back();
-        stack.pop_back();
-        AP_REQUIRE(s.H == cur.H && s.C + cur.C == op.cout, "ap_unet_eps: skip connection shape mismatch");
-        float* o = alloc(px * op.cout);
-        concat_kernel<<<grid_for_n(static_cast<long long>(px) * op.cout / 4, 256), 256, 0, st>>>(
-            reinterpret_cast<const float4*>(cur.p), reinterpret_cast<const float4*>(s.p), reinterpret_cast<float4*>(o),
-            static_cast<long long>(px), cur.C / 4, s.C / 4);
-        AP_LAUNCH_CHECK();
-        cur = {o, cur.H, op.cout};
-      } else if (op.kind == OP_DOWN) {
-        const int Ho = cur.H / 2;
-        float* o = alloc(static_cast<size_t>(bn) * Ho * Ho * op.cout);
-        rc = conv(op.c1, cur.p, cur.H, o, nullptr);
-        cur = {o, Ho, op.cout};
-      } else if (op.kind == OP_UP) {
-        float* up = alloc(4 * px * op.cin);
-        float* o = alloc(4 * px * op.cout);
-        nearest_up2_kernel<<<grid_for_n(static_cast<long long>(px) * op.cin, 256), 256, 0, st>>>(
-            reinterpret_cast<const float4*>(cur.p), reinterpret_cast<float4*>(up), bn, cur.H, cur.H, op.cin / 4);
-        AP_LAUNCH_CHECK();
-        rc = conv(op.c1, up, 2 * cur.H, o, nullptr);
-        cur = {o, 2 * cur.H, op.cout};
-      } else if (op.kind == OP_OUT) {
-        float* n1 = alloc(px * op.cin);
-        rc = gn(cur, n1, op.g1, op.b1, nullptr, 1);
-        if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, eps + static_cast<size_t>(b0) * S * S, nullptr);
-      }
-      if (rc != AP_OK) return rc;
-      if (top > h->arena_floats) return fail(AP_ERR_STATE, "ap_unet_eps: activation arena overflow (%zu > %zu floats)", top, h->arena_floats);
+  return AP_OK;
+}
+static int unet_chunk_size(ap_unet_t h, int B, bool with_backward) {
+  const size_t per = h->need_per_sample + (with_backward ? h->need_grad_per_sample : 0);
+  int chunk = static_cast<int>(std::max<size_t>(1, (static_cast<size_t>(2) << 30) / per));   // 2 Gi floats = 8 GB
+  return chunk > B ? B : chunk;
+}
+static int unet_conv(ap_unet_t h, const ConvLayer& L, const float* in, int bn, int H, float* out, const float* res, cudaStream_t st) {
+  if (h->mode == AP_MODE_TF32 && L.has_tc && conv_tc_supported(L.Cin, L.Cout, L.groups, H, H, L.kh, L.kw, L.stride, L.pad)) {
+    ConvTcBinding bnd;
+    int rcb = L.tc.bind(&bnd, in, bn, H, H, out, res, 0, 0);
+    return rcb != AP_OK ? rcb : L.tc.run(bnd, st);
+  }
+  return L.run(in, bn, H, H, out, res, 0, st);
+}
+
+// forward of `bn` samples starting at x (NHWC == NCHW for one channel); records the operations when `tape` is given
+static int unet_forward_chunk(ap_unet_t h, const float* x, float* eps, int bn, cudaStream_t st, std::vector<TapeEntry>* tape) {
+  const int S = h->cfg.image_size, heads = h->cfg.num_heads;
+  float* arena = h->arena.as<float>();
+  size_t top = 0;
+  auto alloc = [&](size_t n) {
+    float* p = arena + top;
+    top += (n + 3) & ~static_cast<size_t>(3);
+    return p;
+  };
+  struct Act { float* p; int H, C; };
+  std::vector<Act> stack;
+  Act cur{const_cast<float*>(x), S, 1};
+  auto gn = [&](const Act& a, float* out, const DevBuf& g, const DevBuf& b, const float* ss, int act) -> int {
+    gn_kernel<<<bn * 32, 256, 0, st>>>(a.p, out, g.as<float>(), b.as<float>(), ss, a.H * a.H, a.C, a.C / 32, act,
+                                       h->mode == AP_MODE_TF32);
+    AP_LAUNCH_CHECK();
+    if (tape) {
+      TapeEntry e;
+      e.kind = T_GN, e.in = a.p, e.out = out, e.Hin = a.H, e.Cin = e.Cout = a.C, e.gamma = &g, e.beta = &b, e.ss = ss, e.act = act;
+      tape->push_back(e);
     }
+    return AP_OK;
+  };
+  auto conv = [&](const ConvLayer& L, const float* in, int H, float* out, const float* res) -> int {
+    if (tape) {
+      TapeEntry e;
+      e.kind = T_CONV, e.L = &L, e.in = in, e.out = out, e.res = res, e.Hin = H, e.Cin = L.Cin, e.Cout = L.Cout;
+      tape->push_back(e);
+    }
+    return unet_conv(h, L, in, bn, H, out, res, st);
+  };
+  int rc = AP_OK;
+  for (auto& opp : h->ops) {
+    UOp& op = *opp;
+    const size_t px = static_cast<size_t>(bn) * cur.H * cur.H;
+    if (op.kind == OP_CONV_IN) {
+      float* o = alloc(px * op.cout);
+      rc = conv(op.c1, cur.p, cur.H, o, nullptr);
+      cur = {o, cur.H, op.cout};
+      stack.push_back(cur);                              // hs.append(h) of input_blocks[0] (unet.py:483-485)
+    } else if (op.kind == OP_RES) {
+      float* n1 = alloc(px * op.cin);
+      float* y1 = alloc(px * op.cout);
+      float* n2 = alloc(px * op.cout);
+      float* o = alloc(px * op.cout);
+      rc = gn(cur, n1, op.g1, op.b1, nullptr, 1);                                             // in_layers: GN, SiLU
+      if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, y1, nullptr);                              //            conv
+      Act a1{y1, cur.H, op.cout};
+      if (rc == AP_OK) rc = gn(a1, n2, op.g2, op.b2, h->ss.as<float>() + op.ss_off, 1);       // out_layers[0] * (1 + scale) + shift, SiLU
+      const float* res = cur.p;
+      if (rc == AP_OK && op.has_skip) {
+        float* sk = alloc(px * op.cout);
+        rc = conv(op.skip, cur.p, cur.H, sk, nullptr);
+        res = sk;
+      }
+      if (rc == AP_OK) rc = conv(op.c2, n2, cur.H, o, res);                                   // conv + skip_connection(x)
+      cur = {o, cur.H, op.cout};
+    } else if (op.kind == OP_ATTN) {
+      const int T = cur.H * cur.H, Cc = cur.C;
+      float* n1 = alloc(px * Cc);
+      float* qkv = alloc(px * 3 * Cc);
+      float* av = alloc(px * Cc);
+      float* o = alloc(px * Cc);
+      rc = gn(cur, n1, op.g1, op.b1, nullptr, 0);
+      if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, qkv, nullptr);
+      if (rc == AP_OK) {
+        const size_t smem = static_cast<size_t>(2) * T * 64 * sizeof(float);
+        if (!h->attn_attr) {     // per handle, i.e. per device: function attributes belong to the device's context
+          AP_CUDA(cudaFuncSetAttribute(unet_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 64 * 4));
+          AP_CUDA(cudaFuncSetAttribute(unet_attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 64 * 4));
+          h->attn_attr = true;
+        }
+        AP_REQUIRE(T <= 256, "ap_unet_eps: attention over more than 256 positions is not supported");
+        unet_attn_kernel<64><<<bn * heads, T < 256 ? ((T + 31) / 32) * 32 : 256, smem, st>>>(qkv, av, T, Cc, heads);
+        AP_LAUNCH_CHECK();
+        if (tape) {
+          TapeEntry e;
+          e.kind = T_ATTN, e.in = qkv, e.out = av, e.Hin = cur.H, e.Cin = 3 * Cc, e.Cout = Cc;
+          tape->push_back(e);
+        }
+        rc = conv(op.c2, av, cur.H, o, cur.p);                                                // proj_out + x
+      }
+      cur = {o, cur.H, Cc};
+    } else if (op.kind == OP_PUSH) {
+      stack.push_back(cur);
+    } else if (op.kind == OP_POP) {
+      AP_REQUIRE(!stack.empty(), "ap_unet_eps: skip stack underflow");
+      const Act s = stack.back();
+      stack.pop_back();
+      AP_REQUIRE(s.H == cur.H && s.C + cur.C == op.cout, "ap_unet_eps: skip connection shape mismatch");
+      float* o = alloc(px * op.cout);
+      concat_kernel<<<grid_for_n(static_cast<long long>(px) * op.cout / 4, 256), 256, 0, st>>>(
+          reinterpret_cast<const float4*>(cur.p), reinterpret_cast<const float4*>(s.p), reinterpret_cast<float4*>(o),
+          static_cast<long long>(px), cur.C / 4, s.C / 4);
+      AP_LAUNCH_CHECK();
+      if (tape) {
+        TapeEntry e;
+        e.kind = T_CONCAT, e.in = cur.p, e.res = s.p, e.out = o, e.Hin = cur.H, e.Cin = cur.C, e.Cout = op.cout;
+        tape->push_back(e);
+      }
+      cur = {o, cur.H, op.cout};
+    } else if (op.kind == OP_DOWN) {
+      const int Ho = cur.H / 2;
+      float* o = alloc(static_cast<size_t>(bn) * Ho * Ho * op.cout);
+      rc = conv(op.c1, cur.p, cur.H, o, nullptr);
+      cur = {o, Ho, op.cout};
+    } else if (op.kind == OP_UP) {
+      float* up = alloc(4 * px * op.cin);
+      float* o = alloc(4 * px * op.cout);
+      nearest_up2_kernel<<<grid_for_n(static_cast<long long>(px) * op.cin, 256), 256, 0, st>>>(
+          reinterpret_cast<const float4*>(cur.p), reinterpret_cast<float4*>(up), bn, cur.H, cur.H, op.cin / 4);
+      AP_LAUNCH_CHECK();
+      if (tape) {
+        TapeEntry e;
+        e.kind = T_UP2, e.in = cur.p, e.out = up, e.Hin = cur.H, e.Cin = e.Cout = op.cin;
+        tape->push_back(e);
+      }
+      rc = conv(op.c1, up, 2 * cur.H, o, nullptr);
+      cur = {o, 2 * cur.H, op.cout};
+    } else if (op.kind == OP_OUT) {
+      float* n1 = alloc(px * op.cin);
+      rc = gn(cur, n1, op.g1, op.b1, nullptr, 1);
+      if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, eps, nullptr);
+    }
+    if (rc != AP_OK) return rc;
+    if (top > h->arena_floats) return fail(AP_ERR_STATE, "ap_unet_eps: activation arena overflow (%zu > %zu floats)", top, h->arena_floats);
   }
   return AP_OK;
+}
+
+static int unet_reserve(ap_unet_t h, int chunk, bool with_backward) {
+  if (h->cap_B < chunk) {
+    h->cap_B = 0;
+    AP_CUDA(h->arena.alloc(h->need_per_sample * chunk * sizeof(float)));
+    h->cap_B = chunk, h->arena_floats = h->need_per_sample * chunk;
+  }
+  if (with_backward && h->gcap_B < chunk) {
+    h->gcap_B = 0;
+    AP_CUDA(h->garena.alloc(h->need_grad_per_sample * chunk * sizeof(float)));
+    h->gcap_B = chunk, h->garena_floats = h->need_grad_per_sample * chunk;
+  }
+  return AP_OK;
+}
+
+// eps[b] = UNet(x[b], t) with the same discrete step t for every sample (RevVPSDE.rvpsde_fn passes one step per Euler step,
+// improved_diffusion_sde.py:104-105).  x, eps: device fp32 (B, 1, S, S).
+extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int B, void* stream) {
+  AP_REQUIRE(h && x && eps && B > 0, "ap_unet_eps: bad arguments");
+  AP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int S = h->cfg.image_size;
+  const int chunk = unet_chunk_size(h, B, false);          // activations: sub-batches that keep the arena below ~8 GB
+  int rc = unet_reserve(h, chunk, false);
+  if (rc == AP_OK) rc = unet_time_path(h, t, st);
+  for (int b0 = 0; rc == AP_OK && b0 < B; b0 += chunk)
+    rc = unet_forward_chunk(h, x + static_cast<size_t>(b0) * S * S, eps + static_cast<size_t>(b0) * S * S, std::min(chunk, B - b0), st,
+                            nullptr);
+  return rc;
+}
+
+// g_x = (d eps / d x)^T g_eps at (x, t): what autograd computes through UNetModel.forward when a white-box attack back-propagates
+// through RevImprovedDiffusion.  The forward is recomputed with its operations recorded, then walked in reverse.  eps_out may be
+// null.  x, g_eps, g_x, eps_out: device fp32 (B, 1, S, S).
+extern "C" int ap_unet_eps_vjp(ap_unet_t h, const float* x, float t, const float* g_eps, float* g_x, float* eps_out, int B, void* stream) {
+  AP_REQUIRE(h && x && g_eps && g_x && B > 0, "ap_unet_eps_vjp: bad arguments");
+  AP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int S = h->cfg.image_size, heads = h->cfg.num_heads;
+  if (!h->twins_ready) {      // data-gradient twins of every convolution (transposed, rotated weights), built on first use
+    for (auto& opp : h->ops)
+      for (ConvLayer* L : {&opp->c1, &opp->c2, &opp->skip}) {
+        if (L->Cin == 0) continue;
+        auto tw = std::unique_ptr<ConvLayer>(new ConvLayer());
+        int rc = init_dgrad(*tw, *L, true);
+        if (rc != AP_OK) return rc;
+        h->twins[L] = std::move(tw);
+      }
+    h->twins_ready = true;
+  }
+  const int chunk = unet_chunk_size(h, B, true);
+  int rc = unet_reserve(h, chunk, true);
+  if (rc == AP_OK && h->eps_scratch.bytes < static_cast<size_t>(chunk) * S * S * sizeof(float))
+    AP_CUDA(h->eps_scratch.alloc(static_cast<size_t>(chunk) * S * S * sizeof(float)));
+  if (rc == AP_OK) rc = unet_time_path(h, t, st);
+  for (int b0 = 0; rc == AP_OK && b0 < B; b0 += chunk) {
+    const int bn = std::min(chunk, B - b0);
+    const size_t o0 = static_cast<size_t>(b0) * S * S;
+    float* eps = eps_out ? eps_out + o0 : h->eps_scratch.as<float>();
+    std::vector<TapeEntry> tape;
+    rc = unet_forward_chunk(h, x + o0, eps, bn, st, &tape);
+    if (rc != AP_OK) break;
+    // ---- reverse walk
+    float* garena = h->garena.as<float>();
+    size_t gtop = 0;
+    auto galloc = [&](size_t n) {
+      float* p = garena + gtop;
+      gtop += (n + 3) & ~static_cast<size_t>(3);
+      return p;
+    };
+    std::unordered_map<const float*, float*> grad;     // activation -> its gradient buffer (present = holds a value)
+    grad[eps] = const_cast<float*>(g_eps) + o0;
+    const float* x_in = x + o0;
+    // destination for the gradient of `act`: (buffer, whether it already holds a value to accumulate into)
+    auto dest = [&](const float* act, size_t n, bool& had) -> float* {
+      auto it = grad.find(act);
+      if (it != grad.end()) {
+        had = true;
+        return it->second;
+      }
+      had = false;
+      float* p = act == x_in ? g_x + o0 : galloc(n);
+      grad[act] = p;
+      return p;
+    };
+    for (size_t ei = tape.size(); rc == AP_OK && ei-- > 0;) {
+      const TapeEntry& e = tape[ei];
+      auto go = grad.find(e.out);
+      if (go == grad.end()) continue;                  // no gradient reaches this output
+      float* g_out = go->second;
+      const size_t px_in = static_cast<size_t>(bn) * e.Hin * e.Hin;
+      bool had = false;
+      if (e.kind == T_CONV) {
+        const ConvLayer& L = *e.L;
+        const ConvLayer& T = *h->twins.at(e.L);
+        const int Ho = (e.Hin + 2 * L.pad - L.kh) / L.stride + 1;
+        const float* src = g_out;
+        int Hs = Ho;
+        if (L.stride == 2) {
+          float* up = galloc(static_cast<size_t>(bn) * (2 * Ho) * (2 * Ho) * L.Cout);
+          zero_up2_kernel<<<grid_for_n(static_cast<long long>(bn) * 4 * Ho * Ho * L.Cout / 4, 256), 256, 0, st>>>(
+              reinterpret_cast<const float4*>(g_out), reinterpret_cast<float4*>(up), bn, Ho, Ho, L.Cout / 4);
+          AP_LAUNCH_CHECK();
+          src = up, Hs = 2 * Ho;
+        }
+        float* dst = dest(e.in, px_in * L.Cin, had);
+        rc = unet_conv(h, T, src, bn, Hs, dst, had ? dst : nullptr, st);
+        if (rc == AP_OK && e.res) {                    // the tensor added in the epilogue receives g_out unchanged
+          auto ir = grad.find(e.res);
+          if (ir == grad.end()) {
+            if (e.res == x_in) {                       // (cannot happen: x is never a residual)
+              AP_CUDA(cudaMemcpyAsync(g_x + o0, g_out, sizeof(float) * bn * Ho * Ho * L.Cout, cudaMemcpyDeviceToDevice, st));
+              grad[e.res] = g_x + o0;
+            } else {
+              grad[e.res] = g_out;                     // alias: g_out is not needed after this entry
+            }
+          } else {
+            add_inplace_kernel<<<grid_for_n(static_cast<long long>(bn) * Ho * Ho * L.Cout, 256), 256, 0, st>>>(
+                ir->second, g_out, static_cast<long long>(bn) * Ho * Ho * L.Cout);
+            AP_LAUNCH_CHECK();
+          }
+        }
+      } else if (e.kind == T_GN) {
+        float* dst = dest(e.in, px_in * e.Cin, had);
+        gn_bwd_kernel<<<bn * 32, 256, 0, st>>>(e.in, g_out, dst, e.gamma->as<float>(), e.beta->as<float>(), e.ss, e.Hin * e.Hin, e.Cin,
+                                               e.Cin / 32, e.act, had ? 1 : 0);
+        AP_LAUNCH_CHECK();
+      } else if (e.kind == T_ATTN) {
+        const int T = e.Hin * e.Hin, Cc = e.Cout;
+        float* dst = dest(e.in, px_in * e.Cin, had);   // qkv has a single consumer: written in full
+        float* Pm = galloc(static_cast<size_t>(bn) * heads * T * T);
+        float* Gs = galloc(static_cast<size_t>(bn) * heads * T * T);
+        unet_attn_bwd_kernel<64><<<bn * heads, T < 256 ? ((T + 31) / 32) * 32 : 256, static_cast<size_t>(2) * T * 64 * sizeof(float), st>>>(
+            e.in, g_out, dst, Pm, Gs, T, Cc, heads);
+        AP_LAUNCH_CHECK();
+      } else if (e.kind == T_UP2) {
+        float* dst = dest(e.in, px_in * e.Cin, had);
+        up2_bwd_kernel<<<grid_for_n(static_cast<long long>(px_in) * e.Cin / 4, 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(g_out), reinterpret_cast<float4*>(dst), bn, e.Hin, e.Hin, e.Cin / 4, had ? 1 : 0);
+        AP_LAUNCH_CHECK();
+      } else if (e.kind == T_CONCAT) {
+        bool had_s = false;
+        float* da = dest(e.in, px_in * e.Cin, had);
+        float* ds = dest(e.res, px_in * (e.Cout - e.Cin), had_s);
+        split_bwd_kernel<<<grid_for_n(static_cast<long long>(px_in) * e.Cout / 4, 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(g_out), reinterpret_cast<float4*>(da), reinterpret_cast<float4*>(ds),
+            static_cast<long long>(px_in), e.Cin / 4, (e.Cout - e.Cin) / 4, had ? 1 : 0, had_s ? 1 : 0);
+        AP_LAUNCH_CHECK();
+      }
+      if (gtop > h->garena_floats)
+        return fail(AP_ERR_STATE, "ap_unet_eps_vjp: gradient arena overflow (%zu > %zu floats)", gtop, h->garena_floats);
+    }
+    if (rc == AP_OK && grad.find(x_in) == grad.end()) AP_CUDA(cudaMemsetAsync(g_x + o0, 0, sizeof(float) * bn * S * S, st));
+  }
+  return rc;
 }

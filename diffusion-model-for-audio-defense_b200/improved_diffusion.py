@@ -4,9 +4,10 @@ RevImprovedDiffusion :142-226; selected at adaptive_attack_eval.py:134-137 with 
 ``RevImprovedDiffusion(args)`` standardises the dB mel-spectrogram to [-1, 1], diffuses it to level ``args.t`` and integrates the
 reverse VP-SDE with the UNet's eps (torchsde's fixed-step Euler-Maruyama, default dt = 1e-3: one coefficient row per step, built
 on the host with the reference's float32 arithmetic and consumed by the fused ``ap_sde_step`` kernel), then maps back to dB.
-The UNet (``UNet``: UNetModel of improved_diffusion/unet.py) runs on the CUDA kernels of csrc/ap_unet.cu.  Inference only: the
-reference differentiates through this UNet (no ``no_grad`` here, unlike the waveform purifier); an input that requires grad
-raises instead of silently dropping the gradient.
+The UNet (``UNet``: UNetModel of improved_diffusion/unet.py) runs on the CUDA kernels of csrc/ap_unet.cu.  The reference
+differentiates THROUGH this UNet (no ``no_grad`` on the spectrogram path, unlike the waveform purifier's compute_eps_t), so an input
+that requires grad takes the autograd route: the affine Euler steps in torch ops, the network through ``_UNetEps`` whose backward is
+``ap_unet_eps_vjp`` (the input gradient; the weights are constants of a white-box attack).
 """
 from __future__ import annotations
 
@@ -38,6 +39,23 @@ def _np32(t) -> np.ndarray:
     if isinstance(t, torch.Tensor):
         t = t.detach().cpu().numpy()
     return np.ascontiguousarray(np.asarray(t, dtype=np.float32))
+
+
+class _UNetEps(torch.autograd.Function):
+    """eps = UNet(x, t) with the input gradient on the CUDA kernels (``ap_unet_eps_vjp``).  Only x is kept; the backward call
+    recomputes the forward with its operations recorded."""
+
+    @staticmethod
+    def forward(ctx, x, net, t):
+        xd = x.detach().to(torch.float32).contiguous()
+        ctx.net, ctx.t = net, float(t)
+        ctx.save_for_backward(xd)
+        return net.eps(xd, float(t))
+
+    @staticmethod
+    def backward(ctx, g):
+        (xd,) = ctx.saved_tensors
+        return ctx.net.eps_vjp(xd, ctx.t, g), None, None
 
 
 class UNet(torch.nn.Module):
@@ -91,7 +109,9 @@ class UNet(torch.nn.Module):
         if not x.is_cuda:
             raise _lib.AudioPureError("UNet: input must be a CUDA tensor (there is no CPU path)")
         if x.requires_grad and torch.is_grad_enabled():
-            raise _lib.AudioPureError("UNet: inference-only (the spectrogram purifier has no backward pass); detach the input")
+            if out is not None:
+                raise _lib.AudioPureError("UNet.eps: out= cannot be combined with an input that requires grad")
+            return _UNetEps.apply(x, self, float(t))
         _lib.check_device(x, self.device_index, "UNet")
         x = x.detach().to(torch.float32).contiguous()
         S = self.config["image_size"]
@@ -103,17 +123,37 @@ class UNet(torch.nn.Module):
                        "ap_unet_eps")
         return out
 
+    def eps_vjp(self, x: torch.Tensor, t: float, g_eps: torch.Tensor, return_eps: bool = False):
+        """g_x = (d eps / d x)^T g_eps at (x, t) -- torch.autograd.grad(UNetModel(x, t), x, g_eps) of the reference."""
+        if not (x.is_cuda and g_eps.is_cuda):
+            raise _lib.AudioPureError("UNet: inputs must be CUDA tensors (there is no CPU path)")
+        _lib.check_device(x, self.device_index, "UNet")
+        _lib.check_device(g_eps, self.device_index, "UNet")
+        x = x.detach().to(torch.float32).contiguous()
+        g = g_eps.detach().to(torch.float32).contiguous()
+        S = self.config["image_size"]
+        assert x.ndim == 4 and tuple(x.shape[1:]) == (1, S, S) and g.shape == x.shape, (tuple(x.shape), tuple(g.shape))
+        gx = torch.empty_like(x)
+        eps = torch.empty_like(x) if return_eps else None
+        with torch.cuda.device(x.device):
+            _lib.check(self._lib.ap_unet_eps_vjp(self._handle, x.data_ptr(), float(t), g.data_ptr(), gx.data_ptr(),
+                                                 eps.data_ptr() if return_eps else None, x.shape[0], _lib.stream_ptr()),
+                       "ap_unet_eps_vjp")
+        return (gx, eps) if return_eps else gx
+
     def forward(self, x, timesteps, y=None):
         assert y is None, "the spectrogram UNet is unconditional"
         steps = torch.as_tensor(timesteps).reshape(-1).to(torch.float32).cpu()
         uniq = torch.unique(steps)
         if uniq.numel() == 1:
             return self.eps(x, float(uniq[0]))
-        out = torch.empty_like(x, dtype=torch.float32)
+        parts, order = [], []
         for tv in uniq.tolist():
             idx = torch.nonzero(steps == tv).reshape(-1).to(x.device)
-            out[idx] = self.eps(x[idx], tv)
-        return out
+            parts.append(self.eps(x[idx], tv))
+            order.append(idx)
+        inv = torch.argsort(torch.cat(order))
+        return torch.cat(parts, dim=0)[inv]
 
     def __del__(self):
         try:
@@ -190,7 +230,7 @@ class RevImprovedDiffusion(torch.nn.Module):
         assert isinstance(img, torch.Tensor)
         assert img.ndim == 4, img.ndim
         if img.requires_grad and torch.is_grad_enabled():
-            raise _lib.AudioPureError("RevImprovedDiffusion: inference-only (no backward pass through the spectrogram UNet)")
+            return self._image_editing_sample_autograd(img.to(self.device))
         img = img.to(self.device).detach().to(torch.float32).contiguous()
         B, n = img.shape[0], int(np.prod(img.shape[1:]))
         x0 = melspec_standardize(img)
@@ -220,6 +260,43 @@ class RevImprovedDiffusion(torch.nn.Module):
             x0 = x
             xs.append(melspec_inv_standardize(x0))
             # the reference feeds the de-standardised spectrogram of round k back into round k + 1 (improved_diffusion_sde.py:204-205)
+            x0 = xs[-1]
+        return torch.cat(xs, dim=0)
+
+    def _randn(self, shape, device) -> torch.Tensor:
+        z, zp, seed, off = self._noise_args(shape, device)
+        if z is not None:
+            return z
+        zero = torch.zeros(tuple(shape), device=device, dtype=torch.float32)
+        out = torch.empty_like(zero)
+        n = int(np.prod(shape))
+        with torch.cuda.device(device):   # 0 * 0 + 1 * z: the Philox counters the fused kernels would consume for this draw
+            _lib.check(self._lib.ap_diffuse(zero.data_ptr(), 0.0, 1.0, None, seed, off, out.data_ptr(), shape[0], n // shape[0],
+                                            _lib.stream_ptr()), "ap_diffuse")
+        return out
+
+    def _image_editing_sample_autograd(self, img):
+        """The same chain for an input that requires grad (the reference differentiates it with torchsde.sdeint_adjoint,
+        improved_diffusion_sde.py:198-202, THROUGH the UNet): discretise-then-differentiate, the affine step in torch ops and the
+        network through ``_UNetEps``.  Same noise draws, in the same order, as the inference route."""
+        xs = []
+        x0 = melspec_standardize(img.to(torch.float32))
+        for _ in range(self.args.sample_step):
+            level = self.args.t
+            if self.args.rand_t:
+                level = self.args.t + np.random.randint(-self.args.t_delta, self.args.t_delta)
+            a = (1 - self.betas).cumprod(dim=0)
+            sa, sb = float(a[level - 1].sqrt()), float((1.0 - a[level - 1]).sqrt())
+            e = torch.randn_like(x0) if self.noise == "torch" else self._randn(x0.shape, x0.device)
+            x = sa * x0 + sb * e
+            for s, ds in spec_euler_schedule(self.args.t):
+                d, c = self.step_coefficients(s, ds)
+                eps = self.model.eps(x, float(d))
+                x = x + (0.5 * c.beta * x - c.diff2 * eps / c.sqrt_1mab) * c.dt
+                z = self._randn(x.shape, x.device)
+                if c.g != 0.0:
+                    x = x + c.g * c.sqrt_dt * z
+            xs.append(melspec_inv_standardize(x))
             x0 = xs[-1]
         return torch.cat(xs, dim=0)
 

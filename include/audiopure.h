@@ -257,6 +257,12 @@ void ap_unet_destroy(ap_unet_t h);
 int ap_unet_set_mode(ap_unet_t h, int mode);
 /* eps = model(x, timesteps = t for every row).  x, eps: device fp32 (B, 1, image_size, image_size). */
 int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int B, void* stream);
+/* Vector-Jacobian product wrt the input: g_x = (d eps / d x)^T g_eps -- what autograd computes through UNetModel.forward when a
+ * white-box attack back-propagates through RevImprovedDiffusion (the reference calls the model without no_grad,
+ * improved_diffusion_sde.py:104-105).  The forward is recomputed with its operations recorded and walked in reverse (GroupNorm /
+ * SiLU / attention / up-sampling backward kernels, data-gradient twins of every convolution).  eps_out: optional, the network
+ * output at x.  All device fp32 (B, 1, image_size, image_size). */
+int ap_unet_eps_vjp(ap_unet_t h, const float* x, float t, const float* g_eps, float* g_x, float* eps_out, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Votes (replaces the argmax + per-class .sum().item() loop of smooth_predict, certified_robust.py:59-67)

@@ -341,8 +341,42 @@ def test_rev_improved_diffusion_vs_reference(ap, golden_unet):
     with RandnInjector(5301):
         logits = system(wav)
     assert tuple(logits.shape) == (2, 10) and torch.isfinite(logits).all()
-    with pytest.raises(Exception):
-        rid(spec.clone().requires_grad_(True))
+
+
+def test_unet_input_gradient_vs_reference(ap, golden_unet):
+    """ap_unet_eps_vjp == torch.autograd.grad(UNetModel(x, 37), x, g_eps) of the unmodified reference (fp32 mode; tf32 within the
+    tensor-core convolutions' precision), chunk-independent."""
+    net = ap.UNet(synthetic.unet_state_dict(seed=0))
+    x, g = cuda(golden_unet["unet_x"]), cuda(golden_unet["unet_g_eps"])
+    gx_tf32 = net.eps_vjp(x, 37, g)
+    err_tf32 = rel_l2(gx_tf32, golden_unet["unet_vjp_t37"])
+    net.set_mode("fp32")
+    gx, eps = net.eps_vjp(x, 37, g, return_eps=True)
+    err, err_eps = rel_l2(gx, golden_unet["unet_vjp_t37"]), rel_l2(eps, golden_unet["unet_eps_t37"])
+    print(f"UNet input gradient t=37: rel-L2 fp32 {err:.3e} (eps {err_eps:.3e}), tf32 {err_tf32:.3e}")
+    assert err < 5e-5 and err_eps < 2e-5 and err_tf32 < 1e-2
+    xr = x.clone().requires_grad_(True)            # through torch.autograd
+    (ga,) = torch.autograd.grad(net(xr, torch.tensor([37, 37, 37])), xr, g)
+    assert torch.equal(ga, gx)
+    big = net.eps_vjp(cuda(np.tile(golden_unet["unet_x"], (11, 1, 1, 1))), 37, cuda(np.tile(golden_unet["unet_g_eps"], (11, 1, 1, 1))))
+    assert rel_l2(big[30:33], golden_unet["unet_vjp_t37"]) < 5e-5
+
+
+def test_rev_improved_diffusion_gradient_vs_reference(ap, golden_unet):
+    """The white-box gradient through Diffusion-Spec: d <w, purified> / d spec with the reference's noise, t* = 2 -- through the
+    UNet, as the reference's autograd does (improved_diffusion_sde.py:104-105 has no no_grad)."""
+    args = argparse.Namespace(ddpm_path=None, t=2, score_type="guided_diffusion", rand_t=False, t_delta=15, use_bm=False, sample_step=1)
+    rid = ap.RevImprovedDiffusion(args, state_dict=synthetic.unet_state_dict(seed=0), noise="torch")
+    rid.model.set_mode("fp32")
+    spec = cuda(golden_unet["spec_in"]).requires_grad_(True)
+    w = cuda(golden_unet["spec_grad_w"])
+    with RandnInjector(5300):
+        y = rid(spec)
+    err_y = rel_l2(y.detach(), golden_unet["spec_purified_t2"])
+    (gs,) = torch.autograd.grad((y * w).sum(), spec)
+    err = rel_l2(gs, golden_unet["spec_purified_grad_t2"])
+    print(f"Diffusion-Spec t*=2 gradient: rel-L2 {err:.3e} (forward {err_y:.3e})")
+    assert err_y < 1e-5 and err < 5e-5
 
 
 # ------------------------------------------------------------------------------------------------ fused certification front end

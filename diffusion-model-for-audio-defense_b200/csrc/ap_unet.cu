@@ -83,6 +83,404 @@ __global__ void __launch_bounds__(256) gn_kernel(const float* __restrict__ x, fl
   }
 }
 
+// GroupNorm with the (sample, group-chunk) tile resident in shared memory: one HBM read, one write.  A CTA owns `gpc` consecutive
+// groups = Cc = gpc * cpg contiguous channels (>= 32 B per pixel, whole sectors); thread = (pixel row p0, float4 column j) with
+// blockDim.x a multiple of q = Cc / 4, so a thread's group is fixed.  Sums are reduced in a fixed order (no atomics): results are
+// reproducible run to run.  Same two-pass statistics and epilogue as gn_kernel.
+struct GnTile {
+  int q, j, p0, pstep, gl;
+  __device__ GnTile(int Cc, int cpg) {
+    q = Cc >> 2, j = threadIdx.x % q, p0 = threadIdx.x / q, pstep = blockDim.x / q, gl = (4 * j) / cpg;
+  }
+  // per-group sums of v over the CTA: part [blockDim.x] scratch, res [8]
+  __device__ void reduce(float v, float* part, float* res, int cpg, int gpc) const {
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int rows = pstep; rows > 1;) {
+      const int half = (rows + 1) >> 1;
+      if (p0 + half < rows) part[threadIdx.x] += part[threadIdx.x + half * q];
+      rows = half;
+      __syncthreads();
+    }
+    if (threadIdx.x < gpc) {
+      float t = 0.f;
+      for (int jj = threadIdx.x * (cpg >> 2); jj < (threadIdx.x + 1) * (cpg >> 2); ++jj) t += part[jj];
+      res[threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+};
+__device__ __forceinline__ float4 gn_affine(float4 xh, int ch, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            const float* __restrict__ ss, int C, float4* mul_out) {
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + ch), be = *reinterpret_cast<const float4*>(beta + ch);
+  float4 z = make_float4(xh.x * ga.x + be.x, xh.y * ga.y + be.y, xh.z * ga.z + be.z, xh.w * ga.w + be.w);
+  float4 mul = ga;
+  if (ss) {
+    const float4 sc = *reinterpret_cast<const float4*>(ss + ch), sh = *reinterpret_cast<const float4*>(ss + C + ch);
+    z = make_float4(z.x * (1.f + sc.x) + sh.x, z.y * (1.f + sc.y) + sh.y, z.z * (1.f + sc.z) + sh.z, z.w * (1.f + sc.w) + sh.w);
+    mul = make_float4(mul.x * (1.f + sc.x), mul.y * (1.f + sc.y), mul.z * (1.f + sc.z), mul.w * (1.f + sc.w));
+  }
+  if (mul_out) *mul_out = mul;
+  return z;
+}
+__device__ __forceinline__ float round_tf32_f(float y) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(y));
+  return __uint_as_float(r);
+}
+__global__ void __launch_bounds__(256) gn_tile_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ scale_shift, int HW, int C,
+                                                      int cpg, int gpc, int act, int round_tf32) {
+  extern __shared__ float4 gn_sm[];                 // tile [HW][q] | part [blockDim.x] floats
+  __shared__ float res[8];
+  const int chunks = 32 / gpc, b = blockIdx.x / chunks, Cc = gpc * cpg, c0 = (blockIdx.x % chunks) * Cc;
+  const GnTile tl(Cc, cpg);
+  float* part = reinterpret_cast<float*>(gn_sm + static_cast<size_t>(HW) * tl.q);
+  const float4* xb = reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * HW * C + c0);
+  float4* ob = reinterpret_cast<float4*>(out + static_cast<size_t>(b) * HW * C + c0);
+  const int C4 = C >> 2, n = HW * cpg;
+  float s = 0.f;
+  for (int p = tl.p0; p < HW; p += tl.pstep) {
+    const float4 v = xb[static_cast<size_t>(p) * C4 + tl.j];
+    gn_sm[p * tl.q + tl.j] = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  tl.reduce(s, part, res, cpg, gpc);
+  const float mean = res[tl.gl] / n;
+  float vv = 0.f;
+  for (int p = tl.p0; p < HW; p += tl.pstep) {
+    const float4 v = gn_sm[p * tl.q + tl.j];
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    vv += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+  }
+  __syncthreads();                                  // every thread has read res (mean) before it is overwritten
+  tl.reduce(vv, part, res, cpg, gpc);
+  const float rstd = rsqrtf(res[tl.gl] / n + 1e-5f);
+  const int ch = c0 + 4 * tl.j;
+  for (int p = tl.p0; p < HW; p += tl.pstep) {
+    const float4 v = gn_sm[p * tl.q + tl.j];
+    float4 y = gn_affine(make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd), ch, gamma, beta,
+                         scale_shift, C, nullptr);
+    if (act) y = make_float4(silu_f(y.x), silu_f(y.y), silu_f(y.z), silu_f(y.w));
+    if (round_tf32) y = make_float4(round_tf32_f(y.x), round_tf32_f(y.y), round_tf32_f(y.z), round_tf32_f(y.w));
+    ob[static_cast<size_t>(p) * C4 + tl.j] = y;
+  }
+}
+// backward of the same: x-hat and d x-hat tiles in shared memory, g_y read once.
+__global__ void __launch_bounds__(256) gn_bwd_tile_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ scale_shift, int HW, int C, int cpg, int gpc, int act,
+                                                          int accumulate) {
+  extern __shared__ float4 gn_sm[];                 // x-hat [HW][q] | d x-hat [HW][q] | part [blockDim.x]
+  __shared__ float res[8], res2[8];
+  const int chunks = 32 / gpc, b = blockIdx.x / chunks, Cc = gpc * cpg, c0 = (blockIdx.x % chunks) * Cc;
+  const GnTile tl(Cc, cpg);
+  float4* xs = gn_sm;
+  float4* ds = gn_sm + static_cast<size_t>(HW) * tl.q;
+  float* part = reinterpret_cast<float*>(ds + static_cast<size_t>(HW) * tl.q);
+  const size_t off = static_cast<size_t>(b) * HW * C + c0;
+  const float4* xb = reinterpret_cast<const float4*>(x + off);
+  const float4* gb = reinterpret_cast<const float4*>(gy + off);
+  float4* ob = reinterpret_cast<float4*>(gx + off);
+  const int C4 = C >> 2, n = HW * cpg;
+  float s = 0.f;
+  for (int p = tl.p0; p < HW; p += tl.pstep) {
+    const float4 v = xb[static_cast<size_t>(p) * C4 + tl.j];
+    xs[p * tl.q + tl.j] = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  tl.reduce(s, part, res, cpg, gpc);
+  const float mean = res[tl.gl] / n;
+  float vv = 0.f;
+  for (int p = tl.p0; p < HW; p += tl.pstep) {
+    const float4 v = xs[p * tl.q + tl.j];
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    vv += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+  }
+  __syncthreads();
+  tl.reduce(vv, part, res, cpg, gpc);
+  const float rstd = rsqrtf(res[tl.gl] / n + 1e-5f);
+  const int ch = c0 + 4 * tl.j;
+  float s1 = 0.f, s2 = 0.f;
+  for (int p = tl.p0; p < HW; p += tl.pstep) {
+    const float4 v = xs[p * tl.q + tl.j];
+    const float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+    float4 mul;
+    const float4 z = gn_affine(xh, ch, gamma, beta, scale_shift, C, &mul);
+    float4 d = gb[static_cast<size_t>(p) * C4 + tl.j];
+    if (act) {
+      auto dsilu = [](float zz) {
+        const float sg = 1.f / (1.f + __expf(-zz));
+        return sg * (1.f + zz * (1.f - sg));
+      };
+      d = make_float4(d.x * dsilu(z.x), d.y * dsilu(z.y), d.z * dsilu(z.z), d.w * dsilu(z.w));
+    }
+    d = make_float4(d.x * mul.x, d.y * mul.y, d.z * mul.z, d.w * mul.w);
+    xs[p * tl.q + tl.j] = xh;
+    ds[p * tl.q + tl.j] = d;
+    s1 += (d.x + d.y) + (d.z + d.w);
+    s2 += fmaf(d.x, xh.x, d.y * xh.y) + fmaf(d.z, xh.z, d.w * xh.w);
+  }
+  __syncthreads();
+  tl.reduce(s1, part, res, cpg, gpc);
+  tl.reduce(s2, part, res2, cpg, gpc);
+  const float m1 = res[tl.gl] / n, m2 = res2[tl.gl] / n;
+  for (int p = tl.p0; p < HW; p += tl.pstep) {
+    const float4 xh = xs[p * tl.q + tl.j], d = ds[p * tl.q + tl.j];
+    float4 r = make_float4(rstd * (d.x - m1 - xh.x * m2), rstd * (d.y - m1 - xh.y * m2), rstd * (d.z - m1 - xh.z * m2),
+                           rstd * (d.w - m1 - xh.w * m2));
+    if (accumulate) {
+      const float4 o = ob[static_cast<size_t>(p) * C4 + tl.j];
+      r = make_float4(r.x + o.x, r.y + o.y, r.z + o.z, r.w + o.w);
+    }
+    ob[static_cast<size_t>(p) * C4 + tl.j] = r;
+  }
+}
+// groups per CTA for a tile budget: the largest power of two (<= 8) whose `tiles` tiles fit `budget` bytes; 0 = not even one group
+static int gn_groups_per_cta(int HW, int cpg, int tiles, size_t budget) {
+  if (cpg % 4 != 0) return 0;
+  for (int gpc = 8; gpc >= 1; gpc >>= 1)
+    if (static_cast<size_t>(HW) * gpc * cpg * sizeof(float) * tiles <= budget) return gpc;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ attention on the tensor cores
+// (tf32 mode.)  mma.sync m16n8k8 tf32, fp32 accumulation; a warp owns 16 rows (queries, or keys in the key-major backward phase) and
+// walks the other dimension in chunks of NB * 8 columns: C = A . M^T ("nt": scores) and C += P . M ("nn": P in the accumulator
+// layout is fed back as the A operand through a fixed permutation of the k slots -- slot t <-> column 2t, slot t + 4 <-> column
+// 2t + 1 -- applied to the rows of M instead of shuffling registers).  K / V (or Q / g_o) of the head sit in shared memory as tf32
+// with a row stride of 68 words: both access patterns are bank-conflict free.
+constexpr int ATT_LD = 68;
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A fragments of rows r0 .. r0 + 15, 64 channels, of a row-major fp32 matrix (row stride `stride` floats), times `scale`
+__device__ __forceinline__ void att_load_a(uint32_t (&a)[8][4], const float* __restrict__ base, size_t stride, int r0, int lane, float scale) {
+  const int g = lane >> 2, t = lane & 3;
+  const float* lo = base + static_cast<size_t>(r0 + g) * stride;
+  const float* hi = lo + 8 * stride;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    a[ks][0] = to_tf32(lo[8 * ks + t] * scale), a[ks][1] = to_tf32(hi[8 * ks + t] * scale);
+    a[ks][2] = to_tf32(lo[8 * ks + t + 4] * scale), a[ks][3] = to_tf32(hi[8 * ks + t + 4] * scale);
+  }
+}
+template <int NB> __device__ __forceinline__ void att_mma_nt(float (&c)[NB][4], const uint32_t (&a)[8][4], const uint32_t* __restrict__ M,
+                                                             int col0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    const uint32_t* row = M + (col0 + nb * 8 + g) * ATT_LD + t;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) mma_tf32(c[nb], a[ks], row[8 * ks], row[8 * ks + 4]);
+  }
+}
+template <int NB> __device__ __forceinline__ void att_mma_nn(float (&c)[8][4], const float (&p)[NB][4], const uint32_t* __restrict__ M,
+                                                             int k0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kb = 0; kb < NB; ++kb) {
+    const uint32_t a[4] = {to_tf32(p[kb][0]), to_tf32(p[kb][2]), to_tf32(p[kb][1]), to_tf32(p[kb][3])};
+    const uint32_t* r0 = M + (k0 + kb * 8 + 2 * t) * ATT_LD + g;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) mma_tf32(c[nb], a, r0[nb * 8], r0[ATT_LD + nb * 8]);
+  }
+}
+// rows [0, T) x 64 channels of a row-major fp32 matrix -> shared memory as tf32 (stride ATT_LD)
+__device__ __forceinline__ void att_stage(uint32_t* __restrict__ dst, const float* __restrict__ src, size_t stride, int T) {
+  for (int i = threadIdx.x; i < T * 16; i += blockDim.x) {
+    const int s = i >> 4, c4 = (i & 15) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + static_cast<size_t>(s) * stride + c4);
+    *reinterpret_cast<uint4*>(dst + s * ATT_LD + c4) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+  }
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
+// forward: grid (B heads, ceil(T / 128)), one warp per 16 queries.  lse (optional, [B heads][T]): log2-domain log-sum-exp of the
+// scaled scores, kept for the backward pass.
+__global__ void __launch_bounds__(256) unet_attn_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ lse,
+                                                            int T, int C, int heads) {
+  extern __shared__ uint32_t att_sm[];              // K [T][68] | V [T][68]
+  constexpr int NB = 8;
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const float* base = qkv + static_cast<size_t>(b) * T * 3 * C + h * 192;
+  uint32_t* Ks = att_sm;
+  uint32_t* Vs = att_sm + T * ATT_LD;
+  att_stage(Ks, base + 64, 3 * static_cast<size_t>(C), T);
+  att_stage(Vs, base + 128, 3 * static_cast<size_t>(C), T);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, r0 = blockIdx.y * 128 + (threadIdx.x >> 5) * 16;
+  if (r0 >= T) return;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t qa[8][4];
+  att_load_a(qa, base, 3 * static_cast<size_t>(C), r0, lane, 0.125f * kLog2e);      // 1 / sqrt(64): q and k each carry 64^-1/4
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, o[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+  for (int k0 = 0; k0 < T; k0 += NB * 8) {
+    float s[NB][4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+    att_mma_nt<NB>(s, qa, Ks, k0, lane);
+    float x0 = -INFINITY, x1 = -INFINITY;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) x0 = fmaxf(x0, fmaxf(s[nb][0], s[nb][1])), x1 = fmaxf(x1, fmaxf(s[nb][2], s[nb][3]));
+    const float n0 = fmaxf(m0, quad_max(x0)), n1 = fmaxf(m1, quad_max(x1));
+    const float c0 = ex2_approx(m0 - n0), c1 = ex2_approx(m1 - n1);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      s[nb][0] = ex2_approx(s[nb][0] - n0), s[nb][1] = ex2_approx(s[nb][1] - n0);
+      s[nb][2] = ex2_approx(s[nb][2] - n1), s[nb][3] = ex2_approx(s[nb][3] - n1);
+      a0 += s[nb][0] + s[nb][1], a1 += s[nb][2] + s[nb][3];
+    }
+    l0 = l0 * c0 + a0, l1 = l1 * c1 + a1, m0 = n0, m1 = n1;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) o[nb][0] *= c0, o[nb][1] *= c0, o[nb][2] *= c1, o[nb][3] *= c1;
+    att_mma_nn<NB>(o, s, Vs, k0, lane);
+  }
+  l0 = quad_sum(l0), l1 = quad_sum(l1);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  float* olo = out + (static_cast<size_t>(b) * T + r0 + g) * C + h * 64 + 2 * t;
+  float* ohi = olo + 8 * static_cast<size_t>(C);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    *reinterpret_cast<float2*>(olo + nb * 8) = make_float2(o[nb][0] * i0, o[nb][1] * i0);
+    *reinterpret_cast<float2*>(ohi + nb * 8) = make_float2(o[nb][2] * i1, o[nb][3] * i1);
+  }
+  if (lse && t == 0) {
+    lse[static_cast<size_t>(bh) * T + r0 + g] = m0 + log2f(l0);
+    lse[static_cast<size_t>(bh) * T + r0 + g + 8] = m1 + log2f(l1);
+  }
+}
+
+// backward: grid (B heads, 2 ceil(T / 128)).  blockIdx.y < nblk: query-major phase -- P = 2^(S - lse), g_P = g_o V^T,
+// g_S = P (g_P - D), D = rowsum(g_o o); g_q = g_S K / 8.  Otherwise key-major phase on the transposed problem: g_v = P^T g_o,
+// g_k = g_S^T Q / 8.  No atomics, no T x T scratch: each phase recomputes the scores it needs from the stored log-sum-exp.
+__global__ void __launch_bounds__(256) unet_attn_mma_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o_fwd,
+                                                                const float* __restrict__ lse, const float* __restrict__ g_out,
+                                                                float* __restrict__ g_qkv, int T, int C, int heads) {
+  extern __shared__ uint32_t att_sm[];              // two [T][68] operand tiles | lse [T] | D [T]
+  constexpr int NB = 4;
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads, nblk = gridDim.y >> 1;
+  const bool key_major = static_cast<int>(blockIdx.y) >= nblk;
+  const size_t qs = 3 * static_cast<size_t>(C);
+  const float* base = qkv + static_cast<size_t>(b) * T * qs + h * 192;
+  const float* gob = g_out + static_cast<size_t>(b) * T * C + h * 64;
+  const float* ofb = o_fwd + static_cast<size_t>(b) * T * C + h * 64;
+  float* gq = g_qkv + static_cast<size_t>(b) * T * qs + h * 192;
+  uint32_t* M0 = att_sm;
+  uint32_t* M1 = att_sm + T * ATT_LD;
+  float* Ls = reinterpret_cast<float*>(att_sm + 2 * T * ATT_LD);
+  float* Ds = Ls + T;
+  if (!key_major) {
+    att_stage(M0, base + 64, qs, T);                // K
+    att_stage(M1, base + 128, qs, T);               // V
+  } else {
+    att_stage(M0, base, qs, T);                     // Q
+    att_stage(M1, gob, C, T);                       // g_o
+  }
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    const float4* a = reinterpret_cast<const float4*>(gob + static_cast<size_t>(i) * C);
+    const float4* c = reinterpret_cast<const float4*>(ofb + static_cast<size_t>(i) * C);
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 u = a[k], v = c[k];
+      d += fmaf(u.x, v.x, u.y * v.y) + fmaf(u.z, v.z, u.w * v.w);
+    }
+    Ds[i] = d;
+    Ls[i] = lse[static_cast<size_t>(bh) * T + i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, r0 = (blockIdx.y % nblk) * 128 + (threadIdx.x >> 5) * 16;
+  if (r0 >= T) return;
+  const int g = lane >> 2, t = lane & 3;
+  if (!key_major) {
+    uint32_t qa[8][4], da[8][4];
+    att_load_a(qa, base, qs, r0, lane, 0.125f * kLog2e);
+    att_load_a(da, gob, C, r0, lane, 1.f);
+    const float L0 = Ls[r0 + g], L1 = Ls[r0 + g + 8], D0 = Ds[r0 + g], D1 = Ds[r0 + g + 8];
+    float dq[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) dq[nb][0] = dq[nb][1] = dq[nb][2] = dq[nb][3] = 0.f;
+    for (int k0 = 0; k0 < T; k0 += NB * 8) {
+      float s[NB][4], dp[NB][4];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
+      att_mma_nt<NB>(s, qa, M0, k0, lane);
+      att_mma_nt<NB>(dp, da, M1, k0, lane);
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        s[nb][0] = ex2_approx(s[nb][0] - L0) * (dp[nb][0] - D0), s[nb][1] = ex2_approx(s[nb][1] - L0) * (dp[nb][1] - D0);
+        s[nb][2] = ex2_approx(s[nb][2] - L1) * (dp[nb][2] - D1), s[nb][3] = ex2_approx(s[nb][3] - L1) * (dp[nb][3] - D1);
+      }
+      att_mma_nn<NB>(dq, s, M0, k0, lane);
+    }
+    float* lo = gq + static_cast<size_t>(r0 + g) * qs + 2 * t;
+    float* hi = lo + 8 * qs;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      *reinterpret_cast<float2*>(lo + nb * 8) = make_float2(dq[nb][0] * 0.125f, dq[nb][1] * 0.125f);
+      *reinterpret_cast<float2*>(hi + nb * 8) = make_float2(dq[nb][2] * 0.125f, dq[nb][3] * 0.125f);
+    }
+  } else {
+    uint32_t ka[8][4], va[8][4];
+    att_load_a(ka, base + 64, qs, r0, lane, 0.125f * kLog2e);
+    att_load_a(va, base + 128, qs, r0, lane, 1.f);
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) dk[nb][0] = dk[nb][1] = dk[nb][2] = dk[nb][3] = dv[nb][0] = dv[nb][1] = dv[nb][2] = dv[nb][3] = 0.f;
+    for (int q0 = 0; q0 < T; q0 += NB * 8) {
+      float s[NB][4], dp[NB][4];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
+      att_mma_nt<NB>(s, ka, M0, q0, lane);          // S^T[key][query]
+      att_mma_nt<NB>(dp, va, M1, q0, lane);         // g_P^T[key][query]
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int qc = q0 + nb * 8 + 2 * t;
+        const float La = Ls[qc], Lb = Ls[qc + 1], Da = Ds[qc], Db = Ds[qc + 1];
+        s[nb][0] = ex2_approx(s[nb][0] - La), s[nb][1] = ex2_approx(s[nb][1] - Lb);
+        s[nb][2] = ex2_approx(s[nb][2] - La), s[nb][3] = ex2_approx(s[nb][3] - Lb);
+        dp[nb][0] = s[nb][0] * (dp[nb][0] - Da), dp[nb][1] = s[nb][1] * (dp[nb][1] - Db);
+        dp[nb][2] = s[nb][2] * (dp[nb][2] - Da), dp[nb][3] = s[nb][3] * (dp[nb][3] - Db);
+      }
+      att_mma_nn<NB>(dv, s, M1, q0, lane);
+      att_mma_nn<NB>(dk, dp, M0, q0, lane);
+    }
+    float* lo = gq + static_cast<size_t>(r0 + g) * qs + 64 + 2 * t;
+    float* hi = lo + 8 * qs;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      *reinterpret_cast<float2*>(lo + nb * 8) = make_float2(dk[nb][0] * 0.125f, dk[nb][1] * 0.125f);
+      *reinterpret_cast<float2*>(hi + nb * 8) = make_float2(dk[nb][2] * 0.125f, dk[nb][3] * 0.125f);
+      *reinterpret_cast<float2*>(lo + 64 + nb * 8) = make_float2(dv[nb][0], dv[nb][1]);
+      *reinterpret_cast<float2*>(hi + 64 + nb * 8) = make_float2(dv[nb][2], dv[nb][3]);
+    }
+  }
+}
+
 // emb = time_embed(timestep_embedding(t, mc)) (unet.py:335-339,476; nn.py:103-121), then ss[row] = W[row] . silu(emb) + b[row] for
 // the packed rows of every ResBlock's emb_layers (unet.py:140-146).  Two launches: <<<1, 512>>> then one warp per packed row.
 __global__ void __launch_bounds__(512) unet_time_embed_kernel(float t, int mc, const float* __restrict__ w0, const float* __restrict__ b0,
@@ -547,7 +945,9 @@ extern "C" int ap_unet_create(ap_unet_t* out, const ap_unet_cfg* cfg, const int*
       switch (op->kind) {
         case OP_CONV_IN: need += px * op->cout; break;
         case OP_RES: need += px * (op->cin + 3 * static_cast<size_t>(op->cout)) + (op->has_skip ? px * op->cout : 0); break;
-        case OP_ATTN: need += px * (op->cin + 3 * static_cast<size_t>(op->cin) + 2 * static_cast<size_t>(op->cin)); break;
+        case OP_ATTN:      // normalised input, qkv, attention output, block output, log-sum-exp rows kept for the backward pass
+          need += px * (op->cin + 3 * static_cast<size_t>(op->cin) + 2 * static_cast<size_t>(op->cin)) + px * cfg->num_heads;
+          break;
         case OP_POP: need += px * op->cout; break;
         case OP_DOWN: H /= 2; need += static_cast<size_t>(H) * H * op->cout; break;
         case OP_UP: need += 4 * px * op->cin + 4 * px * op->cout; H *= 2; break;
@@ -592,7 +992,40 @@ struct TapeEntry {
   const DevBuf* beta = nullptr;
   const float* ss = nullptr;
   int act = 0;
+  const float* lse = nullptr;         // T_ATTN on the tensor-core kernel: log-sum-exp rows [bn heads][T]
 };
+constexpr size_t kGnSmemMax = 208 * 1024, kAttSmemMax = 2 * 256 * ATT_LD * 4 + 2 * 256 * 4;
+// GroupNorm launch: the shared-memory-tile kernel when a tile fits, else the strided one-group-per-CTA kernel
+int launch_gn(const float* x, float* out, const float* gamma, const float* beta, const float* ss, int bn, int HW, int C, int act,
+              int round_tf32, cudaStream_t st) {
+  const int cpg = C / 32;
+  int gpc = gn_groups_per_cta(HW, cpg, 1, 64 * 1024);
+  if (!gpc) gpc = gn_groups_per_cta(HW, cpg, 1, kGnSmemMax - 2048);
+  if (gpc) {
+    const int q = gpc * cpg / 4, threads = (256 / q) * q;
+    gn_tile_kernel<<<bn * (32 / gpc), threads, static_cast<size_t>(HW) * q * 16 + threads * 4, st>>>(x, out, gamma, beta, ss, HW, C, cpg, gpc,
+                                                                                                    act, round_tf32);
+  } else {
+    gn_kernel<<<bn * 32, 256, 0, st>>>(x, out, gamma, beta, ss, HW, C, cpg, act, round_tf32);
+  }
+  AP_LAUNCH_CHECK();
+  return AP_OK;
+}
+int launch_gn_bwd(const float* x, const float* gy, float* gx, const float* gamma, const float* beta, const float* ss, int bn, int HW, int C,
+                  int act, int accumulate, cudaStream_t st) {
+  const int cpg = C / 32;
+  int gpc = gn_groups_per_cta(HW, cpg, 2, 96 * 1024);
+  if (!gpc) gpc = gn_groups_per_cta(HW, cpg, 2, kGnSmemMax - 2048);
+  if (gpc) {
+    const int q = gpc * cpg / 4, threads = (256 / q) * q;
+    gn_bwd_tile_kernel<<<bn * (32 / gpc), threads, static_cast<size_t>(HW) * q * 32 + threads * 4, st>>>(x, gy, gx, gamma, beta, ss, HW, C, cpg,
+                                                                                                        gpc, act, accumulate);
+  } else {
+    gn_bwd_kernel<<<bn * 32, 256, 0, st>>>(x, gy, gx, gamma, beta, ss, HW, C, cpg, act, accumulate);
+  }
+  AP_LAUNCH_CHECK();
+  return AP_OK;
+}
 }  // namespace
 
 static int unet_time_path(ap_unet_t h, float t, cudaStream_t st) {
@@ -603,6 +1036,17 @@ static int unet_time_path(ap_unet_t h, float t, cudaStream_t st) {
   unet_emb_proj_kernel<<<ceil_div(h->ss_rows * 32, 256), 256, 0, st>>>(h->emb_silu.as<float>(), ted, h->emb_w.as<float>(),
                                                                        h->emb_b.as<float>(), h->ss_rows, h->ss.as<float>());
   AP_LAUNCH_CHECK();
+  return AP_OK;
+}
+static int unet_kernel_attrs(ap_unet_t h) {     // per handle, i.e. per device: function attributes belong to the device's context
+  if (h->attn_attr) return AP_OK;
+  AP_CUDA(cudaFuncSetAttribute(gn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGnSmemMax)));
+  AP_CUDA(cudaFuncSetAttribute(gn_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGnSmemMax)));
+  AP_CUDA(cudaFuncSetAttribute(unet_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAttSmemMax)));
+  AP_CUDA(cudaFuncSetAttribute(unet_attn_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAttSmemMax)));
+  AP_CUDA(cudaFuncSetAttribute(unet_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 64 * 4));
+  AP_CUDA(cudaFuncSetAttribute(unet_attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 64 * 4));
+  h->attn_attr = true;
   return AP_OK;
 }
 static int unet_chunk_size(ap_unet_t h, int B, bool with_backward) {
@@ -633,9 +1077,8 @@ static int unet_forward_chunk(ap_unet_t h, const float* x, float* eps, int bn, c
   std::vector<Act> stack;
   Act cur{const_cast<float*>(x), S, 1};
   auto gn = [&](const Act& a, float* out, const DevBuf& g, const DevBuf& b, const float* ss, int act) -> int {
-    gn_kernel<<<bn * 32, 256, 0, st>>>(a.p, out, g.as<float>(), b.as<float>(), ss, a.H * a.H, a.C, a.C / 32, act,
-                                       h->mode == AP_MODE_TF32);
-    AP_LAUNCH_CHECK();
+    int rcg = launch_gn(a.p, out, g.as<float>(), b.as<float>(), ss, bn, a.H * a.H, a.C, act, h->mode == AP_MODE_TF32, st);
+    if (rcg != AP_OK) return rcg;
     if (tape) {
       TapeEntry e;
       e.kind = T_GN, e.in = a.p, e.out = out, e.Hin = a.H, e.Cin = e.Cout = a.C, e.gamma = &g, e.beta = &b, e.ss = ss, e.act = act;
@@ -687,17 +1130,20 @@ static int unet_forward_chunk(ap_unet_t h, const float* x, float* eps, int bn, c
       if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, qkv, nullptr);
       if (rc == AP_OK) {
         const size_t smem = static_cast<size_t>(2) * T * 64 * sizeof(float);
-        if (!h->attn_attr) {     // per handle, i.e. per device: function attributes belong to the device's context
-          AP_CUDA(cudaFuncSetAttribute(unet_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 64 * 4));
-          AP_CUDA(cudaFuncSetAttribute(unet_attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 64 * 4));
-          h->attn_attr = true;
-        }
         AP_REQUIRE(T <= 256, "ap_unet_eps: attention over more than 256 positions is not supported");
-        unet_attn_kernel<64><<<bn * heads, T < 256 ? ((T + 31) / 32) * 32 : 256, smem, st>>>(qkv, av, T, Cc, heads);
+        AP_REQUIRE(Cc == 64 * heads, "ap_unet_eps: attention heads must have 64 channels");
+        float* lse = nullptr;
+        if (h->mode == AP_MODE_TF32 && T % 64 == 0) {      // tensor cores; the log-sum-exp rows are kept when a backward pass follows
+          if (tape) lse = alloc(static_cast<size_t>(bn) * heads * T);
+          unet_attn_mma_kernel<<<dim3(bn * heads, (T + 127) / 128), T < 128 ? T * 2 : 256, static_cast<size_t>(2) * T * ATT_LD * 4, st>>>(
+              qkv, av, lse, T, Cc, heads);
+        } else {
+          unet_attn_kernel<64><<<bn * heads, T < 256 ? ((T + 31) / 32) * 32 : 256, smem, st>>>(qkv, av, T, Cc, heads);
+        }
         AP_LAUNCH_CHECK();
         if (tape) {
           TapeEntry e;
-          e.kind = T_ATTN, e.in = qkv, e.out = av, e.Hin = cur.H, e.Cin = 3 * Cc, e.Cout = Cc;
+          e.kind = T_ATTN, e.in = qkv, e.out = av, e.Hin = cur.H, e.Cin = 3 * Cc, e.Cout = Cc, e.lse = lse;
           tape->push_back(e);
         }
         rc = conv(op.c2, av, cur.H, o, cur.p);                                                // proj_out + x
@@ -772,7 +1218,8 @@ extern "C" int ap_unet_eps(ap_unet_t h, const float* x, float t, float* eps, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int S = h->cfg.image_size;
   const int chunk = unet_chunk_size(h, B, false);          // activations: sub-batches that keep the arena below ~8 GB
-  int rc = unet_reserve(h, chunk, false);
+  int rc = unet_kernel_attrs(h);
+  if (rc == AP_OK) rc = unet_reserve(h, chunk, false);
   if (rc == AP_OK) rc = unet_time_path(h, t, st);
   for (int b0 = 0; rc == AP_OK && b0 < B; b0 += chunk)
     rc = unet_forward_chunk(h, x + static_cast<size_t>(b0) * S * S, eps + static_cast<size_t>(b0) * S * S, std::min(chunk, B - b0), st,
@@ -800,7 +1247,8 @@ extern "C" int ap_unet_eps_vjp(ap_unet_t h, const float* x, float t, const float
     h->twins_ready = true;
   }
   const int chunk = unet_chunk_size(h, B, true);
-  int rc = unet_reserve(h, chunk, true);
+  int rc = unet_kernel_attrs(h);
+  if (rc == AP_OK) rc = unet_reserve(h, chunk, true);
   if (rc == AP_OK && h->eps_scratch.bytes < static_cast<size_t>(chunk) * S * S * sizeof(float))
     AP_CUDA(h->eps_scratch.alloc(static_cast<size_t>(chunk) * S * S * sizeof(float)));
   if (rc == AP_OK) rc = unet_time_path(h, t, st);
@@ -873,16 +1321,21 @@ extern "C" int ap_unet_eps_vjp(ap_unet_t h, const float* x, float t, const float
         }
       } else if (e.kind == T_GN) {
         float* dst = dest(e.in, px_in * e.Cin, had);
-        gn_bwd_kernel<<<bn * 32, 256, 0, st>>>(e.in, g_out, dst, e.gamma->as<float>(), e.beta->as<float>(), e.ss, e.Hin * e.Hin, e.Cin,
-                                               e.Cin / 32, e.act, had ? 1 : 0);
-        AP_LAUNCH_CHECK();
+        rc = launch_gn_bwd(e.in, g_out, dst, e.gamma->as<float>(), e.beta->as<float>(), e.ss, bn, e.Hin * e.Hin, e.Cin, e.act, had ? 1 : 0,
+                           st);
       } else if (e.kind == T_ATTN) {
         const int T = e.Hin * e.Hin, Cc = e.Cout;
         float* dst = dest(e.in, px_in * e.Cin, had);   // qkv has a single consumer: written in full
-        float* Pm = galloc(static_cast<size_t>(bn) * heads * T * T);
-        float* Gs = galloc(static_cast<size_t>(bn) * heads * T * T);
-        unet_attn_bwd_kernel<64><<<bn * heads, T < 256 ? ((T + 31) / 32) * 32 : 256, static_cast<size_t>(2) * T * 64 * sizeof(float), st>>>(
-            e.in, g_out, dst, Pm, Gs, T, Cc, heads);
+        if (e.lse) {
+          const int nblk = (T + 127) / 128;
+          unet_attn_mma_bwd_kernel<<<dim3(bn * heads, 2 * nblk), T < 128 ? T * 2 : 256, static_cast<size_t>(2) * T * ATT_LD * 4 + 2 * T * 4,
+                                     st>>>(e.in, e.out, e.lse, g_out, dst, T, Cc, heads);
+        } else {
+          float* Pm = galloc(static_cast<size_t>(bn) * heads * T * T);
+          float* Gs = galloc(static_cast<size_t>(bn) * heads * T * T);
+          unet_attn_bwd_kernel<64><<<bn * heads, T < 256 ? ((T + 31) / 32) * 32 : 256, static_cast<size_t>(2) * T * 64 * sizeof(float), st>>>(
+              e.in, g_out, dst, Pm, Gs, T, Cc, heads);
+        }
         AP_LAUNCH_CHECK();
       } else if (e.kind == T_UP2) {
         float* dst = dest(e.in, px_in * e.Cin, had);

@@ -389,6 +389,28 @@ def certification_leg(h: Harness, draws: int):
                               "roofline (DESIGN.md section 5)"}
 
 
+def unet_gflop(synthetic) -> float:
+    """Algorithmic GFLOP of one UNet evaluation on a 32 x 32 spectrogram (2 x MACs of every convolution + QK^T and PV), walked
+    over the same op list the kernels execute."""
+    ops, cfg = synthetic.unet_structure(None)
+    H, fl = cfg["image_size"], 0
+    for _, kind, cin, cout in ops:
+        px = H * H
+        if kind in ("conv_in", "out"):
+            fl += 2 * 9 * cin * cout * px
+        elif kind == "res":
+            fl += 2 * 9 * cin * cout * px + 2 * 9 * cout * cout * px + (2 * cin * cout * px if cin != cout else 0)
+        elif kind == "attn":
+            fl += 2 * cin * 3 * cin * px + 2 * cin * cin * px + 4 * px * px * cin
+        elif kind == "down":
+            H //= 2
+            fl += 2 * 9 * cin * cout * H * H
+        elif kind == "up":
+            H *= 2
+            fl += 2 * 9 * cin * cout * H * H
+    return fl / 1e9
+
+
 def kernels_table(h: Harness, peaks, prof_main):
     """Achieved rate of each hot kernel against the measured peak, timed alone with CUDA events (L2 flushed), B = 512 x 1 s."""
     torch, lib, _lib = h.torch, h.lib, h._lib
@@ -448,6 +470,20 @@ def kernels_table(h: Harness, peaks, prof_main):
     row("ResNeXt-29 8x64 forward (convtc::k_conv tf32 tcgen05 + stem/pool)", "whole classifier, 512 spectrograms", ms,
         gflop=B * RESNEXT_GFLOP, peak_tf=tf32_peak,
         note="peak = torch.matmul 8192^3 with TF32 allowed, measured in this run (burst, best of 10)")
+    del rx
+    unet = h.ap.UNet(h.synthetic.unet_state_dict(seed=0), device=h.dev)
+    xs_ = torch.randn(B, 1, 32, 32, device=h.dev)
+    gs_ = torch.randn(128, 1, 32, 32, device=h.dev)
+    ug = unet_gflop(h.synthetic)
+    ms = h.kernel_time(lambda: unet.eps(xs_, 37.0))
+    row("spectrogram UNet eps (Diffusion-Spec): k_conv tf32 tcgen05 + gn_tile_kernel + unet_attn_mma_kernel",
+        f"one evaluation, 512 spectrograms ({ug:.2f} GFLOP each)", ms, gflop=B * ug, peak_tf=tf32_peak,
+        note="113 convolutions, 61 GroupNorms and 15 attention blocks per evaluation in sub-batches of 128")
+    ms = h.kernel_time(lambda: unet.eps_vjp(xs_[:128], 37.0, gs_))
+    row("spectrogram UNet input gradient (ap_unet_eps_vjp: recomputed forward + reverse walk)",
+        "g_x = (d eps / d x)^T g_eps, 128 spectrograms; flops counted as 2 x forward (recompute + data gradients)", ms,
+        gflop=128 * 2 * ug, peak_tf=tf32_peak)
+    del unet, xs_, gs_
     if prof_main and prof_main.get("k2_n", 0) > 0:
         ms2 = prof_main["k2_ms"] / prof_main["k2_n"]
         wf = prof_main["wf_per_k2"]

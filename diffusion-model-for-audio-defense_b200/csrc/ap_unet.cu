@@ -836,16 +836,17 @@ struct ap_unet_s {
   std::vector<std::unique_ptr<UOp>> ops;
   DevBuf te_w0, te_b0, te_w2, te_b2, emb_w, emb_b, emb_silu, ss;
   int ss_rows = 0;
-  // activation arena (bump allocator, sized for `cap_B` samples) -- every buffer of one evaluation lives here
+  // activation arena (bump allocator over `arena_floats` floats) -- every buffer of one sub-batch lives here
   DevBuf arena;
   size_t arena_floats = 0;
-  int cap_B = 0;
+  // forward-only evaluations keep the block outputs (skip connections) and recycle one scratch region for a block's temporaries
+  size_t need_fwd_persist = 0, need_fwd_tmp = 0, budget_floats = 0;
   size_t need_per_sample = 0;   // floats
   bool attn_attr = false;
   // backward pass: gradient arena, data-gradient twins of every convolution, scratch for the recomputed eps
   DevBuf garena, eps_scratch;
   size_t garena_floats = 0, need_grad_per_sample = 0;
-  int gcap_B = 0;
+
   bool twins_ready = false;
   std::unordered_map<const ConvLayer*, std::unique_ptr<ConvLayer>> twins;
 };
@@ -956,6 +957,27 @@ extern "C" int ap_unet_create(ap_unet_t* out, const ap_unet_cfg* cfg, const int*
       }
     }
     h->need_per_sample = need + 64;
+    {
+      size_t pers = 0, tmp = 0;
+      int Hf = cfg->image_size;
+      for (auto& op : h->ops) {
+        const size_t px = static_cast<size_t>(Hf) * Hf;
+        switch (op->kind) {
+          case OP_CONV_IN: pers += px * op->cout; break;
+          case OP_RES: pers += px * op->cout, tmp = std::max(tmp, px * (op->cin + 2 * static_cast<size_t>(op->cout) + (op->has_skip ? op->cout : 0))); break;
+          case OP_ATTN: pers += px * op->cin, tmp = std::max(tmp, px * 5 * static_cast<size_t>(op->cin)); break;
+          case OP_POP: pers += px * op->cout; break;
+          case OP_DOWN: Hf /= 2; pers += static_cast<size_t>(Hf) * Hf * op->cout; break;
+          case OP_UP: pers += 4 * px * op->cout, tmp = std::max(tmp, 4 * px * op->cin); Hf *= 2; break;
+          case OP_OUT: tmp = std::max(tmp, px * op->cin); break;
+          default: break;
+        }
+      }
+      h->need_fwd_persist = pers + 32, h->need_fwd_tmp = tmp + 32;
+      size_t free_b = 0, total_b = 0;
+      AP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      h->budget_floats = std::min<size_t>(static_cast<size_t>(5) << 30, free_b / 2 / sizeof(float));   // both arenas: <= 20 GB
+    }
     // gradients: one buffer per activation (<= the forward's arena), zero-upsampled gradients of the three stride-2 convolutions,
     // and the attention scratch (P and g_S: 2 x heads x T x T per attention block)
     size_t gneed = need;
@@ -1050,9 +1072,10 @@ static int unet_kernel_attrs(ap_unet_t h) {     // per handle, i.e. per device: 
   return AP_OK;
 }
 static int unet_chunk_size(ap_unet_t h, int B, bool with_backward) {
-  const size_t per = h->need_per_sample + (with_backward ? h->need_grad_per_sample : 0);
-  int chunk = static_cast<int>(std::max<size_t>(1, (static_cast<size_t>(2) << 30) / per));   // 2 Gi floats = 8 GB
-  return chunk > B ? B : chunk;
+  const size_t per = with_backward ? h->need_per_sample + h->need_grad_per_sample : h->need_fwd_persist + h->need_fwd_tmp;
+  const int max_chunk = static_cast<int>(std::min<size_t>(std::max<size_t>(1, h->budget_floats / per), 1u << 20));
+  const int n_chunks = (B + max_chunk - 1) / max_chunk;
+  return (B + n_chunks - 1) / n_chunks;                       // balanced sub-batches
 }
 static int unet_conv(ap_unet_t h, const ConvLayer& L, const float* in, int bn, int H, float* out, const float* res, cudaStream_t st) {
   if (h->mode == AP_MODE_TF32 && L.has_tc && conv_tc_supported(L.Cin, L.Cout, L.groups, H, H, L.kh, L.kw, L.stride, L.pad)) {
@@ -1067,10 +1090,19 @@ static int unet_conv(ap_unet_t h, const ConvLayer& L, const float* in, int bn, i
 static int unet_forward_chunk(ap_unet_t h, const float* x, float* eps, int bn, cudaStream_t st, std::vector<TapeEntry>* tape) {
   const int S = h->cfg.image_size, heads = h->cfg.num_heads;
   float* arena = h->arena.as<float>();
-  size_t top = 0;
+  // alloc: block outputs (alive until the chunk is done); talloc: a block's temporaries -- recycled per block in a forward-only
+  // evaluation (scratch region at the end of the arena), kept like everything else when the operations are recorded
+  const size_t scratch0 = tape ? h->arena_floats : h->arena_floats - h->need_fwd_tmp * bn;
+  size_t top = 0, ttop = 0;
   auto alloc = [&](size_t n) {
     float* p = arena + top;
     top += (n + 3) & ~static_cast<size_t>(3);
+    return p;
+  };
+  auto talloc = [&](size_t n) {
+    if (tape) return alloc(n);
+    float* p = arena + scratch0 + ttop;
+    ttop += (n + 3) & ~static_cast<size_t>(3);
     return p;
   };
   struct Act { float* p; int H, C; };
@@ -1098,15 +1130,16 @@ static int unet_forward_chunk(ap_unet_t h, const float* x, float* eps, int bn, c
   for (auto& opp : h->ops) {
     UOp& op = *opp;
     const size_t px = static_cast<size_t>(bn) * cur.H * cur.H;
+    ttop = 0;
     if (op.kind == OP_CONV_IN) {
       float* o = alloc(px * op.cout);
       rc = conv(op.c1, cur.p, cur.H, o, nullptr);
       cur = {o, cur.H, op.cout};
       stack.push_back(cur);                              // hs.append(h) of input_blocks[0] (unet.py:483-485)
     } else if (op.kind == OP_RES) {
-      float* n1 = alloc(px * op.cin);
-      float* y1 = alloc(px * op.cout);
-      float* n2 = alloc(px * op.cout);
+      float* n1 = talloc(px * op.cin);
+      float* y1 = talloc(px * op.cout);
+      float* n2 = talloc(px * op.cout);
       float* o = alloc(px * op.cout);
       rc = gn(cur, n1, op.g1, op.b1, nullptr, 1);                                             // in_layers: GN, SiLU
       if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, y1, nullptr);                              //            conv
@@ -1114,7 +1147,7 @@ static int unet_forward_chunk(ap_unet_t h, const float* x, float* eps, int bn, c
       if (rc == AP_OK) rc = gn(a1, n2, op.g2, op.b2, h->ss.as<float>() + op.ss_off, 1);       // out_layers[0] * (1 + scale) + shift, SiLU
       const float* res = cur.p;
       if (rc == AP_OK && op.has_skip) {
-        float* sk = alloc(px * op.cout);
+        float* sk = talloc(px * op.cout);
         rc = conv(op.skip, cur.p, cur.H, sk, nullptr);
         res = sk;
       }
@@ -1122,9 +1155,9 @@ static int unet_forward_chunk(ap_unet_t h, const float* x, float* eps, int bn, c
       cur = {o, cur.H, op.cout};
     } else if (op.kind == OP_ATTN) {
       const int T = cur.H * cur.H, Cc = cur.C;
-      float* n1 = alloc(px * Cc);
-      float* qkv = alloc(px * 3 * Cc);
-      float* av = alloc(px * Cc);
+      float* n1 = talloc(px * Cc);
+      float* qkv = talloc(px * 3 * Cc);
+      float* av = talloc(px * Cc);
       float* o = alloc(px * Cc);
       rc = gn(cur, n1, op.g1, op.b1, nullptr, 0);
       if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, qkv, nullptr);
@@ -1173,7 +1206,7 @@ static int unet_forward_chunk(ap_unet_t h, const float* x, float* eps, int bn, c
       rc = conv(op.c1, cur.p, cur.H, o, nullptr);
       cur = {o, Ho, op.cout};
     } else if (op.kind == OP_UP) {
-      float* up = alloc(4 * px * op.cin);
+      float* up = talloc(4 * px * op.cin);
       float* o = alloc(4 * px * op.cout);
       nearest_up2_kernel<<<grid_for_n(static_cast<long long>(px) * op.cin, 256), 256, 0, st>>>(
           reinterpret_cast<const float4*>(cur.p), reinterpret_cast<float4*>(up), bn, cur.H, cur.H, op.cin / 4);
@@ -1186,26 +1219,29 @@ static int unet_forward_chunk(ap_unet_t h, const float* x, float* eps, int bn, c
       rc = conv(op.c1, up, 2 * cur.H, o, nullptr);
       cur = {o, 2 * cur.H, op.cout};
     } else if (op.kind == OP_OUT) {
-      float* n1 = alloc(px * op.cin);
+      float* n1 = talloc(px * op.cin);
       rc = gn(cur, n1, op.g1, op.b1, nullptr, 1);
       if (rc == AP_OK) rc = conv(op.c1, n1, cur.H, eps, nullptr);
     }
     if (rc != AP_OK) return rc;
-    if (top > h->arena_floats) return fail(AP_ERR_STATE, "ap_unet_eps: activation arena overflow (%zu > %zu floats)", top, h->arena_floats);
+    if (top > scratch0 || scratch0 + ttop > h->arena_floats)
+      return fail(AP_ERR_STATE, "ap_unet_eps: activation arena overflow (%zu + %zu > %zu floats)", top, ttop, h->arena_floats);
   }
   return AP_OK;
 }
 
 static int unet_reserve(ap_unet_t h, int chunk, bool with_backward) {
-  if (h->cap_B < chunk) {
-    h->cap_B = 0;
-    AP_CUDA(h->arena.alloc(h->need_per_sample * chunk * sizeof(float)));
-    h->cap_B = chunk, h->arena_floats = h->need_per_sample * chunk;
+  const size_t want = (with_backward ? h->need_per_sample : h->need_fwd_persist + h->need_fwd_tmp) * chunk;
+  if (h->arena_floats < want) {
+    h->arena_floats = 0;
+    AP_CUDA(h->arena.alloc(want * sizeof(float)));
+    h->arena_floats = want;
   }
-  if (with_backward && h->gcap_B < chunk) {
-    h->gcap_B = 0;
-    AP_CUDA(h->garena.alloc(h->need_grad_per_sample * chunk * sizeof(float)));
-    h->gcap_B = chunk, h->garena_floats = h->need_grad_per_sample * chunk;
+  const size_t gwant = with_backward ? h->need_grad_per_sample * chunk : 0;
+  if (h->garena_floats < gwant) {
+    h->garena_floats = 0;
+    AP_CUDA(h->garena.alloc(gwant * sizeof(float)));
+    h->garena_floats = gwant;
   }
   return AP_OK;
 }

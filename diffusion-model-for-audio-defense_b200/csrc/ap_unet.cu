@@ -976,7 +976,9 @@ extern "C" int ap_unet_create(ap_unet_t* out, const ap_unet_cfg* cfg, const int*
       h->need_fwd_persist = pers + 32, h->need_fwd_tmp = tmp + 32;
       size_t free_b = 0, total_b = 0;
       AP_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      h->budget_floats = std::min<size_t>(static_cast<size_t>(5) << 30, free_b / 2 / sizeof(float));   // both arenas: <= 20 GB
+      double cap_gb = 20.0;                           // both arenas together; AP_UNET_ARENA_GB overrides (tests use it to force sub-batches)
+      if (const char* e = std::getenv("AP_UNET_ARENA_GB")) cap_gb = std::max(0.01, std::atof(e));
+      h->budget_floats = std::min<size_t>(static_cast<size_t>(cap_gb * (1u << 30)), free_b / 2) / sizeof(float);
     }
     // gradients: one buffer per activation (<= the forward's arena), zero-upsampled gradients of the three stride-2 convolutions,
     // and the attention scratch (P and g_S: 2 x heads x T x T per attention block)

@@ -362,6 +362,21 @@ def test_unet_input_gradient_vs_reference(ap, golden_unet):
     assert rel_l2(big[30:33], golden_unet["unet_vjp_t37"]) < 5e-5
 
 
+def test_unet_sub_batches(ap, golden_unet, monkeypatch):
+    """A small arena budget forces ragged sub-batches (forward: 14 + 14 + 5 of 33 samples; gradient: 2 per pass): same values."""
+    monkeypatch.setenv("AP_UNET_ARENA_GB", "0.3")
+    net = ap.UNet(synthetic.unet_state_dict(seed=0)).set_mode("fp32")
+    monkeypatch.delenv("AP_UNET_ARENA_GB")
+    ref = ap.UNet(synthetic.unet_state_dict(seed=0)).set_mode("fp32")
+    x = cuda(np.tile(golden_unet["unet_x"], (11, 1, 1, 1)))
+    g = cuda(np.tile(golden_unet["unet_g_eps"], (11, 1, 1, 1)))
+    assert torch.equal(net.eps(x, 37.0), ref.eps(x, 37.0))
+    assert rel_l2(net.eps(x, 37.0)[30:33], golden_unet["unet_eps_t37"]) < 2e-5
+    gx = net.eps_vjp(x[:7], 37, g[:7])
+    assert torch.equal(gx, ref.eps_vjp(x[:7], 37, g[:7]))
+    assert rel_l2(gx[3:6], golden_unet["unet_vjp_t37"]) < 5e-5
+
+
 def test_rev_improved_diffusion_gradient_vs_reference(ap, golden_unet):
     """The white-box gradient through Diffusion-Spec: d <w, purified> / d spec with the reference's noise, t* = 2 -- through the
     UNet, as the reference's autograd does (improved_diffusion_sde.py:104-105 has no no_grad)."""

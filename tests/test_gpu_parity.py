@@ -768,6 +768,35 @@ def test_pgd_steps_through_the_defended_system_raise_the_loss(ap, sd_full):
     assert losses[-1] > losses[0]
 
 
+def test_pgd_through_the_spectrogram_purifier_raises_the_loss(ap):
+    """The same attack loop against the 'spec' defense (adaptive_attack_eval.py:134-137): waveform -> log-mel -> Diffusion-Spec
+    reverse-SDE t* = 1 -> ResNeXt; the gradient runs through the mel, UNet and classifier backward kernels."""
+    import argparse
+    args = argparse.Namespace(ddpm_path=None, t=1, score_type="guided_diffusion", rand_t=False, t_delta=15, use_bm=False, sample_step=1)
+    rid = ap.RevImprovedDiffusion(args, state_dict=synthetic.unet_state_dict(seed=0), noise="philox", seed=11)
+    rx = ap.ResNeXtClassifier(synthetic.resnext_state_dict(seed=0))
+    system = ap.AcousticSystem(classifier=rx, transform=ap.sc09_transform(), defender=rid, defense_type="spec")
+    x = cuda(synthetic.synthetic_waveforms(2, 16000, seed=321))
+    with torch.no_grad():
+        rid._offset = 0
+        logits0 = system(x)
+        y = logits0.argmax(1)
+    delta = torch.zeros_like(x, requires_grad=True)
+    eps, lr, losses = 2e-3, 5e-4, []
+    for i in range(5):
+        rid._offset = 0
+        logits = system(x + delta)
+        if i == 0:     # the autograd route draws the same noise and computes the same chain as the inference route
+            assert float((logits.detach() - logits0).abs().max()) < 1e-2
+        loss = torch.nn.functional.cross_entropy(logits, y)
+        losses.append(float(loss.detach()))
+        (grad,) = torch.autograd.grad(loss, delta)
+        assert torch.isfinite(grad).all() and float(grad.abs().max()) > 0
+        delta.data = (delta.data + lr * grad.sign()).clamp_(-eps, eps)
+    print("PGD through Diffusion-Spec, losses:", [f"{v:.4f}" for v in losses])
+    assert losses[-1] > losses[0]
+
+
 # ------------------------------------------------------------------------------------ black-box query serving (section 8f-3)
 def test_query_loss_kernels_vs_reference_golden(ap, golden_blackbox):
     """ap_query_loss / ap_query_loss_vjp vs nn.CrossEntropyLoss(reduction='none') and SEC4SR_MarginLoss of the reference

@@ -6,8 +6,10 @@ Mirrors, with the same names, argument meaning and error behaviour:
   * ``DiffWave``                              diffwave_ddpm.py:16-249
   * ``create_diffwave_model``                 diffwave_ddpm.py:395-411
 All tensors are CUDA fp32 ``(B, 1, L)`` owned by the caller; every kernel is enqueued on torch's current stream.
-Inference only: an input that requires grad raises (the attack drivers that differentiate through the defender are
-out of scope).
+Gradients wrt the input flow through ``WaveNet.eps`` / ``WaveNet(...)`` / ``DiffWave.forward`` (``_EpsVJP`` -> ``ap_diffwave_eps_vjp``,
+the product autograd forms when a white-box attack back-propagates through the purifier, robustness_eval/white_box_attack.py:438) in
+the tensor-core modes; the remaining entry points (``compute_eps_t`` -- ``@torch.no_grad`` in the reference -- ``one_shot_denoise``,
+the raw update helpers) are inference-only and raise on an input that requires grad instead of silently dropping the gradient.
 """
 from __future__ import annotations
 

@@ -62,10 +62,54 @@ struct ConvEpi {
   }
 };
 
+// 3 x 3, stride 1, pad 1 convolution to ONE output channel (the UNet's output layer; the data gradient of a first layer that reads a
+// one-channel image): the implicit GEMM would compute a 16-column tile for one useful column.  CTA = (image, strip of R output rows)
+// with the R + 2 input rows in shared memory; a warp owns one pixel at a time: 9 taps x (one float4 per lane), then a warp reduction.
+static __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const float* __restrict__ in, const float* __restrict__ w9 /*[9][C]*/, float bias,
+                                                         const float* __restrict__ residual, float* __restrict__ out, int H, int W, int C,
+                                                         int R, int relu) {
+  extern __shared__ float4 c1_rows[];                // [(R + 2)][W][C / 4]
+  const int strips = (H + R - 1) / R, b = blockIdx.x / strips, h0 = (blockIdx.x % strips) * R;
+  const int C4 = C >> 2, rowq = W * C4;
+  const float4* in4 = reinterpret_cast<const float4*>(in) + static_cast<size_t>(b) * H * rowq;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < (R + 2) * rowq; i += blockDim.x) {
+    const int r = i / rowq, ih = h0 - 1 + r;
+    c1_rows[i] = (ih >= 0 && ih < H) ? in4[static_cast<size_t>(ih) * rowq + (i - r * rowq)] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float4* w4 = reinterpret_cast<const float4*>(w9);
+  const int npx = (H - h0 < R ? H - h0 : R) * W;
+  for (int px = warp; px < npx; px += nw) {
+    const int r = px / W, ow = px - r * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dr = tap / 3, iw = ow + (tap - dr * 3) - 1;
+      if (iw < 0 || iw >= W) continue;               // warp-uniform
+      const float4* src = c1_rows + ((r + dr) * W + iw) * C4;
+      for (int c4 = lane; c4 < C4; c4 += 32) {
+        const float4 v = src[c4], k = __ldg(w4 + tap * C4 + c4);
+        acc = fmaf(v.x, k.x, acc), acc = fmaf(v.y, k.y, acc), acc = fmaf(v.z, k.z, acc), acc = fmaf(v.w, k.w, acc);
+      }
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const size_t idx = (static_cast<size_t>(b) * H + h0 + r) * W + ow;
+      float v = acc + bias;
+      if (residual) v += residual[idx];
+      out[idx] = relu ? fmaxf(v, 0.f) : v;
+    }
+  }
+}
+
 struct ConvLayer {
   int Cin = 0, Cout = 0, kh = 1, kw = 1, stride = 1, pad = 0, groups = 1;
   int Cg = 0, Ng = 0, Ngp = 0, K = 0;
   DevBuf w, bias;
+  DevBuf w9;            // [9][Cin] tap-major weights of a 3 x 3 / stride 1 / pad 1 layer with one output channel (conv3x3_c1_kernel)
+  float bias0 = 0.f;
   std::vector<float> wf_host;   // folded torch-layout weights [Cout][Cin/groups][kh][kw], kept when `keep_host` (backward pass)
   bool keep_host = false;
   ConvTc tc;            // TF32 tensor-core twin (weights [Cout][K] K-major), built when the shape allows
@@ -96,6 +140,13 @@ struct ConvLayer {
     AP_CUDA(w.upload(wp.data(), wp.size() * sizeof(float)));
     AP_CUDA(bias.upload(bp.data(), bp.size() * sizeof(float)));
     if (keep_host) wf_host = wf;
+    if (cout == 1 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && groups == 1 && cin % 4 == 0) {
+      std::vector<float> t9(static_cast<size_t>(9) * cin);
+      for (int c = 0; c < cin; ++c)
+        for (int tap = 0; tap < 9; ++tap) t9[static_cast<size_t>(tap) * cin + c] = wf[static_cast<size_t>(c) * 9 + tap];
+      AP_CUDA(w9.upload(t9.data(), t9.size() * sizeof(float)));
+      bias0 = bp[0];
+    }
     // structural part of conv_tc_supported (the spatial part is checked when the layer is bound to buffers)
     if (want_tc && Cg % 32 == 0 && conv_tc_n_tile(Ng) != 0) {
       int rc = tc.init(cin, cout, kh, kw, stride, pad, groups, wf.data(), bp.data());
@@ -114,6 +165,23 @@ struct ConvLayer {
     const int Ho = (H + 2 * pad_h - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
     const long long M = static_cast<long long>(B) * Ho * Wo;
     if (M >= (1ll << 31)) return fail(AP_ERR_INVALID, "conv: too many output pixels");
+    if (w9.p && in_ctot == Cin && out_ctot == 1 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+      const size_t row_bytes = static_cast<size_t>(W) * Cin * sizeof(float);
+      int R = static_cast<int>((96 * 1024) / row_bytes) - 2;
+      if (R > H) R = H;
+      if (R >= 1) {
+        const size_t smem = (R + 2) * row_bytes;
+        if (smem > 48 * 1024) {
+          cudaError_t ea = cudaFuncSetAttribute(conv3x3_c1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+          if (ea != cudaSuccess) return fail(AP_ERR_CUDA, "conv3x3_c1_kernel attribute: %s", cudaGetErrorString(ea));
+        }
+        conv3x3_c1_kernel<<<B * ((H + R - 1) / R), 256, smem, st>>>(in, w9.as<float>(), bias0, residual, out, H, W, Cin, R, relu);
+        cudaError_t el = cudaGetLastError();
+        if (el != cudaSuccess) return fail(AP_ERR_CUDA, "conv3x3_c1_kernel launch: %s", cudaGetErrorString(el));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return AP_OK;
+      }
+    }
     ConvEpi ep{out, bias.as<float>(), residual, out_ctot, Ng, relu};
     cudaError_t e;
     const bool narrow = Ng <= 16;   // 128 x 16 tiles instead of 128 x 128: DenseNet's growth convolutions, 1-channel data gradients

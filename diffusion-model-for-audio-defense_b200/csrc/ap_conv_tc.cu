@@ -205,6 +205,7 @@ int conv_tc_n_tile(int Ng) {
   if (Ng > 0 && Ng % 256 == 0) return 256;
   if (Ng == 64 || Ng == 128) return Ng;
   if (Ng > 0 && Ng % 160 == 0) return 160;
+  if (Ng > 0 && Ng % 128 == 0) return 128;         // 384 (the UNet's concatenated inputs, as outputs of the data-gradient twins)
   return 0;
 }
 

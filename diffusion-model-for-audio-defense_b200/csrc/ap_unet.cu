@@ -94,6 +94,21 @@ struct GnTile {
   }
   // per-group sums of v over the CTA: part [blockDim.x] scratch, res [8]
   __device__ void reduce(float v, float* part, float* res, int cpg, int gpc) const {
+    if ((q & (q - 1)) == 0 && q <= 32) {
+      // q a power of two: lanes with the same column sit q apart -- butterfly inside the warp, then one pass over the warps
+      for (int o = q; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+      if (lane < q) part[(threadIdx.x >> 5) * q + lane] = v;
+      __syncthreads();
+      if (threadIdx.x < gpc) {
+        float t = 0.f;
+        for (int w = 0; w < nw; ++w)
+          for (int jj = threadIdx.x * (cpg >> 2); jj < (threadIdx.x + 1) * (cpg >> 2); ++jj) t += part[w * q + jj];
+        res[threadIdx.x] = t;
+      }
+      __syncthreads();
+      return;
+    }
     part[threadIdx.x] = v;
     __syncthreads();
     for (int rows = pstep; rows > 1;) {
@@ -140,6 +155,7 @@ __global__ void __launch_bounds__(256) gn_tile_kernel(const float* __restrict__ 
   float4* ob = reinterpret_cast<float4*>(out + static_cast<size_t>(b) * HW * C + c0);
   const int C4 = C >> 2, n = HW * cpg;
   float s = 0.f;
+#pragma unroll 8
   for (int p = tl.p0; p < HW; p += tl.pstep) {
     const float4 v = xb[static_cast<size_t>(p) * C4 + tl.j];
     gn_sm[p * tl.q + tl.j] = v;
@@ -184,6 +200,7 @@ __global__ void __launch_bounds__(256) gn_bwd_tile_kernel(const float* __restric
   float4* ob = reinterpret_cast<float4*>(gx + off);
   const int C4 = C >> 2, n = HW * cpg;
   float s = 0.f;
+#pragma unroll 8
   for (int p = tl.p0; p < HW; p += tl.pstep) {
     const float4 v = xb[static_cast<size_t>(p) * C4 + tl.j];
     xs[p * tl.q + tl.j] = v;
@@ -251,6 +268,7 @@ static int gn_groups_per_cta(int HW, int cpg, int tiles, size_t budget) {
 // 2t + 1 -- applied to the rows of M instead of shuffling registers).  K / V (or Q / g_o) of the head sit in shared memory as tf32
 // with a row stride of 68 words: both access patterns are bank-conflict free.
 constexpr int ATT_LD = 68;
+constexpr int ATT_KT = 128;      // rows of the two shared-memory operand tiles resident at a time (70 KB: three CTAs per SM)
 __device__ __forceinline__ uint32_t to_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -262,7 +280,7 @@ __device__ __forceinline__ float ex2_approx(float v) {
   return r;
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -280,12 +298,12 @@ __device__ __forceinline__ void att_load_a(uint32_t (&a)[8][4], const float* __r
 template <int NB> __device__ __forceinline__ void att_mma_nt(float (&c)[NB][4], const uint32_t (&a)[8][4], const uint32_t* __restrict__ M,
                                                              int col0, int lane) {
   const int g = lane >> 2, t = lane & 3;
+  const uint32_t* row = M + (col0 + g) * ATT_LD + t;
+  // k step outermost: consecutive MMAs go to NB different accumulators (a chain on one accumulator would serialise on the MMA latency)
 #pragma unroll
-  for (int nb = 0; nb < NB; ++nb) {
-    const uint32_t* row = M + (col0 + nb * 8 + g) * ATT_LD + t;
+  for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) mma_tf32(c[nb], a[ks], row[8 * ks], row[8 * ks + 4]);
-  }
+    for (int nb = 0; nb < NB; ++nb) mma_tf32(c[nb], a[ks], row[nb * 8 * ATT_LD + 8 * ks], row[nb * 8 * ATT_LD + 8 * ks + 4]);
 }
 template <int NB> __device__ __forceinline__ void att_mma_nn(float (&c)[8][4], const float (&p)[NB][4], const uint32_t* __restrict__ M,
                                                              int k0, int lane) {
@@ -318,26 +336,30 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 // forward: grid (B heads, ceil(T / 128)), one warp per 16 queries.  lse (optional, [B heads][T]): log2-domain log-sum-exp of the
 // scaled scores, kept for the backward pass.
-__global__ void __launch_bounds__(256) unet_attn_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ lse,
+__global__ void __launch_bounds__(256, 2) unet_attn_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ lse,
                                                             int T, int C, int heads) {
-  extern __shared__ uint32_t att_sm[];              // K [T][68] | V [T][68]
-  constexpr int NB = 8;
-  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
-  const float* base = qkv + static_cast<size_t>(b) * T * 3 * C + h * 192;
+  extern __shared__ uint32_t att_sm[];              // K [KT][68] | V [KT][68], KT = min(T, ATT_KT) keys at a time
+  constexpr int NB = 4;                             // 32 keys per softmax step: 128 registers, two CTAs per SM
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads, KT = T < ATT_KT ? T : ATT_KT;
+  const size_t qs = 3 * static_cast<size_t>(C);
+  const float* base = qkv + static_cast<size_t>(b) * T * qs + h * 192;
   uint32_t* Ks = att_sm;
-  uint32_t* Vs = att_sm + T * ATT_LD;
-  att_stage(Ks, base + 64, 3 * static_cast<size_t>(C), T);
-  att_stage(Vs, base + 128, 3 * static_cast<size_t>(C), T);
-  __syncthreads();
+  uint32_t* Vs = att_sm + KT * ATT_LD;
   const int lane = threadIdx.x & 31, r0 = blockIdx.y * 128 + (threadIdx.x >> 5) * 16;
-  if (r0 >= T) return;
+  const bool active = r0 < T;                       // (warp-uniform; inactive warps only help staging)
   const int g = lane >> 2, t = lane & 3;
   uint32_t qa[8][4];
-  att_load_a(qa, base, 3 * static_cast<size_t>(C), r0, lane, 0.125f * kLog2e);      // 1 / sqrt(64): q and k each carry 64^-1/4
+  att_load_a(qa, base, qs, active ? r0 : 0, lane, 0.125f * kLog2e);                 // 1 / sqrt(64): q and k each carry 64^-1/4
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, o[8][4];
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
-  for (int k0 = 0; k0 < T; k0 += NB * 8) {
+  for (int kt = 0; kt < T; kt += KT) {
+   if (kt) __syncthreads();                         // every warp is done with the previous tile
+   att_stage(Ks, base + 64 + kt * qs, qs, KT);
+   att_stage(Vs, base + 128 + kt * qs, qs, KT);
+   __syncthreads();
+   if (active)
+   for (int k0 = 0; k0 < KT; k0 += NB * 8) {
     float s[NB][4];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
@@ -358,7 +380,9 @@ __global__ void __launch_bounds__(256) unet_attn_mma_kernel(const float* __restr
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) o[nb][0] *= c0, o[nb][1] *= c0, o[nb][2] *= c1, o[nb][3] *= c1;
     att_mma_nn<NB>(o, s, Vs, k0, lane);
+   }
   }
+  if (!active) return;
   l0 = quad_sum(l0), l1 = quad_sum(l1);
   const float i0 = 1.f / l0, i1 = 1.f / l1;
   float* olo = out + (static_cast<size_t>(b) * T + r0 + g) * C + h * 64 + 2 * t;
@@ -380,9 +404,9 @@ __global__ void __launch_bounds__(256) unet_attn_mma_kernel(const float* __restr
 __global__ void __launch_bounds__(256) unet_attn_mma_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o_fwd,
                                                                 const float* __restrict__ lse, const float* __restrict__ g_out,
                                                                 float* __restrict__ g_qkv, int T, int C, int heads) {
-  extern __shared__ uint32_t att_sm[];              // two [T][68] operand tiles | lse [T] | D [T]
+  extern __shared__ uint32_t att_sm[];              // two [KT][68] operand tiles | lse [T] | D [T]
   constexpr int NB = 4;
-  const int bh = blockIdx.x, b = bh / heads, h = bh % heads, nblk = gridDim.y >> 1;
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads, nblk = gridDim.y >> 1, KT = T < ATT_KT ? T : ATT_KT;
   const bool key_major = static_cast<int>(blockIdx.y) >= nblk;
   const size_t qs = 3 * static_cast<size_t>(C);
   const float* base = qkv + static_cast<size_t>(b) * T * qs + h * 192;
@@ -390,16 +414,18 @@ __global__ void __launch_bounds__(256) unet_attn_mma_bwd_kernel(const float* __r
   const float* ofb = o_fwd + static_cast<size_t>(b) * T * C + h * 64;
   float* gq = g_qkv + static_cast<size_t>(b) * T * qs + h * 192;
   uint32_t* M0 = att_sm;
-  uint32_t* M1 = att_sm + T * ATT_LD;
-  float* Ls = reinterpret_cast<float*>(att_sm + 2 * T * ATT_LD);
+  uint32_t* M1 = att_sm + KT * ATT_LD;
+  float* Ls = reinterpret_cast<float*>(att_sm + 2 * KT * ATT_LD);
   float* Ds = Ls + T;
-  if (!key_major) {
-    att_stage(M0, base + 64, qs, T);                // K
-    att_stage(M1, base + 128, qs, T);               // V
-  } else {
-    att_stage(M0, base, qs, T);                     // Q
-    att_stage(M1, gob, C, T);                       // g_o
-  }
+  auto stage_tile = [&](int r) {                    // rows r .. r + KT of (K, V) or of (Q, g_o)
+    if (!key_major) {
+      att_stage(M0, base + 64 + r * qs, qs, KT);
+      att_stage(M1, base + 128 + r * qs, qs, KT);
+    } else {
+      att_stage(M0, base + r * qs, qs, KT);
+      att_stage(M1, gob + static_cast<size_t>(r) * C, C, KT);
+    }
+  };
   for (int i = threadIdx.x; i < T; i += blockDim.x) {
     const float4* a = reinterpret_cast<const float4*>(gob + static_cast<size_t>(i) * C);
     const float4* c = reinterpret_cast<const float4*>(ofb + static_cast<size_t>(i) * C);
@@ -412,19 +438,24 @@ __global__ void __launch_bounds__(256) unet_attn_mma_bwd_kernel(const float* __r
     Ds[i] = d;
     Ls[i] = lse[static_cast<size_t>(bh) * T + i];
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, r0 = (blockIdx.y % nblk) * 128 + (threadIdx.x >> 5) * 16;
-  if (r0 >= T) return;
-  const int g = lane >> 2, t = lane & 3;
+  const int lane = threadIdx.x & 31, r0a = (blockIdx.y % nblk) * 128 + (threadIdx.x >> 5) * 16;
+  const bool active = r0a < T;
+  const int r0 = active ? r0a : 0, g = lane >> 2, t = lane & 3;
   if (!key_major) {
     uint32_t qa[8][4], da[8][4];
     att_load_a(qa, base, qs, r0, lane, 0.125f * kLog2e);
     att_load_a(da, gob, C, r0, lane, 1.f);
-    const float L0 = Ls[r0 + g], L1 = Ls[r0 + g + 8], D0 = Ds[r0 + g], D1 = Ds[r0 + g + 8];
+    float L0 = 0.f, L1 = 0.f, D0 = 0.f, D1 = 0.f;
     float dq[8][4];
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) dq[nb][0] = dq[nb][1] = dq[nb][2] = dq[nb][3] = 0.f;
-    for (int k0 = 0; k0 < T; k0 += NB * 8) {
+    for (int kt = 0; kt < T; kt += KT) {
+     if (kt) __syncthreads();
+     stage_tile(kt);
+     __syncthreads();                               // also orders the Ls / Ds writes above before the reads below
+     if (kt == 0) L0 = Ls[r0 + g], L1 = Ls[r0 + g + 8], D0 = Ds[r0 + g], D1 = Ds[r0 + g + 8];
+     if (active)
+     for (int k0 = 0; k0 < KT; k0 += NB * 8) {
       float s[NB][4], dp[NB][4];
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
@@ -436,7 +467,9 @@ __global__ void __launch_bounds__(256) unet_attn_mma_bwd_kernel(const float* __r
         s[nb][2] = ex2_approx(s[nb][2] - L1) * (dp[nb][2] - D1), s[nb][3] = ex2_approx(s[nb][3] - L1) * (dp[nb][3] - D1);
       }
       att_mma_nn<NB>(dq, s, M0, k0, lane);
+     }
     }
+    if (!active) return;
     float* lo = gq + static_cast<size_t>(r0 + g) * qs + 2 * t;
     float* hi = lo + 8 * qs;
 #pragma unroll
@@ -451,7 +484,12 @@ __global__ void __launch_bounds__(256) unet_attn_mma_bwd_kernel(const float* __r
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) dk[nb][0] = dk[nb][1] = dk[nb][2] = dk[nb][3] = dv[nb][0] = dv[nb][1] = dv[nb][2] = dv[nb][3] = 0.f;
-    for (int q0 = 0; q0 < T; q0 += NB * 8) {
+    for (int qt = 0; qt < T; qt += KT) {
+     if (qt) __syncthreads();
+     stage_tile(qt);
+     __syncthreads();
+     if (active)
+     for (int q0 = 0; q0 < KT; q0 += NB * 8) {
       float s[NB][4], dp[NB][4];
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
@@ -459,7 +497,7 @@ __global__ void __launch_bounds__(256) unet_attn_mma_bwd_kernel(const float* __r
       att_mma_nt<NB>(dp, va, M1, q0, lane);         // g_P^T[key][query]
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
-        const int qc = q0 + nb * 8 + 2 * t;
+        const int qc = qt + q0 + nb * 8 + 2 * t;
         const float La = Ls[qc], Lb = Ls[qc + 1], Da = Ds[qc], Db = Ds[qc + 1];
         s[nb][0] = ex2_approx(s[nb][0] - La), s[nb][1] = ex2_approx(s[nb][1] - Lb);
         s[nb][2] = ex2_approx(s[nb][2] - La), s[nb][3] = ex2_approx(s[nb][3] - Lb);
@@ -468,7 +506,9 @@ __global__ void __launch_bounds__(256) unet_attn_mma_bwd_kernel(const float* __r
       }
       att_mma_nn<NB>(dv, s, M1, q0, lane);
       att_mma_nn<NB>(dk, dp, M0, q0, lane);
+     }
     }
+    if (!active) return;
     float* lo = gq + static_cast<size_t>(r0 + g) * qs + 64 + 2 * t;
     float* hi = lo + 8 * qs;
 #pragma unroll
@@ -1018,13 +1058,13 @@ struct TapeEntry {
   int act = 0;
   const float* lse = nullptr;         // T_ATTN on the tensor-core kernel: log-sum-exp rows [bn heads][T]
 };
-constexpr size_t kGnSmemMax = 208 * 1024, kAttSmemMax = 2 * 256 * ATT_LD * 4 + 2 * 256 * 4;
+constexpr size_t kGnSmemMax = 208 * 1024, kAttSmemMax = 2 * ATT_KT * ATT_LD * 4 + 2 * 256 * 4;
 // GroupNorm launch: the shared-memory-tile kernel when a tile fits, else the strided one-group-per-CTA kernel
 int launch_gn(const float* x, float* out, const float* gamma, const float* beta, const float* ss, int bn, int HW, int C, int act,
               int round_tf32, cudaStream_t st) {
   const int cpg = C / 32;
-  int gpc = gn_groups_per_cta(HW, cpg, 1, 64 * 1024);
-  if (!gpc) gpc = gn_groups_per_cta(HW, cpg, 1, kGnSmemMax - 2048);
+  int gpc = gn_groups_per_cta(HW, cpg, 1, 32 * 1024);        // small tiles: 6 CTAs per SM keep HBM busy across the kernel's phases
+  if (!gpc && gn_groups_per_cta(HW, cpg, 1, kGnSmemMax - 2048)) gpc = 1;   // one group per CTA if that is all that fits
   if (gpc) {
     const int q = gpc * cpg / 4, threads = (256 / q) * q;
     gn_tile_kernel<<<bn * (32 / gpc), threads, static_cast<size_t>(HW) * q * 16 + threads * 4, st>>>(x, out, gamma, beta, ss, HW, C, cpg, gpc,
@@ -1038,8 +1078,8 @@ int launch_gn(const float* x, float* out, const float* gamma, const float* beta,
 int launch_gn_bwd(const float* x, const float* gy, float* gx, const float* gamma, const float* beta, const float* ss, int bn, int HW, int C,
                   int act, int accumulate, cudaStream_t st) {
   const int cpg = C / 32;
-  int gpc = gn_groups_per_cta(HW, cpg, 2, 96 * 1024);
-  if (!gpc) gpc = gn_groups_per_cta(HW, cpg, 2, kGnSmemMax - 2048);
+  int gpc = gn_groups_per_cta(HW, cpg, 2, 48 * 1024);
+  if (!gpc && gn_groups_per_cta(HW, cpg, 2, kGnSmemMax - 2048)) gpc = 1;
   if (gpc) {
     const int q = gpc * cpg / 4, threads = (256 / q) * q;
     gn_bwd_tile_kernel<<<bn * (32 / gpc), threads, static_cast<size_t>(HW) * q * 32 + threads * 4, st>>>(x, gy, gx, gamma, beta, ss, HW, C, cpg,
@@ -1170,7 +1210,7 @@ static int unet_forward_chunk(ap_unet_t h, const float* x, float* eps, int bn, c
         float* lse = nullptr;
         if (h->mode == AP_MODE_TF32 && T % 64 == 0) {      // tensor cores; the log-sum-exp rows are kept when a backward pass follows
           if (tape) lse = alloc(static_cast<size_t>(bn) * heads * T);
-          unet_attn_mma_kernel<<<dim3(bn * heads, (T + 127) / 128), T < 128 ? T * 2 : 256, static_cast<size_t>(2) * T * ATT_LD * 4, st>>>(
+          unet_attn_mma_kernel<<<dim3(bn * heads, (T + 127) / 128), T < 128 ? T * 2 : 256, static_cast<size_t>(2) * std::min(T, ATT_KT) * ATT_LD * 4, st>>>(
               qkv, av, lse, T, Cc, heads);
         } else {
           unet_attn_kernel<64><<<bn * heads, T < 256 ? ((T + 31) / 32) * 32 : 256, smem, st>>>(qkv, av, T, Cc, heads);
@@ -1366,8 +1406,8 @@ extern "C" int ap_unet_eps_vjp(ap_unet_t h, const float* x, float t, const float
         float* dst = dest(e.in, px_in * e.Cin, had);   // qkv has a single consumer: written in full
         if (e.lse) {
           const int nblk = (T + 127) / 128;
-          unet_attn_mma_bwd_kernel<<<dim3(bn * heads, 2 * nblk), T < 128 ? T * 2 : 256, static_cast<size_t>(2) * T * ATT_LD * 4 + 2 * T * 4,
-                                     st>>>(e.in, e.out, e.lse, g_out, dst, T, Cc, heads);
+          unet_attn_mma_bwd_kernel<<<dim3(bn * heads, 2 * nblk), T < 128 ? T * 2 : 256,
+                                     static_cast<size_t>(2) * std::min(T, ATT_KT) * ATT_LD * 4 + 2 * T * 4, st>>>(e.in, e.out, e.lse, g_out, dst, T, Cc, heads);
         } else {
           float* Pm = galloc(static_cast<size_t>(bn) * heads * T * T);
           float* Gs = galloc(static_cast<size_t>(bn) * heads * T * T);

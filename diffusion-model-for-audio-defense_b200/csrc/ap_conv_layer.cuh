@@ -81,6 +81,10 @@ static __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const float* __r
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float4* w4 = reinterpret_cast<const float4*>(w9);
   const int npx = (H - h0 < R ? H - h0 : R) * W;
+  const bool reg_w = C4 <= 32;                       // up to 128 channels: the lane's nine weight vectors stay in registers
+  float4 wr[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) wr[tap] = (reg_w && lane < C4) ? __ldg(w4 + tap * C4 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int px = warp; px < npx; px += nw) {
     const int r = px / W, ow = px - r * W;
     float acc = 0.f;
@@ -89,9 +93,16 @@ static __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const float* __r
       const int dr = tap / 3, iw = ow + (tap - dr * 3) - 1;
       if (iw < 0 || iw >= W) continue;               // warp-uniform
       const float4* src = c1_rows + ((r + dr) * W + iw) * C4;
-      for (int c4 = lane; c4 < C4; c4 += 32) {
-        const float4 v = src[c4], k = __ldg(w4 + tap * C4 + c4);
-        acc = fmaf(v.x, k.x, acc), acc = fmaf(v.y, k.y, acc), acc = fmaf(v.z, k.z, acc), acc = fmaf(v.w, k.w, acc);
+      if (reg_w) {
+        if (lane < C4) {
+          const float4 v = src[lane], k = wr[tap];
+          acc = fmaf(v.x, k.x, acc), acc = fmaf(v.y, k.y, acc), acc = fmaf(v.z, k.z, acc), acc = fmaf(v.w, k.w, acc);
+        }
+      } else {
+        for (int c4 = lane; c4 < C4; c4 += 32) {
+          const float4 v = src[c4], k = __ldg(w4 + tap * C4 + c4);
+          acc = fmaf(v.x, k.x, acc), acc = fmaf(v.y, k.y, acc), acc = fmaf(v.z, k.z, acc), acc = fmaf(v.w, k.w, acc);
+        }
       }
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

@@ -25,7 +25,7 @@
 
 namespace ap {
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }   // ex2 + rcp on the MUFU (2 ulp)
 
 // out = [silu]( ((x - mean) * rstd * gamma + beta) [* (1 + scale) + shift] ), x NHWC [B][HW][C], one CTA per (b, group).
 // scale_shift: [2 C] for this block (scale = first C entries, shift = last C: th.chunk(emb_out, 2, dim=1), unet.py:190), or null.
@@ -173,10 +173,13 @@ __global__ void __launch_bounds__(256) gn_tile_kernel(const float* __restrict__ 
   tl.reduce(vv, part, res, cpg, gpc);
   const float rstd = rsqrtf(res[tl.gl] / n + 1e-5f);
   const int ch = c0 + 4 * tl.j;
+  // the thread's four channels are fixed: y = (x - mean) A + Bc with A = rstd gamma [(1 + scale)], Bc = beta [(1 + scale) + shift]
+  float4 A, Bc = gn_affine(make_float4(0.f, 0.f, 0.f, 0.f), ch, gamma, beta, scale_shift, C, &A);
+  A = make_float4(A.x * rstd, A.y * rstd, A.z * rstd, A.w * rstd);
+#pragma unroll 4
   for (int p = tl.p0; p < HW; p += tl.pstep) {
     const float4 v = gn_sm[p * tl.q + tl.j];
-    float4 y = gn_affine(make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd), ch, gamma, beta,
-                         scale_shift, C, nullptr);
+    float4 y = make_float4(fmaf(v.x - mean, A.x, Bc.x), fmaf(v.y - mean, A.y, Bc.y), fmaf(v.z - mean, A.z, Bc.z), fmaf(v.w - mean, A.w, Bc.w));
     if (act) y = make_float4(silu_f(y.x), silu_f(y.y), silu_f(y.z), silu_f(y.w));
     if (round_tf32) y = make_float4(round_tf32_f(y.x), round_tf32_f(y.y), round_tf32_f(y.z), round_tf32_f(y.w));
     ob[static_cast<size_t>(p) * C4 + tl.j] = y;
@@ -219,15 +222,17 @@ __global__ void __launch_bounds__(256) gn_bwd_tile_kernel(const float* __restric
   const float rstd = rsqrtf(res[tl.gl] / n + 1e-5f);
   const int ch = c0 + 4 * tl.j;
   float s1 = 0.f, s2 = 0.f;
+  float4 mul;                                        // the thread's four channels are fixed: z = x-hat mul + Bc
+  const float4 Bc = gn_affine(make_float4(0.f, 0.f, 0.f, 0.f), ch, gamma, beta, scale_shift, C, &mul);
+#pragma unroll 4
   for (int p = tl.p0; p < HW; p += tl.pstep) {
     const float4 v = xs[p * tl.q + tl.j];
     const float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
-    float4 mul;
-    const float4 z = gn_affine(xh, ch, gamma, beta, scale_shift, C, &mul);
+    const float4 z = make_float4(fmaf(xh.x, mul.x, Bc.x), fmaf(xh.y, mul.y, Bc.y), fmaf(xh.z, mul.z, Bc.z), fmaf(xh.w, mul.w, Bc.w));
     float4 d = gb[static_cast<size_t>(p) * C4 + tl.j];
     if (act) {
       auto dsilu = [](float zz) {
-        const float sg = 1.f / (1.f + __expf(-zz));
+        const float sg = __fdividef(1.f, 1.f + __expf(-zz));
         return sg * (1.f + zz * (1.f - sg));
       };
       d = make_float4(d.x * dsilu(z.x), d.y * dsilu(z.y), d.z * dsilu(z.z), d.w * dsilu(z.w));
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(256) gn_bwd_tile_kernel(const float* __restric
     ob[static_cast<size_t>(p) * C4 + tl.j] = r;
   }
 }
+
 // groups per CTA for a tile budget: the largest power of two (<= 8) whose `tiles` tiles fit `budget` bytes; 0 = not even one group
 static int gn_groups_per_cta(int HW, int cpg, int tiles, size_t budget) {
   if (cpg % 4 != 0) return 0;

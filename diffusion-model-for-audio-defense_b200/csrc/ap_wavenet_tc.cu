@@ -148,7 +148,11 @@ template <class G> struct Ctx {
   // weight tile: this CTA's B_ROWS rows starting at row0 (+ rank * B_ROWS)
   __device__ __forceinline__ void load_b(uint32_t s, const CUtensorMap* m, int k0, int row0) const {
     if (CG == 1) tma_load_2d(stage_b(s), m, bar(BAR_FULL + s), k0, row0);
+#ifdef AP_L2_HINTS   // weights: keep (1 MB per layer, re-read by every tile)
+    else tma_load_2d_pair_hint(stage_b(s), m, lbar(BAR_FULL + s), k0, row0 + static_cast<int>(rank) * G::B_ROWS, l2_policy_evict_last());
+#else
     else tma_load_2d_pair(stage_b(s), m, lbar(BAR_FULL + s), k0, row0 + static_cast<int>(rank) * G::B_ROWS);
+#endif
   }
   // issue the 4 MMAs (K = 16 each) of one 64-wide K-block
   __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, bool first) const {
@@ -363,8 +367,13 @@ __device__ __forceinline__ void k1_epilogue(const Ctx<G>& cx, const K1Params& p,
     if (etid == 0) {
       trace(p, ti, 13 + J * 8);
       if (valid) {
+#ifdef AP_L2_HINTS   // gate outputs: not read again before k2_head
+        tma_store_3d_hint(tmO, cx.out_kb(2 * J), (2 * J) * 64, l0, p.layer * p.chunk_alloc + b, l2_policy_evict_first());
+        tma_store_3d_hint(tmO, cx.out_kb(2 * J + 1), (2 * J + 1) * 64, l0, p.layer * p.chunk_alloc + b, l2_policy_evict_first());
+#else
         tma_store_3d(tmO, cx.out_kb(2 * J), (2 * J) * 64, l0, p.layer * p.chunk_alloc + b);
         tma_store_3d(tmO, cx.out_kb(2 * J + 1), (2 * J + 1) * 64, l0, p.layer * p.chunk_alloc + b);
+#endif
       }
       trace(p, ti, 14 + J * 8);
       bulk_commit();                                       // always a group (possibly empty): wait_group counts stay uniform
@@ -687,7 +696,11 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
           mbar_wait(cx.bar(BAR_RES_FREE + buf), ((rcount >> 1) & 1) ^ 1, 14);
           if (elect_one()) {
             mbar_expect_tx(cx.bar(BAR_RES_FULL + buf), A_BYTES);
+#ifdef AP_L2_HINTS   // last use of this part of u in the launch
+            tma_load_3d_hint(cx.base + G::RES_OFF + buf * A_BYTES, &tmUin, cx.bar(BAR_RES_FULL + buf), pass * 64, l0, b, l2_policy_evict_first());
+#else
             tma_load_3d(cx.base + G::RES_OFF + buf * A_BYTES, &tmUin, cx.bar(BAR_RES_FULL + buf), pass * 64, l0, b);
+#endif
           }
           __syncwarp();
         }
@@ -705,7 +718,11 @@ k1_layer(const __grid_constant__ CUtensorMap tmUin, const __grid_constant__ CUte
           const uint32_t buf = rcount & 1;
           mbar_wait(cx.bar(BAR_RES_DONE + buf), (rcount >> 1) & 1, 15);
           if (elect_one()) {
+#ifdef AP_L2_HINTS
+            if (valid) tma_store_3d_hint(&tmUout, cx.base + G::RES_OFF + buf * A_BYTES, pass * 64, l0, b, l2_policy_evict_first());
+#else
             if (valid) tma_store_3d(&tmUout, cx.base + G::RES_OFF + buf * A_BYTES, pass * 64, l0, b);   // rows >= L are clipped
+#endif
             bulk_commit();
             bulk_wait_read<0>();                       // the store has read the buffer: the loader may refill it
             mbar_arrive(cx.bar(BAR_RES_FREE + buf));

@@ -1380,6 +1380,255 @@ k_bwd(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensor
   tc_epilogue_teardown<CG>(tmem);
 }
 
+// ---- MODE 2 of layer l fused with MODE 1 of layer l - 1 (the two are separate launches above because g_a is needed at l +- d;
+// MODE 1 is pointwise in the position, so it can consume g_u(l) of the SAME tile straight from shared memory).  One launch per layer
+// boundary with the structure of the forward's k1_layer: job A (K = 1536, TMEM region X) -> epilogue A adds sqrt(.5) g_u(l+1),
+// writes g_u(l) (the next launch's residual term) and stages it as bf16 K-blocks -> job B (K = 512: g_s by TMA | staged g_u,
+// region Y) -> epilogue B multiplies by the saved gate derivatives and writes g_a(l-1).  The MMA warp issues A(t), B(t-1), A(t+1),
+// ...: the HBM-bound epilogue of one tile runs under the tensor-bound job of the next, instead of one after the other in two
+// launches (0.83 ms per layer and 32 waveforms = HBM time + tensor time).
+struct KfParams {
+  int n_tiles, tiles_per_sample, L, dilation;
+  int has_next;            // layer l < N - 1: g_u(l+1) exists
+  int a_row0, b_row0;      // first rows of layer l in the WdT map and of layer l - 1 in the Wb map
+  const uint16_t* ts;      // [chunk][L][512] gate derivatives of layer l - 1
+  const uint16_t* g_next;  // [chunk][L][256] g_u(l+1)
+  uint16_t* gu_out;        // [chunk][L][256] g_u(l)
+  uint16_t* ga_out;        // [chunk][L][512] g_a(l-1)
+};
+
+template <class G, int HSEL>
+__device__ __forceinline__ void kf_epilogue(const Ctx<G>& cx, const KfParams& p, const uint32_t tmem, const Tiles<G::CG>& tiles) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q4 = warp & 3, etid = threadIdx.x - EPI_WARP0 * 32;
+  const int row = q4 * 32 + lane;
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+  const uint32_t row_off = row * 128, sw = row & 7;
+  const float sqrt_half = 0.70710678118654752440f;
+
+  // epilogue B of unit t_idx: g_a(l-1) = acc_Y * (d o / d a_t | d o / d a_s)
+  auto epi_b = [&](uint32_t t_idx, bool live, size_t pos) {
+    mbar_wait(cx.bar(BAR_ACC_FULL + 1), t_idx & 1, 64);
+    tc_fence_after();
+    // the derivative rows of 64 channels (eight 32-byte loads) are requested together, ahead of the TMEM reads: one exposed
+    // memory latency per half instead of one per 16 channels (the tcgen05.wait below is a compiler barrier for loads)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t tv[4][8], sv[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tv[j][e] = sv[j][e] = 0u;
+        if (live) {
+          ld_global_v8(p.ts + pos * 512 + HSEL * 128 + half * 64 + j * 16, tv[j]);
+          ld_global_v8(p.ts + pos * 512 + 256 + HSEL * 128 + half * 64 + j * 16, sv[j]);
+        }
+      }
+#pragma unroll
+      for (int g2 = 0; g2 < 2; ++g2) {
+        const int gq = half * 2 + g2;
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(lane_addr + 256 + HSEL * 128 + gq * 32, acc);
+        tmem_ld_wait();
+        if (gq == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 1);
+        }
+        const int ch = HSEL * 128 + gq * 32;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          uint32_t o0[8], o1[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float g0 = __uint_as_float(acc[i * 16 + 2 * e]), g1 = __uint_as_float(acc[i * 16 + 2 * e + 1]);
+            o0[e] = pack_bf16x2(g0 * bf16_lo(tv[g2 * 2 + i][e]), g1 * bf16_hi(tv[g2 * 2 + i][e]));
+            o1[e] = pack_bf16x2(g0 * bf16_lo(sv[g2 * 2 + i][e]), g1 * bf16_hi(sv[g2 * 2 + i][e]));
+          }
+          if (live) {
+            st_global_v8(p.ga_out + pos * 512 + ch + i * 16, o0);
+            st_global_v8(p.ga_out + pos * 512 + 256 + ch + i * 16, o1);
+          }
+        }
+      }
+    }
+  };
+
+  uint32_t ti = 0;
+  bool plive = false;
+  size_t ppos = 0;
+  for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+    const bool valid = tile < p.n_tiles;
+    const int b = valid ? tile / p.tiles_per_sample : 0;
+    const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : 0;
+    const bool live = valid && l0 + row < p.L;
+    const size_t pos = static_cast<size_t>(b) * p.L + (live ? l0 + row : 0);
+    // ---- epilogue A: g_u(l) = acc_X + sqrt(.5) g_u(l+1); rows past the end of a waveform stage zeros.  The row of g_u(l+1)
+    //      (eight 32-byte loads) is requested before the wait for the accumulator: its latency hides behind job A.
+    uint32_t gn[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gn[j][e] = 0u;
+      if (live && p.has_next) ld_global_v8(p.g_next + pos * C + HSEL * 128 + j * 16, gn[j]);
+    }
+    mbar_wait(cx.bar(BAR_ACC_FULL + 0), ti & 1, 65);
+    tc_fence_after();
+    uint32_t pk[4][16];
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(lane_addr + HSEL * 128 + gq * 32, acc);
+      tmem_ld_wait();
+      if (gq == 3) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 0);
+      }
+      const int ch = HSEL * 128 + gq * 32;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t (&gv)[8] = gn[gq * 2 + i];
+        uint32_t o0[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o0[e] = live ? pack_bf16x2(fmaf(bf16_lo(gv[e]), sqrt_half, __uint_as_float(acc[i * 16 + 2 * e])),
+                                     fmaf(bf16_hi(gv[e]), sqrt_half, __uint_as_float(acc[i * 16 + 2 * e + 1])))
+                       : 0u;
+          pk[gq][i * 8 + e] = o0[e];
+        }
+        if (live) st_global_v8(p.gu_out + pos * C + ch + i * 16, o0);
+      }
+    }
+    // the staging tile is free once job B of the previous unit has completed
+    if (ti > 0) {
+      mbar_wait(cx.bar(BAR_ACC_FULL + 1), (ti - 1) & 1, 66);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      const uint32_t kb_base = cx.out_kb(HSEL * 2 + (gq >> 1)) + row_off;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        st_shared_v4(kb_base + ((((gq & 1) * 4 + i) ^ sw) << 4), make_uint4(pk[gq][i * 4], pk[gq][i * 4 + 1], pk[gq][i * 4 + 2], pk[gq][i * 4 + 3]));
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, EPI_THREADS);
+    if (etid == 0) cx.arrive_leader(BAR_OUT_READY);
+    // ---- epilogue B of the previous unit (its job B was issued behind this unit's job A)
+    if (ti > 0) epi_b(ti - 1, plive, ppos);
+    plive = live, ppos = pos;
+  }
+  if (ti > 0) epi_b(ti - 1, plive, ppos);
+}
+
+// tmGa: g_a(l) (512 channels); tmGs: g_s; tmWdT / tmWb: the transposed weights
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_bwd_fused(const __grid_constant__ CUtensorMap tmGa, const __grid_constant__ CUtensorMap tmGs, const __grid_constant__ CUtensorMap tmWdT,
+            const __grid_constant__ CUtensorMap tmWb, const __grid_constant__ KfParams p) {
+  using G = Geo<2, 2, 0>;
+  constexpr int CG = 2;
+  Ctx<G> cx;
+  uint8_t* gen;
+  const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
+  if (threadIdx.x == 0) prefetch_tmap(&tmGa), prefetch_tmap(&tmGs), prefetch_tmap(&tmWdT), prefetch_tmap(&tmWb);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  const Tiles<CG> tiles(p.n_tiles, cx.rank);
+  const int oob_l0 = p.tiles_per_sample * TILE_M;
+
+  if (warp < EPI_WARP0) setmaxnreg_dec<96>();
+  if (warp == 0) {
+    RingPos<G::NSTAGE> it;
+    auto load_job_b = [&](bool valid, int b, int l0) {
+      for (int kb = 0; kb < 8; ++kb, ++it) {
+        const uint32_t s = it.s, ph = it.ph;
+        cx.wait_empty(s, ph, 67);
+        if (elect_one()) {
+          if (kb < 4) {      // g_s tile and the Ws rows
+            cx.arm(s, G::STAGE_BYTES);
+            cx.load_a(s, &tmGs, kb * 64, valid ? l0 : oob_l0, b);
+          } else {           // Wr rows only: the A operand is the staged g_u
+            cx.arm(s, G::B_BYTES);
+          }
+          cx.load_b(s, &tmWb, kb * 64, p.b_row0);
+        }
+        __syncwarp();
+      }
+    };
+    uint32_t ti = 0;
+    bool pvalid = false;
+    int pb = 0, pl0 = 0;
+    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+      const bool valid = tile < p.n_tiles;
+      const int b = valid ? tile / p.tiles_per_sample : 0;
+      const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+      for (int tap = 0; tap < 3; ++tap)
+        for (int kb = 0; kb < 8; ++kb, ++it) {
+          const uint32_t s = it.s, ph = it.ph;
+          cx.wait_empty(s, ph, 68);
+          if (elect_one()) {
+            cx.arm(s, G::STAGE_BYTES);
+            cx.load_a(s, &tmGa, kb * 64, valid ? l0 - (tap - 1) * p.dilation : oob_l0, b);
+            cx.load_b(s, &tmWdT, (tap * 8 + kb) * 64, p.a_row0);
+          }
+          __syncwarp();
+        }
+      if (ti > 0) load_job_b(pvalid, pb, pl0);
+      pvalid = valid, pb = b, pl0 = l0;
+    }
+    if (ti > 0) load_job_b(pvalid, pb, pl0);
+  } else if (warp == 1) {
+    if (cx.rank == 0) {
+      RingPos<G::NSTAGE> it;
+      auto job_b = [&](uint32_t t_idx) {
+        mbar_wait(cx.bar(BAR_ACC_EMPTY + 1), (t_idx & 1) ^ 1, 69);
+        tc_fence_after();
+        for (int kb = 0; kb < 8; ++kb, ++it) {
+          const uint32_t s = it.s, ph = it.ph;
+          if (kb == 4) {     // the staged g_u of this unit
+            mbar_wait(cx.bar(BAR_OUT_READY), t_idx & 1, 58);
+            tc_fence_after();
+          }
+          mbar_wait(cx.bar(BAR_FULL + s), ph, 59);
+          tc_fence_after();
+          if (elect_one()) {
+            cx.mma_kblock(tmem + 256, kb < 4 ? cx.stage_a(s) : cx.out_kb(kb - 4), cx.stage_b(s), kb == 0);
+            cx.commit(BAR_EMPTY + s);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) cx.commit(BAR_ACC_FULL + 1);
+        __syncwarp();
+      };
+      uint32_t ti = 0;
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+        mbar_wait(cx.bar(BAR_ACC_EMPTY + 0), (ti & 1) ^ 1, 57);
+        tc_fence_after();
+        for (int k = 0; k < 24; ++k, ++it) {
+          const uint32_t s = it.s, ph = it.ph;
+          mbar_wait(cx.bar(BAR_FULL + s), ph, 56);
+          tc_fence_after();
+          if (elect_one()) {
+            cx.mma_kblock(tmem, cx.stage_a(s), cx.stage_b(s), k == 0);
+            cx.commit(BAR_EMPTY + s);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) cx.commit(BAR_ACC_FULL + 0);
+        __syncwarp();
+        if (ti > 0) job_b(ti - 1);
+      }
+      if (ti > 0) job_b(ti - 1);
+    }
+  } else if (warp >= EPI_WARP0) {
+    setmaxnreg_inc<200>();
+    if (((warp - EPI_WARP0) >> 2) == 0) kf_epilogue<G, 0>(cx, p, tmem, tiles);
+    else kf_epilogue<G, 1>(cx, p, tmem, tiles);
+  }
+  tc_epilogue_teardown<CG>(tmem);
+}
+
 // g_pre[m][c] = mask(m, c) ? g_eps[m] * w2[c] : 0   (bf16; backward of eps = w2 . relu(pre) + b2, WaveNet.py:161-162)
 __global__ void __launch_bounds__(256) gpre_kernel(const float* __restrict__ g_eps, const uint32_t* __restrict__ mask,
                                                     const float* __restrict__ w2, uint4* __restrict__ g_pre, long long M) {
@@ -1860,8 +2109,8 @@ struct TcNet {
   // backward pass (bf16 mode): transposed weights, saved activations and gradient buffers for bchunk waveforms
   DevBuf wb, wdt, wft;                                     // [N][256][512], [N][256][1536], [256][256] bf16, K-major
   CUtensorMap tmWb, tmWdT, tmWfT;
-  DevBuf ts, mask, g_pre, g_s, g_a, g_u[2];
-  CUtensorMap tmGpre, tmGs, tmGa, tmGu[2];
+  DevBuf ts, mask, g_pre, g_s, g_a, g_a2, g_u[2];     // g_a / g_a2: the fused backward launches read one and write the other
+  CUtensorMap tmGpre, tmGs, tmGa, tmGa2, tmGu[2];
   int bchunk = 0, bL = 0;
   bool bwd_attr = false;
   unsigned long long save_gen = 0;   // generation of the saved forward state (tokens of ap_diffwave_eps_save)
@@ -2283,12 +2532,13 @@ static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
   using namespace tc;
   if (n->bchunk == chunk && n->bL == L) return AP_OK;
   const size_t pos = static_cast<size_t>(chunk) * L;
-  DevBuf* bufs[7] = {&n->ts, &n->mask, &n->g_pre, &n->g_s, &n->g_a, &n->g_u[0], &n->g_u[1]};
-  const size_t sizes[7] = {pos * 512 * 2 * n->N, pos * 8 * 4, pos * 256 * 2, pos * 256 * 2, pos * 512 * 2, pos * 256 * 2, pos * 256 * 2};
+  DevBuf* bufs[8] = {&n->ts, &n->mask, &n->g_pre, &n->g_s, &n->g_a, &n->g_a2, &n->g_u[0], &n->g_u[1]};
+  const size_t sizes[8] = {pos * 512 * 2 * n->N, pos * 8 * 4, pos * 256 * 2, pos * 256 * 2, pos * 512 * 2, pos * 512 * 2, pos * 256 * 2,
+                           pos * 256 * 2};
   n->bchunk = 0, n->bL = 0;                 // nothing describes the released buffers if an allocation below fails
   n->save_B = 0, ++n->save_gen;
   for (DevBuf* d : bufs) d->release();
-  for (int i = 0; i < 7; ++i) {
+  for (int i = 0; i < 8; ++i) {
     cudaError_t e = bufs[i]->alloc(sizes[i]);
     if (e != cudaSuccess) {
       for (DevBuf* d : bufs) d->release();
@@ -2305,6 +2555,7 @@ static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
   int rc = encode_bf16(&n->tmGpre, n->g_pre.p, 3, d256, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmGs, n->g_s.p, 3, d256, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmGa, n->g_a.p, 3, d512, bx);
+  if (rc == AP_OK) rc = encode_bf16(&n->tmGa2, n->g_a2.p, 3, d512, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmGu[0], n->g_u[0].p, 3, d256, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmGu[1], n->g_u[1].p, 3, d256, bx);
   if (rc != AP_OK) {
@@ -2315,6 +2566,7 @@ static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
     AP_CUDA(cudaFuncSetAttribute(k_bwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k2_head<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k1_split<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1, 2>::SMEM_BYTES));
@@ -2326,7 +2578,7 @@ static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
 }
 
 size_t tc_net_bwd_bytes_per_waveform(const TcNet* n, int L) {
-  return static_cast<size_t>(L) * (static_cast<size_t>(n->N) * 1024 + 32 + 512 + 512 + 1024 + 1024);
+  return static_cast<size_t>(L) * (static_cast<size_t>(n->N) * 1024 + 32 + 512 + 512 + 1024 + 1024 + 1024);
 }
 
 // forward that keeps what the backward needs (the gate's local derivatives of every layer, the head's ReLU mask); returns a
@@ -2370,17 +2622,45 @@ int tc_net_backward(TcNet* n, const float* x, const float* g_eps, float* g_x, in
   p.ts = nullptr, p.g_next = nullptr, p.out = n->g_s.as<uint16_t>();
   AP_CUDA(launch_pair(k_bwd<0>, grid, smem, st, n->tmGpre, n->tmGpre, n->tmWfT, p));
   AP_LAUNCH_CHECK();
-  for (int l = n->N - 1; l >= 0; --l) {
-    const bool last = l == n->N - 1;
-    // g_u of layer l+1 lives in g_u[(l+1) & 1]; this layer writes g_u[l & 1]
-    p.last = last, p.nkb = last ? 4 : 8, p.b_row0 = l * 256;
-    p.ts = n->ts.as<uint16_t>() + static_cast<size_t>(l) * n->bchunk * L * 512;
-    p.out = n->g_a.as<uint16_t>();
-    AP_CUDA(launch_pair(k_bwd<1>, grid, smem, st, n->tmGs, n->tmGu[(l + 1) & 1], n->tmWb, p));
+  static const bool unfused = std::getenv("AP_BWD_UNFUSED") != nullptr;      // development aid: the two-launch form of every layer
+  if (unfused) {
+    for (int l = n->N - 1; l >= 0; --l) {
+      const bool last = l == n->N - 1;
+      // g_u of layer l+1 lives in g_u[(l+1) & 1]; this layer writes g_u[l & 1]
+      p.last = last, p.nkb = last ? 4 : 8, p.b_row0 = l * 256;
+      p.ts = n->ts.as<uint16_t>() + static_cast<size_t>(l) * n->bchunk * L * 512;
+      p.out = n->g_a.as<uint16_t>();
+      AP_CUDA(launch_pair(k_bwd<1>, grid, smem, st, n->tmGs, n->tmGu[(l + 1) & 1], n->tmWb, p));
+      AP_LAUNCH_CHECK();
+      p.nkb = 8, p.dilation = 1 << (l % n->cfg.dilation_cycle);
+      p.g_next = n->g_u[(l + 1) & 1].as<uint16_t>(), p.out = n->g_u[l & 1].as<uint16_t>();
+      AP_CUDA(launch_pair(k_bwd<2>, grid, smem, st, n->tmGa, n->tmGa, n->tmWdT, p));
+      AP_LAUNCH_CHECK();
+    }
+  } else {
+    // MODE 1 of the last layer alone, then one fused launch per layer boundary (MODE 2 of l + MODE 1 of l - 1), then MODE 2 of
+    // layer 0 alone.  g_a(l) lives in ga[l & 1].
+    DevBuf* ga[2] = {&n->g_a, &n->g_a2};
+    const CUtensorMap* tga[2] = {&n->tmGa, &n->tmGa2};
+    const int top = n->N - 1;
+    p.last = 1, p.nkb = 4, p.b_row0 = top * 256;
+    p.ts = n->ts.as<uint16_t>() + static_cast<size_t>(top) * n->bchunk * L * 512;
+    p.out = ga[top & 1]->as<uint16_t>();
+    AP_CUDA(launch_pair(k_bwd<1>, grid, smem, st, n->tmGs, n->tmGu[0], n->tmWb, p));
     AP_LAUNCH_CHECK();
-    p.nkb = 8, p.dilation = 1 << (l % n->cfg.dilation_cycle);
-    p.g_next = n->g_u[(l + 1) & 1].as<uint16_t>(), p.out = n->g_u[l & 1].as<uint16_t>();
-    AP_CUDA(launch_pair(k_bwd<2>, grid, smem, st, n->tmGa, n->tmGa, n->tmWdT, p));
+    for (int l = top; l >= 1; --l) {
+      KfParams f{};
+      f.n_tiles = n_tiles, f.tiles_per_sample = tps, f.L = L, f.dilation = 1 << (l % n->cfg.dilation_cycle);
+      f.has_next = l < top, f.a_row0 = l * 256, f.b_row0 = (l - 1) * 256;
+      f.ts = n->ts.as<uint16_t>() + static_cast<size_t>(l - 1) * n->bchunk * L * 512;
+      f.g_next = n->g_u[(l + 1) & 1].as<uint16_t>(), f.gu_out = n->g_u[l & 1].as<uint16_t>();
+      f.ga_out = ga[(l - 1) & 1]->as<uint16_t>();
+      AP_CUDA(launch_pair(k_bwd_fused, grid, smem, st, *tga[l & 1], n->tmGs, n->tmWdT, n->tmWb, f));
+      AP_LAUNCH_CHECK();
+    }
+    p.last = top == 0, p.nkb = 8, p.dilation = 1, p.b_row0 = 0;
+    p.g_next = n->g_u[1].as<uint16_t>(), p.out = n->g_u[0].as<uint16_t>();
+    AP_CUDA(launch_pair(k_bwd<2>, grid, smem, st, *tga[0], *tga[0], n->tmWdT, p));
     AP_LAUNCH_CHECK();
   }
   {

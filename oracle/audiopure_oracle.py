@@ -783,24 +783,29 @@ def spec_sde_step_coefficients(tab, s: torch.Tensor):
             "g": torch.sqrt(beta)}
 
 
-def spec_sde_purify(sd, img, t_star: int, noise, ops, cfg, eps_fn=None):
-    """RevImprovedDiffusion.image_editing_sample, sample_step = 1, rand_t = False (improved_diffusion_sde.py:175-219):
-    standardise the dB mel-spectrogram to [-1, 1], diffuse to level t*, integrate the reverse VP-SDE with the UNet's eps,
-    map back.  noise order: e, then one N(0,1) tensor per Euler step."""
+def spec_sde_purify(sd, img, t_star: int, noise, ops, cfg, eps_fn=None, sample_step: int = 1):
+    """RevImprovedDiffusion.image_editing_sample, rand_t = False (improved_diffusion_sde.py:175-219): standardise the dB
+    mel-spectrogram to [-1, 1], diffuse to level t*, integrate the reverse VP-SDE with the UNet's eps, map back.  noise order per
+    round: e, then one N(0,1) tensor per Euler step.  sample_step > 1: round k + 1 starts from the DE-standardised output of round k
+    (:204-205 assign it to x0 without standardising it again); the rounds' outputs are concatenated on the batch axis (:217)."""
     img = _t(img, torch.float32)
     tab = spec_sde_tables()
     eps_fn = eps_fn or (lambda xx, d: unet_forward(sd, xx, d * torch.ones(xx.shape[0]), ops, cfg))
     x0 = 2 * (img - MEL_LOWER_BOUND) / (MEL_UPPER_BOUND - MEL_LOWER_BOUND) - 1                           # melspec_standardize
     a = (1 - tab["discrete_betas"]).cumprod(dim=0)
-    x = x0 * a[t_star - 1].sqrt() + noise(x0.shape) * (1.0 - a[t_star - 1]).sqrt()                       # :190
-    for s, ds in spec_sde_schedule(t_star):
-        c = spec_sde_step_coefficients(tab, s)
-        eps = eps_fn(x, c["d"]).to(torch.float32)                                                        # :105
-        drift = -0.5 * c["beta"] * x                                                                     # :85
-        score = c["neg_recip"] * eps                                                                     # :110
-        rdrift = drift - torch.sqrt(c["beta"]) ** 2 * score                                              # :115
-        x = x + (-rdrift) * ds + c["g"] * torch.sqrt(ds) * noise(x.shape)
-    return (x + 1) * (MEL_UPPER_BOUND - MEL_LOWER_BOUND) / 2 + MEL_LOWER_BOUND                           # melspec_inv_standardize
+    xs = []
+    for _ in range(sample_step):
+        x = x0 * a[t_star - 1].sqrt() + noise(x0.shape) * (1.0 - a[t_star - 1]).sqrt()                   # :190
+        for s, ds in spec_sde_schedule(t_star):
+            c = spec_sde_step_coefficients(tab, s)
+            eps = eps_fn(x, c["d"]).to(torch.float32)                                                    # :105
+            drift = -0.5 * c["beta"] * x                                                                 # :85
+            score = c["neg_recip"] * eps                                                                 # :110
+            rdrift = drift - torch.sqrt(c["beta"]) ** 2 * score                                          # :115
+            x = x + (-rdrift) * ds + c["g"] * torch.sqrt(ds) * noise(x.shape)
+        x0 = (x + 1) * (MEL_UPPER_BOUND - MEL_LOWER_BOUND) / 2 + MEL_LOWER_BOUND                         # melspec_inv_standardize
+        xs.append(x0)
+    return torch.cat(xs, dim=0)
 
 
 # ---------------------------------------------------------------------------------------------- black-box queries (§8f-3)

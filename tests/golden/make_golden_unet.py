@@ -59,6 +59,12 @@ def main():
     with torch.no_grad(), RandnInjector(5300) as inj:
         out["spec_purified_t2"] = rid(spec.clone()).numpy()
         out["spec_noise_draws"] = np.array(inj.i)
+    # ---- sample_step = 2: the de-standardised output of round 1 is fed to round 2 WITHOUT standardising it again (:182,:204-205)
+    args2 = argparse.Namespace(ddpm_path=ckpt, t=1, score_type="guided_diffusion", rand_t=False, t_delta=15, use_bm=False, sample_step=2)
+    rid2 = RevImprovedDiffusion(args2).eval()
+    with torch.no_grad(), RandnInjector(5310) as inj:
+        out["spec_purified_t1_s2"] = rid2(spec.clone()).numpy()
+        out["spec_noise_draws_s2"] = np.array(inj.i)
     # ---- gradients (the reference back-propagates through this UNet: no no_grad on the spectrogram path)
     for prm in model.parameters():
         prm.requires_grad_(False)

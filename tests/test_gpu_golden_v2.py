@@ -343,6 +343,21 @@ def test_rev_improved_diffusion_vs_reference(ap, golden_unet):
     assert tuple(logits.shape) == (2, 10) and torch.isfinite(logits).all()
 
 
+def test_rev_improved_diffusion_sample_step_2(ap, golden_unet):
+    """sample_step = 2 (improved_diffusion_sde.py:182-217): two diffuse + reverse-SDE rounds, the second one starting from the
+    de-standardised output of the first (the reference does not standardise it again); outputs concatenated on the batch axis."""
+    args = argparse.Namespace(ddpm_path=None, t=1, score_type="guided_diffusion", rand_t=False, t_delta=15, use_bm=False, sample_step=2)
+    rid = ap.RevImprovedDiffusion(args, state_dict=synthetic.unet_state_dict(seed=0), noise="torch")
+    rid.model.set_mode("fp32")
+    with RandnInjector(5310) as inj:
+        y = rid(cuda(golden_unet["spec_in"]))
+        assert inj.i == int(golden_unet["spec_noise_draws_s2"])
+    assert tuple(y.shape) == (4, 1, 32, 32)
+    err = rel_l2(y, golden_unet["spec_purified_t1_s2"])
+    print(f"Diffusion-Spec sample_step=2: rel-L2 {err:.3e}")
+    assert err < 1e-5
+
+
 def test_unet_input_gradient_vs_reference(ap, golden_unet):
     """ap_unet_eps_vjp == torch.autograd.grad(UNetModel(x, 37), x, g_eps) of the unmodified reference (fp32 mode; tf32 within the
     tensor-core convolutions' precision), chunk-independent."""

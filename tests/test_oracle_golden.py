@@ -399,6 +399,10 @@ def test_spec_sde_oracle_vs_reference_revimproveddiffusion(golden_unet):
     with torch.no_grad():
         y = orc.spec_sde_purify(sd, golden_unet["spec_in"], 2, _noise(5300, n, (2, 1, 32, 32)), ops, cfg).numpy()
     assert rel_l2(y, golden_unet["spec_purified_t2"]) < 1e-5
+    n2 = int(golden_unet["spec_noise_draws_s2"])        # sample_step = 2: round 2 starts from the de-standardised output of round 1
+    with torch.no_grad():
+        y2 = orc.spec_sde_purify(sd, golden_unet["spec_in"], 1, _noise(5310, n2, (2, 1, 32, 32)), ops, cfg, sample_step=2).numpy()
+    assert y2.shape == (4, 1, 32, 32) and rel_l2(y2, golden_unet["spec_purified_t1_s2"]) < 1e-5
 
 
 def test_unet_oracle_gradients_vs_reference(golden_unet):

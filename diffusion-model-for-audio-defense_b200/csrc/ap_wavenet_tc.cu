@@ -1395,6 +1395,7 @@ struct KfParams {
   const uint16_t* g_next;  // [chunk][L][256] g_u(l+1)
   uint16_t* gu_out;        // [chunk][L][256] g_u(l)
   uint16_t* ga_out;        // [chunk][L][512] g_a(l-1)
+  int ts_row0;             // k_bwd_fused_s: (l - 1) * chunk, first waveform of layer l - 1 in the derivative tensor map
 };
 
 template <class G, int HSEL>
@@ -1625,6 +1626,316 @@ k_bwd_fused(const __grid_constant__ CUtensorMap tmGa, const __grid_constant__ CU
     setmaxnreg_inc<200>();
     if (((warp - EPI_WARP0) >> 2) == 0) kf_epilogue<G, 0>(cx, p, tmem, tiles);
     else kf_epilogue<G, 1>(cx, p, tmem, tiles);
+  }
+  tc_epilogue_teardown<CG>(tmem);
+}
+
+// ---- the same fused launch with every epilogue stream moved by TMA (the epilogue warps issue no global access).  Opt-in
+// (AP_BWD_STAGED=1), kept as the record of an experiment: the 32-byte-per-thread loads / stores of kf_epilogue (96 sectors per position,
+// one cache line per lane; ncu: l1tex throughput 75 % at boost clocks) looked like the limiter of the sustained loop, but this form
+// runs in the same time: the pass is bound by tensor + memory energy under the power cap.  g_u(l+1) of the tile is TMA-loaded INTO the staging
+// K-blocks once job B of the previous unit has read them, the epilogue adds the accumulator in place, and the staging tile is both
+// job B's A operand and the source of the g_u(l) store; the saved gate derivatives come in as 16 KB sub-tiles [128 rows][64 ch]
+// through four buffers, are multiplied in place and leave as g_a(l-1) (loader warp 2, storer warp 3, as in k1_layer).  Shared
+// memory: 3-stage operand ring (96 KB) + staging (64 KB) + 4 stream buffers (64 KB).
+struct GeoF {
+  static constexpr int CG = 2, DT = 0, NCOMBO = 1;
+  static constexpr bool SPLIT = false;
+  static constexpr int B_ROWS = 128, B_BYTES = B_ROWS * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = 3;
+  static constexpr int OUT_OFF = NSTAGE * STAGE_BYTES;
+  static constexpr int RES_OFF = OUT_OFF + OUT_BYTES;          // four stream buffers of A_BYTES
+  static constexpr int BIAS_OFF = RES_OFF + 4 * A_BYTES;
+  static constexpr int BAR_OFF = BIAS_OFF;
+  static constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;
+  static constexpr uint32_t IDESC = umma_idesc_bf16_f32(256, 256);
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+};
+enum { BARF_X_FULL = 24,      // [4] derivative sub-tile landed in stream buffer i
+       BARF_X_DONE = 28,      // [4] the 8 epilogue warps have turned buffer i into g_a
+       BARF_X_FREE = 32,      // [4] the store of buffer i has read it
+       BARF_GN_FULL = 36,     // g_u(l+1) of the tile landed in the staging K-blocks
+       BARF_GU_READY = 37,    // the staging tile holds g_u(l) (-> storer)
+       BARF_GU_STORED = 38,   // the store of g_u(l) has read the staging tile (-> loader)
+       BARF_COUNT = 39 };
+
+template <int HSEL>
+__device__ __forceinline__ void kfs_epilogue(const Ctx<GeoF>& cx, const KfParams& p, const uint32_t tmem, const Tiles<2>& tiles) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q4 = warp & 3, etid = threadIdx.x - EPI_WARP0 * 32;
+  const int row = q4 * 32 + lane;
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+  const uint32_t row_off = row * 128, sw = row & 7;
+  const float sqrt_half = 0.70710678118654752440f;
+  uint32_t xcount = 0;       // derivative sub-tiles consumed: buffer xcount & 3, phase (xcount >> 2) & 1
+
+  auto epi_b = [&](uint32_t t_idx) {
+    mbar_wait(cx.bar(BAR_ACC_FULL + 1), t_idx & 1, 64);
+    tc_fence_after();
+    uint32_t accs[4][32];
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) tmem_ld_32x32b_x32(lane_addr + 256 + pass * 64 + HSEL * 32, accs[pass]);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j, ++xcount) {          // plane j >> 2 (d/d a_t, d/d a_s), channels (j & 3) * 64 ...
+      const uint32_t buf = xcount & 3;
+      const uint32_t (&acc)[32] = accs[j & 3];
+      mbar_wait(cx.bar(BARF_X_FULL + buf), (xcount >> 2) & 1, 52);
+      const uint32_t rb = cx.base + GeoF::RES_OFF + buf * A_BYTES + row_off;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t addr = rb + (((HSEL * 4 + c) ^ sw) << 4);
+        const uint4 dv = ld_shared_v4(addr);
+        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          pk[k] = pack_bf16x2(__uint_as_float(acc[c * 8 + 2 * k]) * bf16_lo(dw[k]), __uint_as_float(acc[c * 8 + 2 * k + 1]) * bf16_hi(dw[k]));
+        st_shared_v4(addr, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(cx.bar(BARF_X_DONE + buf));
+    }
+  };
+
+  uint32_t ti = 0;
+  for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+    // ---- epilogue A: the accumulator to registers (region X is free at once), then g_u(l) = acc + sqrt(.5) g_u(l+1) in place in
+    //      the staging K-blocks (rows past the end of a waveform are zero on both sides: TMA fills out-of-bounds rows with zeros)
+    mbar_wait(cx.bar(BAR_ACC_FULL + 0), ti & 1, 65);
+    tc_fence_after();
+    uint32_t accs[4][32];
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) tmem_ld_32x32b_x32(lane_addr + pass * 64 + HSEL * 32, accs[pass]);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) cx.arrive_leader(BAR_ACC_EMPTY + 0);
+    mbar_wait(cx.bar(BARF_GN_FULL), ti & 1, 53);
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const uint32_t rb = cx.out_kb(pass) + row_off;
+      const uint32_t (&acc)[32] = accs[pass];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t addr = rb + (((HSEL * 4 + c) ^ sw) << 4);
+        const uint4 gv = ld_shared_v4(addr);
+        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          pk[k] = pack_bf16x2(fmaf(bf16_lo(gw[k]), sqrt_half, __uint_as_float(acc[c * 8 + 2 * k])),
+                              fmaf(bf16_hi(gw[k]), sqrt_half, __uint_as_float(acc[c * 8 + 2 * k + 1])));
+        st_shared_v4(addr, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, EPI_THREADS);
+    if (etid == 0) {
+      cx.arrive_leader(BAR_OUT_READY);
+      mbar_arrive(cx.bar(BARF_GU_READY));
+    }
+    if (ti > 0) epi_b(ti - 1);
+  }
+  if (ti > 0) epi_b(ti - 1);
+}
+
+// tmGa: g_a(l); tmGs: g_s; tmWdT / tmWb: transposed weights; tmGn: g_u(l+1) (zeros for the top layer); tmGuOut: g_u(l);
+// tmTs: saved gate derivatives [N chunk][L][512]; tmGaOut: g_a(l-1)
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_bwd_fused_s(const __grid_constant__ CUtensorMap tmGa, const __grid_constant__ CUtensorMap tmGs, const __grid_constant__ CUtensorMap tmWdT,
+              const __grid_constant__ CUtensorMap tmWb, const __grid_constant__ CUtensorMap tmGn, const __grid_constant__ CUtensorMap tmGuOut,
+              const __grid_constant__ CUtensorMap tmTs, const __grid_constant__ CUtensorMap tmGaOut, const __grid_constant__ KfParams p) {
+  using G = GeoF;
+  constexpr int CG = 2;
+  Ctx<G> cx;
+  uint8_t* gen;
+  const uint32_t tmem = tc_prologue<G>(cx, gen, 1);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(cx.bar(BARF_X_FULL + i), 1);
+      mbar_init(cx.bar(BARF_X_DONE + i), 8);
+      mbar_init(cx.bar(BARF_X_FREE + i), 1);
+    }
+    mbar_init(cx.bar(BARF_GN_FULL), 1);
+    mbar_init(cx.bar(BARF_GU_READY), 1);
+    mbar_init(cx.bar(BARF_GU_STORED), 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmGa), prefetch_tmap(&tmGs), prefetch_tmap(&tmWdT), prefetch_tmap(&tmWb);
+    prefetch_tmap(&tmGn), prefetch_tmap(&tmGuOut), prefetch_tmap(&tmTs), prefetch_tmap(&tmGaOut);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Tiles<CG> tiles(p.n_tiles, cx.rank);
+  const int oob_l0 = p.tiles_per_sample * TILE_M;
+
+  if (warp < EPI_WARP0) setmaxnreg_dec<96>();
+  if (warp == 0) {
+    RingPos<G::NSTAGE> it;
+    auto load_job_b = [&](bool valid, int b, int l0) {
+      for (int kb = 0; kb < 8; ++kb, ++it) {
+        const uint32_t s = it.s, ph = it.ph;
+        cx.wait_empty(s, ph, 67);
+        if (elect_one()) {
+          if (kb < 4) {
+            cx.arm(s, G::STAGE_BYTES);
+            cx.load_a(s, &tmGs, kb * 64, valid ? l0 : oob_l0, b);
+          } else {
+            cx.arm(s, G::B_BYTES);
+          }
+          cx.load_b(s, &tmWb, kb * 64, p.b_row0);
+        }
+        __syncwarp();
+      }
+    };
+    uint32_t ti = 0;
+    bool pvalid = false;
+    int pb = 0, pl0 = 0;
+    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+      const bool valid = tile < p.n_tiles;
+      const int b = valid ? tile / p.tiles_per_sample : 0;
+      const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+      for (int tap = 0; tap < 3; ++tap)
+        for (int kb = 0; kb < 8; ++kb, ++it) {
+          const uint32_t s = it.s, ph = it.ph;
+          cx.wait_empty(s, ph, 68);
+          if (elect_one()) {
+            cx.arm(s, G::STAGE_BYTES);
+            cx.load_a(s, &tmGa, kb * 64, valid ? l0 - (tap - 1) * p.dilation : oob_l0, b);
+            cx.load_b(s, &tmWdT, (tap * 8 + kb) * 64, p.a_row0);
+          }
+          __syncwarp();
+        }
+      if (ti > 0) load_job_b(pvalid, pb, pl0);
+      pvalid = valid, pb = b, pl0 = l0;
+    }
+    if (ti > 0) load_job_b(pvalid, pb, pl0);
+  } else if (warp == 1) {
+    if (cx.rank == 0) {
+      RingPos<G::NSTAGE> it;
+      auto job_b = [&](uint32_t t_idx) {
+        mbar_wait(cx.bar(BAR_ACC_EMPTY + 1), (t_idx & 1) ^ 1, 69);
+        tc_fence_after();
+        for (int kb = 0; kb < 8; ++kb, ++it) {
+          const uint32_t s = it.s, ph = it.ph;
+          if (kb == 4) {
+            mbar_wait(cx.bar(BAR_OUT_READY), t_idx & 1, 58);
+            tc_fence_after();
+          }
+          mbar_wait(cx.bar(BAR_FULL + s), ph, 59);
+          tc_fence_after();
+          if (elect_one()) {
+            cx.mma_kblock(tmem + 256, kb < 4 ? cx.stage_a(s) : cx.out_kb(kb - 4), cx.stage_b(s), kb == 0);
+            cx.commit(BAR_EMPTY + s);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) cx.commit(BAR_ACC_FULL + 1);
+        __syncwarp();
+      };
+      uint32_t ti = 0;
+      for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+        mbar_wait(cx.bar(BAR_ACC_EMPTY + 0), (ti & 1) ^ 1, 57);
+        tc_fence_after();
+        for (int k = 0; k < 24; ++k, ++it) {
+          const uint32_t s = it.s, ph = it.ph;
+          mbar_wait(cx.bar(BAR_FULL + s), ph, 56);
+          tc_fence_after();
+          if (elect_one()) {
+            cx.mma_kblock(tmem, cx.stage_a(s), cx.stage_b(s), k == 0);
+            cx.commit(BAR_EMPTY + s);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) cx.commit(BAR_ACC_FULL + 0);
+        __syncwarp();
+        if (ti > 0) job_b(ti - 1);
+      }
+      if (ti > 0) job_b(ti - 1);
+    }
+  } else if (warp == 2) {
+    // ======================================================================================= stream loader
+    uint32_t xcount = 0, ti = 0;
+    bool pvalid = false;
+    int pb = 0, pl0 = 0;
+    auto load_ts = [&](int j, bool valid, int b, int l0) {
+      const uint32_t buf = xcount & 3;
+      mbar_wait(cx.bar(BARF_X_FREE + buf), ((xcount >> 2) & 1) ^ 1, 50);
+      if (lane == 0) {
+        mbar_expect_tx(cx.bar(BARF_X_FULL + buf), A_BYTES);
+        tma_load_3d(cx.base + G::RES_OFF + buf * A_BYTES, &tmTs, cx.bar(BARF_X_FULL + buf), (j >> 2) * 256 + (j & 3) * 64,
+                    valid ? l0 : oob_l0, p.ts_row0 + b);
+      }
+      __syncwarp();
+      ++xcount;
+    };
+    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+      const bool valid = tile < p.n_tiles;
+      const int b = valid ? tile / p.tiles_per_sample : 0;
+      const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+      if (ti > 0)
+        for (int j = 0; j < 4; ++j) load_ts(j, pvalid, pb, pl0);
+      if (ti > 0) {          // the staging tile: job B of the previous unit has read it, and so has the store of its g_u
+        mbar_wait(cx.bar(BAR_ACC_FULL + 1), (ti - 1) & 1, 51);
+        mbar_wait(cx.bar(BARF_GU_STORED), (ti - 1) & 1, 49);
+      }
+      if (lane == 0) {
+        mbar_expect_tx(cx.bar(BARF_GN_FULL), OUT_BYTES);
+        for (int pass = 0; pass < 4; ++pass) tma_load_3d(cx.out_kb(pass), &tmGn, cx.bar(BARF_GN_FULL), pass * 64, valid ? l0 : oob_l0, b);
+      }
+      __syncwarp();
+      if (ti > 0)
+        for (int j = 4; j < 8; ++j) load_ts(j, pvalid, pb, pl0);
+      pvalid = valid, pb = b, pl0 = l0;
+    }
+    if (ti > 0)
+      for (int j = 0; j < 8; ++j) load_ts(j, pvalid, pb, pl0);
+  } else if (warp == 3) {
+    // ======================================================================================= stream storer
+    uint32_t xcount = 0, ti = 0;
+    bool pvalid = false;
+    int pb = 0, pl0 = 0;
+    auto store_ga = [&](int j, bool valid, int b, int l0) {
+      const uint32_t buf = xcount & 3;
+      mbar_wait(cx.bar(BARF_X_DONE + buf), (xcount >> 2) & 1, 48);
+      if (lane == 0) {
+        if (valid) tma_store_3d(&tmGaOut, cx.base + G::RES_OFF + buf * A_BYTES, (j >> 2) * 256 + (j & 3) * 64, l0, b);
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(cx.bar(BARF_X_FREE + buf));
+      }
+      __syncwarp();
+      ++xcount;
+    };
+    for (int tile = tiles.first; tiles.more(tile); tile += tiles.stride, ++ti) {
+      const bool valid = tile < p.n_tiles;
+      const int b = valid ? tile / p.tiles_per_sample : 0;
+      const int l0 = valid ? (tile - b * p.tiles_per_sample) * TILE_M : oob_l0;
+      mbar_wait(cx.bar(BARF_GU_READY), ti & 1, 47);
+      if (lane == 0) {
+        if (valid)
+          for (int pass = 0; pass < 4; ++pass) tma_store_3d(&tmGuOut, cx.out_kb(pass), pass * 64, l0, b);
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(cx.bar(BARF_GU_STORED));
+      }
+      __syncwarp();
+      if (ti > 0)
+        for (int j = 0; j < 8; ++j) store_ga(j, pvalid, pb, pl0);
+      pvalid = valid, pb = b, pl0 = l0;
+    }
+    if (ti > 0)
+      for (int j = 0; j < 8; ++j) store_ga(j, pvalid, pb, pl0);
+    if (lane == 0) bulk_wait_all<0>();
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    setmaxnreg_inc<200>();
+    if (((warp - EPI_WARP0) >> 2) == 0) kfs_epilogue<0>(cx, p, tmem, tiles);
+    else kfs_epilogue<1>(cx, p, tmem, tiles);
   }
   tc_epilogue_teardown<CG>(tmem);
 }
@@ -2110,7 +2421,7 @@ struct TcNet {
   DevBuf wb, wdt, wft;                                     // [N][256][512], [N][256][1536], [256][256] bf16, K-major
   CUtensorMap tmWb, tmWdT, tmWfT;
   DevBuf ts, mask, g_pre, g_s, g_a, g_a2, g_u[2];     // g_a / g_a2: the fused backward launches read one and write the other
-  CUtensorMap tmGpre, tmGs, tmGa, tmGa2, tmGu[2];
+  CUtensorMap tmGpre, tmGs, tmGa, tmGa2, tmGu[2], tmTs;
   int bchunk = 0, bL = 0;
   bool bwd_attr = false;
   unsigned long long save_gen = 0;   // generation of the saved forward state (tokens of ap_diffwave_eps_save)
@@ -2556,6 +2867,8 @@ static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
   if (rc == AP_OK) rc = encode_bf16(&n->tmGs, n->g_s.p, 3, d256, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmGa, n->g_a.p, 3, d512, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmGa2, n->g_a2.p, 3, d512, bx);
+  const uint64_t dts[3] = {512, static_cast<uint64_t>(L), static_cast<uint64_t>(chunk) * n->N};
+  if (rc == AP_OK) rc = encode_bf16(&n->tmTs, n->ts.p, 3, dts, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmGu[0], n->g_u[0].p, 3, d256, bx);
   if (rc == AP_OK) rc = encode_bf16(&n->tmGu[1], n->g_u[1].p, 3, d256, bx);
   if (rc != AP_OK) {
@@ -2567,6 +2880,7 @@ static int tc_bwd_reserve(TcNet* n, int chunk, int L) {
     AP_CUDA(cudaFuncSetAttribute(k_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
+    AP_CUDA(cudaFuncSetAttribute(k_bwd_fused_s, cudaFuncAttributeMaxDynamicSharedMemorySize, GeoF::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k1_layer<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k2_head<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 2>::SMEM_BYTES));
     AP_CUDA(cudaFuncSetAttribute(k1_split<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2, 1, 2>::SMEM_BYTES));
@@ -2643,6 +2957,9 @@ int tc_net_backward(TcNet* n, const float* x, const float* g_eps, float* g_x, in
     DevBuf* ga[2] = {&n->g_a, &n->g_a2};
     const CUtensorMap* tga[2] = {&n->tmGa, &n->tmGa2};
     const int top = n->N - 1;
+    static const bool staged = std::getenv("AP_BWD_STAGED") != nullptr;
+    if (staged)        // the top layer has no g_u(l+1): the fused launches read zeros in its place
+      AP_CUDA(cudaMemsetAsync(n->g_u[(top + 1) & 1].p, 0, static_cast<size_t>(M) * 512, st));
     p.last = 1, p.nkb = 4, p.b_row0 = top * 256;
     p.ts = n->ts.as<uint16_t>() + static_cast<size_t>(top) * n->bchunk * L * 512;
     p.out = ga[top & 1]->as<uint16_t>();
@@ -2655,7 +2972,12 @@ int tc_net_backward(TcNet* n, const float* x, const float* g_eps, float* g_x, in
       f.ts = n->ts.as<uint16_t>() + static_cast<size_t>(l - 1) * n->bchunk * L * 512;
       f.g_next = n->g_u[(l + 1) & 1].as<uint16_t>(), f.gu_out = n->g_u[l & 1].as<uint16_t>();
       f.ga_out = ga[(l - 1) & 1]->as<uint16_t>();
-      AP_CUDA(launch_pair(k_bwd_fused, grid, smem, st, *tga[l & 1], n->tmGs, n->tmWdT, n->tmWb, f));
+      f.ts_row0 = (l - 1) * n->bchunk;
+      if (staged)
+        AP_CUDA(launch_pair(k_bwd_fused_s, grid, GeoF::SMEM_BYTES, st, *tga[l & 1], n->tmGs, n->tmWdT, n->tmWb, n->tmGu[(l + 1) & 1],
+                            n->tmGu[l & 1], n->tmTs, *tga[(l - 1) & 1], f));
+      else
+        AP_CUDA(launch_pair(k_bwd_fused, grid, smem, st, *tga[l & 1], n->tmGs, n->tmWdT, n->tmWb, f));
       AP_LAUNCH_CHECK();
     }
     p.last = top == 0, p.nkb = 8, p.dilation = 1, p.b_row0 = 0;

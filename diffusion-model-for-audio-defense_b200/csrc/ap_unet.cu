@@ -4,12 +4,14 @@
 // fp32 activations.
 //   * every convolution (3x3, stride-2 3x3, 1x1 qkv / proj / skip) is the implicit GEMM of ap_conv_layer.cuh with bias and the
 //     block's residual add fused into its epilogue;
-//   * GroupNorm(32) + [scale-shift] + SiLU is one kernel per use (one CTA per (sample, group): statistics and normalisation in
-//     a single pass over the group, fp32);
+//   * GroupNorm(32) + [scale-shift] + SiLU is one kernel per use: gn_tile_kernel keeps a (sample, 8-32 channel) tile in shared
+//     memory (one HBM read, one write, two-pass statistics in fp32); gn_kernel is the strided fallback for odd channel counts;
 //   * the timestep path is batch-constant in the purifier (every row is at the same discrete step), so the embedding MLP and
 //     all 30 per-block projections are one packed GEMV per network evaluation;
-//   * attention over T = H W <= 256 positions with 64-channel heads: one CTA per (sample, head), K and V in shared memory,
-//     one thread per query with an online softmax.
+//   * attention over T = H W <= 256 positions with 64-channel heads: unet_attn_mma_kernel (tf32 mode: mma.sync tensor cores, a warp
+//     per 16 queries, online softmax) or unet_attn_kernel (fp32 parity mode: one thread per query);
+//   * ap_unet_eps_vjp: the input gradient -- the forward recorded on a tape, then walked in reverse (gn_bwd_tile_kernel,
+//     unet_attn_mma_bwd_kernel, data-gradient twins of every convolution, up-sampling / concatenation / fan-out kernels).
 // The module walk (which block follows which, channel counts, skip-connection stack) is built by the host from the same
 // flat op list the Python side derives from UNetModel.__init__ (synthetic.unet_structure), so names, order and shapes agree
 // with the reference's state dict by construction.

@@ -768,6 +768,27 @@ def test_pgd_steps_through_the_defended_system_raise_the_loss(ap, sd_full):
     assert losses[-1] > losses[0]
 
 
+def test_backward_forms_give_the_same_gradient(tmp_path):
+    """The three forms of the DiffWave backward pass -- one fused launch per layer boundary (default), two launches per layer
+    (AP_BWD_UNFUSED) and the fused launch with TMA-staged epilogue streams (AP_BWD_STAGED) -- are selected per process; run each in
+    its own interpreter on the same input and compare g_x bit for bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "diffusion-model-for-audio-defense_b200", "devtools", "bwd_profile.py")
+    outs = {}
+    for name, extra in (("fused", {}), ("unfused", {"AP_BWD_UNFUSED": "1"}), ("staged", {"AP_BWD_STAGED": "1"})):
+        env = {k: v for k, v in os.environ.items() if k not in ("AP_BWD_UNFUSED", "AP_BWD_STAGED")}
+        env.update(extra)
+        out = str(tmp_path / f"gx_{name}.npy")
+        r = subprocess.run([sys.executable, script, out, "3"], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[name] = np.load(out)
+    assert np.isfinite(outs["fused"]).all() and np.abs(outs["fused"]).max() > 0
+    assert np.array_equal(outs["fused"], outs["unfused"]) and np.array_equal(outs["fused"], outs["staged"])
+
+
 def test_pgd_through_the_spectrogram_purifier_raises_the_loss(ap):
     """The same attack loop against the 'spec' defense (adaptive_attack_eval.py:134-137): waveform -> log-mel -> Diffusion-Spec
     reverse-SDE t* = 1 -> ResNeXt; the gradient runs through the mel, UNet and classifier backward kernels."""

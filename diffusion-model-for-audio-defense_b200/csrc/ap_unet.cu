@@ -187,6 +187,49 @@ __global__ void __launch_bounds__(256) gn_tile_kernel(const float* __restrict__ 
     ob[static_cast<size_t>(p) * C4 + tl.j] = y;
   }
 }
+// The same tile held in REGISTERS: NITER float4 per thread (256 threads: tiles of 4-32 KB), so the two statistics passes and the
+// normalisation cost no shared-memory traffic at all and the NITER loads are in flight together.  Same thread <-> element mapping and
+// the same reduction order as gn_tile_kernel: bitwise the same result.
+template <int NITER>
+__global__ void __launch_bounds__(256) gn_reg_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, const float* __restrict__ scale_shift, int HW, int C,
+                                                     int cpg, int gpc, int act, int round_tf32) {
+  __shared__ float part[256];
+  __shared__ float res[8];
+  const int chunks = 32 / gpc, b = blockIdx.x / chunks, Cc = gpc * cpg, c0 = (blockIdx.x % chunks) * Cc;
+  const GnTile tl(Cc, cpg);
+  const float4* xb = reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * HW * C + c0);
+  float4* ob = reinterpret_cast<float4*>(out + static_cast<size_t>(b) * HW * C + c0);
+  const int C4 = C >> 2, n = HW * cpg;
+  float4 v[NITER];
+#pragma unroll
+  for (int k = 0; k < NITER; ++k) v[k] = xb[static_cast<size_t>(tl.p0 + k * tl.pstep) * C4 + tl.j];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NITER; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  tl.reduce(s, part, res, cpg, gpc);
+  const float mean = res[tl.gl] / n;
+  float vv = 0.f;
+#pragma unroll
+  for (int k = 0; k < NITER; ++k) {
+    const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+    vv += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+  }
+  __syncthreads();
+  tl.reduce(vv, part, res, cpg, gpc);
+  const float rstd = rsqrtf(res[tl.gl] / n + 1e-5f);
+  const int ch = c0 + 4 * tl.j;
+  float4 A, Bc = gn_affine(make_float4(0.f, 0.f, 0.f, 0.f), ch, gamma, beta, scale_shift, C, &A);
+  A = make_float4(A.x * rstd, A.y * rstd, A.z * rstd, A.w * rstd);
+#pragma unroll
+  for (int k = 0; k < NITER; ++k) {
+    float4 y = make_float4(fmaf(v[k].x - mean, A.x, Bc.x), fmaf(v[k].y - mean, A.y, Bc.y), fmaf(v[k].z - mean, A.z, Bc.z),
+                           fmaf(v[k].w - mean, A.w, Bc.w));
+    if (act) y = make_float4(silu_f(y.x), silu_f(y.y), silu_f(y.z), silu_f(y.w));
+    if (round_tf32) y = make_float4(round_tf32_f(y.x), round_tf32_f(y.y), round_tf32_f(y.z), round_tf32_f(y.w));
+    ob[static_cast<size_t>(tl.p0 + k * tl.pstep) * C4 + tl.j] = y;
+  }
+}
 // backward of the same: x-hat and d x-hat tiles in shared memory, g_y read once.
 __global__ void __launch_bounds__(256) gn_bwd_tile_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -1075,8 +1118,17 @@ int launch_gn(const float* x, float* out, const float* gamma, const float* beta,
   if (!gpc && gn_groups_per_cta(HW, cpg, 1, kGnSmemMax - 2048)) gpc = 1;   // one group per CTA if that is all that fits
   if (gpc) {
     const int q = gpc * cpg / 4, threads = (256 / q) * q;
-    gn_tile_kernel<<<bn * (32 / gpc), threads, static_cast<size_t>(HW) * q * 16 + threads * 4, st>>>(x, out, gamma, beta, ss, HW, C, cpg, gpc,
-                                                                                                    act, round_tf32);
+    const int items = HW * q;                        // float4 per tile
+    const bool regs = threads == 256 && items % 256 == 0 && (q & (q - 1)) == 0;
+    const int niter = regs ? items / 256 : 0;
+    const int grid = bn * (32 / gpc);
+    if (niter == 8) gn_reg_kernel<8><<<grid, 256, 0, st>>>(x, out, gamma, beta, ss, HW, C, cpg, gpc, act, round_tf32);
+    else if (niter == 4) gn_reg_kernel<4><<<grid, 256, 0, st>>>(x, out, gamma, beta, ss, HW, C, cpg, gpc, act, round_tf32);
+    else if (niter == 2) gn_reg_kernel<2><<<grid, 256, 0, st>>>(x, out, gamma, beta, ss, HW, C, cpg, gpc, act, round_tf32);
+    else if (niter == 1) gn_reg_kernel<1><<<grid, 256, 0, st>>>(x, out, gamma, beta, ss, HW, C, cpg, gpc, act, round_tf32);
+    else
+      gn_tile_kernel<<<grid, threads, static_cast<size_t>(HW) * q * 16 + threads * 4, st>>>(x, out, gamma, beta, ss, HW, C, cpg, gpc, act,
+                                                                                           round_tf32);
   } else {
     gn_kernel<<<bn * 32, 256, 0, st>>>(x, out, gamma, beta, ss, HW, C, cpg, act, round_tf32);
   }
